@@ -1,0 +1,184 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  Test infrastructure only."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+class OrcGraph(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int64), ("window", C.c_int32), ("maxref", C.c_int32),
+                ("minlen", C.c_int32), ("zetak", C.c_int32), ("flags", C.c_uint32),
+                ("outdegree_coding", C.c_int), ("block_coding", C.c_int), ("residual_coding", C.c_int),
+                ("reference_coding", C.c_int), ("block_count_coding", C.c_int), ("offset_coding", C.c_int),
+                ("graph", C.POINTER(C.c_uint8)), ("graph_bytes", C.c_uint64),
+                ("offsets", C.POINTER(C.c_uint64))]
+
+
+def build():
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("bvg_oracle.c", "bvg_oracle_mt.c", "bvg_oracle.h", "Makefile")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return LIB
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        super().__init__("oracle error %d" % code)
+        self.code = code
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        P = C.POINTER
+        lib.orc_load.argtypes = [C.c_char_p, C.c_int, P(P(OrcGraph))]
+        lib.orc_from_memory.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_uint32, P(P(OrcGraph))]
+        lib.orc_free.argtypes = [P(OrcGraph)]
+        lib.orc_free.restype = None
+        lib.orc_outdegree.argtypes = [P(OrcGraph), C.c_int32, P(C.c_int32)]
+        lib.orc_successors.argtypes = [P(OrcGraph), C.c_int32, C.c_void_p, C.c_int64]
+        lib.orc_successors.restype = C.c_int64
+        lib.orc_decode_range.argtypes = [P(OrcGraph), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+        lib.orc_decode_range.restype = C.c_int64
+        lib.orc_scan_range.argtypes = [P(OrcGraph), C.c_int32, C.c_int32, P(C.c_int64), P(C.c_uint64)]
+        lib.orc_scan_range_mt.argtypes = [P(OrcGraph), C.c_int32, C.c_int32, C.c_int, P(C.c_int64), P(C.c_uint64)]
+        lib.orc_rebuild_offsets.argtypes = [P(OrcGraph), C.c_void_p]
+        lib.orc_chain_bits.argtypes = [P(OrcGraph), C.c_int32, P(C.c_int32)]
+        lib.orc_chain_bits.restype = C.c_int64
+        lib.orc_read_code.argtypes = [C.c_void_p, C.c_uint64, P(C.c_uint64), C.c_int, C.c_int]
+        lib.orc_read_code.restype = C.c_uint64
+
+    def load(self, basename, offsets=True):
+        g = C.POINTER(OrcGraph)()
+        rc = self.lib.orc_load(basename.encode(), 1 if offsets else 0, C.byref(g))
+        if rc:
+            raise OracleError(rc)
+        return OracleGraph(self, g)
+
+    def read_codes(self, data: bytes, coding: int, k: int, count: int):
+        buf = np.frombuffer(data, dtype=np.uint8).copy()
+        pos = C.c_uint64(0)
+        out = []
+        for _ in range(count):
+            out.append(int(self.lib.orc_read_code(buf.ctypes.data, len(buf), C.byref(pos), coding, k)))
+        return out, int(pos.value)
+
+
+class OracleGraph:
+    def __init__(self, orc, g):
+        self.orc, self.g = orc, g
+        c = g.contents
+        self.n, self.m = c.n, c.m
+        self.window, self.maxref, self.minlen, self.zetak, self.flags = c.window, c.maxref, c.minlen, c.zetak, c.flags
+        self.graph_bytes = c.graph_bytes
+
+    def close(self):
+        if self.g:
+            self.orc.lib.orc_free(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def offsets(self):
+        c = self.g.contents
+        return np.ctypeslib.as_array(c.offsets, shape=(self.n + 1,)).copy()
+
+    def outdegree(self, x):
+        d = C.c_int32()
+        rc = self.orc.lib.orc_outdegree(self.g, x, C.byref(d))
+        if rc:
+            raise OracleError(rc)
+        return d.value
+
+    def successors(self, x, cap=None):
+        if cap is None:
+            cap = max(self.outdegree(x), 1)
+        out = np.empty(cap, dtype=np.int32)
+        d = self.orc.lib.orc_successors(self.g, x, out.ctypes.data, cap)
+        if d < 0:
+            raise OracleError(d)
+        return out[:d]
+
+    def decode_range(self, lo, hi):
+        off = np.zeros(hi - lo + 1, dtype=np.int64)
+        tot = self.orc.lib.orc_decode_range(self.g, lo, hi, off.ctypes.data, None, 0)
+        if tot < 0:
+            raise OracleError(tot)
+        out = np.empty(max(tot, 1), dtype=np.int32)
+        tot2 = self.orc.lib.orc_decode_range(self.g, lo, hi, off.ctypes.data, out.ctypes.data, tot)
+        if tot2 < 0:
+            raise OracleError(tot2)
+        return off, out[:tot]
+
+    def scan_range(self, lo, hi, threads=1):
+        arcs, cs = C.c_int64(), C.c_uint64()
+        if threads == 1:
+            rc = self.orc.lib.orc_scan_range(self.g, lo, hi, C.byref(arcs), C.byref(cs))
+        else:
+            rc = self.orc.lib.orc_scan_range_mt(self.g, lo, hi, threads, C.byref(arcs), C.byref(cs))
+        if rc:
+            raise OracleError(rc)
+        return arcs.value, cs.value
+
+    def rebuild_offsets(self):
+        out = np.zeros(self.n + 1, dtype=np.uint64)
+        rc = self.orc.lib.orc_rebuild_offsets(self.g, out.ctypes.data)
+        if rc:
+            raise OracleError(rc)
+        return out
+
+    def chain_bits(self, x):
+        dep = C.c_int32()
+        b = self.orc.lib.orc_chain_bits(self.g, x, C.byref(dep))
+        if b < 0:
+            raise OracleError(b)
+        return b, dep.value
+
+
+_ORACLE = None
+
+
+def load():
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle(C.CDLL(build()))
+    return _ORACLE
+
+
+def read_ascii_graph(path):
+    """ASCIIGraph format (reference ASCIIGraph.java:57-61): first line n, then one line of
+    space-separated successors per node.  Returns (offsets int64[n+1], successors int32[m])."""
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rb") as f:
+        data = f.read()
+    nl = data.index(b"\n")
+    n = int(data[:nl])
+    body = data[nl + 1:]
+    lines = body.split(b"\n")[:n]
+    counts = np.fromiter((len(l.split()) for l in lines), dtype=np.int64, count=n)
+    succ = np.array(body.split(), dtype=np.int64).astype(np.int32)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    assert off[-1] == len(succ)
+    return off, succ
+
+
+def xor_checksum(off, succ, first_node=0):
+    """XOR over arcs (x,y) of (x*0x9E3779B97F4A7C15 + y) mod 2^64."""
+    n = len(off) - 1
+    deg = np.diff(off)
+    xs = np.repeat(np.arange(first_node, first_node + n, dtype=np.uint64), deg)
+    with np.errstate(over="ignore"):
+        v = xs * np.uint64(0x9E3779B97F4A7C15) + succ.astype(np.int64).astype(np.uint64)
+    return int(np.bitwise_xor.reduce(v)) if len(v) else 0
