@@ -1,0 +1,70 @@
+/*
+ * bvgraph_tools.h -- host-side (CPU) tools that PRODUCE BVGraph inputs: a compressor and a seeded
+ * synthetic power-law generator.  C ABI of libbvgraph_tools.so.
+ *
+ * These are the cold side of the format: the reference's BVGraph.store /
+ * CompressionThread.diffComp / intervalize (reference src/it/unimi/dsi/webgraph/BVGraph.java:
+ * 1631-1654, 2049-2219, 2221-2386, 2436-2650) re-done natively because no JVM exists in the image,
+ * so that tests and bench.py can make .graph/.offsets/.properties files.  They never decode: the
+ * decode path is CUDA-only (include/bvgraph_b200.h).
+ */
+#ifndef BVGRAPH_TOOLS_H
+#define BVGRAPH_TOOLS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Coding ids, reference CompressionFlags.java:26-44; flag word layout BVGraph.java:474-523, 1317-1325. */
+enum { BVGT_DELTA = 1, BVGT_GAMMA = 2, BVGT_GOLOMB = 3, BVGT_SKEWED_GOLOMB = 4, BVGT_UNARY = 5,
+       BVGT_ZETA = 6, BVGT_NIBBLE = 7 };
+
+typedef struct bvgt_store_stats {
+    int64_t nodes, arcs;
+    int64_t graph_bits, offsets_bits;
+    int64_t bits_outdegrees, bits_references, bits_blocks, bits_intervals, bits_residuals;
+    int64_t copied_arcs, intervalised_arcs, residual_arcs;
+    int64_t tot_ref, tot_dist;      /* sums behind avgref / avgdist (BVGraph.java:2336-2338) */
+    int32_t max_outdegree, max_ref_chain;
+    uint64_t xor_checksum;          /* XOR over arcs of (x*0x9E3779B97F4A7C15 + y) */
+    uint64_t sum_successors;
+} bvgt_store_stats;
+
+/* BVGraph.store(graph, basename, windowSize, maxRefCount, minIntervalLength, zetaK, flags, threads)
+ * (BVGraph.java:1679-1688, 2436-2650) for a graph given as CSR (off[n+1], succ[off[n]], each list strictly
+ * increasing).  threads > 1 splits nodes into ranges compressed independently with an empty window each and
+ * concatenated bit-exactly, as the reference does (:2471-2477, 2498-2550).  maxref < 0 means unbounded (-m -1).
+ * Writes <basename>.graph/.offsets/.properties.  Returns 0 or a negative error (-1 invalid argument incl.
+ * non-increasing list (BVGraph.java:2201), -4 I/O). */
+int bvgt_store_csr(const char* basename, int32_t n, const int64_t* off, const int32_t* succ,
+                   int32_t window, int32_t maxref, int32_t minlen, int32_t zetak, uint32_t flags,
+                   int threads, bvgt_store_stats* stats);
+
+typedef struct bvgt_gen_params {
+    int32_t  n;            /* nodes */
+    int64_t  target_arcs;  /* approximate number of arcs wanted */
+    uint64_t seed;
+    double   zipf_s;       /* exponent of the rank-size outdegree law, genzipf-style floor((n/r)^s) (reference c/genzipf.c:22-26) */
+    double   p_copy;       /* probability that a node copies part of a prototype x-r, r in [1,7], same block */
+    double   p_interval;   /* probability that a node carries runs of consecutive successors */
+    double   p_local;      /* fraction of the remaining successors drawn near x instead of globally */
+    int32_t  block;        /* nodes per generation block ("host"): prototypes never cross a block */
+} bvgt_gen_params;
+
+void bvgt_gen_defaults(bvgt_gen_params* p, int32_t n, int64_t target_arcs, uint64_t seed);
+
+/* Generates the graph and compresses it straight to <basename>.* with `threads` workers (node ranges aligned
+ * to generation blocks).  If out_off/out_succ are non-NULL the CSR is also returned (out_off: n+1 entries;
+ * out_succ: capacity succ_cap entries; -1 if it does not fit).  The graph is a function of the parameters
+ * only, not of `threads`; the encoding (reference choices at range starts) depends on `threads`. */
+int bvgt_generate_store(const char* basename, const bvgt_gen_params* p,
+                        int32_t window, int32_t maxref, int32_t minlen, int32_t zetak, uint32_t flags,
+                        int threads, int64_t* out_off, int32_t* out_succ, int64_t succ_cap,
+                        bvgt_store_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,93 @@
+"""ctypes binding of the host-side tools (libbvgraph_tools.so): BVGraph compressor and the seeded
+synthetic power-law generator.  See include/bvgraph_tools.h.  These PRODUCE inputs; they never decode."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+DELTA, GAMMA, GOLOMB, SKEWED_GOLOMB, UNARY, ZETA, NIBBLE = 1, 2, 3, 4, 5, 6, 7
+# flag words, reference BVGraph.java:474-523
+OUTDEGREES_DELTA = DELTA
+BLOCKS_DELTA = DELTA << 4
+BLOCKS_UNARY = UNARY << 4
+RESIDUALS_GAMMA = GAMMA << 8
+RESIDUALS_DELTA = DELTA << 8
+REFERENCES_GAMMA = GAMMA << 12
+REFERENCES_DELTA = DELTA << 12
+BLOCK_COUNT_DELTA = DELTA << 16
+BLOCK_COUNT_UNARY = UNARY << 16
+OFFSETS_DELTA = DELTA << 20
+
+
+class StoreStats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "nodes", "arcs", "graph_bits", "offsets_bits", "bits_outdegrees", "bits_references", "bits_blocks",
+        "bits_intervals", "bits_residuals", "copied_arcs", "intervalised_arcs", "residual_arcs", "tot_ref", "tot_dist")] + [
+        ("max_outdegree", C.c_int32), ("max_ref_chain", C.c_int32), ("xor_checksum", C.c_uint64), ("sum_successors", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GenParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("target_arcs", C.c_int64), ("seed", C.c_uint64), ("zipf_s", C.c_double),
+                ("p_copy", C.c_double), ("p_interval", C.c_double), ("p_local", C.c_double), ("block", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_build.tools_library())
+        _lib.bvgt_store_csr.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_uint32, C.c_int, C.POINTER(StoreStats)]
+        _lib.bvgt_gen_defaults.argtypes = [C.POINTER(GenParams), C.c_int32, C.c_int64, C.c_uint64]
+        _lib.bvgt_gen_defaults.restype = None
+        _lib.bvgt_generate_store.argtypes = [C.c_char_p, C.POINTER(GenParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(StoreStats)]
+    return _lib
+
+
+def store_csr(basename, off, succ, window=7, maxref=3, minlen=4, zetak=3, flags=0, threads=1):
+    """BVGraph.store for a CSR graph (defaults: reference BVGraph.java:454-472)."""
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    succ = np.ascontiguousarray(succ, dtype=np.int32)
+    st = StoreStats()
+    rc = lib().bvgt_store_csr(os.fsencode(basename), len(off) - 1, off.ctypes.data, succ.ctypes.data if len(succ) else None,
+                              window, maxref, minlen, zetak, flags, threads, C.byref(st))
+    if rc:
+        raise ValueError("bvgt_store_csr failed: %d" % rc)
+    return st.as_dict()
+
+
+def gen_params(n, target_arcs, seed=0x5EED, **kw):
+    p = GenParams()
+    lib().bvgt_gen_defaults(C.byref(p), n, target_arcs, seed)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def generate_store(basename, n, target_arcs, seed=0x5EED, window=7, maxref=3, minlen=4, zetak=3, flags=0,
+                   threads=None, return_csr=False, **kw):
+    """Synthetic block-local copy-model power-law graph compressed straight to <basename>.*"""
+    p = gen_params(n, target_arcs, seed, **kw)
+    threads = threads or (os.cpu_count() or 1)
+    st = StoreStats()
+    off = succ = None
+    if return_csr:
+        off = np.zeros(n + 1, dtype=np.int64)
+        cap = int(target_arcs * 1.25) + 4 * n + 1024
+        succ = np.empty(cap, dtype=np.int32)
+    rc = lib().bvgt_generate_store(os.fsencode(basename), C.byref(p), window, maxref, minlen, zetak, flags, threads,
+                                   off.ctypes.data if return_csr else None, succ.ctypes.data if return_csr else None,
+                                   len(succ) if return_csr else 0, C.byref(st))
+    if rc:
+        raise ValueError("bvgt_generate_store failed: %d" % rc)
+    if return_csr:
+        return st.as_dict(), off, succ[:off[-1]].copy()
+    return st.as_dict()
