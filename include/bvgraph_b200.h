@@ -1,0 +1,131 @@
+/*
+ * bvgraph_b200.h -- C ABI of libbvgraph_b200.so: B200-native BVGraph adjacency decode.
+ *
+ * This is the drop-in boundary: what a JNI / cffi / ctypes shim binds in place of the
+ * reference's Java decode path.  Plain pointers and sizes only.  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference root, src/it/unimi/dsi/webgraph/).
+ *
+ * The .graph bit stream, the offsets and a small decode index live in HBM; all decoding is done by
+ * hand-written sm_100a kernels.  There is NO CPU decode path: without a CUDA device every compute
+ * call fails with BVG_ECUDA.
+ *
+ * Conventions: every function returns BVG_OK (0) or a negative bvg_status; out-params are untouched
+ * on error; the caller owns every buffer it passes.  `on_device` != 0 means the out / xs pointers
+ * are device pointers on the graph's device (e.g. torch tensors' data_ptr()), and the call is
+ * asynchronous on the graph's stream (bvg_set_stream); otherwise they are host pointers and the
+ * call returns after the results have been copied back.
+ * A bvg_graph is immutable after open and may be shared by host threads that each use their own
+ * stream (== BVGraph.copy() flyweights, ImmutableGraph.java:157-165,411-420); a bvg_cursor is
+ * single-threaded (== BVGraphNodeIterator).
+ */
+#ifndef BVGRAPH_B200_H
+#define BVGRAPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bvg_graph  bvg_graph;
+typedef struct bvg_cursor bvg_cursor;
+
+enum bvg_status {
+    BVG_OK = 0,
+    BVG_EINVAL = -1,        /* IllegalArgumentException: node out of range (BVGraph.java:860,900,1037,1165) */
+    BVG_ESTATE = -2,        /* IllegalStateException: no offsets (:869,1174), ref > window (:705), cursor before next (:1222) */
+    BVG_EUNSUPPORTED = -3,  /* UnsupportedOperationException: random access without offsets (:901); unsupported coding */
+    BVG_EIO = -4,           /* IOException -> RuntimeException: missing/truncated file or stream (:876,1131) */
+    BVG_EFORMAT = -5,       /* malformed .properties, wrong graphclass/version (:1528-1534), impossible record */
+    BVG_ENOMEM = -6,        /* host or device allocation failed / caller buffer too small */
+    BVG_ECUDA = -7,         /* no CUDA device / CUDA runtime error */
+    BVG_EEND = -8           /* NoSuchElementException: cursor past the end (:1202) */
+};
+
+/* ---- loading: BVGraph.load / loadMapped / loadOffline -> loadInternal (BVGraph.java:1380-1500, 1516-1609) ----
+ * offset_type as in BVGraph (:439-441): 2 mapped, 1 standard, 0 sequential (no random access), -1 offline.
+ * On the GPU all four place the bit stream and offsets in HBM; offset_type <= 0 only switches the random-access
+ * entry points to the reference's errors.  devices/ndev: CUDA ordinals to use (NULL/0 = current device); the
+ * first one holds the graph (multi-GPU runs open one shard per process, see bvg_open_shard). */
+int  bvg_open(const char* basename, int offset_type, const int* devices, int ndev, bvg_graph** out);
+
+/* Opens only nodes [from, to) of the graph for range-sharded scans (the reference's own range split is
+ * ImmutableGraph.splitNodeIterators, ImmutableGraph.java:379-409).  Loads the bits of [from - halo, to) where the
+ * halo covers the reference chains leaving the shard (window * maxrefcount nodes, as BVGraphNodeIterator's ctor
+ * re-reads the window before `from`, BVGraph.java:1173-1183). Node ids stay global. */
+int  bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, bvg_graph** out);
+
+/* Opens a graph held in host memory: `graph` is the .graph byte stream, `offsets_stream` the .offsets byte stream
+ * (gamma/delta coded gaps, may be NULL => offset_type 0 semantics are NOT possible: offsets are required). */
+int  bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                     int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                     uint32_t flags, int offset_type, int device, bvg_graph** out);
+void bvg_close(bvg_graph* g);
+
+/* numNodes / numArcs / windowSize / maxRefCount / minIntervalLength / zetaK / flags (BVGraph.java:579-625). */
+int  bvg_info(const bvg_graph* g, int32_t* nodes, int64_t* arcs, int32_t* window, int32_t* maxref,
+              int32_t* minlen, int32_t* zetak, uint32_t* flags, int64_t* graph_bits);
+/* Shard extent [from, to) (whole graph: 0, n), longest reference chain and largest outdegree found at open. */
+int  bvg_extent(const bvg_graph* g, int32_t* from, int32_t* to, int32_t* max_chain, int32_t* max_outdegree);
+/* randomAccess() (BVGraph.java:592-594). */
+int  bvg_random_access(const bvg_graph* g);
+/* CUDA stream (cudaStream_t) the graph's kernels and copies are issued on; NULL = default stream. */
+int  bvg_set_stream(bvg_graph* g, void* cuda_stream);
+int  bvg_device(const bvg_graph* g);
+
+/* ---- random access: BVGraph.outdegree(x) :857-879, successors(x) :896-904, successorArray(x) ImmutableGraph.java:329-333 ---- */
+int  bvg_outdegree(const bvg_graph* g, int32_t x, int32_t* d);
+int  bvg_successors(const bvg_graph* g, int32_t x, int32_t* out, int32_t cap, int32_t* d);
+/* Batched successors(x) for nx nodes: out_off[nx+1] (arc offsets into out, out_off[0]=0), out[cap].
+ * If out == NULL only out_off is produced (sizing call). */
+int  bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int64_t* out_off,
+                          int32_t* out, int64_t cap, int on_device);
+/* Batched outdegree(x): d[i] = outdegree(xs[i]); xs == NULL means the node range [from, from+nx). */
+int  bvg_outdegree_batch(const bvg_graph* g, const int32_t* xs, int32_t from, int64_t nx, int32_t* d, int on_device);
+
+/* ---- sequential access: BVGraph.nodeIterator(from) :1292-1301 drained over [from, to) ----
+ * out_off[to-from+1], out[cap]: the successor lists of from..to-1 back to back (what nextInt()+successorArray() yield). */
+int  bvg_range_arcs(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs);
+int  bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_off, int32_t* out, int64_t cap,
+                      int on_device);
+/* Consume-only scan of [from, to), the loop of the reference's SpeedTest (test/SpeedTest.java:157-185):
+ * every successor is decoded on the GPU and folded into arcs and checksum = XOR over arcs (x,y) of
+ * (x * 0x9E3779B97F4A7C15 + y) mod 2^64; no successor array is written to HBM by the caller. */
+int  bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum);
+/* Asynchronous variant for benchmarking: enqueues the scan on the graph's stream and leaves
+ * {arcs, checksum} in the two-word device buffer d_result (int64, uint64). */
+int  bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_result);
+
+/* ---- NodeIterator: BVGraphNodeIterator :1136-1281 (nextInt, outdegree, successorArray, copy(upperBound)) ---- */
+int  bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor** out);
+/* succ stays valid until the next call on this cursor (NodeIterator.successorArray() aliasing, BVGraph.java:1228-1233). */
+int  bvg_cursor_next(bvg_cursor* c, int32_t* node, int32_t* d, const int32_t** succ);
+int  bvg_cursor_copy(const bvg_cursor* c, int32_t upper, bvg_cursor** out);
+void bvg_cursor_close(bvg_cursor* c);
+
+/* ---- range sharding across GPUs ----
+ * A shard's first nodes may copy from lists of the previous shard.  Either the shard re-decodes that halo from its
+ * own replicated bits (default, what BVGraphNodeIterator's ctor does), or the previous shard exports its last
+ * boundary lists and they are all-gathered (NCCL) and imported:
+ * bvg_boundary_count = number of trailing nodes whose lists a successor shard can reference (<= window*maxref);
+ * bvg_boundary_export decodes them into out_off[count+1] / out[cap] (device pointers);
+ * bvg_halo_import installs `count` lists ending at node from-1 so that scans/decodes of this shard use them
+ * instead of re-decoding.  bvg_halo_needed tells whether any chain actually crosses the shard's start. */
+int  bvg_boundary_count(const bvg_graph* g, int32_t* count);
+int  bvg_boundary_export(const bvg_graph* g, int64_t* out_off, int32_t* out, int64_t cap, int on_device);
+int  bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node);
+int  bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32_t* lists, int on_device);
+
+/* ---- diagnostics ---- */
+const char* bvg_strerror(int status);
+/* Node and bit position of the first record a kernel rejected (BVGraph.java:1129-1131 logs the same pair). */
+int  bvg_last_error_node(const bvg_graph* g, int32_t* node, int64_t* bitpos);
+/* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
+int64_t bvg_kernel_launches(void);
+/* Bytes of HBM held by the graph: bit stream, offsets, decode index. */
+int  bvg_memory_footprint(const bvg_graph* g, int64_t* stream_bytes, int64_t* offsets_bytes, int64_t* index_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

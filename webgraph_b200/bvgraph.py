@@ -1,0 +1,453 @@
+"""Host-side mirror of the reference's graph API over the C ABI (include/bvgraph_b200.h).
+
+Same names, argument meaning and error behaviour as the reference's Java classes so that parity tests read like
+the reference's own tests (WebGraphTestCase.assertGraph, BVGraphTest.testLarge):
+
+  ImmutableGraph  (reference src/it/unimi/dsi/webgraph/ImmutableGraph.java:169-772)
+  BVGraph         (BVGraph.java: load :1380-1500, numNodes/numArcs, outdegree :857, successors :896,
+                   successorArray ImmutableGraph.java:329, nodeIterator :1292, copy :551, randomAccess :592)
+  NodeIterator    (NodeIterator.java:34-107; BVGraphNodeIterator BVGraph.java:1136-1281)
+  LazyIntIterator (LazyIntIterator.java:28-44: nextInt() -> next successor or -1 forever, skip(n))
+
+Exceptions map 1:1 from bvg_status: IllegalArgumentException -> ValueError, IllegalStateException ->
+IllegalStateError, UnsupportedOperationException -> UnsupportedOperationError, NoSuchElementException ->
+StopIteration/NoSuchElementError, IOException -> IOError.
+
+All decoding happens on the GPU inside libbvgraph_b200.so; this file is ctypes glue only.  Importing it without the
+built library, or calling it without a CUDA device, fails loudly (there is no CPU fallback).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+BVG_OK, BVG_EINVAL, BVG_ESTATE, BVG_EUNSUPPORTED, BVG_EIO, BVG_EFORMAT, BVG_ENOMEM, BVG_ECUDA, BVG_EEND = 0, -1, -2, -3, -4, -5, -6, -7, -8
+
+
+class IllegalStateError(RuntimeError):
+    pass
+
+
+class UnsupportedOperationError(RuntimeError):
+    pass
+
+
+class NoSuchElementError(IndexError):
+    pass
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+class FormatError(IOError):
+    pass
+
+
+_lib = None
+
+SYMBOLS = [
+    "bvg_open", "bvg_open_shard", "bvg_open_memory", "bvg_close", "bvg_info", "bvg_extent", "bvg_random_access",
+    "bvg_set_stream", "bvg_device", "bvg_outdegree", "bvg_successors", "bvg_successors_batch", "bvg_outdegree_batch",
+    "bvg_range_arcs", "bvg_decode_range", "bvg_scan_range", "bvg_scan_range_async", "bvg_cursor_open", "bvg_cursor_next",
+    "bvg_cursor_copy", "bvg_cursor_close", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
+    "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
+]
+
+
+def lib():
+    """Loads libbvgraph_b200.so (building it in-tree with nvcc if stale) and declares the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = C.CDLL(_build.cuda_library())
+    P, vp, i32, i64, u32, u64 = C.POINTER, C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+    L.bvg_open.argtypes = [C.c_char_p, C.c_int, P(C.c_int), C.c_int, P(vp)]
+    L.bvg_open_shard.argtypes = [C.c_char_p, C.c_int, i32, i32, P(vp)]
+    L.bvg_open_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, P(vp)]
+    L.bvg_close.argtypes = [vp]
+    L.bvg_close.restype = None
+    L.bvg_info.argtypes = [vp, P(i32), P(i64), P(i32), P(i32), P(i32), P(i32), P(u32), P(i64)]
+    L.bvg_extent.argtypes = [vp, P(i32), P(i32), P(i32), P(i32)]
+    L.bvg_random_access.argtypes = [vp]
+    L.bvg_set_stream.argtypes = [vp, vp]
+    L.bvg_device.argtypes = [vp]
+    L.bvg_outdegree.argtypes = [vp, i32, P(i32)]
+    L.bvg_successors.argtypes = [vp, i32, vp, i32, P(i32)]
+    L.bvg_successors_batch.argtypes = [vp, vp, i64, vp, vp, i64, C.c_int]
+    L.bvg_outdegree_batch.argtypes = [vp, vp, i32, i64, vp, C.c_int]
+    L.bvg_range_arcs.argtypes = [vp, i32, i32, P(i64)]
+    L.bvg_decode_range.argtypes = [vp, i32, i32, vp, vp, i64, C.c_int]
+    L.bvg_scan_range.argtypes = [vp, i32, i32, P(i64), P(u64)]
+    L.bvg_scan_range_async.argtypes = [vp, i32, i32, vp]
+    L.bvg_cursor_open.argtypes = [vp, i32, i32, P(vp)]
+    L.bvg_cursor_next.argtypes = [vp, P(i32), P(i32), P(P(i32))]
+    L.bvg_cursor_copy.argtypes = [vp, i32, P(vp)]
+    L.bvg_cursor_close.argtypes = [vp]
+    L.bvg_cursor_close.restype = None
+    L.bvg_boundary_count.argtypes = [vp, P(i32)]
+    L.bvg_boundary_export.argtypes = [vp, vp, vp, i64, C.c_int]
+    L.bvg_halo_needed.argtypes = [vp, P(i32)]
+    L.bvg_halo_import.argtypes = [vp, i32, vp, vp, C.c_int]
+    L.bvg_strerror.argtypes = [C.c_int]
+    L.bvg_strerror.restype = C.c_char_p
+    L.bvg_last_error_node.argtypes = [vp, P(i32), P(i64)]
+    L.bvg_kernel_launches.argtypes = []
+    L.bvg_kernel_launches.restype = i64
+    L.bvg_memory_footprint.argtypes = [vp, P(i64), P(i64), P(i64)]
+    _lib = L
+    return L
+
+
+def _check(rc, g=None):
+    if rc == BVG_OK:
+        return
+    msg = lib().bvg_strerror(rc).decode()
+    if g is not None and rc in (BVG_ESTATE, BVG_EIO, BVG_EFORMAT):
+        node, pos = C.c_int32(-1), C.c_int64(-1)
+        lib().bvg_last_error_node(g, C.byref(node), C.byref(pos))
+        if node.value >= 0:
+            msg += " [node %d, stream position %d]" % (node.value, pos.value)
+    if rc == BVG_EINVAL:
+        raise ValueError(msg)                    # IllegalArgumentException
+    if rc == BVG_ESTATE:
+        raise IllegalStateError(msg)             # IllegalStateException
+    if rc == BVG_EUNSUPPORTED:
+        raise UnsupportedOperationError(msg)     # UnsupportedOperationException
+    if rc == BVG_EIO:
+        raise IOError(msg)                       # RuntimeException(IOException)
+    if rc == BVG_EFORMAT:
+        raise FormatError(msg)
+    if rc == BVG_ENOMEM:
+        raise MemoryError(msg)
+    if rc == BVG_ECUDA:
+        raise CudaError(msg)
+    if rc == BVG_EEND:
+        raise NoSuchElementError(msg)            # NoSuchElementException
+    raise RuntimeError("bvg status %d: %s" % (rc, msg))
+
+
+class LazyIntIterator:
+    """LazyIntIterator over a decoded successor array (LazyIntIterators.wrap, LazyIntIterators.java:151-154)."""
+
+    def __init__(self, arr):
+        self._a = arr
+        self._i = 0
+
+    def nextInt(self):
+        if self._i >= len(self._a):
+            return -1  # keeps returning -1 after exhaustion (LazyIntIterator.java:35)
+        v = int(self._a[self._i])
+        self._i += 1
+        return v
+
+    def skip(self, n):
+        k = max(0, min(n, len(self._a) - self._i))
+        self._i += k
+        return k
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        v = self.nextInt()
+        if v == -1:
+            raise StopIteration
+        return v
+
+
+class NodeIterator:
+    """BVGraphNodeIterator (BVGraph.java:1136-1281) over a bvg_cursor: the device decodes batches of nodes."""
+
+    def __init__(self, graph, handle, frm):
+        self._g = graph
+        self._h = handle
+        self._from = frm
+        self._curr = frm - 1
+        self._d = 0
+        self._succ = None
+
+    def hasNext(self):
+        return self._curr < min(self._upper(), self._g.numNodes()) - 1
+
+    def _upper(self):
+        return self._up
+
+    def nextInt(self):
+        node, d, ptr = C.c_int32(), C.c_int32(), C.POINTER(C.c_int32)()
+        _check(lib().bvg_cursor_next(self._h, C.byref(node), C.byref(d), C.byref(ptr)), self._g._h)
+        self._curr, self._d = node.value, d.value
+        self._succ = np.ctypeslib.as_array(ptr, shape=(d.value,)) if d.value else np.empty(0, dtype=np.int32)
+        return node.value
+
+    def outdegree(self):
+        if self._curr == self._from - 1:
+            raise IllegalStateError("nextInt() has never been called")  # BVGraph.java:1237
+        return self._d
+
+    def successorArray(self):
+        if self._curr == self._from - 1:
+            raise IllegalStateError("nextInt() has never been called")  # :1230
+        return self._succ
+
+    def successors(self):
+        if self._curr == self._from - 1:
+            raise IllegalStateError("nextInt() has never been called")  # :1222
+        return LazyIntIterator(self._succ)
+
+    def copy(self, upperBound=2**31 - 1):
+        h = C.c_void_p()
+        _check(lib().bvg_cursor_copy(self._h, upperBound, C.byref(h)))
+        it = NodeIterator(self._g, h, self._curr + 1)
+        it._up = min(upperBound, self._g.numNodes())
+        return it
+
+    def close(self):
+        if self._h:
+            lib().bvg_cursor_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if not self.hasNext():
+            raise StopIteration
+        return self.nextInt()
+
+
+class ImmutableGraph:
+    """The abstract surface (ImmutableGraph.java:254-420); BVGraph below is the only implementation here."""
+
+    @staticmethod
+    def load(basename):
+        return BVGraph.load(basename)
+
+    @staticmethod
+    def loadMapped(basename):
+        return BVGraph.loadMapped(basename)
+
+    @staticmethod
+    def loadOffline(basename):
+        return BVGraph.loadOffline(basename)
+
+    def successors(self, x):
+        return LazyIntIterator(self.successorArray(x))
+
+    def nodeIterator(self, frm=0):
+        raise NotImplementedError
+
+    def splitNodeIterators(self, howMany):
+        """ImmutableGraph.splitNodeIterators (:379-409): ceil(n/howMany)-node ranges; trailing entries None."""
+        n = self.numNodes()
+        if n == 0 and howMany == 0:
+            return []
+        if howMany == 0:
+            raise ValueError("howMany == 0")
+        per = (n + howMany - 1) // howMany
+        out = []
+        for i in range(howMany):
+            frm = i * per
+            if frm >= n and not (n == 0 and i == 0):
+                out.append(None)
+                continue
+            it = self.nodeIterator(frm).copy(min(n, frm + per)) if frm else self.nodeIterator(0).copy(min(n, per))
+            out.append(it)
+        return out
+
+    def equals(self, other):
+        """ImmutableGraph.equals (:731-749): same node count and same successor lists through sequential iterators."""
+        if self.numNodes() != other.numNodes():
+            return False
+        a, b = self.nodeIterator(), other.nodeIterator()
+        while a.hasNext():
+            a.nextInt()
+            b.nextInt()
+            if a.outdegree() != b.outdegree() or not np.array_equal(a.successorArray(), b.successorArray()):
+                return False
+        return True
+
+
+class BVGraph(ImmutableGraph):
+    def __init__(self, handle, basename=None):
+        self._h = handle
+        self._basename = basename
+        n, m, w, r, ml, k = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        fl, gb = C.c_uint32(), C.c_int64()
+        _check(lib().bvg_info(handle, C.byref(n), C.byref(m), C.byref(w), C.byref(r), C.byref(ml), C.byref(k), C.byref(fl), C.byref(gb)))
+        self._n, self._m = n.value, m.value
+        self._window, self._maxref, self._minlen, self._zetak, self._flags, self._graph_bits = w.value, r.value, ml.value, k.value, fl.value, gb.value
+
+    # ---- loading (BVGraph.load / loadMapped / loadOffline, BVGraph.java:1380-1500) ----
+    @classmethod
+    def _open(cls, basename, offset_type, device=None):
+        h = C.c_void_p()
+        devs = (C.c_int * 1)(device) if device is not None else None
+        _check(lib().bvg_open(os.fsencode(basename), offset_type, devs, 1 if device is not None else 0, C.byref(h)))
+        return cls(h, str(basename))
+
+    @classmethod
+    def load(cls, basename, offsetType=1, device=None):
+        return cls._open(basename, offsetType, device)
+
+    @classmethod
+    def loadMapped(cls, basename, device=None):
+        return cls._open(basename, 2, device)
+
+    @classmethod
+    def loadSequential(cls, basename, device=None):
+        return cls._open(basename, 0, device)
+
+    @classmethod
+    def loadOffline(cls, basename, device=None):
+        return cls._open(basename, -1, device)
+
+    @classmethod
+    def loadShard(cls, basename, frm, to, device=-1):
+        h = C.c_void_p()
+        _check(lib().bvg_open_shard(os.fsencode(basename), device, frm, to, C.byref(h)))
+        return cls(h, str(basename))
+
+    @classmethod
+    def fromMemory(cls, graph, offsets_stream, nodes, arcs, window, maxref, minlen, zetak=3, flags=0, offsetType=1, device=-1):
+        g = np.frombuffer(graph, dtype=np.uint8)
+        o = np.frombuffer(offsets_stream, dtype=np.uint8)
+        h = C.c_void_p()
+        _check(lib().bvg_open_memory(g.ctypes.data if len(g) else None, len(g), o.ctypes.data, len(o), nodes, arcs, window, maxref,
+                                     minlen, zetak, flags, offsetType, device, C.byref(h)))
+        return cls(h)
+
+    def close(self):
+        if self._h:
+            lib().bvg_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ImmutableGraph surface ----
+    def numNodes(self):
+        return self._n
+
+    def numArcs(self):
+        return self._m
+
+    def randomAccess(self):
+        return bool(lib().bvg_random_access(self._h))
+
+    def hasCopiableIterators(self):
+        return True
+
+    def basename(self):
+        return self._basename
+
+    def windowSize(self):
+        return self._window
+
+    def maxRefCount(self):
+        return self._maxref
+
+    def minIntervalLength(self):
+        return self._minlen
+
+    def zetaK(self):
+        return self._zetak
+
+    def copy(self):
+        return self  # the native graph is immutable and shareable (ImmutableGraph.java:157-165)
+
+    def outdegree(self, x):
+        d = C.c_int32()
+        _check(lib().bvg_outdegree(self._h, x, C.byref(d)), self._h)
+        return d.value
+
+    def successorArray(self, x):
+        """ImmutableGraph.successorArray (:329-333): a fresh array holding exactly the successors of x."""
+        d = self.outdegree_checked(x)
+        out = np.empty(max(d, 1), dtype=np.int32)
+        dd = C.c_int32()
+        _check(lib().bvg_successors(self._h, x, out.ctypes.data, len(out), C.byref(dd)), self._h)
+        return out[:dd.value]
+
+    def outdegree_checked(self, x):
+        if not (0 <= x < self._n):
+            raise ValueError("Node index out of range: %d" % x)  # BVGraph.java:900
+        if not self.randomAccess():
+            raise UnsupportedOperationError("Random access to successor lists is not possible with sequential or offline graphs")  # :901
+        return self.outdegree(x)
+
+    def nodeIterator(self, frm=0):
+        h = C.c_void_p()
+        _check(lib().bvg_cursor_open(self._h, frm, 2**31 - 1, C.byref(h)), self._h)
+        it = NodeIterator(self, h, frm)
+        it._up = self._n
+        return it
+
+    # ---- batched entry points (what the JNI shim would actually call) ----
+    def extent(self):
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().bvg_extent(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def rangeArcs(self, frm, to):
+        a = C.c_int64()
+        _check(lib().bvg_range_arcs(self._h, frm, to, C.byref(a)), self._h)
+        return a.value
+
+    def decodeRange(self, frm, to):
+        """Successor lists of frm..to-1 as CSR (offsets int64[to-frm+1], successors int32[arcs]) in host memory."""
+        arcs = self.rangeArcs(frm, to)
+        off = np.zeros(to - frm + 1, dtype=np.int64)
+        out = np.empty(max(arcs, 1), dtype=np.int32)
+        _check(lib().bvg_decode_range(self._h, frm, to, off.ctypes.data, out.ctypes.data, arcs, 0), self._h)
+        return off, out[:arcs]
+
+    def scanRange(self, frm, to):
+        arcs, cs = C.c_int64(), C.c_uint64()
+        _check(lib().bvg_scan_range(self._h, frm, to, C.byref(arcs), C.byref(cs)), self._h)
+        return arcs.value, cs.value
+
+    def successorsBatch(self, xs):
+        xs = np.ascontiguousarray(xs, dtype=np.int32)
+        off = np.zeros(len(xs) + 1, dtype=np.int64)
+        _check(lib().bvg_successors_batch(self._h, xs.ctypes.data, len(xs), off.ctypes.data, None, 0, 0), self._h)
+        out = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+        _check(lib().bvg_successors_batch(self._h, xs.ctypes.data, len(xs), off.ctypes.data, out.ctypes.data, int(off[-1]), 0), self._h)
+        return off, out[:off[-1]]
+
+    def outdegreeBatch(self, xs):
+        xs = np.ascontiguousarray(xs, dtype=np.int32)
+        d = np.zeros(len(xs), dtype=np.int32)
+        _check(lib().bvg_outdegree_batch(self._h, xs.ctypes.data, 0, len(xs), d.ctypes.data, 0), self._h)
+        return d
+
+    def setStream(self, cuda_stream):
+        _check(lib().bvg_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def memoryFootprint(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib().bvg_memory_footprint(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"stream_bytes": a.value, "offsets_bytes": b.value, "index_bytes": c.value}
+
+    @property
+    def graphBits(self):
+        return self._graph_bits
+
+    @property
+    def handle(self):
+        return self._h
+
+
+def kernel_launches():
+    return int(lib().bvg_kernel_launches())

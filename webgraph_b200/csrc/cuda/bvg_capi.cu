@@ -1,0 +1,746 @@
+// bvg_capi.cu -- the C ABI of include/bvgraph_b200.h over the CUDA kernels.
+//
+// Host-side structure mirrors what the reference keeps per BVGraph (BVGraph.java:420-448: graphMemory, offsets,
+// window/codec parameters), except that the bytes live in HBM and every decode entry point launches kernels.
+// There is no CPU decode path: any compute call without a usable CUDA device returns BVG_ECUDA.
+#include "../../../include/bvgraph_b200.h"
+#include "bvg_format.hpp"
+#include "bvg_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace bvg;
+
+static std::atomic<int64_t> g_launches{0};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_cuda_error(e_, #call); return BVG_ECUDA; } } while (0)
+#define LAUNCH(kernel, grid, block, smem, stream, ...) do { \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches.fetch_add(1, std::memory_order_relaxed); } while (0)
+
+static thread_local char t_cuda_msg[256];
+static void set_cuda_error(cudaError_t e, const char* what) {
+    snprintf(t_cuda_msg, sizeof t_cuda_msg, "%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+
+struct bvg_graph {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int offset_type = 1;
+    // properties
+    int32_t n_total = 0;
+    int64_t m_total = 0;
+    int32_t window = 0, maxref = 0, minlen = 0, zetak = 3;
+    uint32_t flags = 0;
+    uint64_t graph_bits_total = 0;
+    Codec codec{};
+    bool def_codec = true;
+    // loaded window of nodes and the API extent
+    int32_t node_lo = 0, node_hi = 0, ext_from = 0, ext_to = 0;
+    // device state
+    uint32_t* d_words = nullptr;
+    uint64_t nwords = 0, bit_base = 0, bit_end = 0;
+    uint64_t* d_offsets = nullptr;
+    int32_t *d_outdeg = nullptr, *d_ref = nullptr, *d_depth = nullptr;
+    int64_t* d_rowoff = nullptr;
+    ErrWord* d_err = nullptr;
+    int32_t max_depth = 0, max_outdeg = 0;
+    // halo imported from the previous shard (bvg_halo_import)
+    int32_t* d_halo_lists = nullptr;
+    int64_t* d_halo_off = nullptr;
+    int32_t halo_count = 0;
+    // last device error (BVGraph.java:1129-1131 logs node + position)
+    mutable std::mutex mu;
+    mutable int32_t err_node = -1;
+    mutable int64_t err_bitpos = -1;
+
+    GraphDev dev() const {
+        GraphDev g;
+        g.words = d_words; g.nwords = nwords; g.bit_base = bit_base; g.bit_end = bit_end;
+        g.offsets = d_offsets; g.node_lo = node_lo; g.node_hi = node_hi; g.c = codec;
+        g.outdeg = d_outdeg; g.ref = d_ref; g.depth = d_depth; g.rowoff = d_rowoff; g.err = d_err;
+        return g;
+    }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; cudaGetLastError(); return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) { ok = false; cudaGetLastError(); }
+    }
+    ~DeviceGuard() { if (ok && prev >= 0) cudaSetDevice(prev); }
+};
+
+// Stream-ordered temporary.
+template <class T>
+struct Tmp {
+    T* p = nullptr;
+    cudaStream_t s;
+    explicit Tmp(cudaStream_t st) : s(st) {}
+    cudaError_t alloc(size_t count) { return cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), s); }
+    ~Tmp() { if (p) cudaFreeAsync(p, s); }
+};
+
+static int set_codec(bvg_graph* g) {
+    Codec& c = g->codec;
+    c.outdeg = C_GAMMA; c.block = C_GAMMA; c.resid = C_ZETA; c.ref = C_UNARY; c.bcount = C_GAMMA;  // BVGraph.java:525-541
+    const uint32_t f = g->flags;
+    if (f & 0xF) c.outdeg = f & 0xF;
+    if ((f >> 4) & 0xF) c.block = (f >> 4) & 0xF;
+    if ((f >> 8) & 0xF) c.resid = (f >> 8) & 0xF;
+    if ((f >> 12) & 0xF) c.ref = (f >> 12) & 0xF;
+    if ((f >> 16) & 0xF) c.bcount = (f >> 16) & 0xF;
+    c.zetak = g->zetak; c.window = g->window; c.minlen = g->minlen;
+    auto gd = [](int x) { return x == C_GAMMA || x == C_DELTA; };
+    auto gdu = [](int x) { return x == C_GAMMA || x == C_DELTA || x == C_UNARY; };
+    // Golomb / skewed Golomb / nibble residuals are selectable in the reference (BVGraph.java:796-797) but covered by
+    // none of its tests or fixtures: rejected rather than guessed.
+    if (!gd(c.outdeg) || !gdu(c.block) || !gdu(c.ref) || !gdu(c.bcount) ||
+        !(c.resid == C_GAMMA || c.resid == C_DELTA || c.resid == C_ZETA)) return BVG_EUNSUPPORTED;
+    g->def_codec = c.outdeg == C_GAMMA && c.block == C_GAMMA && c.resid == C_ZETA && c.ref == C_UNARY && c.bcount == C_GAMMA;
+    return BVG_OK;
+}
+
+// Pulls the device error word; returns its code (0 if none) and remembers node/bitpos.
+static int fetch_error(const bvg_graph* g) {
+    ErrWord e{};
+    if (cudaMemcpyAsync(&e, g->d_err, sizeof e, cudaMemcpyDeviceToHost, g->stream) != cudaSuccess ||
+        cudaStreamSynchronize(g->stream) != cudaSuccess) { cudaGetLastError(); return BVG_ECUDA; }
+    if (e.code) {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->err_node = e.node; g->err_bitpos = e.bitpos;
+        cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord), g->stream);
+    }
+    return e.code;
+}
+
+static int device_exclusive_scan(cudaStream_t s, const int32_t* d_in, int64_t n, int64_t* d_out /* n+1 */) {
+    const int64_t nblocks = std::max<int64_t>(1, (n + SCAN_TILE - 1) / SCAN_TILE);
+    Tmp<int64_t> sums(s);
+    CK(sums.alloc((size_t)nblocks));
+    LAUNCH(k_scan_sums, (unsigned)nblocks, SCAN_THREADS, 0, s, d_in, n, sums.p);
+    LAUNCH(k_scan_blocks, 1, SCAN_THREADS, 0, s, sums.p, nblocks);
+    LAUNCH(k_scan_apply, (unsigned)nblocks, SCAN_THREADS, 0, s, d_in, n, sums.p, d_out);
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+
+// Uploads the stream bytes + offsets of nodes [node_lo, node_hi] and builds the decode index.
+static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbytes, const uint64_t* offsets) {
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    g->nwords = (nbytes + 3) / 4 + 8;  // >= 4 padding words after the last byte
+    CK(cudaMalloc((void**)&g->d_words, g->nwords * 4));
+    CK(cudaMemsetAsync(g->d_words, 0, g->nwords * 4, g->stream));
+    if (nbytes) CK(cudaMemcpyAsync(g->d_words, bytes, nbytes, cudaMemcpyHostToDevice, g->stream));
+    LAUNCH(k_bswap, grid_for((int64_t)g->nwords, 256), 256, 0, g->stream, g->d_words, g->nwords);
+    CK(cudaMalloc((void**)&g->d_offsets, ((size_t)nn + 1) * 8));
+    CK(cudaMemcpyAsync(g->d_offsets, offsets, ((size_t)nn + 1) * 8, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMalloc((void**)&g->d_outdeg, std::max<size_t>((size_t)nn, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_ref, std::max<size_t>((size_t)nn, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_depth, std::max<size_t>((size_t)nn, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_rowoff, ((size_t)nn + 1) * 8));
+    CK(cudaMalloc((void**)&g->d_err, sizeof(ErrWord) + 2 * sizeof(int32_t)));
+    CK(cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
+    int32_t* d_max = (int32_t*)(g->d_err + 1);  // [0] max depth, [1] max outdegree
+    GraphDev gd = g->dev();
+    if (nn > 0) {
+        if (g->def_codec) LAUNCH(k_header<true>, grid_for(nn, 256), 256, 0, g->stream, gd, g->d_outdeg, g->d_ref);
+        else LAUNCH(k_header<false>, grid_for(nn, 256), 256, 0, g->stream, gd, g->d_outdeg, g->d_ref);
+    }
+    int rc = device_exclusive_scan(g->stream, g->d_outdeg, nn, g->d_rowoff);
+    if (rc) return rc;
+    if (nn > 0) {
+        LAUNCH(k_depth, grid_for(nn, 256), 256, 0, g->stream, gd, g->d_depth, d_max, g->ext_from);
+        LAUNCH(k_max_i32, 512, 256, 0, g->stream, g->d_outdeg, nn, d_max + 1);
+    }
+    CK(cudaGetLastError());
+    int32_t mx[2] = {0, 0};
+    CK(cudaMemcpyAsync(mx, d_max, sizeof mx, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->max_depth = mx[0];
+    g->max_outdeg = mx[1];
+    const int e = fetch_error(g);
+    if (e) return e;
+    return BVG_OK;
+}
+
+static void destroy(bvg_graph* g) {
+    if (!g) return;
+    DeviceGuard dg(g->device);
+    cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
+    cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
+    cudaGetLastError();
+    delete g;
+}
+
+static int pick_device(const int* devices, int ndev, int* out) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return BVG_ECUDA; }
+    int dev = 0;
+    if (devices && ndev > 0) dev = devices[0];
+    else if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return BVG_ECUDA; }
+    if (dev < 0 || dev >= count) return BVG_EINVAL;
+    *out = dev;
+    return BVG_OK;
+}
+
+static int open_common(bvg_graph* g, const Properties& p, int offset_type) {
+    if (offset_type < -1 || offset_type > 2) return BVG_EINVAL;  // BVGraph.java:1545
+    g->offset_type = offset_type;
+    g->n_total = (int32_t)p.nodes; g->m_total = p.arcs; g->window = p.window; g->maxref = p.maxref;
+    g->minlen = p.minlen; g->zetak = p.zetak; g->flags = p.flags;
+    return set_codec(g);
+}
+
+// Nodes before `from` a shard has to hold so that every reference chain stays inside it.
+static int32_t shard_halo(const bvg_graph* g, int32_t from) {
+    if (g->window == 0 || g->maxref == 0) return from;
+    const int64_t reach = (int64_t)g->window * (int64_t)std::min<int32_t>(g->maxref < 0 ? INT32_MAX : g->maxref, 1 << 20);
+    return (int32_t)std::max<int64_t>(0, (int64_t)from - reach);
+}
+
+extern "C" {
+
+int bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                    int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                    uint32_t flags, int offset_type, int device, bvg_graph** out) {
+    if (!out || nodes < 0 || (!graph && graph_bytes) || !offsets_stream) return BVG_EINVAL;
+    int dev;
+    int dl[1] = { device };
+    int rc = pick_device(device >= 0 ? dl : nullptr, device >= 0 ? 1 : 0, &dev);
+    if (rc) return rc;
+    bvg_graph* g = new (std::nothrow) bvg_graph();
+    if (!g) return BVG_ENOMEM;
+    g->device = dev;
+    DeviceGuard dg(dev);
+    Properties p;
+    p.nodes = nodes; p.arcs = arcs; p.window = window; p.maxref = maxref; p.minlen = minlen; p.zetak = zetak; p.flags = flags;
+    rc = open_common(g, p, offset_type);
+    if (rc) { destroy(g); return rc; }
+    std::vector<uint64_t> offs;
+    const int oc = ((flags >> 20) & 0xF) ? (int)((flags >> 20) & 0xF) : C_GAMMA;
+    rc = decode_offsets_stream(offsets_stream, offsets_bytes, oc, nodes, offs);
+    if (rc) { destroy(g); return rc; }
+    if (offs[(size_t)nodes] > graph_bytes * 8) { destroy(g); return BVG_EIO; }
+    g->node_lo = g->ext_from = 0; g->node_hi = g->ext_to = nodes;
+    g->bit_base = 0; g->bit_end = offs[(size_t)nodes]; g->graph_bits_total = g->bit_end;
+    rc = build_device_state(g, graph, graph_bytes, offs.data());
+    if (rc) { destroy(g); return rc; }
+    *out = g;
+    return BVG_OK;
+}
+
+int bvg_open(const char* basename, int offset_type, const int* devices, int ndev, bvg_graph** out) {
+    if (!basename || !out) return BVG_EINVAL;
+    Properties p;
+    int rc = load_properties(basename, p);
+    if (rc) return rc;
+    int dev;
+    rc = pick_device(devices, ndev, &dev);
+    if (rc) return rc;
+    std::vector<uint8_t> graph, offs;
+    if (!slurp_file(std::string(basename) + ".graph", graph)) return BVG_EIO;
+    // The GPU needs record boundaries for every node, so .offsets is read for every offset_type (the reference can
+    // also stream a graph without it, BVGraph.java:1267-1278; that sequential dependence has no GPU counterpart).
+    if (!slurp_file(std::string(basename) + ".offsets", offs)) return offset_type > 0 ? BVG_EIO : BVG_EUNSUPPORTED;
+    return bvg_open_memory(graph.data(), graph.size(), offs.data(), offs.size(), (int32_t)p.nodes, p.arcs, p.window, p.maxref,
+                           p.minlen, p.zetak, p.flags, offset_type, dev, out);
+}
+
+int bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, bvg_graph** out) {
+    if (!basename || !out) return BVG_EINVAL;
+    Properties p;
+    int rc = load_properties(basename, p);
+    if (rc) return rc;
+    if (from < 0 || to < from || to > p.nodes) return BVG_EINVAL;
+    int dev;
+    int dl[1] = { device };
+    rc = pick_device(device >= 0 ? dl : nullptr, device >= 0 ? 1 : 0, &dev);
+    if (rc) return rc;
+    bvg_graph* g = new (std::nothrow) bvg_graph();
+    if (!g) return BVG_ENOMEM;
+    g->device = dev;
+    DeviceGuard dg(dev);
+    rc = open_common(g, p, 1);
+    if (rc) { destroy(g); return rc; }
+    std::vector<uint8_t> ostream;
+    if (!slurp_file(std::string(basename) + ".offsets", ostream)) { destroy(g); return BVG_EIO; }
+    std::vector<uint64_t> offs;
+    const int oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
+    rc = decode_offsets_stream(ostream.data(), ostream.size(), oc, p.nodes, offs);
+    if (rc) { destroy(g); return rc; }
+    g->graph_bits_total = offs[(size_t)p.nodes];
+    g->ext_from = from; g->ext_to = to;
+    g->node_lo = shard_halo(g, from); g->node_hi = to;
+    const uint64_t byte_lo = (offs[(size_t)g->node_lo] >> 3) & ~(uint64_t)15;
+    const uint64_t byte_hi = (offs[(size_t)to] + 7) >> 3;
+    g->bit_base = byte_lo * 8; g->bit_end = offs[(size_t)to];
+    std::vector<uint8_t> bytes;
+    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { destroy(g); return BVG_EIO; }
+    rc = build_device_state(g, bytes.data(), bytes.size(), offs.data() + g->node_lo);
+    if (rc) { destroy(g); return rc; }
+    *out = g;
+    return BVG_OK;
+}
+
+void bvg_close(bvg_graph* g) { destroy(g); }
+
+int bvg_info(const bvg_graph* g, int32_t* nodes, int64_t* arcs, int32_t* window, int32_t* maxref,
+             int32_t* minlen, int32_t* zetak, uint32_t* flags, int64_t* graph_bits) {
+    if (!g) return BVG_EINVAL;
+    if (nodes) *nodes = g->n_total;
+    if (arcs) *arcs = g->m_total;
+    if (window) *window = g->window;
+    if (maxref) *maxref = g->maxref;
+    if (minlen) *minlen = g->minlen;
+    if (zetak) *zetak = g->zetak;
+    if (flags) *flags = g->flags;
+    if (graph_bits) *graph_bits = (int64_t)g->graph_bits_total;
+    return BVG_OK;
+}
+
+int bvg_extent(const bvg_graph* g, int32_t* from, int32_t* to, int32_t* max_chain, int32_t* max_outdegree) {
+    if (!g) return BVG_EINVAL;
+    if (from) *from = g->ext_from;
+    if (to) *to = g->ext_to;
+    if (max_chain) *max_chain = g->max_depth;
+    if (max_outdegree) *max_outdegree = g->max_outdeg;
+    return BVG_OK;
+}
+
+int bvg_random_access(const bvg_graph* g) { return g && g->offset_type > 0 ? 1 : 0; }
+
+int bvg_set_stream(bvg_graph* g, void* cuda_stream) {
+    if (!g) return BVG_EINVAL;
+    g->stream = (cudaStream_t)cuda_stream;
+    return BVG_OK;
+}
+
+int bvg_device(const bvg_graph* g) { return g ? g->device : BVG_EINVAL; }
+
+int bvg_memory_footprint(const bvg_graph* g, int64_t* stream_bytes, int64_t* offsets_bytes, int64_t* index_bytes) {
+    if (!g) return BVG_EINVAL;
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    if (stream_bytes) *stream_bytes = (int64_t)g->nwords * 4;
+    if (offsets_bytes) *offsets_bytes = (nn + 1) * 8;
+    if (index_bytes) *index_bytes = nn * 12 + (nn + 1) * 8;
+    return BVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sequential access
+// ------------------------------------------------------------------------------------------------------------
+
+static int range_check(const bvg_graph* g, int32_t from, int32_t to) {
+    if (!g) return BVG_EINVAL;
+    if (from < g->ext_from || to < from || to > g->ext_to) return BVG_EINVAL;  // BVGraph.java:1165
+    return BVG_OK;
+}
+
+static int fetch_rowoff(const bvg_graph* g, int32_t a, int32_t b, int64_t* va, int64_t* vb) {
+    CK(cudaMemcpyAsync(va, g->d_rowoff + (a - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(vb, g->d_rowoff + (b - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return BVG_OK;
+}
+
+int bvg_range_arcs(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs) {
+    int rc = range_check(g, from, to);
+    if (rc) return rc;
+    DeviceGuard dg(g->device);
+    int64_t a, b;
+    rc = fetch_rowoff(g, from, to, &a, &b);
+    if (rc) return rc;
+    *arcs = b - a;
+    return BVG_OK;
+}
+
+// Enqueues the decode of [from, to) into d_out (device, >= arcs entries). All temporaries are stream-ordered.
+static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from) {
+    if (to == from) return BVG_OK;
+    cudaStream_t s = g->stream;
+    GraphDev gd = g->dev();
+    RowMap rm;
+    rm.out = d_out; rm.out_base = row_from; rm.from = from; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = from;
+    int32_t lo = from;
+    Tmp<int32_t> halo(s);
+    Tmp<int64_t> halo_off(s);
+    if (g->max_depth > 0 && from > g->node_lo) {
+        if (g->d_halo_lists && from == g->ext_from) {  // lists imported from the previous shard
+            rm.halo = g->d_halo_lists; rm.halo_off = g->d_halo_off; rm.halo_lo = from - g->halo_count;
+        } else {  // re-decode the halo, as BVGraphNodeIterator's ctor re-reads the window (BVGraph.java:1173-1183)
+            const int64_t reach = std::min<int64_t>((int64_t)to - from, (int64_t)g->window * g->max_depth);
+            Tmp<int32_t> hs(s);
+            CK(hs.alloc(1));
+            CK(cudaMemcpyAsync(hs.p, &from, 4, cudaMemcpyHostToDevice, s));
+            LAUNCH(k_halo_start, grid_for(reach, 128), 128, 0, s, gd, from, (int32_t)reach, hs.p);
+            int32_t h = from;
+            CK(cudaMemcpyAsync(&h, hs.p, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h < from) {
+                int64_t ra, rb;
+                int rc = fetch_rowoff(g, h, from, &ra, &rb);
+                if (rc) return rc;
+                CK(halo.alloc((size_t)(rb - ra)));
+                CK(halo_off.alloc((size_t)(from - h) + 1));
+                LAUNCH(k_rel_offsets, grid_for((int64_t)from - h + 1, 128), 128, 0, s, g->d_rowoff + (h - g->node_lo), (int64_t)from - h, halo_off.p);
+                rm.halo = halo.p; rm.halo_off = halo_off.p; rm.halo_lo = h;
+                lo = h;
+            }
+        }
+    }
+    const int64_t cnt = (int64_t)to - lo;
+    if (g->def_codec) LAUNCH(k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
+    else LAUNCH(k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
+    for (int32_t level = 1; level <= g->max_depth; level++) {
+        if (g->def_codec) LAUNCH(k_merge<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
+        else LAUNCH(k_merge<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
+    }
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+
+int bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    int rc = range_check(g, from, to);
+    if (rc) return rc;
+    if (!out_off) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    int64_t ra, rb;
+    rc = fetch_rowoff(g, from, to, &ra, &rb);
+    if (rc) return rc;
+    const int64_t arcs = rb - ra, cnt = (int64_t)to - from;
+    if (out && cap < arcs) return BVG_ENOMEM;
+    if (on_device) {
+        LAUNCH(k_rel_offsets, grid_for(cnt + 1, 256), 256, 0, s, g->d_rowoff + (from - g->node_lo), cnt, out_off);
+        if (out) { rc = enqueue_decode(g, from, to, out, ra); if (rc) return rc; }
+        CK(cudaGetLastError());
+        return BVG_OK;
+    }
+    Tmp<int64_t> d_off(s);
+    Tmp<int32_t> d_out(s);
+    CK(d_off.alloc((size_t)cnt + 1));
+    LAUNCH(k_rel_offsets, grid_for(cnt + 1, 256), 256, 0, s, g->d_rowoff + (from - g->node_lo), cnt, d_off.p);
+    CK(cudaMemcpyAsync(out_off, d_off.p, ((size_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (out) {
+        CK(d_out.alloc((size_t)arcs));
+        rc = enqueue_decode(g, from, to, d_out.p, ra);
+        if (rc) return rc;
+        if (arcs) CK(cudaMemcpyAsync(out, d_out.p, (size_t)arcs * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    const int e = fetch_error(g);
+    return e ? e : BVG_OK;
+}
+
+// Scan = decode into a stream-ordered scratch + checksum kernel (general path); ranges are split so that the scratch
+// stays below 2^30 arcs.
+static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned long long* d_result) {
+    if (to == from) return BVG_OK;
+    int64_t ra, rb;
+    int rc = fetch_rowoff(g, from, to, &ra, &rb);
+    if (rc) return rc;
+    const int64_t arcs = rb - ra;
+    if (arcs > ((int64_t)1 << 30) && to - from > 1) {
+        const int32_t mid = from + (to - from) / 2;
+        rc = enqueue_scan(g, from, mid, d_result);
+        if (rc) return rc;
+        return enqueue_scan(g, mid, to, d_result);
+    }
+    cudaStream_t s = g->stream;
+    Tmp<int32_t> rows(s);
+    CK(rows.alloc((size_t)arcs));
+    rc = enqueue_decode(g, from, to, rows.p, ra);
+    if (rc) return rc;
+    const int64_t cnt = (int64_t)to - from;
+    const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (cnt + 7) / 8));
+    LAUNCH(k_checksum, grid, 256, 0, s, rows.p, g->d_rowoff + (from - g->node_lo), from, cnt, d_result);
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+
+int bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_result) {
+    int rc = range_check(g, from, to);
+    if (rc) return rc;
+    if (!d_result) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    CK(cudaMemsetAsync(d_result, 0, 16, g->stream));
+    return enqueue_scan(g, from, to, (unsigned long long*)d_result);
+}
+
+int bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum) {
+    int rc = range_check(g, from, to);
+    if (rc) return rc;
+    DeviceGuard dg(g->device);
+    Tmp<unsigned long long> res(g->stream);
+    CK(res.alloc(2));
+    rc = bvg_scan_range_async(g, from, to, res.p);
+    if (rc) return rc;
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, res.p, 16, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    const int e = fetch_error(g);
+    if (e) return e;
+    if (arcs) *arcs = (int64_t)h[0];
+    if (checksum) *checksum = h[1];
+    return BVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// random access
+// ------------------------------------------------------------------------------------------------------------
+
+int bvg_outdegree_batch(const bvg_graph* g, const int32_t* xs, int32_t from, int64_t nx, int32_t* d, int on_device) {
+    if (!g || nx < 0 || !d) return BVG_EINVAL;
+    if (g->offset_type <= 0) return BVG_ESTATE;  // BVGraph.java:869
+    if (nx == 0) return BVG_OK;
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    GraphDev gd = g->dev();
+    if (on_device) {
+        LAUNCH(k_gather_outdeg, grid_for(nx, 256), 256, 0, s, gd, xs, from, nx, d);
+        CK(cudaGetLastError());
+        return BVG_OK;
+    }
+    Tmp<int32_t> d_xs(s), d_d(s);
+    if (xs) { CK(d_xs.alloc((size_t)nx)); CK(cudaMemcpyAsync(d_xs.p, xs, (size_t)nx * 4, cudaMemcpyHostToDevice, s)); }
+    CK(d_d.alloc((size_t)nx));
+    LAUNCH(k_gather_outdeg, grid_for(nx, 256), 256, 0, s, gd, xs ? d_xs.p : nullptr, from, nx, d_d.p);
+    CK(cudaMemcpyAsync(d, d_d.p, (size_t)nx * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int e = fetch_error(g);
+    return e ? e : BVG_OK;
+}
+
+int bvg_outdegree(const bvg_graph* g, int32_t x, int32_t* d) {
+    if (!g || !d) return BVG_EINVAL;
+    if (x < g->ext_from || x >= g->ext_to) return BVG_EINVAL;  // BVGraph.java:860
+    if (g->offset_type <= 0) return BVG_ESTATE;                 // :869
+    DeviceGuard dg(g->device);
+    CK(cudaMemcpyAsync(d, g->d_outdeg + (x - g->node_lo), 4, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return BVG_OK;
+}
+
+int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    if (!g || nx < 0 || !out_off || (!xs && nx)) return BVG_EINVAL;
+    if (g->offset_type <= 0) return BVG_EUNSUPPORTED;  // BVGraph.java:901
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    GraphDev gd = g->dev();
+    Tmp<int32_t> d_xs(s), dq(s), need(s), d_out(s), scratch(s);
+    Tmp<int64_t> d_off(s), scratch_off(s);
+    const int32_t* xs_dev = xs;
+    if (!on_device) {
+        CK(d_xs.alloc((size_t)nx));
+        if (nx) CK(cudaMemcpyAsync(d_xs.p, xs, (size_t)nx * 4, cudaMemcpyHostToDevice, s));
+        xs_dev = d_xs.p;
+    }
+    CK(dq.alloc((size_t)nx));
+    CK(need.alloc((size_t)nx));
+    CK(scratch_off.alloc((size_t)nx + 1));
+    int64_t* off_dev = out_off;
+    if (!on_device) { CK(d_off.alloc((size_t)nx + 1)); off_dev = d_off.p; }
+    if (nx) LAUNCH(k_query_sizes, grid_for(nx, 256), 256, 0, s, gd, xs_dev, nx, dq.p, need.p);
+    int rc = device_exclusive_scan(s, dq.p, nx, off_dev);
+    if (rc) return rc;
+    rc = device_exclusive_scan(s, need.p, nx, scratch_off.p);
+    if (rc) return rc;
+    int64_t tot[2];
+    CK(cudaMemcpyAsync(&tot[0], off_dev + nx, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&tot[1], scratch_off.p + nx, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int e = fetch_error(g);
+    if (e) return e;
+    if (!on_device) CK(cudaMemcpyAsync(out_off, off_dev, ((size_t)nx + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (!out) { CK(cudaStreamSynchronize(s)); return BVG_OK; }
+    if (cap < tot[0]) return BVG_ENOMEM;
+    int32_t* out_dev = out;
+    if (!on_device) { CK(d_out.alloc((size_t)tot[0])); out_dev = d_out.p; }
+    CK(scratch.alloc((size_t)tot[1]));
+    if (nx) {
+        if (g->def_codec) LAUNCH(k_random<true>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
+        else LAUNCH(k_random<false>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
+    }
+    CK(cudaGetLastError());
+    if (on_device) return BVG_OK;
+    if (tot[0]) CK(cudaMemcpyAsync(out, out_dev, (size_t)tot[0] * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    e = fetch_error(g);
+    return e ? e : BVG_OK;
+}
+
+int bvg_successors(const bvg_graph* g, int32_t x, int32_t* out, int32_t cap, int32_t* d) {
+    if (!g || !d) return BVG_EINVAL;
+    if (x < g->ext_from || x >= g->ext_to) return BVG_EINVAL;  // BVGraph.java:900
+    if (g->offset_type <= 0) return BVG_EUNSUPPORTED;          // :901
+    int32_t deg;
+    int rc = bvg_outdegree(g, x, &deg);
+    if (rc) return rc;
+    if (deg > cap || (!out && deg)) return BVG_ENOMEM;
+    int64_t off[2];
+    rc = bvg_successors_batch(g, &x, 1, off, out, cap, 0);
+    if (rc) return rc;
+    *d = deg;
+    return BVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// NodeIterator
+// ------------------------------------------------------------------------------------------------------------
+
+struct bvg_cursor {
+    const bvg_graph* g;
+    int32_t next;        // next node to return
+    int32_t upper;       // no node >= upper is returned (BVGraph.java:1185)
+    int32_t batch_lo = 0, batch_hi = 0;  // nodes currently held
+    std::vector<int64_t> off;
+    std::vector<int32_t> succ;
+};
+
+int bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor** out) {
+    if (!g || !out) return BVG_EINVAL;
+    if (from < g->ext_from || from > g->ext_to) return BVG_EINVAL;  // BVGraph.java:1165
+    if (from != 0 && g->offset_type <= 0) return BVG_ESTATE;        // :1174
+    bvg_cursor* c = new (std::nothrow) bvg_cursor();
+    if (!c) return BVG_ENOMEM;
+    c->g = g; c->next = from; c->upper = std::min(upper, g->ext_to);
+    *out = c;
+    return BVG_OK;
+}
+
+int bvg_cursor_next(bvg_cursor* c, int32_t* node, int32_t* d, const int32_t** succ) {
+    if (!c) return BVG_EINVAL;
+    if (c->next >= c->upper) return BVG_EEND;  // BVGraph.java:1202
+    if (c->next >= c->batch_hi || c->next < c->batch_lo) {
+        // refill: device decodes a batch of nodes at once (a per-node call would pay a launch per nextInt())
+        int32_t hi = (int32_t)std::min<int64_t>(c->upper, (int64_t)c->next + 65536);
+        int64_t arcs = 0;
+        for (;;) {
+            int rc = bvg_range_arcs(c->g, c->next, hi, &arcs);
+            if (rc) return rc;
+            if (arcs <= ((int64_t)1 << 26) || hi - c->next <= 1) break;
+            hi = c->next + (hi - c->next) / 2;
+        }
+        c->off.resize((size_t)(hi - c->next) + 1);
+        c->succ.resize((size_t)std::max<int64_t>(arcs, 1));
+        int rc = bvg_decode_range(c->g, c->next, hi, c->off.data(), c->succ.data(), arcs, 0);
+        if (rc) return rc;
+        c->batch_lo = c->next; c->batch_hi = hi;
+    }
+    const size_t i = (size_t)(c->next - c->batch_lo);
+    if (node) *node = c->next;
+    if (d) *d = (int32_t)(c->off[i + 1] - c->off[i]);
+    if (succ) *succ = c->succ.data() + c->off[i];
+    c->next++;
+    return BVG_OK;
+}
+
+int bvg_cursor_copy(const bvg_cursor* c, int32_t upper, bvg_cursor** out) {  // BVGraph.java:1252-1260
+    if (!c || !out) return BVG_EINVAL;
+    bvg_cursor* n = new (std::nothrow) bvg_cursor();
+    if (!n) return BVG_ENOMEM;
+    n->g = c->g; n->next = c->next; n->upper = std::min(upper, c->g->ext_to);
+    *out = n;
+    return BVG_OK;
+}
+
+void bvg_cursor_close(bvg_cursor* c) { delete c; }
+
+// ------------------------------------------------------------------------------------------------------------
+// shard boundaries
+// ------------------------------------------------------------------------------------------------------------
+
+int bvg_boundary_count(const bvg_graph* g, int32_t* count) {
+    if (!g || !count) return BVG_EINVAL;
+    if (g->window == 0 || g->maxref == 0) { *count = 0; return BVG_OK; }
+    if (g->maxref < 0 || g->maxref > (1 << 16)) { *count = 0; return BVG_EUNSUPPORTED; }  // unbounded chains: shards re-decode
+    *count = (int32_t)std::min<int64_t>((int64_t)g->window * g->maxref, (int64_t)g->ext_to - g->ext_from);
+    return BVG_OK;
+}
+
+int bvg_boundary_export(const bvg_graph* g, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    int32_t cnt;
+    int rc = bvg_boundary_count(g, &cnt);
+    if (rc) return rc;
+    return bvg_decode_range(g, g->ext_to - cnt, g->ext_to, out_off, out, cap, on_device);
+}
+
+int bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node) {
+    if (!g || !first_needed_node) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    int32_t h = g->ext_from;
+    const int64_t reach = std::min<int64_t>((int64_t)g->ext_to - g->ext_from, (int64_t)g->window * g->max_depth);
+    if (reach > 0 && g->ext_from > g->node_lo) {
+        Tmp<int32_t> hs(s);
+        CK(hs.alloc(1));
+        CK(cudaMemcpyAsync(hs.p, &h, 4, cudaMemcpyHostToDevice, s));
+        LAUNCH(k_halo_start, grid_for(reach, 128), 128, 0, s, g->dev(), g->ext_from, (int32_t)reach, hs.p);
+        CK(cudaMemcpyAsync(&h, hs.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    *first_needed_node = h;
+    return BVG_OK;
+}
+
+int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32_t* lists, int on_device) {
+    if (!g || count < 0 || (count && (!off || !lists))) return BVG_EINVAL;
+    if (count > g->ext_from) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
+    g->d_halo_lists = nullptr; g->d_halo_off = nullptr; g->halo_count = 0;
+    if (count == 0) return BVG_OK;
+    int64_t total = 0;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (on_device) { CK(cudaMemcpyAsync(&total, off + count, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+    else total = off[count];
+    CK(cudaMalloc((void**)&g->d_halo_off, ((size_t)count + 1) * 8));
+    CK(cudaMalloc((void**)&g->d_halo_lists, std::max<size_t>((size_t)total, 1) * 4));
+    CK(cudaMemcpyAsync(g->d_halo_off, off, ((size_t)count + 1) * 8, kind, s));
+    if (total) CK(cudaMemcpyAsync(g->d_halo_lists, lists, (size_t)total * 4, kind, s));
+    CK(cudaStreamSynchronize(s));
+    g->halo_count = count;
+    return BVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------------------------
+
+const char* bvg_strerror(int status) {
+    switch (status) {
+        case BVG_OK: return "ok";
+        case BVG_EINVAL: return "node index out of range / invalid argument (IllegalArgumentException)";
+        case BVG_ESTATE: return "illegal state: offsets not loaded, reference beyond the window, or iterator not advanced (IllegalStateException)";
+        case BVG_EUNSUPPORTED: return "unsupported: random access without offsets, or a coding this build does not decode (UnsupportedOperationException)";
+        case BVG_EIO: return "I/O error or truncated stream (IOException)";
+        case BVG_EFORMAT: return "malformed properties or impossible record";
+        case BVG_ENOMEM: return "out of memory or output buffer too small";
+        case BVG_ECUDA: return t_cuda_msg[0] ? t_cuda_msg : "no usable CUDA device / CUDA runtime error (there is no CPU decode path)";
+        case BVG_EEND: return "no more nodes (NoSuchElementException)";
+        default: return "unknown status";
+    }
+}
+
+int bvg_last_error_node(const bvg_graph* g, int32_t* node, int64_t* bitpos) {
+    if (!g) return BVG_EINVAL;
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (node) *node = g->err_node;
+    if (bitpos) *bitpos = g->err_bitpos;
+    return BVG_OK;
+}
+
+int64_t bvg_kernel_launches(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+// bvg_device.cuh -- device-side bit reader, universal codes and per-record decode steps.
+//
+// Re-designs, for one GPU thread walking one record, what the reference does with
+// it.unimi.dsi.io.InputBitStream + BVGraph.successors(x, ibs, window, outd) (reference
+// src/it/unimi/dsi/webgraph/BVGraph.java:1032-1133) and its lazy iterators (MaskedIntIterator.java:65-97,
+// IntIntervalSequenceIterator.java:57-95, MergedIntIterator.java:50-74, ResidualIntIterator BVGraph.java:939-991).
+// There are no iterators here: a record is decoded in two streaming steps that write straight into the node's
+// row of the output: (1) "extras" = intervals U residuals, merged on the fly from two bit cursors, written to the
+// tail of the row; (2) the copied part, streamed from the parent's finished row through the copy-block list and
+// merged forward, in place, with that tail.
+//
+// Layout: the .graph stream is held in HBM as 32-bit words in big-endian bit order (word i = stream bits
+// [32i, 32i+32), MSB first), so a 64-bit window at any bit position is two funnel shifts over three words.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bvg {
+
+enum { C_DELTA = 1, C_GAMMA = 2, C_GOLOMB = 3, C_SKEWED_GOLOMB = 4, C_UNARY = 5, C_ZETA = 6, C_NIBBLE = 7 };
+
+enum { E_OK = 0, E_INVAL = -1, E_STATE = -2, E_UNSUPPORTED = -3, E_IO = -4, E_FORMAT = -5, E_NOMEM = -6, E_CUDA = -7, E_END = -8 };
+
+// Device-side error word: first failing record wins (the reference throws with node + bit position,
+// BVGraph.java:705, 1129-1131).
+struct ErrWord {
+    int code;       // 0 = none
+    int node;
+    long long bitpos;
+};
+
+struct Codec {
+    int outdeg, block, resid, ref, bcount;  // coding ids, BVGraph.java:525-541
+    int zetak, window, minlen;
+};
+
+// Everything a kernel needs to decode nodes [node_lo, node_hi) held by this graph object.
+struct GraphDev {
+    const uint32_t* __restrict__ words;   // stream words, word 0 = stream bit `bit_base`
+    uint64_t nwords;                      // incl. >= 4 padding words
+    uint64_t bit_base;                    // global bit position of word 0 (multiple of 128)
+    uint64_t bit_end;                     // global bit position one past the last loaded record
+    const uint64_t* __restrict__ offsets; // offsets[x - node_lo], global bit positions, node_hi - node_lo + 1 entries
+    int32_t node_lo, node_hi;
+    Codec c;
+    // decode index (built at open by k_header / scan / k_depth)
+    const int32_t* __restrict__ outdeg;   // [x - node_lo]
+    const int32_t* __restrict__ ref;      // [x - node_lo]  0 = no reference
+    const int32_t* __restrict__ depth;    // [x - node_lo]  reference-chain depth, -1 = chain leaves the loaded window
+    const int64_t* __restrict__ rowoff;   // [x - node_lo]  cumulative outdegree, node_hi - node_lo + 1 entries
+    ErrWord* err;
+};
+
+__device__ __forceinline__ void report(ErrWord* e, int code, int node, uint64_t bitpos) {
+    if (atomicCAS(&e->code, 0, code) == 0) { e->node = node; e->bitpos = (long long)bitpos; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bit cursor over global/shared memory words.
+// ---------------------------------------------------------------------------------------------------
+struct Bits {
+    const uint32_t* __restrict__ w;
+    uint64_t maxw;   // last index for which w[i+2] is readable
+    uint64_t pos;    // bit position relative to w[0]
+
+    __device__ __forceinline__ uint64_t peek() const {
+        uint64_t i = pos >> 5;
+        i = i < maxw ? i : maxw;  // a corrupt stream can run past the end: clamp, the caller reports E_IO
+        const uint32_t s = (uint32_t)pos & 31u;
+        const uint32_t w0 = w[i], w1 = w[i + 1], w2 = w[i + 2];
+        return ((uint64_t)__funnelshift_l(w1, w0, s) << 32) | (uint64_t)__funnelshift_l(w2, w1, s);
+    }
+    // n bits, MSB first, 0 <= n <= 64 (InputBitStream.readInt/readLong)
+    __device__ __forceinline__ uint64_t bits(int n) {
+        if (n == 0) return 0;
+        const uint64_t v = peek() >> (64 - n);
+        pos += (uint64_t)n;
+        return v;
+    }
+    // number of zeros before the first one (InputBitStream.readUnary)
+    __device__ __forceinline__ uint64_t unary() {
+        uint64_t zeros = 0;
+        for (;;) {
+            const uint64_t v = peek();
+            if (v == 0) {
+                zeros += 64; pos += 64;
+                if ((pos >> 5) > maxw + 4) return zeros;
+                continue;
+            }
+            const int z = __clzll((long long)v);
+            pos += (uint64_t)z + 1;
+            return zeros + (uint64_t)z;
+        }
+    }
+    // gamma: unary(msb) then the msb low bits of x+1. One window when the code fits 64 bits (x < 2^32 - 1).
+    __device__ __forceinline__ uint64_t gamma() {
+        const uint64_t v = peek();
+        const int m = __clzll((long long)v);
+        if (m < 32) {  // 2m+1 <= 63 bits: m zeros, a one, m bits == x+1 right-aligned
+            pos += (uint64_t)(2 * m + 1);
+            return (v >> (63 - 2 * m)) - 1;
+        }
+        const uint64_t msb = unary();
+        if (msb > 63) return ~0ull;
+        return ((1ull << msb) | bits((int)msb)) - 1;
+    }
+    __device__ __forceinline__ uint64_t delta() {
+        const uint64_t msb = gamma();
+        if (msb > 63) return ~0ull;
+        return ((1ull << msb) | bits((int)msb)) - 1;
+    }
+    // zeta_k: unary(h), then the minimal binary code of x+1-2^{hk} over [0, 2^{(h+1)k} - 2^{hk})
+    __device__ __forceinline__ uint64_t zeta(int k) {
+        const uint64_t v = peek();
+        const int h = __clzll((long long)v);
+        const int nb = h * k + k - 1;
+        if (v != 0 && h + 1 + nb + 1 <= 64) {
+            const uint64_t left = 1ull << (h * k);
+            const uint64_t t = v << (h + 1);
+            uint64_t m = nb ? t >> (64 - nb) : 0;
+            int len = h + 1 + nb;
+            if (m < left) m += left;
+            else { m = (m << 1) | ((t >> (63 - nb)) & 1ull); len++; }
+            pos += (uint64_t)len;
+            return m - 1;
+        }
+        const uint64_t hh = unary();
+        if (hh * (uint64_t)k + (uint64_t)k > 64) return ~0ull;
+        const uint64_t left = 1ull << (hh * k);
+        const uint64_t m = bits((int)(hh * k) + k - 1);
+        if (m < left) return m + left - 1;
+        return ((m << 1) | bits(1)) - 1;
+    }
+    __device__ __forceinline__ uint64_t coded(int coding, int k) {
+        switch (coding) {
+            case C_GAMMA: return gamma();
+            case C_DELTA: return delta();
+            case C_UNARY: return unary();
+            default:      return zeta(k);
+        }
+    }
+};
+
+// Fast.nat2int (dsiutils): even -> v/2, odd -> -(v+1)/2
+__device__ __forceinline__ int64_t nat2int(uint64_t v) {
+    return (v & 1) ? -(int64_t)((v + 1) >> 1) : (int64_t)(v >> 1);
+}
+
+// Coding policy: DEF = true hard-wires the defaults (gamma outdegrees/blocks/block counts, unary references,
+// zeta residuals; BVGraph.java:525-541) so the switch disappears; k stays a runtime value.
+template <bool DEF>
+struct Rd {
+    static __device__ __forceinline__ uint64_t outdeg(Bits& b, const Codec& c) { return DEF ? b.gamma() : b.coded(c.outdeg, 0); }
+    static __device__ __forceinline__ uint64_t ref(Bits& b, const Codec& c)    { return DEF ? b.unary() : b.coded(c.ref, 0); }
+    static __device__ __forceinline__ uint64_t bcount(Bits& b, const Codec& c) { return DEF ? b.gamma() : b.coded(c.bcount, 0); }
+    static __device__ __forceinline__ uint64_t block(Bits& b, const Codec& c)  { return DEF ? b.gamma() : b.coded(c.block, 0); }
+    static __device__ __forceinline__ uint64_t resid(Bits& b, const Codec& c)  { return DEF ? b.zeta(c.zetak) : b.coded(c.resid, c.zetak); }
+};
+
+__device__ __forceinline__ Bits cursor_at(const GraphDev& g, int32_t x) {
+    Bits b;
+    b.w = g.words;
+    b.maxw = g.nwords - 3;
+    b.pos = g.offsets[x - g.node_lo] - g.bit_base;
+    return b;
+}
+
+#define BVG_INF 0x7fffffffffffffffll
+
+// ---------------------------------------------------------------------------------------------------
+// Step 1: outdegree, reference, copy-block totals, then intervals U residuals merged into row[copied .. d).
+// Returns `copied` (how many successors come from the parent) or a negative error.
+// BVGraph.java:1044-1100; the union order is MergedIntIterator's (equal heads once, :70).
+// ---------------------------------------------------------------------------------------------------
+template <bool DEF>
+__device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restrict__ row) {
+    const Codec& c = g.c;
+    Bits b = cursor_at(g, x);
+    const uint64_t limit = g.bit_end - g.bit_base;
+    const uint64_t d64 = Rd<DEF>::outdeg(b, c);
+    if (d64 > 0x7fffffffull || b.pos > limit) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+    const int64_t d = (int64_t)d64;
+    if (d == 0) return 0;
+    int64_t copied = 0;
+    if (c.window > 0) {
+        const uint64_t r = Rd<DEF>::ref(b, c);
+        if (r > (uint64_t)c.window) { report(g.err, E_STATE, x, b.pos + g.bit_base); return E_STATE; }  // :705
+        if (r > 0) {
+            if ((int64_t)r > (int64_t)x - g.node_lo) { report(g.err, E_FORMAT, x, b.pos + g.bit_base); return E_FORMAT; }
+            const uint64_t bc = Rd<DEF>::bcount(b, c);
+            if (bc > 0x7fffffffull) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+            int64_t total = 0;
+            for (uint64_t i = 0; i < bc; i++) {  // :1062-1066
+                const int64_t blk = (int64_t)Rd<DEF>::block(b, c) + (i ? 1 : 0);
+                total += blk;
+                if (!(i & 1)) copied += blk;
+                if (b.pos > limit) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+            }
+            const int64_t dp = g.outdeg[x - (int32_t)r - g.node_lo];
+            if (!(bc & 1)) copied += dp - total;  // :1069
+            if (total > dp || copied < 0 || copied > d) { report(g.err, E_FORMAT, x, b.pos + g.bit_base); return E_FORMAT; }
+        }
+    }
+    int64_t extra = d - copied;
+    if (extra == 0) return copied;
+    row += copied;
+
+    // interval section: remember where it starts, walk it once to find the residual section (:1076-1096)
+    int64_t ic = 0;
+    Bits ib = b;
+    if (c.minlen != 0) {
+        ic = (int64_t)b.gamma();
+        if (ic > extra || b.pos > limit) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+        ib = b;
+        int64_t tot = 0;
+        for (int64_t i = 0; i < ic; i++) {
+            (void)b.gamma();
+            tot += (int64_t)b.gamma() + c.minlen;
+            if (b.pos > limit || tot > extra) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+        }
+        extra -= tot;
+    }
+    const int64_t total_out = d - copied;
+    int64_t rc = extra;  // residual count
+    // cursors: ib walks intervals, b walks residuals
+    int64_t icur = 0, irem = 0, iprev = 0, ileft = ic;
+    bool ifirst = true;
+    int64_t rnext = 0;
+    if (rc > 0) rnext = (int64_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));  // :954
+    int64_t k = 0;
+    for (;;) {
+        if (irem == 0 && ileft > 0) {  // load the next interval (:1084-1095)
+            if (ifirst) { icur = (int64_t)(int32_t)(nat2int(ib.gamma()) + (int64_t)x); ifirst = false; }
+            else icur = (int64_t)ib.gamma() + iprev + 1;
+            irem = (int64_t)ib.gamma() + c.minlen;
+            iprev = icur + irem;
+            ileft--;
+        }
+        const int64_t iv = irem > 0 ? icur : BVG_INF;
+        const int64_t rv = rc > 0 ? rnext : BVG_INF;
+        if (iv == BVG_INF && rv == BVG_INF) break;
+        if (iv < rv) { row[k++] = (int32_t)iv; icur++; irem--; }
+        else {
+            row[k++] = (int32_t)rv;
+            if (iv == rv) { icur++; irem--; }
+            if (--rc > 0) {
+                rnext += (int64_t)Rd<DEF>::resid(b, c) + 1;  // :966
+                if (b.pos > limit) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+            }
+        }
+    }
+    if (b.pos > limit) { report(g.err, E_IO, x, b.pos + g.bit_base); return E_IO; }
+    while (k < total_out) row[k++] = -1;  // only reachable for files with duplicated successors (:1210 drains -1)
+    return copied;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Step 2: stream the parent's row through the copy blocks (MaskedIntIterator.java:65-97) and merge it, forward and
+// in place, with the extras sitting at row[copied .. d).  Output position never overtakes the unread tail because
+// at most `copied` elements come from the parent.
+// ---------------------------------------------------------------------------------------------------
+template <bool DEF>
+__device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__ row, const int32_t* __restrict__ parent) {
+    const Codec& c = g.c;
+    Bits b = cursor_at(g, x);
+    const int64_t d = (int64_t)Rd<DEF>::outdeg(b, c);
+    const int32_t r = (int32_t)Rd<DEF>::ref(b, c);
+    const int64_t bc = (int64_t)Rd<DEF>::bcount(b, c);
+    const int64_t dp = g.outdeg[x - r - g.node_lo];
+    // first walk: copied count (same arithmetic as step 1)
+    int64_t copied = 0, total = 0;
+    {
+        Bits t = b;
+        for (int64_t i = 0; i < bc; i++) {
+            const int64_t blk = (int64_t)Rd<DEF>::block(t, c) + (i ? 1 : 0);
+            total += blk;
+            if (!(i & 1)) copied += blk;
+        }
+        if (!(bc & 1)) copied += dp - total;
+    }
+    int64_t j = copied, k = 0;   // j: next unread extra, k: next output slot
+    int64_t p = 0;               // next parent index
+    int64_t bi = 0, rem = 0;     // block cursor: index of the next block to read, remaining length of the current copy block
+    bool tail = false;
+    int64_t a = BVG_INF;
+    auto next_a = [&]() -> int64_t {
+        for (;;) {
+            if (rem > 0) { rem--; return parent[p++]; }
+            if (tail) return p < dp ? (int64_t)parent[p++] : BVG_INF;
+            if (bi == bc) { if (bc & 1) return BVG_INF; tail = true; continue; }  // even count: copy the tail
+            const int64_t blk = (int64_t)Rd<DEF>::block(b, c) + (bi ? 1 : 0);
+            if (bi & 1) p += blk; else rem = blk;
+            bi++;
+        }
+    };
+    a = next_a();
+    for (;;) {
+        const int64_t bv = j < d ? (int64_t)row[j] : BVG_INF;
+        if (a == BVG_INF && bv == BVG_INF) break;
+        if (a < bv) { row[k++] = (int32_t)a; a = next_a(); }
+        else { row[k++] = (int32_t)bv; j++; if (a == bv) a = next_a(); }
+    }
+    while (k < d) row[k++] = -1;
+}
+
+}  // namespace bvg

@@ -1,0 +1,291 @@
+// bvg_kernels.cuh -- the general ("any file") kernel set: index build at open, level-synchronous range decode,
+// per-query chain decode for random access, consume-only checksum.  One thread walks one record; reference chains
+// are resolved level by level (depth of the chain, <= maxrefcount for files the reference's writer produced,
+// BVGraph.java:2315,2326), each level reading parents' finished rows.  The tiled shared-memory kernels for the
+// default codings live in bvg_tile.cuh; this set is the fallback they defer to (giant lists, exotic codings,
+// unbounded chains) and the first-round correctness baseline.
+#pragma once
+#include "bvg_device.cuh"
+
+namespace bvg {
+
+// ---------------------------------------------------------------------------------------------------
+// Load-time kernels
+// ---------------------------------------------------------------------------------------------------
+
+// The file's bytes -> big-endian 32-bit words, in place (one-time, at open).
+__global__ void k_bswap(uint32_t* __restrict__ w, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = __byte_perm(w[i], 0, 0x0123);
+}
+
+// Header pass: outdegree and reference of every loaded node (BVGraph.java:1048-1053; outdegree(x) :857-879).
+template <bool DEF>
+__global__ void k_header(GraphDev g, int32_t* __restrict__ outdeg, int32_t* __restrict__ ref) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)g.node_hi - g.node_lo;
+    if (i >= n) return;
+    const int32_t x = g.node_lo + (int32_t)i;
+    Bits b = cursor_at(g, x);
+    const uint64_t limit = g.bit_end - g.bit_base;
+    const uint64_t d = Rd<DEF>::outdeg(b, g.c);
+    int32_t r = 0;
+    if (d > 0x7fffffffull || b.pos > limit) { report(g.err, E_IO, x, b.pos + g.bit_base); outdeg[i] = 0; ref[i] = 0; return; }
+    if (d > 0 && g.c.window > 0) {
+        const uint64_t rr = Rd<DEF>::ref(b, g.c);
+        if (rr > (uint64_t)g.c.window) report(g.err, E_STATE, x, b.pos + g.bit_base);        // BVGraph.java:705
+        else if ((int64_t)rr > (int64_t)x) report(g.err, E_FORMAT, x, b.pos + g.bit_base);    // would address node < 0
+        else r = (int32_t)rr;
+        if (b.pos > limit) report(g.err, E_IO, x, b.pos + g.bit_base);
+    }
+    outdeg[i] = (int32_t)d;
+    ref[i] = r;
+}
+
+// Chain depth of every node; -1 when the chain leaves the loaded window (only possible in a shard's halo).
+__global__ void k_depth(GraphDev g, int32_t* __restrict__ depth, int32_t* __restrict__ maxdepth, int32_t ext_from) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)g.node_hi - g.node_lo;
+    if (i >= n) return;
+    int64_t y = i;
+    int32_t dep = 0;
+    for (;;) {
+        const int32_t r = g.ref[y];
+        if (r == 0) break;
+        if (r > y) { dep = -1; break; }
+        y -= r;
+        dep++;
+    }
+    depth[i] = dep;
+    if (dep > 0) atomicMax(maxdepth, dep);
+    // inside the extent every chain must close within the loaded window (it does when the file honours maxrefcount)
+    if (dep < 0 && g.node_lo + (int32_t)i >= ext_from) report(g.err, E_FORMAT, g.node_lo + (int32_t)i, g.offsets[i]);
+}
+
+__global__ void k_max_i32(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    int32_t m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, in[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// Exclusive scan int32 -> int64, three phases, 2048 items per block.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* total) {
+    __shared__ int64_t warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    int64_t base = 0;
+    int64_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        const int64_t s = warp_sums[w];
+        if (w < wid) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return base + inc - v;
+}
+
+__global__ void k_scan_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ block_sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    int64_t tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void k_scan_blocks(int64_t* __restrict__ block_sums, int64_t nblocks) {  // one block
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nblocks; base += SCAN_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < nblocks ? block_sums[i] : 0;
+        int64_t tot;
+        const int64_t ex = block_exclusive_scan(v, &tot);
+        const int64_t c = carry;
+        if (i < nblocks) block_sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_apply(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ block_sums,
+                             int64_t* __restrict__ out /* n+1 */) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int32_t v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    int64_t run = block_sums[blockIdx.x] + block_exclusive_scan(s, nullptr);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+        if (base + k == n - 1) out[n] = run;
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sequential range decode (general path)
+// ---------------------------------------------------------------------------------------------------
+
+// Where the row of node x lives: nodes of the requested range in `out`, halo nodes (ancestors before `from`)
+// in `halo` (self-decoded or imported from the previous shard).
+struct RowMap {
+    int32_t* out;
+    int64_t out_base;          // rowoff of `from`
+    int32_t from;
+    int32_t* halo;
+    const int64_t* halo_off;   // [x - halo_lo], arc offsets into halo
+    int32_t halo_lo;
+    __device__ __forceinline__ int32_t* row(const GraphDev& g, int32_t x) const {
+        return x >= from ? out + (g.rowoff[x - g.node_lo] - out_base) : halo + halo_off[x - halo_lo];
+    }
+};
+
+// Level 0 for every node of [lo, hi): extras into the row tail; nodes without a reference are complete.
+template <bool DEF>
+__global__ void k_extras(GraphDev g, int32_t lo, int32_t hi, RowMap rm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)hi - lo) return;
+    const int32_t x = lo + (int32_t)i;
+    if (g.outdeg[x - g.node_lo] == 0 || g.depth[x - g.node_lo] < 0) return;  // depth < 0: unneeded halo node
+    decode_extras<DEF>(g, x, rm.row(g, x));
+}
+
+// Level l >= 1: nodes whose chain depth is l merge their parent's (finished) row into their own.
+template <bool DEF>
+__global__ void k_merge(GraphDev g, int32_t lo, int32_t hi, int32_t level, RowMap rm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)hi - lo) return;
+    const int32_t x = lo + (int32_t)i;
+    if (g.depth[x - g.node_lo] != level) return;
+    merge_copied<DEF>(g, x, rm.row(g, x), rm.row(g, x - g.ref[x - g.node_lo]));
+}
+
+// First node any chain starting in [from, to) reaches back to (the halo a range decode has to supply).
+__global__ void k_halo_start(GraphDev g, int32_t from, int32_t count, int32_t* __restrict__ result) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int64_t y = (int64_t)from + i - g.node_lo;
+    for (;;) {
+        const int32_t r = g.ref[y];
+        if (r == 0 || r > y) break;
+        y -= r;
+    }
+    const int32_t root = (int32_t)(y + g.node_lo);
+    if (root < from) atomicMin(result, root);
+}
+
+__global__ void k_rel_offsets(const int64_t* __restrict__ rowoff, int64_t count, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= count) out[i] = rowoff[i] - rowoff[0];
+}
+
+// Consume: one warp per node folds the node's row into (arcs, xor checksum); one atomic pair per block.
+__global__ void k_checksum(const int32_t* __restrict__ rows, const int64_t* __restrict__ rowoff /* at `from` */,
+                           int32_t from, int64_t count, unsigned long long* __restrict__ result /* arcs, xor */) {
+    __shared__ unsigned long long s_x[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    for (int64_t i = (int64_t)blockIdx.x * nw + wid; i < count; i += (int64_t)gridDim.x * nw) {
+        const int64_t a = rowoff[i] - rowoff[0], e = rowoff[i + 1] - rowoff[0];
+        const unsigned long long base = (unsigned long long)(uint32_t)(from + (int32_t)i) * 0x9E3779B97F4A7C15ull;
+        for (int64_t p = a + lane; p < e; p += 32) acc ^= base + (unsigned long long)(uint32_t)rows[p];
+        if (lane == 0) arcs += e - a;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_x[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long v = lane < nw ? s_x[lane] : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicXor(result + 1, v);
+    }
+    if (lane == 0 && arcs) atomicAdd(result, (unsigned long long)arcs);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Random access (general path): one thread per query decodes the query's whole reference chain, root first
+// (the reference recurses lazily down the chain instead, BVGraph.java:1110-1121).
+// ---------------------------------------------------------------------------------------------------
+
+// Per query: outdegree of x and scratch needed for its strict ancestors' rows.
+__global__ void k_query_sizes(GraphDev g, const int32_t* __restrict__ xs, int64_t nx,
+                              int32_t* __restrict__ dq, int32_t* __restrict__ need) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nx) return;
+    const int32_t x = xs[q];
+    if (x < g.node_lo || x >= g.node_hi) { report(g.err, E_INVAL, x, 0); dq[q] = 0; need[q] = 0; return; }
+    int64_t y = x - g.node_lo;
+    dq[q] = g.outdeg[y];
+    if (g.depth[y] < 0) { report(g.err, E_FORMAT, x, 0); need[q] = 0; return; }
+    int64_t s = 0;
+    for (;;) {
+        const int32_t r = g.ref[y];
+        if (r == 0) break;
+        y -= r;
+        s += g.outdeg[y];
+    }
+    need[q] = (int32_t)(s > 0x7fffffff ? 0x7fffffff : s);
+}
+
+template <bool DEF>
+__global__ void k_random(GraphDev g, const int32_t* __restrict__ xs, int64_t nx, const int64_t* __restrict__ out_off,
+                         int32_t* __restrict__ out, const int64_t* __restrict__ scratch_off, int32_t* __restrict__ scratch) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nx) return;
+    const int32_t x = xs[q];
+    if (x < g.node_lo || x >= g.node_hi) return;
+    const int32_t dep = g.depth[x - g.node_lo];
+    if (dep < 0 || g.outdeg[x - g.node_lo] == 0) return;
+    int32_t* cur = scratch + scratch_off[q];
+    const int32_t* parent = nullptr;
+    for (int32_t level = dep; level >= 0; level--) {
+        int32_t y = x;
+        for (int32_t s = 0; s < level; s++) y -= g.ref[y - g.node_lo];  // ancestor at distance `level`
+        int32_t* row = level == 0 ? out + out_off[q] : cur;
+        const int64_t copied = decode_extras<DEF>(g, y, row);
+        if (copied < 0) return;
+        if (g.ref[y - g.node_lo] != 0) merge_copied<DEF>(g, y, row, parent);
+        parent = row;
+        cur += g.outdeg[y - g.node_lo];
+    }
+}
+
+__global__ void k_gather_outdeg(GraphDev g, const int32_t* __restrict__ xs, int32_t from, int64_t nx, int32_t* __restrict__ d) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nx) return;
+    const int32_t x = xs ? xs[q] : from + (int32_t)q;
+    if (x < g.node_lo || x >= g.node_hi) { report(g.err, E_INVAL, x, 0); d[q] = 0; return; }
+    d[q] = g.outdeg[x - g.node_lo];
+}
+
+}  // namespace bvg
