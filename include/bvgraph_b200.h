@@ -60,6 +60,13 @@ int  bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, 
 int  bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                      int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                      uint32_t flags, int offset_type, int device, bvg_graph** out);
+/* Same, holding only nodes [from, to) (+ halo) on the device: what a rank of a multi-GPU run opens when the file is
+ * already in (pinned) host memory. */
+int  bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                           int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                           uint32_t flags, int offset_type, int device, int32_t from, int32_t to, bvg_graph** out);
+/* Host-only: bounds[0..nshards] of contiguous node ranges holding equal shares of the .graph bits. */
+int  bvg_plan_shards(const char* basename, int nshards, int32_t* bounds);
 void bvg_close(bvg_graph* g);
 
 /* numNodes / numArcs / windowSize / maxRefCount / minIntervalLength / zetaK / flags (BVGraph.java:579-625). */
@@ -122,6 +129,10 @@ const char* bvg_strerror(int status);
 int  bvg_last_error_node(const bvg_graph* g, int32_t* node, int64_t* bitpos);
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
 int64_t bvg_kernel_launches(void);
+/* Per-kernel device timing for bench.py's roofline object: while enabled every kernel of this graph is bracketed by CUDA
+ * events on the launching stream; bvg_profile_read drains them into a JSON object {"kernel": {"launches": n, "ms": t}}. */
+int  bvg_profile(const bvg_graph* g, int enable);
+int  bvg_profile_read(const bvg_graph* g, char* buf, int cap);
 /* Bytes of HBM held by the graph: bit stream, offsets, decode index. */
 int  bvg_memory_footprint(const bvg_graph* g, int64_t* stream_bytes, int64_t* offsets_bytes, int64_t* index_bytes);
 

@@ -320,6 +320,26 @@ fail:
  *   ResidualIntIterator, BVGraph.java:939-991 -> inline loop
  *   MergedIntIterator.java:42-74  -> merge_dedup()
  * ---------------------------------------------------------------------------------------- */
+/* Grow-only per-thread scratch so the per-node path does not allocate. */
+typedef struct {
+    int64_t* block; int64_t block_cap;
+    int32_t* buf[4]; int64_t cap[4];   /* copied, extras, intervals, union */
+} scratch_t;
+
+static int64_t* scratch_block(scratch_t* sc, int64_t n) {
+    if (sc->block_cap < n) { free(sc->block); sc->block = (int64_t*)malloc((size_t)(n + 16) * 2 * sizeof(int64_t)); sc->block_cap = (n + 16) * 2; }
+    return sc->block;
+}
+static int32_t* scratch_buf(scratch_t* sc, int which, int64_t n) {
+    if (sc->cap[which] < n + 1) { free(sc->buf[which]); sc->buf[which] = (int32_t*)malloc((size_t)(n + 16) * 2 * sizeof(int32_t)); sc->cap[which] = (n + 16) * 2; }
+    return sc->buf[which];
+}
+static void scratch_free(scratch_t* sc) {
+    free(sc->block);
+    for (int i = 0; i < 4; i++) free(sc->buf[i]);
+    memset(sc, 0, sizeof *sc);
+}
+
 typedef struct {
     int32_t** list;   /* W+1 rows */
     int32_t*  cap;
@@ -343,7 +363,7 @@ static int32_t merge_dedup(const int32_t* a, int32_t na, const int32_t* b, int32
 
 /* Reads a record whose outdegree d has just been read; writes the d successors to out. */
 static int decode_record(const orc_graph* g, int32_t x, ibs_t* s, int32_t d,
-                         const window_t* win, int32_t* out) {
+                         const window_t* win, scratch_t* sc, int32_t* out) {
     int err = 0;
     if (d == 0) return BVGO_OK; /* :1049 */
     const int32_t W = g->window;
@@ -366,13 +386,13 @@ static int decode_record(const orc_graph* g, int32_t x, ibs_t* s, int32_t d,
         if (err) return err;
         if (bc64 > (uint64_t)1 << 31 || s->pos > s->nbits) return BVGO_EIO;
         const int32_t bc = (int32_t)bc64;
-        int64_t* block = bc ? (int64_t*)malloc((size_t)bc * sizeof(int64_t)) : NULL;
+        int64_t* block = scratch_block(sc, bc);
         int64_t total = 0, cp = 0;
         for (int32_t i = 0; i < bc; i++) {
             block[i] = (int64_t)read_coded(s, g->block_coding, 0, &err) + (i == 0 ? 0 : 1); /* :1063 */
             total += block[i];
             if ((i & 1) == 0) cp += block[i];
-            if (err || s->pos > s->nbits) { free(block); return err ? err : BVGO_EIO; }
+            if (err || s->pos > s->nbits) return err ? err : BVGO_EIO;
         }
         /* the reference list: window row (sequential) or recursion (random access), :1116-1120 */
         const int32_t* parent;
@@ -385,14 +405,14 @@ static int decode_record(const orc_graph* g, int32_t x, ibs_t* s, int32_t d,
         } else {
             int32_t pcap = 0;
             int64_t r = decode_random(g, x - ref, &parent_owned, &pcap);
-            if (r < 0) { free(block); free(parent_owned); return (int)r; }
+            if (r < 0) { free(parent_owned); return (int)r; }
             parent = parent_owned;
             dp = (int32_t)r;
         }
         if ((bc & 1) == 0) cp += dp - total; /* :1069 */
-        if (total > dp || cp < 0 || cp > d) { free(block); free(parent_owned); return BVGO_EFORMAT; }
+        if (total > dp || cp < 0 || cp > d) { free(parent_owned); return BVGO_EFORMAT; }
         copied = (int32_t)cp;
-        copied_list = (int32_t*)malloc(((size_t)copied + 1) * sizeof(int32_t));
+        copied_list = scratch_buf(sc, 0, copied);
         /* MaskedIntIterator.java:65-97: copy block[0], skip block[1], ...; tail copied iff bc even */
         int32_t k = 0, p = 0;
         for (int32_t i = 0; i < bc; i++) {
@@ -400,12 +420,11 @@ static int decode_record(const orc_graph* g, int32_t x, ibs_t* s, int32_t d,
             else p += (int32_t)block[i];
         }
         if ((bc & 1) == 0) while (p < dp) copied_list[k++] = parent[p++];
-        free(block);
         free(parent_owned);
     }
 
     int64_t extra = (int64_t)d - copied; /* :1070-1072 */
-    extra_list = (int32_t*)malloc(((size_t)(extra > 0 ? extra : 0) + 1) * sizeof(int32_t));
+    extra_list = scratch_buf(sc, 1, extra > 0 ? extra : 0);
     int32_t ne = 0;
     int32_t* interval_list = NULL;
     int32_t ni = 0;
@@ -414,7 +433,7 @@ static int decode_record(const orc_graph* g, int32_t x, ibs_t* s, int32_t d,
         const uint64_t ic = ibs_read_gamma(s);
         if (ic > (uint64_t)extra || s->pos > s->nbits) { rc = BVGO_EIO; goto done; }
         if (ic) {
-            interval_list = (int32_t*)malloc(((size_t)extra + 1) * sizeof(int32_t));
+            interval_list = scratch_buf(sc, 2, extra);
             int64_t prev = 0;
             for (uint64_t i = 0; i < ic; i++) {
                 int64_t left;
@@ -442,19 +461,17 @@ static int decode_record(const orc_graph* g, int32_t x, ibs_t* s, int32_t d,
     if (s->pos > s->nbits) { rc = BVGO_EIO; goto done; }
 
     { /* Merged(Masked, Merged(Intervals, Residuals)), :1103-1126 */
-        int32_t* tmp = (int32_t*)malloc(((size_t)ni + ne + 1) * sizeof(int32_t));
-        const int32_t nx = merge_dedup(interval_list, ni, extra_list, ne, tmp);
-        int32_t* fin = (int32_t*)malloc(((size_t)copied + nx + 1) * sizeof(int32_t));
-        const int32_t nf = merge_dedup(copied_list, copied, tmp, nx, fin);
+        /* out never aliases a scratch buffer or the parent row, so the last union writes it directly */
+        const int32_t* ex = extra_list;
+        int32_t nx = ne;
+        if (ni) { int32_t* tmp = scratch_buf(sc, 3, (int64_t)ni + ne); nx = merge_dedup(interval_list, ni, extra_list, ne, tmp); ex = tmp; }
+        int32_t nf;
+        if (copied) nf = merge_dedup(copied_list, copied, ex, nx, out);
+        else { memcpy(out, ex, (size_t)nx * sizeof(int32_t)); nf = nx; }
         /* BVGraphNodeIterator.nextInt drains exactly d values, -1 once exhausted (:1210) */
-        for (int32_t i = 0; i < d; i++) out[i] = i < nf ? fin[i] : -1;
-        free(tmp);
-        free(fin);
+        for (int32_t i = nf; i < d; i++) out[i] = -1;
     }
 done:
-    free(copied_list);
-    free(extra_list);
-    free(interval_list);
     return rc;
 }
 
@@ -488,7 +505,10 @@ static int64_t decode_random(const orc_graph* g, int32_t x, int32_t** out, int32
         *out = (int32_t*)malloc(((size_t)d + 1) * sizeof(int32_t));
         *outcap = d;
     }
-    int rc = decode_record(g, x, &s, d, NULL, *out);
+    scratch_t sc;
+    memset(&sc, 0, sizeof sc);
+    int rc = decode_record(g, x, &s, d, NULL, &sc, *out);
+    scratch_free(&sc);
     return rc < 0 ? rc : d;
 }
 
@@ -530,6 +550,8 @@ static int64_t sequential(const orc_graph* g, int32_t from, int32_t to, int mode
     w.cap = (int32_t*)calloc((size_t)w.size, sizeof(int32_t));
     w.outd = (int32_t*)calloc((size_t)w.size, sizeof(int32_t));
     int64_t rc = 0;
+    scratch_t sc;
+    memset(&sc, 0, sizeof sc);
     /* seed the window by random access, :1173-1183 */
     if (from != 0) {
         for (int32_t i = 1; i < (from + 1 < w.size ? from + 1 : w.size); i++) {
@@ -552,7 +574,7 @@ static int64_t sequential(const orc_graph* g, int32_t from, int32_t to, int mode
             if (err) { rc = err; goto done; }
             if (s.pos > s.nbits) { rc = BVGO_EIO; goto done; }
             window_reserve(&w, idx, d);
-            int r = decode_record(g, x, &s, d, &w, w.list[idx]);
+            int r = decode_record(g, x, &s, d, &w, &sc, w.list[idx]);
             if (r < 0) { rc = r; goto done; }
             w.outd[idx] = d;
             if (mode == 0) {
@@ -573,6 +595,7 @@ static int64_t sequential(const orc_graph* g, int32_t from, int32_t to, int mode
     }
 done:
     window_free(&w);
+    scratch_free(&sc);
     return rc;
 }
 

@@ -1,0 +1,349 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the reference's golden pair and the oracle.
+
+Each test names the reference test it mirrors.  Bit-exact (integer work): every successor list must equal
+BVGraph.successors() on the same .graph/.properties input.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests import graphs
+from tests import oracle_binding as ob
+from tests.conftest import CNR
+from webgraph_b200 import bvgraph, tools
+from webgraph_b200.bvgraph import BVGraph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cnr():
+    g = BVGraph.load(CNR)
+    yield g
+    g.close()
+
+
+# ---- BVGraphTest.testLarge (reference test/it/unimi/dsi/webgraph/BVGraphTest.java:101-119) ----
+
+def test_cnr2000_properties(cnr):
+    assert (cnr.numNodes(), cnr.numArcs(), cnr.windowSize(), cnr.maxRefCount(), cnr.minIntervalLength(), cnr.zetaK()) == \
+        (325557, 3216152, 7, 3, 3, 3)
+    assert cnr.randomAccess()
+    assert cnr.extent()[2] == 3 and cnr.extent()[3] == 2716  # chain depth 3, max outdegree 2716
+
+
+def test_cnr2000_sequential_equals_ascii(cnr, cnr_truth):
+    toff, tsucc = cnr_truth
+    off, succ = cnr.decodeRange(0, cnr.numNodes())
+    assert np.array_equal(off, toff)
+    assert np.array_equal(succ, tsucc)
+
+
+def test_cnr2000_node_iterator(cnr, cnr_truth):
+    toff, tsucc = cnr_truth
+    it = cnr.nodeIterator()
+    with pytest.raises(bvgraph.IllegalStateError):
+        it.outdegree()  # BVGraph.java:1237
+    x = -1
+    while it.hasNext():
+        x = it.nextInt()
+        d = it.outdegree()
+        assert d == toff[x + 1] - toff[x]
+        if x % 97 == 0 or d > 500:
+            assert np.array_equal(it.successorArray(), tsucc[toff[x]:toff[x + 1]])
+    assert x == cnr.numNodes() - 1
+    with pytest.raises(bvgraph.NoSuchElementError):
+        it.nextInt()  # :1202
+
+
+def test_cnr2000_random_access_all_nodes(cnr, cnr_truth):
+    toff, tsucc = cnr_truth
+    n = cnr.numNodes()
+    perm = np.random.default_rng(3).permutation(n).astype(np.int32)
+    off, succ = cnr.successorsBatch(perm)
+    assert np.array_equal(np.diff(off), (toff[1:] - toff[:-1])[perm])
+    # compare list by list through a gather of the truth
+    idx = np.concatenate([np.arange(toff[x], toff[x + 1]) for x in perm[:20000]])
+    assert np.array_equal(succ[:len(idx)], tsucc[idx])
+    # checksum of everything: order-independent, covers all nodes
+    assert ob.xor_checksum(toff, tsucc) == _checksum_batch(perm, off, succ)
+    assert np.array_equal(cnr.outdegreeBatch(perm), np.diff(off).astype(np.int32))
+
+
+def _checksum_batch(xs, off, succ):
+    deg = np.diff(off)
+    x64 = np.repeat(xs.astype(np.uint64), deg)
+    with np.errstate(over="ignore"):
+        v = x64 * np.uint64(0x9E3779B97F4A7C15) + succ.astype(np.int64).astype(np.uint64)
+    return int(np.bitwise_xor.reduce(v)) if len(v) else 0
+
+
+def test_cnr2000_single_node_calls(cnr, cnr_truth):
+    toff, tsucc = cnr_truth
+    for x in [0, 1, 2, 3, 4, 1000, 325556, 172345]:
+        d = cnr.outdegree(x)
+        assert d == toff[x + 1] - toff[x]
+        it = cnr.successors(x)
+        got = [it.nextInt() for _ in range(d + 2)]  # the reference test reads the terminating -1 (BVGraphTest.java:115)
+        assert got[:d] == list(tsucc[toff[x]:toff[x + 1]]) and got[d:] == [-1, -1]
+    assert list(cnr.successorArray(0)) == [1, 342, 343, 344, 345, 346, 347, 348, 349, 350, 351, 211284, 223142]
+    assert list(cnr.successorArray(2)) == [211284, 223142]
+
+
+def test_cnr2000_scan_checksum(cnr):
+    arcs, cs = cnr.scanRange(0, cnr.numNodes())
+    assert arcs == 3216152 and cs == 0xf941dd3471d172f1
+
+
+def test_cnr2000_ranges_and_split_iterators(cnr, cnr_truth, oracle):
+    toff, tsucc = cnr_truth
+    n = cnr.numNodes()
+    for lo, hi in [(1, 50), (7, 8), (1000, 1200), (n - 10, n), (n, n), (12345, 12345), (100000, 230000), (3, 4)]:
+        off, succ = cnr.decodeRange(lo, hi)
+        assert np.array_equal(off, toff[lo:hi + 1] - toff[lo])
+        assert np.array_equal(succ, tsucc[toff[lo]:toff[hi]])
+        arcs, cs = cnr.scanRange(lo, hi)
+        assert arcs == toff[hi] - toff[lo]
+        assert cs == ob.xor_checksum(toff[lo:hi + 1], tsucc[toff[lo]:toff[hi]], first_node=lo)
+    # assertSplitIterator (WebGraphTestCase.java:66-103): every node exactly once, same lists
+    for k in (1, 4, 7):
+        seen = 0
+        for it in cnr.splitNodeIterators(k):
+            if it is None:
+                continue
+            while it.hasNext():
+                x = it.nextInt()
+                seen += 1
+                if x % 1013 == 0:
+                    assert np.array_equal(it.successorArray(), tsucc[toff[x]:toff[x + 1]])
+        assert seen == n
+
+
+def test_argument_errors(cnr):
+    n = cnr.numNodes()
+    with pytest.raises(ValueError):
+        cnr.outdegree(n)          # BVGraph.java:860
+    with pytest.raises(ValueError):
+        cnr.successorArray(-1)    # :900
+    with pytest.raises(ValueError):
+        cnr.nodeIterator(n + 1)   # :1165
+    with pytest.raises(ValueError):
+        cnr.decodeRange(5, 4)
+    g = BVGraph.loadOffline(CNR)  # no random access (:901), sequential still fine
+    assert not g.randomAccess()
+    with pytest.raises(bvgraph.UnsupportedOperationError):
+        g.successorArray(3)
+    with pytest.raises(bvgraph.IllegalStateError):
+        g.outdegree(3)            # :869
+    with pytest.raises(bvgraph.IllegalStateError):
+        g.nodeIterator(5)         # :1174
+    arcs, cs = g.scanRange(0, g.numNodes())
+    assert arcs == 3216152 and cs == 0xf941dd3471d172f1
+    g.close()
+
+
+# ---- WebGraphTestCase.assertGraph (reference test/it/unimi/dsi/webgraph/WebGraphTestCase.java:158-260) ----
+
+def assert_graph(g, off, succ):
+    n = g.numNodes()
+    assert n == len(off) - 1
+    o2, s2 = g.decodeRange(0, n)
+    assert np.array_equal(o2, off) and np.array_equal(s2, succ)
+    it = g.nodeIterator()
+    for x in range(n):
+        assert it.hasNext() and it.nextInt() == x
+        assert it.outdegree() == off[x + 1] - off[x]
+        assert np.array_equal(it.successorArray(), succ[off[x]:off[x + 1]])
+    assert not it.hasNext()
+    if n:
+        xs = np.arange(n, dtype=np.int32)
+        bo, bs = g.successorsBatch(xs)
+        assert np.array_equal(bo, off) and np.array_equal(bs, succ)
+    # for every start s: nodeIterator(s) agrees with random access
+    for s in range(0, n + 1, max(1, n // 16)):
+        o3, s3 = g.decodeRange(s, n)
+        assert np.array_equal(o3, off[s:] - off[s]) and np.array_equal(s3, succ[off[s]:])
+    arcs, cs = g.scanRange(0, n)
+    assert arcs == len(succ) and cs == ob.xor_checksum(off, succ)
+
+
+@pytest.mark.parametrize("kind", ["intree", "outtree", "complete"])
+def test_compression_matrix(tmp_path, kind):  # BVGraphTest.testCompression :50-99 (+ complete graphs)
+    for n in range(1, 8):
+        off, succ = {"intree": graphs.binary_intree, "outtree": graphs.binary_outtree, "complete": graphs.complete_graph}[kind](n)
+        for w in range(3):
+            for r in range(1 if w == 0 else 3):
+                for i in (0, 1, 3):
+                    base = str(tmp_path / "g")
+                    tools.store_csr(base, off, succ, window=w, maxref=r, minlen=i, zetak=3)
+                    for loader in (BVGraph.load, BVGraph.loadMapped):
+                        g = loader(base)
+                        assert_graph(g, off, succ)
+                        g.close()
+
+
+@pytest.mark.parametrize("n,p", [(5, .1), (10, .3), (100, .5), (100, .9)])
+def test_erdos_renyi(tmp_path, n, p):  # ImmutableGraphTest.java:68-82
+    off, succ = graphs.erdos_renyi(n, p, seed=n * 7 + int(p * 10))
+    base = str(tmp_path / "er")
+    tools.store_csr(base, off, succ)
+    g = BVGraph.load(base)
+    assert_graph(g, off, succ)
+    g.close()
+
+
+@pytest.mark.parametrize("flags,k", [
+    (0, 1), (0, 2), (0, 5),
+    (tools.OUTDEGREES_DELTA | tools.BLOCKS_DELTA | tools.RESIDUALS_DELTA | tools.REFERENCES_DELTA | tools.BLOCK_COUNT_DELTA | tools.OFFSETS_DELTA, 3),
+    (tools.RESIDUALS_GAMMA | tools.REFERENCES_GAMMA | tools.BLOCK_COUNT_UNARY | tools.BLOCKS_UNARY, 3),
+])
+def test_non_default_codings(tmp_path, oracle, flags, k):  # parity unpinned by the reference; checked against the oracle
+    off, succ, _ = graphs.copy_heavy(1500, seed=5)
+    base = str(tmp_path / "f")
+    tools.store_csr(base, off, succ, flags=flags, zetak=k)
+    g = BVGraph.load(base)
+    assert_graph(g, off, succ)
+    g.close()
+
+
+def test_copy_heavy_chains_and_unbounded_refcount(tmp_path):
+    off, succ, _ = graphs.copy_heavy(5000, seed=21, maxdeg=120)
+    for maxref, w in [(3, 7), (-1, 7), (1, 1), (10, 16)]:
+        base = str(tmp_path / ("c%d_%d" % (maxref, w)))
+        st = tools.store_csr(base, off, succ, maxref=maxref, window=w)
+        g = BVGraph.load(base)
+        assert g.extent()[2] == st["max_ref_chain"]
+        assert_graph(g, off, succ)
+        g.close()
+
+
+# ---- BASELINE configs C1/C2: 100 k-node synthetic power-law graph, full decode bit-exact ----
+
+@pytest.fixture(scope="module")
+def synth100k(tmp_path_factory):
+    base = str(tmp_path_factory.mktemp("synth") / "pl100k")
+    st, off, succ = tools.generate_store(base, 100000, 3000000, seed=0x5EED, return_csr=True, threads=4)
+    return base, st, off, succ
+
+
+def test_synthetic_100k_full_decode(synth100k, oracle):
+    base, st, off, succ = synth100k
+    g = BVGraph.load(base)
+    o, s = g.decodeRange(0, g.numNodes())
+    assert np.array_equal(o, off) and np.array_equal(s, succ)
+    og = oracle.load(base)
+    oo, os_ = og.decode_range(0, og.n)  # the oracle agrees with the generator's own lists
+    assert np.array_equal(oo, off) and np.array_equal(os_, succ)
+    arcs, cs = g.scanRange(0, g.numNodes())
+    assert arcs == st["arcs"] and cs == st["xor_checksum"]
+    g.close()
+
+
+def test_synthetic_100k_random_access(synth100k):
+    base, st, off, succ = synth100k
+    g = BVGraph.load(base)
+    xs = np.random.default_rng(9).integers(0, g.numNodes(), 50000).astype(np.int32)
+    bo, bs = g.successorsBatch(xs)
+    assert np.array_equal(np.diff(bo), (off[1:] - off[:-1])[xs])
+    assert _checksum_batch(xs, bo, bs) == _checksum_batch(xs, bo, np.concatenate([succ[off[x]:off[x + 1]] for x in xs]))
+    g.close()
+
+
+# ---- range sharding (assertSplitIterator + BVGraph.java:1173-1183) ----
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+def test_shards_halo_redecode_and_import(synth100k, shards):
+    base, st, off, succ = synth100k
+    n = len(off) - 1
+    cuts = [n * i // shards for i in range(shards + 1)]
+    cuts[1] = min(cuts[1] + 3, cuts[2])  # an uneven cut for good measure
+    tot_arcs, tot_cs = 0, 0
+    prev = None
+    for i in range(shards):
+        g = BVGraph.loadShard(base, cuts[i], cuts[i + 1])
+        lo, hi = cuts[i], cuts[i + 1]
+        assert g.extent()[:2] == (lo, hi)
+        o, s = g.decodeRange(lo, hi)  # halo re-decoded from the shard's own bits
+        assert np.array_equal(o, off[lo:hi + 1] - off[lo]) and np.array_equal(s, succ[off[lo]:off[hi]])
+        if prev is not None:  # the previous shard's exported boundary lists replace the re-decode
+            import ctypes as C
+            cnt, boff, blists = prev
+            bvgraph._check(bvgraph.lib().bvg_halo_import(g.handle, cnt, boff.ctypes.data, blists.ctypes.data, 0))
+            o2, s2 = g.decodeRange(lo, hi)
+            assert np.array_equal(o2, o) and np.array_equal(s2, s)
+        arcs, cs = g.scanRange(lo, hi)
+        tot_arcs += arcs
+        tot_cs ^= cs
+        import ctypes as C
+        cnt = C.c_int32()
+        bvgraph._check(bvgraph.lib().bvg_boundary_count(g.handle, C.byref(cnt)))
+        assert cnt.value == min(21, hi - lo)
+        boff = np.zeros(cnt.value + 1, dtype=np.int64)
+        cap = int(off[hi] - off[hi - cnt.value])
+        blists = np.empty(max(cap, 1), dtype=np.int32)
+        bvgraph._check(bvgraph.lib().bvg_boundary_export(g.handle, boff.ctypes.data, blists.ctypes.data, cap, 0))
+        assert np.array_equal(blists[:cap], succ[off[hi - cnt.value]:off[hi]])
+        prev = (cnt.value, boff, blists)
+        g.close()
+    assert tot_arcs == st["arcs"] and tot_cs == st["xor_checksum"]
+
+
+# ---- corrupt input: error code + node, never a fault (BVGraph.java:705, 1129-1131) ----
+
+def test_corrupt_stream_reports_error(tmp_path):
+    off, succ, _ = graphs.copy_heavy(3000, seed=2)
+    base = str(tmp_path / "ok")
+    tools.store_csr(base, off, succ)
+    graph = bytearray(open(base + ".graph", "rb").read())
+    offs = open(base + ".offsets", "rb").read()
+    rng = np.random.default_rng(0)
+    failures = 0
+    for trial in range(12):
+        bad = bytearray(graph)
+        for _ in range(40):
+            bad[int(rng.integers(0, len(bad)))] ^= int(rng.integers(1, 256))
+        try:
+            g = BVGraph.fromMemory(bytes(bad), offs, len(off) - 1, len(succ), 7, 3, 4)
+            try:
+                g.decodeRange(0, g.numNodes())
+                g.successorsBatch(np.arange(g.numNodes(), dtype=np.int32))
+            finally:
+                g.close()
+        except (bvgraph.IllegalStateError, IOError, MemoryError):
+            failures += 1
+    assert failures > 0  # some corruption is detected; none of it crashes or hangs the device
+    g = BVGraph.fromMemory(bytes(graph), offs, len(off) - 1, len(succ), 7, 3, 4)  # the device is still healthy
+    o, s = g.decodeRange(0, g.numNodes())
+    assert np.array_equal(s, succ)
+    g.close()
+    with pytest.raises(IOError):  # truncated stream
+        BVGraph.fromMemory(bytes(graph[:len(graph) // 2]), offs, len(off) - 1, len(succ), 7, 3, 4)
+
+
+# ---- extremes (scaled-down BVGraphSlowTest, reference slow/it/unimi/dsi/webgraph/BVGraphSlowTest.java:30-96) ----
+
+def test_extremes_large_ids_and_giant_lists(tmp_path):
+    n = 3_000_000
+    lists = {0: np.arange(0, n, 4, dtype=np.int32), 1: np.arange(1, n, 4, dtype=np.int32),
+             2: np.array([n - 1], dtype=np.int32), n - 1: np.array([0, 1, n - 2], dtype=np.int32),
+             n - 2: np.arange(n - 5000, n, dtype=np.int32)}
+    deg = np.zeros(n, dtype=np.int64)
+    for k, v in lists.items():
+        deg[k] = len(v)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=off[1:])
+    succ = np.concatenate([lists[k] for k in sorted(lists)])
+    base = str(tmp_path / "big")
+    tools.store_csr(base, off, succ, threads=4)
+    g = BVGraph.load(base)
+    assert g.extent()[3] == len(lists[0])
+    o, s = g.decodeRange(0, 3)
+    assert np.array_equal(s, succ[:off[3]])
+    o, s = g.decodeRange(n - 3, n)
+    assert np.array_equal(s, succ[off[n - 3]:])
+    bo, bs = g.successorsBatch(np.array([n - 1, 0, n - 2, 5], dtype=np.int32))
+    assert np.array_equal(bs, np.concatenate([lists[n - 1], lists[0], lists[n - 2]]))
+    arcs, cs = g.scanRange(0, n)
+    assert arcs == len(succ) and cs == ob.xor_checksum(off, succ)
+    g.close()

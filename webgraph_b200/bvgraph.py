@@ -54,6 +54,7 @@ SYMBOLS = [
     "bvg_range_arcs", "bvg_decode_range", "bvg_scan_range", "bvg_scan_range_async", "bvg_cursor_open", "bvg_cursor_next",
     "bvg_cursor_copy", "bvg_cursor_close", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
+    "bvg_open_memory_shard", "bvg_plan_shards", "bvg_profile", "bvg_profile_read",
 ]
 
 
@@ -67,6 +68,10 @@ def lib():
     L.bvg_open.argtypes = [C.c_char_p, C.c_int, P(C.c_int), C.c_int, P(vp)]
     L.bvg_open_shard.argtypes = [C.c_char_p, C.c_int, i32, i32, P(vp)]
     L.bvg_open_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, P(vp)]
+    L.bvg_open_memory_shard.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, i32, i32, P(vp)]
+    L.bvg_plan_shards.argtypes = [C.c_char_p, C.c_int, P(i32)]
+    L.bvg_profile.argtypes = [vp, C.c_int]
+    L.bvg_profile_read.argtypes = [vp, C.c_char_p, C.c_int]
     L.bvg_close.argtypes = [vp]
     L.bvg_close.restype = None
     L.bvg_info.argtypes = [vp, P(i32), P(i64), P(i32), P(i32), P(i32), P(i32), P(u32), P(i64)]
@@ -435,6 +440,15 @@ class BVGraph(ImmutableGraph):
     def setStream(self, cuda_stream):
         _check(lib().bvg_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def profile(self, enable):
+        _check(lib().bvg_profile(self._h, 1 if enable else 0))
+
+    def profileRead(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().bvg_profile_read(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def memoryFootprint(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(lib().bvg_memory_footprint(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -451,3 +465,10 @@ class BVGraph(ImmutableGraph):
 
 def kernel_launches():
     return int(lib().bvg_kernel_launches())
+
+
+def plan_shards(basename, nshards):
+    """Bit-balanced contiguous node ranges: bounds[0..nshards]."""
+    b = (C.c_int32 * (nshards + 1))()
+    _check(lib().bvg_plan_shards(os.fsencode(basename), nshards, b))
+    return list(b)

@@ -21,6 +21,13 @@ static std::atomic<int64_t> g_launches{0};
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_cuda_error(e_, #call); return BVG_ECUDA; } } while (0)
 #define LAUNCH(kernel, grid, block, smem, stream, ...) do { \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches.fetch_add(1, std::memory_order_relaxed); } while (0)
+// Same, bracketed by CUDA events on the launching stream when per-kernel profiling is on (bvg_profile).
+#define LAUNCH_P(g, name, kernel, grid, block, smem, stream, ...) do { \
+    ProfSpan* ps_ = (g)->prof_begin(name, stream); \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); g_launches.fetch_add(1, std::memory_order_relaxed); \
+    (g)->prof_end(ps_, stream); } while (0)
+
+struct ProfSpan { const char* name; cudaEvent_t e0, e1; };
 
 static thread_local char t_cuda_msg[256];
 static void set_cuda_error(cudaError_t e, const char* what) {
@@ -56,6 +63,23 @@ struct bvg_graph {
     int32_t* d_halo_lists = nullptr;
     int64_t* d_halo_off = nullptr;
     int32_t halo_count = 0;
+    int64_t halo_off_cap = 0, halo_lists_cap = 0;
+    // per-kernel timing (bench.py's roofline object): spans recorded while prof_on
+    mutable bool prof_on = false;
+    mutable std::vector<ProfSpan*> prof_spans;
+    ProfSpan* prof_begin(const char* name, cudaStream_t s) const {
+        if (!prof_on) return nullptr;
+        ProfSpan* p = new ProfSpan{ name, nullptr, nullptr };
+        cudaEventCreate(&p->e0); cudaEventCreate(&p->e1);
+        cudaEventRecord(p->e0, s);
+        return p;
+    }
+    void prof_end(ProfSpan* p, cudaStream_t s) const {
+        if (!p) return;
+        cudaEventRecord(p->e1, s);
+        std::lock_guard<std::mutex> lk(mu);
+        prof_spans.push_back(p);
+    }
     // last device error (BVGraph.java:1129-1131 logs node + position)
     mutable std::mutex mu;
     mutable int32_t err_node = -1;
@@ -178,6 +202,7 @@ static void destroy(bvg_graph* g) {
     DeviceGuard dg(g->device);
     cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
     cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
+    for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
     delete g;
 }
@@ -210,10 +235,11 @@ static int32_t shard_halo(const bvg_graph* g, int32_t from) {
 
 extern "C" {
 
-int bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
-                    int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
-                    uint32_t flags, int offset_type, int device, bvg_graph** out) {
+int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                          int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                          uint32_t flags, int offset_type, int device, int32_t from, int32_t to, bvg_graph** out) {
     if (!out || nodes < 0 || (!graph && graph_bytes) || !offsets_stream) return BVG_EINVAL;
+    if (from < 0 || to < from || to > nodes) return BVG_EINVAL;
     int dev;
     int dl[1] = { device };
     int rc = pick_device(device >= 0 ? dl : nullptr, device >= 0 ? 1 : 0, &dev);
@@ -231,11 +257,44 @@ int bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
     rc = decode_offsets_stream(offsets_stream, offsets_bytes, oc, nodes, offs);
     if (rc) { destroy(g); return rc; }
     if (offs[(size_t)nodes] > graph_bytes * 8) { destroy(g); return BVG_EIO; }
-    g->node_lo = g->ext_from = 0; g->node_hi = g->ext_to = nodes;
-    g->bit_base = 0; g->bit_end = offs[(size_t)nodes]; g->graph_bits_total = g->bit_end;
-    rc = build_device_state(g, graph, graph_bytes, offs.data());
+    g->graph_bits_total = offs[(size_t)nodes];
+    g->ext_from = from; g->ext_to = to;
+    g->node_lo = shard_halo(g, from); g->node_hi = to;
+    const uint64_t byte_lo = (offs[(size_t)g->node_lo] >> 3) & ~(uint64_t)15;
+    const uint64_t byte_hi = std::min<uint64_t>(graph_bytes, (offs[(size_t)to] + 7) >> 3);
+    g->bit_base = byte_lo * 8; g->bit_end = offs[(size_t)to];
+    rc = build_device_state(g, graph + byte_lo, byte_hi - byte_lo, offs.data() + g->node_lo);
     if (rc) { destroy(g); return rc; }
     *out = g;
+    return BVG_OK;
+}
+
+int bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                    int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                    uint32_t flags, int offset_type, int device, bvg_graph** out) {
+    return bvg_open_memory_shard(graph, graph_bytes, offsets_stream, offsets_bytes, nodes, arcs, window, maxref, minlen, zetak,
+                                 flags, offset_type, device, 0, nodes, out);
+}
+
+int bvg_plan_shards(const char* basename, int nshards, int32_t* bounds) {
+    if (!basename || nshards < 1 || !bounds) return BVG_EINVAL;
+    Properties p;
+    int rc = load_properties(basename, p);
+    if (rc) return rc;
+    std::vector<uint8_t> ostream;
+    if (!slurp_file(std::string(basename) + ".offsets", ostream)) return BVG_EIO;
+    std::vector<uint64_t> offs;
+    const int oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
+    rc = decode_offsets_stream(ostream.data(), ostream.size(), oc, p.nodes, offs);
+    if (rc) return rc;
+    const uint64_t total = offs[(size_t)p.nodes];
+    bounds[0] = 0;
+    for (int i = 1; i < nshards; i++) {  // equal bits, cut at the nearest node boundary
+        const uint64_t target = total / (uint64_t)nshards * (uint64_t)i;
+        const size_t k = (size_t)(std::lower_bound(offs.begin(), offs.end(), target) - offs.begin());
+        bounds[i] = (int32_t)std::max<int64_t>(bounds[i - 1], std::min<int64_t>((int64_t)k, p.nodes));
+    }
+    bounds[nshards] = (int32_t)p.nodes;
     return BVG_OK;
 }
 
@@ -375,7 +434,7 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     Tmp<int32_t> halo(s);
     Tmp<int64_t> halo_off(s);
     if (g->max_depth > 0 && from > g->node_lo) {
-        if (g->d_halo_lists && from == g->ext_from) {  // lists imported from the previous shard
+        if (g->halo_count > 0 && from == g->ext_from) {  // lists imported from the previous shard
             rm.halo = g->d_halo_lists; rm.halo_off = g->d_halo_off; rm.halo_lo = from - g->halo_count;
         } else {  // re-decode the halo, as BVGraphNodeIterator's ctor re-reads the window (BVGraph.java:1173-1183)
             const int64_t reach = std::min<int64_t>((int64_t)to - from, (int64_t)g->window * g->max_depth);
@@ -399,11 +458,11 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
         }
     }
     const int64_t cnt = (int64_t)to - lo;
-    if (g->def_codec) LAUNCH(k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
-    else LAUNCH(k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
+    if (g->def_codec) LAUNCH_P(g, "k_extras", k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
+    else LAUNCH_P(g, "k_extras", k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
     for (int32_t level = 1; level <= g->max_depth; level++) {
-        if (g->def_codec) LAUNCH(k_merge<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
-        else LAUNCH(k_merge<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
+        if (g->def_codec) LAUNCH_P(g, "k_merge", k_merge<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
+        else LAUNCH_P(g, "k_merge", k_merge<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
     }
     CK(cudaGetLastError());
     return BVG_OK;
@@ -463,7 +522,7 @@ static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned l
     if (rc) return rc;
     const int64_t cnt = (int64_t)to - from;
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (cnt + 7) / 8));
-    LAUNCH(k_checksum, grid, 256, 0, s, rows.p, g->d_rowoff + (from - g->node_lo), from, cnt, d_result);
+    LAUNCH_P(g, "k_checksum", k_checksum, grid, 256, 0, s, rows.p, g->d_rowoff + (from - g->node_lo), from, cnt, d_result);
     CK(cudaGetLastError());
     return BVG_OK;
 }
@@ -568,8 +627,8 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
     if (!on_device) { CK(d_out.alloc((size_t)tot[0])); out_dev = d_out.p; }
     CK(scratch.alloc((size_t)tot[1]));
     if (nx) {
-        if (g->def_codec) LAUNCH(k_random<true>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
-        else LAUNCH(k_random<false>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
+        if (g->def_codec) LAUNCH_P(g, "k_random", k_random<true>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
+        else LAUNCH_P(g, "k_random", k_random<false>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
     }
     CK(cudaGetLastError());
     if (on_device) return BVG_OK;
@@ -698,18 +757,25 @@ int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32
     if (count > g->ext_from) return BVG_EINVAL;
     DeviceGuard dg(g->device);
     cudaStream_t s = g->stream;
-    cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
-    g->d_halo_lists = nullptr; g->d_halo_off = nullptr; g->halo_count = 0;
+    g->halo_count = 0;
     if (count == 0) return BVG_OK;
     int64_t total = 0;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (on_device) { CK(cudaMemcpyAsync(&total, off + count, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
     else total = off[count];
-    CK(cudaMalloc((void**)&g->d_halo_off, ((size_t)count + 1) * 8));
-    CK(cudaMalloc((void**)&g->d_halo_lists, std::max<size_t>((size_t)total, 1) * 4));
+    if (count + 1 > g->halo_off_cap) {
+        cudaFree(g->d_halo_off); g->d_halo_off = nullptr; g->halo_off_cap = 0;
+        CK(cudaMalloc((void**)&g->d_halo_off, ((size_t)count + 1) * 8));
+        g->halo_off_cap = count + 1;
+    }
+    if (total > g->halo_lists_cap) {
+        cudaFree(g->d_halo_lists); g->d_halo_lists = nullptr; g->halo_lists_cap = 0;
+        CK(cudaMalloc((void**)&g->d_halo_lists, (size_t)total * 2 * 4));
+        g->halo_lists_cap = total * 2;
+    }
     CK(cudaMemcpyAsync(g->d_halo_off, off, ((size_t)count + 1) * 8, kind, s));
     if (total) CK(cudaMemcpyAsync(g->d_halo_lists, lists, (size_t)total * 4, kind, s));
-    CK(cudaStreamSynchronize(s));
+    if (!on_device) CK(cudaStreamSynchronize(s));
     g->halo_count = count;
     return BVG_OK;
 }
@@ -742,5 +808,40 @@ int bvg_last_error_node(const bvg_graph* g, int32_t* node, int64_t* bitpos) {
 }
 
 int64_t bvg_kernel_launches(void) { return g_launches.load(); }
+
+int bvg_profile(const bvg_graph* g, int enable) {
+    if (!g) return BVG_EINVAL;
+    g->prof_on = enable != 0;
+    return BVG_OK;
+}
+
+int bvg_profile_read(const bvg_graph* g, char* buf, int cap) {
+    if (!g || !buf || cap < 2) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    std::vector<ProfSpan*> spans;
+    { std::lock_guard<std::mutex> lk(g->mu); spans.swap(g->prof_spans); }
+    std::map<std::string, std::pair<int64_t, double>> acc;
+    for (ProfSpan* p : spans) {
+        float ms = 0;
+        if (cudaEventSynchronize(p->e1) == cudaSuccess && cudaEventElapsedTime(&ms, p->e0, p->e1) == cudaSuccess) {
+            auto& a = acc[p->name];
+            a.first++; a.second += ms;
+        }
+        cudaEventDestroy(p->e0); cudaEventDestroy(p->e1);
+        delete p;
+    }
+    cudaGetLastError();
+    std::string out = "{";
+    for (auto& kv : acc) {
+        char tmp[256];
+        snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", out.size() > 1 ? ", " : "", kv.first.c_str(),
+                 (long long)kv.second.first, kv.second.second);
+        out += tmp;
+    }
+    out += "}";
+    if ((int)out.size() + 1 > cap) return BVG_ENOMEM;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return BVG_OK;
+}
 
 }  // extern "C"
