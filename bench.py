@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--nodes", type=int, default=32_000_000)
     ap.add_argument("--arcs", type=int, default=1_070_000_000)  # dedup shortfall ~6 %: lands on ~1.0e9 arcs
     ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--max-degree", type=int, default=1 << 22, help="experiments only: cap on the generator's outdegree law")
     ap.add_argument("--workdir", default=os.environ.get("BVG_BENCH_DIR", "/tmp/bvg_bench"))
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,13 +55,13 @@ def parse_args():
 def graph_files(args, rank, world, barrier):
     """Rank 0 generates + compresses the synthetic graph once per box (host tools, all cores); others wait."""
     from webgraph_b200 import tools
-    base = os.path.join(args.workdir, "pl_n%d_m%d_s%x" % (args.nodes, args.arcs, args.seed), "g")
+    base = os.path.join(args.workdir, "pl_n%d_m%d_s%x_d%d" % (args.nodes, args.arcs, args.seed, args.max_degree), "g")
     meta = base + ".meta.json"
     if rank == 0 and not os.path.exists(meta):
         os.makedirs(os.path.dirname(base), exist_ok=True)
         t = time.time()
         st = tools.generate_store(base, args.nodes, args.arcs, seed=args.seed, window=7, maxref=3, minlen=4, zetak=3,
-                                  threads=os.cpu_count() or 1)
+                                  threads=os.cpu_count() or 1, max_degree=args.max_degree)
         st["generate_seconds"] = time.time() - t
         with open(meta + ".tmp", "w") as f:
             json.dump(st, f)

@@ -51,6 +51,7 @@ typedef struct bvgt_gen_params {
     double   p_interval;   /* probability that a node carries runs of consecutive successors */
     double   p_local;      /* fraction of the remaining successors drawn near x instead of globally */
     int32_t  block;        /* nodes per generation block ("host"): prototypes never cross a block */
+    int32_t  max_degree;   /* cap on the outdegree law (default 2^22; experiments use smaller caps) */
 } bvgt_gen_params;
 
 void bvgt_gen_defaults(bvgt_gen_params* p, int32_t n, int64_t target_arcs, uint64_t seed);

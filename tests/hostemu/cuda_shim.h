@@ -1,0 +1,16 @@
+// cuda_shim.h -- lets the device-side decode logic (bvg_device.cuh) compile as plain host C++ for debugging under
+// ASan/UBSan (tests/test_device_logic_on_host.py).  Test infrastructure only; never part of the product build.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift) {
+    shift &= 31;
+    return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
+}
+static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+static inline int atomicCAS(int* p, int cmp, int val) { int old = *p; if (old == cmp) *p = val; return old; }

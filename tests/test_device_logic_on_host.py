@@ -1,0 +1,80 @@
+"""The device-side decode steps (bvg_device.cuh: decode_extras / merge_copied and the k_random chain walk) compiled for
+the HOST with ASan+UBSan (tests/hostemu) and compared with the truth.  A debugging net for out-of-bounds row writes and
+arithmetic slips that costs no GPU time; the real parity tests are tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import graphs
+from tests import oracle_binding as ob
+from tests.conftest import CNR, ROOT
+from webgraph_b200 import tools
+
+EMU_DIR = os.path.join(ROOT, "tests", "hostemu")
+EMU = os.path.join(EMU_DIR, "libemu.so")
+
+
+def _find_asan():
+    out = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    return out if os.path.isabs(out) and os.path.exists(out) else None
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"),
+            os.path.join(ROOT, "webgraph_b200", "csrc", "cuda", "bvg_device.cuh")]
+    if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
+        # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
+        subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
+                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0]])
+    lib = C.CDLL(EMU)
+    lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    return lib
+
+
+def run_emu(emu, oracle, base, random_mode):
+    g = oracle.load(base)
+    graph = np.fromfile(base + ".graph", dtype=np.uint8)
+    graph = np.concatenate([graph, np.zeros(8, dtype=np.uint8)])
+    offs = g.offsets()
+    c = g.g.contents
+    is_def = (c.outdegree_coding, c.block_coding, c.residual_coding, c.reference_coding, c.block_count_coding) == (2, 2, 6, 5, 2)
+    toff, tsucc = g.decode_range(0, g.n)
+    GUARD = 64
+    out = np.full(len(tsucc) + 2 * GUARD, -77, dtype=np.int32)
+    out_off = np.zeros(g.n + 1, dtype=np.int64)
+    rc = emu.emu_decode(graph.ctypes.data, len(graph) - 8, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak,
+                        c.outdegree_coding, c.block_coding, c.residual_coding, c.reference_coding, c.block_count_coding,
+                        1 if is_def else 0, out_off.ctypes.data, out[GUARD:].ctypes.data, len(tsucc), random_mode)
+    assert rc == 0
+    assert np.all(out[:GUARD] == -77) and np.all(out[GUARD + len(tsucc):] == -77), "row write out of bounds"
+    assert np.array_equal(out_off, toff)
+    assert np.array_equal(out[GUARD:GUARD + len(tsucc)], tsucc)
+
+
+@pytest.mark.parametrize("random_mode", [0, 1])
+def test_emulated_kernels_on_cnr2000(emu, oracle, random_mode):
+    run_emu(emu, oracle, CNR, random_mode)
+
+
+@pytest.mark.parametrize("n,p", [(10, .3), (100, .5), (100, .9)])
+def test_emulated_kernels_on_erdos_renyi(emu, oracle, tmp_path, n, p):
+    off, succ = graphs.erdos_renyi(n, p, seed=n * 7 + int(p * 10))
+    base = str(tmp_path / "er")
+    tools.store_csr(base, off, succ)
+    run_emu(emu, oracle, base, 0)
+    run_emu(emu, oracle, base, 1)
+
+
+@pytest.mark.parametrize("flags,k,w,r,ml", [(0, 3, 7, 3, 4), (0, 2, 1, 1, 0), (0, 5, 16, 10, 2),
+                                           (tools.OUTDEGREES_DELTA | tools.BLOCKS_DELTA | tools.RESIDUALS_DELTA | tools.REFERENCES_DELTA | tools.BLOCK_COUNT_DELTA, 3, 7, -1, 4),
+                                           (tools.RESIDUALS_GAMMA | tools.REFERENCES_GAMMA | tools.BLOCK_COUNT_UNARY | tools.BLOCKS_UNARY, 3, 3, 2, 3)])
+def test_emulated_kernels_on_copy_heavy(emu, oracle, tmp_path, flags, k, w, r, ml):
+    off, succ, _ = graphs.copy_heavy(1200, seed=33 + k)
+    base = str(tmp_path / "ch")
+    tools.store_csr(base, off, succ, flags=flags, zetak=k, window=w, maxref=r, minlen=ml)
+    run_emu(emu, oracle, base, 0)
+    run_emu(emu, oracle, base, 1)

@@ -13,7 +13,11 @@
 // [32i, 32i+32), MSB first), so a 64-bit window at any bit position is two funnel shifts over three words.
 #pragma once
 #include <cstdint>
+#ifdef BVG_HOST_EMULATION   // tests/hostemu: the same logic compiled for the host, for sanitizer runs
+#include "cuda_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace bvg {
 

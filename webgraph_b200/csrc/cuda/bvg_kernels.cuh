@@ -165,6 +165,19 @@ struct RowMap {
     __device__ __forceinline__ int32_t* row(const GraphDev& g, int32_t x) const {
         return x >= from ? out + (g.rowoff[x - g.node_lo] - out_base) : halo + halo_off[x - halo_lo];
     }
+    // A halo node is decoded only if its whole chain lies inside the halo: halo_lo is the smallest chain root of the
+    // requested range, so a halo node whose chain starts before it is nobody's ancestor (and its parent has no row).
+    __device__ __forceinline__ bool wanted(const GraphDev& g, int32_t x) const {
+        if (x >= from) return true;
+        int64_t y = (int64_t)x - g.node_lo;
+        for (;;) {
+            const int32_t r = g.ref[y];
+            if (r == 0) break;
+            if (r > y) return false;
+            y -= r;
+        }
+        return y + g.node_lo >= halo_lo;
+    }
 };
 
 // Level 0 for every node of [lo, hi): extras into the row tail; nodes without a reference are complete.
@@ -173,7 +186,8 @@ __global__ void k_extras(GraphDev g, int32_t lo, int32_t hi, RowMap rm) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)hi - lo) return;
     const int32_t x = lo + (int32_t)i;
-    if (g.outdeg[x - g.node_lo] == 0 || g.depth[x - g.node_lo] < 0) return;  // depth < 0: unneeded halo node
+    if (g.outdeg[x - g.node_lo] == 0 || g.depth[x - g.node_lo] < 0) return;  // depth < 0: chain leaves the shard
+    if (!rm.wanted(g, x)) return;
     decode_extras<DEF>(g, x, rm.row(g, x));
 }
 
@@ -183,7 +197,7 @@ __global__ void k_merge(GraphDev g, int32_t lo, int32_t hi, int32_t level, RowMa
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)hi - lo) return;
     const int32_t x = lo + (int32_t)i;
-    if (g.depth[x - g.node_lo] != level) return;
+    if (g.depth[x - g.node_lo] != level || !rm.wanted(g, x)) return;
     merge_copied<DEF>(g, x, rm.row(g, x), rm.row(g, x - g.ref[x - g.node_lo]));
 }
 

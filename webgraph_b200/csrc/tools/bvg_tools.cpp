@@ -397,7 +397,7 @@ struct Generator {
     }
     inline int32_t degree(int32_t x) const {
         const double d = std::floor(scale * weight(x));
-        const double cap = std::min<double>((double)p.n - 1.0, 1 << 22);
+        const double cap = std::min<double>((double)p.n - 1.0, (double)p.max_degree);
         return (int32_t)std::min(d, cap);
     }
     void calibrate(int threads) {
@@ -501,7 +501,7 @@ int bvgt_store_csr(const char* basename, int32_t n, const int64_t* off, const in
 
 void bvgt_gen_defaults(bvgt_gen_params* p, int32_t n, int64_t target_arcs, uint64_t seed) {
     p->n = n; p->target_arcs = target_arcs; p->seed = seed;
-    p->zipf_s = 0.65; p->p_copy = 0.5; p->p_interval = 0.1; p->p_local = 0.5; p->block = 1024;
+    p->zipf_s = 0.65; p->p_copy = 0.5; p->p_interval = 0.1; p->p_local = 0.5; p->block = 1024; p->max_degree = 1 << 22;
 }
 
 int bvgt_generate_store(const char* basename, const bvgt_gen_params* gp,
