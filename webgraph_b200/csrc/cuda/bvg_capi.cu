@@ -218,8 +218,20 @@ static int pick_device(const int* devices, int ndev, int* out) {
     return BVG_OK;
 }
 
+// Stream-ordered temporaries come from the device's default pool; keep freed blocks cached instead of returning them to
+// the driver at every synchronisation (a scan re-allocates the same scratch each call).
+static void keep_pool_warm(int dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+}
+
 static int open_common(bvg_graph* g, const Properties& p, int offset_type) {
     if (offset_type < -1 || offset_type > 2) return BVG_EINVAL;  // BVGraph.java:1545
+    keep_pool_warm(g->device);
     g->offset_type = offset_type;
     g->n_total = (int32_t)p.nodes; g->m_total = p.arcs; g->window = p.window; g->maxref = p.maxref;
     g->minlen = p.minlen; g->zetak = p.zetak; g->flags = p.flags;
