@@ -347,3 +347,20 @@ def test_extremes_large_ids_and_giant_lists(tmp_path):
     arcs, cs = g.scanRange(0, n)
     assert arcs == len(succ) and cs == ob.xor_checksum(off, succ)
     g.close()
+
+
+# ---- the C++ mirror of the reference interface (include/bvgraph_b200.hpp) ----
+
+def test_cpp_mirror(tmp_path):
+    import shutil
+    import subprocess
+    from webgraph_b200 import build
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "cpp_mirror_test")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(build.cuda_library())
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp_mirror_test.cpp"),
+                           "-L", libdir, "-lbvgraph_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe, CNR], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["3216152", "f941dd3471d172f1", "1", "-1", "1", "3216152", "f941dd3471d172f1"]
