@@ -59,6 +59,10 @@ struct bvg_graph {
     int64_t* d_rowoff = nullptr;
     ErrWord* d_err = nullptr;
     int32_t max_depth = 0, max_outdeg = 0;
+    // length-bucketed schedules (k_order_keys): extras order over all nodes with successors, merge order level-major
+    int32_t *d_order_e = nullptr, *d_order_m = nullptr;
+    int64_t order_e_count = 0;
+    std::vector<int64_t> level_start;  // merge schedule: nodes of chain level l+1 are order_m[level_start[l] .. level_start[l+1])
     // halo imported from the previous shard (bvg_halo_import)
     int32_t* d_halo_lists = nullptr;
     int64_t* d_halo_off = nullptr;
@@ -158,6 +162,48 @@ static int device_exclusive_scan(cudaStream_t s, const int32_t* d_in, int64_t n,
     return BVG_OK;
 }
 
+// Counting sort of the nodes into the two length-bucketed schedules (see bvg_kernels.cuh).  Chains deeper than
+// MAX_LEVEL_KEYS levels (only files written with an unbounded maxrefcount) keep the natural-order kernels.
+constexpr int32_t MAX_LEVEL_KEYS = 64;
+static int build_schedules(bvg_graph* g) {
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    g->level_start.clear();
+    if (nn == 0) return BVG_OK;
+    cudaStream_t s = g->stream;
+    const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
+    const int64_t nb_e = ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * ORDER_BUCKETS;
+    Tmp<int32_t> key_e(s), key_m(s), bins(s);
+    CK(key_e.alloc((size_t)nn));
+    CK(key_m.alloc((size_t)nn));
+    CK(bins.alloc((size_t)(nb_e + nb_m)));
+    CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
+    GraphDev gd = g->dev();
+    LAUNCH(k_order_keys, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels);
+    LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
+    LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e);
+    std::vector<int32_t> h((size_t)(nb_e + nb_m));
+    CK(cudaMemcpyAsync(h.data(), bins.p, h.size() * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int64_t run = 0;
+    for (int64_t i = 0; i < nb_e; i++) { const int32_t c = h[(size_t)i]; h[(size_t)i] = (int32_t)run; run += c; }
+    g->order_e_count = run;
+    run = 0;
+    g->level_start.assign((size_t)levels + 1, 0);
+    for (int64_t i = 0; i < nb_m; i++) {
+        if (i % ORDER_BUCKETS == 0 && i / ORDER_BUCKETS <= levels) g->level_start[(size_t)(i / ORDER_BUCKETS)] = run;
+        const int32_t c = h[(size_t)(nb_e + i)]; h[(size_t)(nb_e + i)] = (int32_t)run; run += c;
+    }
+    g->level_start[(size_t)levels] = run;
+    CK(cudaMemcpyAsync(bins.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMalloc((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4));
+    LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p, g->node_lo, g->d_order_e);
+    LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e, g->node_lo, g->d_order_m);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return BVG_OK;
+}
+
 // Uploads the stream bytes + offsets of nodes [node_lo, node_hi] and builds the decode index.
 static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbytes, const uint64_t* offsets) {
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
@@ -194,7 +240,7 @@ static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbyte
     g->max_outdeg = mx[1];
     const int e = fetch_error(g);
     if (e) return e;
-    return BVG_OK;
+    return build_schedules(g);
 }
 
 static void destroy(bvg_graph* g) {
@@ -202,6 +248,7 @@ static void destroy(bvg_graph* g) {
     DeviceGuard dg(g->device);
     cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
     cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
+    cudaFree(g->d_order_e); cudaFree(g->d_order_m);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
     delete g;
@@ -470,6 +517,20 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
         }
     }
     const int64_t cnt = (int64_t)to - lo;
+    // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
+    const bool ordered = g->d_order_e && g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
+    if (ordered) {
+        if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+        else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+        for (int32_t level = 1; level <= g->max_depth; level++) {
+            const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
+            if (c == 0) continue;
+            if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+            else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+        }
+        CK(cudaGetLastError());
+        return BVG_OK;
+    }
     if (g->def_codec) LAUNCH_P(g, "k_extras", k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
     else LAUNCH_P(g, "k_extras", k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
     for (int32_t level = 1; level <= g->max_depth; level++) {
