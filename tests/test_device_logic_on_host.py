@@ -24,14 +24,16 @@ def _find_asan():
 
 @pytest.fixture(scope="module")
 def emu():
-    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"),
-            os.path.join(ROOT, "webgraph_b200", "csrc", "cuda", "bvg_device.cuh")]
+    cuda_dir = os.path.join(ROOT, "webgraph_b200", "csrc", "cuda")
+    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"),
+            os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
         # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
-                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0]])
+                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1]])
     lib = C.CDLL(EMU)
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
     return lib
 
 
@@ -46,16 +48,17 @@ def run_emu(emu, oracle, base, random_mode):
     GUARD = 64
     out = np.full(len(tsucc) + 2 * GUARD, -77, dtype=np.int32)
     out_off = np.zeros(g.n + 1, dtype=np.int64)
-    rc = emu.emu_decode(graph.ctypes.data, len(graph) - 8, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak,
-                        c.outdegree_coding, c.block_coding, c.residual_coding, c.reference_coding, c.block_count_coding,
-                        1 if is_def else 0, out_off.ctypes.data, out[GUARD:].ctypes.data, len(tsucc), random_mode)
+    args = (graph.ctypes.data, len(graph) - 8, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak,
+            c.outdegree_coding, c.block_coding, c.residual_coding, c.reference_coding, c.block_count_coding,
+            1 if is_def else 0, out_off.ctypes.data, out[GUARD:].ctypes.data, len(tsucc))
+    rc = emu.emu_decode_long(*args) if random_mode == 2 else emu.emu_decode(*args, random_mode)
     assert rc == 0
     assert np.all(out[:GUARD] == -77) and np.all(out[GUARD + len(tsucc):] == -77), "row write out of bounds"
     assert np.array_equal(out_off, toff)
     assert np.array_equal(out[GUARD:GUARD + len(tsucc)], tsucc)
 
 
-@pytest.mark.parametrize("random_mode", [0, 1])
+@pytest.mark.parametrize("random_mode", [0, 1, 2])  # 2 = every record through the split (long-record) path
 def test_emulated_kernels_on_cnr2000(emu, oracle, random_mode):
     run_emu(emu, oracle, CNR, random_mode)
 
@@ -67,6 +70,7 @@ def test_emulated_kernels_on_erdos_renyi(emu, oracle, tmp_path, n, p):
     tools.store_csr(base, off, succ)
     run_emu(emu, oracle, base, 0)
     run_emu(emu, oracle, base, 1)
+    run_emu(emu, oracle, base, 2)
 
 
 @pytest.mark.parametrize("flags,k,w,r,ml", [(0, 3, 7, 3, 4), (0, 2, 1, 1, 0), (0, 5, 16, 10, 2),
@@ -78,3 +82,4 @@ def test_emulated_kernels_on_copy_heavy(emu, oracle, tmp_path, flags, k, w, r, m
     tools.store_csr(base, off, succ, flags=flags, zetak=k, window=w, maxref=r, minlen=ml)
     run_emu(emu, oracle, base, 0)
     run_emu(emu, oracle, base, 1)
+    run_emu(emu, oracle, base, 2)

@@ -6,6 +6,7 @@
 #include "../../../include/bvgraph_b200.h"
 #include "bvg_format.hpp"
 #include "bvg_kernels.cuh"
+#include "bvg_long.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -63,6 +64,22 @@ struct bvg_graph {
     int32_t *d_order_e = nullptr, *d_order_m = nullptr;
     int64_t order_e_count = 0;
     std::vector<int64_t> level_start;  // merge schedule: nodes of chain level l+1 are order_m[level_start[l] .. level_start[l+1])
+    // long records split across threads (bvg_long.cuh)
+    int32_t nlong = 0;
+    LongMeta* d_long_meta = nullptr;
+    int32_t *d_cb_cum = nullptr, *d_cb_ppos = nullptr, *d_iv_cum = nullptr, *d_iv_left = nullptr;
+    uint64_t* d_seg_pos = nullptr;
+    int64_t* d_seg_val = nullptr;
+    LongItem *d_items_resid = nullptr, *d_items_extras = nullptr, *d_items_merge = nullptr;
+    int64_t n_items_resid = 0, n_items_extras = 0;
+    std::vector<int64_t> merge_item_start;  // items of chain level l+1: d_items_merge[merge_item_start[l] .. [l+1])
+    int64_t long_tmp_entries = 0;
+    LongIndex long_index() const {
+        LongIndex li;
+        li.meta = d_long_meta; li.cb_cum = d_cb_cum; li.cb_ppos = d_cb_ppos; li.iv_cum = d_iv_cum; li.iv_left = d_iv_left;
+        li.seg_pos = d_seg_pos; li.seg_val = d_seg_val;
+        return li;
+    }
     // halo imported from the previous shard (bvg_halo_import)
     int32_t* d_halo_lists = nullptr;
     int64_t* d_halo_off = nullptr;
@@ -162,6 +179,81 @@ static int device_exclusive_scan(cudaStream_t s, const int32_t* d_in, int64_t n,
     return BVG_OK;
 }
 
+// Index of the long records (bvg_long.cuh): list them, walk each once for sizes, lay out the arrays, walk again to fill
+// them, and list the per-scan work items.
+static int build_long_index(bvg_graph* g) {
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    cudaStream_t s = g->stream;
+    g->nlong = 0;
+    if (nn == 0 || g->max_outdeg <= LONG_D || g->max_depth > 64) return BVG_OK;
+    GraphDev gd = g->dev();
+    Tmp<int32_t> flags(s), long_nodes(s);
+    Tmp<int64_t> pos(s);
+    CK(flags.alloc((size_t)nn));
+    CK(pos.alloc((size_t)nn + 1));
+    LAUNCH(k_long_flags, grid_for(nn, 256), 256, 0, s, gd, LONG_D, flags.p);
+    int rc = device_exclusive_scan(s, flags.p, nn, pos.p);
+    if (rc) return rc;
+    int64_t nl = 0;
+    CK(cudaMemcpyAsync(&nl, pos.p + nn, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (nl == 0) return BVG_OK;
+    CK(long_nodes.alloc((size_t)nl));
+    LAUNCH(k_long_compact, grid_for(nn, 256), 256, 0, s, flags.p, pos.p, nn, g->node_lo, long_nodes.p);
+    CK(cudaMalloc((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta)));
+    if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
+    else LAUNCH(k_long_count<false>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
+    std::vector<LongMeta> meta((size_t)nl);
+    CK(cudaMemcpyAsync(meta.data(), g->d_long_meta, (size_t)nl * sizeof(LongMeta), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int64_t cb = 0, iv = 0, seg = 0, tmp = 0;
+    std::vector<LongItem> it_r, it_x;
+    std::vector<std::vector<LongItem>> it_m((size_t)g->max_depth + 1);
+    for (int64_t l = 0; l < nl; l++) {
+        LongMeta& m = meta[(size_t)l];
+        m.cb_off = cb; cb += (int64_t)m.ncb + 1;
+        m.iv_off = iv; iv += (int64_t)m.ic + 1;
+        m.seg_off = seg;
+        const int32_t nseg = (m.rc + LONG_SEG - 1) / LONG_SEG;
+        seg += nseg;
+        m.tmp_off = tmp; tmp += 2 * (int64_t)m.d;
+        for (int32_t q = 0; q < nseg; q++) it_r.push_back(LongItem{ (int32_t)l, q });
+        if (m.ic > 0) for (int32_t q = 0; q * LONG_CHUNK < m.ilen + m.rc; q++) it_x.push_back(LongItem{ (int32_t)l, q });
+        if (m.copied > 0 && m.level >= 1) for (int32_t q = 0; q * LONG_CHUNK < m.d; q++) it_m[(size_t)m.level].push_back(LongItem{ (int32_t)l, q });
+    }
+    CK(cudaMemcpyAsync(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), cudaMemcpyHostToDevice, s));
+    CK(cudaMalloc((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_iv_cum, (size_t)std::max<int64_t>(iv, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_iv_left, (size_t)std::max<int64_t>(iv, 1) * 4));
+    CK(cudaMalloc((void**)&g->d_seg_pos, (size_t)std::max<int64_t>(seg, 1) * 8));
+    CK(cudaMalloc((void**)&g->d_seg_val, (size_t)std::max<int64_t>(seg, 1) * 8));
+    if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val);
+    else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val);
+    std::vector<LongItem> merged;
+    g->merge_item_start.assign((size_t)g->max_depth + 1, 0);
+    for (int32_t lv = 1; lv <= g->max_depth; lv++) {
+        g->merge_item_start[(size_t)lv - 1] = (int64_t)merged.size();
+        merged.insert(merged.end(), it_m[(size_t)lv].begin(), it_m[(size_t)lv].end());
+    }
+    g->merge_item_start[(size_t)g->max_depth] = (int64_t)merged.size();
+    auto upload = [&](const std::vector<LongItem>& v, LongItem** dst) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(LongItem));
+        if (e != cudaSuccess) return e;
+        return v.empty() ? cudaSuccess : cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(LongItem), cudaMemcpyHostToDevice, s);
+    };
+    CK(upload(it_r, &g->d_items_resid));
+    CK(upload(it_x, &g->d_items_extras));
+    CK(upload(merged, &g->d_items_merge));
+    g->n_items_resid = (int64_t)it_r.size();
+    g->n_items_extras = (int64_t)it_x.size();
+    g->long_tmp_entries = tmp;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    g->nlong = (int32_t)nl;
+    return BVG_OK;
+}
+
 // Counting sort of the nodes into the two length-bucketed schedules (see bvg_kernels.cuh).  Chains deeper than
 // MAX_LEVEL_KEYS levels (only files written with an unbounded maxrefcount) keep the natural-order kernels.
 constexpr int32_t MAX_LEVEL_KEYS = 64;
@@ -178,7 +270,7 @@ static int build_schedules(bvg_graph* g) {
     CK(bins.alloc((size_t)(nb_e + nb_m)));
     CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
     GraphDev gd = g->dev();
-    LAUNCH(k_order_keys, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels);
+    LAUNCH(k_order_keys, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e);
     std::vector<int32_t> h((size_t)(nb_e + nb_m));
@@ -201,7 +293,7 @@ static int build_schedules(bvg_graph* g) {
     LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e, g->node_lo, g->d_order_m);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
-    return BVG_OK;
+    return build_long_index(g);
 }
 
 // Uploads the stream bytes + offsets of nodes [node_lo, node_hi] and builds the decode index.
@@ -249,6 +341,8 @@ static void destroy(bvg_graph* g) {
     cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
     cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
     cudaFree(g->d_order_e); cudaFree(g->d_order_m);
+    cudaFree(g->d_long_meta); cudaFree(g->d_cb_cum); cudaFree(g->d_cb_ppos); cudaFree(g->d_iv_cum); cudaFree(g->d_iv_left);
+    cudaFree(g->d_seg_pos); cudaFree(g->d_seg_val); cudaFree(g->d_items_resid); cudaFree(g->d_items_extras); cudaFree(g->d_items_merge);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
     delete g;
@@ -522,11 +616,26 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     if (ordered) {
         if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
         else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+        Tmp<int32_t> long_tmp(s);
+        LongDst ld{ nullptr };
+        const LongIndex li = g->long_index();
+        if (g->nlong) {
+            CK(long_tmp.alloc((size_t)g->long_tmp_entries));
+            ld.tmp = long_tmp.p;
+            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
+            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
+            if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->d_items_extras, g->n_items_extras, lo, to, rm, ld);
+        }
         for (int32_t level = 1; level <= g->max_depth; level++) {
             const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
-            if (c == 0) continue;
-            if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
-            else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+            if (c > 0) {
+                if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+                else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+            }
+            if (g->nlong) {
+                const int64_t ma = g->merge_item_start[(size_t)level - 1], mc = g->merge_item_start[(size_t)level] - ma;
+                if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->d_items_merge + ma, mc, lo, to, rm, ld);
+            }
         }
         CK(cudaGetLastError());
         return BVG_OK;

@@ -389,6 +389,9 @@ __device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__
     };
     a = next_a();
     for (;;) {
+        // once the parent stream is exhausted the remaining extras already sit at their final positions (k == j),
+        // unless duplicates were dropped earlier (k < j), which only malformed files produce
+        if (a == BVG_INF && k == j) return;
         const int64_t bv = j < d ? (int64_t)row[j] : BVG_INF;
         if (a == BVG_INF && bv == BVG_INF) break;
         if (a < bv) { row[k++] = (int32_t)a; a = next_a(); }

@@ -86,13 +86,14 @@ __device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // 0..127, mono
 }
 
 // key_e: extras schedule (all nodes with successors); key_m: merge schedule (nodes with a reference), level-major.
-__global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* __restrict__ key_m, int32_t max_level_keys) {
+__global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* __restrict__ key_m, int32_t max_level_keys,
+                             int32_t long_d) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = (int64_t)g.node_hi - g.node_lo;
     if (i >= n) return;
     const int32_t d = g.outdeg[i], dep = g.depth[i];
     int32_t ke = -1, km = -1;
-    if (d > 0 && dep >= 0) {
+    if (d > 0 && d <= long_d && dep >= 0) {  // longer records are split across threads (bvg_long.cuh)
         ke = ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]);
         if (dep >= 1 && dep <= max_level_keys) {
             const int32_t dp = g.outdeg[i - g.ref[i]];
@@ -116,6 +117,18 @@ __global__ void k_key_scatter(const int32_t* __restrict__ keys, int64_t n, int32
     if (i >= n) return;
     const int32_t k = keys[i];
     if (k >= 0) order[atomicAdd(cursors + k, 1)] = node_lo + (int32_t)i;
+}
+
+__global__ void k_long_flags(GraphDev g, int32_t long_d, int32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)g.node_hi - g.node_lo) return;
+    flags[i] = (g.outdeg[i] > long_d && g.depth[i] >= 0) ? 1 : 0;
+}
+
+__global__ void k_long_compact(const int32_t* __restrict__ flags, const int64_t* __restrict__ pos, int64_t n, int32_t node_lo,
+                               int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = node_lo + (int32_t)i;
 }
 
 // Exclusive scan int32 -> int64, three phases, 2048 items per block.

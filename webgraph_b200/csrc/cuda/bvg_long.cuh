@@ -1,0 +1,294 @@
+// bvg_long.cuh -- long records, split across threads.
+//
+// One thread per record cannot work for the heavy tail of a power-law graph: the 858 018-successor node of the 1 B-arc
+// benchmark graph is ~10^6 dependent code reads on a single thread.  Codeword k+1 starts where codeword k ends, so a
+// record can only be entered at positions somebody has already walked to.  The reference has the same problem and
+// solves it the same way for whole records: it keeps an index of record starts (.offsets / Elias-Fano,
+// BVGraph.java:1594).  For records with more than LONG_D successors this file extends that idea inside the record:
+// at open, one thread walks the record once and leaves
+//   * its copy blocks as prefix sums (parent position and copied count at the start of every copy block),
+//   * its intervals as (left, cumulative length),
+//   * a sync point (bit position, running successor value) every LONG_SEG residuals.
+// Per scan the work is then data-parallel with bounded items:
+//   k_long_resid   one thread per residual segment  : zeta_k codes -> successor values            (BVGraph.java:939-972)
+//   k_long_extras  one thread per output chunk      : intervals U residuals by merge path          (:1103-1108, MergedIntIterator)
+//   k_long_merge   one thread per output chunk      : masked parent list U extras by merge path    (:1110-1126, MaskedIntIterator)
+// Files whose lists contain duplicated successors (never produced by BVGraph.store, BVGraph.java:2201) keep the
+// sequential kernels' -1 fill semantics only on the short path; the merge path assumes the three parts are disjoint.
+#pragma once
+#include "bvg_device.cuh"
+
+namespace bvg {
+
+#ifndef BVG_LONG_D        // overridable so that tests/hostemu can push every record through the split path
+#define BVG_LONG_D 2048
+#define BVG_LONG_SEG 512
+#define BVG_LONG_CHUNK 512
+#endif
+constexpr int32_t LONG_D = BVG_LONG_D;          // records with more successors than this take the split path
+constexpr int32_t LONG_SEG = BVG_LONG_SEG;      // residuals per sync point
+constexpr int32_t LONG_CHUNK = BVG_LONG_CHUNK;  // outputs per merge-path item
+
+struct LongMeta {
+    int32_t x, d, ref, copied;
+    int32_t ncb;          // copy blocks, including the implicit tail block of an even block count
+    int32_t ic, ilen;     // intervals and their total length
+    int32_t rc;           // residuals
+    int32_t level;        // reference-chain depth
+    int32_t pad_;
+    int64_t cb_off;       // cb_cum[cb_off .. +ncb] (ncb+1 entries), cb_ppos[cb_off - l .. ] (ncb entries): see LongIndex
+    int64_t iv_off;       // iv_cum[iv_off .. +ic] (ic+1 entries), iv_left (ic entries)
+    int64_t seg_off;      // seg_pos / seg_val, ceil(rc / LONG_SEG) entries
+    int64_t tmp_off;      // per-scan temp: residuals at [tmp_off, +rc), extras at [tmp_off + d, +d-copied)
+    uint64_t after_header;  // bit position (relative to word 0) right after outdegree + reference
+};
+
+struct LongIndex {
+    const LongMeta* __restrict__ meta;
+    const int32_t* __restrict__ cb_cum;    // copied count before copy block t (per node: ncb+1 entries, last = copied)
+    const int32_t* __restrict__ cb_ppos;   // parent position of copy block t   (allocated with the same stride as cb_cum)
+    const int32_t* __restrict__ iv_cum;    // interval elements before interval t (ic+1 entries, last = ilen)
+    const int32_t* __restrict__ iv_left;   // left extreme of interval t          (same stride as iv_cum)
+    const uint64_t* __restrict__ seg_pos;  // bit position of the first code of residual segment s
+    const int64_t* __restrict__ seg_val;   // successor value just before it (unused for s = 0)
+};
+
+// Largest t in [0, n) with cum[t] <= q, for a non-decreasing cum[0..n] with cum[0] = 0 <= q < cum[n].
+__device__ __forceinline__ int32_t upper_slot(const int32_t* __restrict__ cum, int32_t n, int32_t q) {
+    int32_t lo = 0, hi = n;  // invariant: cum[lo] <= q < cum[hi]
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (cum[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Open-time walk of one long record.  pass 0 counts (ncb, ic, ilen, copied, rc); pass 1 fills the arrays.
+// ---------------------------------------------------------------------------------------------------
+template <bool DEF>
+__device__ void long_walk(const GraphDev& g, LongMeta& m, int pass, int32_t* cb_cum, int32_t* cb_ppos,
+                          int32_t* iv_cum, int32_t* iv_left, uint64_t* seg_pos, int64_t* seg_val) {
+    const Codec& c = g.c;
+    const int32_t x = m.x;
+    BitBuf b = buffer_at(g, x);
+    const int64_t d = (int64_t)Rd<DEF>::outdeg(b, c);
+    int32_t r = 0;
+    if (c.window > 0) r = (int32_t)Rd<DEF>::ref(b, c);
+    m.d = (int32_t)d;
+    m.ref = r;
+    m.after_header = b.pos();
+    int64_t copied = 0;
+    int32_t ncb = 0;
+    if (r > 0) {
+        const int64_t bc = (int64_t)Rd<DEF>::bcount(b, c);
+        const int64_t dp = g.outdeg[x - r - g.node_lo];
+        int64_t p = 0;
+        for (int64_t i = 0; i < bc; i++) {
+            const int64_t blk = (int64_t)Rd<DEF>::block(b, c) + (i ? 1 : 0);
+            if (!(i & 1)) {
+                if (pass) { cb_cum[ncb] = (int32_t)copied; cb_ppos[ncb] = (int32_t)p; }
+                ncb++;
+                copied += blk;
+            }
+            p += blk;
+        }
+        if (!(bc & 1)) {  // implicit tail block (MaskedIntIterator: left = -1)
+            if (pass) { cb_cum[ncb] = (int32_t)copied; cb_ppos[ncb] = (int32_t)p; }
+            ncb++;
+            copied += dp - p;
+        }
+        if (pass) cb_cum[ncb] = (int32_t)copied;
+    }
+    m.copied = (int32_t)copied;
+    m.ncb = ncb;
+    int64_t extra = d - copied;
+    int64_t ic = 0, ilen = 0;
+    if (extra > 0 && c.minlen != 0) {
+        ic = (int64_t)b.gamma();
+        int64_t prev = 0;
+        for (int64_t i = 0; i < ic; i++) {
+            int64_t left;
+            if (i == 0) left = (int64_t)(int32_t)(nat2int(b.gamma()) + (int64_t)x);
+            else left = (int64_t)b.gamma() + prev + 1;
+            const int64_t len = (int64_t)b.gamma() + c.minlen;
+            if (pass) { iv_cum[i] = (int32_t)ilen; iv_left[i] = (int32_t)left; }
+            prev = left + len;
+            ilen += len;
+        }
+        if (pass) iv_cum[ic] = (int32_t)ilen;
+    }
+    m.ic = (int32_t)ic;
+    m.ilen = (int32_t)ilen;
+    const int64_t rc = extra - ilen;
+    m.rc = (int32_t)(rc > 0 ? rc : 0);
+    if (!pass || rc <= 0) return;
+    // residual sync points (the one sequential pass over this record's residuals, paid once at open)
+    int64_t v = 0;
+    for (int64_t i = 0; i < rc; i++) {
+        if (i % LONG_SEG == 0) { seg_pos[i / LONG_SEG] = b.pos(); seg_val[i / LONG_SEG] = v; }
+        if (i == 0) v = (int64_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));
+        else v += (int64_t)Rd<DEF>::resid(b, c) + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-scan items
+// ---------------------------------------------------------------------------------------------------
+
+// Residual segment s of long record m: LONG_SEG (or fewer) successors into dst[s * LONG_SEG ..].
+template <bool DEF>
+__device__ void long_resid_segment(const GraphDev& g, const LongMeta& m, const LongIndex& li, int32_t s, int32_t* __restrict__ dst) {
+    const int32_t first = s * LONG_SEG;
+    const int32_t cnt = min(LONG_SEG, m.rc - first);
+    BitBuf b;
+    b.w = g.words;
+    b.maxw = g.nwords - 3;
+    b.seek(li.seg_pos[m.seg_off + s]);
+    int64_t v = li.seg_val[m.seg_off + s];
+    dst += first;
+    for (int32_t i = 0; i < cnt; i++) {
+        if (first + i == 0) v = (int64_t)(int32_t)((int64_t)m.x + nat2int(Rd<DEF>::resid(b, g.c)));
+        else v += (int64_t)Rd<DEF>::resid(b, g.c) + 1;
+        dst[i] = (int32_t)v;
+    }
+}
+
+// Virtual interval sequence: element q of the concatenated intervals.
+struct IntervalSeq {
+    const int32_t* __restrict__ cum;
+    const int32_t* __restrict__ left;
+    int32_t n, len;
+    __device__ __forceinline__ int32_t at(int32_t q) const {
+        const int32_t t = upper_slot(cum, n, q);
+        return left[t] + (q - cum[t]);
+    }
+};
+
+// Virtual copied sequence: element q of the parent's list seen through the copy blocks.
+struct CopiedSeq {
+    const int32_t* __restrict__ cum;
+    const int32_t* __restrict__ ppos;
+    const int32_t* __restrict__ parent;
+    int32_t n, len;
+    __device__ __forceinline__ int32_t at(int32_t q) const {
+        const int32_t t = upper_slot(cum, n, q);
+        return parent[ppos[t] + (q - cum[t])];
+    }
+};
+
+// Merge path: how many of the first q0 outputs of merge(A, B) come from A (A, B ascending and disjoint).
+template <class A>
+__device__ __forceinline__ int32_t merge_path(const A& a, const int32_t* __restrict__ bv, int32_t blen, int32_t q0) {
+    int32_t lo = max(0, q0 - blen), hi = min(q0, a.len);
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (a.at(mid) < bv[q0 - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Outputs [q0, q0 + cnt) of merge(A, B) into out, A being a virtual block-structured sequence walked by (slot, offset).
+template <class A, class ValueOf>
+__device__ void merge_chunk(const A& a, ValueOf value_of, const int32_t* __restrict__ bv, int32_t blen,
+                            int32_t q0, int32_t cnt, int32_t* __restrict__ out) {
+    int32_t i = merge_path(a, bv, blen, q0), j = q0 - i;
+    int32_t t = 0, t_end = 0;  // current slot of A and the index where it ends
+    if (i < a.len) { t = upper_slot(a.cum, a.n, i); t_end = a.cum[t + 1]; }
+    for (int32_t k = 0; k < cnt; k++) {
+        const bool has_a = i < a.len, has_b = j < blen;
+        int32_t av = 0;
+        if (has_a) {
+            while (i >= t_end) { t++; t_end = a.cum[t + 1]; }  // skips empty slots
+            av = value_of(t, i - a.cum[t]);
+        }
+        if (has_a && (!has_b || av < bv[j])) { out[q0 + k] = av; i++; }
+        else { out[q0 + k] = bv[j]; j++; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Kernels.  Items are (long record, segment | chunk) pairs listed at open.
+// ---------------------------------------------------------------------------------------------------
+struct LongItem { int32_t l, part; };
+
+template <bool DEF>
+__global__ void k_long_count(GraphDev g, const int32_t* __restrict__ long_nodes, int32_t nlong, LongMeta* __restrict__ meta) {
+    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlong) return;
+    LongMeta m;
+    m.x = long_nodes[l];
+    m.level = g.depth[m.x - g.node_lo];
+    m.pad_ = 0;
+    long_walk<DEF>(g, m, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    m.cb_off = m.iv_off = m.seg_off = m.tmp_off = 0;
+    meta[l] = m;
+}
+
+template <bool DEF>
+__global__ void k_long_fill(GraphDev g, int32_t nlong, LongMeta* __restrict__ meta, int32_t* cb_cum, int32_t* cb_ppos,
+                            int32_t* iv_cum, int32_t* iv_left, uint64_t* seg_pos, int64_t* seg_val) {
+    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlong) return;
+    LongMeta m = meta[l];
+    long_walk<DEF>(g, m, 1, cb_cum + m.cb_off, cb_ppos + m.cb_off, iv_cum + m.iv_off, iv_left + m.iv_off,
+                   seg_pos + m.seg_off, seg_val + m.seg_off);
+}
+
+// Where the parts of a long record go during a scan: residuals straight to their final place when nothing has to be
+// merged with them, else to the temp.
+struct LongDst {
+    int32_t* tmp;
+    __device__ __forceinline__ int32_t* resid(const LongMeta& m, int32_t* row) const {
+        if (m.ic == 0) return m.copied == 0 ? row : tmp + m.tmp_off + m.d;
+        return tmp + m.tmp_off;
+    }
+    __device__ __forceinline__ int32_t* extras(const LongMeta& m, int32_t* row) const {
+        return m.copied == 0 ? row : tmp + m.tmp_off + m.d;
+    }
+};
+
+template <bool DEF, class RM>
+__global__ void k_long_resid(GraphDev g, LongIndex li, const LongItem* __restrict__ items, int64_t nitems,
+                             int32_t lo, int32_t hi, RM rm, LongDst dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    const LongItem it = items[i];
+    const LongMeta m = li.meta[it.l];
+    if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
+    long_resid_segment<DEF>(g, m, li, it.part, dst.resid(m, rm.row(g, m.x)));
+}
+
+template <class RM>
+__global__ void k_long_extras(GraphDev g, LongIndex li, const LongItem* __restrict__ items, int64_t nitems,
+                              int32_t lo, int32_t hi, RM rm, LongDst dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    const LongItem it = items[i];
+    const LongMeta m = li.meta[it.l];
+    if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
+    IntervalSeq a{ li.iv_cum + m.iv_off, li.iv_left + m.iv_off, m.ic, m.ilen };
+    const int32_t total = m.ilen + m.rc;
+    const int32_t q0 = it.part * LONG_CHUNK;
+    const int32_t* left = a.left;
+    merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
+                min(LONG_CHUNK, total - q0), dst.extras(m, rm.row(g, m.x)));
+}
+
+template <class RM>
+__global__ void k_long_merge(GraphDev g, LongIndex li, const LongItem* __restrict__ items, int64_t nitems,
+                             int32_t lo, int32_t hi, RM rm, LongDst dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    const LongItem it = items[i];
+    const LongMeta m = li.meta[it.l];
+    if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
+    const int32_t* parent = rm.row(g, m.x - m.ref);
+    CopiedSeq a{ li.cb_cum + m.cb_off, li.cb_ppos + m.cb_off, parent, m.ncb, m.copied };
+    const int32_t* ppos = a.ppos;
+    const int32_t q0 = it.part * LONG_CHUNK;
+    merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
+                m.d - m.copied, q0, min(LONG_CHUNK, m.d - q0), rm.row(g, m.x));
+}
+
+}  // namespace bvg
