@@ -64,6 +64,8 @@ struct bvg_graph {
     int32_t *d_order_e = nullptr, *d_order_m = nullptr;
     int64_t order_e_count = 0;
     std::vector<int64_t> level_start;  // merge schedule: nodes of chain level l+1 are order_m[level_start[l] .. level_start[l+1])
+    uint8_t* d_is_parent = nullptr;    // nodes some other node copies from (k_mark_parents)
+    int32_t* d_long_nodes = nullptr;   // ids of the long records
     // long records split across threads (bvg_long.cuh)
     int32_t nlong = 0;
     LongMeta* d_long_meta = nullptr;
@@ -187,7 +189,8 @@ static int build_long_index(bvg_graph* g) {
     g->nlong = 0;
     if (nn == 0 || g->max_outdeg <= LONG_D || g->max_depth > 64) return BVG_OK;
     GraphDev gd = g->dev();
-    Tmp<int32_t> flags(s), long_nodes(s);
+    Tmp<int32_t> flags(s);
+    struct { int32_t* p; } long_nodes{ nullptr };
     Tmp<int64_t> pos(s);
     CK(flags.alloc((size_t)nn));
     CK(pos.alloc((size_t)nn + 1));
@@ -198,7 +201,8 @@ static int build_long_index(bvg_graph* g) {
     CK(cudaMemcpyAsync(&nl, pos.p + nn, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (nl == 0) return BVG_OK;
-    CK(long_nodes.alloc((size_t)nl));
+    CK(cudaMalloc((void**)&g->d_long_nodes, (size_t)nl * 4));
+    long_nodes.p = g->d_long_nodes;
     LAUNCH(k_long_compact, grid_for(nn, 256), 256, 0, s, flags.p, pos.p, nn, g->node_lo, long_nodes.p);
     CK(cudaMalloc((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta)));
     if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
@@ -262,6 +266,9 @@ static int build_schedules(bvg_graph* g) {
     g->level_start.clear();
     if (nn == 0) return BVG_OK;
     cudaStream_t s = g->stream;
+    CK(cudaMalloc((void**)&g->d_is_parent, (size_t)nn));
+    CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
+    LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
     const int64_t nb_e = ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * ORDER_BUCKETS;
     Tmp<int32_t> key_e(s), key_m(s), bins(s);
@@ -340,7 +347,7 @@ static void destroy(bvg_graph* g) {
     DeviceGuard dg(g->device);
     cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
     cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
-    cudaFree(g->d_order_e); cudaFree(g->d_order_m);
+    cudaFree(g->d_order_e); cudaFree(g->d_order_m); cudaFree(g->d_is_parent); cudaFree(g->d_long_nodes);
     cudaFree(g->d_long_meta); cudaFree(g->d_cb_cum); cudaFree(g->d_cb_ppos); cudaFree(g->d_iv_cum); cudaFree(g->d_iv_left);
     cudaFree(g->d_seg_pos); cudaFree(g->d_seg_val); cudaFree(g->d_items_resid); cudaFree(g->d_items_extras); cudaFree(g->d_items_merge);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
@@ -576,16 +583,19 @@ int bvg_range_arcs(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs) 
     return BVG_OK;
 }
 
-// Enqueues the decode of [from, to) into d_out (device, >= arcs entries). All temporaries are stream-ordered.
-static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from) {
-    if (to == from) return BVG_OK;
+// Resolves where the parents before `from` come from (imported lists or a re-decoded halo) and fills the RowMap.
+struct HaloPlan {
+    Tmp<int32_t> halo;
+    Tmp<int64_t> halo_off;
+    int32_t lo;
+    explicit HaloPlan(cudaStream_t s) : halo(s), halo_off(s), lo(0) {}
+};
+
+static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from, RowMap& rm, HaloPlan& hp) {
     cudaStream_t s = g->stream;
     GraphDev gd = g->dev();
-    RowMap rm;
     rm.out = d_out; rm.out_base = row_from; rm.from = from; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = from;
-    int32_t lo = from;
-    Tmp<int32_t> halo(s);
-    Tmp<int64_t> halo_off(s);
+    hp.lo = from;
     if (g->max_depth > 0 && from > g->node_lo) {
         if (g->halo_count > 0 && from == g->ext_from) {  // lists imported from the previous shard
             rm.halo = g->d_halo_lists; rm.halo_off = g->d_halo_off; rm.halo_lo = from - g->halo_count;
@@ -602,14 +612,26 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
                 int64_t ra, rb;
                 int rc = fetch_rowoff(g, h, from, &ra, &rb);
                 if (rc) return rc;
-                CK(halo.alloc((size_t)(rb - ra)));
-                CK(halo_off.alloc((size_t)(from - h) + 1));
-                LAUNCH(k_rel_offsets, grid_for((int64_t)from - h + 1, 128), 128, 0, s, g->d_rowoff + (h - g->node_lo), (int64_t)from - h, halo_off.p);
-                rm.halo = halo.p; rm.halo_off = halo_off.p; rm.halo_lo = h;
-                lo = h;
+                CK(hp.halo.alloc((size_t)(rb - ra)));
+                CK(hp.halo_off.alloc((size_t)(from - h) + 1));
+                LAUNCH(k_rel_offsets, grid_for((int64_t)from - h + 1, 128), 128, 0, s, g->d_rowoff + (h - g->node_lo), (int64_t)from - h, hp.halo_off.p);
+                rm.halo = hp.halo.p; rm.halo_off = hp.halo_off.p; rm.halo_lo = h;
+                hp.lo = h;
             }
         }
     }
+    return BVG_OK;
+}
+
+// Enqueues the decode of [from, to) into d_out (device, >= arcs entries). All temporaries are stream-ordered.
+static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from) {
+    if (to == from) return BVG_OK;
+    cudaStream_t s = g->stream;
+    GraphDev gd = g->dev();
+    RowMap rm;
+    HaloPlan hp(s);
+    { const int rc = plan_halo(g, from, to, d_out, row_from, rm, hp); if (rc) return rc; }
+    const int32_t lo = hp.lo;
     const int64_t cnt = (int64_t)to - lo;
     // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
     const bool ordered = g->d_order_e && g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
@@ -683,6 +705,49 @@ int bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_
     return e ? e : BVG_OK;
 }
 
+// Fused consume-only scan over the length-bucketed schedules: parents' rows go to `rows` (addressed like the CSR of
+// [from, to)), everything else is folded in registers; long records are materialised by the split path and folded by
+// k_checksum_nodes.
+static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int32_t* rows, int64_t row_from, unsigned long long* d_result) {
+    cudaStream_t s = g->stream;
+    GraphDev gd = g->dev();
+    RowMap rm;
+    HaloPlan hp(s);
+    { const int rc = plan_halo(g, from, to, rows, row_from, rm, hp); if (rc) return rc; }
+    const int32_t lo = hp.lo;
+    const unsigned grid = 148 * 8;
+    if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
+    else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
+    Tmp<int32_t> long_tmp(s);
+    LongDst ld{ nullptr };
+    const LongIndex li = g->long_index();
+    if (g->nlong) {
+        CK(long_tmp.alloc((size_t)g->long_tmp_entries));
+        ld.tmp = long_tmp.p;
+        if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
+        else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
+        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->d_items_extras, g->n_items_extras, lo, to, rm, ld);
+    }
+    for (int32_t level = 1; level <= g->max_depth; level++) {
+        const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
+        if (c > 0) {
+            const unsigned gm = (unsigned)std::min<int64_t>(grid, (c + 127) / 128);
+            if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_order_m + a, c, lo, to, from, rm, g->d_is_parent, d_result);
+            else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_order_m + a, c, lo, to, from, rm, g->d_is_parent, d_result);
+        }
+        if (g->nlong) {
+            const int64_t ma = g->merge_item_start[(size_t)level - 1], mc = g->merge_item_start[(size_t)level] - ma;
+            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->d_items_merge + ma, mc, lo, to, rm, ld);
+        }
+    }
+    if (g->nlong) {
+        const unsigned gl = (unsigned)std::min<int64_t>(148 * 4, ((int64_t)g->nlong + 3) / 4);
+        LAUNCH_P(g, "k_checksum_nodes", k_checksum_nodes, gl, 128, 0, s, gd, g->d_long_nodes, (int64_t)g->nlong, from, to, rm, d_result);
+    }
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+
 // Scan = decode into a stream-ordered scratch + checksum kernel (general path); ranges are split so that the scratch
 // stays below 2^30 arcs.
 static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned long long* d_result) {
@@ -700,6 +765,8 @@ static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned l
     cudaStream_t s = g->stream;
     Tmp<int32_t> rows(s);
     CK(rows.alloc((size_t)arcs));
+    if (g->d_order_e && g->d_is_parent && g->max_depth <= MAX_LEVEL_KEYS && ((int64_t)to - from) * 4 >= (int64_t)g->node_hi - g->node_lo)
+        return enqueue_scan_fused(g, from, to, rows.p, ra, d_result);
     rc = enqueue_decode(g, from, to, rows.p, ra);
     if (rc) return rc;
     const int64_t cnt = (int64_t)to - from;

@@ -266,9 +266,15 @@ __device__ __forceinline__ BitBuf buffer_at(const GraphDev& g, int32_t x) {
 // Returns `copied` (how many successors come from the parent) or a negative error.
 // BVGraph.java:1044-1100; the union order is MergedIntIterator's (equal heads once, :70).
 // ---------------------------------------------------------------------------------------------------
-template <bool DEF>
-__device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restrict__ row) {
+// FOLD = true additionally XORs (x * K + y) of every emitted successor y into acc (the consume-only scan); `store`
+// = false then skips the row writes altogether (nodes nobody copies from need no materialised list).
+#define BVG_MIX 0x9E3779B97F4A7C15ull
+template <bool DEF, bool FOLD = false>
+__device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restrict__ row, bool store = true,
+                                 unsigned long long* acc = nullptr) {
     const Codec& c = g.c;
+    const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
+    unsigned long long fold = 0;
     BitBuf b = buffer_at(g, x);
     const uint64_t limit = g.bit_end - g.bit_base;
     const uint64_t d64 = Rd<DEF>::outdeg(b, c);
@@ -333,9 +339,14 @@ __device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restri
         const int64_t iv = irem > 0 ? icur : BVG_INF;
         const int64_t rv = rc > 0 ? rnext : BVG_INF;
         if (iv == BVG_INF && rv == BVG_INF) break;
-        if (iv < rv) { row[k++] = (int32_t)iv; icur++; irem--; }
-        else {
-            row[k++] = (int32_t)rv;
+        if (iv < rv) {
+            if (store) row[k] = (int32_t)iv;
+            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)iv;
+            k++; icur++; irem--;
+        } else {
+            if (store) row[k] = (int32_t)rv;
+            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)rv;
+            k++;
             if (iv == rv) { icur++; irem--; }
             if (--rc > 0) {
                 rnext += (int64_t)Rd<DEF>::resid(b, c) + 1;  // :966
@@ -344,7 +355,12 @@ __device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restri
         }
     }
     if (b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-    while (k < total_out) row[k++] = -1;  // only reachable for files with duplicated successors (:1210 drains -1)
+    while (k < total_out) {  // only reachable for files with duplicated successors (:1210 drains -1)
+        if (store) row[k] = -1;
+        if (FOLD) fold ^= fold_base + 0xffffffffull;
+        k++;
+    }
+    if (FOLD) *acc ^= fold;
     return copied;
 }
 
@@ -353,9 +369,12 @@ __device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restri
 // in place, with the extras sitting at row[copied .. d).  Output position never overtakes the unread tail because
 // at most `copied` elements come from the parent.
 // ---------------------------------------------------------------------------------------------------
-template <bool DEF>
-__device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__ row, const int32_t* __restrict__ parent) {
+template <bool DEF, bool FOLD = false>
+__device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__ row, const int32_t* __restrict__ parent,
+                             bool store = true, unsigned long long* acc = nullptr) {
     const Codec& c = g.c;
+    const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
+    unsigned long long fold = 0;
     BitBuf b = buffer_at(g, x);
     const int64_t d = (int64_t)Rd<DEF>::outdeg(b, c);
     const int32_t r = (int32_t)Rd<DEF>::ref(b, c);
@@ -388,16 +407,27 @@ __device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__
         }
     };
     a = next_a();
+    if (FOLD && !store) {  // nobody copies from x: the copied successors are only consumed, never merged
+        while (a != BVG_INF) { fold ^= fold_base + (unsigned long long)(uint32_t)a; a = next_a(); }
+        *acc ^= fold;
+        return;
+    }
     for (;;) {
         // once the parent stream is exhausted the remaining extras already sit at their final positions (k == j),
         // unless duplicates were dropped earlier (k < j), which only malformed files produce
-        if (a == BVG_INF && k == j) return;
+        if (a == BVG_INF && k == j) break;
         const int64_t bv = j < d ? (int64_t)row[j] : BVG_INF;
-        if (a == BVG_INF && bv == BVG_INF) break;
-        if (a < bv) { row[k++] = (int32_t)a; a = next_a(); }
-        else { row[k++] = (int32_t)bv; j++; if (a == bv) a = next_a(); }
+        if (a == BVG_INF && bv == BVG_INF) { while (k < d) row[k++] = -1; break; }
+        if (a < bv) {
+            row[k++] = (int32_t)a;
+            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)a;
+            a = next_a();
+        } else {
+            row[k++] = (int32_t)bv; j++;
+            if (a == bv) a = next_a();  // equal heads are emitted once (MergedIntIterator.java:70)
+        }
     }
-    while (k < d) row[k++] = -1;
+    if (FOLD) *acc ^= fold;
 }
 
 }  // namespace bvg

@@ -327,6 +327,97 @@ __global__ void k_checksum(const int32_t* __restrict__ rows, const int64_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Consume-only scan, fused: successors are folded into (arcs, XOR checksum) as they are decoded.  Only lists somebody
+// copies from (is_parent) are materialised, in a scratch addressed like the CSR; every other node's successors -- its
+// extras and the elements it copies through its block list -- are consumed straight out of registers.
+// Persistent grid-stride kernels over the length-bucketed schedules; one atomic pair per block.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_mark_parents(GraphDev g, uint8_t* __restrict__ is_parent) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)g.node_hi - g.node_lo) return;
+    const int32_t r = g.ref[i];
+    if (r > 0 && r <= i) is_parent[i - r] = 1;
+}
+
+__device__ __forceinline__ void block_fold(unsigned long long acc, long long arcs, unsigned long long* __restrict__ result) {
+    __shared__ unsigned long long s_x[32];
+    __shared__ long long s_a[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+        arcs += __shfl_xor_sync(0xffffffffu, arcs, o);
+    }
+    if (lane == 0) { s_x[wid] = acc; s_a[wid] = arcs; }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long v = lane < nw ? s_x[lane] : 0;
+        long long a = lane < nw ? s_a[lane] : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            v ^= __shfl_xor_sync(0xffffffffu, v, o);
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+        }
+        if (lane == 0) {
+            if (v) atomicXor(result + 1, v);
+            if (a) atomicAdd(result, (unsigned long long)a);
+        }
+    }
+}
+
+template <bool DEF>
+__global__ void k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
+                              RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t x = order[i];
+        if (x < lo || x >= hi || !rm.wanted(g, x)) continue;
+        const bool store = is_parent[x - g.node_lo] != 0;
+        if (x >= from) {
+            decode_extras<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, store, &acc);
+            arcs += g.outdeg[x - g.node_lo];
+        } else if (store) {
+            decode_extras<DEF, false>(g, x, rm.row(g, x));  // halo: a parent of the range, not part of it
+        }
+    }
+    block_fold(acc, arcs, result);
+}
+
+template <bool DEF>
+__global__ void k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
+                             RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t x = order[i];
+        if (x < lo || x >= hi || !rm.wanted(g, x)) continue;
+        const bool store = is_parent[x - g.node_lo] != 0;
+        const int32_t* parent = rm.row(g, x - g.ref[x - g.node_lo]);
+        if (x >= from) merge_copied<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, parent, store, &acc);
+        else if (store) merge_copied<DEF, false>(g, x, rm.row(g, x), parent);
+    }
+    block_fold(acc, 0, result);
+}
+
+// Rows of listed nodes (the long records, always materialised) folded by one warp per node.
+__global__ void k_checksum_nodes(GraphDev g, const int32_t* __restrict__ nodes, int64_t count, int32_t lo, int32_t hi,
+                                 RowMap rm, unsigned long long* __restrict__ result) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    for (int64_t i = (int64_t)blockIdx.x * nw + wid; i < count; i += (int64_t)gridDim.x * nw) {
+        const int32_t x = nodes[i];
+        if (x < lo || x >= hi) continue;
+        const int32_t d = g.outdeg[x - g.node_lo];
+        const int32_t* row = rm.row(g, x);
+        const unsigned long long base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        for (int32_t p = lane; p < d; p += 32) acc ^= base + (unsigned long long)(uint32_t)row[p];
+        if (lane == 0) arcs += d;
+    }
+    block_fold(acc, arcs, result);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Random access (general path): one thread per query decodes the query's whole reference chain, root first
 // (the reference recurses lazily down the chain instead, BVGraph.java:1110-1121).
 // ---------------------------------------------------------------------------------------------------
