@@ -12,6 +12,7 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift)
     shift &= 31;
     return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
 }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 static inline int atomicCAS(int* p, int cmp, int val) { int old = *p; if (old == cmp) *p = val; return old; }
 // kernels in the included headers are compiled but never called on the host: give their index variables a meaning

@@ -65,6 +65,8 @@ struct bvg_graph {
     int64_t order_e_count = 0;
     std::vector<int64_t> level_start;  // merge schedule: nodes of chain level l+1 are order_m[level_start[l] .. level_start[l+1])
     uint8_t* d_is_parent = nullptr;    // nodes some other node copies from (k_mark_parents)
+    int32_t* d_copied = nullptr;       // successors each node copies from its parent (k_order_keys)
+    bool copied_ready = false;
     int32_t* d_long_nodes = nullptr;   // ids of the long records
     // long records split across threads (bvg_long.cuh)
     int32_t nlong = 0;
@@ -113,6 +115,7 @@ struct bvg_graph {
         g.words = d_words; g.nwords = nwords; g.bit_base = bit_base; g.bit_end = bit_end;
         g.offsets = d_offsets; g.node_lo = node_lo; g.node_hi = node_hi; g.c = codec;
         g.outdeg = d_outdeg; g.ref = d_ref; g.depth = d_depth; g.rowoff = d_rowoff; g.err = d_err;
+        g.copied = copied_ready ? d_copied : nullptr;
         return g;
     }
 };
@@ -277,7 +280,9 @@ static int build_schedules(bvg_graph* g) {
     CK(bins.alloc((size_t)(nb_e + nb_m)));
     CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
     GraphDev gd = g->dev();
-    LAUNCH(k_order_keys, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D);
+    CK(cudaMalloc((void**)&g->d_copied, (size_t)nn * 4));
+    if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
+    else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e);
     std::vector<int32_t> h((size_t)(nb_e + nb_m));
@@ -300,6 +305,7 @@ static int build_schedules(bvg_graph* g) {
     LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e, g->node_lo, g->d_order_m);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
+    g->copied_ready = true;
     return build_long_index(g);
 }
 
@@ -347,7 +353,7 @@ static void destroy(bvg_graph* g) {
     DeviceGuard dg(g->device);
     cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
     cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
-    cudaFree(g->d_order_e); cudaFree(g->d_order_m); cudaFree(g->d_is_parent); cudaFree(g->d_long_nodes);
+    cudaFree(g->d_order_e); cudaFree(g->d_order_m); cudaFree(g->d_is_parent); cudaFree(g->d_long_nodes); cudaFree(g->d_copied);
     cudaFree(g->d_long_meta); cudaFree(g->d_cb_cum); cudaFree(g->d_cb_ppos); cudaFree(g->d_iv_cum); cudaFree(g->d_iv_left);
     cudaFree(g->d_seg_pos); cudaFree(g->d_seg_val); cudaFree(g->d_items_resid); cudaFree(g->d_items_extras); cudaFree(g->d_items_merge);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }

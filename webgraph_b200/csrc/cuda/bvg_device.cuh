@@ -52,6 +52,7 @@ struct GraphDev {
     const int32_t* __restrict__ ref;      // [x - node_lo]  0 = no reference
     const int32_t* __restrict__ depth;    // [x - node_lo]  reference-chain depth, -1 = chain leaves the loaded window
     const int64_t* __restrict__ rowoff;   // [x - node_lo]  cumulative outdegree, node_hi - node_lo + 1 entries
+    const int32_t* __restrict__ copied;   // [x - node_lo]  successors copied from the parent (k_order_keys); may be null
     ErrWord* err;
 };
 
@@ -200,6 +201,23 @@ struct BitBuf {
         return slow([](Bits& t) { return t.gamma(); });
     }
     __device__ __forceinline__ uint64_t delta() { return slow([](Bits& t) { return t.delta(); }); }
+    // zeta_k gap that fits 32 bits of code (k = 3: gaps < 2^24): all-32-bit arithmetic on the top half of the buffer.
+    // Returns false (nothing consumed) when the code is longer; the caller then takes zeta().
+    __device__ __forceinline__ bool zeta32(int k, uint32_t& out) {
+        const uint32_t hi = (uint32_t)(buf >> 32);  // avail > 32 always holds
+        const int h = __clz((int)hi);
+        const int nb = h * k + k - 1;
+        if (h + nb + 2 > 32) return false;
+        const uint32_t left = 1u << (h * k);
+        const uint32_t t = hi << (h + 1);
+        uint32_t m = nb ? t >> (32 - nb) : 0;
+        int len = h + 1 + nb;
+        if (m < left) m += left;
+        else { m = (m << 1) | ((t >> (31 - nb)) & 1u); len++; }
+        consume(len);
+        out = m - 1;
+        return true;
+    }
     __device__ __forceinline__ uint64_t zeta(int k) {
         const uint64_t v = buf;
         const int h = __clzll((long long)v);
@@ -241,6 +259,11 @@ struct Rd {
     template <class B> static __device__ __forceinline__ uint64_t bcount(B& b, const Codec& c) { return DEF ? b.gamma() : b.coded(c.bcount, 0); }
     template <class B> static __device__ __forceinline__ uint64_t block(B& b, const Codec& c)  { return DEF ? b.gamma() : b.coded(c.block, 0); }
     template <class B> static __device__ __forceinline__ uint64_t resid(B& b, const Codec& c)  { return DEF ? b.zeta(c.zetak) : b.coded(c.resid, c.zetak); }
+    // gap between consecutive residuals (fits 32 bits in any valid file: successors are int32)
+    static __device__ __forceinline__ uint32_t gap(BitBuf& b, const Codec& c) {
+        if (DEF) { uint32_t v; if (b.zeta32(c.zetak, v)) return v; }
+        return (uint32_t)resid(b, c);
+    }
 };
 
 __device__ __forceinline__ Bits cursor_at(const GraphDev& g, int32_t x) {
@@ -321,6 +344,20 @@ __device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restri
         extra -= tot;
     }
     const int64_t total_out = d - copied;
+    if (ic == 0) {  // the common case: residuals only -- a tight loop in 32-bit arithmetic (ResidualIntIterator, :939-972)
+        uint32_t v = (uint32_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));  // :954
+        const int32_t n = (int32_t)extra;
+        if (store) row[0] = (int32_t)v;
+        if (FOLD) fold ^= fold_base + (unsigned long long)v;
+        for (int32_t i = 1; i < n; i++) {
+            v += Rd<DEF>::gap(b, c) + 1u;  // :966
+            if (store) row[i] = (int32_t)v;
+            if (FOLD) fold ^= fold_base + (unsigned long long)v;
+        }
+        if (b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
+        if (FOLD) *acc ^= fold;
+        return copied;
+    }
     int64_t rc = extra;  // residual count
     // cursors: ib walks intervals, b walks residuals
     int64_t icur = 0, irem = 0, iprev = 0, ileft = ic;
@@ -380,9 +417,10 @@ __device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__
     const int32_t r = (int32_t)Rd<DEF>::ref(b, c);
     const int64_t bc = (int64_t)Rd<DEF>::bcount(b, c);
     const int64_t dp = g.outdeg[x - r - g.node_lo];
-    // first walk: copied count (same arithmetic as step 1)
+    // copied count: from the index when it has one, else a first walk over the blocks (same arithmetic as step 1)
     int64_t copied = 0, total = 0;
-    {
+    if (g.copied) copied = g.copied[x - g.node_lo];
+    else {
         BitBuf t = b;
         for (int64_t i = 0; i < bc; i++) {
             const int64_t blk = (int64_t)Rd<DEF>::block(t, c) + (i ? 1 : 0);

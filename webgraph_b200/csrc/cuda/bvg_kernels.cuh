@@ -86,22 +86,42 @@ __device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // 0..127, mono
 }
 
 // key_e: extras schedule (all nodes with successors); key_m: merge schedule (nodes with a reference), level-major.
+// The merge work of a node is its block list (walked twice) plus the elements it copies, plus -- when its own list has
+// to be materialised because somebody copies from it -- the extras it merges them with; the block list is parsed
+// here once to learn that, and the copied count is kept for the merge step.
+template <bool DEF>
 __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* __restrict__ key_m, int32_t max_level_keys,
-                             int32_t long_d) {
+                             int32_t long_d, const uint8_t* __restrict__ is_parent, int32_t* __restrict__ copied_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = (int64_t)g.node_hi - g.node_lo;
     if (i >= n) return;
     const int32_t d = g.outdeg[i], dep = g.depth[i];
-    int32_t ke = -1, km = -1;
-    if (d > 0 && d <= long_d && dep >= 0) {  // longer records are split across threads (bvg_long.cuh)
-        ke = ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]);
-        if (dep >= 1 && dep <= max_level_keys) {
-            const int32_t dp = g.outdeg[i - g.ref[i]];
-            km = (dep - 1) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket((uint64_t)d + (uint64_t)dp));
+    int32_t ke = -1, km = -1, copied = 0;
+    if (d > 0 && dep >= 1) {
+        const int32_t x = g.node_lo + (int32_t)i;
+        BitBuf b = buffer_at(g, x);
+        (void)Rd<DEF>::outdeg(b, g.c);
+        const int32_t r = (int32_t)Rd<DEF>::ref(b, g.c);
+        const int64_t bc = (int64_t)Rd<DEF>::bcount(b, g.c);
+        const uint64_t limit = g.bit_end - g.bit_base;
+        int64_t total = 0, cp = 0;
+        for (int64_t k = 0; k < bc && b.pos() <= limit; k++) {
+            const int64_t blk = (int64_t)Rd<DEF>::block(b, g.c) + (k ? 1 : 0);
+            total += blk;
+            if (!(k & 1)) cp += blk;
+        }
+        if (!(bc & 1)) cp += (int64_t)g.outdeg[i - r] - total;
+        copied = (int32_t)(cp < 0 ? 0 : (cp > d ? d : cp));  // malformed records are reported by the decode step
+        if (d <= long_d && dep <= max_level_keys) {
+            const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (is_parent[i] ? (uint64_t)(d - copied) : 0);
+            km = (dep - 1) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
         }
     }
+    if (d > 0 && d <= long_d && dep >= 0)  // longer records are split across threads (bvg_long.cuh)
+        ke = ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]);
     key_e[i] = ke;
     key_m[i] = km;
+    copied_out[i] = copied;
 }
 
 __global__ void k_key_hist(const int32_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins) {
