@@ -390,16 +390,22 @@ __global__ void k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int
                               RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
     long long arcs = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t x = order[i];
-        if (x < lo || x >= hi || !rm.wanted(g, x)) continue;
-        const bool store = is_parent[x - g.node_lo] != 0;
-        if (x >= from) {
-            decode_extras<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, store, &acc);
-            arcs += g.outdeg[x - g.node_lo];
-        } else if (store) {
-            decode_extras<DEF, false>(g, x, rm.row(g, x));  // halo: a parent of the range, not part of it
+    // warp-uniform trip count and an explicit reconvergence point per item: without it lanes that finish early run
+    // ahead into their next item and the warp never executes the decode loop in lockstep again
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
+        const int64_t i = base + (threadIdx.x & 31);
+        const int32_t x = i < count ? order[i] : -1;
+        if (x >= lo && x < hi && rm.wanted(g, x)) {
+            const bool store = is_parent[x - g.node_lo] != 0;
+            if (x >= from) {
+                decode_extras<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, store, &acc);
+                arcs += g.outdeg[x - g.node_lo];
+            } else if (store) {
+                decode_extras<DEF, false>(g, x, rm.row(g, x));  // halo: a parent of the range, not part of it
+            }
         }
+        __syncwarp();
     }
     block_fold(acc, arcs, result);
 }
@@ -408,13 +414,17 @@ template <bool DEF>
 __global__ void k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
                              RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t x = order[i];
-        if (x < lo || x >= hi || !rm.wanted(g, x)) continue;
-        const bool store = is_parent[x - g.node_lo] != 0;
-        const int32_t* parent = rm.row(g, x - g.ref[x - g.node_lo]);
-        if (x >= from) merge_copied<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, parent, store, &acc);
-        else if (store) merge_copied<DEF, false>(g, x, rm.row(g, x), parent);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
+        const int64_t i = base + (threadIdx.x & 31);
+        const int32_t x = i < count ? order[i] : -1;
+        if (x >= lo && x < hi && rm.wanted(g, x)) {
+            const bool store = is_parent[x - g.node_lo] != 0;
+            const int32_t* parent = rm.row(g, x - g.ref[x - g.node_lo]);
+            if (x >= from) merge_copied<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, parent, store, &acc);
+            else if (store) merge_copied<DEF, false>(g, x, rm.row(g, x), parent);
+        }
+        __syncwarp();
     }
     block_fold(acc, 0, result);
 }
