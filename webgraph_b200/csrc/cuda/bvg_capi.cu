@@ -273,7 +273,8 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
     LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
-    const int64_t nb_e = ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * ORDER_BUCKETS;
+    const int64_t per_level = 2 * ORDER_BUCKETS;  // (parent | not) x half-octave bucket
+    const int64_t nb_e = 2 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
     Tmp<int32_t> key_e(s), key_m(s), bins(s);
     CK(key_e.alloc((size_t)nn));
     CK(key_m.alloc((size_t)nn));
@@ -294,7 +295,7 @@ static int build_schedules(bvg_graph* g) {
     run = 0;
     g->level_start.assign((size_t)levels + 1, 0);
     for (int64_t i = 0; i < nb_m; i++) {
-        if (i % ORDER_BUCKETS == 0 && i / ORDER_BUCKETS <= levels) g->level_start[(size_t)(i / ORDER_BUCKETS)] = run;
+        if (i % per_level == 0 && i / per_level <= levels) g->level_start[(size_t)(i / per_level)] = run;
         const int32_t c = h[(size_t)(nb_e + i)]; h[(size_t)(nb_e + i)] = (int32_t)run; run += c;
     }
     g->level_start[(size_t)levels] = run;

@@ -286,185 +286,259 @@ __device__ __forceinline__ BitBuf buffer_at(const GraphDev& g, int32_t x) {
 
 // ---------------------------------------------------------------------------------------------------
 // Step 1: outdegree, reference, copy-block totals, then intervals U residuals merged into row[copied .. d).
-// Returns `copied` (how many successors come from the parent) or a negative error.
 // BVGraph.java:1044-1100; the union order is MergedIntIterator's (equal heads once, :70).
+//
+// The walk is split into three phases with a single exit each so that a kernel can put a __syncwarp() between them:
+// with early returns inside divergent branches the compiler's reconvergence point moves to the end of the function and
+// the lanes of a warp, once apart, walk their residual loops one after the other instead of in lockstep.
+//   header()          outdegree, reference, block list (copied count), interval section located, counts
+//   residuals_only()  records without intervals: a tight loop in 32-bit arithmetic
+//   with_intervals()  records with intervals: intervals and residuals merged on the fly from two bit cursors
 // ---------------------------------------------------------------------------------------------------
-// FOLD = true additionally XORs (x * K + y) of every emitted successor y into acc (the consume-only scan); `store`
-// = false then skips the row writes altogether (nodes nobody copies from need no materialised list).
 #define BVG_MIX 0x9E3779B97F4A7C15ull
-template <bool DEF, bool FOLD = false>
-__device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restrict__ row, bool store = true,
-                                 unsigned long long* acc = nullptr) {
-    const Codec& c = g.c;
-    const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
-    unsigned long long fold = 0;
-    BitBuf b = buffer_at(g, x);
-    const uint64_t limit = g.bit_end - g.bit_base;
-    const uint64_t d64 = Rd<DEF>::outdeg(b, c);
-    if (d64 > 0x7fffffffull || b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-    const int64_t d = (int64_t)d64;
-    if (d == 0) return 0;
-    int64_t copied = 0;
-    if (c.window > 0) {
-        const uint64_t r = Rd<DEF>::ref(b, c);
-        if (r > (uint64_t)c.window) { report(g.err, E_STATE, x, b.pos() + g.bit_base); return E_STATE; }  // :705
-        if (r > 0) {
-            if ((int64_t)r > (int64_t)x - g.node_lo) { report(g.err, E_FORMAT, x, b.pos() + g.bit_base); return E_FORMAT; }
-            const uint64_t bc = Rd<DEF>::bcount(b, c);
-            if (bc > 0x7fffffffull) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-            int64_t total = 0;
-            for (uint64_t i = 0; i < bc; i++) {  // :1062-1066
-                const int64_t blk = (int64_t)Rd<DEF>::block(b, c) + (i ? 1 : 0);
-                total += blk;
-                if (!(i & 1)) copied += blk;
-                if (b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-            }
-            const int64_t dp = g.outdeg[x - (int32_t)r - g.node_lo];
-            if (!(bc & 1)) copied += dp - total;  // :1069
-            if (total > dp || copied < 0 || copied > d) { report(g.err, E_FORMAT, x, b.pos() + g.bit_base); return E_FORMAT; }
-        }
-    }
-    int64_t extra = d - copied;
-    if (extra == 0) return copied;
-    row += copied;
 
-    // interval section: remember where it starts, walk it once to find the residual section (:1076-1096)
-    int64_t ic = 0;
-    BitBuf ib = b;
-    if (c.minlen != 0) {
-        ic = (int64_t)b.gamma();
-        if (ic > extra || b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-        ib = b;
-        int64_t tot = 0;
-        for (int64_t i = 0; i < ic; i++) {
-            (void)b.gamma();
-            tot += (int64_t)b.gamma() + c.minlen;
-            if (b.pos() > limit || tot > extra) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-        }
-        extra -= tot;
+template <bool DEF>
+struct ExtrasWalk {
+    BitBuf b, ib;        // b: residual cursor (after header()), ib: interval cursor
+    int32_t x;
+    int32_t d, copied;   // outdegree, successors copied from the parent
+    int32_t ic, rc;      // intervals, residuals
+    int32_t nout;        // d - copied: entries this step produces
+    int err;             // 0 or a negative status; an erroneous or empty record has nout == 0
+
+    __device__ __forceinline__ void fail(const GraphDev& g, int code) {
+        report(g.err, code, x, b.pos() + g.bit_base);
+        err = code; nout = 0; ic = 0; rc = 0;
     }
-    const int64_t total_out = d - copied;
-    if (ic == 0) {  // the common case: residuals only -- a tight loop in 32-bit arithmetic (ResidualIntIterator, :939-972)
+
+    __device__ __forceinline__ void header(const GraphDev& g, int32_t x_, bool active) {
+        const Codec& c = g.c;
+        x = x_; d = 0; copied = 0; ic = 0; rc = 0; nout = 0; err = 0;
+        if (!active) return;
+        b = buffer_at(g, x);
+        ib = b;
+        const uint64_t limit = g.bit_end - g.bit_base;
+        const uint64_t d64 = Rd<DEF>::outdeg(b, c);
+        if (d64 > 0x7fffffffull || b.pos() > limit) { fail(g, E_IO); return; }
+        d = (int32_t)d64;
+        int64_t cp = 0;
+        bool ok = d != 0;
+        if (ok && c.window > 0) {
+            const uint64_t r = Rd<DEF>::ref(b, c);
+            if (r > (uint64_t)c.window) { fail(g, E_STATE); ok = false; }  // :705
+            else if (r > 0) {
+                if ((int64_t)r > (int64_t)x - g.node_lo) { fail(g, E_FORMAT); ok = false; }
+                else {
+                    const uint64_t bc = Rd<DEF>::bcount(b, c);
+                    int64_t total = 0;
+                    if (bc > 0x7fffffffull) { fail(g, E_IO); ok = false; }
+                    for (uint64_t i = 0; ok && i < bc; i++) {  // :1062-1066
+                        const int64_t blk = (int64_t)Rd<DEF>::block(b, c) + (i ? 1 : 0);
+                        total += blk;
+                        if (!(i & 1)) cp += blk;
+                        if (b.pos() > limit) { fail(g, E_IO); ok = false; }
+                    }
+                    if (ok) {
+                        const int64_t dp = g.outdeg[x - (int32_t)r - g.node_lo];
+                        if (!(bc & 1)) cp += dp - total;  // :1069
+                        if (total > dp || cp < 0 || cp > d) { fail(g, E_FORMAT); ok = false; }
+                    }
+                }
+            }
+        }
+        if (!ok) return;
+        copied = (int32_t)cp;
+        int64_t extra = (int64_t)d - cp;
+        nout = (int32_t)extra;
+        if (extra == 0) return;
+        // interval section: remember where it starts, walk it once to find the residual section (:1076-1096)
+        if (c.minlen != 0) {
+            const int64_t n_iv = (int64_t)b.gamma();
+            if (n_iv > extra || b.pos() > limit) { fail(g, E_IO); return; }
+            ib = b;
+            int64_t tot = 0;
+            for (int64_t i = 0; ok && i < n_iv; i++) {
+                (void)b.gamma();
+                tot += (int64_t)b.gamma() + c.minlen;
+                if (b.pos() > limit || tot > extra) { fail(g, E_IO); ok = false; }
+            }
+            if (!ok) return;
+            ic = (int32_t)n_iv;
+            extra -= tot;
+        }
+        rc = (int32_t)extra;
+    }
+
+    // Records without intervals (ResidualIntIterator, :939-972).
+    template <bool FOLD>
+    __device__ __forceinline__ void residuals_only(const GraphDev& g, int32_t* __restrict__ row, bool store, unsigned long long& fold) {
+        if (ic != 0 || rc <= 0) return;
+        const Codec& c = g.c;
+        const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        row += copied;
         uint32_t v = (uint32_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));  // :954
-        const int32_t n = (int32_t)extra;
         if (store) row[0] = (int32_t)v;
         if (FOLD) fold ^= fold_base + (unsigned long long)v;
-        for (int32_t i = 1; i < n; i++) {
+        for (int32_t i = 1; i < rc; i++) {
             v += Rd<DEF>::gap(b, c) + 1u;  // :966
             if (store) row[i] = (int32_t)v;
             if (FOLD) fold ^= fold_base + (unsigned long long)v;
         }
-        if (b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-        if (FOLD) *acc ^= fold;
-        return copied;
+        if (b.pos() > g.bit_end - g.bit_base) fail(g, E_IO);
     }
-    int64_t rc = extra;  // residual count
-    // cursors: ib walks intervals, b walks residuals
-    int64_t icur = 0, irem = 0, iprev = 0, ileft = ic;
-    bool ifirst = true;
-    int64_t rnext = 0;
-    if (rc > 0) rnext = (int64_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));  // :954
-    int64_t k = 0;
-    for (;;) {
-        if (irem == 0 && ileft > 0) {  // load the next interval (:1084-1095)
-            if (ifirst) { icur = (int64_t)(int32_t)(nat2int(ib.gamma()) + (int64_t)x); ifirst = false; }
-            else icur = (int64_t)ib.gamma() + iprev + 1;
-            irem = (int64_t)ib.gamma() + c.minlen;
-            iprev = icur + irem;
-            ileft--;
-        }
-        const int64_t iv = irem > 0 ? icur : BVG_INF;
-        const int64_t rv = rc > 0 ? rnext : BVG_INF;
-        if (iv == BVG_INF && rv == BVG_INF) break;
-        if (iv < rv) {
-            if (store) row[k] = (int32_t)iv;
-            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)iv;
-            k++; icur++; irem--;
-        } else {
-            if (store) row[k] = (int32_t)rv;
-            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)rv;
-            k++;
-            if (iv == rv) { icur++; irem--; }
-            if (--rc > 0) {
-                rnext += (int64_t)Rd<DEF>::resid(b, c) + 1;  // :966
-                if (b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
+
+    // Records with intervals: Merged(IntIntervalSequenceIterator, ResidualIntIterator) streamed from two cursors.
+    template <bool FOLD>
+    __device__ __forceinline__ void with_intervals(const GraphDev& g, int32_t* __restrict__ row, bool store, unsigned long long& fold) {
+        if (ic == 0) return;
+        const Codec& c = g.c;
+        const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        const uint64_t limit = g.bit_end - g.bit_base;
+        row += copied;
+        int64_t icur = 0, irem = 0, iprev = 0;
+        int32_t ileft = ic, left_r = rc;
+        bool ifirst = true;
+        int64_t rnext = 0;
+        if (left_r > 0) rnext = (int64_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));  // :954
+        int32_t k = 0;
+        for (;;) {
+            if (irem == 0 && ileft > 0) {  // load the next interval (:1084-1095)
+                if (ifirst) { icur = (int64_t)(int32_t)(nat2int(ib.gamma()) + (int64_t)x); ifirst = false; }
+                else icur = (int64_t)ib.gamma() + iprev + 1;
+                irem = (int64_t)ib.gamma() + c.minlen;
+                iprev = icur + irem;
+                ileft--;
             }
+            const int64_t iv = irem > 0 ? icur : BVG_INF;
+            const int64_t rv = left_r > 0 ? rnext : BVG_INF;
+            if (iv == BVG_INF && rv == BVG_INF) break;
+            int64_t out;
+            if (iv < rv) { out = iv; icur++; irem--; }
+            else {
+                out = rv;
+                if (iv == rv) { icur++; irem--; }
+                if (--left_r > 0) rnext += (int64_t)Rd<DEF>::gap(b, c) + 1;  // :966
+            }
+            if (store) row[k] = (int32_t)out;
+            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)out;
+            k++;
+            if (k >= nout) break;
         }
+        while (k < nout) {  // only reachable for files with duplicated successors (:1210 drains -1)
+            if (store) row[k] = -1;
+            if (FOLD) fold ^= fold_base + 0xffffffffull;
+            k++;
+        }
+        if (b.pos() > limit) fail(g, E_IO);
     }
-    if (b.pos() > limit) { report(g.err, E_IO, x, b.pos() + g.bit_base); return E_IO; }
-    while (k < total_out) {  // only reachable for files with duplicated successors (:1210 drains -1)
-        if (store) row[k] = -1;
-        if (FOLD) fold ^= fold_base + 0xffffffffull;
-        k++;
-    }
+};
+
+// The three phases back to back (natural-order kernels, random access). Returns `copied` or a negative error.
+template <bool DEF, bool FOLD = false>
+__device__ int64_t decode_extras(const GraphDev& g, int32_t x, int32_t* __restrict__ row, bool store = true,
+                                 unsigned long long* acc = nullptr) {
+    ExtrasWalk<DEF> w;
+    unsigned long long fold = 0;
+    w.header(g, x, true);
+    w.template residuals_only<FOLD>(g, row, store, fold);
+    w.template with_intervals<FOLD>(g, row, store, fold);
     if (FOLD) *acc ^= fold;
-    return copied;
+    return w.err ? (int64_t)w.err : (int64_t)w.copied;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Step 2: stream the parent's row through the copy blocks (MaskedIntIterator.java:65-97) and merge it, forward and
-// in place, with the extras sitting at row[copied .. d).  Output position never overtakes the unread tail because
-// at most `copied` elements come from the parent.
+// Step 2: stream the parent's row through the copy blocks (MaskedIntIterator.java:65-97) and either merge it, forward
+// and in place, with the extras sitting at row[copied .. d) -- the output position never overtakes the unread tail
+// because exactly `copied` elements come from the parent, and once the parent stream is exhausted the rest is already
+// in place -- or, when nobody copies from this node during a consume-only scan, just fold the copied successors.
+// Same three-phase shape as ExtrasWalk.
 // ---------------------------------------------------------------------------------------------------
-template <bool DEF, bool FOLD = false>
-__device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__ row, const int32_t* __restrict__ parent,
-                             bool store = true, unsigned long long* acc = nullptr) {
-    const Codec& c = g.c;
-    const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
-    unsigned long long fold = 0;
-    BitBuf b = buffer_at(g, x);
-    const int64_t d = (int64_t)Rd<DEF>::outdeg(b, c);
-    const int32_t r = (int32_t)Rd<DEF>::ref(b, c);
-    const int64_t bc = (int64_t)Rd<DEF>::bcount(b, c);
-    const int64_t dp = g.outdeg[x - r - g.node_lo];
-    // copied count: from the index when it has one, else a first walk over the blocks (same arithmetic as step 1)
-    int64_t copied = 0, total = 0;
-    if (g.copied) copied = g.copied[x - g.node_lo];
-    else {
-        BitBuf t = b;
-        for (int64_t i = 0; i < bc; i++) {
-            const int64_t blk = (int64_t)Rd<DEF>::block(t, c) + (i ? 1 : 0);
-            total += blk;
-            if (!(i & 1)) copied += blk;
+template <bool DEF>
+struct MergeWalk {
+    BitBuf b;            // block-list cursor
+    int32_t x;
+    int32_t d, dp, copied;
+    int32_t bc, bi;      // blocks, next block to read
+    int32_t p, rem;      // next parent index, remaining length of the current copy block
+    bool tail, active;
+    const int32_t* __restrict__ parent;
+
+    __device__ __forceinline__ void header(const GraphDev& g, int32_t x_, const int32_t* __restrict__ parent_, bool active_) {
+        const Codec& c = g.c;
+        x = x_; parent = parent_; active = active_;
+        d = dp = copied = bc = bi = p = rem = 0;
+        tail = false;
+        if (!active) return;
+        b = buffer_at(g, x);
+        d = (int32_t)Rd<DEF>::outdeg(b, c);
+        const int32_t r = (int32_t)Rd<DEF>::ref(b, c);
+        bc = (int32_t)Rd<DEF>::bcount(b, c);
+        dp = g.outdeg[x - r - g.node_lo];
+        // copied count: from the index when it has one, else a first walk over the blocks (same arithmetic as step 1)
+        if (g.copied) copied = g.copied[x - g.node_lo];
+        else {
+            BitBuf t = b;
+            int64_t total = 0, cp = 0;
+            for (int32_t i = 0; i < bc; i++) {
+                const int64_t blk = (int64_t)Rd<DEF>::block(t, c) + (i ? 1 : 0);
+                total += blk;
+                if (!(i & 1)) cp += blk;
+            }
+            if (!(bc & 1)) cp += dp - total;
+            copied = (int32_t)cp;
         }
-        if (!(bc & 1)) copied += dp - total;
     }
-    int64_t j = copied, k = 0;   // j: next unread extra, k: next output slot
-    int64_t p = 0;               // next parent index
-    int64_t bi = 0, rem = 0;     // block cursor: index of the next block to read, remaining length of the current copy block
-    bool tail = false;
-    int64_t a = BVG_INF;
-    auto next_a = [&]() -> int64_t {
+
+    // next copied successor, or BVG_INF
+    __device__ __forceinline__ int64_t next_a(const Codec& c) {
         for (;;) {
             if (rem > 0) { rem--; return parent[p++]; }
             if (tail) return p < dp ? (int64_t)parent[p++] : BVG_INF;
             if (bi == bc) { if (bc & 1) return BVG_INF; tail = true; continue; }  // even count: copy the tail
-            const int64_t blk = (int64_t)Rd<DEF>::block(b, c) + (bi ? 1 : 0);
+            const int32_t blk = (int32_t)Rd<DEF>::block(b, c) + (bi ? 1 : 0);
             if (bi & 1) p += blk; else rem = blk;
             bi++;
         }
-    };
-    a = next_a();
-    if (FOLD && !store) {  // nobody copies from x: the copied successors are only consumed, never merged
-        while (a != BVG_INF) { fold ^= fold_base + (unsigned long long)(uint32_t)a; a = next_a(); }
-        *acc ^= fold;
-        return;
     }
-    for (;;) {
-        // once the parent stream is exhausted the remaining extras already sit at their final positions (k == j),
-        // unless duplicates were dropped earlier (k < j), which only malformed files produce
-        if (a == BVG_INF && k == j) break;
-        const int64_t bv = j < d ? (int64_t)row[j] : BVG_INF;
-        if (a == BVG_INF && bv == BVG_INF) { while (k < d) row[k++] = -1; break; }
-        if (a < bv) {
-            row[k++] = (int32_t)a;
-            if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)a;
-            a = next_a();
-        } else {
-            row[k++] = (int32_t)bv; j++;
-            if (a == bv) a = next_a();  // equal heads are emitted once (MergedIntIterator.java:70)
+
+    // nobody copies from x: the copied successors are only consumed
+    __device__ __forceinline__ void stream_only(const GraphDev& g, unsigned long long& fold) {
+        if (!active) return;
+        const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        for (int64_t a = next_a(g.c); a != BVG_INF; a = next_a(g.c)) fold ^= fold_base + (unsigned long long)(uint32_t)a;
+    }
+
+    template <bool FOLD>
+    __device__ __forceinline__ void merge_in_place(const GraphDev& g, int32_t* __restrict__ row, unsigned long long& fold) {
+        if (!active) return;
+        const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        int32_t j = copied, k = 0;  // j: next unread extra, k: next output slot
+        int64_t a = next_a(g.c);
+        for (;;) {
+            // parent exhausted and nothing was dropped: the remaining extras already sit at their final positions
+            if (a == BVG_INF && k == j) break;
+            const int64_t bv = j < d ? (int64_t)row[j] : BVG_INF;
+            if (a == BVG_INF && bv == BVG_INF) { while (k < d) row[k++] = -1; break; }  // duplicates were dropped (:1210)
+            if (a < bv) {
+                row[k++] = (int32_t)a;
+                if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)a;
+                a = next_a(g.c);
+            } else {
+                row[k++] = (int32_t)bv; j++;
+                if (a == bv) a = next_a(g.c);  // equal heads are emitted once (MergedIntIterator.java:70)
+            }
         }
     }
+};
+
+template <bool DEF, bool FOLD = false>
+__device__ void merge_copied(const GraphDev& g, int32_t x, int32_t* __restrict__ row, const int32_t* __restrict__ parent,
+                             bool store = true, unsigned long long* acc = nullptr) {
+    MergeWalk<DEF> w;
+    unsigned long long fold = 0;
+    w.header(g, x, parent, true);
+    if (FOLD && !store) w.stream_only(g, fold);
+    else w.template merge_in_place<FOLD>(g, row, fold);
     if (FOLD) *acc ^= fold;
 }
 

@@ -97,28 +97,37 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
     if (i >= n) return;
     const int32_t d = g.outdeg[i], dep = g.depth[i];
     int32_t ke = -1, km = -1, copied = 0;
-    if (d > 0 && dep >= 1) {
+    if (d > 0 && dep >= 0) {
         const int32_t x = g.node_lo + (int32_t)i;
+        const uint64_t limit = g.bit_end - g.bit_base;
         BitBuf b = buffer_at(g, x);
         (void)Rd<DEF>::outdeg(b, g.c);
-        const int32_t r = (int32_t)Rd<DEF>::ref(b, g.c);
-        const int64_t bc = (int64_t)Rd<DEF>::bcount(b, g.c);
-        const uint64_t limit = g.bit_end - g.bit_base;
-        int64_t total = 0, cp = 0;
-        for (int64_t k = 0; k < bc && b.pos() <= limit; k++) {
-            const int64_t blk = (int64_t)Rd<DEF>::block(b, g.c) + (k ? 1 : 0);
-            total += blk;
-            if (!(k & 1)) cp += blk;
+        int64_t bc = 0;
+        if (g.c.window > 0) {
+            const int32_t r = (int32_t)Rd<DEF>::ref(b, g.c);
+            if (r > 0) {
+                bc = (int64_t)Rd<DEF>::bcount(b, g.c);
+                int64_t total = 0, cp = 0;
+                for (int64_t k = 0; k < bc && b.pos() <= limit; k++) {
+                    const int64_t blk = (int64_t)Rd<DEF>::block(b, g.c) + (k ? 1 : 0);
+                    total += blk;
+                    if (!(k & 1)) cp += blk;
+                }
+                if (!(bc & 1)) cp += (int64_t)g.outdeg[i - r] - total;
+                copied = (int32_t)(cp < 0 ? 0 : (cp > d ? d : cp));  // malformed records are reported by the decode step
+            }
         }
-        if (!(bc & 1)) cp += (int64_t)g.outdeg[i - r] - total;
-        copied = (int32_t)(cp < 0 ? 0 : (cp > d ? d : cp));  // malformed records are reported by the decode step
-        if (d <= long_d && dep <= max_level_keys) {
-            const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (is_parent[i] ? (uint64_t)(d - copied) : 0);
-            km = (dep - 1) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
+        // records with intervals take a different loop than records without: keep the two kinds in separate warps
+        const int has_iv = (d > copied && g.c.minlen != 0 && b.pos() <= limit && b.gamma() != 0) ? 1 : 0;
+        if (d <= long_d) {  // longer records are split across threads (bvg_long.cuh)
+            ke = has_iv * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]));
+            if (dep >= 1 && dep <= max_level_keys) {
+                const int par = is_parent[i] ? 1 : 0;  // parents merge in place, the others only stream: separate warps too
+                const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (par ? (uint64_t)(d - copied) : 0);
+                km = ((dep - 1) * 2 + par) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
+            }
         }
     }
-    if (d > 0 && d <= long_d && dep >= 0)  // longer records are split across threads (bvg_long.cuh)
-        ke = ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]);
     key_e[i] = ke;
     key_m[i] = km;
     copied_out[i] = copied;
@@ -283,22 +292,32 @@ __global__ void k_merge(GraphDev g, int32_t lo, int32_t hi, int32_t level, RowMa
 }
 
 // The same two steps over a length-bucketed schedule (order[0..count)): node ids outside [lo, hi) are skipped.
+// Phases are separated by __syncwarp() so that the 32 lanes enter each loop together (see ExtrasWalk).
 template <bool DEF>
 __global__ void k_extras_ordered(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, RowMap rm) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const int32_t x = order[i];
-    if (x < lo || x >= hi || !rm.wanted(g, x)) return;
-    decode_extras<DEF>(g, x, rm.row(g, x));
+    const int32_t x = i < count ? order[i] : -1;
+    const bool active = x >= lo && x < hi && rm.wanted(g, x);
+    ExtrasWalk<DEF> w;
+    w.header(g, x, active);
+    int32_t* row = active ? rm.row(g, x) : nullptr;
+    unsigned long long f = 0;
+    __syncwarp();
+    w.template residuals_only<false>(g, row, true, f);
+    __syncwarp();
+    w.template with_intervals<false>(g, row, true, f);
 }
 
 template <bool DEF>
 __global__ void k_merge_ordered(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, RowMap rm) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const int32_t x = order[i];
-    if (x < lo || x >= hi || !rm.wanted(g, x)) return;
-    merge_copied<DEF>(g, x, rm.row(g, x), rm.row(g, x - g.ref[x - g.node_lo]));
+    const int32_t x = i < count ? order[i] : -1;
+    const bool active = x >= lo && x < hi && rm.wanted(g, x);
+    MergeWalk<DEF> w;
+    w.header(g, x, active ? rm.row(g, x - g.ref[x - g.node_lo]) : nullptr, active);
+    unsigned long long f = 0;
+    __syncwarp();
+    if (active) w.template merge_in_place<false>(g, rm.row(g, x), f);
 }
 
 // First node any chain starting in [from, to) reaches back to (the halo a range decode has to supply).
@@ -390,22 +409,26 @@ __global__ void k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int
                               RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
     long long arcs = 0;
-    // warp-uniform trip count and an explicit reconvergence point per item: without it lanes that finish early run
-    // ahead into their next item and the warp never executes the decode loop in lockstep again
+    // warp-uniform trip count and explicit reconvergence between the phases of each item: the lanes of a warp walk
+    // 32 records of similar length, and they only do so in lockstep if they enter each loop together
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
         const int64_t i = base + (threadIdx.x & 31);
         const int32_t x = i < count ? order[i] : -1;
-        if (x >= lo && x < hi && rm.wanted(g, x)) {
-            const bool store = is_parent[x - g.node_lo] != 0;
-            if (x >= from) {
-                decode_extras<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, store, &acc);
-                arcs += g.outdeg[x - g.node_lo];
-            } else if (store) {
-                decode_extras<DEF, false>(g, x, rm.row(g, x));  // halo: a parent of the range, not part of it
-            }
-        }
+        bool active = x >= lo && x < hi && rm.wanted(g, x);
+        const bool store = active && is_parent[x - g.node_lo] != 0;
+        const bool fold = active && x >= from;
+        active = active && (fold || store);  // halo nodes matter only as parents
+        ExtrasWalk<DEF> w;
+        w.header(g, x, active);
+        int32_t* row = store ? rm.row(g, x) : nullptr;
+        unsigned long long f = 0;
         __syncwarp();
+        w.template residuals_only<true>(g, row, store, f);
+        __syncwarp();
+        w.template with_intervals<true>(g, row, store, f);
+        __syncwarp();
+        if (fold) { acc ^= f; arcs += w.d; }
     }
     block_fold(acc, arcs, result);
 }
@@ -418,13 +441,20 @@ __global__ void k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int6
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
         const int64_t i = base + (threadIdx.x & 31);
         const int32_t x = i < count ? order[i] : -1;
-        if (x >= lo && x < hi && rm.wanted(g, x)) {
-            const bool store = is_parent[x - g.node_lo] != 0;
-            const int32_t* parent = rm.row(g, x - g.ref[x - g.node_lo]);
-            if (x >= from) merge_copied<DEF, true>(g, x, store ? rm.row(g, x) : nullptr, parent, store, &acc);
-            else if (store) merge_copied<DEF, false>(g, x, rm.row(g, x), parent);
-        }
+        bool active = x >= lo && x < hi && rm.wanted(g, x);
+        const bool store = active && is_parent[x - g.node_lo] != 0;
+        const bool fold = active && x >= from;
+        active = active && (fold || store);
+        MergeWalk<DEF> w;
+        w.header(g, x, active ? rm.row(g, x - g.ref[x - g.node_lo]) : nullptr, active);
+        int32_t* row = store ? rm.row(g, x) : nullptr;
+        unsigned long long f = 0;
         __syncwarp();
+        if (!store) w.stream_only(g, f);
+        __syncwarp();
+        if (store) w.template merge_in_place<true>(g, row, f);
+        __syncwarp();
+        if (fold) acc ^= f;
     }
     block_fold(acc, 0, result);
 }
