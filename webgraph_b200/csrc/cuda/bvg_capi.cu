@@ -75,6 +75,8 @@ struct bvg_graph {
     uint64_t* d_seg_pos = nullptr;
     int64_t* d_seg_val = nullptr;
     LongItem *d_items_resid = nullptr, *d_items_extras = nullptr, *d_items_merge = nullptr;
+    RowChunk* d_items_fold = nullptr;
+    int64_t n_items_fold = 0;
     int64_t n_items_resid = 0, n_items_extras = 0;
     std::vector<int64_t> merge_item_start;  // items of chain level l+1: d_items_merge[merge_item_start[l] .. [l+1])
     int64_t long_tmp_entries = 0;
@@ -215,6 +217,7 @@ static int build_long_index(bvg_graph* g) {
     CK(cudaStreamSynchronize(s));
     int64_t cb = 0, iv = 0, seg = 0, tmp = 0;
     std::vector<LongItem> it_r, it_x;
+    std::vector<RowChunk> it_f;
     std::vector<std::vector<LongItem>> it_m((size_t)g->max_depth + 1);
     for (int64_t l = 0; l < nl; l++) {
         LongMeta& m = meta[(size_t)l];
@@ -225,6 +228,7 @@ static int build_long_index(bvg_graph* g) {
         seg += nseg;
         m.tmp_off = tmp; tmp += 2 * (int64_t)m.d;
         for (int32_t q = 0; q < nseg; q++) it_r.push_back(LongItem{ (int32_t)l, q });
+        for (int32_t q = 0; q * FOLD_CHUNK < m.d; q++) it_f.push_back(RowChunk{ m.x, q });
         if (m.ic > 0) for (int32_t q = 0; q * LONG_CHUNK < m.ilen + m.rc; q++) it_x.push_back(LongItem{ (int32_t)l, q });
         if (m.copied > 0 && m.level >= 1) for (int32_t q = 0; q * LONG_CHUNK < m.d; q++) it_m[(size_t)m.level].push_back(LongItem{ (int32_t)l, q });
     }
@@ -252,6 +256,9 @@ static int build_long_index(bvg_graph* g) {
     CK(upload(it_r, &g->d_items_resid));
     CK(upload(it_x, &g->d_items_extras));
     CK(upload(merged, &g->d_items_merge));
+    CK(cudaMalloc((void**)&g->d_items_fold, std::max<size_t>(it_f.size(), 1) * sizeof(RowChunk)));
+    if (!it_f.empty()) CK(cudaMemcpyAsync(g->d_items_fold, it_f.data(), it_f.size() * sizeof(RowChunk), cudaMemcpyHostToDevice, s));
+    g->n_items_fold = (int64_t)it_f.size();
     g->n_items_resid = (int64_t)it_r.size();
     g->n_items_extras = (int64_t)it_x.size();
     g->long_tmp_entries = tmp;
@@ -356,7 +363,7 @@ static void destroy(bvg_graph* g) {
     cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
     cudaFree(g->d_order_e); cudaFree(g->d_order_m); cudaFree(g->d_is_parent); cudaFree(g->d_long_nodes); cudaFree(g->d_copied);
     cudaFree(g->d_long_meta); cudaFree(g->d_cb_cum); cudaFree(g->d_cb_ppos); cudaFree(g->d_iv_cum); cudaFree(g->d_iv_left);
-    cudaFree(g->d_seg_pos); cudaFree(g->d_seg_val); cudaFree(g->d_items_resid); cudaFree(g->d_items_extras); cudaFree(g->d_items_merge);
+    cudaFree(g->d_seg_pos); cudaFree(g->d_seg_val); cudaFree(g->d_items_resid); cudaFree(g->d_items_extras); cudaFree(g->d_items_merge); cudaFree(g->d_items_fold);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
     delete g;
@@ -747,9 +754,9 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->d_items_merge + ma, mc, lo, to, rm, ld);
         }
     }
-    if (g->nlong) {
-        const unsigned gl = (unsigned)std::min<int64_t>(148 * 4, ((int64_t)g->nlong + 3) / 4);
-        LAUNCH_P(g, "k_checksum_nodes", k_checksum_nodes, gl, 128, 0, s, gd, g->d_long_nodes, (int64_t)g->nlong, from, to, rm, d_result);
+    if (g->nlong && g->n_items_fold) {
+        const unsigned gl = (unsigned)std::min<int64_t>(148 * 8, (g->n_items_fold + 7) / 8);
+        LAUNCH_P(g, "k_checksum_chunks", k_checksum_chunks, gl, 256, 0, s, gd, g->d_items_fold, g->n_items_fold, from, to, rm, d_result);
     }
     CK(cudaGetLastError());
     return BVG_OK;

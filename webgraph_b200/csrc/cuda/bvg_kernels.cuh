@@ -459,20 +459,24 @@ __global__ void k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int6
     block_fold(acc, 0, result);
 }
 
-// Rows of listed nodes (the long records, always materialised) folded by one warp per node.
-__global__ void k_checksum_nodes(GraphDev g, const int32_t* __restrict__ nodes, int64_t count, int32_t lo, int32_t hi,
-                                 RowMap rm, unsigned long long* __restrict__ result) {
+// Rows of the long records (always materialised by the split path) folded by one warp per 1024-entry chunk.
+struct RowChunk { int32_t x, part; };
+constexpr int32_t FOLD_CHUNK = 1024;
+
+__global__ void k_checksum_chunks(GraphDev g, const RowChunk* __restrict__ items, int64_t count, int32_t lo, int32_t hi,
+                                  RowMap rm, unsigned long long* __restrict__ result) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned long long acc = 0;
     long long arcs = 0;
     for (int64_t i = (int64_t)blockIdx.x * nw + wid; i < count; i += (int64_t)gridDim.x * nw) {
-        const int32_t x = nodes[i];
-        if (x < lo || x >= hi) continue;
-        const int32_t d = g.outdeg[x - g.node_lo];
-        const int32_t* row = rm.row(g, x);
-        const unsigned long long base = (unsigned long long)(uint32_t)x * BVG_MIX;
-        for (int32_t p = lane; p < d; p += 32) acc ^= base + (unsigned long long)(uint32_t)row[p];
-        if (lane == 0) arcs += d;
+        const RowChunk it = items[i];
+        if (it.x < lo || it.x >= hi) continue;
+        const int32_t d = g.outdeg[it.x - g.node_lo];
+        const int32_t a = it.part * FOLD_CHUNK, e = min(d, a + FOLD_CHUNK);
+        const int32_t* row = rm.row(g, it.x);
+        const unsigned long long base = (unsigned long long)(uint32_t)it.x * BVG_MIX;
+        for (int32_t p = a + lane; p < e; p += 32) acc ^= base + (unsigned long long)(uint32_t)row[p];
+        if (lane == 0) arcs += e - a;
     }
     block_fold(acc, arcs, result);
 }
