@@ -280,8 +280,9 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
     LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
-    const int64_t per_level = 2 * ORDER_BUCKETS;  // (parent | not) x half-octave bucket
-    const int64_t nb_e = 2 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
+    const int64_t nchunks = (nn + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG;
+    const int64_t per_level = nchunks * 2 * ORDER_BUCKETS;  // chunk x (parent | not) x half-octave bucket
+    const int64_t nb_e = nchunks * 2 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
     Tmp<int32_t> key_e(s), key_m(s), bins(s);
     CK(key_e.alloc((size_t)nn));
     CK(key_m.alloc((size_t)nn));

@@ -77,6 +77,10 @@ __global__ void k_max_i32(const int32_t* __restrict__ in, int64_t n, int32_t* __
 // for the merge step), longest first, so the 32 lanes of a warp get records of similar length.
 // ---------------------------------------------------------------------------------------------------
 constexpr int ORDER_BUCKETS = 128;
+// Schedules are bucketed inside chunks of 2^ORDER_CHUNK_LOG consecutive nodes, chunks in node order: the lanes of a
+// warp still get records of similar length, but everything in flight at one time comes from a few tens of MB of the
+// stream, the index arrays and the rows, which the 126 MB L2 can hold.
+constexpr int ORDER_CHUNK_LOG = 18;
 
 __device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // 0..127, monotone in v
     if (v == 0) return 0;
@@ -96,6 +100,7 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
     const int64_t n = (int64_t)g.node_hi - g.node_lo;
     if (i >= n) return;
     const int32_t d = g.outdeg[i], dep = g.depth[i];
+    const int32_t chunk = (int32_t)(i >> ORDER_CHUNK_LOG);
     int32_t ke = -1, km = -1, copied = 0;
     if (d > 0 && dep >= 0) {
         const int32_t x = g.node_lo + (int32_t)i;
@@ -120,11 +125,12 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
         // records with intervals take a different loop than records without: keep the two kinds in separate warps
         const int has_iv = (d > copied && g.c.minlen != 0 && b.pos() <= limit && b.gamma() != 0) ? 1 : 0;
         if (d <= long_d) {  // longer records are split across threads (bvg_long.cuh)
-            ke = has_iv * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]));
+            ke = (chunk * 2 + has_iv) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]));
             if (dep >= 1 && dep <= max_level_keys) {
                 const int par = is_parent[i] ? 1 : 0;  // parents merge in place, the others only stream: separate warps too
                 const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (par ? (uint64_t)(d - copied) : 0);
-                km = ((dep - 1) * 2 + par) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
+                const int32_t nchunks = (int32_t)((n + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG);
+                km = (((dep - 1) * nchunks + chunk) * 2 + par) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
             }
         }
     }
