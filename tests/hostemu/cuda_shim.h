@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+struct uint4 { uint32_t x, y, z, w; };
 #define __device__
 #define __host__
 #define __global__

@@ -10,7 +10,7 @@ using namespace bvg;
 extern "C" int emu_decode(const uint8_t* graph, uint64_t nbytes, const uint64_t* offsets, int32_t n,
                           int window, int minlen, int zetak, int c_outdeg, int c_block, int c_resid, int c_ref, int c_bcount,
                           int def_codec, int64_t* out_off, int32_t* out, int64_t cap, int random_mode) {
-    std::vector<uint32_t> words((nbytes + 3) / 4 + 8, 0);
+    std::vector<uint32_t> words((((nbytes + 3) / 4 + 8 + 3) / 4) * 4, 0);
     for (uint64_t i = 0; i < nbytes; i++) words[i >> 2] |= (uint32_t)graph[i] << (24 - 8 * (i & 3));
     std::vector<int32_t> outdeg(n), ref(n), depth(n);
     std::vector<int64_t> rowoff(n + 1, 0);

@@ -321,7 +321,7 @@ static int build_schedules(bvg_graph* g) {
 // Uploads the stream bytes + offsets of nodes [node_lo, node_hi] and builds the decode index.
 static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbytes, const uint64_t* offsets) {
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
-    g->nwords = (nbytes + 3) / 4 + 8;  // >= 4 padding words after the last byte
+    g->nwords = ((nbytes + 3) / 4 + 8 + 3) & ~(uint64_t)3;  // >= 8 padding words, a whole number of 128-bit groups
     CK(cudaMalloc((void**)&g->d_words, g->nwords * 4));
     CK(cudaMemsetAsync(g->d_words, 0, g->nwords * 4, g->stream));
     if (nbytes) CK(cudaMemcpyAsync(g->d_words, bytes, nbytes, cudaMemcpyHostToDevice, g->stream));
@@ -730,7 +730,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     HaloPlan hp(s);
     { const int rc = plan_halo(g, from, to, rows, row_from, rm, hp); if (rc) return rc; }
     const int32_t lo = hp.lo;
-    const unsigned grid = 148 * 8;
+    const unsigned grid = 148 * SCAN_BLOCKS_PER_SM;
     if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
     Tmp<int32_t> long_tmp(s);

@@ -21,6 +21,15 @@
 
 namespace bvg {
 
+// L1 prefetch of the sector a few refills ahead: a lane walks its record word by word, and without it every new
+// 32-byte sector is a serial L1 miss for the whole warp.
+#ifdef BVG_HOST_EMULATION
+#define BVG_PREFETCH_L1(p)
+#else
+#define BVG_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#endif
+constexpr int PREFETCH_WORDS_AHEAD = 16;
+
 enum { C_DELTA = 1, C_GAMMA = 2, C_GOLOMB = 3, C_SKEWED_GOLOMB = 4, C_UNARY = 5, C_ZETA = 6, C_NIBBLE = 7 };
 
 enum { E_OK = 0, E_INVAL = -1, E_STATE = -2, E_UNSUPPORTED = -3, E_IO = -4, E_FORMAT = -5, E_NOMEM = -6, E_CUDA = -7, E_END = -8 };
@@ -155,15 +164,35 @@ struct Bits {
 struct BitBuf {
     const uint32_t* __restrict__ w;
     uint64_t maxw;   // as in Bits: w[maxw + 2] is the last readable word
-    uint64_t widx;   // next word to load
+    uint64_t widx;   // next word to enter the window (the queue holds words widx .. widx + qn - 1)
+    uint64_t gnext;  // next 4-word group to load (multiple of 4)
     uint64_t buf;    // MSB-aligned window; bits beyond `avail` are zero
+    uint4 q;         // word queue, filled by one 128-bit load per four words: a lane walks its own record, so every
+    int qn;          // load instruction costs one L1 wavefront per lane whatever its width -- make it 16 bytes wide
     int avail;
 
+    __device__ __forceinline__ void load_group() {
+        const uint64_t lim = (maxw + 2) & ~(uint64_t)3;  // last whole group inside the padded array
+        const uint64_t gi = gnext < lim ? gnext : lim;
+        q = *reinterpret_cast<const uint4*>(w + gi);
+        gnext += 4;
+        qn = 4;
+    }
+    __device__ __forceinline__ uint32_t take() {
+        const uint32_t r = q.x;
+        q.x = q.y; q.y = q.z; q.z = q.w;
+        if (--qn == 0) load_group();  // issued as soon as the queue runs dry, used about two codes later
+        return r;
+    }
     __device__ __forceinline__ void seek(uint64_t pos) {
         uint64_t i = pos >> 5;
         i = i < maxw ? i : maxw;
         const uint32_t s = (uint32_t)pos & 31u;
-        buf = (((uint64_t)w[i] << 32) | (uint64_t)w[i + 1]) << s;
+        gnext = i & ~(uint64_t)3;
+        load_group();
+        for (uint32_t k = (uint32_t)i & 3u; k; k--) (void)take();
+        const uint64_t w0 = take(), w1 = take();
+        buf = ((w0 << 32) | w1) << s;
         avail = 64 - (int)s;
         widx = i + 2;
     }
@@ -172,8 +201,7 @@ struct BitBuf {
         buf <<= n;
         avail -= n;
         if (avail <= 32) {
-            const uint64_t i = widx < maxw + 2 ? widx : maxw + 2;
-            buf |= (uint64_t)w[i] << (32 - avail);
+            buf |= (uint64_t)take() << (32 - avail);
             avail += 32;
             widx++;
         }
@@ -299,7 +327,8 @@ __device__ __forceinline__ BitBuf buffer_at(const GraphDev& g, int32_t x) {
 
 template <bool DEF>
 struct ExtrasWalk {
-    BitBuf b, ib;        // b: residual cursor (after header()), ib: interval cursor
+    BitBuf b;            // residual cursor (after header())
+    Bits ib;             // interval cursor (position-based: intervals are few, registers are not)
     int32_t x;
     int32_t d, copied;   // outdegree, successors copied from the parent
     int32_t ic, rc;      // intervals, residuals
@@ -316,7 +345,7 @@ struct ExtrasWalk {
         x = x_; d = 0; copied = 0; ic = 0; rc = 0; nout = 0; err = 0;
         if (!active) return;
         b = buffer_at(g, x);
-        ib = b;
+        ib.w = g.words; ib.maxw = g.nwords - 3; ib.pos = 0;
         const uint64_t limit = g.bit_end - g.bit_base;
         const uint64_t d64 = Rd<DEF>::outdeg(b, c);
         if (d64 > 0x7fffffffull || b.pos() > limit) { fail(g, E_IO); return; }
@@ -355,7 +384,7 @@ struct ExtrasWalk {
         if (c.minlen != 0) {
             const int64_t n_iv = (int64_t)b.gamma();
             if (n_iv > extra || b.pos() > limit) { fail(g, E_IO); return; }
-            ib = b;
+            ib.pos = b.pos();
             int64_t tot = 0;
             for (int64_t i = 0; ok && i < n_iv; i++) {
                 (void)b.gamma();

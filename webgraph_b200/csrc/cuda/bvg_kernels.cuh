@@ -410,8 +410,11 @@ __device__ __forceinline__ void block_fold(unsigned long long acc, long long arc
     }
 }
 
+constexpr int SCAN_BLOCK = 128;
+constexpr int SCAN_BLOCKS_PER_SM = 8;
+
 template <bool DEF>
-__global__ void k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
                               RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
     long long arcs = 0;
@@ -440,7 +443,7 @@ __global__ void k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int
 }
 
 template <bool DEF>
-__global__ void k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
                              RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
