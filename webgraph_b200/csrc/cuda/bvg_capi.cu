@@ -730,7 +730,10 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     HaloPlan hp(s);
     { const int rc = plan_halo(g, from, to, rows, row_from, rm, hp); if (rc) return rc; }
     const int32_t lo = hp.lo;
-    const unsigned grid = 148 * SCAN_BLOCKS_PER_SM;
+    // persistent grids: one resident wave (SM count x the blocks per SM the kernels are bounded to)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+    const unsigned grid = (unsigned)(sms * SCAN_BLOCKS_PER_SM), grid_m = grid;
     if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
     Tmp<int32_t> long_tmp(s);
@@ -746,7 +749,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     for (int32_t level = 1; level <= g->max_depth; level++) {
         const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
         if (c > 0) {
-            const unsigned gm = (unsigned)std::min<int64_t>(grid, (c + 127) / 128);
+            const unsigned gm = (unsigned)std::min<int64_t>(grid_m, (c + 127) / 128);
             if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_order_m + a, c, lo, to, from, rm, g->d_is_parent, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_order_m + a, c, lo, to, from, rm, g->d_is_parent, d_result);
         }

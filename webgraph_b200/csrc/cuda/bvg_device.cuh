@@ -164,45 +164,31 @@ struct Bits {
 struct BitBuf {
     const uint32_t* __restrict__ w;
     uint64_t maxw;   // as in Bits: w[maxw + 2] is the last readable word
-    uint64_t widx;   // next word to enter the window (the queue holds words widx .. widx + qn - 1)
-    uint64_t gnext;  // next 4-word group to load (multiple of 4)
+    uint64_t widx;   // next word to enter the window
     uint64_t buf;    // MSB-aligned window; bits beyond `avail` are zero
-    uint4 q;         // word queue, filled by one 128-bit load per four words: a lane walks its own record, so every
-    int qn;          // load instruction costs one L1 wavefront per lane whatever its width -- make it 16 bytes wide
-    int avail;
+    uint32_t q0, q1; // w[widx], w[widx + 1]: loaded two refills before they are used, so that the (compulsory)
+    int avail;       // sector miss every eighth word overlaps with decoding instead of stalling the warp
 
-    __device__ __forceinline__ void load_group() {
-        const uint64_t lim = (maxw + 2) & ~(uint64_t)3;  // last whole group inside the padded array
-        const uint64_t gi = gnext < lim ? gnext : lim;
-        q = *reinterpret_cast<const uint4*>(w + gi);
-        gnext += 4;
-        qn = 4;
-    }
-    __device__ __forceinline__ uint32_t take() {
-        const uint32_t r = q.x;
-        q.x = q.y; q.y = q.z; q.z = q.w;
-        if (--qn == 0) load_group();  // issued as soon as the queue runs dry, used about two codes later
-        return r;
-    }
+    __device__ __forceinline__ uint32_t word(uint64_t i) const { return w[i < maxw + 2 ? i : maxw + 2]; }
     __device__ __forceinline__ void seek(uint64_t pos) {
         uint64_t i = pos >> 5;
         i = i < maxw ? i : maxw;
         const uint32_t s = (uint32_t)pos & 31u;
-        gnext = i & ~(uint64_t)3;
-        load_group();
-        for (uint32_t k = (uint32_t)i & 3u; k; k--) (void)take();
-        const uint64_t w0 = take(), w1 = take();
-        buf = ((w0 << 32) | w1) << s;
+        buf = (((uint64_t)w[i] << 32) | (uint64_t)w[i + 1]) << s;
         avail = 64 - (int)s;
         widx = i + 2;
+        q0 = word(widx);
+        q1 = word(widx + 1);
     }
     __device__ __forceinline__ uint64_t pos() const { return widx * 32 - (uint64_t)avail; }
     __device__ __forceinline__ void consume(int n) {  // 0 <= n <= 63, n <= avail
         buf <<= n;
         avail -= n;
         if (avail <= 32) {
-            buf |= (uint64_t)take() << (32 - avail);
+            buf |= (uint64_t)q0 << (32 - avail);
             avail += 32;
+            q0 = q1;
+            q1 = word(widx + 2);
             widx++;
         }
     }
