@@ -25,15 +25,17 @@ def _find_asan():
 @pytest.fixture(scope="module")
 def emu():
     cuda_dir = os.path.join(ROOT, "webgraph_b200", "csrc", "cuda")
-    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"),
-            os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh")]
+    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "emu_offsets.cpp"),
+            os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
+            os.path.join(cuda_dir, "bvg_offsets.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
         # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
-                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1]])
+                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2]])
     lib = C.CDLL(EMU)
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.emu_decode_offsets.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
     return lib
 
 
@@ -83,3 +85,33 @@ def test_emulated_kernels_on_copy_heavy(emu, oracle, tmp_path, flags, k, w, r, m
     run_emu(emu, oracle, base, 0)
     run_emu(emu, oracle, base, 1)
     run_emu(emu, oracle, base, 2)
+
+
+def _emu_offsets(emu, oracle, base):
+    g = oracle.load(base)
+    stream = np.fromfile(base + ".offsets", dtype=np.uint8)
+    out = np.zeros(g.n + 1, dtype=np.uint64)
+    passes = C.c_int(0)
+    rc = emu.emu_decode_offsets(stream.ctypes.data, len(stream), g.g.contents.offset_coding, g.n, out.ctypes.data, C.byref(passes))
+    assert rc == 0
+    assert np.array_equal(out, g.offsets())
+    return passes.value
+
+
+def test_emulated_parallel_offsets_decode(emu, oracle, tmp_path):
+    assert _emu_offsets(emu, oracle, CNR) >= 1  # 331 195-byte gamma stream, 96-bit sub-ranges
+    off, succ, _ = graphs.copy_heavy(3000, seed=8)
+    for flags in (0, tools.OFFSETS_DELTA):
+        base = str(tmp_path / ("o%d" % flags))
+        tools.store_csr(base, off, succ, flags=flags)
+        _emu_offsets(emu, oracle, base)
+    # records of very different lengths: empty nodes (1-bit gaps) next to a 100 000-successor list (long gamma gaps)
+    deg = np.zeros(5000, dtype=np.int64)
+    deg[7] = 100000
+    deg[4000:4010] = 3
+    off2 = np.zeros(5001, dtype=np.int64)
+    np.cumsum(deg, out=off2[1:])
+    succ2 = np.concatenate([np.arange(0, 400000, 4, dtype=np.int32)] + [np.array([1, 5, 9], dtype=np.int32)] * 10)
+    base = str(tmp_path / "skew")
+    tools.store_csr(base, off2, succ2)
+    _emu_offsets(emu, oracle, base)

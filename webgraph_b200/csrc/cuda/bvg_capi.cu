@@ -7,6 +7,7 @@
 #include "bvg_format.hpp"
 #include "bvg_kernels.cuh"
 #include "bvg_long.cuh"
+#include "bvg_offsets.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -35,6 +36,22 @@ static void set_cuda_error(cudaError_t e, const char* what) {
     snprintf(t_cuda_msg, sizeof t_cuda_msg, "%s: %s", what, cudaGetErrorString(e));
     cudaGetLastError();
 }
+
+// BVG_TRACE=1 prints host-side phase timings of open to stderr (each phase synchronised).
+#include <chrono>
+struct Trace {
+    bool on;
+    cudaStream_t s;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(cudaStream_t st) : on(getenv("BVG_TRACE") != nullptr), s(st), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvg] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
 
@@ -186,6 +203,57 @@ static int device_exclusive_scan(cudaStream_t s, const int32_t* d_in, int64_t n,
     return BVG_OK;
 }
 
+// The .offsets stream decoded on the device (bvg_offsets.cuh): upload, byte-swap, speculate, fix until stable, scan, emit.
+// *d_full receives n+1 absolute bit offsets (device memory, cudaMalloc).
+static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t nbytes, int coding, int64_t n, uint64_t** d_full) {
+    if (coding != C_GAMMA && coding != C_DELTA) return BVG_EUNSUPPORTED;  // readOffset, BVGraph.java:631-637
+    const uint64_t nwords = ((nbytes + 3) / 4 + 8 + 3) & ~(uint64_t)3;
+    const uint64_t total_bits = nbytes * 8;
+    const int64_t nsub = std::max<int64_t>(1, (int64_t)((total_bits + OFF_SUB_BITS - 1) / OFF_SUB_BITS));
+    Tmp<uint32_t> words(s);
+    Tmp<OffSub> sa(s), sb(s);
+    Tmp<int> changed(s);
+    Tmp<int64_t> cbase(s);
+    Tmp<uint64_t> sbase(s);
+    CK(words.alloc((size_t)nwords));
+    CK(cudaMemsetAsync(words.p, 0, (size_t)nwords * 4, s));
+    if (nbytes) CK(cudaMemcpyAsync(words.p, stream, (size_t)nbytes, cudaMemcpyHostToDevice, s));
+    LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, words.p, nwords);
+    CK(sa.alloc((size_t)nsub));
+    CK(sb.alloc((size_t)nsub));
+    CK(changed.alloc(1));
+    LAUNCH(k_off_speculate, grid_for(nsub, 128), 128, 0, s, words.p, nwords, total_bits, coding, nsub, sa.p);
+    OffSub *in = sa.p, *out = sb.p;
+    for (int64_t pass = 0;; pass++) {
+        CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
+        LAUNCH(k_off_fix, grid_for(nsub, 128), 128, 0, s, words.p, nwords, total_bits, coding, nsub, in, out, changed.p);
+        int ch = 0;
+        CK(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::swap(in, out);
+        if (!ch) break;
+        if (pass > nsub + 2) return BVG_EIO;
+    }
+    std::vector<OffSub> h((size_t)nsub);
+    CK(cudaMemcpyAsync(h.data(), in, (size_t)nsub * sizeof(OffSub), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int64_t> cb((size_t)nsub);
+    std::vector<uint64_t> sbv((size_t)nsub);
+    int64_t c = 0;
+    uint64_t sum = 0;
+    for (int64_t j = 0; j < nsub; j++) { cb[(size_t)j] = c; sbv[(size_t)j] = sum; c += h[(size_t)j].count; sum += h[(size_t)j].sum; }
+    if (c < n + 1) return BVG_EIO;  // the stream ends before n+1 gaps (EOFException in the reference)
+    CK(cbase.alloc((size_t)nsub));
+    CK(sbase.alloc((size_t)nsub));
+    CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sbase.p, sbv.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMalloc((void**)d_full, ((size_t)n + 1) * 8));
+    LAUNCH(k_off_emit, grid_for(nsub, 128), 128, 0, s, words.p, nwords, total_bits, coding, nsub, in, cbase.p, sbase.p, n, *d_full);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));  // cb / sbv are host vectors
+    return BVG_OK;
+}
+
 // Index of the long records (bvg_long.cuh): list them, walk each once for sizes, lay out the arrays, walk again to fill
 // them, and list the per-scan work items.
 static int build_long_index(bvg_graph* g) {
@@ -315,19 +383,26 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     g->copied_ready = true;
-    return build_long_index(g);
+    { Trace t2(s); const int rl = build_long_index(g); t2.mark("  long index"); return rl; }
 }
 
 // Uploads the stream bytes + offsets of nodes [node_lo, node_hi] and builds the decode index.
-static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbytes, const uint64_t* offsets) {
+static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbytes, uint64_t* d_offsets_full, int64_t n_full) {
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    Trace tr(g->stream);
     g->nwords = ((nbytes + 3) / 4 + 8 + 3) & ~(uint64_t)3;  // >= 8 padding words, a whole number of 128-bit groups
     CK(cudaMalloc((void**)&g->d_words, g->nwords * 4));
     CK(cudaMemsetAsync(g->d_words, 0, g->nwords * 4, g->stream));
     if (nbytes) CK(cudaMemcpyAsync(g->d_words, bytes, nbytes, cudaMemcpyHostToDevice, g->stream));
     LAUNCH(k_bswap, grid_for((int64_t)g->nwords, 256), 256, 0, g->stream, g->d_words, g->nwords);
-    CK(cudaMalloc((void**)&g->d_offsets, ((size_t)nn + 1) * 8));
-    CK(cudaMemcpyAsync(g->d_offsets, offsets, ((size_t)nn + 1) * 8, cudaMemcpyHostToDevice, g->stream));
+    tr.mark("alloc + H2D stream + bswap");
+    if (g->node_lo == 0 && nn == n_full) g->d_offsets = d_offsets_full;  // whole graph: adopt the decoded array
+    else {
+        CK(cudaMalloc((void**)&g->d_offsets, ((size_t)nn + 1) * 8));
+        CK(cudaMemcpyAsync(g->d_offsets, d_offsets_full + g->node_lo, ((size_t)nn + 1) * 8, cudaMemcpyDeviceToDevice, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        cudaFree(d_offsets_full);
+    }
     CK(cudaMalloc((void**)&g->d_outdeg, std::max<size_t>((size_t)nn, 1) * 4));
     CK(cudaMalloc((void**)&g->d_ref, std::max<size_t>((size_t)nn, 1) * 4));
     CK(cudaMalloc((void**)&g->d_depth, std::max<size_t>((size_t)nn, 1) * 4));
@@ -336,6 +411,7 @@ static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbyte
     CK(cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
     int32_t* d_max = (int32_t*)(g->d_err + 1);  // [0] max depth, [1] max outdegree
     GraphDev gd = g->dev();
+    tr.mark("offsets slice + allocs");
     if (nn > 0) {
         if (g->def_codec) LAUNCH(k_header<true>, grid_for(nn, 256), 256, 0, g->stream, gd, g->d_outdeg, g->d_ref);
         else LAUNCH(k_header<false>, grid_for(nn, 256), 256, 0, g->stream, gd, g->d_outdeg, g->d_ref);
@@ -354,7 +430,10 @@ static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbyte
     g->max_outdeg = mx[1];
     const int e = fetch_error(g);
     if (e) return e;
-    return build_schedules(g);
+    tr.mark("header + scan + depth");
+    const int rs = build_schedules(g);
+    tr.mark("schedules + long index");
+    return rs;
 }
 
 static void destroy(bvg_graph* g) {
@@ -427,18 +506,24 @@ int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint
     p.nodes = nodes; p.arcs = arcs; p.window = window; p.maxref = maxref; p.minlen = minlen; p.zetak = zetak; p.flags = flags;
     rc = open_common(g, p, offset_type);
     if (rc) { destroy(g); return rc; }
-    std::vector<uint64_t> offs;
     const int oc = ((flags >> 20) & 0xF) ? (int)((flags >> 20) & 0xF) : C_GAMMA;
-    rc = decode_offsets_stream(offsets_stream, offsets_bytes, oc, nodes, offs);
-    if (rc) { destroy(g); return rc; }
-    if (offs[(size_t)nodes] > graph_bytes * 8) { destroy(g); return BVG_EIO; }
-    g->graph_bits_total = offs[(size_t)nodes];
+    Trace tr(g->stream);
+    uint64_t* d_full = nullptr;
+    rc = device_decode_offsets(g->stream, offsets_stream, offsets_bytes, oc, nodes, &d_full);
+    tr.mark("device: decode .offsets");
+    if (rc) { cudaFree(d_full); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     g->node_lo = shard_halo(g, from); g->node_hi = to;
-    const uint64_t byte_lo = (offs[(size_t)g->node_lo] >> 3) & ~(uint64_t)15;
-    const uint64_t byte_hi = std::min<uint64_t>(graph_bytes, (offs[(size_t)to] + 7) >> 3);
-    g->bit_base = byte_lo * 8; g->bit_end = offs[(size_t)to];
-    rc = build_device_state(g, graph + byte_lo, byte_hi - byte_lo, offs.data() + g->node_lo);
+    uint64_t o3[3];  // offsets of node_lo, to, nodes
+    if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&o3[1], d_full + to, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&o3[2], d_full + nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFree(d_full); destroy(g); return BVG_ECUDA; }
+    if (o3[2] > graph_bytes * 8) { cudaFree(d_full); destroy(g); return BVG_EIO; }
+    g->graph_bits_total = o3[2];
+    const uint64_t byte_lo = (o3[0] >> 3) & ~(uint64_t)15;
+    const uint64_t byte_hi = std::min<uint64_t>(graph_bytes, (o3[1] + 7) >> 3);
+    g->bit_base = byte_lo * 8; g->bit_end = o3[1];
+    rc = build_device_state(g, graph + byte_lo, byte_hi - byte_lo, d_full, nodes);
     if (rc) { destroy(g); return rc; }
     *out = g;
     return BVG_OK;
@@ -508,19 +593,23 @@ int bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, b
     if (rc) { destroy(g); return rc; }
     std::vector<uint8_t> ostream;
     if (!slurp_file(std::string(basename) + ".offsets", ostream)) { destroy(g); return BVG_EIO; }
-    std::vector<uint64_t> offs;
     const int oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
-    rc = decode_offsets_stream(ostream.data(), ostream.size(), oc, p.nodes, offs);
-    if (rc) { destroy(g); return rc; }
-    g->graph_bits_total = offs[(size_t)p.nodes];
+    uint64_t* d_full = nullptr;
+    rc = device_decode_offsets(g->stream, ostream.data(), ostream.size(), oc, p.nodes, &d_full);
+    if (rc) { cudaFree(d_full); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     g->node_lo = shard_halo(g, from); g->node_hi = to;
-    const uint64_t byte_lo = (offs[(size_t)g->node_lo] >> 3) & ~(uint64_t)15;
-    const uint64_t byte_hi = (offs[(size_t)to] + 7) >> 3;
-    g->bit_base = byte_lo * 8; g->bit_end = offs[(size_t)to];
+    uint64_t o3[3];
+    if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&o3[1], d_full + to, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&o3[2], d_full + p.nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFree(d_full); destroy(g); return BVG_ECUDA; }
+    g->graph_bits_total = o3[2];
+    const uint64_t byte_lo = (o3[0] >> 3) & ~(uint64_t)15;
+    const uint64_t byte_hi = (o3[1] + 7) >> 3;
+    g->bit_base = byte_lo * 8; g->bit_end = o3[1];
     std::vector<uint8_t> bytes;
-    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { destroy(g); return BVG_EIO; }
-    rc = build_device_state(g, bytes.data(), bytes.size(), offs.data() + g->node_lo);
+    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { cudaFree(d_full); destroy(g); return BVG_EIO; }
+    rc = build_device_state(g, bytes.data(), bytes.size(), d_full, p.nodes);
     if (rc) { destroy(g); return rc; }
     *out = g;
     return BVG_OK;
