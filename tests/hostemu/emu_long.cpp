@@ -5,6 +5,7 @@
 #define BVG_LONG_D 2
 #define BVG_LONG_SEG 3
 #define BVG_LONG_CHUNK 4
+#define BVG_LSPEC_BITS 80
 #include <algorithm>
 using std::min;
 using std::max;
@@ -67,6 +68,49 @@ extern "C" int emu_decode_long(const uint8_t* graph, uint64_t nbytes, const uint
     for (auto& m : meta) {
         if (def_codec) long_walk<true>(g, m, 1, cb_cum.data() + m.cb_off, cb_ppos.data() + m.cb_off, iv_cum.data() + m.iv_off, iv_left.data() + m.iv_off, seg_pos.data() + m.seg_off, seg_val.data() + m.seg_off);
         else long_walk<false>(g, m, 1, cb_cum.data() + m.cb_off, cb_ppos.data() + m.cb_off, iv_cum.data() + m.iv_off, iv_left.data() + m.iv_off, seg_pos.data() + m.seg_off, seg_val.data() + m.seg_off);
+    }
+    {   // the same sync points through the speculative sub-range path (80-bit sub-ranges): must be identical
+        std::vector<uint64_t> sp2(seg + 1, 0);
+        std::vector<int64_t> sv2(seg + 1, 0);
+        std::vector<SpecItem> items;
+        for (size_t l = 0; l < meta.size(); l++) {
+            const LongMeta& m = meta[l];
+            if (m.rc <= 0) continue;
+            const uint64_t end = offsets[m.x + 1];
+            for (uint64_t lo = m.resid_pos; lo < end; lo += LSPEC_BITS) {
+                SpecItem it{};
+                it.lo = lo; it.hi = std::min<uint64_t>(lo + LSPEC_BITS, end); it.l = (int32_t)l; it.first = lo == m.resid_pos;
+                items.push_back(it);
+            }
+        }
+        for (auto& it : items) { if (def_codec) lspec_speculate_one<true>(g, it); else lspec_speculate_one<false>(g, it); }
+        std::vector<SpecItem> tmp2(items.size());
+        for (int pass = 0;; pass++) {
+            int changed = 0;
+            for (size_t j = 0; j < items.size(); j++) { if (def_codec) lspec_fix_one<true>(g, (int64_t)j, items.data(), tmp2.data(), &changed); else lspec_fix_one<false>(g, (int64_t)j, items.data(), tmp2.data(), &changed); }
+            items.swap(tmp2);
+            if (!changed) break;
+            if (pass > (int)items.size() + 2) return -101;
+        }
+        std::vector<int64_t> v0(meta.size(), 0);
+        int64_t cbase = 0, sbase = 0;
+        for (size_t j = 0; j < items.size(); j++) {
+            const SpecItem& it = items[j];
+            if (it.first) { cbase = 0; sbase = 0; }
+            if (def_codec) lspec_emit_one<true>(g, it, meta[it.l], cbase, sbase, v0.data(), v0.data(), sp2.data(), sv2.data());
+            else lspec_emit_one<false>(g, it, meta[it.l], cbase, sbase, v0.data(), v0.data(), sp2.data(), sv2.data());
+            cbase += it.count; sbase += it.sum;
+            if ((j + 1 == items.size() || items[j + 1].first) && cbase != meta[it.l].rc) return -102;
+        }
+        for (int64_t k = 0; k < seg; k++) {
+            if (sp2[k] != seg_pos[k]) return -103;
+            if (sv2[k] != seg_val[k] && !(seg_val[k] == 0 && sp2[k] == seg_pos[k] && false)) {
+                // seg_val of a record's first segment is unused (both paths leave their initial 0 there)
+                bool first_of_record = false;
+                for (auto& m : meta) if (m.seg_off == k) first_of_record = true;
+                if (!first_of_record) return -104;
+            }
+        }
     }
     LongIndex li{ meta.data(), cb_cum.data(), cb_ppos.data(), iv_cum.data(), iv_left.data(), seg_pos.data(), seg_val.data() };
     FlatRows rm{ out, rowoff.data() };

@@ -307,8 +307,70 @@ static int build_long_index(bvg_graph* g) {
     CK(cudaMalloc((void**)&g->d_iv_left, (size_t)std::max<int64_t>(iv, 1) * 4));
     CK(cudaMalloc((void**)&g->d_seg_pos, (size_t)std::max<int64_t>(seg, 1) * 8));
     CK(cudaMalloc((void**)&g->d_seg_val, (size_t)std::max<int64_t>(seg, 1) * 8));
-    if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val);
-    else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val);
+    // copy blocks and intervals: one short walk per record; residual sync points: speculative sub-ranges (bvg_long.cuh)
+    if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
+    else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
+    {
+        std::vector<SpecItem> items;
+        for (int64_t l = 0; l < nl; l++) {
+            const LongMeta& m = meta[(size_t)l];
+            if (m.rc <= 0) continue;
+            for (uint64_t lo = m.resid_pos; lo < m.rec_end; lo += (uint64_t)LSPEC_BITS) {
+                SpecItem it{};
+                it.lo = lo; it.hi = std::min<uint64_t>(lo + (uint64_t)LSPEC_BITS, m.rec_end); it.l = (int32_t)l; it.first = lo == m.resid_pos ? 1 : 0;
+                items.push_back(it);
+            }
+        }
+        const int64_t ni = (int64_t)items.size();
+        if (ni > 0) {
+            Tmp<SpecItem> ia(s), ib(s);
+            Tmp<int> changed(s);
+            Tmp<int64_t> v0(s), cbase(s), sbase(s);
+            CK(ia.alloc((size_t)ni));
+            CK(ib.alloc((size_t)ni));
+            CK(changed.alloc(1));
+            CK(v0.alloc((size_t)nl));
+            CK(cudaMemcpyAsync(ia.p, items.data(), (size_t)ni * sizeof(SpecItem), cudaMemcpyHostToDevice, s));
+            if (g->def_codec) {
+                LAUNCH(k_lspec_first<true>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
+                LAUNCH(k_lspec_speculate<true>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
+            } else {
+                LAUNCH(k_lspec_first<false>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
+                LAUNCH(k_lspec_speculate<false>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
+            }
+            SpecItem *in = ia.p, *out = ib.p;
+            for (int64_t pass = 0;; pass++) {
+                CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
+                if (g->def_codec) LAUNCH(k_lspec_fix<true>, grid_for(ni, 128), 128, 0, s, gd, in, out, ni, changed.p);
+                else LAUNCH(k_lspec_fix<false>, grid_for(ni, 128), 128, 0, s, gd, in, out, ni, changed.p);
+                int ch = 0;
+                CK(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                std::swap(in, out);
+                if (!ch) break;
+                if (pass > ni + 2) return BVG_EIO;
+            }
+            CK(cudaMemcpyAsync(items.data(), in, (size_t)ni * sizeof(SpecItem), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            std::vector<int64_t> cb((size_t)ni), sb((size_t)ni);
+            int64_t c = 0, sum = 0;
+            for (int64_t j = 0; j < ni; j++) {
+                if (items[(size_t)j].first) { c = 0; sum = 0; }
+                cb[(size_t)j] = c; sb[(size_t)j] = sum;
+                c += items[(size_t)j].count; sum += items[(size_t)j].sum;
+                const bool last = j + 1 == ni || items[(size_t)j + 1].first;
+                if (last && c != meta[(size_t)items[(size_t)j].l].rc) return BVG_EFORMAT;  // the record does not hold rc residuals
+            }
+            CK(cbase.alloc((size_t)ni));
+            CK(sbase.alloc((size_t)ni));
+            CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)ni * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(sbase.p, sb.data(), (size_t)ni * 8, cudaMemcpyHostToDevice, s));
+            if (g->def_codec) LAUNCH(k_lspec_emit<true>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val);
+            else LAUNCH(k_lspec_emit<false>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(s));
+        }
+    }
     std::vector<LongItem> merged;
     g->merge_item_start.assign((size_t)g->max_depth + 1, 0);
     for (int32_t lv = 1; lv <= g->max_depth; lv++) {

@@ -41,6 +41,8 @@ struct LongMeta {
     int64_t seg_off;      // seg_pos / seg_val, ceil(rc / LONG_SEG) entries
     int64_t tmp_off;      // per-scan temp: residuals at [tmp_off, +rc), extras at [tmp_off + d, +d-copied)
     uint64_t after_header;  // bit position (relative to word 0) right after outdegree + reference
+    uint64_t resid_pos;     // bit position of the first residual code
+    uint64_t rec_end;       // bit position one past the record (= end of the residual section)
 };
 
 struct LongIndex {
@@ -122,7 +124,8 @@ __device__ void long_walk(const GraphDev& g, LongMeta& m, int pass, int32_t* cb_
     m.ilen = (int32_t)ilen;
     const int64_t rc = extra - ilen;
     m.rc = (int32_t)(rc > 0 ? rc : 0);
-    if (!pass || rc <= 0) return;
+    m.resid_pos = b.pos();
+    if (!pass || rc <= 0 || !seg_pos) return;
     // residual sync points (the one sequential pass over this record's residuals, paid once at open)
     int64_t v = 0;
     for (int64_t i = 0; i < rc; i++) {
@@ -130,6 +133,128 @@ __device__ void long_walk(const GraphDev& g, LongMeta& m, int pass, int32_t* cb_
         if (i == 0) v = (int64_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));
         else v += (int64_t)Rd<DEF>::resid(b, c) + 1;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sync points without a sequential pass.  Walking the residuals of every long record on one thread each costs
+// ~10^6 dependent code reads for the largest record of the benchmark graph (120 ms at open).  The residual section of a
+// long record is a run of zeta_k codes between two known bit positions, so it is cut into LSPEC_BITS sub-ranges that
+// are entered speculatively and proven exactly as bvg_offsets.cuh does for the .offsets stream:
+// speculate (count, sum of gap+1, exit) -> fix against the previous sub-range's exit until nothing moves ->
+// per-record scan -> emit a sync point wherever the ordinal is a multiple of LONG_SEG.
+// ---------------------------------------------------------------------------------------------------
+#ifndef BVG_LSPEC_BITS
+#define BVG_LSPEC_BITS 4096
+#endif
+constexpr int64_t LSPEC_BITS = BVG_LSPEC_BITS;
+
+struct SpecItem {
+    uint64_t lo, hi;      // bit range of the sub-range (hi of a record's last item = end of the record)
+    uint64_t entry, exit; // proven entry / exit of the chain
+    int64_t count;        // codes on the chain inside the sub-range
+    int64_t sum;          // sum of (gap + 1) of those codes, the record's very first code excluded
+    int32_t l;            // long record
+    int32_t first;        // 1 = first sub-range of its record: entry is exact, first code is the long residual
+};
+
+template <bool DEF>
+__device__ inline void lspec_walk(const GraphDev& g, uint64_t pos, uint64_t hi, bool skip_first, uint64_t& exit, int64_t& count, int64_t& sum) {
+    BitBuf b;
+    b.w = g.words; b.maxw = g.nwords - 3;
+    b.seek(pos);
+    count = 0; sum = 0;
+    while (b.pos() < hi) {
+        const uint64_t v = Rd<DEF>::resid(b, g.c);
+        if (!(skip_first && count == 0)) sum += (int64_t)v + 1;
+        count++;
+    }
+    exit = b.pos();
+}
+
+template <bool DEF>
+__device__ inline void lspec_speculate_one(const GraphDev& g, SpecItem& it) {
+    it.entry = it.lo;
+    lspec_walk<DEF>(g, it.lo, it.hi, it.first != 0, it.exit, it.count, it.sum);
+}
+
+template <bool DEF>
+__device__ inline void lspec_fix_one(const GraphDev& g, int64_t j, const SpecItem* __restrict__ in, SpecItem* __restrict__ out, int* changed) {
+    SpecItem s = in[j];
+    if (!s.first) {
+        const uint64_t t = in[j - 1].exit;
+        if (t != s.entry) {
+            BitBuf a, b;
+            a.w = b.w = g.words; a.maxw = b.maxw = g.nwords - 3;
+            a.seek(t); b.seek(s.entry);
+            int64_t ca = 0, cb = 0, sa = 0, sb = 0;
+            while (a.pos() != b.pos() && a.pos() < s.hi && b.pos() < s.hi) {
+                if (a.pos() < b.pos()) { sa += (int64_t)Rd<DEF>::resid(a, g.c) + 1; ca++; }
+                else { sb += (int64_t)Rd<DEF>::resid(b, g.c) + 1; cb++; }
+            }
+            if (a.pos() == b.pos()) { s.count += ca - cb; s.sum += sa - sb; }
+            else {
+                while (a.pos() < s.hi) { sa += (int64_t)Rd<DEF>::resid(a, g.c) + 1; ca++; }
+                s.count = ca; s.sum = sa;
+                if (a.pos() != s.exit) { s.exit = a.pos(); *changed = 1; }
+            }
+            s.entry = t;
+        }
+    }
+    out[j] = s;
+}
+
+// cbase: residual ordinal of the item's first code; sbase: sum of (gap+1) of the record's codes before it.
+template <bool DEF>
+__device__ inline void lspec_emit_one(const GraphDev& g, const SpecItem& it, const LongMeta& m, int64_t cbase, int64_t sbase,
+                                      const int64_t* __restrict__ v0, int64_t* __restrict__ v0_out,
+                                      uint64_t* __restrict__ seg_pos, int64_t* __restrict__ seg_val) {
+    BitBuf b;
+    b.w = g.words; b.maxw = g.nwords - 3;
+    b.seek(it.entry);
+    int64_t ord = cbase;
+    int64_t v = it.first ? 0 : v0[it.l] + sbase;
+    while (b.pos() < it.hi && ord < m.rc) {
+        if (ord % LONG_SEG == 0) { seg_pos[m.seg_off + ord / LONG_SEG] = b.pos(); seg_val[m.seg_off + ord / LONG_SEG] = v; }
+        const uint64_t code = Rd<DEF>::resid(b, g.c);
+        if (ord == 0) { v = (int64_t)(int32_t)((int64_t)m.x + nat2int(code)); if (v0_out) v0_out[it.l] = v; }
+        else v += (int64_t)code + 1;
+        ord++;
+    }
+}
+
+template <bool DEF>
+__global__ void k_lspec_speculate(GraphDev g, SpecItem* __restrict__ items, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { SpecItem it = items[j]; lspec_speculate_one<DEF>(g, it); items[j] = it; }
+}
+
+template <bool DEF>
+__global__ void k_lspec_fix(GraphDev g, const SpecItem* __restrict__ in, SpecItem* __restrict__ out, int64_t n, int* __restrict__ changed) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) lspec_fix_one<DEF>(g, j, in, out, changed);
+}
+
+// The first residual of every record (its value anchors all the others): read by the record's first item.
+template <bool DEF>
+__global__ void k_lspec_first(GraphDev g, const LongMeta* __restrict__ meta, int32_t nlong, int64_t* __restrict__ v0) {
+    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlong) return;
+    const LongMeta m = meta[l];
+    if (m.rc <= 0) { v0[l] = 0; return; }
+    BitBuf b;
+    b.w = g.words; b.maxw = g.nwords - 3;
+    b.seek(m.resid_pos);
+    v0[l] = (int64_t)(int32_t)((int64_t)m.x + nat2int(Rd<DEF>::resid(b, g.c)));
+}
+
+template <bool DEF>
+__global__ void k_lspec_emit(GraphDev g, const SpecItem* __restrict__ items, int64_t n, const LongMeta* __restrict__ meta,
+                             const int64_t* __restrict__ cbase, const int64_t* __restrict__ sbase, const int64_t* __restrict__ v0,
+                             uint64_t* __restrict__ seg_pos, int64_t* __restrict__ seg_val) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const SpecItem it = items[j];
+    lspec_emit_one<DEF>(g, it, meta[it.l], cbase[j], sbase[j], v0, nullptr, seg_pos, seg_val);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -220,6 +345,7 @@ __global__ void k_long_count(GraphDev g, const int32_t* __restrict__ long_nodes,
     m.x = long_nodes[l];
     m.level = g.depth[m.x - g.node_lo];
     m.pad_ = 0;
+    m.rec_end = g.offsets[m.x - g.node_lo + 1] - g.bit_base;
     long_walk<DEF>(g, m, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     m.cb_off = m.iv_off = m.seg_off = m.tmp_off = 0;
     meta[l] = m;
