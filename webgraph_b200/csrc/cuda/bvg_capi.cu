@@ -247,7 +247,7 @@ static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t
     CK(sbase.alloc((size_t)nsub));
     CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(sbase.p, sbv.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMalloc((void**)d_full, ((size_t)n + 1) * 8));
+    CK(cudaMallocAsync((void**)d_full, ((size_t)n + 1) * 8, s));
     LAUNCH(k_off_emit, grid_for(nsub, 128), 128, 0, s, words.p, nwords, total_bits, coding, nsub, in, cbase.p, sbase.p, n, *d_full);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // cb / sbv are host vectors
@@ -274,10 +274,10 @@ static int build_long_index(bvg_graph* g) {
     CK(cudaMemcpyAsync(&nl, pos.p + nn, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (nl == 0) return BVG_OK;
-    CK(cudaMalloc((void**)&g->d_long_nodes, (size_t)nl * 4));
+    CK(cudaMallocAsync((void**)&g->d_long_nodes, (size_t)nl * 4, g->stream));
     long_nodes.p = g->d_long_nodes;
     LAUNCH(k_long_compact, grid_for(nn, 256), 256, 0, s, flags.p, pos.p, nn, g->node_lo, long_nodes.p);
-    CK(cudaMalloc((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta)));
+    CK(cudaMallocAsync((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta), g->stream));
     if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
     else LAUNCH(k_long_count<false>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
     std::vector<LongMeta> meta((size_t)nl);
@@ -301,12 +301,12 @@ static int build_long_index(bvg_graph* g) {
         if (m.copied > 0 && m.level >= 1) for (int32_t q = 0; q * LONG_CHUNK < m.d; q++) it_m[(size_t)m.level].push_back(LongItem{ (int32_t)l, q });
     }
     CK(cudaMemcpyAsync(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), cudaMemcpyHostToDevice, s));
-    CK(cudaMalloc((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_iv_cum, (size_t)std::max<int64_t>(iv, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_iv_left, (size_t)std::max<int64_t>(iv, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_seg_pos, (size_t)std::max<int64_t>(seg, 1) * 8));
-    CK(cudaMalloc((void**)&g->d_seg_val, (size_t)std::max<int64_t>(seg, 1) * 8));
+    CK(cudaMallocAsync((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_iv_cum, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_iv_left, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_seg_pos, (size_t)std::max<int64_t>(seg, 1) * 8, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_seg_val, (size_t)std::max<int64_t>(seg, 1) * 8, g->stream));
     // copy blocks and intervals: one short walk per record; residual sync points: speculative sub-ranges (bvg_long.cuh)
     if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
     else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
@@ -379,14 +379,14 @@ static int build_long_index(bvg_graph* g) {
     }
     g->merge_item_start[(size_t)g->max_depth] = (int64_t)merged.size();
     auto upload = [&](const std::vector<LongItem>& v, LongItem** dst) -> cudaError_t {
-        cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(LongItem));
+        cudaError_t e = cudaMallocAsync((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(LongItem), s);
         if (e != cudaSuccess) return e;
         return v.empty() ? cudaSuccess : cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(LongItem), cudaMemcpyHostToDevice, s);
     };
     CK(upload(it_r, &g->d_items_resid));
     CK(upload(it_x, &g->d_items_extras));
     CK(upload(merged, &g->d_items_merge));
-    CK(cudaMalloc((void**)&g->d_items_fold, std::max<size_t>(it_f.size(), 1) * sizeof(RowChunk)));
+    CK(cudaMallocAsync((void**)&g->d_items_fold, std::max<size_t>(it_f.size(), 1) * sizeof(RowChunk), g->stream));
     if (!it_f.empty()) CK(cudaMemcpyAsync(g->d_items_fold, it_f.data(), it_f.size() * sizeof(RowChunk), cudaMemcpyHostToDevice, s));
     g->n_items_fold = (int64_t)it_f.size();
     g->n_items_resid = (int64_t)it_r.size();
@@ -406,7 +406,7 @@ static int build_schedules(bvg_graph* g) {
     g->level_start.clear();
     if (nn == 0) return BVG_OK;
     cudaStream_t s = g->stream;
-    CK(cudaMalloc((void**)&g->d_is_parent, (size_t)nn));
+    CK(cudaMallocAsync((void**)&g->d_is_parent, (size_t)nn, g->stream));
     CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
     LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
@@ -419,7 +419,7 @@ static int build_schedules(bvg_graph* g) {
     CK(bins.alloc((size_t)(nb_e + nb_m)));
     CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
     GraphDev gd = g->dev();
-    CK(cudaMalloc((void**)&g->d_copied, (size_t)nn * 4));
+    CK(cudaMallocAsync((void**)&g->d_copied, (size_t)nn * 4, g->stream));
     if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
     else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
@@ -438,8 +438,8 @@ static int build_schedules(bvg_graph* g) {
     }
     g->level_start[(size_t)levels] = run;
     CK(cudaMemcpyAsync(bins.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMalloc((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4));
+    CK(cudaMallocAsync((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4, g->stream));
     LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p, g->node_lo, g->d_order_e);
     LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e, g->node_lo, g->d_order_m);
     CK(cudaGetLastError());
@@ -453,23 +453,23 @@ static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbyte
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
     Trace tr(g->stream);
     g->nwords = ((nbytes + 3) / 4 + 8 + 3) & ~(uint64_t)3;  // >= 8 padding words, a whole number of 128-bit groups
-    CK(cudaMalloc((void**)&g->d_words, g->nwords * 4));
+    CK(cudaMallocAsync((void**)&g->d_words, g->nwords * 4, g->stream));
     CK(cudaMemsetAsync(g->d_words, 0, g->nwords * 4, g->stream));
     if (nbytes) CK(cudaMemcpyAsync(g->d_words, bytes, nbytes, cudaMemcpyHostToDevice, g->stream));
     LAUNCH(k_bswap, grid_for((int64_t)g->nwords, 256), 256, 0, g->stream, g->d_words, g->nwords);
     tr.mark("alloc + H2D stream + bswap");
     if (g->node_lo == 0 && nn == n_full) g->d_offsets = d_offsets_full;  // whole graph: adopt the decoded array
     else {
-        CK(cudaMalloc((void**)&g->d_offsets, ((size_t)nn + 1) * 8));
+        CK(cudaMallocAsync((void**)&g->d_offsets, ((size_t)nn + 1) * 8, g->stream));
         CK(cudaMemcpyAsync(g->d_offsets, d_offsets_full + g->node_lo, ((size_t)nn + 1) * 8, cudaMemcpyDeviceToDevice, g->stream));
         CK(cudaStreamSynchronize(g->stream));
-        cudaFree(d_offsets_full);
+        cudaFreeAsync(d_offsets_full, g->stream);
     }
-    CK(cudaMalloc((void**)&g->d_outdeg, std::max<size_t>((size_t)nn, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_ref, std::max<size_t>((size_t)nn, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_depth, std::max<size_t>((size_t)nn, 1) * 4));
-    CK(cudaMalloc((void**)&g->d_rowoff, ((size_t)nn + 1) * 8));
-    CK(cudaMalloc((void**)&g->d_err, sizeof(ErrWord) + 2 * sizeof(int32_t)));
+    CK(cudaMallocAsync((void**)&g->d_outdeg, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_ref, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_depth, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_rowoff, ((size_t)nn + 1) * 8, g->stream));
+    CK(cudaMallocAsync((void**)&g->d_err, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
     CK(cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
     int32_t* d_max = (int32_t*)(g->d_err + 1);  // [0] max depth, [1] max outdegree
     GraphDev gd = g->dev();
@@ -501,11 +501,14 @@ static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbyte
 static void destroy(bvg_graph* g) {
     if (!g) return;
     DeviceGuard dg(g->device);
-    cudaFree(g->d_words); cudaFree(g->d_offsets); cudaFree(g->d_outdeg); cudaFree(g->d_ref); cudaFree(g->d_depth);
-    cudaFree(g->d_rowoff); cudaFree(g->d_err); cudaFree(g->d_halo_lists); cudaFree(g->d_halo_off);
-    cudaFree(g->d_order_e); cudaFree(g->d_order_m); cudaFree(g->d_is_parent); cudaFree(g->d_long_nodes); cudaFree(g->d_copied);
-    cudaFree(g->d_long_meta); cudaFree(g->d_cb_cum); cudaFree(g->d_cb_ppos); cudaFree(g->d_iv_cum); cudaFree(g->d_iv_left);
-    cudaFree(g->d_seg_pos); cudaFree(g->d_seg_val); cudaFree(g->d_items_resid); cudaFree(g->d_items_extras); cudaFree(g->d_items_merge); cudaFree(g->d_items_fold);
+    // graph memory comes from the device's stream-ordered pool (kept warm): a later open reuses it without going back
+    // to the driver, which is what makes open-scan-close cycles cheap
+    void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
+                     g->d_order_e, g->d_order_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
+                     g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_items_resid, g->d_items_extras, g->d_items_merge,
+                     g->d_items_fold };
+    for (void* p : ptrs) if (p) cudaFreeAsync(p, g->stream);
+    cudaStreamSynchronize(g->stream);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
     delete g;
@@ -573,14 +576,14 @@ int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint
     uint64_t* d_full = nullptr;
     rc = device_decode_offsets(g->stream, offsets_stream, offsets_bytes, oc, nodes, &d_full);
     tr.mark("device: decode .offsets");
-    if (rc) { cudaFree(d_full); destroy(g); return rc; }
+    if (rc) { cudaFreeAsync(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     g->node_lo = shard_halo(g, from); g->node_hi = to;
     uint64_t o3[3];  // offsets of node_lo, to, nodes
     if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
         cudaMemcpy(&o3[1], d_full + to, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(&o3[2], d_full + nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFree(d_full); destroy(g); return BVG_ECUDA; }
-    if (o3[2] > graph_bytes * 8) { cudaFree(d_full); destroy(g); return BVG_EIO; }
+        cudaMemcpy(&o3[2], d_full + nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_ECUDA; }
+    if (o3[2] > graph_bytes * 8) { cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_EIO; }
     g->graph_bits_total = o3[2];
     const uint64_t byte_lo = (o3[0] >> 3) & ~(uint64_t)15;
     const uint64_t byte_hi = std::min<uint64_t>(graph_bytes, (o3[1] + 7) >> 3);
@@ -658,19 +661,19 @@ int bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, b
     const int oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
     uint64_t* d_full = nullptr;
     rc = device_decode_offsets(g->stream, ostream.data(), ostream.size(), oc, p.nodes, &d_full);
-    if (rc) { cudaFree(d_full); destroy(g); return rc; }
+    if (rc) { cudaFreeAsync(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     g->node_lo = shard_halo(g, from); g->node_hi = to;
     uint64_t o3[3];
     if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
         cudaMemcpy(&o3[1], d_full + to, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(&o3[2], d_full + p.nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFree(d_full); destroy(g); return BVG_ECUDA; }
+        cudaMemcpy(&o3[2], d_full + p.nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_ECUDA; }
     g->graph_bits_total = o3[2];
     const uint64_t byte_lo = (o3[0] >> 3) & ~(uint64_t)15;
     const uint64_t byte_hi = (o3[1] + 7) >> 3;
     g->bit_base = byte_lo * 8; g->bit_end = o3[1];
     std::vector<uint8_t> bytes;
-    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { cudaFree(d_full); destroy(g); return BVG_EIO; }
+    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_EIO; }
     rc = build_device_state(g, bytes.data(), bytes.size(), d_full, p.nodes);
     if (rc) { destroy(g); return rc; }
     *out = g;
@@ -1182,13 +1185,13 @@ int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32
     if (on_device) { CK(cudaMemcpyAsync(&total, off + count, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
     else total = off[count];
     if (count + 1 > g->halo_off_cap) {
-        cudaFree(g->d_halo_off); g->d_halo_off = nullptr; g->halo_off_cap = 0;
-        CK(cudaMalloc((void**)&g->d_halo_off, ((size_t)count + 1) * 8));
+        cudaFreeAsync(g->d_halo_off, g->stream); g->d_halo_off = nullptr; g->halo_off_cap = 0;
+        CK(cudaMallocAsync((void**)&g->d_halo_off, ((size_t)count + 1) * 8, g->stream));
         g->halo_off_cap = count + 1;
     }
     if (total > g->halo_lists_cap) {
-        cudaFree(g->d_halo_lists); g->d_halo_lists = nullptr; g->halo_lists_cap = 0;
-        CK(cudaMalloc((void**)&g->d_halo_lists, (size_t)total * 2 * 4));
+        cudaFreeAsync(g->d_halo_lists, g->stream); g->d_halo_lists = nullptr; g->halo_lists_cap = 0;
+        CK(cudaMallocAsync((void**)&g->d_halo_lists, (size_t)total * 2 * 4, g->stream));
         g->halo_lists_cap = total * 2;
     }
     CK(cudaMemcpyAsync(g->d_halo_off, off, ((size_t)count + 1) * 8, kind, s));
