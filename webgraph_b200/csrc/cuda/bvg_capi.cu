@@ -406,6 +406,7 @@ static int build_schedules(bvg_graph* g) {
     g->level_start.clear();
     if (nn == 0) return BVG_OK;
     cudaStream_t s = g->stream;
+    Trace tr(s);
     CK(cudaMallocAsync((void**)&g->d_is_parent, (size_t)nn, g->stream));
     CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
     LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
@@ -422,11 +423,13 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaMallocAsync((void**)&g->d_copied, (size_t)nn * 4, g->stream));
     if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
     else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
+    tr.mark("  sched: parents + keys");
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e);
     std::vector<int32_t> h((size_t)(nb_e + nb_m));
     CK(cudaMemcpyAsync(h.data(), bins.p, h.size() * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    tr.mark("  sched: histograms");
     int64_t run = 0;
     for (int64_t i = 0; i < nb_e; i++) { const int32_t c = h[(size_t)i]; h[(size_t)i] = (int32_t)run; run += c; }
     g->order_e_count = run;
@@ -444,6 +447,7 @@ static int build_schedules(bvg_graph* g) {
     LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e, g->node_lo, g->d_order_m);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
+    tr.mark("  sched: scatter");
     g->copied_ready = true;
     { Trace t2(s); const int rl = build_long_index(g); t2.mark("  long index"); return rl; }
 }
