@@ -79,6 +79,8 @@ struct bvg_graph {
     int32_t max_depth = 0, max_outdeg = 0;
     // length-bucketed schedules (k_order_keys): extras order over all nodes with successors, merge order level-major
     int32_t *d_order_e = nullptr, *d_order_m = nullptr;
+    ExtraRec* d_rec_e = nullptr;
+    MergeRec* d_rec_m = nullptr;
     int64_t order_e_count = 0;
     std::vector<int64_t> level_start;  // merge schedule: nodes of chain level l+1 are order_m[level_start[l] .. level_start[l+1])
     uint8_t* d_is_parent = nullptr;    // nodes some other node copies from (k_mark_parents)
@@ -414,15 +416,19 @@ static int build_schedules(bvg_graph* g) {
     const int64_t nchunks = (nn + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG;
     const int64_t per_level = nchunks * 2 * ORDER_BUCKETS;  // chunk x (parent | not) x half-octave bucket
     const int64_t nb_e = nchunks * 2 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
-    Tmp<int32_t> key_e(s), key_m(s), bins(s);
+    Tmp<int32_t> key_e(s), key_m(s), bins(s), bcs(s);
+    Tmp<uint64_t> epos(s), bpos(s);
     CK(key_e.alloc((size_t)nn));
     CK(key_m.alloc((size_t)nn));
+    CK(bcs.alloc((size_t)nn));
+    CK(epos.alloc((size_t)nn));
+    CK(bpos.alloc((size_t)nn));
     CK(bins.alloc((size_t)(nb_e + nb_m)));
     CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
     GraphDev gd = g->dev();
     CK(cudaMallocAsync((void**)&g->d_copied, (size_t)nn * 4, g->stream));
-    if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
-    else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied);
+    if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
+    else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
     tr.mark("  sched: parents + keys");
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e);
@@ -443,8 +449,10 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaMemcpyAsync(bins.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMallocAsync((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4, g->stream));
     CK(cudaMallocAsync((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4, g->stream));
-    LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p, g->node_lo, g->d_order_e);
-    LAUNCH(k_key_scatter, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e, g->node_lo, g->d_order_m);
+    CK(cudaMallocAsync((void**)&g->d_rec_e, std::max<size_t>((size_t)g->order_e_count, 1) * sizeof(ExtraRec), g->stream));
+    CK(cudaMallocAsync((void**)&g->d_rec_m, std::max<size_t>((size_t)run, 1) * sizeof(MergeRec), g->stream));
+    LAUNCH(k_key_scatter_recs, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, nn, bins.p, bins.p + nb_e, g->d_is_parent, g->d_copied,
+           epos.p, bpos.p, bcs.p, g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     tr.mark("  sched: scatter");
@@ -508,7 +516,7 @@ static void destroy(bvg_graph* g) {
     // graph memory comes from the device's stream-ordered pool (kept warm): a later open reuses it without going back
     // to the driver, which is what makes open-scan-close cycles cheap
     void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
-                     g->d_order_e, g->d_order_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
+                     g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
                      g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_items_resid, g->d_items_extras, g->d_items_merge,
                      g->d_items_fold };
     for (void* p : ptrs) if (p) cudaFreeAsync(p, g->stream);
@@ -767,11 +775,14 @@ struct HaloPlan {
 static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from, RowMap& rm, HaloPlan& hp) {
     cudaStream_t s = g->stream;
     GraphDev gd = g->dev();
-    rm.out = d_out; rm.out_base = row_from; rm.from = from; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = from;
+    rm.out = d_out; rm.out_base = row_from; rm.from = from; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = from; rm.halo_base = row_from;
     hp.lo = from;
     if (g->max_depth > 0 && from > g->node_lo) {
         if (g->halo_count > 0 && from == g->ext_from) {  // lists imported from the previous shard
             rm.halo = g->d_halo_lists; rm.halo_off = g->d_halo_off; rm.halo_lo = from - g->halo_count;
+            int64_t hb, dummy;
+            { const int rc = fetch_rowoff(g, rm.halo_lo, from, &hb, &dummy); if (rc) return rc; }
+            rm.halo_base = hb;
         } else {  // re-decode the halo, as BVGraphNodeIterator's ctor re-reads the window (BVGraph.java:1173-1183)
             const int64_t reach = std::min<int64_t>((int64_t)to - from, (int64_t)g->window * g->max_depth);
             Tmp<int32_t> hs(s);
@@ -788,7 +799,7 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
                 CK(hp.halo.alloc((size_t)(rb - ra)));
                 CK(hp.halo_off.alloc((size_t)(from - h) + 1));
                 LAUNCH(k_rel_offsets, grid_for((int64_t)from - h + 1, 128), 128, 0, s, g->d_rowoff + (h - g->node_lo), (int64_t)from - h, hp.halo_off.p);
-                rm.halo = hp.halo.p; rm.halo_off = hp.halo_off.p; rm.halo_lo = h;
+                rm.halo = hp.halo.p; rm.halo_off = hp.halo_off.p; rm.halo_lo = h; rm.halo_base = ra;
                 hp.lo = h;
             }
         }
@@ -892,8 +903,8 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
     const unsigned grid = (unsigned)(sms * SCAN_BLOCKS_PER_SM), grid_m = grid;
-    if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
-    else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, from, rm, g->d_is_parent, d_result);
+    if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
+    else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     Tmp<int32_t> long_tmp(s);
     LongDst ld{ nullptr };
     const LongIndex li = g->long_index();
@@ -908,8 +919,8 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
         const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
         if (c > 0) {
             const unsigned gm = (unsigned)std::min<int64_t>(grid_m, (c + 127) / 128);
-            if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_order_m + a, c, lo, to, from, rm, g->d_is_parent, d_result);
-            else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_order_m + a, c, lo, to, from, rm, g->d_is_parent, d_result);
+            if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
+            else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }
         if (g->nlong) {
             const int64_t ma = g->merge_item_start[(size_t)level - 1], mc = g->merge_item_start[(size_t)level] - ma;

@@ -363,10 +363,31 @@ struct ExtrasWalk {
         }
         if (!ok) return;
         copied = (int32_t)cp;
-        int64_t extra = (int64_t)d - cp;
-        nout = (int32_t)extra;
+        nout = d - copied;
+        sections(g);
+    }
+
+    // Entry from a schedule record (bvg_kernels.cuh, ExtraRec): outdegree, reference and block list were parsed at
+    // open; the cursor starts at the extras section and the row pointer the caller passes is already past the copied part.
+    __device__ __forceinline__ void header_rec(const GraphDev& g, int32_t x_, int32_t d_, int32_t nout_, uint64_t pos, bool active) {
+        x = x_; d = 0; copied = 0; ic = 0; rc = 0; nout = 0; err = 0;
+        if (!active) return;
+        d = d_;
+        nout = nout_;
+        b.w = g.words; b.maxw = g.nwords - 3;
+        b.seek(pos);
+        ib.w = g.words; ib.maxw = g.nwords - 3; ib.pos = 0;
+        sections(g);
+    }
+
+    // interval section located, residual count (:1076-1096)
+    __device__ __forceinline__ void sections(const GraphDev& g) {
+        const Codec& c = g.c;
+        const uint64_t limit = g.bit_end - g.bit_base;
+        int64_t extra = nout;
+        bool ok = true;
         if (extra == 0) return;
-        // interval section: remember where it starts, walk it once to find the residual section (:1076-1096)
+        // interval section: remember where it starts, walk it once to find the residual section
         if (c.minlen != 0) {
             const int64_t n_iv = (int64_t)b.gamma();
             if (n_iv > extra || b.pos() > limit) { fail(g, E_IO); return; }
@@ -502,6 +523,18 @@ struct MergeWalk {
             if (!(bc & 1)) cp += dp - total;
             copied = (int32_t)cp;
         }
+    }
+
+    // Entry from a schedule record (MergeRec): the cursor starts at the first block code.
+    __device__ __forceinline__ void header_rec(const GraphDev& g, int32_t x_, int32_t d_, int32_t dp_, int32_t bc_, int32_t copied_,
+                                               uint64_t pos, const int32_t* __restrict__ parent_, bool active_) {
+        x = x_; parent = parent_; active = active_;
+        d = d_; dp = dp_; copied = copied_; bc = bc_;
+        bi = p = rem = 0;
+        tail = false;
+        if (!active) return;
+        b.w = g.words; b.maxw = g.nwords - 3;
+        b.seek(pos);
     }
 
     // next copied successor, or BVG_INF

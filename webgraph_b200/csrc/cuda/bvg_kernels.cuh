@@ -95,23 +95,26 @@ __device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // 0..127, mono
 // here once to learn that, and the copied count is kept for the merge step.
 template <bool DEF>
 __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* __restrict__ key_m, int32_t max_level_keys,
-                             int32_t long_d, const uint8_t* __restrict__ is_parent, int32_t* __restrict__ copied_out) {
+                             int32_t long_d, const uint8_t* __restrict__ is_parent, int32_t* __restrict__ copied_out,
+                             uint64_t* __restrict__ extras_pos, uint64_t* __restrict__ blocks_pos, int32_t* __restrict__ bc_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = (int64_t)g.node_hi - g.node_lo;
     if (i >= n) return;
     const int32_t d = g.outdeg[i], dep = g.depth[i];
     const int32_t chunk = (int32_t)(i >> ORDER_CHUNK_LOG);
     int32_t ke = -1, km = -1, copied = 0;
+    uint64_t epos = 0, bpos = 0;
+    int64_t bc = 0;
     if (d > 0 && dep >= 0) {
         const int32_t x = g.node_lo + (int32_t)i;
         const uint64_t limit = g.bit_end - g.bit_base;
         BitBuf b = buffer_at(g, x);
         (void)Rd<DEF>::outdeg(b, g.c);
-        int64_t bc = 0;
         if (g.c.window > 0) {
             const int32_t r = (int32_t)Rd<DEF>::ref(b, g.c);
             if (r > 0) {
                 bc = (int64_t)Rd<DEF>::bcount(b, g.c);
+                bpos = b.pos();
                 int64_t total = 0, cp = 0;
                 for (int64_t k = 0; k < bc && b.pos() <= limit; k++) {
                     const int64_t blk = (int64_t)Rd<DEF>::block(b, g.c) + (k ? 1 : 0);
@@ -122,6 +125,7 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
                 copied = (int32_t)(cp < 0 ? 0 : (cp > d ? d : cp));  // malformed records are reported by the decode step
             }
         }
+        epos = b.pos();
         // records with intervals take a different loop than records without: keep the two kinds in separate warps
         const int has_iv = (d > copied && g.c.minlen != 0 && b.pos() <= limit && b.gamma() != 0) ? 1 : 0;
         if (d <= long_d) {  // longer records are split across threads (bvg_long.cuh)
@@ -137,6 +141,59 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
     key_e[i] = ke;
     key_m[i] = km;
     copied_out[i] = copied;
+    extras_pos[i] = epos;
+    blocks_pos[i] = bpos;
+    bc_out[i] = (int32_t)bc;
+}
+
+// Schedule records: everything the scan kernels need about a node in one coalesced 32- / 56-byte load, in schedule
+// order, instead of six scattered index reads and a second parse of the record header per node and scan.
+struct ExtraRec {
+    uint64_t pos;    // bit position (relative to word 0) of the extras section: interval count, else first residual
+    int64_t row;     // CSR-space offset of the first extra: rowoff[x] + copied
+    int32_t x, nout; // node, successors that are not copied (d - copied)
+    int32_t d;       // outdegree
+    uint32_t flags;  // bit 0: somebody copies from x (its list is materialised)
+};
+struct MergeRec {
+    uint64_t pos;    // bit position of the first copy-block code
+    int64_t row;     // CSR-space offset of x's row
+    int64_t prow;    // CSR-space offset of the parent's row
+    int32_t x, px;   // node, parent
+    int32_t d, dp;   // outdegrees of both
+    int32_t bc, copied;
+    uint32_t flags;  // bit 0 as above
+    int32_t pad_;
+};
+
+__global__ void k_key_scatter_recs(GraphDev g, const int32_t* __restrict__ key_e, const int32_t* __restrict__ key_m, int64_t n,
+                                   int32_t* __restrict__ cur_e, int32_t* __restrict__ cur_m, const uint8_t* __restrict__ is_parent,
+                                   const int32_t* __restrict__ copied, const uint64_t* __restrict__ extras_pos,
+                                   const uint64_t* __restrict__ blocks_pos, const int32_t* __restrict__ bc,
+                                   int32_t* __restrict__ order_e, int32_t* __restrict__ order_m,
+                                   ExtraRec* __restrict__ rec_e, MergeRec* __restrict__ rec_m) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t x = g.node_lo + (int32_t)i;
+    const int32_t ke = key_e[i], km = key_m[i];
+    if (ke >= 0) {
+        const int32_t slot = atomicAdd(cur_e + ke, 1);
+        order_e[slot] = x;
+        ExtraRec r;
+        r.pos = extras_pos[i]; r.row = g.rowoff[i] + copied[i]; r.x = x; r.d = g.outdeg[i]; r.nout = r.d - copied[i];
+        r.flags = is_parent[i] ? 1u : 0u;
+        rec_e[slot] = r;
+    }
+    if (km >= 0) {
+        const int32_t slot = atomicAdd(cur_m + km, 1);
+        order_m[slot] = x;
+        const int32_t rf = g.ref[i];
+        MergeRec r;
+        r.pos = blocks_pos[i]; r.row = g.rowoff[i]; r.prow = g.rowoff[i - rf]; r.x = x; r.px = x - rf;
+        r.d = g.outdeg[i]; r.dp = g.outdeg[i - rf]; r.bc = bc[i]; r.copied = copied[i];
+        r.flags = is_parent[i] ? 1u : 0u; r.pad_ = 0;
+        rec_m[slot] = r;
+    }
 }
 
 __global__ void k_key_hist(const int32_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins) {
@@ -260,6 +317,11 @@ struct RowMap {
     int32_t halo_lo;
     __device__ __forceinline__ int32_t* row(const GraphDev& g, int32_t x) const {
         return x >= from ? out + (g.rowoff[x - g.node_lo] - out_base) : halo + halo_off[x - halo_lo];
+    }
+    int64_t halo_base;         // rowoff of halo_lo (both halo kinds are laid out like the CSR from there)
+    // row pointer of node y from its CSR-space offset (schedule records carry the offsets)
+    __device__ __forceinline__ int32_t* at(int32_t y, int64_t off) const {
+        return y >= from ? out + (off - out_base) : halo + (off - halo_base);
     }
     // A halo node is decoded only if its whole chain lies inside the halo: halo_lo is the smallest chain root of the
     // requested range, so a halo node whose chain starts before it is nobody's ancestor (and its parent has no row).
@@ -414,8 +476,8 @@ constexpr int SCAN_BLOCK = 128;
 constexpr int SCAN_BLOCKS_PER_SM = 8;
 
 template <bool DEF>
-__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
-                              RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
+                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
     long long arcs = 0;
     // warp-uniform trip count and explicit reconvergence between the phases of each item: the lanes of a warp walk
@@ -423,14 +485,16 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
         const int64_t i = base + (threadIdx.x & 31);
-        const int32_t x = i < count ? order[i] : -1;
-        bool active = x >= lo && x < hi && rm.wanted(g, x);
-        const bool store = active && is_parent[x - g.node_lo] != 0;
-        const bool fold = active && x >= from;
+        ExtraRec r;
+        r.x = -1;
+        if (i < count) r = recs[i];
+        bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
+        const bool store = active && (r.flags & 1u);
+        const bool fold = active && r.x >= from;
         active = active && (fold || store);  // halo nodes matter only as parents
         ExtrasWalk<DEF> w;
-        w.header(g, x, active);
-        int32_t* row = store ? rm.row(g, x) : nullptr;
+        w.header_rec(g, r.x, r.d, r.nout, r.pos, active);
+        int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
         unsigned long long f = 0;
         __syncwarp();
         w.template residuals_only<true>(g, row, store, f);
@@ -443,20 +507,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 }
 
 template <bool DEF>
-__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(GraphDev g, const int32_t* __restrict__ order, int64_t count, int32_t lo, int32_t hi, int32_t from,
-                             RowMap rm, const uint8_t* __restrict__ is_parent, unsigned long long* __restrict__ result) {
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
+                             int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
     unsigned long long acc = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
         const int64_t i = base + (threadIdx.x & 31);
-        const int32_t x = i < count ? order[i] : -1;
-        bool active = x >= lo && x < hi && rm.wanted(g, x);
-        const bool store = active && is_parent[x - g.node_lo] != 0;
-        const bool fold = active && x >= from;
+        MergeRec r;
+        r.x = -1;
+        if (i < count) r = recs[i];
+        bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
+        const bool store = active && (r.flags & 1u);
+        const bool fold = active && r.x >= from;
         active = active && (fold || store);
         MergeWalk<DEF> w;
-        w.header(g, x, active ? rm.row(g, x - g.ref[x - g.node_lo]) : nullptr, active);
-        int32_t* row = store ? rm.row(g, x) : nullptr;
+        w.header_rec(g, r.x, r.d, r.dp, r.bc, r.copied, r.pos, active ? rm.at(r.px, r.prow) : nullptr, active);
+        int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
         unsigned long long f = 0;
         __syncwarp();
         if (!store) w.stream_only(g, f);
