@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--workdir", default=os.environ.get("BVG_BENCH_DIR", "/tmp/bvg_bench"))
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational random-access / materialise legs")
+    ap.add_argument("--random-nodes", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample-arcs", type=float, default=3.0e8)
     return ap.parse_args()
 
@@ -346,6 +348,48 @@ def main():
            "h2d_bytes_per_step": int(foot["stream_bytes"] + foot["offsets_bytes"]), "d2h_bytes_per_step": 16 + 24,
            "steps": es, "what": "bvg_open_memory_shard(pinned host .graph/.offsets) + bvg_scan_range + bvg_close per step"}
 
+    # ---- the other BASELINE configs on the same graph, outside the timed region (N = 1 only): C4 random access to 10 M
+    # uniformly random nodes (seeded, as SpeedTest -r, reference test/SpeedTest.java:98-111) and the materialising decode ----
+    extra = None
+    if world == 1 and not args.no_extras:
+        extra = {}
+        g3 = open_shard()
+        g3.setStream(stream.cuda_stream)
+        try:
+            nq = args.random_nodes
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(args.seed)
+            xs = torch.randint(0, n_total, (nq,), device=dev, dtype=torch.int32, generator=gen)
+            qoff = torch.zeros(nq + 1, dtype=torch.int64, device=dev)
+            bvgraph._check(L.bvg_successors_batch(g3.handle, xs.data_ptr(), nq, qoff.data_ptr(), None, 0, 1))
+            torch.cuda.synchronize()
+            qarcs = int(qoff[-1].item())
+            qout = torch.empty(max(qarcs, 1), dtype=torch.int32, device=dev)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for rep in range(2):  # first repetition warms the allocator
+                r0.record()
+                bvgraph._check(L.bvg_successors_batch(g3.handle, xs.data_ptr(), nq, qoff.data_ptr(), qout.data_ptr(), qarcs, 1))
+                r1.record()
+                torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1)
+            extra["random_access"] = {"config": "C4", "nodes": nq, "arcs": qarcs, "ms": rms, "nodes_per_s": nq / (rms * 1e-3),
+                                      "edges_per_s": qarcs / (rms * 1e-3), "what": "bvg_successors_batch, device buffers, sizes + decode"}
+            del qout, qoff, xs
+            moff = torch.zeros(n_total + 1, dtype=torch.int64, device=dev)
+            mout = torch.empty(m_total, dtype=torch.int32, device=dev)
+            for rep in range(2):
+                r0.record()
+                bvgraph._check(L.bvg_decode_range(g3.handle, 0, n_total, moff.data_ptr(), mout.data_ptr(), m_total, 1))
+                r1.record()
+                torch.cuda.synchronize()
+            mms = r0.elapsed_time(r1)
+            extra["materialise"] = {"ms": mms, "edges_per_s": m_total / (mms * 1e-3), "bytes_written": 4 * m_total + 8 * (n_total + 1),
+                                    "what": "bvg_decode_range of the whole graph into device CSR (int64 offsets + int32 successors)"}
+            del moff, mout
+        except Exception as e:  # informational legs must never take the headline down
+            extra["error"] = repr(e)
+        g3.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         arcs_c, dt_c, hi_c = cpu_port_baseline(base, args.cpu_sample_arcs, 1)
@@ -363,7 +407,7 @@ def main():
                            "max_outdegree": st["max_outdegree"], "seed": args.seed, "generator": "webgraph_b200.tools.generate_store (SURVEY 8d)",
                            "l2": "input stream (%.2f GB) is far larger than L2; no flush needed" % (st["graph_bits"] / 8e9),
                            "halo_exchange": bool(need_halo), "mode": "consume-only scan (arcs + XOR checksum verified against the generator)"},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks}
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -64,3 +64,40 @@ extern "C" int emu_decode(const uint8_t* graph, uint64_t nbytes, const uint64_t*
     }
     return err.code;
 }
+
+// Fold-only path (stream_only): checksum of the copied successors of every node with a reference, against the same
+// value computed from the materialised rows through merge_in_place's companion (next_a).
+extern "C" int emu_stream_fold(const uint8_t* graph, uint64_t nbytes, const uint64_t* offsets, int32_t n,
+                               int window, int minlen, int zetak, int def_codec, const int64_t* row_off, const int32_t* rows,
+                               unsigned long long* out_flat, unsigned long long* out_ref) {
+    std::vector<uint32_t> words((((nbytes + 3) / 4 + 8 + 3) / 4) * 4, 0);
+    for (uint64_t i = 0; i < nbytes; i++) words[i >> 2] |= (uint32_t)graph[i] << (24 - 8 * (i & 3));
+    std::vector<int32_t> outdeg(n), ref(n), depth(n);
+    ErrWord err{0, 0, 0};
+    GraphDev g;
+    g.words = words.data(); g.nwords = words.size(); g.bit_base = 0; g.bit_end = offsets[n];
+    g.offsets = offsets; g.node_lo = 0; g.node_hi = n;
+    g.c = Codec{ C_GAMMA, C_GAMMA, C_ZETA, C_UNARY, C_GAMMA, zetak, window, minlen };
+    g.outdeg = outdeg.data(); g.ref = ref.data(); g.depth = depth.data(); g.rowoff = row_off; g.copied = nullptr; g.err = &err;
+    if (!def_codec) return -3;
+    unsigned long long flat = 0, refv = 0;
+    for (int32_t x = 0; x < n; x++) {
+        Bits b = cursor_at(g, x);
+        uint64_t d = Rd<true>::outdeg(b, g.c);
+        int32_t r = 0;
+        if (d > 0 && window > 0) r = (int32_t)Rd<true>::ref(b, g.c);
+        outdeg[x] = (int32_t)d; ref[x] = r;
+    }
+    for (int32_t x = 0; x < n; x++) if (ref[x]) {
+        const int32_t* parent = rows + row_off[x - ref[x]];
+        MergeWalk<true> w;
+        w.header(g, x, parent, true);
+        w.stream_only(g, flat);
+        MergeWalk<true> v;
+        v.header(g, x, parent, true);
+        const unsigned long long base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        for (int64_t a = v.next_a(g.c); a != BVG_INF; a = v.next_a(g.c)) refv ^= base + (unsigned long long)(uint32_t)a;
+    }
+    *out_flat = flat; *out_ref = refv;
+    return err.code;
+}

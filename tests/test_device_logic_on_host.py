@@ -36,6 +36,8 @@ def emu():
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
     lib.emu_decode_offsets.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
+    lib.emu_stream_fold.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     return lib
 
 
@@ -115,3 +117,21 @@ def test_emulated_parallel_offsets_decode(emu, oracle, tmp_path):
     base = str(tmp_path / "skew")
     tools.store_csr(base, off2, succ2)
     _emu_offsets(emu, oracle, base)
+
+
+def test_emulated_fold_only_stream(emu, oracle, tmp_path):
+    """stream_only (copied successors folded without a merge) == the same elements pulled through next_a."""
+    bases = [CNR]
+    off, succ, _ = graphs.copy_heavy(2500, seed=3)
+    base = str(tmp_path / "ch")
+    tools.store_csr(base, off, succ)
+    bases.append(base)
+    for b in bases:
+        g = oracle.load(b)
+        graph = np.concatenate([np.fromfile(b + ".graph", dtype=np.uint8), np.zeros(8, dtype=np.uint8)])
+        offs = g.offsets()
+        toff, tsucc = g.decode_range(0, g.n)
+        a, r = C.c_ulonglong(0), C.c_ulonglong(0)
+        rc = emu.emu_stream_fold(graph.ctypes.data, len(graph) - 8, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak, 1,
+                                 toff.ctypes.data, tsucc.ctypes.data, C.byref(a), C.byref(r))
+        assert rc == 0 and a.value == r.value and a.value != 0

@@ -549,11 +549,26 @@ struct MergeWalk {
         }
     }
 
-    // nobody copies from x: the copied successors are only consumed
+    // nobody copies from x: the copied successors are only consumed.  One flat loop whose every trip is either a block
+    // boundary (parse the next length), a jump over a skip block, or one copied element -- so that the lanes of a warp,
+    // which sit in different blocks, still share the loop.
     __device__ __forceinline__ void stream_only(const GraphDev& g, unsigned long long& fold) {
         if (!active) return;
+        const Codec& c = g.c;
         const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
-        for (int64_t a = next_a(g.c); a != BVG_INF; a = next_a(g.c)) fold ^= fold_base + (unsigned long long)(uint32_t)a;
+        int32_t pos = 0, edge = dp, blk = 0;
+        bool copying = true, in_tail = bc == 0;  // no blocks: everything is copied (MaskedIntIterator, left = -1)
+        if (!in_tail) edge = (int32_t)Rd<DEF>::block(b, c);
+        while (pos < dp) {
+            if (pos == edge && !in_tail) {
+                if (++blk < bc) { edge += (int32_t)Rd<DEF>::block(b, c) + 1; copying = !(blk & 1); }
+                else { in_tail = true; copying = !(bc & 1); edge = dp; }
+            } else if (!copying) {
+                pos = edge;
+            } else {
+                fold ^= fold_base + (unsigned long long)(uint32_t)parent[pos++];
+            }
+        }
     }
 
     template <bool FOLD>
