@@ -899,10 +899,14 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     HaloPlan hp(s);
     { const int rc = plan_halo(g, from, to, rows, row_from, rm, hp); if (rc) return rc; }
     const int32_t lo = hp.lo;
-    // persistent grids: one resident wave (SM count x the blocks per SM the kernels are bounded to)
+    // One item per thread and as many blocks as that takes: the schedules are longest-first, so the hardware block
+    // scheduler balances the SMs by itself (BVG_SCAN_PERSISTENT=1 keeps one resident wave looping instead).
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
-    const unsigned grid = (unsigned)(sms * SCAN_BLOCKS_PER_SM), grid_m = grid;
+    static const bool persistent = getenv("BVG_SCAN_PERSISTENT") && atoi(getenv("BVG_SCAN_PERSISTENT")) != 0;
+    const unsigned wave = (unsigned)(sms * SCAN_BLOCKS_PER_SM);
+    const unsigned grid = persistent ? wave : (unsigned)std::max<int64_t>(1, (g->order_e_count + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    const unsigned grid_m = persistent ? wave : 0x7fffffffu;
     if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     Tmp<int32_t> long_tmp(s);
@@ -969,7 +973,15 @@ int bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_r
     if (!d_result) return BVG_EINVAL;
     DeviceGuard dg(g->device);
     CK(cudaMemsetAsync(d_result, 0, 16, g->stream));
-    return enqueue_scan(g, from, to, (unsigned long long*)d_result);
+    // blocks fold into FOLD_SLOTS slot pairs (bvg_kernels.cuh, block_fold); one small kernel reduces them into d_result
+    Tmp<unsigned long long> slots(g->stream);
+    CK(slots.alloc(2 * FOLD_SLOTS));
+    CK(cudaMemsetAsync(slots.p, 0, 2 * FOLD_SLOTS * sizeof(unsigned long long), g->stream));
+    rc = enqueue_scan(g, from, to, slots.p);
+    if (rc) return rc;
+    LAUNCH(k_reduce_slots, 1, 256, 0, g->stream, slots.p, (unsigned long long*)d_result);
+    CK(cudaGetLastError());
+    return BVG_OK;
 }
 
 int bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum) {

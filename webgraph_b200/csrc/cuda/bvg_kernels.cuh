@@ -76,17 +76,17 @@ __global__ void k_max_i32(const int32_t* __restrict__ in, int64_t n, int32_t* __
 // half-octave bucket of their work (record bits for the extras step; chain level, then outdegree + parent outdegree
 // for the merge step), longest first, so the 32 lanes of a warp get records of similar length.
 // ---------------------------------------------------------------------------------------------------
-constexpr int ORDER_BUCKETS = 128;
+constexpr int ORDER_BUCKETS = 256;
 // Schedules are bucketed inside chunks of 2^ORDER_CHUNK_LOG consecutive nodes, chunks in node order: the lanes of a
 // warp still get records of similar length, but everything in flight at one time comes from a few tens of MB of the
 // stream, the index arrays and the rows, which the 126 MB L2 can hold.
 constexpr int ORDER_CHUNK_LOG = 18;
 
-__device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // 0..127, monotone in v
+__device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // quarter octaves: 0..255, monotone in v
     if (v == 0) return 0;
     const int l = 63 - __clzll((long long)v);
-    const int half = l > 0 ? (int)((v >> (l - 1)) & 1) : 0;
-    return 2 * l + half;
+    const int frac = l >= 2 ? (int)((v >> (l - 2)) & 3) : (l == 1 ? (int)((v & 1) << 1) : 0);
+    return 4 * l + frac;
 }
 
 // key_e: extras schedule (all nodes with successors); key_m: merge schedule (nodes with a reference), level-major.
@@ -129,7 +129,9 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
         // records with intervals take a different loop than records without: keep the two kinds in separate warps
         const int has_iv = (d > copied && g.c.minlen != 0 && b.pos() <= limit && b.gamma() != 0) ? 1 : 0;
         if (d <= long_d) {  // longer records are split across threads (bvg_long.cuh)
-            ke = (chunk * 2 + has_iv) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(g.offsets[i + 1] - g.offsets[i]));
+            // what a lane's loop length is: residual count for the tight loop, record bits for the interval loop
+            const uint64_t work_e = has_iv ? g.offsets[i + 1] - g.offsets[i] : (uint64_t)(d - copied);
+            ke = (chunk * 2 + has_iv) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work_e));
             if (dep >= 1 && dep <= max_level_keys) {
                 const int par = is_parent[i] ? 1 : 0;  // parents merge in place, the others only stream: separate warps too
                 const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (par ? (uint64_t)(d - copied) : 0);
@@ -446,6 +448,8 @@ __global__ void k_mark_parents(GraphDev g, uint8_t* __restrict__ is_parent) {
     if (r > 0 && r <= i) is_parent[i - r] = 1;
 }
 
+constexpr int FOLD_SLOTS = 1024;
+
 __device__ __forceinline__ void block_fold(unsigned long long acc, long long arcs, unsigned long long* __restrict__ result) {
     __shared__ unsigned long long s_x[32];
     __shared__ long long s_a[32];
@@ -465,10 +469,29 @@ __device__ __forceinline__ void block_fold(unsigned long long acc, long long arc
             v ^= __shfl_xor_sync(0xffffffffu, v, o);
             a += __shfl_xor_sync(0xffffffffu, a, o);
         }
-        if (lane == 0) {
-            if (v) atomicXor(result + 1, v);
-            if (a) atomicAdd(result, (unsigned long long)a);
+        if (lane == 0) {  // spread over FOLD_SLOTS slot pairs: a dynamic grid has ~10^5 blocks, two hot words would serialise them
+            unsigned long long* slot = result + 2 * (blockIdx.x & (FOLD_SLOTS - 1));
+            if (v) atomicXor(slot + 1, v);
+            if (a) atomicAdd(slot, (unsigned long long)a);
         }
+    }
+}
+
+// slots[FOLD_SLOTS][2] -> out[2] (arcs added, checksum xored)
+__global__ void k_reduce_slots(const unsigned long long* __restrict__ slots, unsigned long long* __restrict__ out) {
+    unsigned long long a = 0, v = 0;
+    for (int i = threadIdx.x; i < FOLD_SLOTS; i += blockDim.x) { a += slots[2 * i]; v ^= slots[2 * i + 1]; }
+    __shared__ unsigned long long sa[32], sv[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); v ^= __shfl_xor_sync(0xffffffffu, v, o); }
+    if (lane == 0) { sa[wid] = a; sv[wid] = v; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0; v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += sa[w]; v ^= sv[w]; }
+        atomicAdd(out, a);
+        atomicXor(out + 1, v);
     }
 }
 
