@@ -112,7 +112,7 @@ extern "C" int emu_decode_long(const uint8_t* graph, uint64_t nbytes, const uint
             }
         }
     }
-    LongIndex li{ meta.data(), cb_cum.data(), cb_ppos.data(), iv_cum.data(), iv_left.data(), seg_pos.data(), seg_val.data() };
+    LongIndex li{ meta.data(), cb_cum.data(), cb_ppos.data(), iv_cum.data(), iv_left.data(), seg_pos.data(), seg_val.data(), LONG_SEG, LONG_CHUNK };
     FlatRows rm{ out, rowoff.data() };
     LongDst dst{ tmpbuf.data() };
     // level 0 work: short records sequentially, long records by segments / chunks

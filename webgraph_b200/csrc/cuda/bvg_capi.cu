@@ -99,8 +99,11 @@ struct bvg_graph {
     int64_t n_items_resid = 0, n_items_extras = 0;
     std::vector<int64_t> merge_item_start;  // items of chain level l+1: d_items_merge[merge_item_start[l] .. [l+1])
     int64_t long_tmp_entries = 0;
+    // tunables (BVG_LONG_D / BVG_LONG_SEG / BVG_LONG_CHUNK override the defaults of bvg_long.cuh)
+    int32_t long_d = LONG_D, long_seg = LONG_SEG, long_chunk = LONG_CHUNK;
     LongIndex long_index() const {
         LongIndex li;
+        li.seg = long_seg; li.chunk = long_chunk;
         li.meta = d_long_meta; li.cb_cum = d_cb_cum; li.cb_ppos = d_cb_ppos; li.iv_cum = d_iv_cum; li.iv_left = d_iv_left;
         li.seg_pos = d_seg_pos; li.seg_val = d_seg_val;
         return li;
@@ -262,14 +265,15 @@ static int build_long_index(bvg_graph* g) {
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
     cudaStream_t s = g->stream;
     g->nlong = 0;
-    if (nn == 0 || g->max_outdeg <= LONG_D || g->max_depth > 64) return BVG_OK;
+    if (nn == 0 || g->max_outdeg <= g->long_d || g->max_depth > 64) return BVG_OK;
+    const int32_t LSEG = g->long_seg, LCHUNK = g->long_chunk;
     GraphDev gd = g->dev();
     Tmp<int32_t> flags(s);
     struct { int32_t* p; } long_nodes{ nullptr };
     Tmp<int64_t> pos(s);
     CK(flags.alloc((size_t)nn));
     CK(pos.alloc((size_t)nn + 1));
-    LAUNCH(k_long_flags, grid_for(nn, 256), 256, 0, s, gd, LONG_D, flags.p);
+    LAUNCH(k_long_flags, grid_for(nn, 256), 256, 0, s, gd, g->long_d, flags.p);
     int rc = device_exclusive_scan(s, flags.p, nn, pos.p);
     if (rc) return rc;
     int64_t nl = 0;
@@ -294,13 +298,13 @@ static int build_long_index(bvg_graph* g) {
         m.cb_off = cb; cb += (int64_t)m.ncb + 1;
         m.iv_off = iv; iv += (int64_t)m.ic + 1;
         m.seg_off = seg;
-        const int32_t nseg = (m.rc + LONG_SEG - 1) / LONG_SEG;
+        const int32_t nseg = (m.rc + LSEG - 1) / LSEG;
         seg += nseg;
         m.tmp_off = tmp; tmp += 2 * (int64_t)m.d;
         for (int32_t q = 0; q < nseg; q++) it_r.push_back(LongItem{ (int32_t)l, q });
         for (int32_t q = 0; q * FOLD_CHUNK < m.d; q++) it_f.push_back(RowChunk{ m.x, q });
-        if (m.ic > 0) for (int32_t q = 0; q * LONG_CHUNK < m.ilen + m.rc; q++) it_x.push_back(LongItem{ (int32_t)l, q });
-        if (m.copied > 0 && m.level >= 1) for (int32_t q = 0; q * LONG_CHUNK < m.d; q++) it_m[(size_t)m.level].push_back(LongItem{ (int32_t)l, q });
+        if (m.ic > 0) for (int32_t q = 0; (int64_t)q * LCHUNK < (int64_t)m.ilen + m.rc; q++) it_x.push_back(LongItem{ (int32_t)l, q });
+        if (m.copied > 0 && m.level >= 1) for (int32_t q = 0; (int64_t)q * LCHUNK < m.d; q++) it_m[(size_t)m.level].push_back(LongItem{ (int32_t)l, q });
     }
     CK(cudaMemcpyAsync(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), cudaMemcpyHostToDevice, s));
     CK(cudaMallocAsync((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
@@ -367,8 +371,8 @@ static int build_long_index(bvg_graph* g) {
             CK(sbase.alloc((size_t)ni));
             CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)ni * 8, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(sbase.p, sb.data(), (size_t)ni * 8, cudaMemcpyHostToDevice, s));
-            if (g->def_codec) LAUNCH(k_lspec_emit<true>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val);
-            else LAUNCH(k_lspec_emit<false>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val);
+            if (g->def_codec) LAUNCH(k_lspec_emit<true>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
+            else LAUNCH(k_lspec_emit<false>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(s));
         }
@@ -427,8 +431,8 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
     GraphDev gd = g->dev();
     CK(cudaMallocAsync((void**)&g->d_copied, (size_t)nn * 4, g->stream));
-    if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
-    else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, LONG_D, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
+    if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, g->long_d, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
+    else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, g->long_d, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
     tr.mark("  sched: parents + keys");
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_e.p, nn, bins.p);
     LAUNCH(k_key_hist, grid_for(nn, 256), 256, 0, s, key_m.p, nn, bins.p + nb_e);
@@ -548,9 +552,19 @@ static void keep_pool_warm(int dev) {
     cudaGetLastError();
 }
 
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v) return dflt;
+    const long x = atol(v);
+    return (int)(x < lo ? lo : (x > hi ? hi : x));
+}
+
 static int open_common(bvg_graph* g, const Properties& p, int offset_type) {
     if (offset_type < -1 || offset_type > 2) return BVG_EINVAL;  // BVGraph.java:1545
     keep_pool_warm(g->device);
+    g->long_d = env_int("BVG_LONG_D", LONG_D, 2, 1 << 30);
+    g->long_seg = env_int("BVG_LONG_SEG", LONG_SEG, 1, 1 << 20);
+    g->long_chunk = env_int("BVG_LONG_CHUNK", LONG_CHUNK, 1, 1 << 20);
     g->offset_type = offset_type;
     g->n_total = (int32_t)p.nodes; g->m_total = p.arcs; g->window = p.window; g->maxref = p.maxref;
     g->minlen = p.minlen; g->zetak = p.zetak; g->flags = p.flags;

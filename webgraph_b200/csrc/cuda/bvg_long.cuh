@@ -53,6 +53,7 @@ struct LongIndex {
     const int32_t* __restrict__ iv_left;   // left extreme of interval t          (same stride as iv_cum)
     const uint64_t* __restrict__ seg_pos;  // bit position of the first code of residual segment s
     const int64_t* __restrict__ seg_val;   // successor value just before it (unused for s = 0)
+    int32_t seg, chunk;                    // residuals per sync point, outputs per merge-path item (LONG_SEG, LONG_CHUNK by default)
 };
 
 // Largest t in [0, n) with cum[t] <= q, for a non-decreasing cum[0..n] with cum[0] = 0 <= q < cum[n].
@@ -70,7 +71,7 @@ __device__ __forceinline__ int32_t upper_slot(const int32_t* __restrict__ cum, i
 // ---------------------------------------------------------------------------------------------------
 template <bool DEF>
 __device__ void long_walk(const GraphDev& g, LongMeta& m, int pass, int32_t* cb_cum, int32_t* cb_ppos,
-                          int32_t* iv_cum, int32_t* iv_left, uint64_t* seg_pos, int64_t* seg_val) {
+                          int32_t* iv_cum, int32_t* iv_left, uint64_t* seg_pos, int64_t* seg_val, int32_t seg = LONG_SEG) {
     const Codec& c = g.c;
     const int32_t x = m.x;
     BitBuf b = buffer_at(g, x);
@@ -129,7 +130,7 @@ __device__ void long_walk(const GraphDev& g, LongMeta& m, int pass, int32_t* cb_
     // residual sync points (the one sequential pass over this record's residuals, paid once at open)
     int64_t v = 0;
     for (int64_t i = 0; i < rc; i++) {
-        if (i % LONG_SEG == 0) { seg_pos[i / LONG_SEG] = b.pos(); seg_val[i / LONG_SEG] = v; }
+        if (i % seg == 0) { seg_pos[i / seg] = b.pos(); seg_val[i / seg] = v; }
         if (i == 0) v = (int64_t)(int32_t)((int64_t)x + nat2int(Rd<DEF>::resid(b, c)));
         else v += (int64_t)Rd<DEF>::resid(b, c) + 1;
     }
@@ -207,14 +208,14 @@ __device__ inline void lspec_fix_one(const GraphDev& g, int64_t j, const SpecIte
 template <bool DEF>
 __device__ inline void lspec_emit_one(const GraphDev& g, const SpecItem& it, const LongMeta& m, int64_t cbase, int64_t sbase,
                                       const int64_t* __restrict__ v0, int64_t* __restrict__ v0_out,
-                                      uint64_t* __restrict__ seg_pos, int64_t* __restrict__ seg_val) {
+                                      uint64_t* __restrict__ seg_pos, int64_t* __restrict__ seg_val, int32_t seg = LONG_SEG) {
     BitBuf b;
     b.w = g.words; b.maxw = g.nwords - 3;
     b.seek(it.entry);
     int64_t ord = cbase;
     int64_t v = it.first ? 0 : v0[it.l] + sbase;
     while (b.pos() < it.hi && ord < m.rc) {
-        if (ord % LONG_SEG == 0) { seg_pos[m.seg_off + ord / LONG_SEG] = b.pos(); seg_val[m.seg_off + ord / LONG_SEG] = v; }
+        if (ord % seg == 0) { seg_pos[m.seg_off + ord / seg] = b.pos(); seg_val[m.seg_off + ord / seg] = v; }
         const uint64_t code = Rd<DEF>::resid(b, g.c);
         if (ord == 0) { v = (int64_t)(int32_t)((int64_t)m.x + nat2int(code)); if (v0_out) v0_out[it.l] = v; }
         else v += (int64_t)code + 1;
@@ -250,11 +251,11 @@ __global__ void k_lspec_first(GraphDev g, const LongMeta* __restrict__ meta, int
 template <bool DEF>
 __global__ void k_lspec_emit(GraphDev g, const SpecItem* __restrict__ items, int64_t n, const LongMeta* __restrict__ meta,
                              const int64_t* __restrict__ cbase, const int64_t* __restrict__ sbase, const int64_t* __restrict__ v0,
-                             uint64_t* __restrict__ seg_pos, int64_t* __restrict__ seg_val) {
+                             uint64_t* __restrict__ seg_pos, int64_t* __restrict__ seg_val, int32_t seg) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const SpecItem it = items[j];
-    lspec_emit_one<DEF>(g, it, meta[it.l], cbase[j], sbase[j], v0, nullptr, seg_pos, seg_val);
+    lspec_emit_one<DEF>(g, it, meta[it.l], cbase[j], sbase[j], v0, nullptr, seg_pos, seg_val, seg);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -264,8 +265,8 @@ __global__ void k_lspec_emit(GraphDev g, const SpecItem* __restrict__ items, int
 // Residual segment s of long record m: LONG_SEG (or fewer) successors into dst[s * LONG_SEG ..].
 template <bool DEF>
 __device__ void long_resid_segment(const GraphDev& g, const LongMeta& m, const LongIndex& li, int32_t s, int32_t* __restrict__ dst) {
-    const int32_t first = s * LONG_SEG;
-    const int32_t cnt = min(LONG_SEG, m.rc - first);
+    const int32_t first = s * li.seg;
+    const int32_t cnt = min(li.seg, m.rc - first);
     BitBuf b;
     b.w = g.words;
     b.maxw = g.nwords - 3;
@@ -395,10 +396,10 @@ __global__ void k_long_extras(GraphDev g, LongIndex li, const LongItem* __restri
     if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
     IntervalSeq a{ li.iv_cum + m.iv_off, li.iv_left + m.iv_off, m.ic, m.ilen };
     const int32_t total = m.ilen + m.rc;
-    const int32_t q0 = it.part * LONG_CHUNK;
+    const int32_t q0 = it.part * li.chunk;
     const int32_t* left = a.left;
     merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
-                min(LONG_CHUNK, total - q0), dst.extras(m, rm.row(g, m.x)));
+                min(li.chunk, total - q0), dst.extras(m, rm.row(g, m.x)));
 }
 
 template <class RM>
@@ -412,9 +413,9 @@ __global__ void k_long_merge(GraphDev g, LongIndex li, const LongItem* __restric
     const int32_t* parent = rm.row(g, m.x - m.ref);
     CopiedSeq a{ li.cb_cum + m.cb_off, li.cb_ppos + m.cb_off, parent, m.ncb, m.copied };
     const int32_t* ppos = a.ppos;
-    const int32_t q0 = it.part * LONG_CHUNK;
+    const int32_t q0 = it.part * li.chunk;
     merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
-                m.d - m.copied, q0, min(LONG_CHUNK, m.d - q0), rm.row(g, m.x));
+                m.d - m.copied, q0, min(li.chunk, m.d - q0), rm.row(g, m.x));
 }
 
 }  // namespace bvg
