@@ -571,24 +571,46 @@ struct MergeWalk {
         }
     }
 
+    // Somebody copies from x: its list has to exist, sorted.  Same flat loop as stream_only, with one more kind of trip:
+    // when the head of the parent stream is known, emit the smaller of it and the next unread extra.
     template <bool FOLD>
     __device__ __forceinline__ void merge_in_place(const GraphDev& g, int32_t* __restrict__ row, unsigned long long& fold) {
         if (!active) return;
+        const Codec& c = g.c;
         const unsigned long long fold_base = (unsigned long long)(uint32_t)x * BVG_MIX;
-        int32_t j = copied, k = 0;  // j: next unread extra, k: next output slot
-        int64_t a = next_a(g.c);
+        int32_t pos = 0, edge = dp, blk = 0;
+        bool copying = true, in_tail = bc == 0;
+        if (!in_tail) edge = (int32_t)Rd<DEF>::block(b, c);
+        int32_t j = copied, k = 0;   // j: next unread extra, k: next output slot
+        bool have_a = false;
+        int32_t a = 0;
         for (;;) {
-            // parent exhausted and nothing was dropped: the remaining extras already sit at their final positions
-            if (a == BVG_INF && k == j) break;
-            const int64_t bv = j < d ? (int64_t)row[j] : BVG_INF;
-            if (a == BVG_INF && bv == BVG_INF) { while (k < d) row[k++] = -1; break; }  // duplicates were dropped (:1210)
-            if (a < bv) {
-                row[k++] = (int32_t)a;
+            if (!have_a && pos < dp) {           // bring the parent stream to its next copied element
+                if (pos == edge && !in_tail) {
+                    if (++blk < bc) { edge += (int32_t)Rd<DEF>::block(b, c) + 1; copying = !(blk & 1); }
+                    else { in_tail = true; copying = !(bc & 1); edge = dp; }
+                } else if (!copying) {
+                    pos = edge;
+                } else {
+                    a = parent[pos++];
+                    have_a = true;
+                }
+                continue;
+            }
+            if (!have_a) {                       // parent exhausted
+                if (k == j) break;               // nothing was dropped: the remaining extras already sit in place
+                if (j < d) { row[k++] = row[j++]; continue; }
+                while (k < d) row[k++] = -1;     // duplicates were dropped (:1210)
+                break;
+            }
+            const int32_t bv = j < d ? row[j] : 0x7fffffff;
+            if (j >= d || a < bv) {
+                row[k++] = a;
                 if (FOLD) fold ^= fold_base + (unsigned long long)(uint32_t)a;
-                a = next_a(g.c);
+                have_a = false;
             } else {
-                row[k++] = (int32_t)bv; j++;
-                if (a == bv) a = next_a(g.c);  // equal heads are emitted once (MergedIntIterator.java:70)
+                row[k++] = bv; j++;
+                if (a == bv) have_a = false;     // equal heads are emitted once (MergedIntIterator.java:70)
             }
         }
     }
