@@ -26,16 +26,17 @@ def _find_asan():
 def emu():
     cuda_dir = os.path.join(ROOT, "webgraph_b200", "csrc", "cuda")
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "emu_offsets.cpp"),
-            os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
-            os.path.join(cuda_dir, "bvg_offsets.cuh")]
+            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
+            os.path.join(cuda_dir, "bvg_offsets.cuh"), os.path.join(cuda_dir, "bvg_scan.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
         # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
-                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2]])
+                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2], srcs[3]])
     lib = C.CDLL(EMU)
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
     lib.emu_decode_offsets.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
+    lib.emu_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_stream_fold.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     return lib
@@ -135,3 +136,49 @@ def test_emulated_fold_only_stream(emu, oracle, tmp_path):
         rc = emu.emu_stream_fold(graph.ctypes.data, len(graph) - 8, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak, 1,
                                  toff.ctypes.data, tsucc.ctypes.data, C.byref(a), C.byref(r))
         assert rc == 0 and a.value == r.value and a.value != 0
+
+
+def _emu_scan(emu, oracle, base):
+    g = oracle.load(base)
+    graph = np.concatenate([np.fromfile(base + ".graph", dtype=np.uint8), np.zeros(8, dtype=np.uint8)])
+    offs = g.offsets()
+    toff, tsucc = g.decode_range(0, g.n)
+    rows = np.full(len(tsucc) + 1, -77, dtype=np.int32)
+    out_off = np.zeros(g.n + 1, dtype=np.int64)
+    parent = np.zeros(g.n + 1, dtype=np.uint8)
+    res = (C.c_ulonglong * 2)()
+    rc = emu.emu_scan(graph.ctypes.data, len(graph) - 8, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak,
+                      out_off.ctypes.data, rows.ctypes.data, parent.ctypes.data, res)
+    assert rc == 0
+    assert (res[0], res[1]) == g.scan_range(0, g.n)
+    assert rows[len(tsucc)] == -77
+    # rows of the nodes somebody copies from are materialised, sorted, exactly as the oracle decodes them
+    for x in np.nonzero(parent[:g.n])[0]:
+        assert np.array_equal(rows[toff[x]:toff[x + 1]], tsucc[toff[x]:toff[x + 1]]), x
+    return int(parent.sum())
+
+
+def test_emulated_fused_scan(emu, oracle, tmp_path):
+    """k_scan_extras_lean / k_scan_merge logic (bvg_scan.cuh) record by record on the host: checksum == oracle's scan,
+    parents' rows == oracle's lists."""
+    assert _emu_scan(emu, oracle, CNR) > 1000
+    for k, w, r, ml in [(3, 7, 3, 4), (3, 7, 3, 0), (2, 1, 1, 2), (5, 16, 10, 3), (1, 3, 2, 4)]:
+        off, succ, _ = graphs.copy_heavy(2000, seed=5 + k + ml)
+        base = str(tmp_path / ("s%d_%d" % (k, ml)))
+        tools.store_csr(base, off, succ, zetak=k, window=w, maxref=r, minlen=ml)
+        _emu_scan(emu, oracle, base)
+    # ids near 2^31, gaps that need zeta codes longer than the 32-bit window, long gammas for the first interval left
+    n = 300
+    deg = np.zeros(n, dtype=np.int64)
+    deg[5] = 10
+    deg[100:110] = 3
+    deg[200] = 9
+    off2 = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=off2[1:])
+    succ2 = np.concatenate([np.array([0, 1, 2, 3, 2 ** 30, 2 ** 30 + 1, 2 ** 30 + 2, 2 ** 30 + 3, 2 ** 30 + 4, 2 ** 31 - 2], dtype=np.int64)] +
+                           [np.array([7, 2 ** 26 + i, 2 ** 31 - 5 + i // 3], dtype=np.int64) for i in range(10)] +
+                           [np.array([2 ** 29 + j for j in range(8)] + [2 ** 31 - 1], dtype=np.int64)]).astype(np.int32)
+    for k in (3, 4):
+        base = str(tmp_path / ("big%d" % k))
+        tools.store_csr(base, off2, succ2, zetak=k)
+        _emu_scan(emu, oracle, base)

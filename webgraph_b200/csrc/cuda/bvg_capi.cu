@@ -419,7 +419,7 @@ static int build_schedules(bvg_graph* g) {
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
     const int64_t nchunks = (nn + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG;
     const int64_t per_level = nchunks * 2 * ORDER_BUCKETS;  // chunk x (parent | not) x half-octave bucket
-    const int64_t nb_e = nchunks * 2 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
+    const int64_t nb_e = nchunks * 4 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
     Tmp<int32_t> key_e(s), key_m(s), bins(s), bcs(s);
     Tmp<uint64_t> epos(s), bpos(s);
     CK(key_e.alloc((size_t)nn));
@@ -468,7 +468,7 @@ static int build_schedules(bvg_graph* g) {
 static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbytes, uint64_t* d_offsets_full, int64_t n_full) {
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
     Trace tr(g->stream);
-    g->nwords = ((nbytes + 3) / 4 + 8 + 3) & ~(uint64_t)3;  // >= 8 padding words, a whole number of 128-bit groups
+    g->nwords = ((nbytes + 3) / 4 + STREAM_PAD_WORDS + 3) & ~(uint64_t)3;  // padding words, a whole number of 128-bit groups
     CK(cudaMallocAsync((void**)&g->d_words, g->nwords * 4, g->stream));
     CK(cudaMemsetAsync(g->d_words, 0, g->nwords * 4, g->stream));
     if (nbytes) CK(cudaMemcpyAsync(g->d_words, bytes, nbytes, cudaMemcpyHostToDevice, g->stream));
@@ -921,7 +921,14 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     const unsigned wave = (unsigned)(sms * SCAN_BLOCKS_PER_SM);
     const unsigned grid = persistent ? wave : (unsigned)std::max<int64_t>(1, (g->order_e_count + SCAN_BLOCK - 1) / SCAN_BLOCK);
     const unsigned grid_m = persistent ? wave : 0x7fffffffu;
-    if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
+    static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
+    static const int la = env_int("BVG_SCAN_LA", 1, 1, 3);
+    static const uint32_t pf_mask = (uint32_t)env_int("BVG_SCAN_PF", 7, 0, 1 << 30);  // prefetch every pf_mask + 1 residuals
+    if (g->def_codec && lean && g->zetak == 3 && la == 1) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, 1>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, pf_mask);
+    else if (g->def_codec && lean && g->zetak == 3 && la == 2) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, 2>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, pf_mask);
+    else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, 3>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, pf_mask);
+    else if (g->def_codec && lean) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, 2>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, pf_mask);
+    else if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     Tmp<int32_t> long_tmp(s);
     LongDst ld{ nullptr };
@@ -937,7 +944,9 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
         const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
         if (c > 0) {
             const unsigned gm = (unsigned)std::min<int64_t>(grid_m, (c + 127) / 128);
-            if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
+            static const bool lean_m = !(getenv("BVG_MERGE_LEAN") && atoi(getenv("BVG_MERGE_LEAN")) == 0);
+            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", k_scan_merge_lean, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
+            else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }
         if (g->nlong) {

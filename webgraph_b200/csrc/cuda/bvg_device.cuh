@@ -29,6 +29,8 @@ namespace bvg {
 #define BVG_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #endif
 constexpr int PREFETCH_WORDS_AHEAD = 16;
+// Zero words kept after the last stream word: readers look at most 5 words past a record.
+constexpr int STREAM_PAD_WORDS = 8;
 
 enum { C_DELTA = 1, C_GAMMA = 2, C_GOLOMB = 3, C_SKEWED_GOLOMB = 4, C_UNARY = 5, C_ZETA = 6, C_NIBBLE = 7 };
 

@@ -6,6 +6,7 @@
 // unbounded chains) and the first-round correctness baseline.
 #pragma once
 #include "bvg_device.cuh"
+#include "bvg_scan.cuh"
 
 namespace bvg {
 
@@ -130,8 +131,9 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
         const int has_iv = (d > copied && g.c.minlen != 0 && b.pos() <= limit && b.gamma() != 0) ? 1 : 0;
         if (d <= long_d) {  // longer records are split across threads (bvg_long.cuh)
             // what a lane's loop length is: residual count for the tight loop, record bits for the interval loop
+            // (and records whose list somebody copies from store it: a third kind of loop, see k_scan_extras_lean)
             const uint64_t work_e = has_iv ? g.offsets[i + 1] - g.offsets[i] : (uint64_t)(d - copied);
-            ke = (chunk * 2 + has_iv) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work_e));
+            ke = (chunk * 4 + has_iv * 2 + (is_parent[i] ? 1 : 0)) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work_e));
             if (dep >= 1 && dep <= max_level_keys) {
                 const int par = is_parent[i] ? 1 : 0;  // parents merge in place, the others only stream: separate warps too
                 const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (par ? (uint64_t)(d - copied) : 0);
@@ -155,7 +157,7 @@ struct ExtraRec {
     int64_t row;     // CSR-space offset of the first extra: rowoff[x] + copied
     int32_t x, nout; // node, successors that are not copied (d - copied)
     int32_t d;       // outdegree
-    uint32_t flags;  // bit 0: somebody copies from x (its list is materialised)
+    uint32_t flags;  // bit 0: somebody copies from x (its list is materialised); bit 1: the record has intervals
 };
 struct MergeRec {
     uint64_t pos;    // bit position of the first copy-block code
@@ -183,7 +185,7 @@ __global__ void k_key_scatter_recs(GraphDev g, const int32_t* __restrict__ key_e
         order_e[slot] = x;
         ExtraRec r;
         r.pos = extras_pos[i]; r.row = g.rowoff[i] + copied[i]; r.x = x; r.d = g.outdeg[i]; r.nout = r.d - copied[i];
-        r.flags = is_parent[i] ? 1u : 0u;
+        r.flags = (is_parent[i] ? 1u : 0u) | ((((uint32_t)ke / ORDER_BUCKETS) & 2u) ? 2u : 0u);
         rec_e[slot] = r;
     }
     if (km >= 0) {
@@ -477,6 +479,21 @@ __device__ __forceinline__ void block_fold(unsigned long long acc, long long arc
     }
 }
 
+// The same without a block barrier: one atomic pair per warp (blocks of the dynamic-grid scan kernels live for one
+// item per thread; a barrier at the end makes every warp wait for the block's longest record).
+__device__ __forceinline__ void warp_fold(unsigned long long acc, long long arcs, unsigned long long* __restrict__ result) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+        arcs += __shfl_xor_sync(0xffffffffu, arcs, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* slot = result + 2 * ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (FOLD_SLOTS - 1));
+        if (acc) atomicXor(slot + 1, acc);
+        if (arcs) atomicAdd(slot, (unsigned long long)arcs);
+    }
+}
+
 // slots[FOLD_SLOTS][2] -> out[2] (arcs added, checksum xored)
 __global__ void k_reduce_slots(const unsigned long long* __restrict__ slots, unsigned long long* __restrict__ out) {
     unsigned long long a = 0, v = 0;
@@ -529,6 +546,49 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
     block_fold(acc, arcs, result);
 }
 
+// The same step for the default codings with the lean walkers of bvg_scan.cuh.  The schedule keeps four kinds of
+// records in separate warps: (no intervals | intervals) x (only consumed | stored because somebody copies from it).
+// Only stored records with intervals need the element-wise merge of ExtrasWalk::with_intervals; everything else is the
+// tight residual loop, preceded for consumed records with intervals by a walk of the interval section that folds as it goes.
+template <int K, int LA>
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
+                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, uint32_t pf_mask) {
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
+        const int64_t i = base + (threadIdx.x & 31);
+        ExtraRec r;
+        r.x = -1; r.flags = 0;
+        if (i < count) r = recs[i];
+        bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
+        const bool store = active && (r.flags & 1u);
+        const bool fold = active && r.x >= from;
+        active = active && (fold || store);  // halo nodes matter only as parents
+        const bool has_iv = (r.flags & 2u) != 0;
+        const bool merged = active && has_iv && store;  // intervals and residuals have to come out in order
+        int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
+        unsigned long long f = 0;
+        ScanExtras<K, LA> w;
+        w.begin(g, r.x, r.nout, r.pos, active && !merged);
+        if (has_iv) w.iv_fold(g); else w.iv_none(g);
+        __syncwarp();
+        if (__any_sync(0xffffffffu, store && !merged)) w.template resid<true>(g, row, store, pf_mask);
+        else w.template resid<false>(g, row, false, pf_mask);
+        __syncwarp();
+        if (active && !merged) f = w.finish();
+        if (__any_sync(0xffffffffu, merged)) {
+            ExtrasWalk<true> o;
+            o.header_rec(g, r.x, r.d, r.nout, r.pos, merged);
+            __syncwarp();
+            o.template with_intervals<true>(g, row, merged, f);
+            __syncwarp();
+        }
+        if (fold) { acc ^= f; arcs += r.d; }
+    }
+    warp_fold(acc, arcs, result);
+}
+
 template <bool DEF>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
@@ -555,6 +615,36 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(G
         if (fold) acc ^= f;
     }
     block_fold(acc, 0, result);
+}
+
+// Merge step with the staged copy runs of bvg_scan.cuh (default codings).
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
+                             int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
+    __shared__ int32_t runs[2 * COPY_RUNS * SCAN_BLOCK];
+    unsigned long long acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
+        const int64_t i = base + (threadIdx.x & 31);
+        MergeRec r;
+        r.x = -1; r.flags = 0;
+        if (i < count) r = recs[i];
+        bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
+        const bool store = active && (r.flags & 1u);
+        const bool fold = active && r.x >= from;
+        active = active && (fold || store);
+        CopyRuns c;
+        c.begin(g, r.pos, r.bc, r.dp, runs + threadIdx.x, SCAN_BLOCK, active);
+        c.stage(g);
+        __syncwarp();
+        const int32_t* parent = active ? rm.at(r.px, r.prow) : nullptr;
+        unsigned long long f = 0;
+        if (active && !store) f = copied_fold(g, c, r.x, parent);
+        __syncwarp();
+        if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
+        __syncwarp();
+        if (fold) acc ^= f;
+    }
+    warp_fold(acc, 0, result);
 }
 
 // Rows of the long records (always materialised by the split path) folded by one warp per 1024-entry chunk.

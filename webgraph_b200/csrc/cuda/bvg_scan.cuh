@@ -1,0 +1,366 @@
+// bvg_scan.cuh -- the lean per-record walkers of the consume-only scan (default codings).
+//
+// The fused scan (k_scan_extras / k_scan_merge in bvg_kernels.cuh) is bound by the integer (alu) pipe of the SM, not by
+// memory: ncu shows the alu pipe as the busiest unit and ~57 SASS instructions per residual in the first version.  What
+// is here is the same arithmetic as ExtrasWalk / MergeWalk (bvg_device.cuh; reference BVGraph.java:1044-1100,
+// ResidualIntIterator :939-991, MaskedIntIterator.java:65-97) written for the instruction count:
+//   * Win: a sliding window of two stream words + one word of lookahead; the next code's first 32 bits are one funnel
+//     shift, a refill is three register moves and one load, and all indices are 32-bit.
+//   * zeta_k / gamma codes that fit 32 bits are decoded from that window with one count-leading-zeros and two shifts;
+//     longer ones (gaps >= 2^24 for k = 3) fall back to the position-based reader `Bits`.
+//   * the checksum fold keeps 32-bit halves: XOR of the low words plus a count of the carries into the high word
+//     (the high word of x*MIX + y is hi(x*MIX) or hi(x*MIX) + 1).
+//   * records whose list nobody copies from are only consumed, so their intervals need not be merged with their
+//     residuals: interval elements are folded while the interval section is walked, then the residuals in a tight loop.
+#pragma once
+#include "bvg_device.cuh"
+
+namespace bvg {
+
+__device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// Codes that do not fit the 32-bit window go through the position-based reader, out of line: they are rare (gaps >= 2^24
+// for zeta_3, values >= 2^16 - 1 for gamma) and inlining them at every call site triples the size of the hot loops.
+#ifdef BVG_HOST_EMULATION
+#define BVG_NOINLINE
+#else
+#define BVG_NOINLINE __noinline__
+#endif
+__device__ BVG_NOINLINE uint64_t slow_gamma(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t* pos) {
+    Bits t;
+    t.w = words; t.maxw = nwords - 3; t.pos = *pos;
+    const uint64_t r = t.gamma();
+    *pos = t.pos;
+    return r;
+}
+__device__ BVG_NOINLINE uint64_t slow_zeta(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t* pos, int k) {
+    Bits t;
+    t.w = words; t.maxw = nwords - 3; t.pos = *pos;
+    const uint64_t r = t.zeta(k);
+    *pos = t.pos;
+    return r;
+}
+
+// LA = words of lookahead (1..3).  A lane opens a new 32-byte sector of its record every eighth word and a warp-wide
+// refill load therefore almost always carries a lane that misses L1; the loaded word has to be requested long enough
+// before the funnel shift that needs it (ncu, LA = 1: 20 % of all stall samples sit on that shift).
+template <int LA>
+struct WinT {
+    const uint32_t* __restrict__ p0;  // word holding the bit the window was opened at
+    uint32_t idx, lim;                // index (from p0) of the last lookahead word; last readable index
+    uint32_t w0, w1, q0, q1, q2;      // current two words, lookahead queue (q0 next; q1, q2 used when LA >= 2, 3)
+    uint32_t s;                       // bits of w0 already consumed, 0..31
+
+    __device__ __forceinline__ void seek(const GraphDev& g, uint64_t pos) {
+        uint64_t i = pos >> 5;
+        const uint64_t last = g.nwords - 1;
+        if (i > last) i = last;  // a corrupt stream can point past the end: clamp, the caller reports E_IO
+        p0 = g.words + i;
+        const uint64_t room = last - i;
+        lim = room > 0x7fffffffull ? 0x7fffffffu : (uint32_t)room;
+        s = (uint32_t)pos & 31u;
+        w0 = p0[0];
+        w1 = p0[umin32(1u, lim)];
+        q0 = p0[umin32(2u, lim)];
+        q1 = q2 = 0;
+        if (LA >= 2) q1 = p0[umin32(3u, lim)];
+        if (LA >= 3) q2 = p0[umin32(4u, lim)];
+        idx = umin32(1u + LA, lim);
+    }
+    // bit position relative to word 0 of the stream buffer (exact unless the window ran into the end of the buffer)
+    __device__ __forceinline__ uint64_t pos(const GraphDev& g) const {
+        return ((uint64_t)(p0 - g.words) + idx - (1u + LA)) * 32u + s;
+    }
+    __device__ __forceinline__ bool overrun() const { return idx >= lim; }
+    // Fire-and-forget L1 prefetch `words` past the lookahead word.  The refill loads cannot run far ahead by themselves:
+    // ptxas tracks them with one scoreboard, and the loop waits on it every trip, so a refill that misses L1 stalls the
+    // warp for the full memory latency however many words of lookahead the window keeps.  Called once every few codes.
+    __device__ __forceinline__ void prefetch(uint32_t words) const { BVG_PREFETCH_L1(p0 + umin32(idx + words, lim)); }
+    __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, s); }
+    __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
+        s += n;
+        if (s >= 32u) {
+            s -= 32u;
+            w0 = w1;
+            w1 = q0;
+            idx = umin32(idx + 1u, lim);
+            if (LA == 1) q0 = p0[idx];
+            if (LA == 2) { q0 = q1; q1 = p0[idx]; }
+            if (LA == 3) { q0 = q1; q1 = q2; q2 = p0[idx]; }
+        }
+    }
+    __device__ __forceinline__ uint64_t gamma_slow(const GraphDev& g) {
+        uint64_t p = pos(g);
+        const uint64_t r = slow_gamma(g.words, g.nwords, &p);
+        seek(g, p);
+        return r;
+    }
+    __device__ __forceinline__ uint64_t zeta_slow(const GraphDev& g, int k) {
+        uint64_t p = pos(g);
+        const uint64_t r = slow_zeta(g.words, g.nwords, &p, k);
+        seek(g, p);
+        return r;
+    }
+    // gamma (BVGraph's block, block-count, interval codes): 32-bit window when the code has at most 31 bits
+    __device__ __forceinline__ uint64_t gamma(const GraphDev& g) {
+        const uint32_t t = top();
+        const int m = __clz((int)t);
+        if (m <= 15) {
+            skip(2u * m + 1u);
+            return (uint64_t)((t >> (31 - 2 * m)) - 1u);
+        }
+        return gamma_slow(g);
+    }
+};
+#ifndef BVG_WIN_LA
+#define BVG_WIN_LA 1
+#endif
+typedef WinT<1> Win;  // block lists and interval sections: a few codes per record
+
+// zeta_k code that fits the 32-bit window: m = value + 1, len = code length.  K = 3 is BVGraph's default and gets
+// constants; K = 0 takes k at run time.  With h = leading zeros, P = 2^(hk): the bits after the unary part, read with
+// the stop bit as r = 1:m' (hk + k bits after the leading one), give the short form iff r < P(2^k + 2).
+template <int K>
+__device__ __forceinline__ bool zeta_fast(uint32_t t, int k, uint32_t& m, uint32_t& len) {
+    const int h = __clz((int)t);
+    if (K == 3) {
+        if (h > 7) return false;
+        const uint32_t r = t >> (28 - 4 * h);
+        const uint32_t P8 = 8u << (3 * h);          // the leading one of r
+        const bool sh = 4u * r < 5u * P8;           // r < 10 P
+        m = sh ? (4u * r - 3u * P8) >> 3 : r - P8;  // (r >> 1) - 3 P : r - 8 P
+        len = 4u * h + (sh ? 3u : 4u);
+        return true;
+    } else {
+        const int hk = h * k;
+        const int total = h + 1 + hk + k;  // long form
+        if (total > 32) return false;
+        const uint32_t r = t >> (32 - total);
+        const uint32_t P = 1u << hk;
+        const uint32_t two_k = 1u << k;
+        const bool sh = r < P * (two_k + 2u);
+        m = sh ? (r >> 1) - P * ((two_k >> 1) - 1u) : r - P * two_k;
+        len = (uint32_t)total - (sh ? 1u : 0u);
+        return true;
+    }
+}
+
+template <int K, class W>
+__device__ __forceinline__ uint64_t zeta_any(W& b, const GraphDev& g, int k) {  // value + 1
+    uint32_t m, len;
+    if (zeta_fast<K>(b.top(), k, m, len)) { b.skip(len); return m; }
+    return b.zeta_slow(g, k) + 1ull;
+}
+
+// 32-bit halves of the checksum of one record: XOR of lo(base + y), number of carries out of the low word.
+struct Fold32 {
+    uint32_t base_lo, xlo, carries, n;
+    __device__ __forceinline__ void begin(int32_t x) { base_lo = (uint32_t)((unsigned long long)(uint32_t)x * BVG_MIX); xlo = 0; carries = 0; n = 0; }
+    __device__ __forceinline__ void add(uint32_t y) {
+        const uint32_t lo = base_lo + y;
+        carries += lo < y ? 1u : 0u;
+        xlo ^= lo;
+    }
+    // XOR over the n folded successors of (x*MIX + y): hi word is base_hi for the ones without a carry, base_hi + 1 with
+    __device__ __forceinline__ unsigned long long finish(int32_t x) const {
+        const uint32_t base_hi = (uint32_t)(((unsigned long long)(uint32_t)x * BVG_MIX) >> 32);
+        uint32_t hi = 0;
+        if ((n - carries) & 1u) hi ^= base_hi;
+        if (carries & 1u) hi ^= base_hi + 1u;
+        return ((unsigned long long)hi << 32) | xlo;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Extras of one record (everything that is not copied), consume-only or into the row when `store`.
+// Entry: the cursor at the extras section (ExtraRec.pos), nout = outdegree - copied.
+//   phase iv()      interval section; fold-only records fold the elements here, storing records take the merge of
+//                   ExtrasWalk::with_intervals instead (kept in separate warps by the schedule)
+//   phase resid()   residuals, tight loop
+// ---------------------------------------------------------------------------------------------------
+template <int K, int LA = BVG_WIN_LA>
+struct ScanExtras {
+    WinT<LA> b;
+    Fold32 f;
+    int32_t x, nout, rc;
+    uint32_t v;
+    int err;
+
+    __device__ __forceinline__ void fail(const GraphDev& g, int code) {
+        report(g.err, code, x, b.pos(g) + g.bit_base);
+        err = code; rc = 0;
+    }
+
+    __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active) {
+        x = x_; nout = 0; rc = 0; err = 0; v = 0;
+        f.begin(x_);
+        if (!active) return;
+        nout = nout_;
+        rc = nout_;
+        b.seek(g, pos);
+    }
+
+    // Interval section of a record that is only consumed (IntIntervalSequenceIterator.java:57-95, BVGraph.java:1076-1095)
+    __device__ __forceinline__ void iv_fold(const GraphDev& g) {
+        if (nout <= 0 || g.c.minlen == 0) return;
+        const uint64_t ic = b.gamma(g);
+        if (ic > (uint64_t)nout) { fail(g, E_IO); return; }
+        int64_t total = 0;
+        uint32_t prev = 0;
+        for (uint32_t i = 0; i < (uint32_t)ic; i++) {
+            uint32_t left;
+            if (i == 0) left = (uint32_t)(int32_t)(nat2int(b.gamma(g)) + (int64_t)x);
+            else left = prev + 1u + (uint32_t)b.gamma(g);
+            const uint64_t len64 = b.gamma(g) + (uint64_t)g.c.minlen;
+            total += (int64_t)len64;
+            if (total > (int64_t)nout || b.overrun()) { fail(g, E_IO); return; }
+            const uint32_t len = (uint32_t)len64;
+            for (uint32_t j = 0; j < len; j++) f.add(left + j);
+            prev = left + len;
+        }
+        rc = nout - (int32_t)total;
+    }
+
+    // Interval section skipped over (storing records without intervals still carry the count)
+    __device__ __forceinline__ void iv_none(const GraphDev& g) {
+        if (nout <= 0 || g.c.minlen == 0) return;
+        const uint64_t ic = b.gamma(g);
+        if (ic != 0) fail(g, E_FORMAT);  // the schedule said "no intervals"
+    }
+
+    // Residuals (ResidualIntIterator, BVGraph.java:939-972): first = x + nat2int(zeta), then += zeta + 1.
+    template <bool STORE>
+    __device__ __forceinline__ void resid(const GraphDev& g, int32_t* __restrict__ row, bool store, uint32_t pf_mask) {
+        if (rc <= 0) return;
+        const int k = g.c.zetak;
+        v = (uint32_t)(int32_t)((int64_t)x + nat2int(zeta_any<K>(b, g, k) - 1ull));  // :954
+        f.add(v);
+        if (STORE && store) row[0] = (int32_t)v;
+#pragma unroll 1
+        for (int32_t i = 1; i < rc; i++) {
+            if (((uint32_t)i & pf_mask) == 1u) b.prefetch(PREFETCH_WORDS_AHEAD);
+            uint32_t m, len;
+            if (zeta_fast<K>(b.top(), k, m, len)) b.skip(len);
+            else m = (uint32_t)(b.zeta_slow(g, k) + 1ull);
+            v += m;  // :966 (gap + 1)
+            f.add(v);
+            if (STORE && store) row[i] = (int32_t)v;
+        }
+        if (b.overrun() || b.pos(g) > g.bit_end - g.bit_base) fail(g, E_IO);
+    }
+
+    __device__ __forceinline__ unsigned long long finish() {
+        f.n = (uint32_t)nout;
+        return err ? 0ull : f.finish(x);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Copied part of one record (MaskedIntIterator.java:65-97): the copy-block list is parsed first, a few blocks at a
+// time, into a short list of non-empty copy runs [start, end) of parent positions kept in shared memory; the element
+// loops then only compare an index with the end of the current run.  With the parse inside the element loop (the flat
+// loop of MergeWalk) every trip of a warp pays for a gamma decode as soon as one of its 32 lanes sits at a block
+// boundary, which is almost always (ncu: 2.2 active lanes on the boundary path, 20 % of the kernel's instructions).
+// ---------------------------------------------------------------------------------------------------
+constexpr int COPY_RUNS = 8;  // runs staged per lane at a time (16 blocks); longer lists are staged in rounds
+
+struct CopyRuns {
+    Win b;
+    int32_t* __restrict__ st;   // this lane's slots: start of run i at st[2 * i * stride], end at st[(2 * i + 1) * stride]
+    int32_t stride;
+    uint32_t bc, bi;            // blocks in the list, blocks parsed (bi == bc + 1: the implicit tail has been handled too)
+    uint32_t ppos, dp;          // parent position after the parsed blocks, parent outdegree
+    int32_t nr, r;              // runs staged, next run to take
+    uint32_t pos, end;          // current run
+
+    __device__ __forceinline__ void begin(const GraphDev& g, uint64_t recpos, int32_t bc_, int32_t dp_, int32_t* slots, int32_t stride_, bool active) {
+        st = slots; stride = stride_;
+        bc = (uint32_t)bc_; bi = 0; ppos = 0; dp = (uint32_t)dp_; nr = 0; r = 0; pos = 0; end = 0;
+        if (!active) { bi = 1; bc = 0; dp = 0; return; }  // nothing to stage, nothing to copy
+        if (bc) b.seek(g, recpos);
+    }
+    // Parses blocks until COPY_RUNS runs are staged or the list (and its implicit tail: an even number of blocks copies
+    // the rest of the parent, MaskedIntIterator.java:76) is exhausted.  Positions are clamped to the parent's outdegree,
+    // so a malformed list can make the result wrong but never the reads out of bounds.
+    __device__ __forceinline__ void stage(const GraphDev& g) {
+        nr = 0; r = 0;
+        while (nr < COPY_RUNS && bi <= bc) {
+            if (bi == bc) {
+                if (!(bc & 1u) && ppos < dp) { st[2 * nr * stride] = (int32_t)ppos; st[(2 * nr + 1) * stride] = (int32_t)dp; nr++; ppos = dp; }
+                bi++;
+                break;
+            }
+            const uint64_t raw = b.gamma(g);
+            uint32_t len = raw > 0x7fffffffull ? 0x7fffffffu : (uint32_t)raw;
+            if (bi) len++;
+            const uint32_t e = umin32(ppos + len, dp);
+            if (!(bi & 1u) && e > ppos) { st[2 * nr * stride] = (int32_t)ppos; st[(2 * nr + 1) * stride] = (int32_t)e; nr++; }
+            ppos = e;
+            bi++;
+        }
+    }
+    __device__ __forceinline__ bool done() const { return pos == end && r == nr && bi > bc; }
+    // next parent position to copy; false when the list is exhausted
+    __device__ __forceinline__ bool next(const GraphDev& g, uint32_t& at) {
+        if (pos == end) {
+            if (r == nr) {
+                if (bi > bc) return false;
+                stage(g);
+                if (nr == 0) return false;
+            }
+            pos = (uint32_t)st[2 * r * stride];
+            end = (uint32_t)st[(2 * r + 1) * stride];
+            r++;
+        }
+        at = pos++;
+        return true;
+    }
+};
+
+// nobody copies from x: its copied successors are only consumed
+__device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CopyRuns& c, int32_t x, const int32_t* __restrict__ parent) {
+    Fold32 f;
+    f.begin(x);
+    uint32_t at;
+#pragma unroll 1
+    while (c.next(g, at)) { f.add((uint32_t)parent[at]); f.n++; }
+    return f.finish(x);
+}
+
+// somebody copies from x: merge the copied successors, forward and in place, with the extras at row[copied .. d)
+// (MergedIntIterator.java:50-74: ascending union, equal heads once; a list that loses duplicates is padded with -1 as
+// BVGraphNodeIterator does when it drains, BVGraph.java:1210).  Folds the copied successors only: the extras were
+// folded when they were decoded.
+__device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CopyRuns& c, int32_t x, int32_t d, int32_t copied,
+                                                           int32_t* __restrict__ row, const int32_t* __restrict__ parent) {
+    Fold32 f;
+    f.begin(x);
+    int32_t j = copied, k = 0;
+    uint32_t at;
+    bool have_a = c.next(g, at);
+    uint32_t a = have_a ? (uint32_t)parent[at] : 0xffffffffu;
+    uint32_t bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
+#pragma unroll 1
+    while (k < d) {
+        if (!have_a) {
+            if (k == j) break;  // nothing was dropped: the remaining extras already sit in place
+            if (j < d) { row[k++] = (int32_t)bv; j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; continue; }
+            row[k++] = -1;      // duplicates were dropped
+            continue;
+        }
+        if (a <= bv) {
+            row[k++] = (int32_t)a;
+            f.add(a); f.n++;
+            if (a == bv) { j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; }  // equal heads are emitted once
+            have_a = c.next(g, at);
+            if (have_a) a = (uint32_t)parent[at];
+        } else {
+            row[k++] = (int32_t)bv;
+            j++;
+            bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
+        }
+    }
+    return f.finish(x);
+}
+
+}  // namespace bvg
