@@ -93,11 +93,13 @@ struct bvg_graph {
     int32_t *d_cb_cum = nullptr, *d_cb_ppos = nullptr, *d_iv_cum = nullptr, *d_iv_left = nullptr;
     uint64_t* d_seg_pos = nullptr;
     int64_t* d_seg_val = nullptr;
-    LongItem *d_items_resid = nullptr, *d_items_extras = nullptr, *d_items_merge = nullptr;
-    RowChunk* d_items_fold = nullptr;
+    // per-scan work items of the long records: running item counts per record (ItemMap, bvg_long.cuh), one array of
+    // nlong + 1 entries per item family: [residual segments | row chunks | extras chunks | merge chunks of level 1, 2, ...]
+    int64_t* d_long_cum = nullptr;
     int64_t n_items_fold = 0;
     int64_t n_items_resid = 0, n_items_extras = 0;
-    std::vector<int64_t> merge_item_start;  // items of chain level l+1: d_items_merge[merge_item_start[l] .. [l+1])
+    std::vector<int64_t> n_items_merge;  // [level]
+    ItemMap item_map(int family) const { return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong }; }
     int64_t long_tmp_entries = 0;
     // tunables (BVG_LONG_D / BVG_LONG_SEG / BVG_LONG_CHUNK override the defaults of bvg_long.cuh)
     int32_t long_d = LONG_D, long_seg = LONG_SEG, long_chunk = LONG_CHUNK;
@@ -284,28 +286,36 @@ static int build_long_index(bvg_graph* g) {
     long_nodes.p = g->d_long_nodes;
     LAUNCH(k_long_compact, grid_for(nn, 256), 256, 0, s, flags.p, pos.p, nn, g->node_lo, long_nodes.p);
     CK(cudaMallocAsync((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta), g->stream));
-    if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
-    else LAUNCH(k_long_count<false>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_long_meta);
+    if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_is_parent, g->d_long_meta);
+    else LAUNCH(k_long_count<false>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_is_parent, g->d_long_meta);
     std::vector<LongMeta> meta((size_t)nl);
     CK(cudaMemcpyAsync(meta.data(), g->d_long_meta, (size_t)nl * sizeof(LongMeta), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    // Array offsets and running item counts: one pass over the long records (not over their items).
+    const size_t stride = (size_t)nl + 1;
+    const int32_t levels = g->max_depth;
+    const int fam_spec = 3 + levels;  // families: 0 residual segments, 1 row chunks, 2 extras chunks, 3.. merge chunks per level, then sub-ranges
+    std::vector<int64_t> cum((size_t)(fam_spec + 1) * stride, 0);
     int64_t cb = 0, iv = 0, seg = 0, tmp = 0;
-    std::vector<LongItem> it_r, it_x;
-    std::vector<RowChunk> it_f;
-    std::vector<std::vector<LongItem>> it_m((size_t)g->max_depth + 1);
     for (int64_t l = 0; l < nl; l++) {
         LongMeta& m = meta[(size_t)l];
         m.cb_off = cb; cb += (int64_t)m.ncb + 1;
         m.iv_off = iv; iv += (int64_t)m.ic + 1;
         m.seg_off = seg;
-        const int32_t nseg = (m.rc + LSEG - 1) / LSEG;
+        const int64_t nseg = ((int64_t)m.rc + LSEG - 1) / LSEG;
         seg += nseg;
         m.tmp_off = tmp; tmp += 2 * (int64_t)m.d;
-        for (int32_t q = 0; q < nseg; q++) it_r.push_back(LongItem{ (int32_t)l, q });
-        for (int32_t q = 0; q * FOLD_CHUNK < m.d; q++) it_f.push_back(RowChunk{ m.x, q });
-        if (m.ic > 0) for (int32_t q = 0; (int64_t)q * LCHUNK < (int64_t)m.ilen + m.rc; q++) it_x.push_back(LongItem{ (int32_t)l, q });
-        if (m.copied > 0 && m.level >= 1) for (int32_t q = 0; (int64_t)q * LCHUNK < m.d; q++) it_m[(size_t)m.level].push_back(LongItem{ (int32_t)l, q });
+        int64_t add[3] = { nseg, ((int64_t)m.d + FOLD_CHUNK - 1) / FOLD_CHUNK, m.ic > 0 ? ((int64_t)m.ilen + m.rc + LCHUNK - 1) / LCHUNK : 0 };
+        for (int f = 0; f < 3; f++) cum[(size_t)f * stride + (size_t)l + 1] = cum[(size_t)f * stride + (size_t)l] + add[f];
+        for (int32_t lv = 1; lv <= levels; lv++)
+            cum[(size_t)(2 + lv) * stride + (size_t)l + 1] = cum[(size_t)(2 + lv) * stride + (size_t)l] +
+                ((m.copied > 0 && m.level == lv) ? ((int64_t)m.d + LCHUNK - 1) / LCHUNK : 0);
+        cum[(size_t)fam_spec * stride + (size_t)l + 1] = cum[(size_t)fam_spec * stride + (size_t)l] +
+            (m.rc > 0 ? (int64_t)((m.rec_end - m.resid_pos + (uint64_t)LSPEC_BITS - 1) / (uint64_t)LSPEC_BITS) : 0);
     }
+    g->nlong = (int32_t)nl;  // item_map() below needs it; reset on failure by the caller's destroy
+    CK(cudaMallocAsync((void**)&g->d_long_cum, cum.size() * 8, g->stream));
+    CK(cudaMemcpyAsync(g->d_long_cum, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), cudaMemcpyHostToDevice, s));
     CK(cudaMallocAsync((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
     CK(cudaMallocAsync((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
@@ -316,91 +326,54 @@ static int build_long_index(bvg_graph* g) {
     // copy blocks and intervals: one short walk per record; residual sync points: speculative sub-ranges (bvg_long.cuh)
     if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
     else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
-    {
-        std::vector<SpecItem> items;
-        for (int64_t l = 0; l < nl; l++) {
-            const LongMeta& m = meta[(size_t)l];
-            if (m.rc <= 0) continue;
-            for (uint64_t lo = m.resid_pos; lo < m.rec_end; lo += (uint64_t)LSPEC_BITS) {
-                SpecItem it{};
-                it.lo = lo; it.hi = std::min<uint64_t>(lo + (uint64_t)LSPEC_BITS, m.rec_end); it.l = (int32_t)l; it.first = lo == m.resid_pos ? 1 : 0;
-                items.push_back(it);
-            }
+    const int64_t ni = cum[(size_t)fam_spec * stride + (size_t)nl];
+    if (ni > 0) {
+        const ItemMap im = g->item_map(fam_spec);
+        Tmp<SpecItem> ia(s), ib(s);
+        Tmp<int> changed(s);
+        Tmp<int64_t> v0(s), cbase(s), sbase(s);
+        CK(ia.alloc((size_t)ni));
+        CK(ib.alloc((size_t)ni));
+        CK(changed.alloc(1));
+        CK(v0.alloc((size_t)nl));
+        CK(cbase.alloc((size_t)ni));
+        CK(sbase.alloc((size_t)ni));
+        LAUNCH(k_lspec_init, grid_for(ni, 128), 128, 0, s, g->d_long_meta, im, ni, ia.p);
+        if (g->def_codec) {
+            LAUNCH(k_lspec_first<true>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
+            LAUNCH(k_lspec_speculate<true>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
+        } else {
+            LAUNCH(k_lspec_first<false>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
+            LAUNCH(k_lspec_speculate<false>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
         }
-        const int64_t ni = (int64_t)items.size();
-        if (ni > 0) {
-            Tmp<SpecItem> ia(s), ib(s);
-            Tmp<int> changed(s);
-            Tmp<int64_t> v0(s), cbase(s), sbase(s);
-            CK(ia.alloc((size_t)ni));
-            CK(ib.alloc((size_t)ni));
-            CK(changed.alloc(1));
-            CK(v0.alloc((size_t)nl));
-            CK(cudaMemcpyAsync(ia.p, items.data(), (size_t)ni * sizeof(SpecItem), cudaMemcpyHostToDevice, s));
-            if (g->def_codec) {
-                LAUNCH(k_lspec_first<true>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
-                LAUNCH(k_lspec_speculate<true>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
-            } else {
-                LAUNCH(k_lspec_first<false>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
-                LAUNCH(k_lspec_speculate<false>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
-            }
-            SpecItem *in = ia.p, *out = ib.p;
-            for (int64_t pass = 0;; pass++) {
-                CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
-                if (g->def_codec) LAUNCH(k_lspec_fix<true>, grid_for(ni, 128), 128, 0, s, gd, in, out, ni, changed.p);
-                else LAUNCH(k_lspec_fix<false>, grid_for(ni, 128), 128, 0, s, gd, in, out, ni, changed.p);
-                int ch = 0;
-                CK(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-                CK(cudaStreamSynchronize(s));
-                std::swap(in, out);
-                if (!ch) break;
-                if (pass > ni + 2) return BVG_EIO;
-            }
-            CK(cudaMemcpyAsync(items.data(), in, (size_t)ni * sizeof(SpecItem), cudaMemcpyDeviceToHost, s));
+        SpecItem *in = ia.p, *out = ib.p;
+        for (int64_t pass = 0;; pass++) {
+            CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
+            if (g->def_codec) LAUNCH(k_lspec_fix<true>, grid_for(ni, 128), 128, 0, s, gd, in, out, ni, changed.p);
+            else LAUNCH(k_lspec_fix<false>, grid_for(ni, 128), 128, 0, s, gd, in, out, ni, changed.p);
+            int ch = 0;
+            CK(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            std::vector<int64_t> cb((size_t)ni), sb((size_t)ni);
-            int64_t c = 0, sum = 0;
-            for (int64_t j = 0; j < ni; j++) {
-                if (items[(size_t)j].first) { c = 0; sum = 0; }
-                cb[(size_t)j] = c; sb[(size_t)j] = sum;
-                c += items[(size_t)j].count; sum += items[(size_t)j].sum;
-                const bool last = j + 1 == ni || items[(size_t)j + 1].first;
-                if (last && c != meta[(size_t)items[(size_t)j].l].rc) return BVG_EFORMAT;  // the record does not hold rc residuals
-            }
-            CK(cbase.alloc((size_t)ni));
-            CK(sbase.alloc((size_t)ni));
-            CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)ni * 8, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(sbase.p, sb.data(), (size_t)ni * 8, cudaMemcpyHostToDevice, s));
-            if (g->def_codec) LAUNCH(k_lspec_emit<true>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
-            else LAUNCH(k_lspec_emit<false>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
-            CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(s));
+            std::swap(in, out);
+            if (!ch) break;
+            if (pass > ni + 2) return BVG_EIO;
         }
+        LAUNCH(k_lspec_scan, grid_for(nl, 64), 64, 0, s, gd, g->d_long_meta, im, in, cbase.p, sbase.p);
+        if (g->def_codec) LAUNCH(k_lspec_emit<true>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
+        else LAUNCH(k_lspec_emit<false>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s));
+        const int e = fetch_error(g);  // a record that does not hold rc residuals (k_lspec_scan)
+        if (e) return e;
     }
-    std::vector<LongItem> merged;
-    g->merge_item_start.assign((size_t)g->max_depth + 1, 0);
-    for (int32_t lv = 1; lv <= g->max_depth; lv++) {
-        g->merge_item_start[(size_t)lv - 1] = (int64_t)merged.size();
-        merged.insert(merged.end(), it_m[(size_t)lv].begin(), it_m[(size_t)lv].end());
-    }
-    g->merge_item_start[(size_t)g->max_depth] = (int64_t)merged.size();
-    auto upload = [&](const std::vector<LongItem>& v, LongItem** dst) -> cudaError_t {
-        cudaError_t e = cudaMallocAsync((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(LongItem), s);
-        if (e != cudaSuccess) return e;
-        return v.empty() ? cudaSuccess : cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(LongItem), cudaMemcpyHostToDevice, s);
-    };
-    CK(upload(it_r, &g->d_items_resid));
-    CK(upload(it_x, &g->d_items_extras));
-    CK(upload(merged, &g->d_items_merge));
-    CK(cudaMallocAsync((void**)&g->d_items_fold, std::max<size_t>(it_f.size(), 1) * sizeof(RowChunk), g->stream));
-    if (!it_f.empty()) CK(cudaMemcpyAsync(g->d_items_fold, it_f.data(), it_f.size() * sizeof(RowChunk), cudaMemcpyHostToDevice, s));
-    g->n_items_fold = (int64_t)it_f.size();
-    g->n_items_resid = (int64_t)it_r.size();
-    g->n_items_extras = (int64_t)it_x.size();
+    g->n_items_resid = cum[0 * stride + (size_t)nl];
+    g->n_items_fold = cum[1 * stride + (size_t)nl];
+    g->n_items_extras = cum[2 * stride + (size_t)nl];
+    g->n_items_merge.assign((size_t)levels + 1, 0);
+    for (int32_t lv = 1; lv <= levels; lv++) g->n_items_merge[(size_t)lv] = cum[(size_t)(2 + lv) * stride + (size_t)nl];
     g->long_tmp_entries = tmp;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s));
-    g->nlong = (int32_t)nl;
+    CK(cudaStreamSynchronize(s));  // cum / meta are host vectors
     return BVG_OK;
 }
 
@@ -521,8 +494,7 @@ static void destroy(bvg_graph* g) {
     // to the driver, which is what makes open-scan-close cycles cheap
     void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
                      g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
-                     g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_items_resid, g->d_items_extras, g->d_items_merge,
-                     g->d_items_fold };
+                     g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum };
     for (void* p : ptrs) if (p) cudaFreeAsync(p, g->stream);
     cudaStreamSynchronize(g->stream);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
@@ -842,9 +814,12 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
         if (g->nlong) {
             CK(long_tmp.alloc((size_t)g->long_tmp_entries));
             ld.tmp = long_tmp.p;
-            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
-            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
-            if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->d_items_extras, g->n_items_extras, lo, to, rm, ld);
+            const LongFold lf{ nullptr, 0 };  // range decode: every long record is materialised
+            if (g->n_items_resid) {
+                if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+                else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            }
+            if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
         }
         for (int32_t level = 1; level <= g->max_depth; level++) {
             const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
@@ -853,8 +828,8 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
                 else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
             }
             if (g->nlong) {
-                const int64_t ma = g->merge_item_start[(size_t)level - 1], mc = g->merge_item_start[(size_t)level] - ma;
-                if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->d_items_merge + ma, mc, lo, to, rm, ld);
+                const int64_t mc = g->n_items_merge[(size_t)level];
+                if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, LongFold{ nullptr, 0 });
             }
         }
         CK(cudaGetLastError());
@@ -933,12 +908,15 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     Tmp<int32_t> long_tmp(s);
     LongDst ld{ nullptr };
     const LongIndex li = g->long_index();
+    const LongFold lf{ d_result, from };  // long records nobody copies from are folded where their parts are produced
     if (g->nlong) {
         CK(long_tmp.alloc((size_t)g->long_tmp_entries));
         ld.tmp = long_tmp.p;
-        if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
-        else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->d_items_resid, g->n_items_resid, lo, to, rm, ld);
-        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->d_items_extras, g->n_items_extras, lo, to, rm, ld);
+        if (g->n_items_resid) {
+            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+        }
+        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
         const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
@@ -950,14 +928,12 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }
         if (g->nlong) {
-            const int64_t ma = g->merge_item_start[(size_t)level - 1], mc = g->merge_item_start[(size_t)level] - ma;
-            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->d_items_merge + ma, mc, lo, to, rm, ld);
+            const int64_t mc = g->n_items_merge[(size_t)level];
+            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
         }
     }
-    if (g->nlong && g->n_items_fold) {
-        const unsigned gl = (unsigned)std::min<int64_t>(148 * 8, (g->n_items_fold + 7) / 8);
-        LAUNCH_P(g, "k_checksum_chunks", k_checksum_chunks, gl, 256, 0, s, gd, g->d_items_fold, g->n_items_fold, from, to, rm, d_result);
-    }
+    if (g->nlong && g->n_items_fold)
+        LAUNCH_P(g, "k_long_fold_rows", k_long_fold_rows<RowMap>, grid_for(g->n_items_fold * 32, 256), 256, 0, s, gd, li, g->item_map(1), g->n_items_fold, lo, to, rm, lf);
     CK(cudaGetLastError());
     return BVG_OK;
 }

@@ -450,8 +450,6 @@ __global__ void k_mark_parents(GraphDev g, uint8_t* __restrict__ is_parent) {
     if (r > 0 && r <= i) is_parent[i - r] = 1;
 }
 
-constexpr int FOLD_SLOTS = 1024;
-
 __device__ __forceinline__ void block_fold(unsigned long long acc, long long arcs, unsigned long long* __restrict__ result) {
     __shared__ unsigned long long s_x[32];
     __shared__ long long s_a[32];
@@ -476,21 +474,6 @@ __device__ __forceinline__ void block_fold(unsigned long long acc, long long arc
             if (v) atomicXor(slot + 1, v);
             if (a) atomicAdd(slot, (unsigned long long)a);
         }
-    }
-}
-
-// The same without a block barrier: one atomic pair per warp (blocks of the dynamic-grid scan kernels live for one
-// item per thread; a barrier at the end makes every warp wait for the block's longest record).
-__device__ __forceinline__ void warp_fold(unsigned long long acc, long long arcs, unsigned long long* __restrict__ result) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
-        arcs += __shfl_xor_sync(0xffffffffu, arcs, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        unsigned long long* slot = result + 2 * ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (FOLD_SLOTS - 1));
-        if (acc) atomicXor(slot + 1, acc);
-        if (arcs) atomicAdd(slot, (unsigned long long)arcs);
     }
 }
 
@@ -645,28 +628,6 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_l
         if (fold) acc ^= f;
     }
     warp_fold(acc, 0, result);
-}
-
-// Rows of the long records (always materialised by the split path) folded by one warp per 1024-entry chunk.
-struct RowChunk { int32_t x, part; };
-constexpr int32_t FOLD_CHUNK = 1024;
-
-__global__ void k_checksum_chunks(GraphDev g, const RowChunk* __restrict__ items, int64_t count, int32_t lo, int32_t hi,
-                                  RowMap rm, unsigned long long* __restrict__ result) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    unsigned long long acc = 0;
-    long long arcs = 0;
-    for (int64_t i = (int64_t)blockIdx.x * nw + wid; i < count; i += (int64_t)gridDim.x * nw) {
-        const RowChunk it = items[i];
-        if (it.x < lo || it.x >= hi) continue;
-        const int32_t d = g.outdeg[it.x - g.node_lo];
-        const int32_t a = it.part * FOLD_CHUNK, e = min(d, a + FOLD_CHUNK);
-        const int32_t* row = rm.row(g, it.x);
-        const unsigned long long base = (unsigned long long)(uint32_t)it.x * BVG_MIX;
-        for (int32_t p = a + lane; p < e; p += 32) acc ^= base + (unsigned long long)(uint32_t)row[p];
-        if (lane == 0) arcs += e - a;
-    }
-    block_fold(acc, arcs, result);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 // sequential kernels' -1 fill semantics only on the short path; the merge path assumes the three parts are disjoint.
 #pragma once
 #include "bvg_device.cuh"
+#include "bvg_scan.cuh"
 
 namespace bvg {
 
@@ -35,7 +36,7 @@ struct LongMeta {
     int32_t ic, ilen;     // intervals and their total length
     int32_t rc;           // residuals
     int32_t level;        // reference-chain depth
-    int32_t pad_;
+    int32_t flags;        // bit 0: somebody copies from this record (its list has to exist during a consume-only scan)
     int64_t cb_off;       // cb_cum[cb_off .. +ncb] (ncb+1 entries), cb_ppos[cb_off - l .. ] (ncb entries): see LongIndex
     int64_t iv_off;       // iv_cum[iv_off .. +ic] (ic+1 entries), iv_left (ic entries)
     int64_t seg_off;      // seg_pos / seg_val, ceil(rc / LONG_SEG) entries
@@ -336,16 +337,31 @@ __device__ void merge_chunk(const A& a, ValueOf value_of, const int32_t* __restr
 // ---------------------------------------------------------------------------------------------------
 // Kernels.  Items are (long record, segment | chunk) pairs listed at open.
 // ---------------------------------------------------------------------------------------------------
-struct LongItem { int32_t l, part; };
+// Work items of every per-scan kernel are (long record, part) pairs.  They are not listed: item i belongs to the record l
+// with cum[l] <= i < cum[l + 1] (cum = running item count per record, nlong + 1 entries built at open), found by
+// binary search; a list would cost one host-side push per 128 successors of every long record at every open.
+struct ItemMap {
+    const int64_t* __restrict__ cum;
+    int32_t nlong;
+    __device__ __forceinline__ void find(int64_t i, int32_t& l, int32_t& part) const {
+        int32_t lo = 0, hi = nlong;  // invariant: cum[lo] <= i < cum[hi]
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (cum[mid] <= i) lo = mid; else hi = mid;
+        }
+        l = lo; part = (int32_t)(i - cum[lo]);
+    }
+};
 
 template <bool DEF>
-__global__ void k_long_count(GraphDev g, const int32_t* __restrict__ long_nodes, int32_t nlong, LongMeta* __restrict__ meta) {
+__global__ void k_long_count(GraphDev g, const int32_t* __restrict__ long_nodes, int32_t nlong, const uint8_t* __restrict__ is_parent,
+                             LongMeta* __restrict__ meta) {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlong) return;
     LongMeta m;
     m.x = long_nodes[l];
     m.level = g.depth[m.x - g.node_lo];
-    m.pad_ = 0;
+    m.flags = (is_parent && is_parent[m.x - g.node_lo]) ? 1 : 0;
     m.rec_end = g.offsets[m.x - g.node_lo + 1] - g.bit_base;
     long_walk<DEF>(g, m, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     m.cb_off = m.iv_off = m.seg_off = m.tmp_off = 0;
@@ -375,47 +391,191 @@ struct LongDst {
     }
 };
 
+// Consume-only scans (`fold` != nullptr) materialise a long record only when somebody copies from it; the successors of
+// every other long record are folded where they are produced: residual segments here, interval elements in
+// k_long_extras, copied elements in k_long_merge (the three parts of a list are disjoint, so the order they are
+// consumed in is immaterial to the checksum).
+struct LongFold {
+    unsigned long long* result;   // FOLD_SLOTS slot pairs; nullptr = materialise everything (range decode)
+    int32_t from;                 // nodes below `from` are halo: they matter only as parents
+    __device__ __forceinline__ bool only_consumed(const LongMeta& m) const { return result != nullptr && !(m.flags & 1); }
+};
+
+#ifndef BVG_HOST_EMULATION
 template <bool DEF, class RM>
-__global__ void k_long_resid(GraphDev g, LongIndex li, const LongItem* __restrict__ items, int64_t nitems,
-                             int32_t lo, int32_t hi, RM rm, LongDst dst) {
+__global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nitems) return;
-    const LongItem it = items[i];
-    const LongMeta m = li.meta[it.l];
-    if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
-    long_resid_segment<DEF>(g, m, li, it.part, dst.resid(m, rm.row(g, m.x)));
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    if (i < nitems) {
+        int32_t l, part;
+        im.find(i, l, part);
+        const LongMeta m = li.meta[l];
+        if (m.x >= lo && m.x < hi && rm.wanted(g, m.x)) {
+            if (!lf.only_consumed(m)) long_resid_segment<DEF>(g, m, li, part, dst.resid(m, rm.row(g, m.x)));
+            else if (m.x >= lf.from) {
+                const int32_t first = part * li.seg;
+                const int32_t cnt = min(li.seg, m.rc - first);
+                Fold32 f;
+                f.begin(m.x);
+                if (DEF) {
+                    const int k = g.c.zetak;
+                    Win b;
+                    b.seek(g, li.seg_pos[m.seg_off + part]);
+                    uint32_t v = (uint32_t)li.seg_val[m.seg_off + part];
+#pragma unroll 1
+                    for (int32_t t = 0; t < cnt; t++) {
+                        if (first + t == 0) v = (uint32_t)(int32_t)((int64_t)m.x + nat2int(zeta_any<0>(b, g, k) - 1ull));
+                        else {
+                            uint32_t mm, len;
+                            if (zeta_fast<0>(b.top(), k, mm, len)) b.skip(len);
+                            else mm = (uint32_t)(b.zeta_slow(g, k) + 1ull);
+                            v += mm;
+                        }
+                        f.add(v);
+                    }
+                } else {
+                    BitBuf b;
+                    b.w = g.words; b.maxw = g.nwords - 3;
+                    b.seek(li.seg_pos[m.seg_off + part]);
+                    int64_t v = li.seg_val[m.seg_off + part];
+                    for (int32_t t = 0; t < cnt; t++) {
+                        if (first + t == 0) v = (int64_t)(int32_t)((int64_t)m.x + nat2int(Rd<DEF>::resid(b, g.c)));
+                        else v += (int64_t)Rd<DEF>::resid(b, g.c) + 1;
+                        f.add((uint32_t)v);
+                    }
+                }
+                f.n = (uint32_t)cnt;
+                acc = f.finish(m.x);
+                arcs = cnt;
+            }
+        }
+    }
+    if (lf.result) warp_fold(acc, arcs, lf.result);
 }
 
 template <class RM>
-__global__ void k_long_extras(GraphDev g, LongIndex li, const LongItem* __restrict__ items, int64_t nitems,
-                              int32_t lo, int32_t hi, RM rm, LongDst dst) {
+__global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nitems) return;
-    const LongItem it = items[i];
-    const LongMeta m = li.meta[it.l];
-    if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
-    IntervalSeq a{ li.iv_cum + m.iv_off, li.iv_left + m.iv_off, m.ic, m.ilen };
-    const int32_t total = m.ilen + m.rc;
-    const int32_t q0 = it.part * li.chunk;
-    const int32_t* left = a.left;
-    merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
-                min(li.chunk, total - q0), dst.extras(m, rm.row(g, m.x)));
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    if (i < nitems) {
+        int32_t l, part;
+        im.find(i, l, part);
+        const LongMeta m = li.meta[l];
+        if (m.x >= lo && m.x < hi && rm.wanted(g, m.x)) {
+            IntervalSeq a{ li.iv_cum + m.iv_off, li.iv_left + m.iv_off, m.ic, m.ilen };
+            const int32_t q0 = part * li.chunk;
+            if (!lf.only_consumed(m)) {
+                const int32_t total = m.ilen + m.rc;
+                const int32_t* left = a.left;
+                merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
+                            min(li.chunk, total - q0), dst.extras(m, rm.row(g, m.x)));
+            } else if (m.x >= lf.from && q0 < m.ilen) {  // interval elements [q0, q0 + chunk) of the concatenated intervals
+                const int32_t cnt = min(li.chunk, m.ilen - q0);
+                Fold32 f;
+                f.begin(m.x);
+                int32_t t = upper_slot(a.cum, a.n, q0), t_end = a.cum[t + 1];
+                for (int32_t q = q0; q < q0 + cnt; q++) {
+                    while (q >= t_end) { t++; t_end = a.cum[t + 1]; }
+                    f.add((uint32_t)(a.left[t] + (q - a.cum[t])));
+                }
+                f.n = (uint32_t)cnt;
+                acc = f.finish(m.x);
+                arcs = cnt;
+            }
+        }
+    }
+    if (lf.result) warp_fold(acc, arcs, lf.result);
 }
 
 template <class RM>
-__global__ void k_long_merge(GraphDev g, LongIndex li, const LongItem* __restrict__ items, int64_t nitems,
-                             int32_t lo, int32_t hi, RM rm, LongDst dst) {
+__global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nitems) return;
-    const LongItem it = items[i];
-    const LongMeta m = li.meta[it.l];
-    if (m.x < lo || m.x >= hi || !rm.wanted(g, m.x)) return;
-    const int32_t* parent = rm.row(g, m.x - m.ref);
-    CopiedSeq a{ li.cb_cum + m.cb_off, li.cb_ppos + m.cb_off, parent, m.ncb, m.copied };
-    const int32_t* ppos = a.ppos;
-    const int32_t q0 = it.part * li.chunk;
-    merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
-                m.d - m.copied, q0, min(li.chunk, m.d - q0), rm.row(g, m.x));
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    if (i < nitems) {
+        int32_t l, part;
+        im.find(i, l, part);
+        const LongMeta m = li.meta[l];
+        if (m.x >= lo && m.x < hi && rm.wanted(g, m.x)) {
+            const int32_t* parent = rm.row(g, m.x - m.ref);
+            CopiedSeq a{ li.cb_cum + m.cb_off, li.cb_ppos + m.cb_off, parent, m.ncb, m.copied };
+            const int32_t* ppos = a.ppos;
+            const int32_t q0 = part * li.chunk;
+            if (!lf.only_consumed(m)) {
+                merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
+                            m.d - m.copied, q0, min(li.chunk, m.d - q0), rm.row(g, m.x));
+            } else if (m.x >= lf.from && q0 < m.copied) {  // copied elements [q0, q0 + chunk) seen through the copy blocks
+                const int32_t cnt = min(li.chunk, m.copied - q0);
+                Fold32 f;
+                f.begin(m.x);
+                int32_t t = upper_slot(a.cum, a.n, q0), t_end = a.cum[t + 1];
+                for (int32_t q = q0; q < q0 + cnt; q++) {
+                    while (q >= t_end) { t++; t_end = a.cum[t + 1]; }
+                    f.add((uint32_t)parent[ppos[t] + (q - a.cum[t])]);
+                }
+                f.n = (uint32_t)cnt;
+                acc = f.finish(m.x);
+                arcs = cnt;
+            }
+        }
+    }
+    if (lf.result) warp_fold(acc, arcs, lf.result);
 }
+
+// Rows of the long records a consume-only scan materialised (the ones somebody copies from), folded by one warp per
+// FOLD_CHUNK entries.
+constexpr int32_t FOLD_CHUNK = 1024;
+template <class RM>
+__global__ void k_long_fold_rows(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongFold lf) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long acc = 0;
+    long long arcs = 0;
+    if (i < nitems) {
+        int32_t l, part;
+        im.find(i, l, part);
+        const LongMeta m = li.meta[l];
+        if (m.x >= lf.from && m.x >= lo && m.x < hi && !lf.only_consumed(m)) {
+            const int32_t a = part * FOLD_CHUNK, e = min(m.d, a + FOLD_CHUNK);
+            const int32_t* row = rm.row(g, m.x);
+            const unsigned long long base = (unsigned long long)(uint32_t)m.x * BVG_MIX;
+            for (int32_t p = a + lane; p < e; p += 32) acc ^= base + (unsigned long long)(uint32_t)row[p];
+            if (lane == 0) arcs = e - a;
+        }
+    }
+    warp_fold(acc, arcs, lf.result);
+}
+
+// Speculative sub-ranges of the residual sections (see above), listed on the device: item j of record l covers
+// LSPEC_BITS bits from resid_pos + part * LSPEC_BITS.
+__global__ void k_lspec_init(const LongMeta* __restrict__ meta, ItemMap im, int64_t nitems, SpecItem* __restrict__ items) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nitems) return;
+    int32_t l, part;
+    im.find(j, l, part);
+    const LongMeta m = meta[l];
+    SpecItem it;
+    it.lo = m.resid_pos + (uint64_t)part * (uint64_t)LSPEC_BITS;
+    it.hi = min(it.lo + (uint64_t)LSPEC_BITS, m.rec_end);
+    it.entry = it.lo; it.exit = it.lo; it.count = 0; it.sum = 0;
+    it.l = l; it.first = part == 0 ? 1 : 0;
+    items[j] = it;
+}
+
+// Per record: running (count, sum) before each of its sub-ranges; the counts must add up to the record's residuals.
+__global__ void k_lspec_scan(GraphDev g, const LongMeta* __restrict__ meta, ItemMap im, const SpecItem* __restrict__ items,
+                             int64_t* __restrict__ cbase, int64_t* __restrict__ sbase) {
+    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= im.nlong) return;
+    int64_t c = 0, sum = 0;
+    for (int64_t j = im.cum[l]; j < im.cum[l + 1]; j++) {
+        cbase[j] = c; sbase[j] = sum;
+        c += items[j].count; sum += items[j].sum;
+    }
+    if (im.cum[l + 1] > im.cum[l] && c != meta[l].rc) report(g.err, E_FORMAT, meta[l].x, meta[l].resid_pos + g.bit_base);
+}
+#endif  // BVG_HOST_EMULATION
 
 }  // namespace bvg

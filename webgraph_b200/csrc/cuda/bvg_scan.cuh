@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < 
 // Codes that do not fit the 32-bit window go through the position-based reader, out of line: they are rare (gaps >= 2^24
 // for zeta_3, values >= 2^16 - 1 for gamma) and inlining them at every call site triples the size of the hot loops.
 #ifdef BVG_HOST_EMULATION
-#define BVG_NOINLINE
+#define BVG_NOINLINE inline
 #else
 #define BVG_NOINLINE __noinline__
 #endif
@@ -362,5 +362,26 @@ __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, Co
     }
     return f.finish(x);
 }
+
+#ifndef BVG_HOST_EMULATION
+// Blocks of the scan kernels fold into FOLD_SLOTS slot pairs (arcs, XOR) instead of two hot words; k_reduce_slots sums them.
+constexpr int FOLD_SLOTS = 1024;
+
+// The same without a block barrier: one atomic pair per warp (blocks of the dynamic-grid scan kernels live for one
+// item per thread; a barrier at the end makes every warp wait for the block's longest record).
+__device__ __forceinline__ void warp_fold(unsigned long long acc, long long arcs, unsigned long long* __restrict__ result) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+        arcs += __shfl_xor_sync(0xffffffffu, arcs, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* slot = result + 2 * ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (FOLD_SLOTS - 1));
+        if (acc) atomicXor(slot + 1, acc);
+        if (arcs) atomicAdd(slot, (unsigned long long)arcs);
+    }
+}
+
+#endif
 
 }  // namespace bvg
