@@ -49,10 +49,11 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             o.template with_intervals<true>(g, row, true, f);  // header_rec leaves copied = 0: the row is already advanced
             if (o.err) return o.err;
         } else {
-            ScanExtras<K> w;
-            w.begin(g, x, nout, epos, true);
+            alignas(16) unsigned char ring[RING_GROUPS * 16];
+            ScanExtras<K, WinRing<1>> w;
+            w.begin(g, x, nout, epos, true, ring_address(ring));
             if (has_iv) w.iv_fold(g); else w.iv_none(g);
-            if (store) w.template resid<true>(g, row, true, 7u); else w.template resid<false>(g, row, false, 7u);
+            if (store) w.template resid<true>(g, row, true); else w.template resid<false>(g, row, false);
             if (w.err) return w.err;
             f = w.finish();
         }

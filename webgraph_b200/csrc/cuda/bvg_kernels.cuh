@@ -5,6 +5,7 @@
 // default codings live in bvg_tile.cuh; this set is the fallback they defer to (giant lists, exotic codings,
 // unbounded chains) and the first-round correctness baseline.
 #pragma once
+#include <type_traits>
 #include "bvg_device.cuh"
 #include "bvg_scan.cuh"
 
@@ -533,9 +534,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // records in separate warps: (no intervals | intervals) x (only consumed | stored because somebody copies from it).
 // Only stored records with intervals need the element-wise merge of ExtrasWalk::with_intervals; everything else is the
 // tight residual loop, preceded for consumed records with intervals by a walk of the interval section that folds as it goes.
-template <int K, int LA>
+template <int K, bool RING>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
-                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, uint32_t pf_mask) {
+                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
+    __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
+    typedef typename std::conditional<RING, WinRing<SCAN_BLOCK>, Win>::type W;
+    const ring_addr my_ring = ring_address(&ring[RING ? threadIdx.x : 0]);
     unsigned long long acc = 0;
     long long arcs = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -552,12 +556,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         const bool merged = active && has_iv && store;  // intervals and residuals have to come out in order
         int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
         unsigned long long f = 0;
-        ScanExtras<K, LA> w;
-        w.begin(g, r.x, r.nout, r.pos, active && !merged);
+        ScanExtras<K, W> w;
+        w.begin(g, r.x, r.nout, r.pos, active && !merged, my_ring);
         if (has_iv) w.iv_fold(g); else w.iv_none(g);
         __syncwarp();
-        if (__any_sync(0xffffffffu, store && !merged)) w.template resid<true>(g, row, store, pf_mask);
-        else w.template resid<false>(g, row, false, pf_mask);
+        if (__any_sync(0xffffffffu, store && !merged)) w.template resid<true>(g, row, store);
+        else w.template resid<false>(g, row, false);
         __syncwarp();
         if (active && !merged) f = w.finish();
         if (__any_sync(0xffffffffu, merged)) {

@@ -41,6 +41,34 @@ __device__ BVG_NOINLINE uint64_t slow_zeta(const uint32_t* __restrict__ words, u
     return r;
 }
 
+// A ring is addressed by its 32-bit shared-memory address on the device (kept in a register; a generic pointer makes
+// ptxas rebuild it from %tid at every refill) and by a plain pointer under host emulation.
+#ifdef BVG_HOST_EMULATION
+typedef unsigned char* ring_addr;
+__device__ __forceinline__ ring_addr ring_address(void* p) { return (unsigned char*)p; }
+__device__ __forceinline__ uint32_t ring_load(ring_addr a, uint32_t off) { uint32_t v; memcpy(&v, a + off, 4); return v; }
+#define BVG_CP_ASYNC16(dst, off, src) memcpy((dst) + (off), (src), 16)
+#define BVG_CP_COMMIT()
+#define BVG_CP_WAIT_ALL()
+#define BVG_CP_WAIT_1()
+#else
+typedef uint32_t ring_addr;
+__device__ __forceinline__ ring_addr ring_address(void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));  // opaque: keep it in a register
+    return a;
+}
+__device__ __forceinline__ uint32_t ring_load(ring_addr a, uint32_t off) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + off) : "memory");
+    return v;
+}
+#define BVG_CP_ASYNC16(dst, off, src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((dst) + (off)), "l"(src) : "memory")
+#define BVG_CP_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define BVG_CP_WAIT_ALL() asm volatile("cp.async.wait_group 0;" ::: "memory")
+#define BVG_CP_WAIT_1() asm volatile("cp.async.wait_group 1;" ::: "memory")
+#endif
+
 // LA = words of lookahead (1..3).  A lane opens a new 32-byte sector of its record every eighth word and a warp-wide
 // refill load therefore almost always carries a lane that misses L1; the loaded word has to be requested long enough
 // before the funnel shift that needs it (ncu, LA = 1: 20 % of all stall samples sit on that shift).
@@ -72,10 +100,8 @@ struct WinT {
         return ((uint64_t)(p0 - g.words) + idx - (1u + LA)) * 32u + s;
     }
     __device__ __forceinline__ bool overrun() const { return idx >= lim; }
-    // Fire-and-forget L1 prefetch `words` past the lookahead word.  The refill loads cannot run far ahead by themselves:
-    // ptxas tracks them with one scoreboard, and the loop waits on it every trip, so a refill that misses L1 stalls the
-    // warp for the full memory latency however many words of lookahead the window keeps.  Called once every few codes.
-    __device__ __forceinline__ void prefetch(uint32_t words) const { BVG_PREFETCH_L1(p0 + umin32(idx + words, lim)); }
+    __device__ __forceinline__ void attach(ring_addr) {}
+    __device__ __forceinline__ void topup() {}
     __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, s); }
     __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
         s += n;
@@ -116,6 +142,103 @@ struct WinT {
 #define BVG_WIN_LA 1
 #endif
 typedef WinT<1> Win;  // block lists and interval sections: a few codes per record
+
+// ---------------------------------------------------------------------------------------------------
+// The same window fed from shared memory: every lane owns a ring of RING_GROUPS 16-byte groups of its record's stream,
+// filled by asynchronous global->shared copies (cp.async, no register and no scoreboard involved) that run two to
+// three groups ahead of the decoder; a refill is then a shared-memory load.  With refills straight from global memory
+// the loop waits for an L1 miss almost every trip: each lane opens a new 32-byte sector every eighth word, a warp-wide
+// load nearly always carries such a lane, and ptxas keeps all of the window's loads on one scoreboard, so no amount of
+// register lookahead helps (measured: 1, 2 and 3 words of lookahead and L1/L2 prefetches all give the same time).
+//   topup() must be called at least once every four words consumed (the residual loop calls it every fourth code, all
+//   lanes together): it issues at most one group copy and waits for everything but the newest group.
+//   Invariant (cg = group of the lookahead word, fg = next group to copy): after every topup fg >= cg + 3.  At most four
+//   words, hence one group boundary, are crossed before the next topup, so there fg >= cg + 2: group cg + 2 is copied now
+//   if it was not yet, and the groups up to cg + 1 -- all the window can reach before the topup after this one -- were
+//   copied at least one topup ago and are complete once this topup's wait returns.  A slot is rewritten only by group
+//   fg <= cg + 2 <= cg + RING_GROUPS - 1, whose previous tenant fg - RING_GROUPS < cg is dead.  seek() loads four groups.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RING_GROUPS = 4;
+
+template <int NT>  // threads per block: group slot i of a lane lives NT * 16 bytes after slot i - 1
+struct WinRing {
+    ring_addr ring;                   // this lane's 16 bytes of slot 0 (shared memory)
+    const uint4* __restrict__ g0;     // group holding the bit the window was opened at
+    uint32_t glim;                    // last readable group, from g0
+    uint32_t r;                       // word index (from g0's first word) of the lookahead word
+    uint32_t fg;                      // next group to copy, from g0
+    uint32_t w0, w1, q;               // current two words, lookahead
+    uint32_t s;                       // bits of w0 already consumed, 0..31
+
+    __device__ __forceinline__ void attach(ring_addr lane_slot0) { ring = lane_slot0; }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+        return ring_load(ring, ((i >> 2) & (RING_GROUPS - 1)) * (NT * 16) + (i & 3u) * 4u);
+    }
+    __device__ __forceinline__ void copy_group(uint32_t gi) {
+        BVG_CP_ASYNC16(ring, (gi & (RING_GROUPS - 1)) * (NT * 16), g0 + umin32(gi, glim));
+    }
+    __device__ __forceinline__ void seek(const GraphDev& g, uint64_t pos) {
+        uint64_t wi = pos >> 5;
+        const uint64_t last = g.nwords - 1;
+        if (wi > last) wi = last;  // a corrupt stream can point past the end: clamp, the caller reports E_IO
+        const uint64_t gi = wi >> 2, glast = (g.nwords >> 2) - 1;   // nwords is a multiple of 4
+        g0 = (const uint4*)g.words + gi;
+        const uint64_t room = glast - gi;
+        glim = room > 0x3fffffffull ? 0x3fffffffu : (uint32_t)room;
+        BVG_CP_WAIT_ALL();  // a re-seek (slow path) must not race with copies still in flight to the same slots
+        copy_group(0); copy_group(1); copy_group(2); copy_group(3);
+        BVG_CP_COMMIT();
+        BVG_CP_WAIT_ALL();
+        fg = RING_GROUPS;
+        r = (uint32_t)wi & 3u;
+        s = (uint32_t)pos & 31u;
+        w0 = word(r);
+        w1 = word(r + 1);
+        q = word(r + 2);
+        r += 2;
+    }
+    __device__ __forceinline__ void topup() {
+        if (fg - (r >> 2) <= 2u) { copy_group(fg); fg++; }
+        BVG_CP_COMMIT();
+        BVG_CP_WAIT_1();
+    }
+    __device__ __forceinline__ uint64_t pos(const GraphDev& g) const {
+        return ((uint64_t)(g0 - (const uint4*)g.words) * 4u + r - 2u) * 32u + s;
+    }
+    __device__ __forceinline__ bool overrun() const { return (r >> 2) > glim; }
+    __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, s); }
+    __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
+        s += n;
+        if (s >= 32u) {
+            s -= 32u;
+            w0 = w1;
+            w1 = q;
+            r++;
+            q = word(r);
+        }
+    }
+    __device__ __forceinline__ uint64_t gamma_slow(const GraphDev& g) {
+        uint64_t p = pos(g);
+        const uint64_t v = slow_gamma(g.words, g.nwords, &p);
+        seek(g, p);
+        return v;
+    }
+    __device__ __forceinline__ uint64_t zeta_slow(const GraphDev& g, int k) {
+        uint64_t p = pos(g);
+        const uint64_t v = slow_zeta(g.words, g.nwords, &p, k);
+        seek(g, p);
+        return v;
+    }
+    __device__ __forceinline__ uint64_t gamma(const GraphDev& g) {
+        const uint32_t t = top();
+        const int m = __clz((int)t);
+        if (m <= 15) {
+            skip(2u * m + 1u);
+            return (uint64_t)((t >> (31 - 2 * m)) - 1u);
+        }
+        return gamma_slow(g);
+    }
+};
 
 // zeta_k code that fits the 32-bit window: m = value + 1, len = code length.  K = 3 is BVGraph's default and gets
 // constants; K = 0 takes k at run time.  With h = leading zeros, P = 2^(hk): the bits after the unary part, read with
@@ -178,9 +301,9 @@ struct Fold32 {
 //                   ExtrasWalk::with_intervals instead (kept in separate warps by the schedule)
 //   phase resid()   residuals, tight loop
 // ---------------------------------------------------------------------------------------------------
-template <int K, int LA = BVG_WIN_LA>
+template <int K, class W = Win>
 struct ScanExtras {
-    WinT<LA> b;
+    W b;
     Fold32 f;
     int32_t x, nout, rc;
     uint32_t v;
@@ -191,9 +314,10 @@ struct ScanExtras {
         err = code; rc = 0;
     }
 
-    __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active) {
+    __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active, ring_addr ring_slot = ring_addr()) {
         x = x_; nout = 0; rc = 0; err = 0; v = 0;
         f.begin(x_);
+        b.attach(ring_slot);
         if (!active) return;
         nout = nout_;
         rc = nout_;
@@ -217,6 +341,7 @@ struct ScanExtras {
             const uint32_t len = (uint32_t)len64;
             for (uint32_t j = 0; j < len; j++) f.add(left + j);
             prev = left + len;
+            b.topup();
         }
         rc = nout - (int32_t)total;
     }
@@ -230,15 +355,16 @@ struct ScanExtras {
 
     // Residuals (ResidualIntIterator, BVGraph.java:939-972): first = x + nat2int(zeta), then += zeta + 1.
     template <bool STORE>
-    __device__ __forceinline__ void resid(const GraphDev& g, int32_t* __restrict__ row, bool store, uint32_t pf_mask) {
+    __device__ __forceinline__ void resid(const GraphDev& g, int32_t* __restrict__ row, bool store) {
         if (rc <= 0) return;
         const int k = g.c.zetak;
+        b.topup();
         v = (uint32_t)(int32_t)((int64_t)x + nat2int(zeta_any<K>(b, g, k) - 1ull));  // :954
         f.add(v);
         if (STORE && store) row[0] = (int32_t)v;
 #pragma unroll 1
         for (int32_t i = 1; i < rc; i++) {
-            if (((uint32_t)i & pf_mask) == 1u) b.prefetch(PREFETCH_WORDS_AHEAD);
+            if (((uint32_t)i & 3u) == 0u) b.topup();
             uint32_t m, len;
             if (zeta_fast<K>(b.top(), k, m, len)) b.skip(len);
             else m = (uint32_t)(b.zeta_slow(g, k) + 1ull);
