@@ -43,17 +43,13 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
         const int32_t nout = d - (int32_t)cp;
         int32_t* row = rows + rowoff[x] + cp;
         unsigned long long f = 0;
-        if (has_iv && store) {
-            ExtrasWalk<true> o;
-            o.header_rec(g, x, d, nout, epos, true);
-            o.template with_intervals<true>(g, row, true, f);  // header_rec leaves copied = 0: the row is already advanced
-            if (o.err) return o.err;
-        } else {
+        {
             alignas(16) unsigned char ring[RING_GROUPS * 16];
             ScanExtras<K, WinRing<1>> w;
             w.begin(g, x, nout, epos, true, ring_address(ring));
             if (has_iv) w.iv_fold(g); else w.iv_none(g);
             if (store) w.template resid<true>(g, row, true); else w.template resid<false>(g, row, false);
+            if (store && has_iv) w.iv_merge(g, row);
             if (w.err) return w.err;
             f = w.finish();
         }

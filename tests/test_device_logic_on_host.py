@@ -173,11 +173,14 @@ def test_emulated_fused_scan(emu, oracle, tmp_path):
     deg[5] = 10
     deg[100:110] = 3
     deg[200] = 9
+    deg[250] = 2
+    deg[251] = 3
     off2 = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(deg, out=off2[1:])
     succ2 = np.concatenate([np.array([0, 1, 2, 3, 2 ** 30, 2 ** 30 + 1, 2 ** 30 + 2, 2 ** 30 + 3, 2 ** 30 + 4, 2 ** 31 - 2], dtype=np.int64)] +
                            [np.array([7, 2 ** 26 + i, 2 ** 31 - 5 + i // 3], dtype=np.int64) for i in range(10)] +
-                           [np.array([2 ** 29 + j for j in range(8)] + [2 ** 31 - 1], dtype=np.int64)]).astype(np.int32)
+                           [np.array([2 ** 29 + j for j in range(8)] + [2 ** 31 - 1], dtype=np.int64)] +
+                           [np.array([2 ** 28 + 5, 2 ** 28 + 900], dtype=np.int64), np.array([2 ** 30 + 1, 2 ** 30 + 2 ** 25, 2 ** 31 - 3], dtype=np.int64)]).astype(np.int32)
     for k in (3, 4):
         base = str(tmp_path / ("big%d" % k))
         tools.store_csr(base, off2, succ2, zetak=k)

@@ -532,11 +532,12 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 
 // The same step for the default codings with the lean walkers of bvg_scan.cuh.  The schedule keeps four kinds of
 // records in separate warps: (no intervals | intervals) x (only consumed | stored because somebody copies from it).
-// Only stored records with intervals need the element-wise merge of ExtrasWalk::with_intervals; everything else is the
-// tight residual loop, preceded for consumed records with intervals by a walk of the interval section that folds as it goes.
+// Every kind runs the same tight residual loop, preceded for records with intervals by a walk of the interval section
+// that folds its elements; stored records with intervals write their residuals right-aligned and merge the intervals in
+// front of them in a second walk (ScanExtras::iv_merge).
 template <int K, bool RING>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
-                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
+                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
     typedef typename std::conditional<RING, WinRing<SCAN_BLOCK>, Win>::type W;
     const ring_addr my_ring = ring_address(&ring[RING ? threadIdx.x : 0]);
@@ -549,28 +550,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         r.x = -1; r.flags = 0;
         if (i < count) r = recs[i];
         bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
-        const bool store = active && (r.flags & 1u);
+        const bool store = active && (r.flags & 1u) && debug_nostore != 1;
         const bool fold = active && r.x >= from;
         active = active && (fold || store);  // halo nodes matter only as parents
         const bool has_iv = (r.flags & 2u) != 0;
-        const bool merged = active && has_iv && store;  // intervals and residuals have to come out in order
         int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
         unsigned long long f = 0;
         ScanExtras<K, W> w;
-        w.begin(g, r.x, r.nout, r.pos, active && !merged, my_ring);
+        w.begin(g, r.x, r.nout, r.pos, active, my_ring);
         if (has_iv) w.iv_fold(g); else w.iv_none(g);
         __syncwarp();
-        if (__any_sync(0xffffffffu, store && !merged)) w.template resid<true>(g, row, store);
+        if (__any_sync(0xffffffffu, store)) w.template resid<true>(g, row, store);
         else w.template resid<false>(g, row, false);
         __syncwarp();
-        if (active && !merged) f = w.finish();
-        if (__any_sync(0xffffffffu, merged)) {
-            ExtrasWalk<true> o;
-            o.header_rec(g, r.x, r.d, r.nout, r.pos, merged);
-            __syncwarp();
-            o.template with_intervals<true>(g, row, merged, f);
-            __syncwarp();
-        }
+        if (store && has_iv) w.iv_merge(g, row);
+        __syncwarp();
+        if (active) f = w.finish();
         if (fold) { acc ^= f; arcs += r.d; }
     }
     warp_fold(acc, arcs, result);

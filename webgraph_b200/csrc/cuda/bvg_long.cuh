@@ -429,7 +429,7 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
                         else {
                             uint32_t mm, len;
                             if (zeta_fast<0>(b.top(), k, mm, len)) b.skip(len);
-                            else mm = (uint32_t)(b.zeta_slow(g, k) + 1ull);
+                            else mm = (uint32_t)zeta_any<0>(b, g, k);
                             v += mm;
                         }
                         f.add(v);

@@ -103,6 +103,7 @@ struct WinT {
     __device__ __forceinline__ void attach(ring_addr) {}
     __device__ __forceinline__ void topup() {}
     __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, s); }
+    __device__ __forceinline__ uint64_t top64() const { return ((uint64_t)__funnelshift_l(w1, w0, s) << 32) | __funnelshift_l(q0, w1, s); }
     __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
         s += n;
         if (s >= 32u) {
@@ -207,6 +208,7 @@ struct WinRing {
     }
     __device__ __forceinline__ bool overrun() const { return (r >> 2) > glim; }
     __device__ __forceinline__ uint32_t top() const { return __funnelshift_l(w1, w0, s); }
+    __device__ __forceinline__ uint64_t top64() const { return ((uint64_t)__funnelshift_l(w1, w0, s) << 32) | __funnelshift_l(q, w1, s); }
     __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
         s += n;
         if (s >= 32u) {
@@ -268,10 +270,36 @@ __device__ __forceinline__ bool zeta_fast(uint32_t t, int k, uint32_t& m, uint32
     }
 }
 
+// The same on a 64-bit window (codes of up to 64 bits: every zeta_3 code of a value below 2^48).  Used for the first
+// residual of a record, x +- a distance that often exceeds 2^24 on a graph without locality; the out-of-line reader
+// would re-open the window, which costs a full memory round trip.
+template <int K>
+__device__ __forceinline__ bool zeta_fast64(uint64_t t, int k, uint64_t& m, uint32_t& len) {
+    if (t == 0) return false;
+    const int h = __clzll((long long)t);
+    const int kk = K == 3 ? 3 : k;
+    const int hk = h * kk;
+    const int total = h + 1 + hk + kk;  // long form
+    if (total > 64) return false;
+    const uint64_t r = t >> (64 - total);
+    const uint64_t P = 1ull << hk;
+    const uint64_t two_k = 1ull << kk;
+    const bool sh = r < P * (two_k + 2ull);
+    m = sh ? (r >> 1) - P * ((two_k >> 1) - 1ull) : r - P * two_k;
+    len = (uint32_t)total - (sh ? 1u : 0u);
+    return true;
+}
+
 template <int K, class W>
 __device__ __forceinline__ uint64_t zeta_any(W& b, const GraphDev& g, int k) {  // value + 1
     uint32_t m, len;
     if (zeta_fast<K>(b.top(), k, m, len)) { b.skip(len); return m; }
+    uint64_t m64;
+    if (zeta_fast64<K>(b.top64(), k, m64, len)) {
+        if (len > 32u) { b.skip(32u); len -= 32u; }
+        b.skip(len);
+        return m64;
+    }
     return b.zeta_slow(g, k) + 1ull;
 }
 
@@ -294,6 +322,50 @@ struct Fold32 {
     }
 };
 
+// Sequential writer of one lane's row with 16-byte write combining.  The 32 lanes of a warp write 32 unrelated rows, so
+// a 4-byte store per successor is 32 separate sector writes per instruction at the L2; measured on the benchmark graph
+// they cost 37 % of the extras kernel (3.92 ms with, 2.48 ms without the row stores).  The writer keeps the last three
+// values in registers and issues one 16-byte store whenever the write position reaches a 16-byte boundary; the unaligned
+// head and tail of a row (at most three values each) are stored singly.
+template <bool VEC>
+struct RowWriter {
+    int32_t* __restrict__ p;   // next position to write
+    uint32_t b1, b2, b3;       // the last three values put (b3 newest)
+    uint32_t pend;             // values put but not yet stored, 0..3
+    uint32_t ph;               // (address of p / 4) & 3
+    __device__ __forceinline__ void begin(int32_t* row) {
+        p = row; b1 = b2 = b3 = 0; pend = 0;
+        ph = (uint32_t)(((uintptr_t)row) >> 2) & 3u;
+    }
+    __device__ __forceinline__ void put(uint32_t v) {
+        if (!VEC) { *p++ = (int32_t)v; return; }
+        p++;
+        ph = (ph + 1u) & 3u;
+        if (ph == 0u) {  // p is 16-byte aligned again: the four values before it are one aligned group
+            if (pend == 3u) {
+#ifdef BVG_HOST_EMULATION
+                p[-4] = (int32_t)b1; p[-3] = (int32_t)b2; p[-2] = (int32_t)b3; p[-1] = (int32_t)v;
+#else
+                *reinterpret_cast<uint4*>(p - 4) = make_uint4(b1, b2, b3, v);
+#endif
+            } else {       // head of the row: fewer than four values since it started
+                p[-1] = (int32_t)v;
+                if (pend >= 1u) p[-2] = (int32_t)b3;
+                if (pend >= 2u) p[-3] = (int32_t)b2;
+            }
+            pend = 0;
+        } else pend++;
+        b1 = b2; b2 = b3; b3 = v;
+    }
+    __device__ __forceinline__ void flush() {  // tail of the row
+        if (!VEC) return;
+        if (pend >= 1u) p[-1] = (int32_t)b3;
+        if (pend >= 2u) p[-2] = (int32_t)b2;
+        if (pend >= 3u) p[-3] = (int32_t)b1;
+        pend = 0;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------
 // Extras of one record (everything that is not copied), consume-only or into the row when `store`.
 // Entry: the cursor at the extras section (ExtraRec.pos), nout = outdegree - copied.
@@ -308,6 +380,8 @@ struct ScanExtras {
     int32_t x, nout, rc;
     uint32_t v;
     int err;
+    uint32_t ic;       // intervals (iv_fold)
+    uint64_t iv_pos;   // bit position of the first interval's left extreme
 
     __device__ __forceinline__ void fail(const GraphDev& g, int code) {
         report(g.err, code, x, b.pos(g) + g.bit_base);
@@ -315,7 +389,7 @@ struct ScanExtras {
     }
 
     __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active, ring_addr ring_slot = ring_addr()) {
-        x = x_; nout = 0; rc = 0; err = 0; v = 0;
+        x = x_; nout = 0; rc = 0; err = 0; v = 0; ic = 0; iv_pos = 0;
         f.begin(x_);
         b.attach(ring_slot);
         if (!active) return;
@@ -327,11 +401,13 @@ struct ScanExtras {
     // Interval section of a record that is only consumed (IntIntervalSequenceIterator.java:57-95, BVGraph.java:1076-1095)
     __device__ __forceinline__ void iv_fold(const GraphDev& g) {
         if (nout <= 0 || g.c.minlen == 0) return;
-        const uint64_t ic = b.gamma(g);
-        if (ic > (uint64_t)nout) { fail(g, E_IO); return; }
+        const uint64_t ic64 = b.gamma(g);
+        if (ic64 > (uint64_t)nout) { fail(g, E_IO); return; }
+        ic = (uint32_t)ic64;
+        iv_pos = b.pos(g);
         int64_t total = 0;
         uint32_t prev = 0;
-        for (uint32_t i = 0; i < (uint32_t)ic; i++) {
+        for (uint32_t i = 0; i < ic; i++) {
             uint32_t left;
             if (i == 0) left = (uint32_t)(int32_t)(nat2int(b.gamma(g)) + (int64_t)x);
             else left = prev + 1u + (uint32_t)b.gamma(g);
@@ -344,6 +420,36 @@ struct ScanExtras {
             b.topup();
         }
         rc = nout - (int32_t)total;
+    }
+
+    // Stored records with intervals: the residuals were written right-aligned, row[nout - rc .. nout); walk the interval
+    // section a second time and merge, forward and in place (Merged(IntIntervalSequenceIterator, ResidualIntIterator),
+    // BVGraph.java:1103-1108; equal heads once, MergedIntIterator.java:70; a list that loses duplicates is padded with -1
+    // as BVGraphNodeIterator does when it drains, :1210).  The write index never overtakes the unread residuals: it trails
+    // them by the number of interval elements still to come.
+    __device__ __forceinline__ void iv_merge(const GraphDev& g, int32_t* row) {
+        if (ic == 0 || err) return;
+        Win c;
+        c.seek(g, iv_pos);
+        int32_t k = 0, j = nout - rc;
+        RowWriter<true> wr;
+        wr.begin(row);
+        uint32_t prev = 0;
+        for (uint32_t i = 0; i < ic; i++) {
+            uint32_t left;
+            if (i == 0) left = (uint32_t)(int32_t)(nat2int(c.gamma(g)) + (int64_t)x);
+            else left = prev + 1u + (uint32_t)c.gamma(g);
+            const uint32_t len = (uint32_t)(c.gamma(g) + (uint64_t)g.c.minlen);
+            while (j < nout && (uint32_t)row[j] < left) { wr.put((uint32_t)row[j++]); k++; }
+            for (uint32_t e = 0; e < len; e++) { wr.put(left + e); k++; }
+            prev = left + len;
+            while (j < nout && (uint32_t)row[j] < prev) j++;  // residuals inside an interval: emitted once
+        }
+        if (k != j) {
+            while (j < nout) { wr.put((uint32_t)row[j++]); k++; }
+            while (k < nout) { wr.put(0xffffffffu); k++; }
+        }
+        wr.flush();
     }
 
     // Interval section skipped over (storing records without intervals still carry the count)
@@ -361,17 +467,20 @@ struct ScanExtras {
         b.topup();
         v = (uint32_t)(int32_t)((int64_t)x + nat2int(zeta_any<K>(b, g, k) - 1ull));  // :954
         f.add(v);
-        if (STORE && store) row[0] = (int32_t)v;
+        RowWriter<true> wr;
+        if (STORE) wr.begin(row + (nout - rc));  // after the interval elements a later iv_merge puts in front (rc == nout without intervals)
+        if (STORE && store) wr.put(v);
 #pragma unroll 1
         for (int32_t i = 1; i < rc; i++) {
-            if (((uint32_t)i & 3u) == 0u) b.topup();
+            if ((((uint32_t)i + 1u) & 3u) == 0u) b.topup();  // the first residual may have taken two words: 2 + 2, then every 4 codes
             uint32_t m, len;
             if (zeta_fast<K>(b.top(), k, m, len)) b.skip(len);
-            else m = (uint32_t)(b.zeta_slow(g, k) + 1ull);
+            else { m = (uint32_t)zeta_any<K>(b, g, k); b.topup(); }  // gap >= 2^24: up to two words, then the ring is topped up out of turn
             v += m;  // :966 (gap + 1)
             f.add(v);
-            if (STORE && store) row[i] = (int32_t)v;
+            if (STORE && store) wr.put(v);
         }
+        if (STORE && store) wr.flush();
         if (b.overrun() || b.pos(g) > g.bit_end - g.bit_base) fail(g, E_IO);
     }
 
@@ -447,9 +556,25 @@ struct CopyRuns {
 __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CopyRuns& c, int32_t x, const int32_t* __restrict__ parent) {
     Fold32 f;
     f.begin(x);
-    uint32_t at;
+    // four positions first, then their four loads together: a lane opens a new sector of its parent's row every eighth
+    // element, and with one load per trip the warp would wait for that miss on every trip
 #pragma unroll 1
-    while (c.next(g, at)) { f.add((uint32_t)parent[at]); f.n++; }
+    for (;;) {
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const bool h0 = c.next(g, a0);
+        const bool h1 = h0 && c.next(g, a1);
+        const bool h2 = h1 && c.next(g, a2);
+        const bool h3 = h2 && c.next(g, a3);
+        const uint32_t v0 = h0 ? (uint32_t)parent[a0] : 0u;
+        const uint32_t v1 = h1 ? (uint32_t)parent[a1] : 0u;
+        const uint32_t v2 = h2 ? (uint32_t)parent[a2] : 0u;
+        const uint32_t v3 = h3 ? (uint32_t)parent[a3] : 0u;
+        if (h0) { f.add(v0); f.n++; }
+        if (h1) { f.add(v1); f.n++; }
+        if (h2) { f.add(v2); f.n++; }
+        if (h3) { f.add(v3); f.n++; }
+        if (!h3) break;
+    }
     return f.finish(x);
 }
 
@@ -458,10 +583,12 @@ __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, Cop
 // BVGraphNodeIterator does when it drains, BVGraph.java:1210).  Folds the copied successors only: the extras were
 // folded when they were decoded.
 __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CopyRuns& c, int32_t x, int32_t d, int32_t copied,
-                                                           int32_t* __restrict__ row, const int32_t* __restrict__ parent) {
+                                                           int32_t* row, const int32_t* __restrict__ parent) {
     Fold32 f;
     f.begin(x);
     int32_t j = copied, k = 0;
+    RowWriter<false> wr;  // measured: combining helps the extras kernel (3.92 -> 3.71 ms) and costs registers here (2.22 -> 2.49 ms)
+    wr.begin(row);
     uint32_t at;
     bool have_a = c.next(g, at);
     uint32_t a = have_a ? (uint32_t)parent[at] : 0xffffffffu;
@@ -470,22 +597,23 @@ __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, Co
     while (k < d) {
         if (!have_a) {
             if (k == j) break;  // nothing was dropped: the remaining extras already sit in place
-            if (j < d) { row[k++] = (int32_t)bv; j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; continue; }
-            row[k++] = -1;      // duplicates were dropped
+            if (j < d) { wr.put(bv); k++; j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; continue; }
+            wr.put(0xffffffffu); k++;  // duplicates were dropped
             continue;
         }
         if (a <= bv) {
-            row[k++] = (int32_t)a;
+            wr.put(a); k++;
             f.add(a); f.n++;
             if (a == bv) { j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; }  // equal heads are emitted once
             have_a = c.next(g, at);
             if (have_a) a = (uint32_t)parent[at];
         } else {
-            row[k++] = (int32_t)bv;
+            wr.put(bv); k++;
             j++;
             bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
         }
     }
+    wr.flush();
     return f.finish(x);
 }
 
