@@ -475,7 +475,7 @@ struct ScanExtras {
             if ((((uint32_t)i + 1u) & 3u) == 0u) b.topup();  // the first residual may have taken two words: 2 + 2, then every 4 codes
             uint32_t m, len;
             if (zeta_fast<K>(b.top(), k, m, len)) b.skip(len);
-            else { m = (uint32_t)zeta_any<K>(b, g, k); b.topup(); }  // gap >= 2^24: up to two words, then the ring is topped up out of turn
+            else { b.topup(); m = (uint32_t)zeta_any<K>(b, g, k); b.topup(); }  // gap >= 2^24: up to two words, between two out-of-turn topups
             v += m;  // :966 (gap + 1)
             f.add(v);
             if (STORE && store) wr.put(v);
