@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--max-degree", type=int, default=1 << 22, help="experiments only: cap on the generator's outdegree law")
     ap.add_argument("--workdir", default=os.environ.get("BVG_BENCH_DIR", "/tmp/bvg_bench"))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational random-access / materialise legs")
     ap.add_argument("--random-nodes", type=int, default=10_000_000)

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -52,6 +53,88 @@ struct Trace {
         t0 = t1;
     }
 };
+
+// ------------------------------------------------------------------------------------------------------------
+// Device memory.  Graph arrays, open-time temporaries and per-scan scratch come from a size-keyed cache of cudaMalloc'd
+// blocks owned by the library: an open-scan-close cycle asks for the same ~70 sizes every time, and the driver's
+// stream-ordered pool (cudaMallocAsync), which served them before, occasionally takes 0.5 s to hand out a 256 MB block
+// it had cached a moment earlier (measured: one open in seven on the 1 B-arc graph).  A freed block remembers an event
+// on the stream it was last used on; reuse on that stream is ordered by the stream itself, reuse on another stream
+// waits for the event.
+// ------------------------------------------------------------------------------------------------------------
+struct DevBlock { void* p; size_t bytes; int dev; cudaStream_t stream; cudaEvent_t ev; };
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, DevBlock> idle;
+    std::map<void*, DevBlock> live;
+    size_t idle_bytes = 0;
+    size_t cap() const {
+        static const size_t c = [] { const char* v = getenv("BVG_CACHE_GB"); return (size_t)(v ? atol(v) : 32) << 30; }();
+        return c;
+    }
+    void drop_idle(int dev) {  // caller holds mu
+        for (auto it = idle.begin(); it != idle.end();) {
+            if (it->second.dev == dev) { cudaEventDestroy(it->second.ev); cudaFree(it->second.p); idle_bytes -= it->second.bytes; it = idle.erase(it); }
+            else ++it;
+        }
+        cudaGetLastError();
+    }
+};
+static DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }  // leaked on purpose: no CUDA calls at exit
+
+static cudaError_t dev_alloc(void** out, size_t bytes, cudaStream_t s) {
+    *out = nullptr;
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.idle.lower_bound(std::make_pair(dev, bytes));
+    if (it != c.idle.end() && it->first.first == dev && it->second.bytes <= bytes + bytes / 8) {
+        DevBlock b = it->second;
+        c.idle.erase(it);
+        c.idle_bytes -= b.bytes;
+        if (b.stream != s) { e = cudaStreamWaitEvent(s, b.ev, 0); if (e != cudaSuccess) { cudaGetLastError(); cudaEventSynchronize(b.ev); } }
+        b.stream = s;
+        c.live[b.p] = b;
+        *out = b.p;
+        return cudaSuccess;
+    }
+    DevBlock b{ nullptr, bytes, dev, s, nullptr };
+    e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {  // give the idle blocks back and try once more
+        cudaGetLastError();
+        c.drop_idle(dev);
+        e = cudaMalloc(&b.p, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFree(b.p); return e; }
+    c.live[b.p] = b;
+    *out = b.p;
+    return cudaSuccess;
+}
+
+static cudaError_t dev_free(void* p, cudaStream_t s) {
+    if (!p) return cudaSuccess;
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return cudaErrorInvalidValue;
+    DevBlock b = it->second;
+    c.live.erase(it);
+    if (c.idle_bytes + b.bytes > c.cap() || cudaEventRecord(b.ev, s) != cudaSuccess) {
+        cudaGetLastError();
+        cudaEventDestroy(b.ev);
+        cudaFree(b.p);  // synchronises with everything that may still use the block
+        return cudaSuccess;
+    }
+    b.stream = s;
+    c.idle.emplace(std::make_pair(b.dev, b.bytes), b);
+    c.idle_bytes += b.bytes;
+    return cudaSuccess;
+}
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
 
@@ -162,8 +245,8 @@ struct Tmp {
     T* p = nullptr;
     cudaStream_t s;
     explicit Tmp(cudaStream_t st) : s(st) {}
-    cudaError_t alloc(size_t count) { return cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), s); }
-    ~Tmp() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t count) { return dev_alloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T), s); }
+    ~Tmp() { if (p) dev_free(p, s); }
 };
 
 static int set_codec(bvg_graph* g) {
@@ -254,7 +337,7 @@ static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t
     CK(sbase.alloc((size_t)nsub));
     CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(sbase.p, sbv.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMallocAsync((void**)d_full, ((size_t)n + 1) * 8, s));
+    CK(dev_alloc((void**)d_full, ((size_t)n + 1) * 8, s));
     LAUNCH(k_off_emit, grid_for(nsub, 128), 128, 0, s, words.p, nwords, total_bits, coding, nsub, in, cbase.p, sbase.p, n, *d_full);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // cb / sbv are host vectors
@@ -282,10 +365,10 @@ static int build_long_index(bvg_graph* g) {
     CK(cudaMemcpyAsync(&nl, pos.p + nn, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (nl == 0) return BVG_OK;
-    CK(cudaMallocAsync((void**)&g->d_long_nodes, (size_t)nl * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_long_nodes, (size_t)nl * 4, g->stream));
     long_nodes.p = g->d_long_nodes;
     LAUNCH(k_long_compact, grid_for(nn, 256), 256, 0, s, flags.p, pos.p, nn, g->node_lo, long_nodes.p);
-    CK(cudaMallocAsync((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta), g->stream));
+    CK(dev_alloc((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta), g->stream));
     if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_is_parent, g->d_long_meta);
     else LAUNCH(k_long_count<false>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_is_parent, g->d_long_meta);
     std::vector<LongMeta> meta((size_t)nl);
@@ -314,15 +397,15 @@ static int build_long_index(bvg_graph* g) {
             (m.rc > 0 ? (int64_t)((m.rec_end - m.resid_pos + (uint64_t)LSPEC_BITS - 1) / (uint64_t)LSPEC_BITS) : 0);
     }
     g->nlong = (int32_t)nl;  // item_map() below needs it; reset on failure by the caller's destroy
-    CK(cudaMallocAsync((void**)&g->d_long_cum, cum.size() * 8, g->stream));
+    CK(dev_alloc((void**)&g->d_long_cum, cum.size() * 8, g->stream));
     CK(cudaMemcpyAsync(g->d_long_cum, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), cudaMemcpyHostToDevice, s));
-    CK(cudaMallocAsync((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_iv_cum, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_iv_left, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_seg_pos, (size_t)std::max<int64_t>(seg, 1) * 8, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_seg_val, (size_t)std::max<int64_t>(seg, 1) * 8, g->stream));
+    CK(dev_alloc((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_iv_cum, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_iv_left, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_seg_pos, (size_t)std::max<int64_t>(seg, 1) * 8, g->stream));
+    CK(dev_alloc((void**)&g->d_seg_val, (size_t)std::max<int64_t>(seg, 1) * 8, g->stream));
     // copy blocks and intervals: one short walk per record; residual sync points: speculative sub-ranges (bvg_long.cuh)
     if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
     else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
@@ -386,11 +469,11 @@ static int build_schedules(bvg_graph* g) {
     if (nn == 0) return BVG_OK;
     cudaStream_t s = g->stream;
     Trace tr(s);
-    CK(cudaMallocAsync((void**)&g->d_is_parent, (size_t)nn, g->stream));
+    CK(dev_alloc((void**)&g->d_is_parent, (size_t)nn, g->stream));
     CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
     LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
-    const int64_t nchunks = (nn + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG;
+    const int64_t nchunks = ((nn + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG) + 1;  // + the slot of the heavy records, scheduled first
     const int64_t per_level = nchunks * 2 * ORDER_BUCKETS;  // chunk x (parent | not) x half-octave bucket
     const int64_t nb_e = nchunks * 4 * ORDER_BUCKETS, nb_m = (int64_t)std::max(levels, 1) * per_level;
     Tmp<int32_t> key_e(s), key_m(s), bins(s), bcs(s);
@@ -403,7 +486,7 @@ static int build_schedules(bvg_graph* g) {
     CK(bins.alloc((size_t)(nb_e + nb_m)));
     CK(cudaMemsetAsync(bins.p, 0, (size_t)(nb_e + nb_m) * 4, s));
     GraphDev gd = g->dev();
-    CK(cudaMallocAsync((void**)&g->d_copied, (size_t)nn * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_copied, (size_t)nn * 4, g->stream));
     if (g->def_codec) LAUNCH(k_order_keys<true>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, g->long_d, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
     else LAUNCH(k_order_keys<false>, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, levels, g->long_d, g->d_is_parent, g->d_copied, epos.p, bpos.p, bcs.p);
     tr.mark("  sched: parents + keys");
@@ -424,10 +507,10 @@ static int build_schedules(bvg_graph* g) {
     }
     g->level_start[(size_t)levels] = run;
     CK(cudaMemcpyAsync(bins.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMallocAsync((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_rec_e, std::max<size_t>((size_t)g->order_e_count, 1) * sizeof(ExtraRec), g->stream));
-    CK(cudaMallocAsync((void**)&g->d_rec_m, std::max<size_t>((size_t)run, 1) * sizeof(MergeRec), g->stream));
+    CK(dev_alloc((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_rec_e, std::max<size_t>((size_t)g->order_e_count, 1) * sizeof(ExtraRec), g->stream));
+    CK(dev_alloc((void**)&g->d_rec_m, std::max<size_t>((size_t)run, 1) * sizeof(MergeRec), g->stream));
     LAUNCH(k_key_scatter_recs, grid_for(nn, 256), 256, 0, s, gd, key_e.p, key_m.p, nn, bins.p, bins.p + nb_e, g->d_is_parent, g->d_copied,
            epos.p, bpos.p, bcs.p, g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m);
     CK(cudaGetLastError());
@@ -442,23 +525,23 @@ static int build_device_state(bvg_graph* g, const uint8_t* bytes, uint64_t nbyte
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
     Trace tr(g->stream);
     g->nwords = ((nbytes + 3) / 4 + STREAM_PAD_WORDS + 3) & ~(uint64_t)3;  // padding words, a whole number of 128-bit groups
-    CK(cudaMallocAsync((void**)&g->d_words, g->nwords * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_words, g->nwords * 4, g->stream));
     CK(cudaMemsetAsync(g->d_words, 0, g->nwords * 4, g->stream));
     if (nbytes) CK(cudaMemcpyAsync(g->d_words, bytes, nbytes, cudaMemcpyHostToDevice, g->stream));
     LAUNCH(k_bswap, grid_for((int64_t)g->nwords, 256), 256, 0, g->stream, g->d_words, g->nwords);
     tr.mark("alloc + H2D stream + bswap");
     if (g->node_lo == 0 && nn == n_full) g->d_offsets = d_offsets_full;  // whole graph: adopt the decoded array
     else {
-        CK(cudaMallocAsync((void**)&g->d_offsets, ((size_t)nn + 1) * 8, g->stream));
+        CK(dev_alloc((void**)&g->d_offsets, ((size_t)nn + 1) * 8, g->stream));
         CK(cudaMemcpyAsync(g->d_offsets, d_offsets_full + g->node_lo, ((size_t)nn + 1) * 8, cudaMemcpyDeviceToDevice, g->stream));
         CK(cudaStreamSynchronize(g->stream));
-        cudaFreeAsync(d_offsets_full, g->stream);
+        dev_free(d_offsets_full, g->stream);
     }
-    CK(cudaMallocAsync((void**)&g->d_outdeg, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_ref, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_depth, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_rowoff, ((size_t)nn + 1) * 8, g->stream));
-    CK(cudaMallocAsync((void**)&g->d_err, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
+    CK(dev_alloc((void**)&g->d_outdeg, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_ref, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_depth, std::max<size_t>((size_t)nn, 1) * 4, g->stream));
+    CK(dev_alloc((void**)&g->d_rowoff, ((size_t)nn + 1) * 8, g->stream));
+    CK(dev_alloc((void**)&g->d_err, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
     CK(cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord) + 2 * sizeof(int32_t), g->stream));
     int32_t* d_max = (int32_t*)(g->d_err + 1);  // [0] max depth, [1] max outdegree
     GraphDev gd = g->dev();
@@ -495,7 +578,7 @@ static void destroy(bvg_graph* g) {
     void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
                      g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
                      g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum };
-    for (void* p : ptrs) if (p) cudaFreeAsync(p, g->stream);
+    for (void* p : ptrs) if (p) dev_free(p, g->stream);
     cudaStreamSynchronize(g->stream);
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
@@ -574,14 +657,14 @@ int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint
     uint64_t* d_full = nullptr;
     rc = device_decode_offsets(g->stream, offsets_stream, offsets_bytes, oc, nodes, &d_full);
     tr.mark("device: decode .offsets");
-    if (rc) { cudaFreeAsync(d_full, g->stream); destroy(g); return rc; }
+    if (rc) { dev_free(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     g->node_lo = shard_halo(g, from); g->node_hi = to;
     uint64_t o3[3];  // offsets of node_lo, to, nodes
     if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
         cudaMemcpy(&o3[1], d_full + to, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(&o3[2], d_full + nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_ECUDA; }
-    if (o3[2] > graph_bytes * 8) { cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_EIO; }
+        cudaMemcpy(&o3[2], d_full + nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); dev_free(d_full, g->stream); destroy(g); return BVG_ECUDA; }
+    if (o3[2] > graph_bytes * 8) { dev_free(d_full, g->stream); destroy(g); return BVG_EIO; }
     g->graph_bits_total = o3[2];
     const uint64_t byte_lo = (o3[0] >> 3) & ~(uint64_t)15;
     const uint64_t byte_hi = std::min<uint64_t>(graph_bytes, (o3[1] + 7) >> 3);
@@ -659,19 +742,19 @@ int bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, b
     const int oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
     uint64_t* d_full = nullptr;
     rc = device_decode_offsets(g->stream, ostream.data(), ostream.size(), oc, p.nodes, &d_full);
-    if (rc) { cudaFreeAsync(d_full, g->stream); destroy(g); return rc; }
+    if (rc) { dev_free(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     g->node_lo = shard_halo(g, from); g->node_hi = to;
     uint64_t o3[3];
     if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
         cudaMemcpy(&o3[1], d_full + to, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(&o3[2], d_full + p.nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_ECUDA; }
+        cudaMemcpy(&o3[2], d_full + p.nodes, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); dev_free(d_full, g->stream); destroy(g); return BVG_ECUDA; }
     g->graph_bits_total = o3[2];
     const uint64_t byte_lo = (o3[0] >> 3) & ~(uint64_t)15;
     const uint64_t byte_hi = (o3[1] + 7) >> 3;
     g->bit_base = byte_lo * 8; g->bit_end = o3[1];
     std::vector<uint8_t> bytes;
-    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { cudaFreeAsync(d_full, g->stream); destroy(g); return BVG_EIO; }
+    if (!slurp_file(std::string(basename) + ".graph", bytes, byte_lo, byte_hi - byte_lo) || bytes.size() != byte_hi - byte_lo) { dev_free(d_full, g->stream); destroy(g); return BVG_EIO; }
     rc = build_device_state(g, bytes.data(), bytes.size(), d_full, p.nodes);
     if (rc) { destroy(g); return rc; }
     *out = g;
@@ -1211,13 +1294,13 @@ int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32
     if (on_device) { CK(cudaMemcpyAsync(&total, off + count, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
     else total = off[count];
     if (count + 1 > g->halo_off_cap) {
-        cudaFreeAsync(g->d_halo_off, g->stream); g->d_halo_off = nullptr; g->halo_off_cap = 0;
-        CK(cudaMallocAsync((void**)&g->d_halo_off, ((size_t)count + 1) * 8, g->stream));
+        dev_free(g->d_halo_off, g->stream); g->d_halo_off = nullptr; g->halo_off_cap = 0;
+        CK(dev_alloc((void**)&g->d_halo_off, ((size_t)count + 1) * 8, g->stream));
         g->halo_off_cap = count + 1;
     }
     if (total > g->halo_lists_cap) {
-        cudaFreeAsync(g->d_halo_lists, g->stream); g->d_halo_lists = nullptr; g->halo_lists_cap = 0;
-        CK(cudaMallocAsync((void**)&g->d_halo_lists, (size_t)total * 2 * 4, g->stream));
+        dev_free(g->d_halo_lists, g->stream); g->d_halo_lists = nullptr; g->halo_lists_cap = 0;
+        CK(dev_alloc((void**)&g->d_halo_lists, (size_t)total * 2 * 4, g->stream));
         g->halo_lists_cap = total * 2;
     }
     CK(cudaMemcpyAsync(g->d_halo_off, off, ((size_t)count + 1) * 8, kind, s));

@@ -83,6 +83,10 @@ constexpr int ORDER_BUCKETS = 256;
 // warp still get records of similar length, but everything in flight at one time comes from a few tens of MB of the
 // stream, the index arrays and the rows, which the 126 MB L2 can hold.
 constexpr int ORDER_CHUNK_LOG = 18;
+// Heavy records (work >= ORDER_HEAVY) of all chunks are scheduled first, before chunk 0: a record is one lane's serial
+// work, so a kernel cannot end before the heaviest record of its LAST chunk has been walked -- ~0.2 ms per launch on the
+// benchmark graph when the heavy records start with their chunk.
+constexpr int ORDER_HEAVY = 192;
 
 __device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // quarter octaves: 0..255, monotone in v
     if (v == 0) return 0;
@@ -134,12 +138,15 @@ __global__ void k_order_keys(GraphDev g, int32_t* __restrict__ key_e, int32_t* _
             // what a lane's loop length is: residual count for the tight loop, record bits for the interval loop
             // (and records whose list somebody copies from store it: a third kind of loop, see k_scan_extras_lean)
             const uint64_t work_e = has_iv ? g.offsets[i + 1] - g.offsets[i] : (uint64_t)(d - copied);
-            ke = (chunk * 4 + has_iv * 2 + (is_parent[i] ? 1 : 0)) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work_e));
+            const uint64_t serial_e = (uint64_t)(d - copied);  // trips of the lane that walks it
+            const int32_t slot_e = serial_e >= (uint64_t)ORDER_HEAVY ? 0 : chunk + 1;
+            ke = (slot_e * 4 + has_iv * 2 + (is_parent[i] ? 1 : 0)) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work_e));
             if (dep >= 1 && dep <= max_level_keys) {
                 const int par = is_parent[i] ? 1 : 0;  // parents merge in place, the others only stream: separate warps too
                 const uint64_t work = 2 * (uint64_t)bc + (uint64_t)copied + (par ? (uint64_t)(d - copied) : 0);
-                const int32_t nchunks = (int32_t)((n + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG);
-                km = (((dep - 1) * nchunks + chunk) * 2 + par) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
+                const int32_t nslots = (int32_t)((n + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG) + 1;
+                const int32_t slot_m = work >= (uint64_t)ORDER_HEAVY ? 0 : chunk + 1;
+                km = (((dep - 1) * nslots + slot_m) * 2 + par) * ORDER_BUCKETS + (ORDER_BUCKETS - 1 - half_octave_bucket(work + 1));
             }
         }
     }
