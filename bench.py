@@ -178,7 +178,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from webgraph_b200 import bvgraph
+    from webgraph_b200 import bvgraph, sharding
     from webgraph_b200.bvgraph import BVGraph
 
     if not torch.cuda.is_available():
@@ -233,8 +233,8 @@ def main():
         cap_t = torch.tensor([barcs], device=dev)
         dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
         bcap = int(cap_t.item())
-        # fixed-size message: [count+1 offsets as int64 | bcap successors as int32 padded to int64 words]
-        msg_words = (bc + 1) + (bcap + 1) // 2
+        # fixed-size message: [count+1 offsets as int64 | bcap successors as int32 padded to int64 words] (webgraph_b200/sharding.py)
+        msg_words = sharding.message_words(bc, bcap)
         send = torch.zeros(msg_words, dtype=torch.int64, device=dev)
         recv = torch.zeros(world * msg_words, dtype=torch.int64, device=dev)
 
@@ -245,9 +245,9 @@ def main():
         off_ptr = send.data_ptr()
         lists_ptr = send.data_ptr() + 8 * (bc + 1)
         bvgraph._check(L.bvg_boundary_export(g.handle, off_ptr, lists_ptr, bcap, 1))
-        dist.all_gather_into_tensor(recv, send)
+        sharding.exchange(send, recv)
         if rank > 0:
-            src = recv.data_ptr() + 8 * msg_words * (rank - 1)
+            src = sharding.previous_rank_message(recv, rank, msg_words).data_ptr()
             bvgraph._check(L.bvg_halo_import(g.handle, bc, src, src + 8 * (bc + 1), 1))
 
     def step():
