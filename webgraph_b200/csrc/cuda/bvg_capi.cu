@@ -889,7 +889,13 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
     const bool ordered = g->d_order_e && g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
     if (ordered) {
-        if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+        // default codings: the lean walkers of the consume-only scan with every list stored (bvg_scan.cuh)
+        static const bool lean = !(getenv("BVG_DECODE_LEAN") && atoi(getenv("BVG_DECODE_LEAN")) == 0);
+        const bool use_lean = g->def_codec && lean && g->d_rec_e && g->d_rec_m;
+        unsigned long long* const no_fold = nullptr;
+        if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
+        else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
+        else if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
         else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
         Tmp<int32_t> long_tmp(s);
         LongDst ld{ nullptr };
@@ -907,7 +913,8 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
         for (int32_t level = 1; level <= g->max_depth; level++) {
             const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
             if (c > 0) {
-                if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+                if (use_lean) LAUNCH_P(g, "k_merge_lean", k_scan_merge_lean, grid_for(c, 128), 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, no_fold, 1);
+                else if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
                 else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
             }
             if (g->nlong) {
@@ -982,10 +989,10 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
     static const int dbg_nostore = env_int("BVG_DEBUG_NOSTORE", 0, 0, 1);  // timing experiments only: no row stores, results are wrong
     static const bool ring = env_int("BVG_SCAN_RING", 1, 0, 1) != 0;  // stream staged in shared memory by cp.async (bvg_scan.cuh, WinRing)
-    if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore);
-    else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore);
-    else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore);
-    else if (g->def_codec && lean) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore);
+    if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
+    else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
+    else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
+    else if (g->def_codec && lean) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
     else if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     Tmp<int32_t> long_tmp(s);
@@ -1006,7 +1013,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
         if (c > 0) {
             const unsigned gm = (unsigned)std::min<int64_t>(grid_m, (c + 127) / 128);
             static const bool lean_m = !(getenv("BVG_MERGE_LEAN") && atoi(getenv("BVG_MERGE_LEAN")) == 0);
-            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", k_scan_merge_lean, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
+            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", k_scan_merge_lean, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
             else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }

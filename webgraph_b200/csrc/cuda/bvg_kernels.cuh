@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // front of them in a second walk (ScanExtras::iv_merge).
 template <int K, bool RING>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
-                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore) {
+                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
     typedef typename std::conditional<RING, WinRing<SCAN_BLOCK>, Win>::type W;
     const ring_addr my_ring = ring_address(&ring[RING ? threadIdx.x : 0]);
@@ -557,8 +557,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         r.x = -1; r.flags = 0;
         if (i < count) r = recs[i];
         bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
-        const bool store = active && (r.flags & 1u) && debug_nostore != 1;
-        const bool fold = active && r.x >= from;
+        const bool store = active && ((r.flags & 1u) || store_all) && debug_nostore != 1;  // store_all: range decode, every list is materialised
+        const bool fold = active && r.x >= from && !store_all;
         active = active && (fold || store);  // halo nodes matter only as parents
         const bool has_iv = (r.flags & 2u) != 0;
         int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         if (active) f = w.finish();
         if (fold) { acc ^= f; arcs += r.d; }
     }
-    warp_fold(acc, arcs, result);
+    if (result) warp_fold(acc, arcs, result);
 }
 
 template <bool DEF>
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(G
 
 // Merge step with the staged copy runs of bvg_scan.cuh (default codings).
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
-                             int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result) {
+                             int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int store_all) {
     __shared__ int32_t runs[2 * COPY_RUNS * SCAN_BLOCK];
     unsigned long long acc = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -618,8 +618,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_l
         r.x = -1; r.flags = 0;
         if (i < count) r = recs[i];
         bool active = r.x >= lo && r.x < hi && rm.wanted(g, r.x);
-        const bool store = active && (r.flags & 1u);
-        const bool fold = active && r.x >= from;
+        const bool store = active && ((r.flags & 1u) || store_all);
+        const bool fold = active && r.x >= from && !store_all;
         active = active && (fold || store);
         CopyRuns c;
         c.begin(g, r.pos, r.bc, r.dp, runs + threadIdx.x, SCAN_BLOCK, active);
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_l
         __syncwarp();
         if (fold) acc ^= f;
     }
-    warp_fold(acc, 0, result);
+    if (result) warp_fold(acc, 0, result);
 }
 
 // ---------------------------------------------------------------------------------------------------
