@@ -845,6 +845,7 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
     cudaStream_t s = g->stream;
     GraphDev gd = g->dev();
     rm.out = d_out; rm.out_base = row_from; rm.from = from; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = from; rm.halo_base = row_from;
+    rm.mask = nullptr;
     hp.lo = from;
     if (g->max_depth > 0 && from > g->node_lo) {
         if (g->halo_count > 0 && from == g->ext_from) {  // lists imported from the previous shard
@@ -877,6 +878,48 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
 }
 
 // Enqueues the decode of [from, to) into d_out (device, >= arcs entries). All temporaries are stream-ordered.
+// Range decode over the length-bucketed schedules: extras of every wanted node, long records split across threads, one
+// merge launch per chain level.
+static int run_ordered_decode(const bvg_graph* g, int32_t lo, int32_t to, int32_t from, const RowMap& rm) {
+    cudaStream_t s = g->stream;
+    GraphDev gd = g->dev();
+    // default codings: the lean walkers of the consume-only scan with every list stored (bvg_scan.cuh)
+    static const bool lean = !(getenv("BVG_DECODE_LEAN") && atoi(getenv("BVG_DECODE_LEAN")) == 0);
+    const bool use_lean = g->def_codec && lean && g->d_rec_e && g->d_rec_m;
+    unsigned long long* const no_fold = nullptr;
+    if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
+    else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
+    else if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+    else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+    Tmp<int32_t> long_tmp(s);
+    LongDst ld{ nullptr };
+    const LongIndex li = g->long_index();
+    if (g->nlong) {
+        CK(long_tmp.alloc((size_t)g->long_tmp_entries));
+        ld.tmp = long_tmp.p;
+        const LongFold lf{ nullptr, 0 };  // range decode: every long record is materialised
+        if (g->n_items_resid) {
+            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+        }
+        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
+    }
+    for (int32_t level = 1; level <= g->max_depth; level++) {
+        const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
+        if (c > 0) {
+            if (use_lean) LAUNCH_P(g, "k_merge_lean", k_scan_merge_lean, grid_for(c, 128), 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, no_fold, 1);
+            else if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+            else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
+        }
+        if (g->nlong) {
+            const int64_t mc = g->n_items_merge[(size_t)level];
+            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, LongFold{ nullptr, 0 });
+        }
+    }
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+
 static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from) {
     if (to == from) return BVG_OK;
     cudaStream_t s = g->stream;
@@ -888,43 +931,7 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     const int64_t cnt = (int64_t)to - lo;
     // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
     const bool ordered = g->d_order_e && g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
-    if (ordered) {
-        // default codings: the lean walkers of the consume-only scan with every list stored (bvg_scan.cuh)
-        static const bool lean = !(getenv("BVG_DECODE_LEAN") && atoi(getenv("BVG_DECODE_LEAN")) == 0);
-        const bool use_lean = g->def_codec && lean && g->d_rec_e && g->d_rec_m;
-        unsigned long long* const no_fold = nullptr;
-        if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
-        else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
-        else if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
-        else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
-        Tmp<int32_t> long_tmp(s);
-        LongDst ld{ nullptr };
-        const LongIndex li = g->long_index();
-        if (g->nlong) {
-            CK(long_tmp.alloc((size_t)g->long_tmp_entries));
-            ld.tmp = long_tmp.p;
-            const LongFold lf{ nullptr, 0 };  // range decode: every long record is materialised
-            if (g->n_items_resid) {
-                if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-                else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-            }
-            if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
-        }
-        for (int32_t level = 1; level <= g->max_depth; level++) {
-            const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
-            if (c > 0) {
-                if (use_lean) LAUNCH_P(g, "k_merge_lean", k_scan_merge_lean, grid_for(c, 128), 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, no_fold, 1);
-                else if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
-                else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
-            }
-            if (g->nlong) {
-                const int64_t mc = g->n_items_merge[(size_t)level];
-                if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, LongFold{ nullptr, 0 });
-            }
-        }
-        CK(cudaGetLastError());
-        return BVG_OK;
-    }
+    if (ordered) return run_ordered_decode(g, lo, to, from, rm);
     if (g->def_codec) LAUNCH_P(g, "k_extras", k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
     else LAUNCH_P(g, "k_extras", k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
     for (int32_t level = 1; level <= g->max_depth; level++) {
@@ -1146,14 +1153,28 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
     CK(scratch_off.alloc((size_t)nx + 1));
     int64_t* off_dev = out_off;
     if (!on_device) { CK(d_off.alloc((size_t)nx + 1)); off_dev = d_off.p; }
-    if (nx) LAUNCH(k_query_sizes, grid_for(nx, 256), 256, 0, s, gd, xs_dev, nx, dq.p, need.p);
+    // queries whose chain holds a long record go through the range kernels (k_query_sizes marks their chains)
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    const bool split_long = g->nlong > 0 && g->d_order_e && g->d_rec_e && g->max_depth <= MAX_LEVEL_KEYS;
+    Tmp<uint8_t> mask(s), heavy(s);
+    Tmp<int32_t> nheavy(s);
+    if (split_long) {
+        CK(mask.alloc((size_t)nn));
+        CK(heavy.alloc((size_t)std::max<int64_t>(nx, 1)));
+        CK(nheavy.alloc(1));
+        CK(cudaMemsetAsync(mask.p, 0, (size_t)nn, s));
+        CK(cudaMemsetAsync(nheavy.p, 0, 4, s));
+    }
+    if (nx) LAUNCH(k_query_sizes, grid_for(nx, 256), 256, 0, s, gd, xs_dev, nx, dq.p, need.p, g->long_d, mask.p, heavy.p, nheavy.p);
     int rc = device_exclusive_scan(s, dq.p, nx, off_dev);
     if (rc) return rc;
     rc = device_exclusive_scan(s, need.p, nx, scratch_off.p);
     if (rc) return rc;
     int64_t tot[2];
+    int32_t n_heavy = 0;
     CK(cudaMemcpyAsync(&tot[0], off_dev + nx, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&tot[1], scratch_off.p + nx, 8, cudaMemcpyDeviceToHost, s));
+    if (split_long) CK(cudaMemcpyAsync(&n_heavy, nheavy.p, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     int e = fetch_error(g);
     if (e) return e;
@@ -1163,9 +1184,23 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
     int32_t* out_dev = out;
     if (!on_device) { CK(d_out.alloc((size_t)tot[0])); out_dev = d_out.p; }
     CK(scratch.alloc((size_t)tot[1]));
+    const uint8_t* heavy_flags = n_heavy > 0 ? heavy.p : nullptr;
     if (nx) {
-        if (g->def_codec) LAUNCH_P(g, "k_random", k_random<true>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
-        else LAUNCH_P(g, "k_random", k_random<false>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p);
+        if (g->def_codec) LAUNCH_P(g, "k_random", k_random<true>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p, heavy_flags);
+        else LAUNCH_P(g, "k_random", k_random<false>, grid_for(nx, 128), 128, 0, s, gd, xs_dev, nx, off_dev, out_dev, scratch_off.p, scratch.p, heavy_flags);
+    }
+    Tmp<int32_t> rows(s);
+    if (n_heavy > 0) {  // the marked chains, decoded by the range kernels into a scratch laid out like the CSR
+        int64_t ra, rb;
+        rc = fetch_rowoff(g, g->node_lo, g->node_hi, &ra, &rb);
+        if (rc) return rc;
+        CK(rows.alloc((size_t)(rb - ra)));
+        RowMap rm;
+        rm.out = rows.p; rm.out_base = ra; rm.from = g->node_lo; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = g->node_lo; rm.halo_base = ra;
+        rm.mask = mask.p;
+        rc = run_ordered_decode(g, g->node_lo, g->node_hi, g->node_lo, rm);
+        if (rc) return rc;
+        LAUNCH_P(g, "k_gather_rows", k_gather_rows, 148 * 8, 256, 0, s, gd, xs_dev, nx, heavy.p, off_dev, out_dev, rm);
     }
     CK(cudaGetLastError());
     if (on_device) return BVG_OK;

@@ -331,6 +331,7 @@ struct RowMap {
         return x >= from ? out + (g.rowoff[x - g.node_lo] - out_base) : halo + halo_off[x - halo_lo];
     }
     int64_t halo_base;         // rowoff of halo_lo (both halo kinds are laid out like the CSR from there)
+    const uint8_t* mask;       // when set: decode exactly the nodes with mask[x - node_lo] != 0 (indexed like the graph's arrays)
     // row pointer of node y from its CSR-space offset (schedule records carry the offsets)
     __device__ __forceinline__ int32_t* at(int32_t y, int64_t off) const {
         return y >= from ? out + (off - out_base) : halo + (off - halo_base);
@@ -338,6 +339,7 @@ struct RowMap {
     // A halo node is decoded only if its whole chain lies inside the halo: halo_lo is the smallest chain root of the
     // requested range, so a halo node whose chain starts before it is nobody's ancestor (and its parent has no row).
     __device__ __forceinline__ bool wanted(const GraphDev& g, int32_t x) const {
+        if (mask) return mask[x - g.node_lo] != 0;  // random-access batches: only the nodes on the queried chains
         if (x >= from) return true;
         int64_t y = (int64_t)x - g.node_lo;
         for (;;) {
@@ -642,30 +644,66 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_l
 // ---------------------------------------------------------------------------------------------------
 
 // Per query: outdegree of x and scratch needed for its strict ancestors' rows.
+// A query whose chain holds a record of more than `long_d` successors is not walked by one thread: its chain is marked
+// in `mask` (when given), decoded by the range kernels -- which split long records across threads -- into a scratch laid
+// out like the CSR, and copied out by k_gather_rows.  heavy[q] = 1 for those queries, and they need no chain scratch.
 __global__ void k_query_sizes(GraphDev g, const int32_t* __restrict__ xs, int64_t nx,
-                              int32_t* __restrict__ dq, int32_t* __restrict__ need) {
+                              int32_t* __restrict__ dq, int32_t* __restrict__ need,
+                              int32_t long_d, uint8_t* __restrict__ mask, uint8_t* __restrict__ heavy, int32_t* __restrict__ nheavy) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nx) return;
     const int32_t x = xs[q];
+    if (heavy) heavy[q] = 0;
     if (x < g.node_lo || x >= g.node_hi) { report(g.err, E_INVAL, x, 0); dq[q] = 0; need[q] = 0; return; }
     int64_t y = x - g.node_lo;
     dq[q] = g.outdeg[y];
     if (g.depth[y] < 0) { report(g.err, E_FORMAT, x, 0); need[q] = 0; return; }
     int64_t s = 0;
+    bool is_heavy = mask != nullptr && g.outdeg[y] > long_d;
     for (;;) {
         const int32_t r = g.ref[y];
         if (r == 0) break;
         y -= r;
         s += g.outdeg[y];
+        is_heavy = is_heavy || (mask != nullptr && g.outdeg[y] > long_d);
+    }
+    if (is_heavy) {
+        heavy[q] = 1;
+        atomicAdd(nheavy, 1);
+        y = x - g.node_lo;
+        for (;;) {
+            mask[y] = 1;
+            const int32_t r = g.ref[y];
+            if (r == 0) break;
+            y -= r;
+        }
+        s = 0;
     }
     need[q] = (int32_t)(s > 0x7fffffff ? 0x7fffffff : s);
 }
 
+// rows of the heavy queries, decoded into the CSR-shaped scratch, copied to their place in the batch output: one warp per query
+__global__ void k_gather_rows(GraphDev g, const int32_t* __restrict__ xs, int64_t nx, const uint8_t* __restrict__ heavy,
+                              const int64_t* __restrict__ out_off, int32_t* __restrict__ out, RowMap rm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nx; q += nw) {
+        if (!heavy[q]) continue;
+        const int32_t x = xs[q];
+        const int32_t d = g.outdeg[x - g.node_lo];
+        const int32_t* row = rm.row(g, x);
+        int32_t* dst = out + out_off[q];
+        for (int32_t i = lane; i < d; i += 32) dst[i] = row[i];
+    }
+}
+
 template <bool DEF>
 __global__ void k_random(GraphDev g, const int32_t* __restrict__ xs, int64_t nx, const int64_t* __restrict__ out_off,
-                         int32_t* __restrict__ out, const int64_t* __restrict__ scratch_off, int32_t* __restrict__ scratch) {
+                         int32_t* __restrict__ out, const int64_t* __restrict__ scratch_off, int32_t* __restrict__ scratch,
+                         const uint8_t* __restrict__ heavy) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nx) return;
+    if (heavy && heavy[q]) return;  // decoded by the range kernels, copied by k_gather_rows
     const int32_t x = xs[q];
     if (x < g.node_lo || x >= g.node_hi) return;
     const int32_t dep = g.depth[x - g.node_lo];
