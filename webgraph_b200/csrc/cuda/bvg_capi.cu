@@ -214,6 +214,17 @@ struct bvg_graph {
         std::lock_guard<std::mutex> lk(mu);
         prof_spans.push_back(p);
     }
+    // second stream + fork/join events: a consume-only scan runs the long-record kernels beside the short-record ones
+    mutable cudaStream_t aux = nullptr;
+    mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    mutable std::mutex scan_mu;
+    bool aux_ready() const {
+        if (aux) return true;
+        if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); aux = nullptr; return false; }
+        return true;
+    }
     // last device error (BVGraph.java:1129-1131 logs node + position)
     mutable std::mutex mu;
     mutable int32_t err_node = -1;
@@ -580,6 +591,7 @@ static void destroy(bvg_graph* g) {
                      g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum };
     for (void* p : ptrs) if (p) dev_free(p, g->stream);
     cudaStreamSynchronize(g->stream);
+    if (g->aux) { cudaStreamSynchronize(g->aux); cudaStreamDestroy(g->aux); cudaEventDestroy(g->ev_fork); cudaEventDestroy(g->ev_join); }
     for (ProfSpan* p : g->prof_spans) { cudaEventDestroy(p->e0); cudaEventDestroy(p->e1); delete p; }
     cudaGetLastError();
     delete g;
@@ -993,6 +1005,31 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     const unsigned wave = (unsigned)(sms * SCAN_BLOCKS_PER_SM);
     const unsigned grid = persistent ? wave : (unsigned)std::max<int64_t>(1, (g->order_e_count + SCAN_BLOCK - 1) / SCAN_BLOCK);
     const unsigned grid_m = persistent ? wave : 0x7fffffffu;
+    Tmp<int32_t> long_tmp(s);
+    LongDst ld{ nullptr };
+    const LongIndex li = g->long_index();
+    const LongFold lf{ d_result, from };  // long records nobody copies from are folded where their parts are produced
+    // BVG_SCAN_OVERLAP=1: the long-record kernels run on a second stream beside the short-record kernels of the same chain
+    // level; the two streams meet before every level, because a short record may copy from a long one and the other way
+    // round.  Measured 6.54 -> 6.44 ms per scan: the short-record kernels already fill the machine, so it is off by default
+    // and the per-kernel times of bvg_profile stay disjoint.
+    static const bool overlap = env_int("BVG_SCAN_OVERLAP", 0, 0, 1) != 0;
+    std::unique_lock<std::mutex> scan_lock(g->scan_mu, std::defer_lock);
+    cudaStream_t sa = s;
+    if (g->nlong && overlap) { scan_lock.lock(); if (g->aux_ready()) sa = g->aux; else scan_lock.unlock(); }
+    auto meet = [&]() -> cudaError_t {  // everything enqueued so far on either stream precedes everything enqueued after
+        if (sa == s) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(g->ev_join, sa);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, g->ev_join, 0);
+        if (e == cudaSuccess) e = cudaEventRecord(g->ev_fork, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(sa, g->ev_fork, 0);
+        return e;
+    };
+    if (g->nlong) {
+        CK(long_tmp.alloc((size_t)g->long_tmp_entries));
+        ld.tmp = long_tmp.p;
+        if (sa != s) { CK(cudaEventRecord(g->ev_fork, s)); CK(cudaStreamWaitEvent(sa, g->ev_fork, 0)); }
+    }
     static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
     static const int dbg_nostore = env_int("BVG_DEBUG_NOSTORE", 0, 0, 1);  // timing experiments only: no row stores, results are wrong
     static const bool ring = env_int("BVG_SCAN_RING", 1, 0, 1) != 0;  // stream staged in shared memory by cp.async (bvg_scan.cuh, WinRing)
@@ -1002,20 +1039,15 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     else if (g->def_codec && lean) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
     else if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
-    Tmp<int32_t> long_tmp(s);
-    LongDst ld{ nullptr };
-    const LongIndex li = g->long_index();
-    const LongFold lf{ d_result, from };  // long records nobody copies from are folded where their parts are produced
     if (g->nlong) {
-        CK(long_tmp.alloc((size_t)g->long_tmp_entries));
-        ld.tmp = long_tmp.p;
         if (g->n_items_resid) {
-            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
         }
-        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
+        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
+        CK(meet());
         const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
         if (c > 0) {
             const unsigned gm = (unsigned)std::min<int64_t>(grid_m, (c + 127) / 128);
@@ -1026,11 +1058,12 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
         }
         if (g->nlong) {
             const int64_t mc = g->n_items_merge[(size_t)level];
-            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
+            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
         }
     }
     if (g->nlong && g->n_items_fold)
-        LAUNCH_P(g, "k_long_fold_rows", k_long_fold_rows<RowMap>, grid_for(g->n_items_fold * 32, 256), 256, 0, s, gd, li, g->item_map(1), g->n_items_fold, lo, to, rm, lf);
+        LAUNCH_P(g, "k_long_fold_rows", k_long_fold_rows<RowMap>, grid_for(g->n_items_fold * 32, 256), 256, 0, sa, gd, li, g->item_map(1), g->n_items_fold, lo, to, rm, lf);
+    if (sa != s) { CK(cudaEventRecord(g->ev_join, sa)); CK(cudaStreamWaitEvent(s, g->ev_join, 0)); }
     CK(cudaGetLastError());
     return BVG_OK;
 }
