@@ -123,6 +123,17 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture of
+    this same workload (profiles/r01_traffic.json, written by profiles/summarise.py); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return t["kernels"].get(kernel)
+    except Exception:
+        return None
+
+
 def cpu_port_baseline(base, sample_arcs, threads):
     """The oracle's sequential scan (C restatement of BVGraph.nodeIterator()) on the host: the only place besides tests
     where bench.py executes oracle/."""
@@ -323,7 +334,8 @@ def main():
                 "kernel_ms": dom_ms, "kernel_share_of_step": dom[1]["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
                 "step_kernels_ms": {k: v["ms"] / min(args.steps, 5) for k, v in prof.items()},
                 "launches_per_step": per_step_launches,
-                "whole_step_frac": (bits / 8 / (total_ms * 1e-3) / 1e9) / peak}
+                "whole_step_frac": (bits / 8 / (ms / args.steps * 1e-3) / 1e9) / peak}
+        roof["traffic"] = ncu_traffic(dom[0])
 
     # ---- e2e: host buffers in, result out, every step (open from pinned host memory + scan + close) ----
     e2e = None

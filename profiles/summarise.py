@@ -55,6 +55,17 @@ P("|---|---|---|---|")
 for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     P("| %s | %d | %.3f | %.1f %% |" % (k, n, ms, 100 * ms / tot))
 P("")
+step = collections.OrderedDict((k, v) for k, v in agg.items() if k.startswith(("k_scan_", "k_long_resid", "k_long_extras", "k_long_merge", "k_long_fold", "k_reduce_slots")))
+st = sum(v[1] for v in step.values())
+ev = r["step_kernels_ms"]; evt = sum(ev.values())
+P("Shares inside a step (scan kernels only) against bench.py's CUDA-event shares of the same kernels:")
+P("")
+P("| kernel | ncu share of step | CUDA-event share of step |")
+P("|---|---|---|")
+for k, (n, ms_) in sorted(step.items(), key=lambda kv: -kv[1][1]):
+    base = k.split("<")[0].replace("_lean", "")
+    P("| %s | %.1f %% | %s |" % (k, 100 * ms_ / st, ("%.1f %%" % (100 * ev[base] / evt)) if base in ev else "-"))
+P("")
 # full report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
@@ -85,4 +96,17 @@ for key, label in want:
     if key in hh:
         i = hh.index(key)
         P("| %s [%s] | " % (label, units[i]) + " | ".join(x[i] for _, x in cols) + " |")
+# traffic per launch of the scan kernels (read by bench.py's roofline object)
+if "dram__bytes_read.sum" in hh:
+    ir, iw = hh.index("dram__bytes_read.sum"), hh.index("dram__bytes_write.sum")
+    def to_bytes(v, u):
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+    best = {}
+    for name, x in cols:
+        key = "k_scan_extras" if "k_scan_extras" in name else ("k_scan_merge" if "k_scan_merge" in name else name.split("<")[0])
+        tr = to_bytes(x[ir], units[ir]) + to_bytes(x[iw], units[iw])
+        best[key] = max(best.get(key, 0), tr)  # the largest launch of a kernel (merge level 1)
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r01_traffic.json"), "w") as f:
+        json.dump({"source": os.path.basename(rep) + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)", "kernels": best}, f, indent=1)
 print("\n".join(out))
