@@ -64,7 +64,7 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             c.begin(g, blocks_pos[x], bcs[x], outdeg[px], slots, 1, true);
             c.stage(g);
             if (parent_flag[x]) acc ^= copied_merge(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
-            else acc ^= copied_fold(g, c, x, rows + rowoff[px]);
+            else acc ^= copied_fold<8>(g, c, x, rows + rowoff[px]);
         }
     out[0] = arcs; out[1] = acc;
     return 0;

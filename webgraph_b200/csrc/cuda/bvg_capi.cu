@@ -626,6 +626,22 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     return (int)(x < lo ? lo : (x > hi ? hi : x));
 }
 
+// Records with more than long_d successors are split across threads (bvg_long.cuh).  Shorter records are one lane's
+// serial work, and a kernel cannot end before its longest record has been walked: ~0.3 us per successor, once per launch
+// (the extras step and every merge level).  That floor has to stay small against the scan itself (~5.5 ps per arc), so the
+// threshold follows the arcs this graph object holds: 512 for the 1 B-arc benchmark graph, 128 for one eighth of it
+// (measured on 125 M arcs: 2.64 ms per scan with 1024, 1.52 ms with 128; on 1 B arcs 512 and 1024 are level at 6.5 ms,
+// 256 costs 0.7 ms more).  BVG_LONG_D / BVG_LONG_SEG / BVG_LONG_CHUNK override.
+static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to) {
+    const double arcs = (double)g->m_total * (double)(to - from) / (double)std::max<int32_t>(g->n_total, 1);
+    int32_t d = 1024;
+    while (d > 128 && (double)d > arcs * 7e-7) d >>= 1;
+    const int32_t part = d <= 256 ? 64 : 128;
+    g->long_d = env_int("BVG_LONG_D", d, 2, 1 << 30);
+    g->long_seg = env_int("BVG_LONG_SEG", part, 1, 1 << 20);
+    g->long_chunk = env_int("BVG_LONG_CHUNK", part, 1, 1 << 20);
+}
+
 static int open_common(bvg_graph* g, const Properties& p, int offset_type) {
     if (offset_type < -1 || offset_type > 2) return BVG_EINVAL;  // BVGraph.java:1545
     keep_pool_warm(g->device);
@@ -671,6 +687,7 @@ int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint
     tr.mark("device: decode .offsets");
     if (rc) { dev_free(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
+    choose_long_threshold(g, from, to);
     g->node_lo = shard_halo(g, from); g->node_hi = to;
     uint64_t o3[3];  // offsets of node_lo, to, nodes
     if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -756,6 +773,7 @@ int bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, b
     rc = device_decode_offsets(g->stream, ostream.data(), ostream.size(), oc, p.nodes, &d_full);
     if (rc) { dev_free(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
+    choose_long_threshold(g, from, to);
     g->node_lo = shard_halo(g, from); g->node_hi = to;
     uint64_t o3[3];
     if (cudaMemcpy(&o3[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -919,7 +937,7 @@ static int run_ordered_decode(const bvg_graph* g, int32_t lo, int32_t to, int32_
     for (int32_t level = 1; level <= g->max_depth; level++) {
         const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
         if (c > 0) {
-            if (use_lean) LAUNCH_P(g, "k_merge_lean", k_scan_merge_lean, grid_for(c, 128), 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, no_fold, 1);
+            if (use_lean) LAUNCH_P(g, "k_merge_lean", (k_scan_merge_lean<8, 4>), grid_for(c, 128), 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, no_fold, 1);
             else if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
             else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
         }
@@ -1052,7 +1070,9 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
         if (c > 0) {
             const unsigned gm = (unsigned)std::min<int64_t>(grid_m, (c + 127) / 128);
             static const bool lean_m = !(getenv("BVG_MERGE_LEAN") && atoi(getenv("BVG_MERGE_LEAN")) == 0);
-            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", k_scan_merge_lean, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            // 8 resident blocks per SM (64 registers) and 4 parent loads in flight per lane: measured against 8/8, 6/8 and
+            // 5/16 (blocks / batch): 1.92, 2.12, 2.19, 2.52 ms for the three levels -- occupancy beats deeper batching here
+            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
             else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }

@@ -609,7 +609,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(G
 }
 
 // Merge step with the staged copy runs of bvg_scan.cuh (default codings).
-__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
+template <int MINB, int BATCH>
+__global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int store_all) {
     __shared__ int32_t runs[2 * COPY_RUNS * SCAN_BLOCK];
     unsigned long long acc = 0;
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge_l
         __syncwarp();
         const int32_t* parent = active ? rm.at(r.px, r.prow) : nullptr;
         unsigned long long f = 0;
-        if (active && !store) f = copied_fold(g, c, r.x, parent);
+        if (active && !store) f = copied_fold<BATCH>(g, c, r.x, parent);
         __syncwarp();
         if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
         __syncwarp();

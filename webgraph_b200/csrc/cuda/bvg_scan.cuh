@@ -553,27 +553,24 @@ struct CopyRuns {
 };
 
 // nobody copies from x: its copied successors are only consumed
+template <int BATCH>
 __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CopyRuns& c, int32_t x, const int32_t* __restrict__ parent) {
     Fold32 f;
     f.begin(x);
-    // four positions first, then their four loads together: a lane opens a new sector of its parent's row every eighth
-    // element, and with one load per trip the warp would wait for that miss on every trip
+    // BATCH positions first, then their loads together: a lane opens a new sector of its parent's row every eighth element,
+    // the 32 lanes read 32 unrelated rows, and with one load per trip the warp waits a memory round trip on every trip
 #pragma unroll 1
     for (;;) {
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        const bool h0 = c.next(g, a0);
-        const bool h1 = h0 && c.next(g, a1);
-        const bool h2 = h1 && c.next(g, a2);
-        const bool h3 = h2 && c.next(g, a3);
-        const uint32_t v0 = h0 ? (uint32_t)parent[a0] : 0u;
-        const uint32_t v1 = h1 ? (uint32_t)parent[a1] : 0u;
-        const uint32_t v2 = h2 ? (uint32_t)parent[a2] : 0u;
-        const uint32_t v3 = h3 ? (uint32_t)parent[a3] : 0u;
-        if (h0) { f.add(v0); f.n++; }
-        if (h1) { f.add(v1); f.n++; }
-        if (h2) { f.add(v2); f.n++; }
-        if (h3) { f.add(v3); f.n++; }
-        if (!h3) break;
+        uint32_t at[BATCH], val[BATCH];
+        bool has[BATCH];
+        bool more = true;
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) { at[u] = 0; has[u] = more && c.next(g, at[u]); more = has[u]; }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) val[u] = has[u] ? (uint32_t)parent[at[u]] : 0u;
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) if (has[u]) { f.add(val[u]); f.n++; }
+        if (!more) break;
     }
     return f.finish(x);
 }
