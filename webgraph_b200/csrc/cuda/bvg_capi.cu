@@ -170,6 +170,7 @@ struct bvg_graph {
     int32_t* d_copied = nullptr;       // successors each node copies from its parent (k_order_keys)
     bool copied_ready = false;
     int32_t* d_long_nodes = nullptr;   // ids of the long records
+    std::vector<int32_t> h_long_nodes; // the same on the host, ascending (does a small range hold a long record?)
     // long records split across threads (bvg_long.cuh)
     int32_t nlong = 0;
     LongMeta* d_long_meta = nullptr;
@@ -198,6 +199,8 @@ struct bvg_graph {
     int64_t* d_halo_off = nullptr;
     int32_t halo_count = 0;
     int64_t halo_off_cap = 0, halo_lists_cap = 0;
+    int32_t halo_import_count = -1;   // shape of the last import (bvg_halo_import)
+    int64_t halo_import_total = -1;
     // per-kernel timing (bench.py's roofline object): spans recorded while prof_on
     mutable bool prof_on = false;
     mutable std::vector<ProfSpan*> prof_spans;
@@ -229,6 +232,9 @@ struct bvg_graph {
     mutable std::mutex mu;
     mutable int32_t err_node = -1;
     mutable int64_t err_bitpos = -1;
+    // host-side memo of immutable index values (guarded by mu): row offsets fetched so far, first chain root before `from`
+    mutable std::map<int32_t, int64_t> rowoff_seen;
+    mutable std::map<std::pair<int32_t, int32_t>, int32_t> halo_start_seen;
 
     GraphDev dev() const {
         GraphDev g;
@@ -408,6 +414,8 @@ static int build_long_index(bvg_graph* g) {
             (m.rc > 0 ? (int64_t)((m.rec_end - m.resid_pos + (uint64_t)LSPEC_BITS - 1) / (uint64_t)LSPEC_BITS) : 0);
     }
     g->nlong = (int32_t)nl;  // item_map() below needs it; reset on failure by the caller's destroy
+    g->h_long_nodes.resize((size_t)nl);
+    for (int64_t l = 0; l < nl; l++) g->h_long_nodes[(size_t)l] = meta[(size_t)l].x;
     CK(dev_alloc((void**)&g->d_long_cum, cum.size() * 8, g->stream));
     CK(cudaMemcpyAsync(g->d_long_cum, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), cudaMemcpyHostToDevice, s));
@@ -845,10 +853,20 @@ static int range_check(const bvg_graph* g, int32_t from, int32_t to) {
     return BVG_OK;
 }
 
+// Row offsets of two nodes on the host.  The graph is immutable, so what has been fetched once is remembered: the calls
+// of a steady-state step (range decode of the boundary lists, scan of the shard) then cost no device round trip.
 static int fetch_rowoff(const bvg_graph* g, int32_t a, int32_t b, int64_t* va, int64_t* vb) {
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        auto ia = g->rowoff_seen.find(a), ib = g->rowoff_seen.find(b);
+        if (ia != g->rowoff_seen.end() && ib != g->rowoff_seen.end()) { *va = ia->second; *vb = ib->second; return BVG_OK; }
+    }
     CK(cudaMemcpyAsync(va, g->d_rowoff + (a - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
     CK(cudaMemcpyAsync(vb, g->d_rowoff + (b - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->rowoff_seen.size() > 4096) g->rowoff_seen.clear();
+    g->rowoff_seen[a] = *va; g->rowoff_seen[b] = *vb;
     return BVG_OK;
 }
 
@@ -885,13 +903,24 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
             rm.halo_base = hb;
         } else {  // re-decode the halo, as BVGraphNodeIterator's ctor re-reads the window (BVGraph.java:1173-1183)
             const int64_t reach = std::min<int64_t>((int64_t)to - from, (int64_t)g->window * g->max_depth);
-            Tmp<int32_t> hs(s);
-            CK(hs.alloc(1));
-            CK(cudaMemcpyAsync(hs.p, &from, 4, cudaMemcpyHostToDevice, s));
-            LAUNCH(k_halo_start, grid_for(reach, 128), 128, 0, s, gd, from, (int32_t)reach, hs.p);
             int32_t h = from;
-            CK(cudaMemcpyAsync(&h, hs.p, 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            bool known = false;
+            {
+                std::lock_guard<std::mutex> lk(g->mu);
+                auto it = g->halo_start_seen.find(std::make_pair(from, (int32_t)reach));
+                if (it != g->halo_start_seen.end()) { h = it->second; known = true; }
+            }
+            if (!known) {
+                Tmp<int32_t> hs(s);
+                CK(hs.alloc(1));
+                CK(cudaMemcpyAsync(hs.p, &from, 4, cudaMemcpyHostToDevice, s));
+                LAUNCH(k_halo_start, grid_for(reach, 128), 128, 0, s, gd, from, (int32_t)reach, hs.p);
+                CK(cudaMemcpyAsync(&h, hs.p, 4, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                std::lock_guard<std::mutex> lk(g->mu);
+                if (g->halo_start_seen.size() > 4096) g->halo_start_seen.clear();
+                g->halo_start_seen[std::make_pair(from, (int32_t)reach)] = h;
+            }
             if (h < from) {
                 int64_t ra, rb;
                 int rc = fetch_rowoff(g, h, from, &ra, &rb);
@@ -962,11 +991,33 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
     const bool ordered = g->d_order_e && g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
     if (ordered) return run_ordered_decode(g, lo, to, from, rm);
-    if (g->def_codec) LAUNCH_P(g, "k_extras", k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
-    else LAUNCH_P(g, "k_extras", k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm);
+    // Small ranges (cursor batches, boundary lists): natural node order, one thread per record -- except the long records,
+    // which are split across threads exactly as in a whole-graph decode (their items are filtered by [lo, to)).
+    const bool split = g->nlong > 0 &&
+        std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), lo) != std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), to);
+    const int32_t skip_above = split ? g->long_d : INT32_MAX;
+    if (g->def_codec) LAUNCH_P(g, "k_extras", k_extras<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm, skip_above);
+    else LAUNCH_P(g, "k_extras", k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm, skip_above);
+    Tmp<int32_t> long_tmp(s);
+    LongDst ld{ nullptr };
+    const LongIndex li = g->long_index();
+    const LongFold lf{ nullptr, 0 };
+    if (split) {
+        CK(long_tmp.alloc((size_t)g->long_tmp_entries));
+        ld.tmp = long_tmp.p;
+        if (g->n_items_resid) {
+            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+        }
+        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
+    }
     for (int32_t level = 1; level <= g->max_depth; level++) {
-        if (g->def_codec) LAUNCH_P(g, "k_merge", k_merge<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
-        else LAUNCH_P(g, "k_merge", k_merge<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm);
+        if (g->def_codec) LAUNCH_P(g, "k_merge", k_merge<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm, skip_above);
+        else LAUNCH_P(g, "k_merge", k_merge<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm, skip_above);
+        if (split) {
+            const int64_t mc = g->n_items_merge[(size_t)level];
+            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
+        }
     }
     CK(cudaGetLastError());
     return BVG_OK;
@@ -1386,8 +1437,17 @@ int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32
     if (count == 0) return BVG_OK;
     int64_t total = 0;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (on_device && g->halo_import_count == count && g->halo_import_total >= 0 && count + 1 <= g->halo_off_cap) {
+        // same shape as the previous import (a shard re-imports its neighbour's boundary every step): copy by a kernel that
+        // reads the arc count on the device and checks it against the capacity, no round trip to the host
+        LAUNCH(k_halo_copy, 64, 256, 0, s, off, lists, count, g->d_halo_off, g->d_halo_lists, g->halo_lists_cap, g->d_err);
+        CK(cudaGetLastError());
+        g->halo_count = count;
+        return BVG_OK;
+    }
     if (on_device) { CK(cudaMemcpyAsync(&total, off + count, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
     else total = off[count];
+    g->halo_import_count = count; g->halo_import_total = total;
     if (count + 1 > g->halo_off_cap) {
         dev_free(g->d_halo_off, g->stream); g->d_halo_off = nullptr; g->halo_off_cap = 0;
         CK(dev_alloc((void**)&g->d_halo_off, ((size_t)count + 1) * 8, g->stream));

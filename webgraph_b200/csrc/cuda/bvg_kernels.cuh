@@ -354,22 +354,24 @@ struct RowMap {
 
 // Level 0 for every node of [lo, hi): extras into the row tail; nodes without a reference are complete.
 template <bool DEF>
-__global__ void k_extras(GraphDev g, int32_t lo, int32_t hi, RowMap rm) {
+__global__ void k_extras(GraphDev g, int32_t lo, int32_t hi, RowMap rm, int32_t skip_above) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)hi - lo) return;
     const int32_t x = lo + (int32_t)i;
     if (g.outdeg[x - g.node_lo] == 0 || g.depth[x - g.node_lo] < 0) return;  // depth < 0: chain leaves the shard
+    if (g.outdeg[x - g.node_lo] > skip_above) return;                          // split across threads by the k_long_* kernels
     if (!rm.wanted(g, x)) return;
     decode_extras<DEF>(g, x, rm.row(g, x));
 }
 
 // Level l >= 1: nodes whose chain depth is l merge their parent's (finished) row into their own.
 template <bool DEF>
-__global__ void k_merge(GraphDev g, int32_t lo, int32_t hi, int32_t level, RowMap rm) {
+__global__ void k_merge(GraphDev g, int32_t lo, int32_t hi, int32_t level, RowMap rm, int32_t skip_above) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)hi - lo) return;
     const int32_t x = lo + (int32_t)i;
     if (g.depth[x - g.node_lo] != level || !rm.wanted(g, x)) return;
+    if (g.outdeg[x - g.node_lo] > skip_above) return;
     merge_copied<DEF>(g, x, rm.row(g, x), rm.row(g, x - g.ref[x - g.node_lo]));
 }
 
@@ -414,6 +416,16 @@ __global__ void k_halo_start(GraphDev g, int32_t from, int32_t count, int32_t* _
     }
     const int32_t root = (int32_t)(y + g.node_lo);
     if (root < from) atomicMin(result, root);
+}
+
+// Imported boundary lists (bvg_halo_import): offsets and lists copied on the device; the arc count is read here, not on the host.
+__global__ void k_halo_copy(const int64_t* __restrict__ off, const int32_t* __restrict__ lists, int32_t count,
+                            int64_t* __restrict__ dst_off, int32_t* __restrict__ dst_lists, int64_t cap, ErrWord* err) {
+    const int64_t total = off[count];
+    if (total < 0 || total > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) report(err, E_NOMEM, -1, 0); return; }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i <= count; i += stride) dst_off[i] = off[i];
+    for (int64_t i = t0; i < total; i += stride) dst_lists[i] = lists[i];
 }
 
 __global__ void k_rel_offsets(const int64_t* __restrict__ rowoff, int64_t count, int64_t* __restrict__ out) {
