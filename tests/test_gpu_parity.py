@@ -289,6 +289,40 @@ def test_shards_halo_redecode_and_import(synth100k, shards):
     assert tot_arcs == st["arcs"] and tot_cs == st["xor_checksum"]
 
 
+def test_halo_import_from_device_buffers_twice(synth100k):
+    """What bench.py does every step at N > 1: boundary lists exported into device buffers, imported from device buffers.
+    The first import sizes the halo buffers (one round trip), every later one of the same shape is a device-side copy."""
+    import ctypes as C
+    import torch
+    base, st, off, succ = synth100k
+    n = len(off) - 1
+    cut = n // 2 + 5
+    a = BVGraph.loadShard(base, 0, cut)
+    b = BVGraph.loadShard(base, cut, n)
+    L = bvgraph.lib()
+    cnt = C.c_int32()
+    bvgraph._check(L.bvg_boundary_count(a.handle, C.byref(cnt)))
+    cap = int(off[cut] - off[cut - cnt.value])
+    d_off = torch.zeros(cnt.value + 1, dtype=torch.int64, device="cuda")
+    d_lists = torch.zeros(max(cap, 1), dtype=torch.int32, device="cuda")
+    want = (int(st["arcs"]) - int(off[cut]), None)
+    results = []
+    for rep in range(3):
+        d_lists.zero_()
+        bvgraph._check(L.bvg_boundary_export(a.handle, d_off.data_ptr(), d_lists.data_ptr(), cap, 1))
+        bvgraph._check(L.bvg_halo_import(b.handle, cnt.value, d_off.data_ptr(), d_lists.data_ptr(), 1))
+        o, s = b.decodeRange(cut, n)
+        assert np.array_equal(o, off[cut:n + 1] - off[cut]) and np.array_equal(s, succ[off[cut]:off[n]])
+        results.append(b.scanRange(cut, n))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_lists.cpu().numpy()[:cap], succ[off[cut - cnt.value]:off[cut]])
+    assert results[0][0] == want[0] and results[0] == results[1] == results[2]
+    arcs_a, cs_a = a.scanRange(0, cut)
+    assert arcs_a + results[0][0] == st["arcs"] and (cs_a ^ results[0][1]) == st["xor_checksum"]
+    a.close()
+    b.close()
+
+
 # ---- corrupt input: error code + node, never a fault (BVGraph.java:705, 1129-1131) ----
 
 def test_corrupt_stream_reports_error(tmp_path):

@@ -21,14 +21,6 @@
 
 namespace bvg {
 
-// L1 prefetch of the sector a few refills ahead: a lane walks its record word by word, and without it every new
-// 32-byte sector is a serial L1 miss for the whole warp.
-#ifdef BVG_HOST_EMULATION
-#define BVG_PREFETCH_L1(p)
-#else
-#define BVG_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
-#endif
-constexpr int PREFETCH_WORDS_AHEAD = 16;
 // Zero words kept after the last stream word: readers look at most 5 words past a record.
 constexpr int STREAM_PAD_WORDS = 8;
 
