@@ -412,29 +412,16 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
         im.find(i, l, part);
         const LongMeta m = li.meta[l];
         if (m.x >= lo && m.x < hi && rm.wanted(g, m.x)) {
-            if (!lf.only_consumed(m)) long_resid_segment<DEF>(g, m, li, part, dst.resid(m, rm.row(g, m.x)));
-            else if (m.x >= lf.from) {
-                const int32_t first = part * li.seg;
-                const int32_t cnt = min(li.seg, m.rc - first);
-                Fold32 f;
-                f.begin(m.x);
-                if (DEF) {
-                    const int k = g.c.zetak;
-                    Win b;
-                    b.seek(g, li.seg_pos[m.seg_off + part]);
-                    uint32_t v = (uint32_t)li.seg_val[m.seg_off + part];
-#pragma unroll 1
-                    for (int32_t t = 0; t < cnt; t++) {
-                        if (first + t == 0) v = (uint32_t)(int32_t)((int64_t)m.x + nat2int(zeta_any<0>(b, g, k) - 1ull));
-                        else {
-                            uint32_t mm, len;
-                            if (zeta_fast<0>(b.top(), k, mm, len)) b.skip(len);
-                            else mm = (uint32_t)zeta_any<0>(b, g, k);
-                            v += mm;
-                        }
-                        f.add(v);
-                    }
-                } else {
+            // one loop for both kinds of record, so that the lanes of a warp (segments of four to eight different records)
+            // stay together: stored segments write their values, consumed ones fold them
+            const bool consume = lf.only_consumed(m);
+            if (!DEF) {
+                if (!consume) long_resid_segment<DEF>(g, m, li, part, dst.resid(m, rm.row(g, m.x)));
+                else if (m.x >= lf.from) {
+                    const int32_t first = part * li.seg;
+                    const int32_t cnt = min(li.seg, m.rc - first);
+                    Fold32 f;
+                    f.begin(m.x);
                     BitBuf b;
                     b.w = g.words; b.maxw = g.nwords - 3;
                     b.seek(li.seg_pos[m.seg_off + part]);
@@ -444,10 +431,37 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
                         else v += (int64_t)Rd<DEF>::resid(b, g.c) + 1;
                         f.add((uint32_t)v);
                     }
+                    f.n = (uint32_t)cnt;
+                    acc = f.finish(m.x);
+                    arcs = cnt;
                 }
-                f.n = (uint32_t)cnt;
-                acc = f.finish(m.x);
-                arcs = cnt;
+            } else if (!consume || m.x >= lf.from) {
+                const int32_t first = part * li.seg;
+                const int32_t cnt = min(li.seg, m.rc - first);
+                Fold32 f;
+                f.begin(m.x);
+                const int k = g.c.zetak;
+                Win b;
+                b.seek(g, li.seg_pos[m.seg_off + part]);
+                uint32_t v = (uint32_t)li.seg_val[m.seg_off + part];
+                int32_t* out = consume ? nullptr : dst.resid(m, rm.row(g, m.x)) + first;
+#pragma unroll 1
+                for (int32_t t = 0; t < cnt; t++) {
+                    if (first + t == 0) v = (uint32_t)(int32_t)((int64_t)m.x + nat2int(zeta_any<0>(b, g, k) - 1ull));
+                    else {
+                        uint32_t mm, len;
+                        if (zeta_fast<0>(b.top(), k, mm, len)) b.skip(len);
+                        else mm = (uint32_t)zeta_any<0>(b, g, k);
+                        v += mm;
+                    }
+                    f.add(v);
+                    if (!consume) out[t] = (int32_t)v;
+                }
+                if (consume) {
+                    f.n = (uint32_t)cnt;
+                    acc = f.finish(m.x);
+                    arcs = cnt;
+                }
             }
         }
     }
