@@ -289,6 +289,58 @@ def test_shards_halo_redecode_and_import(synth100k, shards):
     assert tot_arcs == st["arcs"] and tot_cs == st["xor_checksum"]
 
 
+def test_size_independent_properties_on_a_larger_graph(tmp_path):
+    """No oracle at this size in the test budget: 1 M nodes / ~33 M arcs (long records, every chain depth) checked through
+    properties that do not depend on size -- the scan of the whole equals the generator's own (arcs, checksum), equals the
+    XOR / sum over uneven sub-range scans, equals the checksum recomputed on the device from the materialised CSR; rows are
+    strictly increasing; random-access rows equal the CSR rows.  bench.py checks the first property at the full 1 B arcs."""
+    import ctypes as C
+    import torch
+    base = str(tmp_path / "pl1m")
+    st = tools.generate_store(base, 1_000_000, 33_000_000, seed=0xBEEF, threads=os.cpu_count() or 4)
+    g = BVGraph.load(base)
+    n = g.numNodes()
+    assert g.scanRange(0, n) == (st["arcs"], st["xor_checksum"])
+    cuts = [0, 1, 7, 1000, 333_333, 333_340, 700_001, n - 3, n]
+    parts = [g.scanRange(a, b) for a, b in zip(cuts, cuts[1:])]
+    x = 0
+    for _, c in parts:
+        x ^= c
+    assert sum(a for a, _ in parts) == st["arcs"] and x == st["xor_checksum"]
+    L = bvgraph.lib()
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    d_succ = torch.empty(int(st["arcs"]), dtype=torch.int32, device="cuda")
+    bvgraph._check(L.bvg_decode_range(g.handle, 0, n, d_off.data_ptr(), d_succ.data_ptr(), int(st["arcs"]), 1))
+    torch.cuda.synchronize()
+    assert int(d_off[-1]) == st["arcs"]
+    deg = d_off[1:] - d_off[:-1]
+    src = torch.repeat_interleave(torch.arange(n, device="cuda", dtype=torch.int64), deg)
+    # x * MIX + y mod 2^64 in int64 two's complement (torch has no uint64 arithmetic): wrap-around is what we want
+    MIX = 0x9E3779B97F4A7C15 - (1 << 64)
+    terms = src * MIX + (d_succ.to(torch.int64) & 0xFFFFFFFF)
+    acc = terms
+    while acc.numel() > 1:  # XOR-reduce by halving
+        h = acc.numel() // 2
+        rest = acc[2 * h:]
+        acc = torch.bitwise_xor(acc[:h], acc[h:2 * h])
+        if rest.numel():
+            acc = torch.cat([acc, rest])
+    assert (int(acc[0]) & 0xFFFFFFFFFFFFFFFF) == st["xor_checksum"]
+    assert int(d_succ.to(torch.int64).sum()) == st["sum_successors"]
+    # strictly increasing inside every row: the only non-increasing steps are at row starts
+    drops = torch.nonzero(d_succ[1:] <= d_succ[:-1]).flatten() + 1
+    starts = d_off[1:-1][deg[1:] > 0]
+    assert torch.isin(drops, starts).all()
+    # random access == sequential
+    xs = np.random.default_rng(5).integers(0, n, 20000).astype(np.int32)
+    boff, bsucc = g.successorsBatch(xs)
+    h_off = d_off.cpu().numpy()
+    h_succ = d_succ.cpu().numpy()
+    ref = np.concatenate([h_succ[h_off[v]:h_off[v + 1]] for v in xs])
+    assert np.array_equal(bsucc, ref) and np.array_equal(np.diff(boff), h_off[xs + 1] - h_off[xs])
+    g.close()
+
+
 def test_halo_import_from_device_buffers_twice(synth100k):
     """What bench.py does every step at N > 1: boundary lists exported into device buffers, imported from device buffers.
     The first import sizes the halo buffers (one round trip), every later one of the same shape is a device-side copy."""
