@@ -180,7 +180,6 @@ struct bvg_graph {
     // per-scan work items of the long records: running item counts per record (ItemMap, bvg_long.cuh), one array of
     // nlong + 1 entries per item family: [residual segments | row chunks | extras chunks | merge chunks of level 1, 2, ...]
     int64_t* d_long_cum = nullptr;
-    int64_t n_items_fold = 0;
     int64_t n_items_resid = 0, n_items_extras = 0;
     std::vector<int64_t> n_items_merge;  // [level]
     ItemMap item_map(int family) const { return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong }; }
@@ -405,7 +404,7 @@ static int build_long_index(bvg_graph* g) {
         const int64_t nseg = ((int64_t)m.rc + LSEG - 1) / LSEG;
         seg += nseg;
         m.tmp_off = tmp; tmp += 2 * (int64_t)m.d;
-        int64_t add[3] = { nseg, ((int64_t)m.d + FOLD_CHUNK - 1) / FOLD_CHUNK, m.ic > 0 ? ((int64_t)m.ilen + m.rc + LCHUNK - 1) / LCHUNK : 0 };
+        int64_t add[3] = { nseg, 0 /* unused family */, m.ic > 0 ? ((int64_t)m.ilen + m.rc + LCHUNK - 1) / LCHUNK : 0 };
         for (int f = 0; f < 3; f++) cum[(size_t)f * stride + (size_t)l + 1] = cum[(size_t)f * stride + (size_t)l] + add[f];
         for (int32_t lv = 1; lv <= levels; lv++)
             cum[(size_t)(2 + lv) * stride + (size_t)l + 1] = cum[(size_t)(2 + lv) * stride + (size_t)l] +
@@ -469,7 +468,6 @@ static int build_long_index(bvg_graph* g) {
         if (e) return e;
     }
     g->n_items_resid = cum[0 * stride + (size_t)nl];
-    g->n_items_fold = cum[1 * stride + (size_t)nl];
     g->n_items_extras = cum[2 * stride + (size_t)nl];
     g->n_items_merge.assign((size_t)levels + 1, 0);
     for (int32_t lv = 1; lv <= levels; lv++) g->n_items_merge[(size_t)lv] = cum[(size_t)(2 + lv) * stride + (size_t)nl];
@@ -1136,8 +1134,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
         }
     }
-    if (g->nlong && g->n_items_fold)
-        LAUNCH_P(g, "k_long_fold_rows", k_long_fold_rows<RowMap>, grid_for(g->n_items_fold * 32, 256), 256, 0, sa, gd, li, g->item_map(1), g->n_items_fold, lo, to, rm, lf);
+    // (stored long records are folded where their final rows are produced: k_long_resid / k_long_extras / k_long_merge)
     if (sa != s) { CK(cudaEventRecord(g->ev_join, sa)); CK(cudaStreamWaitEvent(s, g->ev_join, 0)); }
     CK(cudaGetLastError());
     return BVG_OK;

@@ -318,7 +318,7 @@ __device__ __forceinline__ int32_t merge_path(const A& a, const int32_t* __restr
 // Outputs [q0, q0 + cnt) of merge(A, B) into out, A being a virtual block-structured sequence walked by (slot, offset).
 template <class A, class ValueOf>
 __device__ void merge_chunk(const A& a, ValueOf value_of, const int32_t* __restrict__ bv, int32_t blen,
-                            int32_t q0, int32_t cnt, int32_t* __restrict__ out) {
+                            int32_t q0, int32_t cnt, int32_t* __restrict__ out, Fold32* fold = nullptr) {
     int32_t i = merge_path(a, bv, blen, q0), j = q0 - i;
     int32_t t = 0, t_end = 0;  // current slot of A and the index where it ends
     if (i < a.len) { t = upper_slot(a.cum, a.n, i); t_end = a.cum[t + 1]; }
@@ -329,8 +329,11 @@ __device__ void merge_chunk(const A& a, ValueOf value_of, const int32_t* __restr
             while (i >= t_end) { t++; t_end = a.cum[t + 1]; }  // skips empty slots
             av = value_of(t, i - a.cum[t]);
         }
-        if (has_a && (!has_b || av < bv[j])) { out[q0 + k] = av; i++; }
-        else { out[q0 + k] = bv[j]; j++; }
+        int32_t o;
+        if (has_a && (!has_b || av < bv[j])) { o = av; i++; }
+        else { o = bv[j]; j++; }
+        out[q0 + k] = o;
+        if (fold) fold->add((uint32_t)o);  // a consume-only scan folds a stored row where its final values are produced
     }
 }
 
@@ -394,7 +397,7 @@ struct LongDst {
 // Consume-only scans (`fold` != nullptr) materialise a long record only when somebody copies from it; the successors of
 // every other long record are folded where they are produced: residual segments here, interval elements in
 // k_long_extras, copied elements in k_long_merge (the three parts of a list are disjoint, so the order they are
-// consumed in is immaterial to the checksum).
+// consumed in is immaterial to the checksum).  The materialised ones are folded where their final rows are produced.
 struct LongFold {
     unsigned long long* result;   // FOLD_SLOTS slot pairs; nullptr = materialise everything (range decode)
     int32_t from;                 // nodes below `from` are halo: they matter only as parents
@@ -457,7 +460,8 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
                     f.add(v);
                     if (!consume) out[t] = (int32_t)v;
                 }
-                if (consume) {
+                // stored records with neither intervals nor a copied part get their final row here: fold it now
+                if (consume || (lf.result != nullptr && m.ic == 0 && m.copied == 0 && m.x >= lf.from)) {
                     f.n = (uint32_t)cnt;
                     acc = f.finish(m.x);
                     arcs = cnt;
@@ -483,8 +487,13 @@ __global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t nite
             if (!lf.only_consumed(m)) {
                 const int32_t total = m.ilen + m.rc;
                 const int32_t* left = a.left;
+                const int32_t cnt = min(li.chunk, total - q0);
+                const bool final_row = lf.result != nullptr && m.copied == 0 && m.x >= lf.from;  // no copied part follows
+                Fold32 f;
+                f.begin(m.x);
                 merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
-                            min(li.chunk, total - q0), dst.extras(m, rm.row(g, m.x)));
+                            cnt, dst.extras(m, rm.row(g, m.x)), final_row ? &f : nullptr);
+                if (final_row) { f.n = (uint32_t)cnt; acc = f.finish(m.x); arcs = cnt; }
             } else if (m.x >= lf.from && q0 < m.ilen) {  // interval elements [q0, q0 + chunk) of the concatenated intervals
                 const int32_t cnt = min(li.chunk, m.ilen - q0);
                 Fold32 f;
@@ -518,8 +527,13 @@ __global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
             const int32_t* ppos = a.ppos;
             const int32_t q0 = part * li.chunk;
             if (!lf.only_consumed(m)) {
+                const int32_t cnt = min(li.chunk, m.d - q0);
+                const bool final_row = lf.result != nullptr && m.x >= lf.from;
+                Fold32 f;
+                f.begin(m.x);
                 merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
-                            m.d - m.copied, q0, min(li.chunk, m.d - q0), rm.row(g, m.x));
+                            m.d - m.copied, q0, cnt, rm.row(g, m.x), final_row ? &f : nullptr);
+                if (final_row) { f.n = (uint32_t)cnt; acc = f.finish(m.x); arcs = cnt; }
             } else if (m.x >= lf.from && q0 < m.copied) {  // copied elements [q0, q0 + chunk) seen through the copy blocks
                 const int32_t cnt = min(li.chunk, m.copied - q0);
                 Fold32 f;
@@ -536,30 +550,6 @@ __global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
         }
     }
     if (lf.result) warp_fold(acc, arcs, lf.result);
-}
-
-// Rows of the long records a consume-only scan materialised (the ones somebody copies from), folded by one warp per
-// FOLD_CHUNK entries.
-constexpr int32_t FOLD_CHUNK = 1024;
-template <class RM>
-__global__ void k_long_fold_rows(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongFold lf) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    unsigned long long acc = 0;
-    long long arcs = 0;
-    if (i < nitems) {
-        int32_t l, part;
-        im.find(i, l, part);
-        const LongMeta m = li.meta[l];
-        if (m.x >= lf.from && m.x >= lo && m.x < hi && !lf.only_consumed(m)) {
-            const int32_t a = part * FOLD_CHUNK, e = min(m.d, a + FOLD_CHUNK);
-            const int32_t* row = rm.row(g, m.x);
-            const unsigned long long base = (unsigned long long)(uint32_t)m.x * BVG_MIX;
-            for (int32_t p = a + lane; p < e; p += 32) acc ^= base + (unsigned long long)(uint32_t)row[p];
-            if (lane == 0) arcs = e - a;
-        }
-    }
-    warp_fold(acc, arcs, lf.result);
 }
 
 // Speculative sub-ranges of the residual sections (see above), listed on the device: item j of record l covers
