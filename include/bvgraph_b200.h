@@ -109,6 +109,11 @@ int  bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor
 int  bvg_cursor_next(bvg_cursor* c, int32_t* node, int32_t* d, const int32_t** succ);
 int  bvg_cursor_copy(const bvg_cursor* c, int32_t upper, bvg_cursor** out);
 void bvg_cursor_close(bvg_cursor* c);
+/* The inner loop of a binding, in C: up to max_nodes calls of bvg_cursor_next (all that is left when max_nodes < 0),
+ * every successor consumed into arcs and the checksum of bvg_scan_range -- what the reference's SpeedTest does with
+ * nodeIterator() (test/SpeedTest.java:157-185).  Measures the NodeIterator route end to end (device decode of batches,
+ * copies to pinned host memory, host-side iteration) without a per-node FFI call.  Returns BVG_OK also at the end. */
+int  bvg_cursor_drain(bvg_cursor* c, int64_t max_nodes, int64_t* nodes, int64_t* arcs, uint64_t* checksum);
 
 /* ---- range sharding across GPUs ----
  * A shard's first nodes may copy from lists of the previous shard.  Either the shard re-decodes that halo from its

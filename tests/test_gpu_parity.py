@@ -341,6 +341,40 @@ def test_size_independent_properties_on_a_larger_graph(tmp_path):
     g.close()
 
 
+def test_cursor_drain_equals_scan(cnr, synth100k):
+    """bvg_cursor_drain (the C loop a binding runs over bvg_cursor_next: double-buffered batches in pinned memory) consumes
+    exactly what the consume-only scan does; mixing single steps, partial drains and a copied cursor keeps the position."""
+    import ctypes as C
+    L = bvgraph.lib()
+    for g, want in ((cnr, (3216152, 0xf941dd3471d172f1)), (BVGraph.load(synth100k[0]), (synth100k[1]["arcs"], synth100k[1]["xor_checksum"]))):
+        n = g.numNodes()
+        h = C.c_void_p()
+        bvgraph._check(L.bvg_cursor_open(g.handle, 0, 2 ** 31 - 1, C.byref(h)))
+        nodes, arcs, cs = C.c_int64(), C.c_int64(), C.c_uint64()
+        bvgraph._check(L.bvg_cursor_drain(h, -1, C.byref(nodes), C.byref(arcs), C.byref(cs)))
+        assert (nodes.value, arcs.value, cs.value) == (n, want[0], want[1])
+        assert L.bvg_cursor_next(h, None, None, None) == -8  # BVG_EEND, NoSuchElementException in the reference
+        L.bvg_cursor_close(h)
+        # from the middle, in pieces that straddle batch boundaries (65536 nodes), with a copy taken on the way
+        frm = 70000 if n > 200000 else n // 3
+        bvgraph._check(L.bvg_cursor_open(g.handle, frm, 2 ** 31 - 1, C.byref(h)))
+        tot_n, tot_a, x = 0, 0, 0
+        bvgraph._check(L.bvg_cursor_drain(h, 61000, C.byref(nodes), C.byref(arcs), C.byref(cs)))
+        tot_n += nodes.value; tot_a += arcs.value; x ^= cs.value
+        h2 = C.c_void_p()
+        bvgraph._check(L.bvg_cursor_copy(h, 2 ** 31 - 1, C.byref(h2)))
+        bvgraph._check(L.bvg_cursor_drain(h, -1, C.byref(nodes), C.byref(arcs), C.byref(cs)))
+        rest = (nodes.value, arcs.value, cs.value)
+        bvgraph._check(L.bvg_cursor_drain(h2, -1, C.byref(nodes), C.byref(arcs), C.byref(cs)))
+        assert rest == (nodes.value, arcs.value, cs.value)
+        tot_n += rest[0]; tot_a += rest[1]; x ^= rest[2]
+        assert tot_n == n - frm and (tot_a, x) == g.scanRange(frm, n)
+        L.bvg_cursor_close(h)
+        L.bvg_cursor_close(h2)
+        if g is not cnr:
+            g.close()
+
+
 def test_halo_import_from_device_buffers_twice(synth100k):
     """What bench.py does every step at N > 1: boundary lists exported into device buffers, imported from device buffers.
     The first import sizes the halo buffers (one round trip), every later one of the same shape is a device-side copy."""

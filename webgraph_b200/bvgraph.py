@@ -52,7 +52,7 @@ SYMBOLS = [
     "bvg_open", "bvg_open_shard", "bvg_open_memory", "bvg_close", "bvg_info", "bvg_extent", "bvg_random_access",
     "bvg_set_stream", "bvg_device", "bvg_outdegree", "bvg_successors", "bvg_successors_batch", "bvg_outdegree_batch",
     "bvg_range_arcs", "bvg_decode_range", "bvg_scan_range", "bvg_scan_range_async", "bvg_cursor_open", "bvg_cursor_next",
-    "bvg_cursor_copy", "bvg_cursor_close", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
+    "bvg_cursor_copy", "bvg_cursor_close", "bvg_cursor_drain", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
     "bvg_open_memory_shard", "bvg_plan_shards", "bvg_profile", "bvg_profile_read",
 ]
@@ -92,6 +92,7 @@ def lib():
     L.bvg_cursor_copy.argtypes = [vp, i32, P(vp)]
     L.bvg_cursor_close.argtypes = [vp]
     L.bvg_cursor_close.restype = None
+    L.bvg_cursor_drain.argtypes = [vp, C.c_int64, P(C.c_int64), P(C.c_int64), P(C.c_uint64)]
     L.bvg_boundary_count.argtypes = [vp, P(i32)]
     L.bvg_boundary_export.argtypes = [vp, vp, vp, i64, C.c_int]
     L.bvg_halo_needed.argtypes = [vp, P(i32)]

@@ -1334,14 +1334,113 @@ int bvg_successors(const bvg_graph* g, int32_t x, int32_t* out, int32_t cap, int
 // NodeIterator
 // ------------------------------------------------------------------------------------------------------------
 
+// A cursor holds two batches of decoded nodes in pinned host memory: the host iterates over one while the device decodes
+// the next one and copies it out (the reference's iterator decodes lazily, one successor per nextInt(); a per-node
+// round trip to the device would cost a launch per node).
+struct CursorBatch {
+    int32_t lo = 0, hi = 0;              // nodes held (or being decoded)
+    int64_t arcs = 0;
+    int64_t* h_off = nullptr;            // pinned: hi - lo + 1 relative arc offsets
+    int32_t* h_succ = nullptr;           // pinned: arcs successors
+    size_t hcap_nodes = 0, hcap_arcs = 0;
+    int64_t* d_off = nullptr;
+    int32_t* d_succ = nullptr;
+    size_t dcap_nodes = 0, dcap_arcs = 0;
+    cudaEvent_t ready = nullptr;
+    bool pending = false;                // enqueued, not yet waited for
+};
 struct bvg_cursor {
     const bvg_graph* g;
     int32_t next;        // next node to return
     int32_t upper;       // no node >= upper is returned (BVGraph.java:1185)
-    int32_t batch_lo = 0, batch_hi = 0;  // nodes currently held
-    std::vector<int64_t> off;
-    std::vector<int32_t> succ;
+    CursorBatch b[2];
+    int cur = 0;         // b[cur] is the batch being iterated; b[1 - cur] the one in flight
+    bool have = false;   // b[cur] holds [lo, hi)
 };
+static const int32_t CURSOR_BATCH_NODES = 65536;
+
+static void cursor_release(bvg_cursor* c) {
+    for (CursorBatch& b : c->b) {
+        if (b.pending) { cudaEventSynchronize(b.ready); b.pending = false; }
+        if (b.h_off) cudaFreeHost(b.h_off);
+        if (b.h_succ) cudaFreeHost(b.h_succ);
+        dev_free(b.d_off, c->g->stream);
+        dev_free(b.d_succ, c->g->stream);
+        if (b.ready) cudaEventDestroy(b.ready);
+        b = CursorBatch();
+    }
+    cudaGetLastError();
+}
+
+// Enqueues decode + copy-out of the batch starting at `lo` into b; returns without waiting.
+static int cursor_enqueue(bvg_cursor* c, CursorBatch& b, int32_t lo) {
+    const bvg_graph* g = c->g;
+    cudaStream_t s = g->stream;
+    int32_t hi = (int32_t)std::min<int64_t>(c->upper, (int64_t)lo + CURSOR_BATCH_NODES);
+    int64_t ra = 0, rb = 0;
+    for (;;) {
+        int rc = fetch_rowoff(g, lo, hi, &ra, &rb);
+        if (rc) return rc;
+        if (rb - ra <= ((int64_t)1 << 26) || hi - lo <= 1) break;
+        hi = lo + (hi - lo) / 2;
+    }
+    const int64_t arcs = rb - ra, cnt = (int64_t)hi - lo;
+    if ((size_t)cnt + 1 > b.hcap_nodes) {
+        if (b.h_off) cudaFreeHost(b.h_off);
+        b.h_off = nullptr; b.hcap_nodes = 0;
+        CK(cudaHostAlloc((void**)&b.h_off, ((size_t)CURSOR_BATCH_NODES + 1) * 8, cudaHostAllocDefault));
+        b.hcap_nodes = (size_t)CURSOR_BATCH_NODES + 1;
+    }
+    if ((size_t)arcs > b.hcap_arcs) {
+        if (b.h_succ) cudaFreeHost(b.h_succ);
+        b.h_succ = nullptr; b.hcap_arcs = 0;
+        const size_t want = std::max<size_t>((size_t)arcs + (size_t)arcs / 4, (size_t)1 << 20);
+        CK(cudaHostAlloc((void**)&b.h_succ, want * 4, cudaHostAllocDefault));
+        b.hcap_arcs = want;
+    }
+    if ((size_t)cnt + 1 > b.dcap_nodes) {
+        dev_free(b.d_off, s); b.d_off = nullptr; b.dcap_nodes = 0;
+        CK(dev_alloc((void**)&b.d_off, ((size_t)CURSOR_BATCH_NODES + 1) * 8, s));
+        b.dcap_nodes = (size_t)CURSOR_BATCH_NODES + 1;
+    }
+    if ((size_t)arcs > b.dcap_arcs) {
+        dev_free(b.d_succ, s); b.d_succ = nullptr; b.dcap_arcs = 0;
+        const size_t want = std::max<size_t>((size_t)arcs + (size_t)arcs / 4, (size_t)1 << 20);
+        CK(dev_alloc((void**)&b.d_succ, want * 4, s));
+        b.dcap_arcs = want;
+    }
+    if (!b.ready) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
+    LAUNCH(k_rel_offsets, grid_for(cnt + 1, 256), 256, 0, s, g->d_rowoff + (lo - g->node_lo), cnt, b.d_off);
+    if (arcs) { const int rc = enqueue_decode(g, lo, hi, b.d_succ, ra); if (rc) return rc; }
+    CK(cudaMemcpyAsync(b.h_off, b.d_off, ((size_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (arcs) CK(cudaMemcpyAsync(b.h_succ, b.d_succ, (size_t)arcs * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(b.ready, s));
+    b.lo = lo; b.hi = hi; b.arcs = arcs; b.pending = true;
+    return BVG_OK;
+}
+
+// Makes b[cur] the batch that holds c->next and starts the one after it.
+static int cursor_refill(bvg_cursor* c) {
+    const bvg_graph* g = c->g;
+    DeviceGuard dg(g->device);
+    CursorBatch& nb = c->b[1 - c->cur];
+    if (!(nb.pending && nb.lo == c->next)) {  // first call, or the iteration did not run into the prefetched batch
+        if (nb.pending) { CK(cudaEventSynchronize(nb.ready)); nb.pending = false; }
+        const int rc = cursor_enqueue(c, nb, c->next);
+        if (rc) return rc;
+    }
+    CK(cudaEventSynchronize(nb.ready));
+    nb.pending = false;
+    const int e = fetch_error(g);
+    if (e) return e;
+    c->cur = 1 - c->cur;
+    c->have = true;
+    if (c->b[c->cur].hi < c->upper) {  // the host iterates over b[cur] while the device fills the other one
+        const int rc = cursor_enqueue(c, c->b[1 - c->cur], c->b[c->cur].hi);
+        if (rc) return rc;
+    }
+    return BVG_OK;
+}
 
 int bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor** out) {
     if (!g || !out) return BVG_EINVAL;
@@ -1357,26 +1456,15 @@ int bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor*
 int bvg_cursor_next(bvg_cursor* c, int32_t* node, int32_t* d, const int32_t** succ) {
     if (!c) return BVG_EINVAL;
     if (c->next >= c->upper) return BVG_EEND;  // BVGraph.java:1202
-    if (c->next >= c->batch_hi || c->next < c->batch_lo) {
-        // refill: device decodes a batch of nodes at once (a per-node call would pay a launch per nextInt())
-        int32_t hi = (int32_t)std::min<int64_t>(c->upper, (int64_t)c->next + 65536);
-        int64_t arcs = 0;
-        for (;;) {
-            int rc = bvg_range_arcs(c->g, c->next, hi, &arcs);
-            if (rc) return rc;
-            if (arcs <= ((int64_t)1 << 26) || hi - c->next <= 1) break;
-            hi = c->next + (hi - c->next) / 2;
-        }
-        c->off.resize((size_t)(hi - c->next) + 1);
-        c->succ.resize((size_t)std::max<int64_t>(arcs, 1));
-        int rc = bvg_decode_range(c->g, c->next, hi, c->off.data(), c->succ.data(), arcs, 0);
+    if (!c->have || c->next >= c->b[c->cur].hi || c->next < c->b[c->cur].lo) {
+        const int rc = cursor_refill(c);
         if (rc) return rc;
-        c->batch_lo = c->next; c->batch_hi = hi;
     }
-    const size_t i = (size_t)(c->next - c->batch_lo);
+    const CursorBatch& b = c->b[c->cur];
+    const size_t i = (size_t)(c->next - b.lo);
     if (node) *node = c->next;
-    if (d) *d = (int32_t)(c->off[i + 1] - c->off[i]);
-    if (succ) *succ = c->succ.data() + c->off[i];
+    if (d) *d = (int32_t)(b.h_off[i + 1] - b.h_off[i]);
+    if (succ) *succ = b.h_succ + b.h_off[i];
     c->next++;
     return BVG_OK;
 }
@@ -1390,7 +1478,33 @@ int bvg_cursor_copy(const bvg_cursor* c, int32_t upper, bvg_cursor** out) {  // 
     return BVG_OK;
 }
 
-void bvg_cursor_close(bvg_cursor* c) { delete c; }
+void bvg_cursor_close(bvg_cursor* c) {
+    if (!c) return;
+    DeviceGuard dg(c->g->device);
+    cursor_release(c);
+    delete c;
+}
+
+int bvg_cursor_drain(bvg_cursor* c, int64_t max_nodes, int64_t* nodes, int64_t* arcs, uint64_t* checksum) {
+    if (!c) return BVG_EINVAL;
+    int64_t nn = 0, na = 0;
+    uint64_t cs = 0;
+    while (max_nodes < 0 || nn < max_nodes) {
+        int32_t x, d;
+        const int32_t* succ;
+        const int rc = bvg_cursor_next(c, &x, &d, &succ);
+        if (rc == BVG_EEND) break;
+        if (rc) return rc;
+        const uint64_t base = (uint64_t)(uint32_t)x * 0x9E3779B97F4A7C15ull;
+        for (int32_t i = 0; i < d; i++) cs ^= base + (uint64_t)(uint32_t)succ[i];
+        na += d;
+        nn++;
+    }
+    if (nodes) *nodes = nn;
+    if (arcs) *arcs = na;
+    if (checksum) *checksum = cs;
+    return BVG_OK;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // shard boundaries
