@@ -944,8 +944,8 @@ static int run_ordered_decode(const bvg_graph* g, int32_t lo, int32_t to, int32_
     static const bool lean = !(getenv("BVG_DECODE_LEAN") && atoi(getenv("BVG_DECODE_LEAN")) == 0);
     const bool use_lean = g->def_codec && lean && g->d_rec_e && g->d_rec_m;
     unsigned long long* const no_fold = nullptr;
-    if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
-    else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1);
+    if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1, 1);
+    else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1, 1);
     else if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
     else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
     Tmp<int32_t> long_tmp(s);
@@ -1070,10 +1070,10 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
     static const bool persistent = getenv("BVG_SCAN_PERSISTENT") && atoi(getenv("BVG_SCAN_PERSISTENT")) != 0;
     const unsigned wave = (unsigned)(sms * SCAN_BLOCKS_PER_SM);
-    // Extras step: BVG_SCAN_ITEMS records per thread (grid-stride: a thread's records are gridDim * 128 schedule positions
-    // apart, so every block gets a heavy, a medium and light ones).  Measured 2.88 / 2.80 / 2.78 / 2.77 ms for 1 / 2 / 4 / 8;
-    // the merge levels are fastest with one record per thread (1.90 / 1.94 / 1.96 / 2.20 ms).
-    static const int items = env_int("BVG_SCAN_ITEMS", 4, 1, 64);
+    // Extras step: BVG_SCAN_ITEMS records per thread, neighbours in the schedule (same chunk, similar length): 2.85 / 2.72 /
+    // 2.82 / 3.07 ms for 1 / 2 / 4 / 8.  (With a thread's records a grid apart: 2.88 / 2.80 / 2.78 / 2.77 ms, but 4.8 instead
+    // of 3.5 GB of DRAM reads.)  The merge levels are fastest with one record per thread (1.90 / 1.94 / 1.96 / 2.20 ms).
+    static const int items = env_int("BVG_SCAN_ITEMS", 2, 1, 64);
     const unsigned grid = persistent ? wave : (unsigned)std::max<int64_t>(1, (g->order_e_count + (int64_t)SCAN_BLOCK * items - 1) / ((int64_t)SCAN_BLOCK * items));
     const unsigned grid_m = persistent ? wave : 0x7fffffffu;
     Tmp<int32_t> long_tmp(s);
@@ -1104,10 +1104,10 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
     static const int dbg_nostore = env_int("BVG_DEBUG_NOSTORE", 0, 0, 1);  // timing experiments only: no row stores, results are wrong
     static const bool ring = env_int("BVG_SCAN_RING", 1, 0, 1) != 0;  // stream staged in shared memory by cp.async (bvg_scan.cuh, WinRing)
-    if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
-    else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
-    else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
-    else if (g->def_codec && lean) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0);
+    if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
+    else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
+    else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
+    else if (g->def_codec && lean) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     if (g->nlong) {

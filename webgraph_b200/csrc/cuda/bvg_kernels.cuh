@@ -558,14 +558,16 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // front of them in a second walk (ScanExtras::iv_merge).
 template <int K, bool RING>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
-                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all) {
+                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all, int items) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
     typedef typename std::conditional<RING, WinRing<SCAN_BLOCK>, Win>::type W;
     const ring_addr my_ring = ring_address(&ring[RING ? threadIdx.x : 0]);
     unsigned long long acc = 0;
     long long arcs = 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += stride) {
+    // `items` consecutive groups of 128 schedule records per block (neighbours in the schedule: same chunk, similar length)
+    for (int32_t it = 0; it < items; it++) {
+        const int64_t base = ((int64_t)blockIdx.x * items + it) * blockDim.x + (threadIdx.x & ~31);
+        if (base >= count) break;
         const int64_t i = base + (threadIdx.x & 31);
         ExtraRec r;
         r.x = -1; r.flags = 0;
