@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--max-degree", type=int, default=1 << 22, help="experiments only: cap on the generator's outdegree law")
     ap.add_argument("--workdir", default=os.environ.get("BVG_BENCH_DIR", "/tmp/bvg_bench"))
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-pieces", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational random-access / materialise legs")
     ap.add_argument("--random-nodes", type=int, default=10_000_000)
@@ -351,14 +352,26 @@ def main():
         g2.close()
     torch.cuda.synchronize()
     barrier()
+    pieces = args.e2e_pieces
+    a_out, c_out = C.c_int64(), C.c_uint64()
+
+    def scan_from_host():
+        bvgraph._check(L.bvg_scan_memory(graph_pin.data_ptr(), graph_pin.numel(), offs_pin.data_ptr(), offs_pin.numel(),
+                                         n_total, m_total, 7, 3, 4, 3, 0, local_rank, lo, hi, pieces, C.byref(a_out), C.byref(c_out)))
+        return a_out.value, c_out.value
+
+    for _ in range(2):  # two more untimed calls: the piece-sized blocks of the device memory cache
+        scan_from_host()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_parts = []
     t0 = time.perf_counter()
     for _ in range(es):
-        g2 = open_shard()
-        g2.setStream(stream.cuda_stream)
-        arcs2, cs2 = g2.scanRange(lo, hi)
-        g2.close()
+        e2e_parts.append(scan_from_host())
     torch.cuda.synchronize()
     te = time.perf_counter() - t0
+    if world == 1 and any(r != (m_total, int(st["xor_checksum"])) for r in e2e_parts):
+        raise SystemExit("e2e decode mismatch: %r" % (e2e_parts,))
     tt = torch.tensor([te], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -366,7 +379,8 @@ def main():
     e2e = {"value": m_total * es / te, "unit": UNIT,
            "h2d_bytes_per_step": int(foot["stream_bytes"] + foot["offsets_bytes"]), "d2h_bytes_per_step": 16 + 24,
            "steps": es, "warmup": 1,
-           "what": "bvg_open_memory_shard(pinned host .graph/.offsets: H2D, offsets decode, index build) + bvg_scan_range + bvg_close per step"}
+           "pieces": pieces,
+           "what": "bvg_scan_memory(pinned host .graph/.offsets, %d pieces): per step H2D of every byte, offsets decode, index build and scan of each piece (piece p + 1 crosses PCIe while piece p is indexed and scanned), result back to the host" % pieces}
 
     # ---- the other BASELINE configs on the same graph, outside the timed region (N = 1 only): C4 random access to 10 M
     # uniformly random nodes (seeded, as SpeedTest -r, reference test/SpeedTest.java:98-111) and the materialising decode ----

@@ -99,6 +99,14 @@ int  bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out
  * every successor is decoded on the GPU and folded into arcs and checksum = XOR over arcs (x,y) of
  * (x * 0x9E3779B97F4A7C15 + y) mod 2^64; no successor array is written to HBM by the caller. */
 int  bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum);
+/* The same over a graph held in HOST memory that is used once (the reference's offline / sequential access,
+ * BVGraph.loadOffline / loadSequential, BVGraph.java:1380-1500, scanned as by test/SpeedTest.java:157-185): nothing stays
+ * on the device.  The node range is cut into `pieces` bit-balanced pieces; while the device indexes and scans piece p,
+ * the bytes of piece p + 1 cross PCIe (give pinned memory for that overlap).  pieces = 1 is open + scan + close.
+ * [from, to) is the node range to scan (a shard of a multi-GPU scan, or 0, nodes). */
+int  bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                     int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                     uint32_t flags, int device, int32_t from, int32_t to, int pieces, int64_t* arcs_out, uint64_t* checksum_out);
 /* Asynchronous variant for benchmarking: enqueues the scan on the graph's stream and leaves
  * {arcs, checksum} in the two-word device buffer d_result (int64, uint64). */
 int  bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_result);

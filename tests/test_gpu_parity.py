@@ -375,6 +375,29 @@ def test_cursor_drain_equals_scan(cnr, synth100k):
             g.close()
 
 
+def test_scan_memory_pipelined_pieces(synth100k):
+    """bvg_scan_memory (one pass over a graph in host memory, piece p + 1 uploaded while piece p is indexed and scanned):
+    every number of pieces and every sub-range gives what bvg_scan_range gives on the opened graph."""
+    import ctypes as C
+    base, st, off, succ = synth100k
+    graph = np.fromfile(base + ".graph", dtype=np.uint8)
+    offs = np.fromfile(base + ".offsets", dtype=np.uint8)
+    n = len(off) - 1
+    L = bvgraph.lib()
+    g = BVGraph.load(base)
+    a, c = C.c_int64(), C.c_uint64()
+    for frm, to in ((0, n), (0, n // 3), (n // 3 + 7, n - 11), (5, 6)):
+        want = g.scanRange(frm, to)
+        for pieces in (1, 2, 5, 16):
+            bvgraph._check(L.bvg_scan_memory(graph.ctypes.data, len(graph), offs.ctypes.data, len(offs), n, int(st["arcs"]),
+                                             7, 3, 4, 3, 0, 0, frm, to, pieces, C.byref(a), C.byref(c)))
+            assert (a.value, c.value) == want, (frm, to, pieces)
+    assert g.scanRange(0, n) == (st["arcs"], st["xor_checksum"])
+    g.close()
+    assert L.bvg_scan_memory(graph.ctypes.data, len(graph), offs.ctypes.data, len(offs), n, int(st["arcs"]),
+                             7, 3, 4, 3, 0, 0, 0, n + 1, 2, C.byref(a), C.byref(c)) == -1  # BVG_EINVAL
+
+
 def test_halo_import_from_device_buffers_twice(synth100k):
     """What bench.py does every step at N > 1: boundary lists exported into device buffers, imported from device buffers.
     The first import sizes the halo buffers (one round trip), every later one of the same shape is a device-side copy."""

@@ -21,6 +21,14 @@ __global__ void k_bswap(uint32_t* __restrict__ w, uint64_t n) {
     if (i < n) w[i] = __byte_perm(w[i], 0, 0x0123);
 }
 
+// Small host-to-device transfers of an index build, pulled by a kernel out of pinned staging memory instead of queued on
+// the copy engine, whose queue is shared by all streams.  Both pointers 16-byte aligned; bytes a multiple of 4.
+__global__ void k_pull_copy(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t nwords) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) dst[i] = src[i];
+}
+__global__ void k_set_i32(int32_t* __restrict__ p, int32_t v) { *p = v; }
+
 // Header pass: outdegree and reference of every loaded node (BVGraph.java:1048-1053; outdegree(x) :857-879).
 template <bool DEF>
 __global__ void k_header(GraphDev g, int32_t* __restrict__ outdeg, int32_t* __restrict__ ref) {
@@ -62,6 +70,23 @@ __global__ void k_depth(GraphDev g, int32_t* __restrict__ depth, int32_t* __rest
     if (dep > 0) atomicMax(maxdepth, dep);
     // inside the extent every chain must close within the loaded window (it does when the file honours maxrefcount)
     if (dep < 0 && g.node_lo + (int32_t)i >= ext_from) report(g.err, E_FORMAT, g.node_lo + (int32_t)i, g.offsets[i]);
+}
+
+// Bit-balanced cuts of the node range [from, to) (bvg_plan_shards on the device): bounds[i] = first node whose record starts
+// at or after offsets[from] + i * bits / pieces; one thread per cut.
+__global__ void k_plan_cuts(const uint64_t* __restrict__ offsets, int32_t from, int32_t to, int32_t pieces, int32_t* __restrict__ bounds) {
+    const uint64_t first = offsets[from], total = offsets[to] - first;
+    for (int32_t i = threadIdx.x; i <= pieces; i += blockDim.x) {
+        if (i == 0) { bounds[0] = from; continue; }
+        if (i == pieces) { bounds[pieces] = to; continue; }
+        const uint64_t target = first + total / (uint64_t)pieces * (uint64_t)i;
+        int32_t lo = from, hi = to;  // first node with offsets[node] >= target
+        while (lo < hi) {
+            const int32_t mid = lo + (hi - lo) / 2;
+            if (offsets[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        bounds[i] = lo;
+    }
 }
 
 __global__ void k_max_i32(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
