@@ -11,8 +11,10 @@ bit-balanced contiguous node ranges, one per rank (config C5, strong scaling); e
 exchange their boundary reference lists with one NCCL all-gather and each rank scans its shard.
 
 value      : arcs decoded by all ranks / max-over-ranks device time, inputs resident in HBM
-e2e        : same metric through the public call with HOST buffers: bvg_open_memory (H2D of the .graph bytes and
-             offsets from pinned memory, index build) + scan + result D2H, every step
+e2e        : same metric through the public call with HOST buffers: bvg_scan_memory -- every step uploads every byte
+             of the rank's .graph range and .offsets from pinned memory, decodes the offsets, builds the index, scans and
+             brings (arcs, checksum) back; the node range goes in --e2e-pieces pieces over two streams so that piece
+             p + 1 crosses PCIe while piece p is indexed and scanned (1 piece = open + scan + close)
 roofline   : dominant kernel's algorithmic bytes (.graph bits of the scanned range / 8) / its CUDA-event time,
              against MEASURED_PEAKS.json's hbm_gbs
 cpu_baseline: the oracle (C restatement of BVGraph.nodeIterator(), kind "port": no JVM exists in the image) on one

@@ -142,6 +142,10 @@ const char* bvg_strerror(int status);
 int  bvg_last_error_node(const bvg_graph* g, int32_t* node, int64_t* bitpos);
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
 int64_t bvg_kernel_launches(void);
+/* Device memory of closed graphs and of temporaries stays in a library-owned cache (so that open / scan / close cycles
+ * and repeated scans cost no cudaMalloc; at most BVG_CACHE_GB gigabytes, default 32, 0 = no caching).  This gives it back
+ * to the driver: every idle block of `device`, or of all devices when device < 0.  Returns the bytes released. */
+int64_t bvg_release_cached_memory(int device);
 /* Per-kernel device timing for bench.py's roofline object: while enabled every kernel of this graph is bracketed by CUDA
  * events on the launching stream; bvg_profile_read drains them into a JSON object {"kernel": {"launches": n, "ms": t}}. */
 int  bvg_profile(const bvg_graph* g, int enable);

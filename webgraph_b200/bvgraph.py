@@ -54,7 +54,7 @@ SYMBOLS = [
     "bvg_range_arcs", "bvg_decode_range", "bvg_scan_range", "bvg_scan_range_async", "bvg_cursor_open", "bvg_cursor_next",
     "bvg_cursor_copy", "bvg_cursor_close", "bvg_cursor_drain", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
-    "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_profile", "bvg_profile_read",
+    "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_release_cached_memory", "bvg_profile", "bvg_profile_read",
 ]
 
 
@@ -70,6 +70,8 @@ def lib():
     L.bvg_open_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, P(vp)]
     L.bvg_open_memory_shard.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, i32, i32, P(vp)]
     L.bvg_plan_shards.argtypes = [C.c_char_p, C.c_int, P(i32)]
+    L.bvg_release_cached_memory.argtypes = [C.c_int]
+    L.bvg_release_cached_memory.restype = C.c_int64
     L.bvg_scan_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, i32, i32, C.c_int, P(i64), P(u64)]
     L.bvg_profile.argtypes = [vp, C.c_int]
     L.bvg_profile_read.argtypes = [vp, C.c_char_p, C.c_int]

@@ -1761,6 +1761,27 @@ int bvg_last_error_node(const bvg_graph* g, int32_t* node, int64_t* bitpos) {
 
 int64_t bvg_kernel_launches(void) { return g_launches.load(); }
 
+int64_t bvg_release_cached_memory(int device) {
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    int64_t freed = 0;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto it = c.idle.begin(); it != c.idle.end();) {
+        if (device < 0 || it->second.dev == device) {
+            cudaSetDevice(it->second.dev);
+            cudaEventDestroy(it->second.ev);
+            cudaFree(it->second.p);  // waits for whatever may still use the block
+            freed += (int64_t)it->second.bytes;
+            c.idle_bytes -= it->second.bytes;
+            it = c.idle.erase(it);
+        } else ++it;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+    return freed;
+}
+
 int bvg_profile(const bvg_graph* g, int enable) {
     if (!g) return BVG_EINVAL;
     g->prof_on = enable != 0;
