@@ -42,6 +42,12 @@ int bvgt_store_csr(const char* basename, int32_t n, const int64_t* off, const in
                    int32_t window, int32_t maxref, int32_t minlen, int32_t zetak, uint32_t flags,
                    int threads, bvgt_store_stats* stats);
 
+/* Writes `count` values back to back in one of the instantaneous codes of dsiutils' OutputBitStream (coding ids above;
+ * k = shrinking factor of zeta, modulus of Golomb, ignored otherwise), MSB first, zero-padded to a byte.  Returns the
+ * number of bits written, -1 on a bad argument or when `cap` bytes do not suffice, -3 for skewed Golomb (which the
+ * reference's BVGraph cannot read either).  For code-level tests of the readers. */
+int64_t bvgt_write_codes(int coding, int32_t k, const uint64_t* values, int64_t count, uint8_t* out, int64_t cap);
+
 typedef struct bvgt_gen_params {
     int32_t  n;            /* nodes */
     int64_t  target_arcs;  /* approximate number of arcs wanted */

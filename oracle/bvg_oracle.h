@@ -13,9 +13,10 @@
  * cnr-2000.graph-txt.gz, the pair BVGraphTest.testLarge asserts equal
  * (reference test/it/unimi/dsi/webgraph/BVGraphTest.java:101-119).
  * UNPINNED ("parity unpinned") for the non-default codings (delta anywhere,
- * gamma residuals/references, unary block counts, zeta_k with k != 3): no
- * reference test or fixture covers them and no JVM exists in this image to
- * make one.  Golomb / nibble residuals are rejected (BVGO_EUNSUPPORTED).
+ * gamma / Golomb / nibble residuals, gamma references, unary block counts,
+ * zeta_k with k != 3): no reference test or fixture covers them and no JVM
+ * exists in this image to make one.  Skewed Golomb has no reader in the
+ * reference (BVGraph.java:791-816) and is rejected (BVGO_EUNSUPPORTED).
  *
  * The bit-level codes live in dsiutils (it.unimi.dsi:dsiutils, pinned only as
  * `latest.release` in the reference's ivy.xml:18, not vendored); they are

@@ -80,7 +80,8 @@ def test_emulated_kernels_on_erdos_renyi(emu, oracle, tmp_path, n, p):
 
 @pytest.mark.parametrize("flags,k,w,r,ml", [(0, 3, 7, 3, 4), (0, 2, 1, 1, 0), (0, 5, 16, 10, 2),
                                            (tools.OUTDEGREES_DELTA | tools.BLOCKS_DELTA | tools.RESIDUALS_DELTA | tools.REFERENCES_DELTA | tools.BLOCK_COUNT_DELTA, 3, 7, -1, 4),
-                                           (tools.RESIDUALS_GAMMA | tools.REFERENCES_GAMMA | tools.BLOCK_COUNT_UNARY | tools.BLOCKS_UNARY, 3, 3, 2, 3)])
+                                           (tools.RESIDUALS_GAMMA | tools.REFERENCES_GAMMA | tools.BLOCK_COUNT_UNARY | tools.BLOCKS_UNARY, 3, 3, 2, 3),
+                                           (tools.RESIDUALS_NIBBLE, 3, 7, 3, 4), (tools.RESIDUALS_GOLOMB, 3, 7, 3, 4)])
 def test_emulated_kernels_on_copy_heavy(emu, oracle, tmp_path, flags, k, w, r, ml):
     off, succ, _ = graphs.copy_heavy(1200, seed=33 + k)
     base = str(tmp_path / "ch")

@@ -197,6 +197,7 @@ def test_erdos_renyi(tmp_path, n, p):  # ImmutableGraphTest.java:68-82
     (0, 1), (0, 2), (0, 5),
     (tools.OUTDEGREES_DELTA | tools.BLOCKS_DELTA | tools.RESIDUALS_DELTA | tools.REFERENCES_DELTA | tools.BLOCK_COUNT_DELTA | tools.OFFSETS_DELTA, 3),
     (tools.RESIDUALS_GAMMA | tools.REFERENCES_GAMMA | tools.BLOCK_COUNT_UNARY | tools.BLOCKS_UNARY, 3),
+    (tools.RESIDUALS_NIBBLE, 3), (tools.RESIDUALS_GOLOMB | tools.BLOCKS_DELTA, 3),
 ])
 def test_non_default_codings(tmp_path, oracle, flags, k):  # parity unpinned by the reference; checked against the oracle
     off, succ, _ = graphs.copy_heavy(1500, seed=5)

@@ -316,10 +316,14 @@ static int set_codec(bvg_graph* g) {
     c.zetak = g->zetak; c.window = g->window; c.minlen = g->minlen;
     auto gd = [](int x) { return x == C_GAMMA || x == C_DELTA; };
     auto gdu = [](int x) { return x == C_GAMMA || x == C_DELTA || x == C_UNARY; };
-    // Golomb / skewed Golomb / nibble residuals are selectable in the reference (BVGraph.java:796-797) but covered by
-    // none of its tests or fixtures: rejected rather than guessed.
+    // Exactly the codings the reference's readers accept (BVGraph.java:631-637, 658-664, 696-707, 732-739, 762-769,
+    // 791-816): gamma | delta outdegrees; unary | gamma | delta blocks, block counts and references; gamma | zeta | delta |
+    // Golomb (modulus zetaK) | nibble residuals.  Anything else (skewed Golomb anywhere) is the reference's
+    // UnsupportedOperationException.  Golomb and nibble are covered by none of the reference's tests or fixtures
+    // ("parity unpinned"): they follow the published dsiutils definitions.
     if (!gd(c.outdeg) || !gdu(c.block) || !gdu(c.ref) || !gdu(c.bcount) ||
-        !(c.resid == C_GAMMA || c.resid == C_DELTA || c.resid == C_ZETA)) return BVG_EUNSUPPORTED;
+        !(c.resid == C_GAMMA || c.resid == C_DELTA || c.resid == C_ZETA || c.resid == C_GOLOMB || c.resid == C_NIBBLE)) return BVG_EUNSUPPORTED;
+    if (c.resid == C_GOLOMB && c.zetak < 0) return BVG_EINVAL;  // readGolomb: IllegalArgumentException on a negative modulus
     g->def_codec = c.outdeg == C_GAMMA && c.block == C_GAMMA && c.resid == C_ZETA && c.ref == C_UNARY && c.bcount == C_GAMMA;
     return BVG_OK;
 }

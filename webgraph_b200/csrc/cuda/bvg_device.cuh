@@ -18,6 +18,11 @@
 #else
 #include <cuda_runtime.h>
 #endif
+#ifdef BVG_HOST_EMULATION
+#define BVG_NOINLINE inline
+#else
+#define BVG_NOINLINE __noinline__
+#endif
 
 namespace bvg {
 
@@ -139,12 +144,37 @@ struct Bits {
         if (m < left) return m + left - 1;
         return ((m << 1) | bits(1)) - 1;
     }
+    // Golomb with modulus b (InputBitStream.readGolomb(b), dsiutils; BVGraph passes zetaK as the modulus,
+    // BVGraph.java:796, 812): unary(x / b), then x % b in minimal binary -- with l = msb(b) and m = 2^(l+1) - b,
+    // remainders below m take l bits, the others l + 1 bits holding (remainder + m).  b == 0 reads nothing.
+    __device__ BVG_NOINLINE uint64_t golomb(int b) {
+        if (b <= 0) return 0;
+        const uint64_t q = unary();
+        const int l = 31 - __clz(b);
+        const uint64_t m = (2ull << l) - (uint64_t)b;
+        uint64_t r = bits(l);
+        if (r >= m) r = ((r << 1) | bits(1)) - m;
+        return q * (uint64_t)b + r;
+    }
+    // Nibble code (InputBitStream.readNibble): 4-bit groups, MSB group first, each a stop flag (1 = last group)
+    // followed by three bits of the value.  At most 22 groups make a 64-bit value; more is a corrupt stream.
+    __device__ BVG_NOINLINE uint64_t nibble() {
+        uint64_t x = 0;
+        for (int i = 0; i < 22; i++) {
+            const uint64_t grp = bits(4);
+            x = (x << 3) | (grp & 7ull);
+            if (grp & 8ull) return x;
+        }
+        return ~0ull;
+    }
     __device__ __forceinline__ uint64_t coded(int coding, int k) {
         switch (coding) {
-            case C_GAMMA: return gamma();
-            case C_DELTA: return delta();
-            case C_UNARY: return unary();
-            default:      return zeta(k);
+            case C_GAMMA:  return gamma();
+            case C_DELTA:  return delta();
+            case C_UNARY:  return unary();
+            case C_GOLOMB: return golomb(k);
+            case C_NIBBLE: return nibble();
+            default:       return zeta(k);
         }
     }
 };
@@ -245,10 +275,12 @@ struct BitBuf {
     }
     __device__ __forceinline__ uint64_t coded(int coding, int k) {
         switch (coding) {
-            case C_GAMMA: return gamma();
-            case C_DELTA: return delta();
-            case C_UNARY: return unary();
-            default:      return zeta(k);
+            case C_GAMMA:  return gamma();
+            case C_DELTA:  return delta();
+            case C_UNARY:  return unary();
+            case C_GOLOMB: return slow([k](Bits& t) { return t.golomb(k); });
+            case C_NIBBLE: return slow([](Bits& t) { return t.nibble(); });
+            default:       return zeta(k);
         }
     }
 };

@@ -21,11 +21,6 @@ __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < 
 
 // Codes that do not fit the 32-bit window go through the position-based reader, out of line: they are rare (gaps >= 2^24
 // for zeta_3, values >= 2^16 - 1 for gamma) and inlining them at every call site triples the size of the hot loops.
-#ifdef BVG_HOST_EMULATION
-#define BVG_NOINLINE inline
-#else
-#define BVG_NOINLINE __noinline__
-#endif
 __device__ BVG_NOINLINE uint64_t slow_gamma(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t* pos) {
     Bits t;
     t.w = words; t.maxw = nwords - 3; t.pos = *pos;

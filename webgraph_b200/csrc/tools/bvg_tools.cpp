@@ -100,6 +100,33 @@ inline void put_zeta(BitBuf& b, uint64_t x, int k) {
     else b.put(y, h * k + k);
 }
 
+// Golomb with modulus b (OutputBitStream.writeGolomb: unary(x / b), then x % b in minimal binary: with l = msb(b),
+// m = 2^(l+1) - b, remainders below m in l bits, the others as remainder + m in l + 1 bits); BVGraph uses b = zetaK
+// (BVGraph.java:779, 809-813).  b == 0 writes nothing (and only encodes 0).
+inline int len_golomb(uint64_t x, int b) {
+    if (b <= 0) return 0;
+    const int l = 31 - __builtin_clz((unsigned)b);
+    const uint64_t m = (2ULL << l) - (uint64_t)b;
+    const uint64_t q = x / (uint64_t)b;
+    return (int)std::min<uint64_t>(q + 1, 1u << 30) + l + (x % (uint64_t)b < m ? 0 : 1);
+}
+inline void put_golomb(BitBuf& bb, uint64_t x, int b) {
+    if (b <= 0) return;
+    const int l = 31 - __builtin_clz((unsigned)b);
+    const uint64_t m = (2ULL << l) - (uint64_t)b;
+    put_unary(bb, x / (uint64_t)b);
+    const uint64_t r = x % (uint64_t)b;
+    if (r < m) { if (l) bb.put(r, l); }
+    else bb.put(r + m, l + 1);
+}
+// Nibble code (OutputBitStream.writeNibble): the value in 3-bit groups, most significant first, each preceded by a
+// stop flag that is 1 on the last group only; 0 is the single group 1000.
+inline int len_nibble(uint64_t x) { return x == 0 ? 4 : 4 * (msb64(x) / 3 + 1); }
+inline void put_nibble(BitBuf& b, uint64_t x) {
+    int h = x == 0 ? 0 : msb64(x) / 3;
+    do b.put((h == 0 ? 8u : 0u) | ((x >> (3 * h)) & 7u), 4); while (h-- != 0);
+}
+
 inline uint64_t int2nat(int64_t v) { return v >= 0 ? (uint64_t)v << 1 : (((uint64_t)(-v)) << 1) - 1; }
 
 struct Codec {
@@ -119,13 +146,16 @@ struct Codec {
         auto gd = [](int c) { return c == BVGT_GAMMA || c == BVGT_DELTA; };
         auto gdu = [](int c) { return c == BVGT_GAMMA || c == BVGT_DELTA || c == BVGT_UNARY; };
         ok = gd(outdegree) && gdu(block) && gdu(reference) && gdu(block_count) && gd(offset) &&
-             (residual == BVGT_GAMMA || residual == BVGT_DELTA || residual == BVGT_ZETA);
+             (residual == BVGT_GAMMA || residual == BVGT_DELTA || residual == BVGT_ZETA ||
+              (residual == BVGT_GOLOMB && zetak > 0) || residual == BVGT_NIBBLE);
     }
     inline int len(int coding, uint64_t x) const {
         switch (coding) {
             case BVGT_GAMMA: return len_gamma(x);
             case BVGT_DELTA: return len_delta(x);
             case BVGT_UNARY: return len_unary(x);
+            case BVGT_GOLOMB: return len_golomb(x, zetak);
+            case BVGT_NIBBLE: return len_nibble(x);
             default: return len_zeta(x, zetak);
         }
     }
@@ -134,6 +164,8 @@ struct Codec {
             case BVGT_GAMMA: put_gamma(b, x); break;
             case BVGT_DELTA: put_delta(b, x); break;
             case BVGT_UNARY: put_unary(b, x); break;
+            case BVGT_GOLOMB: put_golomb(b, x, zetak); break;
+            case BVGT_NIBBLE: put_nibble(b, x); break;
             default: put_zeta(b, x, zetak); break;
         }
     }
@@ -497,6 +529,19 @@ int bvgt_store_csr(const char* basename, int32_t n, const int64_t* off, const in
     const int rc = finish(basename, c, parts, stats);
     for (auto* p : parts) delete p;
     return rc;
+}
+
+int64_t bvgt_write_codes(int coding, int32_t k, const uint64_t* values, int64_t count, uint8_t* out, int64_t cap) {
+    if (!values || count < 0 || !out || cap < 0) return -1;
+    if (coding < BVGT_DELTA || coding > BVGT_NIBBLE || coding == BVGT_SKEWED_GOLOMB) return -3;
+    if ((coding == BVGT_ZETA || coding == BVGT_GOLOMB) && k < 1) return -1;
+    Codec c{ 0, 0, 0, k, 0 };
+    BitBuf b;
+    for (int64_t i = 0; i < count; i++) c.put(b, coding, values[i]);
+    const int64_t nbytes = (int64_t)((b.nbits + 7) >> 3);
+    if (nbytes > cap) return -1;
+    for (int64_t i = 0; i < nbytes; i++) out[i] = (uint8_t)(b.w[(size_t)(i >> 3)] >> (56 - 8 * (i & 7)));
+    return (int64_t)b.nbits;
 }
 
 void bvgt_gen_defaults(bvgt_gen_params* p, int32_t n, int64_t target_arcs, uint64_t seed) {

@@ -14,6 +14,8 @@ BLOCKS_DELTA = DELTA << 4
 BLOCKS_UNARY = UNARY << 4
 RESIDUALS_GAMMA = GAMMA << 8
 RESIDUALS_DELTA = DELTA << 8
+RESIDUALS_NIBBLE = NIBBLE << 8
+RESIDUALS_GOLOMB = GOLOMB << 8
 REFERENCES_GAMMA = GAMMA << 12
 REFERENCES_DELTA = DELTA << 12
 BLOCK_COUNT_DELTA = DELTA << 16
@@ -50,7 +52,23 @@ def lib():
         _lib.bvgt_gen_defaults.restype = None
         _lib.bvgt_generate_store.argtypes = [C.c_char_p, C.POINTER(GenParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(StoreStats)]
+        _lib.bvgt_write_codes.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        _lib.bvgt_write_codes.restype = C.c_int64
     return _lib
+
+
+def write_codes(coding, k, values):
+    """`values` written back to back in one of dsiutils' instantaneous codes; returns (bytes, number of bits)."""
+    v = np.ascontiguousarray(values, dtype=np.uint64)
+    cap = 64
+    while True:
+        out = np.zeros(cap, dtype=np.uint8)
+        nbits = lib().bvgt_write_codes(coding, k, v.ctypes.data, len(v), out.ctypes.data, cap)
+        if nbits >= 0:
+            return out[:(nbits + 7) // 8].tobytes(), int(nbits)
+        if nbits != -1 or cap > (1 << 30):
+            raise ValueError("bvgt_write_codes failed: %d" % nbits)
+        cap *= 8
 
 
 def store_csr(basename, off, succ, window=7, maxref=3, minlen=4, zetak=3, flags=0, threads=1):
