@@ -45,7 +45,11 @@ enum bvg_status {
 /* ---- loading: BVGraph.load / loadMapped / loadOffline -> loadInternal (BVGraph.java:1380-1500, 1516-1609) ----
  * offset_type as in BVGraph (:439-441): 2 mapped, 1 standard, 0 sequential (no random access), -1 offline.
  * On the GPU all four place the bit stream and offsets in HBM; offset_type <= 0 only switches the random-access
- * entry points to the reference's errors.  devices/ndev: CUDA ordinals to use (NULL/0 = current device); the
+ * entry points to the reference's errors.  As in the reference, offset_type <= 0 does not need the .offsets file
+ * (loadInternal never opens it, :1581-1609; the iterator just keeps reading, :1201-1213): when it is missing the record
+ * boundaries are found from the .graph stream itself, in parallel on the device (what BVGraph.writeOffsets, :2662-2676,
+ * does with one sequential pass).  offset_type > 0 without .offsets is BVG_EIO (FileNotFoundException).
+ * devices/ndev: CUDA ordinals to use (NULL/0 = current device); the
  * first one holds the graph (multi-GPU runs open one shard per process, see bvg_open_shard). */
 int  bvg_open(const char* basename, int offset_type, const int* devices, int ndev, bvg_graph** out);
 
@@ -56,7 +60,8 @@ int  bvg_open(const char* basename, int offset_type, const int* devices, int nde
 int  bvg_open_shard(const char* basename, int device, int32_t from, int32_t to, bvg_graph** out);
 
 /* Opens a graph held in host memory: `graph` is the .graph byte stream, `offsets_stream` the .offsets byte stream
- * (gamma/delta coded gaps, may be NULL => offset_type 0 semantics are NOT possible: offsets are required). */
+ * (gamma/delta coded gaps).  offsets_stream may be NULL when offset_type <= 0: the record boundaries are then found
+ * from the graph stream on the device (see bvg_open); NULL with offset_type > 0 is BVG_EINVAL. */
 int  bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                      int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                      uint32_t flags, int offset_type, int device, bvg_graph** out);
@@ -103,7 +108,8 @@ int  bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs,
  * BVGraph.loadOffline / loadSequential, BVGraph.java:1380-1500, scanned as by test/SpeedTest.java:157-185): nothing stays
  * on the device.  The node range is cut into `pieces` bit-balanced pieces; while the device indexes and scans piece p,
  * the bytes of piece p + 1 cross PCIe (give pinned memory for that overlap).  pieces = 1 is open + scan + close.
- * [from, to) is the node range to scan (a shard of a multi-GPU scan, or 0, nodes). */
+ * [from, to) is the node range to scan (a shard of a multi-GPU scan, or 0, nodes).  offsets_stream may be NULL (no
+ * .offsets file): the boundaries are found from the stream first, which sends it to the device one more time. */
 int  bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                      int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                      uint32_t flags, int device, int32_t from, int32_t to, int pieces, int64_t* arcs_out, uint64_t* checksum_out);

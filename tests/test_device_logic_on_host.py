@@ -26,16 +26,17 @@ def _find_asan():
 def emu():
     cuda_dir = os.path.join(ROOT, "webgraph_b200", "csrc", "cuda")
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "emu_offsets.cpp"),
-            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
-            os.path.join(cuda_dir, "bvg_offsets.cuh"), os.path.join(cuda_dir, "bvg_scan.cuh")]
+            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "emu_boundaries.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
+            os.path.join(cuda_dir, "bvg_offsets.cuh"), os.path.join(cuda_dir, "bvg_scan.cuh"), os.path.join(cuda_dir, "bvg_boundaries.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
         # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
-                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2], srcs[3]])
+                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2], srcs[3], srcs[4]])
     lib = C.CDLL(EMU)
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
     lib.emu_decode_offsets.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
+    lib.emu_boundaries.argtypes = [C.c_void_p, C.c_uint64, C.c_int64] + [C.c_int] * 9 + [C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     lib.emu_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_stream_fold.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
@@ -119,6 +120,53 @@ def test_emulated_parallel_offsets_decode(emu, oracle, tmp_path):
     base = str(tmp_path / "skew")
     tools.store_csr(base, off2, succ2)
     _emu_offsets(emu, oracle, base)
+
+
+def _emu_boundaries(emu, oracle, base, sub_bits, cap=1 << 26):
+    g = oracle.load(base)
+    graph = np.fromfile(base + ".graph", dtype=np.uint8)
+    c = g.g.contents
+    is_def = (c.outdegree_coding, c.block_coding, c.residual_coding, c.reference_coding, c.block_count_coding) == (2, 2, 6, 5, 2)
+    out = np.full(g.n + 1, 2**64 - 1, dtype=np.uint64)
+    passes, walks = C.c_int(0), C.c_int64(0)
+    rc = emu.emu_boundaries(graph.ctypes.data, len(graph), g.n, g.window, g.minlen, g.zetak, c.outdegree_coding, c.block_coding,
+                            c.residual_coding, c.reference_coding, c.block_count_coding, 1 if is_def else 0, sub_bits, cap,
+                            out.ctypes.data, C.byref(passes), C.byref(walks))
+    assert rc == 0
+    assert np.array_equal(out, g.offsets())
+    nsub = max(1, -(-len(graph) * 8 // sub_bits))
+    return passes.value, walks.value, nsub
+
+
+def test_emulated_boundaries_from_graph_alone(emu, oracle, tmp_path):
+    """Record boundaries found without .offsets (bvg_boundaries.cuh) == the .offsets the writer (and, for cnr-2000, the
+    reference) produced; sub-ranges from far too small (every speculation wrong, passes do the work) to one."""
+    for sub_bits in (1 << 30, 1 << 20, 1 << 17, 1 << 14):
+        passes, walks, nsub = _emu_boundaries(emu, oracle, CNR, sub_bits)
+        assert passes <= nsub + 1
+    # a wrong chain falls onto the right one well inside a 1 Mbit sub-range: speculate, adopt, confirm
+    passes, walks, nsub = _emu_boundaries(emu, oracle, CNR, 1 << 20)
+    assert nsub == 11 and passes <= 4
+    off, succ, _ = graphs.copy_heavy(3000, seed=8)
+    for i, (flags, w, r, ml) in enumerate([(0, 7, 3, 4), (0, 0, 3, 0), (0, 1, 1, 2), (0, 16, -1, 3),
+                                           (tools.OUTDEGREES_DELTA | tools.BLOCKS_DELTA | tools.RESIDUALS_DELTA | tools.REFERENCES_DELTA | tools.BLOCK_COUNT_DELTA, 7, 3, 4),
+                                           (tools.RESIDUALS_GAMMA | tools.REFERENCES_GAMMA | tools.BLOCK_COUNT_UNARY | tools.BLOCKS_UNARY, 3, 2, 3),
+                                           (tools.RESIDUALS_NIBBLE, 7, 3, 4)]):
+        base = str(tmp_path / ("b%d" % i))
+        tools.store_csr(base, off, succ, flags=flags, window=w, maxref=r, minlen=ml)
+        for sub_bits in (1 << 30, 1 << 13, 1 << 10):
+            _emu_boundaries(emu, oracle, base, sub_bits)
+    # a record far longer than a sub-range and than the cap of unproven walks, empty nodes around it
+    deg = np.zeros(5000, dtype=np.int64)
+    deg[7] = 100000
+    deg[4000:4010] = 3
+    off2 = np.zeros(5001, dtype=np.int64)
+    np.cumsum(deg, out=off2[1:])
+    succ2 = np.concatenate([np.arange(0, 400000, 4, dtype=np.int32)] + [np.array([1, 5, 9], dtype=np.int32)] * 10)
+    base = str(tmp_path / "skew")
+    tools.store_csr(base, off2, succ2)
+    for sub_bits, cap in ((1 << 12, 1 << 26), (1 << 12, 1 << 10), (1 << 16, 64)):
+        _emu_boundaries(emu, oracle, base, sub_bits, cap)
 
 
 def test_emulated_fold_only_stream(emu, oracle, tmp_path):

@@ -143,6 +143,61 @@ def test_argument_errors(cnr):
     g.close()
 
 
+def test_sequential_graph_without_offsets_file(tmp_path, cnr_truth, monkeypatch):
+    """loadSequential / loadOffline of a graph that has no .offsets (the reference never opens the file for
+    offsetType <= 0, BVGraph.java:1581-1609; BVGraph.writeOffsets :2662-2676 is how it makes one): the record
+    boundaries come from the .graph stream alone (bvg_boundaries.cuh) and must equal what .offsets holds."""
+    import shutil
+    toff, tsucc = cnr_truth
+    base = str(tmp_path / "noff")
+    shutil.copy(CNR + ".graph", base + ".graph")
+    shutil.copy(CNR + ".properties", base + ".properties")
+    with pytest.raises(IOError):
+        BVGraph.load(base)  # random access needs the file
+    for sub_bits in (None, 1 << 16):  # default sub-ranges; sub-ranges so short that most speculative entries are wrong
+        if sub_bits:
+            monkeypatch.setenv("BVG_BND_SUB_BITS", str(sub_bits))
+        g = BVGraph.loadOffline(base)
+        assert not g.randomAccess()
+        with pytest.raises(bvgraph.UnsupportedOperationError):
+            g.successorArray(3)
+        assert g.scanRange(0, g.numNodes()) == (3216152, 0xf941dd3471d172f1)
+        off, succ = g.decodeRange(0, g.numNodes())
+        assert np.array_equal(off, toff) and np.array_equal(succ, tsucc)
+        g.close()
+    monkeypatch.delenv("BVG_BND_SUB_BITS")
+    # non-default codings, no window, a record far longer than a sub-range; in-memory entry point with offsets = None
+    off, succ, _ = graphs.copy_heavy(3000, seed=8)
+    deg = np.zeros(3000, dtype=np.int64)
+    deg[7] = 100000
+    big_off = np.zeros(3001, dtype=np.int64)
+    np.cumsum(deg, out=big_off[1:])
+    big_succ = np.arange(0, 400000, 4, dtype=np.int32)
+    cases = [(off, succ, dict(flags=0, window=7, maxref=3, minlen=4)), (off, succ, dict(flags=0, window=0, maxref=3, minlen=0)),
+             (off, succ, dict(flags=tools.RESIDUALS_NIBBLE | tools.REFERENCES_GAMMA | tools.BLOCKS_DELTA, window=3, maxref=-1, minlen=2)),
+             (big_off, big_succ, dict(flags=0, window=7, maxref=3, minlen=4))]
+    monkeypatch.setenv("BVG_BND_SUB_BITS", "4096")
+    for i, (o, s_, kw) in enumerate(cases):
+        b = str(tmp_path / ("n%d" % i))
+        tools.store_csr(b, o, s_, **kw)
+        os.remove(b + ".offsets")
+        g = BVGraph.loadSequential(b)
+        o2, s2 = g.decodeRange(0, g.numNodes())
+        assert np.array_equal(o2, o) and np.array_equal(s2, s_)
+        g.close()
+        g = BVGraph.fromMemory(open(b + ".graph", "rb").read(), None, len(o) - 1, len(s_), kw["window"], kw["maxref"], kw["minlen"],
+                               flags=kw["flags"], offsetType=0)
+        assert g.scanRange(0, g.numNodes())[0] == len(s_)
+        g.close()
+    # a stream cut short is an error, not a fault
+    b = str(tmp_path / "n0")
+    data = open(b + ".graph", "rb").read()
+    with open(b + ".graph", "wb") as f:
+        f.write(data[:len(data) // 2])
+    with pytest.raises((IOError, bvgraph.FormatError)):
+        BVGraph.loadSequential(b)
+
+
 # ---- WebGraphTestCase.assertGraph (reference test/it/unimi/dsi/webgraph/WebGraphTestCase.java:158-260) ----
 
 def assert_graph(g, off, succ):

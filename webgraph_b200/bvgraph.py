@@ -328,9 +328,10 @@ class BVGraph(ImmutableGraph):
     @classmethod
     def fromMemory(cls, graph, offsets_stream, nodes, arcs, window, maxref, minlen, zetak=3, flags=0, offsetType=1, device=-1):
         g = np.frombuffer(graph, dtype=np.uint8)
-        o = np.frombuffer(offsets_stream, dtype=np.uint8)
+        o = np.frombuffer(offsets_stream, dtype=np.uint8) if offsets_stream is not None else None  # None: sequential graph without .offsets
         h = C.c_void_p()
-        _check(lib().bvg_open_memory(g.ctypes.data if len(g) else None, len(g), o.ctypes.data, len(o), nodes, arcs, window, maxref,
+        _check(lib().bvg_open_memory(g.ctypes.data if len(g) else None, len(g), o.ctypes.data if o is not None else None,
+                                     len(o) if o is not None else 0, nodes, arcs, window, maxref,
                                      minlen, zetak, flags, offsetType, device, C.byref(h)))
         return cls(h)
 

@@ -8,6 +8,7 @@
 #include "bvg_kernels.cuh"
 #include "bvg_long.cuh"
 #include "bvg_offsets.cuh"
+#include "bvg_boundaries.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -403,6 +404,83 @@ static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t
     return BVG_OK;
 }
 
+// Record boundaries of a graph that comes without .offsets (bvg_boundaries.cuh): the whole stream goes to the device for
+// the duration of the call; *d_full receives the n + 1 bit positions .offsets would have held.
+static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint64_t graph_bytes, const Codec& c, bool def_codec,
+                                     int64_t n, uint64_t** d_full, int32_t* err_node, int64_t* err_bitpos) {
+    const uint64_t stream_bits = graph_bytes * 8;
+    const uint64_t nwords = ((graph_bytes + 3) / 4 + STREAM_PAD_WORDS + 3) & ~(uint64_t)3;
+    Tmp<uint32_t> words(s);
+    CK(words.alloc((size_t)nwords));
+    CK(cudaMemsetAsync(words.p, 0, nwords * 4, s));
+    if (graph_bytes) CK(cudaMemcpyAsync(words.p, graph, graph_bytes, cudaMemcpyHostToDevice, s));
+    LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, words.p, nwords);
+    // Sub-ranges long enough for a wrong chain to fall onto the right one well inside them (a few hundred records),
+    // few enough that their window-sized histories stay small.
+    uint64_t sub_bits = 1ull << 21, cap = 1ull << 25;
+    if (const char* e = getenv("BVG_BND_SUB_BITS")) sub_bits = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("BVG_BND_CAP_BITS")) cap = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
+    const int32_t W = c.window;
+    const int64_t max_sub = std::max<int64_t>(1, std::min<int64_t>(16384, ((int64_t)1 << 24) / std::max<int32_t>(W, 1)));
+    while ((int64_t)((stream_bits + sub_bits - 1) / sub_bits) > max_sub) sub_bits *= 2;
+    const int64_t nsub = std::max<int64_t>(1, (int64_t)((stream_bits + sub_bits - 1) / sub_bits));
+    const size_t hw = (size_t)nsub * (size_t)std::max<int32_t>(W, 1);
+    Tmp<BndSub> sa(s), sb(s);
+    Tmp<int32_t> he_a(s), he_b(s), hx_a(s), hx_b(s), ring(s), ok(s);
+    CK(sa.alloc((size_t)nsub)); CK(sb.alloc((size_t)nsub));
+    CK(he_a.alloc(hw)); CK(he_b.alloc(hw)); CK(hx_a.alloc(hw)); CK(hx_b.alloc(hw)); CK(ring.alloc(hw)); CK(ok.alloc((size_t)nsub));
+    CK(cudaMemsetAsync(he_a.p, 0, hw * 4, s)); CK(cudaMemsetAsync(hx_a.p, 0, hw * 4, s));
+    LAUNCH(k_bnd_init, grid_for(nsub, 128), 128, 0, s, sa.p, nsub, sub_bits, stream_bits);
+    BndSub *in = sa.p, *out = sb.p;
+    int32_t *he_in = he_a.p, *he_out = he_b.p, *hx_in = hx_a.p, *hx_out = hx_b.p;
+    std::vector<int32_t> h_ok((size_t)nsub);
+    int64_t trusted = 0;
+    for (int64_t pass = 0;; pass++) {
+        // 32 threads per block: a walk is one thread's serial work, spread them over all SMs
+        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
+        else LAUNCH(k_bnd_walk<false>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
+        LAUNCH(k_bnd_check, grid_for(nsub, 128), 128, 0, s, out, nsub, he_out, hx_out, W, ok.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_ok.data(), ok.p, (size_t)nsub * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::swap(in, out); std::swap(he_in, he_out); std::swap(hx_in, hx_out);
+        int64_t first_bad = nsub;
+        for (int64_t j = 0; j < nsub; j++) if (!h_ok[(size_t)j]) { first_bad = j; break; }
+        if (first_bad == nsub) break;   // every entry is the exit before it, and sub-range 0 starts at bit 0: proven
+        trusted = first_bad;
+        if (pass > nsub + 2) return BVG_EIO;  // cannot happen: every pass proves at least one more sub-range
+    }
+    std::vector<BndSub> h_sub((size_t)nsub);
+    CK(cudaMemcpyAsync(h_sub.data(), in, (size_t)nsub * sizeof(BndSub), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int64_t> base((size_t)nsub);
+    int64_t total = 0;
+    for (int64_t j = 0; j < nsub; j++) {
+        base[(size_t)j] = total;
+        const BndSub& b = h_sub[(size_t)j];
+        if (b.bad_pos != BND_UNKNOWN && total + b.bad_index < n) {  // a record of the graph itself does not parse
+            if (err_node) *err_node = (int32_t)(total + b.bad_index);
+            if (err_bitpos) *err_bitpos = (int64_t)b.bad_pos;
+            return BVG_EFORMAT;
+        }
+        total += b.count;
+    }
+    if (total < n) { if (err_node) *err_node = (int32_t)total; if (err_bitpos) *err_bitpos = (int64_t)stream_bits; return BVG_EIO; }  // the stream ends early
+    Tmp<int64_t> d_base(s);
+    CK(d_base.alloc((size_t)nsub));
+    CK(cudaMemcpyAsync(d_base.p, base.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
+    CK(dev_alloc((void**)d_full, ((size_t)n + 1) * 8, s));
+    if (total == n) {  // no padding bit after the last record: nobody tries to parse at its end
+        const uint64_t end = h_sub[(size_t)nsub - 1].exit;
+        CK(cudaMemcpyAsync(*d_full + n, &end, 8, cudaMemcpyHostToDevice, s));
+    }
+    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
+    else LAUNCH(k_bnd_emit<false>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));  // base and end are host memory
+    return BVG_OK;
+}
+
 // Index of the long records (bvg_long.cuh): list them, walk each once for sizes, lay out the arrays, walk again to fill
 // them, and list the per-scan work items.
 static int build_long_index(bvg_graph* g) {
@@ -731,7 +809,8 @@ extern "C" {
 int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                           int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                           uint32_t flags, int offset_type, int device, int32_t from, int32_t to, bvg_graph** out) {
-    if (!out || nodes < 0 || (!graph && graph_bytes) || !offsets_stream) return BVG_EINVAL;
+    if (!out || nodes < 0 || (!graph && graph_bytes)) return BVG_EINVAL;
+    if (!offsets_stream && offset_type > 0) return BVG_EINVAL;  // random access needs .offsets (BVGraph.java:1581-1609)
     if (from < 0 || to < from || to > nodes) return BVG_EINVAL;
     int dev;
     int dl[1] = { device };
@@ -748,8 +827,9 @@ int bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint
     const int oc = ((flags >> 20) & 0xF) ? (int)((flags >> 20) & 0xF) : C_GAMMA;
     Trace tr(g->stream);
     uint64_t* d_full = nullptr;
-    rc = device_decode_offsets(g->stream, offsets_stream, offsets_bytes, oc, nodes, &d_full);
-    tr.mark("device: decode .offsets");
+    if (offsets_stream) rc = device_decode_offsets(g->stream, offsets_stream, offsets_bytes, oc, nodes, &d_full);
+    else rc = device_offsets_from_graph(g->stream, graph, graph_bytes, g->codec, g->def_codec, nodes, &d_full, nullptr, nullptr);
+    tr.mark(offsets_stream ? "device: decode .offsets" : "device: record boundaries from .graph");
     if (rc) { dev_free(d_full, g->stream); destroy(g); return rc; }
     g->ext_from = from; g->ext_to = to;
     choose_long_threshold(g, from, to);
@@ -781,7 +861,7 @@ int bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
 int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                     int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                     uint32_t flags, int device, int32_t from, int32_t to, int pieces, int64_t* arcs_out, uint64_t* checksum_out) {
-    if (nodes < 0 || (!graph && graph_bytes) || !offsets_stream || pieces < 1) return BVG_EINVAL;
+    if (nodes < 0 || (!graph && graph_bytes) || pieces < 1) return BVG_EINVAL;
     if (from < 0 || to < from || to > nodes) return BVG_EINVAL;
     int dev;
     int dl[1] = { device };
@@ -807,7 +887,13 @@ int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
         cudaStreamDestroy(st[0]); cudaStreamDestroy(st[1]);
         cudaGetLastError();
     };
-    rc = device_decode_offsets(st[0], offsets_stream, offsets_bytes, oc, nodes, &d_full);
+    if (offsets_stream) rc = device_decode_offsets(st[0], offsets_stream, offsets_bytes, oc, nodes, &d_full);
+    else {  // no .offsets: record boundaries from the stream itself (the whole stream visits the device once more for that)
+        bvg_graph probe;
+        probe.flags = flags; probe.zetak = zetak; probe.window = window; probe.minlen = minlen;
+        rc = set_codec(&probe);
+        if (!rc) rc = device_offsets_from_graph(st[0], graph, graph_bytes, probe.codec, probe.def_codec, nodes, &d_full, nullptr, nullptr);
+    }
     if (rc) { cleanup(); return rc; }
     {   // bit-balanced cuts (as bvg_plan_shards), found on the device
         Tmp<int32_t> d_bounds(st[0]);
@@ -905,10 +991,12 @@ int bvg_open(const char* basename, int offset_type, const int* devices, int ndev
     if (rc) return rc;
     std::vector<uint8_t> graph, offs;
     if (!slurp_file(std::string(basename) + ".graph", graph)) return BVG_EIO;
-    // The GPU needs record boundaries for every node, so .offsets is read for every offset_type (the reference can
-    // also stream a graph without it, BVGraph.java:1267-1278; that sequential dependence has no GPU counterpart).
-    if (!slurp_file(std::string(basename) + ".offsets", offs)) return offset_type > 0 ? BVG_EIO : BVG_EUNSUPPORTED;
-    return bvg_open_memory(graph.data(), graph.size(), offs.data(), offs.size(), (int32_t)p.nodes, p.arcs, p.window, p.maxref,
+    // The GPU needs record boundaries for every node, so .offsets is read for every offset_type when it exists.  The
+    // reference streams a sequential / offline graph without it (offsetType <= 0, BVGraph.java:1516-1609, 1201-1213):
+    // then the boundaries are found from the .graph stream itself (bvg_boundaries.cuh).
+    const bool have_offsets = slurp_file(std::string(basename) + ".offsets", offs);
+    if (!have_offsets && offset_type > 0) return BVG_EIO;
+    return bvg_open_memory(graph.data(), graph.size(), have_offsets ? offs.data() : nullptr, offs.size(), (int32_t)p.nodes, p.arcs, p.window, p.maxref,
                            p.minlen, p.zetak, p.flags, offset_type, dev, out);
 }
 
