@@ -436,6 +436,27 @@ def main():
         except Exception as e:  # informational legs must never take the headline down
             extra["error"] = repr(e)
         g3.close()
+        # a graph that comes without .offsets (loadSequential / loadOffline in the reference, BVGraph.java:1581-1609): the
+        # record boundaries are found from the .graph stream on the device (bvg_boundaries.cuh); timed against the same
+        # open with .offsets, result checked by a scan
+        try:
+            def timed_open(offs_ptr, offs_len):
+                h = C.c_void_p()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                bvgraph._check(L.bvg_open_memory(graph_pin.data_ptr(), graph_pin.numel(), offs_ptr, offs_len, n_total, m_total,
+                                                 7, 3, 4, 3, 0, 0, local_rank, C.byref(h)))
+                torch.cuda.synchronize()
+                return BVGraph(h), (time.perf_counter() - t0) * 1e3
+            g4, with_ms = timed_open(offs_pin.data_ptr(), offs_pin.numel())
+            g4.close()
+            g4, without_ms = timed_open(None, 0)
+            ok = g4.scanRange(0, n_total) == (m_total, int(st["xor_checksum"]))
+            g4.close()
+            extra["open_without_offsets"] = {"ms": without_ms, "ms_with_offsets": with_ms, "scan_matches": bool(ok),
+                                             "what": "bvg_open_memory of the pinned .graph with offsets = NULL (offset_type 0): record boundaries from the stream alone, then the usual index build; beside the same open given .offsets"}
+        except Exception as e:
+            extra["open_without_offsets"] = {"error": repr(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

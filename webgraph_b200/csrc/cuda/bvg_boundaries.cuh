@@ -132,7 +132,7 @@ __device__ inline void bnd_walk(const uint32_t* __restrict__ words, uint64_t nwo
             continue;
         }
         if (s.bad_pos == BND_UNKNOWN) { s.bad_pos = pos; s.bad_index = s.count; }
-        if (st == 2) { pos = cap ? BND_UNKNOWN : stream_bits; break; }  // gave up / the stream ends inside a record
+        if (st == 2) { pos = stop == stream_bits ? stream_bits : BND_UNKNOWN; break; }  // the stream ends inside a record (padding bits after the last one, or a truncated file) / gave up at the cap
         pos++;
         reseek = true;
     }
