@@ -220,7 +220,10 @@ __global__ void k_bnd_walk(const uint32_t* __restrict__ words, uint64_t nwords, 
                            const int32_t* __restrict__ hist_entry_in, const int32_t* __restrict__ hist_exit_in,
                            int32_t* __restrict__ hist_entry_out, int32_t* __restrict__ hist_exit_out, int32_t* __restrict__ ring,
                            int pass, int64_t trusted, uint64_t cap) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one walk per WARP (lane 0): a walk is a chain of data-dependent branches, and 32 of them in one warp run one
+    // after the other (measured: 2.4 s instead of 0.3 s for the boundaries of the 1 B-arc graph)
+    if (threadIdx.x & 31) return;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j < nsub) bnd_pass_one<DEF>(j, words, nwords, stream_bits, c, in, out, hist_entry_in, hist_exit_in, hist_entry_out, hist_exit_out, ring, pass, trusted, cap);
 }
 
@@ -234,7 +237,8 @@ template <bool DEF>
 __global__ void k_bnd_emit(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, Codec c, int64_t nsub,
                            const BndSub* __restrict__ sub, const int32_t* __restrict__ hist_entry, int32_t* __restrict__ ring,
                            int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x & 31) return;  // one walk per warp, as in k_bnd_walk
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j < nsub) bnd_emit_one<DEF>(j, words, nwords, stream_bits, c, sub, hist_entry, ring, hist_scratch, base, n, starts);
 }
 #endif

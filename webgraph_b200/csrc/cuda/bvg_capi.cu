@@ -436,9 +436,9 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     std::vector<int32_t> h_ok((size_t)nsub);
     int64_t trusted = 0;
     for (int64_t pass = 0;; pass++) {
-        // 32 threads per block: a walk is one thread's serial work, spread them over all SMs
-        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
-        else LAUNCH(k_bnd_walk<false>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
+        // one walk per warp (see k_bnd_walk), two warps per block
+        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
+        else LAUNCH(k_bnd_walk<false>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
         LAUNCH(k_bnd_check, grid_for(nsub, 128), 128, 0, s, out, nsub, he_out, hx_out, W, ok.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ok.data(), ok.p, (size_t)nsub * 4, cudaMemcpyDeviceToHost, s));
@@ -446,6 +446,8 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
         std::swap(in, out); std::swap(he_in, he_out); std::swap(hx_in, hx_out);
         int64_t first_bad = nsub;
         for (int64_t j = 0; j < nsub; j++) if (!h_ok[(size_t)j]) { first_bad = j; break; }
+        if (getenv("BVG_TRACE")) fprintf(stderr, "[bvg] boundaries: pass %lld, %lld sub-ranges of %llu bits, first unproven %lld\n",
+                                         (long long)pass, (long long)nsub, (unsigned long long)sub_bits, (long long)first_bad);
         if (first_bad == nsub) break;   // every entry is the exit before it, and sub-range 0 starts at bit 0: proven
         trusted = first_bad;
         if (pass > nsub + 2) return BVG_EIO;  // cannot happen: every pass proves at least one more sub-range
@@ -474,8 +476,8 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
         const uint64_t end = h_sub[(size_t)nsub - 1].exit;
         CK(cudaMemcpyAsync(*d_full + n, &end, 8, cudaMemcpyHostToDevice, s));
     }
-    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
-    else LAUNCH(k_bnd_emit<false>, grid_for(nsub, 32), 32, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
+    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
+    else LAUNCH(k_bnd_emit<false>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // base and end are host memory
     return BVG_OK;
