@@ -581,8 +581,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // Every kind runs the same tight residual loop, preceded for records with intervals by a walk of the interval section
 // that folds its elements; stored records with intervals write their residuals right-aligned and merge the intervals in
 // front of them in a second walk (ScanExtras::iv_merge).
-template <int K, bool RING>
-__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
+template <int K, bool RING, int MINB = SCAN_BLOCKS_PER_SM>
+__global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
                               int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all, int items) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
     typedef typename std::conditional<RING, WinRing<SCAN_BLOCK>, Win>::type W;
