@@ -43,11 +43,56 @@ struct BndSub {
     int32_t capped;       // 1 = the last walk was capped (its entry was not known to be proven)
 };
 
+// Long residual runs are remembered: the position after `count` residual codes starting at `pos` is a function of the
+// stream alone, and the same run is walked in pass 0, again when its sub-range adopts its proven entry, and by the emit
+// step -- 0.2 s each time for the 858 018 residuals of the benchmark graph's largest record, all on one lane.  A small
+// open-addressing table in global memory, filled as runs are completed; a slot is published by its `ready` word.
+constexpr int64_t BND_MEMO_MIN = 8192;  // residuals from which a run is remembered
+constexpr int BND_MEMO_SLOTS = 1024;
+struct BndMemo {
+    unsigned long long pos;   // bit position of the first residual code, 0 = free slot (a record never starts with its residuals)
+    long long count;
+    unsigned long long end;
+    int ready;
+    int pad_;
+};
+
+__device__ inline bool bnd_memo_find(const BndMemo* memo, uint64_t pos, int64_t count, uint64_t& end) {
+    if (!memo) return false;
+    unsigned h = (unsigned)((pos * 0x9E3779B97F4A7C15ull) >> 54);  // 10 bits
+    for (int probe = 0; probe < 8; probe++, h = (h + 1) & (BND_MEMO_SLOTS - 1)) {
+        const volatile BndMemo* m = memo + h;
+        const unsigned long long p = m->pos;
+        if (p == 0) return false;
+        if (p == pos && m->ready) {
+            __threadfence();
+            if (m->count == count) { end = m->end; return true; }
+        }
+    }
+    return false;
+}
+
+__device__ inline void bnd_memo_put(BndMemo* memo, uint64_t pos, int64_t count, uint64_t end) {
+    if (!memo) return;
+    unsigned h = (unsigned)((pos * 0x9E3779B97F4A7C15ull) >> 54);
+    for (int probe = 0; probe < 8; probe++, h = (h + 1) & (BND_MEMO_SLOTS - 1)) {
+        BndMemo* m = memo + h;
+        const unsigned long long old = atomicCAS(&m->pos, 0ull, (unsigned long long)pos);
+        if (old == 0ull) {
+            m->count = count; m->end = end;
+            __threadfence();
+            *(volatile int*)&m->ready = 1;
+            return;
+        }
+        if (old == pos) return;  // somebody else is publishing (or has published) a run from the same position
+    }
+}
+
 // One record parsed for its length.  `ring` holds the outdegrees of the `window` records before it (record r back,
 // r = 1 the latest, at ring[(head + r - 1) % window]).  Returns 0 and the outdegree, 1 if the parse makes no sense, 2 if it
 // ran beyond `stop`.  Follows BVGraph.successors (:1044-1100) without producing anything.
 template <bool DEF>
-__device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const int32_t* ring, int32_t head, int32_t& d_out) {
+__device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const int32_t* ring, int32_t head, int32_t& d_out, BndMemo* memo) {
     const uint64_t d64 = Rd<DEF>::outdeg(b, c);
     if (b.pos() > stop) return 2;
     if (d64 > 0x7fffffffull) return 1;
@@ -94,11 +139,19 @@ __device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const
         }
         extra -= tot;
     }
+    const uint64_t run_pos = b.pos();
+    uint64_t run_end;
+    if (extra >= BND_MEMO_MIN && bnd_memo_find(memo, run_pos, extra, run_end)) {
+        if (run_end > stop) return 2;
+        b.seek(run_end);
+        return 0;
+    }
     for (int64_t i = 0; i < extra; i++) {  // :939-972, values not needed
         (void)Rd<DEF>::resid(b, c);
         if ((i & 7) == 7 && b.pos() > stop) return 2;
     }
     if (b.pos() > stop) return 2;
+    if (extra >= BND_MEMO_MIN) bnd_memo_put(memo, run_pos, extra, b.pos());
     return 0;
 }
 
@@ -109,7 +162,7 @@ __device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const
 template <bool DEF>
 __device__ inline void bnd_walk(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, const Codec& c, BndSub& s,
                                 const int32_t* hist_in, int32_t* ring, int32_t* hist_out, uint64_t cap,
-                                uint64_t* __restrict__ starts, int64_t ord_base, int64_t n) {
+                                uint64_t* __restrict__ starts, int64_t ord_base, int64_t n, BndMemo* memo) {
     const int32_t W = c.window;
     for (int32_t k = 0; k < W; k++) ring[k] = hist_in ? hist_in[k] : 0;
     int32_t head = 0;
@@ -124,7 +177,7 @@ __device__ inline void bnd_walk(const uint32_t* __restrict__ words, uint64_t nwo
         if (starts && !(reseek && pos != s.entry) && ord_base + s.count <= n) starts[ord_base + s.count] = pos;
         if (reseek) { b.seek(pos); reseek = false; }
         int32_t d = 0;
-        const int st = bnd_record<DEF>(b, c, stop, ring, head, d);
+        const int st = bnd_record<DEF>(b, c, stop, ring, head, d, memo);
         if (st == 0) {
             pos = b.pos();
             s.count++;
@@ -147,13 +200,24 @@ __device__ inline void bnd_pass_one(int64_t j, const uint32_t* __restrict__ word
                                     const BndSub* __restrict__ in, BndSub* __restrict__ out,
                                     const int32_t* __restrict__ hist_entry_in, const int32_t* __restrict__ hist_exit_in,
                                     int32_t* __restrict__ hist_entry_out, int32_t* __restrict__ hist_exit_out, int32_t* __restrict__ ring,
-                                    int pass, int64_t trusted, uint64_t cap) {
+                                    int pass, int64_t trusted, uint64_t cap, BndMemo* memo) {
     const int32_t W = c.window;
     BndSub s = in[j];
     const int32_t* he = hist_entry_in + j * W;
     bool walk = pass == 0;
     const int32_t* hin = nullptr;
+    bool proven_entry = j <= trusted;
     if (pass == 0) { s.entry = s.lo; }
+    else if (j > trusted && trusted >= 1 && in[trusted - 1].exit != BND_UNKNOWN && in[trusted - 1].exit >= s.lo) {
+        // the proven chain leaves sub-range trusted - 1 inside a record that reaches into (or beyond) this sub-range: every
+        // sub-range it covers learns its true entry in this one pass instead of one sub-range per pass
+        const BndSub& q = in[trusted - 1];
+        const int32_t* hq = hist_exit_in + (trusted - 1) * W;
+        bool same = q.exit == s.entry && !(s.capped && s.exit == BND_UNKNOWN);
+        for (int32_t k = 0; same && k < W; k++) same = hq[k] == he[k];
+        if (!same) { walk = true; s.entry = q.exit; hin = hq; }
+        proven_entry = true;
+    }
     else if (j > 0) {
         const BndSub& p = in[j - 1];
         // An exit beyond this whole sub-range is believed only from a proven sub-range: made-up outdegrees of wrong chains
@@ -177,7 +241,7 @@ __device__ inline void bnd_pass_one(int64_t j, const uint32_t* __restrict__ word
         s.exit = s.entry; s.count = 0; s.bad_pos = BND_UNKNOWN; s.bad_index = 0; s.walked = 1; s.capped = 0;
         for (int32_t k = 0; k < W; k++) hist_exit_out[j * W + k] = hin ? hin[k] : 0;
     } else {
-        bnd_walk<DEF>(words, nwords, stream_bits, c, s, hin, ring + j * (W > 0 ? W : 1), hist_exit_out + j * W, j <= trusted ? 0 : cap, nullptr, 0, 0);
+        bnd_walk<DEF>(words, nwords, stream_bits, c, s, hin, ring + j * (W > 0 ? W : 1), hist_exit_out + j * W, proven_entry ? 0 : cap, nullptr, 0, 0, memo);
     }
     out[j] = s;
 }
@@ -196,11 +260,11 @@ __device__ inline void bnd_check_one(int64_t j, const BndSub* __restrict__ sub, 
 template <bool DEF>
 __device__ inline void bnd_emit_one(int64_t j, const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, Codec c,
                                     const BndSub* __restrict__ sub, const int32_t* __restrict__ hist_entry, int32_t* __restrict__ ring,
-                                    int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts) {
+                                    int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo) {
     const int32_t W = c.window;
     BndSub s = sub[j];
     if (s.entry >= s.hi || s.entry >= stream_bits) return;
-    bnd_walk<DEF>(words, nwords, stream_bits, c, s, hist_entry + j * W, ring + j * (W > 0 ? W : 1), hist_scratch + j * W, 0, starts, base[j], n);
+    bnd_walk<DEF>(words, nwords, stream_bits, c, s, hist_entry + j * W, ring + j * (W > 0 ? W : 1), hist_scratch + j * W, 0, starts, base[j], n, memo);
 }
 
 #ifndef BVG_HOST_EMULATION
@@ -219,12 +283,12 @@ __global__ void k_bnd_walk(const uint32_t* __restrict__ words, uint64_t nwords, 
                            const BndSub* __restrict__ in, BndSub* __restrict__ out,
                            const int32_t* __restrict__ hist_entry_in, const int32_t* __restrict__ hist_exit_in,
                            int32_t* __restrict__ hist_entry_out, int32_t* __restrict__ hist_exit_out, int32_t* __restrict__ ring,
-                           int pass, int64_t trusted, uint64_t cap) {
+                           int pass, int64_t trusted, uint64_t cap, BndMemo* memo) {
     // one walk per WARP (lane 0): a walk is a chain of data-dependent branches, and 32 of them in one warp run one
     // after the other (measured: 2.4 s instead of 0.3 s for the boundaries of the 1 B-arc graph)
     if (threadIdx.x & 31) return;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j < nsub) bnd_pass_one<DEF>(j, words, nwords, stream_bits, c, in, out, hist_entry_in, hist_exit_in, hist_entry_out, hist_exit_out, ring, pass, trusted, cap);
+    if (j < nsub) bnd_pass_one<DEF>(j, words, nwords, stream_bits, c, in, out, hist_entry_in, hist_exit_in, hist_entry_out, hist_exit_out, ring, pass, trusted, cap, memo);
 }
 
 __global__ void k_bnd_check(const BndSub* __restrict__ sub, int64_t nsub, const int32_t* __restrict__ hist_entry,
@@ -236,10 +300,10 @@ __global__ void k_bnd_check(const BndSub* __restrict__ sub, int64_t nsub, const 
 template <bool DEF>
 __global__ void k_bnd_emit(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, Codec c, int64_t nsub,
                            const BndSub* __restrict__ sub, const int32_t* __restrict__ hist_entry, int32_t* __restrict__ ring,
-                           int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts) {
+                           int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo) {
     if (threadIdx.x & 31) return;  // one walk per warp, as in k_bnd_walk
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j < nsub) bnd_emit_one<DEF>(j, words, nwords, stream_bits, c, sub, hist_entry, ring, hist_scratch, base, n, starts);
+    if (j < nsub) bnd_emit_one<DEF>(j, words, nwords, stream_bits, c, sub, hist_entry, ring, hist_scratch, base, n, starts, memo);
 }
 #endif
 

@@ -427,6 +427,9 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     const size_t hw = (size_t)nsub * (size_t)std::max<int32_t>(W, 1);
     Tmp<BndSub> sa(s), sb(s);
     Tmp<int32_t> he_a(s), he_b(s), hx_a(s), hx_b(s), ring(s), ok(s);
+    Tmp<BndMemo> memo(s);
+    CK(memo.alloc(BND_MEMO_SLOTS));
+    CK(cudaMemsetAsync(memo.p, 0, BND_MEMO_SLOTS * sizeof(BndMemo), s));
     CK(sa.alloc((size_t)nsub)); CK(sb.alloc((size_t)nsub));
     CK(he_a.alloc(hw)); CK(he_b.alloc(hw)); CK(hx_a.alloc(hw)); CK(hx_b.alloc(hw)); CK(ring.alloc(hw)); CK(ok.alloc((size_t)nsub));
     CK(cudaMemsetAsync(he_a.p, 0, hw * 4, s)); CK(cudaMemsetAsync(hx_a.p, 0, hw * 4, s));
@@ -437,8 +440,8 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     int64_t trusted = 0;
     for (int64_t pass = 0;; pass++) {
         // one walk per warp (see k_bnd_walk), two warps per block
-        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
-        else LAUNCH(k_bnd_walk<false>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap);
+        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap, memo.p);
+        else LAUNCH(k_bnd_walk<false>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap, memo.p);
         LAUNCH(k_bnd_check, grid_for(nsub, 128), 128, 0, s, out, nsub, he_out, hx_out, W, ok.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ok.data(), ok.p, (size_t)nsub * 4, cudaMemcpyDeviceToHost, s));
@@ -476,8 +479,8 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
         const uint64_t end = h_sub[(size_t)nsub - 1].exit;
         CK(cudaMemcpyAsync(*d_full + n, &end, 8, cudaMemcpyHostToDevice, s));
     }
-    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
-    else LAUNCH(k_bnd_emit<false>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full);
+    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full, memo.p);
+    else LAUNCH(k_bnd_emit<false>, grid_for(nsub * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full, memo.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // base and end are host memory
     return BVG_OK;
