@@ -5,6 +5,7 @@
 #define BVG_HOST_EMULATION
 #include "../../webgraph_b200/csrc/cuda/bvg_scan.cuh"
 #include <vector>
+#include <cstdlib>
 using namespace bvg;
 
 template <int K>
@@ -12,6 +13,7 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
                     const std::vector<int32_t>& depth, int maxdepth, const std::vector<int64_t>& rowoff,
                     int32_t* rows, uint8_t* parent_flag, unsigned long long* out) {
     unsigned long long acc = 0, arcs = 0;
+    const bool v2 = getenv("EMU_SCAN_V2") && atoi(getenv("EMU_SCAN_V2")) != 0;  // ScanExtras::resid_v2 instead of resid
     std::vector<uint64_t> blocks_pos(n, 0);
     std::vector<int32_t> copied(n, 0), bcs(n, 0);
     for (int32_t x = 0; x < n; x++) if (ref[x]) parent_flag[x - ref[x]] = 1;
@@ -48,7 +50,8 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             ScanExtras<K, WinRing<1>> w;
             w.begin(g, x, nout, epos, true, ring_address(ring));
             if (has_iv) w.iv_fold(g); else w.iv_none(g);
-            if (store) w.template resid<true>(g, row, true); else w.template resid<false>(g, row, false);
+            if (v2) { if (store) w.template resid_v2<true>(g, row, true); else w.template resid_v2<false>(g, row, false); }
+            else { if (store) w.template resid<true>(g, row, true); else w.template resid<false>(g, row, false); }
             if (store && has_iv) w.iv_merge(g, row);
             if (w.err) return w.err;
             f = w.finish();

@@ -1353,10 +1353,10 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
     static const int dbg_nostore = env_int("BVG_DEBUG_NOSTORE", 0, 0, 1);  // timing experiments only: no row stores, results are wrong
     static const bool ring = env_int("BVG_SCAN_RING", 1, 0, 1) != 0;  // stream staged in shared memory by cp.async (bvg_scan.cuh, WinRing)
-    // BVG_EXTRAS_MINB / BVG_MERGE_MINB: resident blocks per SM the compiler is asked to allow (8 -> 64 registers, 10 -> 51, 12 -> 42)
-    static const int extras_minb = env_int("BVG_EXTRAS_MINB", 8, 8, 12);
-    if (g->def_codec && lean && g->zetak == 3 && ring && extras_minb == 10) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true, 10>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
-    else if (g->def_codec && lean && g->zetak == 3 && ring && extras_minb == 12) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true, 12>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
+    // BVG_SCAN_V2=1: the residual loop of ScanExtras::resid_v2 (unrolled by the topup period, selects instead of the refill
+    // branch, second zeta_3 formulation, 64-bit fold).  Off until measured against the default on the GPU.
+    static const bool scan_v2 = env_int("BVG_SCAN_V2", 0, 0, 1) != 0;
+    if (g->def_codec && lean && g->zetak == 3 && ring && scan_v2) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
@@ -1378,10 +1378,8 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             static const bool lean_m = !(getenv("BVG_MERGE_LEAN") && atoi(getenv("BVG_MERGE_LEAN")) == 0);
             // 8 resident blocks per SM (64 registers) and 4 parent loads in flight per lane: measured against 8/8, 6/8 and
             // 5/16 (blocks / batch): 1.92, 2.12, 2.19, 2.52 ms for the three levels -- occupancy beats deeper batching here
-            static const int merge_minb = env_int("BVG_MERGE_MINB", 8, 8, 12);
-            if (g->def_codec && lean_m && merge_minb == 10) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<10, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
-            else if (g->def_codec && lean_m && merge_minb == 12) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<12, 2>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
-            else if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            // (10 / 12 resident blocks, 48 / 40 registers: 1.89 -> 2.16 / 2.50 ms, spills)
+            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
             else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }

@@ -581,8 +581,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // Every kind runs the same tight residual loop, preceded for records with intervals by a walk of the interval section
 // that folds its elements; stored records with intervals write their residuals right-aligned and merge the intervals in
 // front of them in a second walk (ScanExtras::iv_merge).
-template <int K, bool RING, int MINB = SCAN_BLOCKS_PER_SM>
-__global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
+template <int K, bool RING, bool V2 = false>
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
                               int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all, int items) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
     typedef typename std::conditional<RING, WinRing<SCAN_BLOCK>, Win>::type W;
@@ -608,8 +608,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_extras_lean(GraphDev 
         w.begin(g, r.x, r.nout, r.pos, active, my_ring);
         if (has_iv) w.iv_fold(g); else w.iv_none(g);
         __syncwarp();
-        if (__any_sync(0xffffffffu, store)) w.template resid<true>(g, row, store);
-        else w.template resid<false>(g, row, false);
+        if (V2) {
+            if (__any_sync(0xffffffffu, store)) w.template resid_v2<true>(g, row, store);
+            else w.template resid_v2<false>(g, row, false);
+        } else {
+            if (__any_sync(0xffffffffu, store)) w.template resid<true>(g, row, store);
+            else w.template resid<false>(g, row, false);
+        }
         __syncwarp();
         if (store && has_iv) w.iv_merge(g, row);
         __syncwarp();

@@ -111,6 +111,7 @@ struct WinT {
             if (LA == 3) { q0 = q1; q1 = q2; q2 = p0[idx]; }
         }
     }
+    __device__ __forceinline__ void skip_sel(uint32_t n) { skip(n); }
     __device__ __forceinline__ uint64_t gamma_slow(const GraphDev& g) {
         uint64_t p = pos(g);
         const uint64_t r = slow_gamma(g.words, g.nwords, &p);
@@ -214,6 +215,17 @@ struct WinRing {
             q = word(r);
         }
     }
+    // The same written with selects (resid_v2): a refill branch is taken by about half of the lanes on every trip, so the
+    // warp pays for both sides of it almost always.
+    __device__ __forceinline__ void skip_sel(uint32_t n) {  // n <= 32
+        s += n;
+        const bool adv = s >= 32u;
+        s &= 31u;
+        w0 = adv ? w1 : w0;
+        w1 = adv ? q : w1;
+        r += adv ? 1u : 0u;
+        if (adv) q = word(r);
+    }
     __device__ __forceinline__ uint64_t gamma_slow(const GraphDev& g) {
         uint64_t p = pos(g);
         const uint64_t v = slow_gamma(g.words, g.nwords, &p);
@@ -236,6 +248,19 @@ struct WinRing {
         return gamma_slow(g);
     }
 };
+
+// zeta_3 code of at most 32 bits (t >= 2^24, i.e. h <= 7), second formulation (resid_v2): with r the top 4h + 4 bits of
+// the window and P8 = 8^(h+1) its leading one, u = r ^ P8 is what follows the leading one; the short form (4h + 3 bits)
+// holds iff u < P8 / 4, its value + 1 is u / 2 + P8 / 8, and the long form's is u.  Same results as zeta_fast<3>.
+__device__ __forceinline__ void zeta3_fast_v2(uint32_t t, uint32_t& m, uint32_t& len) {
+    const uint32_t h = (uint32_t)__clz((int)t);
+    const uint32_t r = t >> (28u - 4u * h);
+    const uint32_t P8 = 8u << (3u * h);
+    const uint32_t u = r ^ P8;
+    const bool sh = u < (P8 >> 2);
+    m = sh ? (u >> 1) + (P8 >> 3) : u;
+    len = 4u * h + (sh ? 3u : 4u);
+}
 
 // zeta_k code that fits the 32-bit window: m = value + 1, len = code length.  K = 3 is BVGraph's default and gets
 // constants; K = 0 takes k at run time.  With h = leading zeros, P = 2^(hk): the bits after the unary part, read with
@@ -377,6 +402,8 @@ struct ScanExtras {
     int err;
     uint32_t ic;       // intervals (iv_fold)
     uint64_t iv_pos;   // bit position of the first interval's left extreme
+    unsigned long long acc2;  // residuals folded by resid_v2 (plain 64-bit XOR of x*MIX + y), joined in finish()
+    uint32_t n_acc2;          // how many
 
     __device__ __forceinline__ void fail(const GraphDev& g, int code) {
         report(g.err, code, x, b.pos(g) + g.bit_base);
@@ -384,7 +411,7 @@ struct ScanExtras {
     }
 
     __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active, ring_addr ring_slot = ring_addr()) {
-        x = x_; nout = 0; rc = 0; err = 0; v = 0; ic = 0; iv_pos = 0;
+        x = x_; nout = 0; rc = 0; err = 0; v = 0; ic = 0; iv_pos = 0; acc2 = 0; n_acc2 = 0;
         f.begin(x_);
         b.attach(ring_slot);
         if (!active) return;
@@ -479,9 +506,65 @@ struct ScanExtras {
         if (b.overrun() || b.pos(g) > g.bit_end - g.bit_base) fail(g, E_IO);
     }
 
+    // The residual loop rewritten for the instruction count (BVG_SCAN_V2=1; measured against resid() on the GPU before it
+    // becomes the default): four codes between two topups in an unrolled body (no per-code topup test, a quarter of the
+    // loop overhead), the window advanced with selects (skip_sel), the second formulation of the zeta_3 decode, and the
+    // checksum as a plain 64-bit add + XOR (the residuals' share of n is taken out of the 32-bit fold in finish()).
+    template <bool STORE>
+    __device__ __forceinline__ void resid_v2(const GraphDev& g, int32_t* __restrict__ row, bool store) {
+        if (rc <= 0) return;
+        const int k = g.c.zetak;
+        const unsigned long long base = (unsigned long long)(uint32_t)x * BVG_MIX;
+        unsigned long long acc = 0;
+        b.topup();
+        v = (uint32_t)(int32_t)((int64_t)x + nat2int(zeta_any<K>(b, g, k) - 1ull));  // :954
+        acc ^= base + v;
+        RowWriter<true> wr;
+        if (STORE) wr.begin(row + (nout - rc));
+        if (STORE && store) wr.put(v);
+        // Groups of up to four codes between two topups; a code that does not fit the 32-bit window ends its group and is
+        // read by the one out-of-line-sized step below (a single copy of the slow path in the loop).
+        int32_t i = 1;
+#pragma unroll 1
+        while (i < rc) {
+            b.topup();  // at most four words are consumed before the next one
+            const int32_t left = rc - i;
+            bool slow = false;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (!slow && u < left) {
+                    const uint32_t t = b.top();
+                    uint32_t m, len;
+                    bool fast;
+                    if (K == 3) { fast = t >= 0x1000000u; if (fast) zeta3_fast_v2(t, m, len); }
+                    else fast = zeta_fast<K>(t, k, m, len);
+                    if (fast) {
+                        b.skip_sel(len);
+                        v += m;  // :966 (gap + 1)
+                        acc ^= base + v;
+                        if (STORE && store) wr.put(v);
+                        i++;
+                    } else slow = true;
+                }
+            }
+            if (slow) {  // gap >= 2^24: up to two words, between two out-of-turn topups
+                b.topup();
+                v += (uint32_t)zeta_any<K>(b, g, k);
+                b.topup();
+                acc ^= base + v;
+                if (STORE && store) wr.put(v);
+                i++;
+            }
+        }
+        if (STORE && store) wr.flush();
+        acc2 ^= acc;
+        n_acc2 += (uint32_t)rc;  // folded here, not in the 32-bit halves
+        if (b.overrun() || b.pos(g) > g.bit_end - g.bit_base) fail(g, E_IO);
+    }
+
     __device__ __forceinline__ unsigned long long finish() {
-        f.n = (uint32_t)nout;
-        return err ? 0ull : f.finish(x);
+        f.n = (uint32_t)nout - n_acc2;  // n_acc2, acc2: successors resid_v2 folded on its own (0 with resid())
+        return err ? 0ull : f.finish(x) ^ acc2;
     }
 };
 
