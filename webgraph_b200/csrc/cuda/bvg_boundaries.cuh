@@ -283,11 +283,13 @@ __global__ void k_bnd_walk(const uint32_t* __restrict__ words, uint64_t nwords, 
                            const BndSub* __restrict__ in, BndSub* __restrict__ out,
                            const int32_t* __restrict__ hist_entry_in, const int32_t* __restrict__ hist_exit_in,
                            int32_t* __restrict__ hist_entry_out, int32_t* __restrict__ hist_exit_out, int32_t* __restrict__ ring,
-                           int pass, int64_t trusted, uint64_t cap, BndMemo* memo) {
-    // one walk per WARP (lane 0): a walk is a chain of data-dependent branches, and 32 of them in one warp run one
-    // after the other (measured: 2.4 s instead of 0.3 s for the boundaries of the 1 B-arc graph)
-    if (threadIdx.x & 31) return;
-    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                           int pass, int64_t trusted, uint64_t cap, BndMemo* memo, int lanes) {
+    // `lanes` walks per warp (default 1, lane 0 only; BVG_BND_LANES).  With 32 walks per warp there are too few warps to
+    // hide latency and the walks of a warp diverge (2.4 s for the 1 B-arc graph); with one, every issue slot serves a
+    // single lane (1.15 s).  The walks run the same loops, so a few per warp should converge most of the time.
+    const int lane = threadIdx.x & 31;
+    if (lane >= lanes) return;
+    const int64_t j = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane;
     if (j < nsub) bnd_pass_one<DEF>(j, words, nwords, stream_bits, c, in, out, hist_entry_in, hist_exit_in, hist_entry_out, hist_exit_out, ring, pass, trusted, cap, memo);
 }
 
@@ -300,9 +302,10 @@ __global__ void k_bnd_check(const BndSub* __restrict__ sub, int64_t nsub, const 
 template <bool DEF>
 __global__ void k_bnd_emit(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, Codec c, int64_t nsub,
                            const BndSub* __restrict__ sub, const int32_t* __restrict__ hist_entry, int32_t* __restrict__ ring,
-                           int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo) {
-    if (threadIdx.x & 31) return;  // one walk per warp, as in k_bnd_walk
-    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                           int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo, int lanes) {
+    const int lane = threadIdx.x & 31;  // `lanes` walks per warp, as in k_bnd_walk
+    if (lane >= lanes) return;
+    const int64_t j = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane;
     if (j < nsub) bnd_emit_one<DEF>(j, words, nwords, stream_bits, c, sub, hist_entry, ring, hist_scratch, base, n, starts, memo);
 }
 #endif
