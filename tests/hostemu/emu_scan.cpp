@@ -14,6 +14,7 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
                     int32_t* rows, uint8_t* parent_flag, unsigned long long* out) {
     unsigned long long acc = 0, arcs = 0;
     const bool v2 = getenv("EMU_SCAN_V2") && atoi(getenv("EMU_SCAN_V2")) != 0;  // ScanExtras::resid_v2 instead of resid
+    const bool merge_v2 = getenv("EMU_MERGE_V2") && atoi(getenv("EMU_MERGE_V2")) != 0;  // copied_fold_v2 instead of copied_fold
     std::vector<uint64_t> blocks_pos(n, 0);
     std::vector<int32_t> copied(n, 0), bcs(n, 0);
     for (int32_t x = 0; x < n; x++) if (ref[x]) parent_flag[x - ref[x]] = 1;
@@ -67,6 +68,7 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             c.begin(g, blocks_pos[x], bcs[x], outdeg[px], slots, 1, true);
             c.stage(g);
             if (parent_flag[x]) acc ^= copied_merge(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
+            else if (merge_v2) acc ^= copied_fold_v2<2>(g, c, x, rows + rowoff[px]);
             else acc ^= copied_fold<8>(g, c, x, rows + rowoff[px]);
         }
     out[0] = arcs; out[1] = acc;

@@ -207,11 +207,12 @@ def _emu_scan(emu, oracle, base):
     return int(parent.sum())
 
 
-@pytest.mark.parametrize("v2", [0, 1])  # 1: the alternative residual loop ScanExtras::resid_v2 (BVG_SCAN_V2)
+@pytest.mark.parametrize("v2", [0, 1, 2])  # 1: the alternative residual loop ScanExtras::resid_v2 (BVG_SCAN_V2); 2: copied_fold_v2 (BVG_MERGE_V2)
 def test_emulated_fused_scan(emu, oracle, tmp_path, monkeypatch, v2):
     """k_scan_extras_lean / k_scan_merge logic (bvg_scan.cuh) record by record on the host: checksum == oracle's scan,
     parents' rows == oracle's lists."""
-    monkeypatch.setenv("EMU_SCAN_V2", str(v2))
+    monkeypatch.setenv("EMU_SCAN_V2", "1" if v2 == 1 else "0")
+    monkeypatch.setenv("EMU_MERGE_V2", "1" if v2 == 2 else "0")
     assert _emu_scan(emu, oracle, CNR) > 1000
     for k, w, r, ml in [(3, 7, 3, 4), (3, 7, 3, 0), (2, 1, 1, 2), (5, 16, 10, 3), (1, 3, 2, 4)]:
         off, succ, _ = graphs.copy_heavy(2000, seed=5 + k + ml)

@@ -1380,7 +1380,11 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             // 8 resident blocks per SM (64 registers) and 4 parent loads in flight per lane: measured against 8/8, 6/8 and
             // 5/16 (blocks / batch): 1.92, 2.12, 2.19, 2.52 ms for the three levels -- occupancy beats deeper batching here
             // (10 / 12 resident blocks, 48 / 40 registers: 1.89 -> 2.16 / 2.50 ms, spills)
-            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            // BVG_MERGE_V2=1: consumed-only children read their parent's row in aligned 16-byte groups (copied_fold_v2).
+            // Off until measured against the default on the GPU.
+            static const bool merge_v2 = env_int("BVG_MERGE_V2", 0, 0, 1) != 0;
+            if (g->def_codec && lean_m && merge_v2) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4, true>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            else if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
             else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(G
 }
 
 // Merge step with the staged copy runs of bvg_scan.cuh (default codings).
-template <int MINB, int BATCH>
+template <int MINB, int BATCH, bool V2 = false>
 __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int store_all) {
     __shared__ int32_t runs[2 * COPY_RUNS * SCAN_BLOCK];
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g
         __syncwarp();
         const int32_t* parent = active ? rm.at(r.px, r.prow) : nullptr;
         unsigned long long f = 0;
-        if (active && !store) f = copied_fold<BATCH>(g, c, r.x, parent);
+        if (active && !store) f = V2 ? copied_fold_v2<2>(g, c, r.x, parent) : copied_fold<BATCH>(g, c, r.x, parent);
         __syncwarp();
         if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
         __syncwarp();

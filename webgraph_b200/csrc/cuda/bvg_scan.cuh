@@ -18,6 +18,7 @@
 namespace bvg {
 
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // Codes that do not fit the 32-bit window go through the position-based reader, out of line: they are rare (gaps >= 2^24
 // for zeta_3, values >= 2^16 - 1 for gamma) and inlining them at every call site triples the size of the hot loops.
@@ -613,6 +614,18 @@ struct CopyRuns {
         }
     }
     __device__ __forceinline__ bool done() const { return pos == end && r == nr && bi > bc; }
+    // next run [s, e) of parent positions as a whole (copied_fold_v2); false when the list is exhausted
+    __device__ __forceinline__ bool next_run(const GraphDev& g, uint32_t& s, uint32_t& e) {
+        if (r == nr) {
+            if (bi > bc) return false;
+            stage(g);
+            if (nr == 0) return false;
+        }
+        s = (uint32_t)st[2 * r * stride];
+        e = (uint32_t)st[(2 * r + 1) * stride];
+        r++;
+        return true;
+    }
     // next parent position to copy; false when the list is exhausted
     __device__ __forceinline__ bool next(const GraphDev& g, uint32_t& at) {
         if (pos == end) {
@@ -649,6 +662,55 @@ __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, Cop
 #pragma unroll
         for (int u = 0; u < BATCH; u++) if (has[u]) { f.add(val[u]); f.n++; }
         if (!more) break;
+    }
+    return f.finish(x);
+}
+
+// The same with the parent's row read in aligned 16-byte groups (BVG_MERGE_V2=1; to be measured against copied_fold on
+// the GPU before it becomes the default).  copied_fold issues one 4-byte load per copied successor; the merge kernels are
+// latency-bound on exactly those loads (IPC 1.2-1.4, long-scoreboard stall 10-12 warps per issue).  Copy runs are short
+// and close together, so here the row is streamed group by group from the first copied position on -- four successors
+// per load, NG loads in flight -- and every slot is tested against the current run; groups that lie wholly inside a
+// skipped block are jumped over.  Slots are counted from the 16-byte boundary at or before the row (slot = position +
+// mis), so the slots in front of the row and behind it belong to neighbouring rows: they are loaded and ignored, and they
+// never leave the allocation (rows live in library-owned buffers: 512-byte aligned, sizes rounded up to 512 bytes).
+template <int NG>
+__device__ __forceinline__ unsigned long long copied_fold_v2(const GraphDev& g, CopyRuns& c, int32_t x, const int32_t* __restrict__ parent) {
+    Fold32 f;
+    f.begin(x);
+    uint32_t rs, re;
+    if (!c.next_run(g, rs, re)) return f.finish(x);
+    const uint32_t mis = (uint32_t)(((uintptr_t)parent) >> 2) & 3u;
+    const uint32_t glast = (c.dp + mis - 1u) >> 2;  // dp >= 1: a run exists
+    rs += mis; re += mis;                           // slot space
+    uint32_t gi = rs >> 2;
+    bool more = true;
+#pragma unroll 1
+    while (more) {
+        uint32_t val[4 * NG];
+#pragma unroll
+        for (int u = 0; u < NG; u++) {
+            const uint32_t gq = umin32(gi + (uint32_t)u, glast);
+#ifdef BVG_HOST_EMULATION
+            for (int e = 0; e < 4; e++) {  // element-wise and guarded: the emulated rows are not padded to 16 bytes
+                const int64_t idx = (int64_t)gq * 4 + e - (int64_t)mis;
+                val[4 * u + e] = idx >= 0 && idx < (int64_t)c.dp ? (uint32_t)parent[idx] : 0xdeadbeefu;
+            }
+#else
+            const uint4 q = *(reinterpret_cast<const uint4*>(parent - mis) + gq);
+            val[4 * u + 0] = q.x; val[4 * u + 1] = q.y; val[4 * u + 2] = q.z; val[4 * u + 3] = q.w;
+#endif
+        }
+#pragma unroll
+        for (int t = 0; t < 4 * NG; t++) {
+            const uint32_t slot = gi * 4u + (uint32_t)t;
+            if (more && slot >= re) {  // the run ended at the slot before: the next one starts at least one slot further on
+                more = c.next_run(g, rs, re);
+                rs += mis; re += mis;
+            }
+            if (more && slot >= rs) { f.add(val[t]); f.n++; }
+        }
+        gi = umax32(gi + (uint32_t)NG, rs >> 2);
     }
     return f.finish(x);
 }
