@@ -146,8 +146,9 @@ __device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const
         b.seek(run_end);
         return 0;
     }
-    for (int64_t i = 0; i < extra; i++) {  // :939-972, values not needed
-        (void)Rd<DEF>::resid(b, c);
+    if (extra > 0) (void)Rd<DEF>::resid(b, c);  // :939-972, values not needed; the first residual is often a long code
+    for (int64_t i = 1; i < extra; i++) {
+        (void)Rd<DEF>::gap(b, c);               // the 32-bit fast path of the default zeta codes, else the same reader
         if ((i & 7) == 7 && b.pos() > stop) return 2;
     }
     if (b.pos() > stop) return 2;
