@@ -67,7 +67,8 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             CopyRuns c;
             c.begin(g, blocks_pos[x], bcs[x], outdeg[px], slots, 1, true);
             c.stage(g);
-            if (parent_flag[x]) acc ^= copied_merge(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
+            if (parent_flag[x] && merge_v2) acc ^= copied_merge_v2<2>(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
+            else if (parent_flag[x]) acc ^= copied_merge(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
             else if (merge_v2) acc ^= copied_fold_v2<2>(g, c, x, rows + rowoff[px]);
             else acc ^= copied_fold<8>(g, c, x, rows + rowoff[px]);
         }

@@ -676,7 +676,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g
         unsigned long long f = 0;
         if (active && !store) f = V2 ? copied_fold_v2<2>(g, c, r.x, parent) : copied_fold<BATCH>(g, c, r.x, parent);
         __syncwarp();
-        if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
+        if (store) f = V2 ? copied_merge_v2<2>(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent)
+                          : copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
         __syncwarp();
         if (fold) acc ^= f;
     }

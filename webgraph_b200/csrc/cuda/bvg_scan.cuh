@@ -754,6 +754,72 @@ __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, Co
     return f.finish(x);
 }
 
+// copied_merge with the parent's row read in aligned 16-byte groups, as copied_fold_v2 does (BVG_MERGE_V2=1).  The merge is
+// driven by the parent's side: for every copied successor a, the own extras below a are moved down first, then a itself
+// (equal heads once).  copied_merge pays one dependent load round trip per copied successor -- c.next(), parent[at],
+// compare -- with nothing in flight; here NG groups are.  Same in-place argument: the write index never overtakes the
+// unread extras while the parent yields no more than `copied` successors, and every write is bounded by d.
+template <int NG>
+__device__ __forceinline__ unsigned long long copied_merge_v2(const GraphDev& g, CopyRuns& c, int32_t x, int32_t d, int32_t copied,
+                                                              int32_t* row, const int32_t* __restrict__ parent) {
+    Fold32 f;
+    f.begin(x);
+    int32_t j = copied, k = 0;
+    uint32_t bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
+    uint32_t rs, re;
+    bool more = c.next_run(g, rs, re);
+    if (more) {
+        const uint32_t mis = (uint32_t)(((uintptr_t)parent) >> 2) & 3u;
+        const uint32_t glast = (c.dp + mis - 1u) >> 2;
+        rs += mis; re += mis;
+        uint32_t gi = rs >> 2;
+#pragma unroll 1
+        while (more) {
+            uint32_t val[4 * NG];
+#pragma unroll
+            for (int u = 0; u < NG; u++) {
+                const uint32_t gq = umin32(gi + (uint32_t)u, glast);
+#ifdef BVG_HOST_EMULATION
+                for (int e = 0; e < 4; e++) {
+                    const int64_t idx = (int64_t)gq * 4 + e - (int64_t)mis;
+                    val[4 * u + e] = idx >= 0 && idx < (int64_t)c.dp ? (uint32_t)parent[idx] : 0xdeadbeefu;
+                }
+#else
+                const uint4 q = *(reinterpret_cast<const uint4*>(parent - mis) + gq);
+                val[4 * u + 0] = q.x; val[4 * u + 1] = q.y; val[4 * u + 2] = q.z; val[4 * u + 3] = q.w;
+#endif
+            }
+#pragma unroll
+            for (int t = 0; t < 4 * NG; t++) {
+                const uint32_t slot = gi * 4u + (uint32_t)t;
+                if (more && slot >= re) {
+                    more = c.next_run(g, rs, re);
+                    rs += mis; re += mis;
+                }
+                if (more && slot >= rs) {
+                    const uint32_t a = val[t];
+                    while (bv < a && k < d) {  // own extras below a (bv is 0xffffffff once they are used up)
+                        row[k++] = (int32_t)bv;
+                        j++;
+                        bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
+                    }
+                    if (k < d) {
+                        row[k++] = (int32_t)a;
+                        f.add(a); f.n++;
+                        if (a == bv) { j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; }  // equal heads are emitted once
+                    } else more = false;  // a malformed record copies more than its outdegree: stop, the checksum will tell
+                }
+            }
+            gi = umax32(gi + (uint32_t)NG, rs >> 2);
+        }
+    }
+    if (k != j) {  // duplicates were dropped: move the remaining extras down and pad (BVGraph.java:1210)
+        while (j < d && k < d) row[k++] = row[j++];
+        while (k < d) row[k++] = -1;
+    }
+    return f.finish(x);
+}
+
 #ifndef BVG_HOST_EMULATION
 // Blocks of the scan kernels fold into FOLD_SLOTS slot pairs (arcs, XOR) instead of two hot words; k_reduce_slots sums them.
 constexpr int FOLD_SLOTS = 1024;
