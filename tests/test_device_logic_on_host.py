@@ -26,17 +26,19 @@ def _find_asan():
 def emu():
     cuda_dir = os.path.join(ROOT, "webgraph_b200", "csrc", "cuda")
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "emu_offsets.cpp"),
-            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "emu_boundaries.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
+            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "emu_boundaries.cpp"), os.path.join(EMU_DIR, "emu_iterators.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
             os.path.join(cuda_dir, "bvg_offsets.cuh"), os.path.join(cuda_dir, "bvg_scan.cuh"), os.path.join(cuda_dir, "bvg_boundaries.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
         # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
-                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2], srcs[3], srcs[4]])
+                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2], srcs[3], srcs[4], srcs[5]])
     lib = C.CDLL(EMU)
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
     lib.emu_decode_offsets.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
     lib.emu_boundaries.argtypes = [C.c_void_p, C.c_uint64, C.c_int64] + [C.c_int] * 9 + [C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    lib.emu_masked.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
+                               C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_ulonglong)]
     lib.emu_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_stream_fold.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
@@ -237,3 +239,93 @@ def test_emulated_fused_scan(emu, oracle, tmp_path, monkeypatch, v2):
         base = str(tmp_path / ("big%d" % k))
         tools.store_csr(base, off2, succ2, zetak=k)
         _emu_scan(emu, oracle, base)
+
+
+MIX = 0x9E3779B97F4A7C15
+
+
+def _fold(x, ys):
+    acc = 0
+    for y in ys:
+        acc ^= (x * MIX + int(y)) & (2 ** 64 - 1)
+    return acc
+
+
+def _masked(emu, parent, blocks, extras, copied, x, variant):
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    blocks = np.ascontiguousarray(blocks, dtype=np.int32)
+    extras = np.ascontiguousarray(extras, dtype=np.int32)
+    out = np.full(len(parent) + len(extras) + 8, -555, dtype=np.int32)
+    n, f = C.c_int32(0), C.c_ulonglong(0)
+    rc = emu.emu_masked(parent.ctypes.data, len(parent), blocks.ctypes.data, len(blocks), extras.ctypes.data, len(extras), copied, x,
+                        variant, out.ctypes.data, C.byref(n), C.byref(f))
+    assert rc == 0
+    return out[:n.value].tolist(), f.value
+
+
+def test_masked_iterator_like_the_reference(emu):
+    """MaskedIntIteratorTest.test (reference test/it/unimi/dsi/webgraph/MaskedIntIteratorTest.java:32-110): every
+    (length, number of dropped elements) up to 19 x 19, the mask given as the alternating block lengths
+    MaskedIntIterator takes (MaskedIntIterator.java:65-97: first block copied, possibly empty; an even number of blocks
+    keeps the tail), here through the staged copy runs of the scan kernels -- pulled one by one, folded, folded with
+    16-byte group reads -- which must agree with the filter computed directly."""
+    rng = np.random.default_rng(20)
+    for length in range(20):
+        for zeros in range(20):
+            x = np.cumsum(rng.integers(1, 1000, length)).astype(np.int32)
+            keep = np.zeros(length, dtype=bool)
+            keep[:max(0, length - zeros)] = True
+            rng.shuffle(keep)
+            expected = x[keep].tolist()
+            blocks, look, curr = [], True, 0
+            for i in range(length):
+                if keep[i] == look:
+                    curr += 1
+                else:
+                    blocks.append(curr)
+                    look = not look
+                    curr = 1
+            got, _ = _masked(emu, x, blocks, [], 0, 7, 0)
+            assert got == expected, (length, zeros, blocks)
+            for variant in (1, 2):
+                _, f = _masked(emu, x, blocks, [], 0, 12345, variant)
+                assert f == _fold(12345, expected), (length, zeros, blocks, variant)
+
+
+def test_merged_iterator_like_the_reference(emu):
+    """MergedIntIteratorTest.testMerge (reference test/.../MergedIntIteratorTest.java:31-66): the ascending union of two
+    ascending lists, an element present in both emitted once (MergedIntIterator.java:50-74) -- here the in-place merge
+    of a record's copied successors with its extras (copied_merge / copied_merge_v2); what the union loses to
+    duplicates is padded with -1, as BVGraphNodeIterator leaves it (BVGraph.java:1210)."""
+    rng = np.random.default_rng(21)
+    for i in range(10):
+        for n0, n1 in ((i, i), (i, i + 1), (i, i * 2), (i + 1, i), (i * 2, i), (i * 7, i * 5)):
+            a = sorted(set(np.cumsum(rng.integers(0, 10, n0)).tolist()))   # the reference builds sets of the two lists
+            b = sorted(set(np.cumsum(rng.integers(0, 10, n1)).tolist()))
+            union = sorted(set(a) | set(b))
+            for variant in (3, 4):
+                got, f = _masked(emu, a, [], b, len(a), 99, variant)  # no blocks: the whole parent is copied
+                assert got[:len(union)] == union and all(v == -1 for v in got[len(union):]), (a, b, variant)
+                assert len(got) == len(a) + len(b)
+                assert f == _fold(99, a), (a, b, variant)  # the copied successors are folded here, the extras where they are decoded
+    # and both at once: a mask over the parent, extras in between
+    for trial in range(200):
+        dp = int(rng.integers(1, 60))
+        parent = np.cumsum(rng.integers(1, 9, dp)).astype(np.int32)
+        keep = rng.random(dp) < rng.random()
+        blocks, look, curr = [], True, 0
+        for t in range(dp):
+            if keep[t] == look:
+                curr += 1
+            else:
+                blocks.append(curr)
+                look = not look
+                curr = 1
+        copied = parent[keep].tolist()
+        pool = sorted(set(range(int(parent[-1]) + 20)) - set(copied))
+        extras = sorted(rng.choice(pool, size=min(len(pool), int(rng.integers(0, 30))), replace=False).tolist())
+        union = sorted(copied + extras)
+        for variant in (3, 4):
+            got, f = _masked(emu, parent, blocks, extras, len(copied), 5, variant)
+            assert got == union, (trial, variant)
+            assert f == _fold(5, copied)
