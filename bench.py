@@ -151,6 +151,13 @@ def cpu_port_baseline(base, sample_arcs, threads):
     return arcs, dt, hi
 
 
+def workload_name(n_gpus):
+    """config.workload, the same string on both arms (BASELINE configs C3 / C5)."""
+    if n_gpus <= 1:
+        return "C3: consume-only sequential scan of a 1 B-arc synthetic power-law BVGraph (zeta_3, W=7, R=3, minLen=4)"
+    return "C5: the C3 graph range-sharded over %d GPUs (bit-balanced node ranges), NCCL all-gather of boundary reference lists per step" % n_gpus
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's algorithm on the box's host cores.  The reference is Java and no JVM/JAR exists
     in this image, so this is the oracle port (oracle/, pinned on the reference's cnr-2000 golden pair) split over all
@@ -172,8 +179,11 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "sequential scan (nodeIterator) of a synthetic power-law BVGraph, zeta_3 W=7 R=3 minLen=4",
-                       "nodes": st["nodes"], "arcs": st["arcs"], "bits_per_arc": st["graph_bits"] / max(st["arcs"], 1)},
+            "config": {"workload": workload_name(args.gpus),
+                       "nodes": st["nodes"], "arcs": st["arcs"], "bits_per_arc": st["graph_bits"] / max(st["arcs"], 1),
+                       "graph_bytes": (int(st["graph_bits"]) + 7) // 8, "max_outdegree": st["max_outdegree"], "seed": args.seed,
+                       "generator": "webgraph_b200.tools.generate_store (SURVEY 8d)",
+                       "mode": "the same graph scanned by the CPU port of BVGraph.nodeIterator() (every successor consumed, arcs + XOR checksum)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "first %d nodes (%d arcs) per step, all host threads, node ranges split like splitNodeIterators" % (hi, arcs)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -468,8 +478,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
-                "config": {"workload": "C3: consume-only sequential scan of a 1 B-arc synthetic power-law BVGraph (zeta_3, W=7, R=3, minLen=4)" if world == 1
-                           else "C5: the C3 graph range-sharded over %d GPUs (bit-balanced node ranges), NCCL all-gather of boundary reference lists per step" % world,
+                "config": {"workload": workload_name(world),
                            "nodes": n_total, "arcs": m_total, "bits_per_arc": st["graph_bits"] / max(m_total, 1),
                            "graph_bytes": (int(st["graph_bits"]) + 7) // 8, "avg_ref_chain": st["tot_ref"] / max(n_total, 1),
                            "max_outdegree": st["max_outdegree"], "seed": args.seed, "generator": "webgraph_b200.tools.generate_store (SURVEY 8d)",
