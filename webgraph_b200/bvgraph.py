@@ -138,6 +138,33 @@ def _check(rc, g=None):
     raise RuntimeError("bvg status %d: %s" % (rc, msg))
 
 
+def immutable_graph_hash(off, succ, first_node=0):
+    """ImmutableGraph.hashCode (ImmutableGraph.java:755-769) of a graph given as CSR: h = -1, then per node h = 31 h + x
+    followed by its successors in REVERSE order, in 32-bit wrap-around arithmetic; returned as a Java int."""
+    off = np.asarray(off, dtype=np.int64)
+    n, m = len(off) - 1, int(off[-1] - off[0])
+    seq = np.empty(n + m, dtype=np.uint32)
+    d = np.diff(off)
+    node_pos = np.arange(n, dtype=np.int64) + (off[:-1] - off[0])  # where node x sits in the sequence
+    seq[node_pos] = (np.arange(n, dtype=np.int64) + first_node).astype(np.uint32)
+    if m:
+        # successor j of node x (0-based) goes to node_pos[x] + d[x] - j
+        owner = np.repeat(np.arange(n, dtype=np.int64), d)
+        j = np.arange(m, dtype=np.int64) - np.repeat(off[:-1] - off[0], d)
+        seq[node_pos[owner] + d[owner] - j] = np.asarray(succ[:m] if off[0] == 0 else succ[off[0]:off[-1]], dtype=np.int64).astype(np.uint32)
+    # h = (-1) 31^L + sum seq[i] 31^(L-1-i)  (mod 2^32)
+    L = n + m
+    pw = np.ones(L + 1, dtype=np.uint32)
+    if L:
+        pw[1:] = 31
+        pw = np.cumprod(pw, dtype=np.uint32)  # pw[k] = 31^k mod 2^32
+    h = (np.uint64(0xFFFFFFFF) * np.uint64(pw[L])) & np.uint64(0xFFFFFFFF)
+    if L:
+        h = (h + np.uint64(np.sum(seq.astype(np.uint64) * pw[L - 1::-1][:L].astype(np.uint64) & np.uint64(0xFFFFFFFF), dtype=np.uint64))) & np.uint64(0xFFFFFFFF)
+    h = int(h)
+    return h - (1 << 32) if h >= (1 << 31) else h
+
+
 class LazyIntIterator:
     """LazyIntIterator over a decoded successor array (LazyIntIterators.wrap, LazyIntIterators.java:151-154)."""
 
@@ -271,6 +298,11 @@ class ImmutableGraph:
             it = self.nodeIterator(frm).copy(min(n, frm + per)) if frm else self.nodeIterator(0).copy(min(n, per))
             out.append(it)
         return out
+
+    def hashCode(self):
+        """ImmutableGraph.hashCode (:755-769), computed from one bulk decode of the whole graph."""
+        off, succ = self.decodeRange(0, self.numNodes())
+        return immutable_graph_hash(off, succ)
 
     def equals(self, other):
         """ImmutableGraph.equals (:731-749): same node count and same successor lists through sequential iterators."""
