@@ -108,8 +108,8 @@ int  bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs,
  * BVGraph.loadOffline / loadSequential, BVGraph.java:1380-1500, scanned as by test/SpeedTest.java:157-185): nothing stays
  * on the device.  The node range is cut into `pieces` bit-balanced pieces; while the device indexes and scans piece p,
  * the bytes of piece p + 1 cross PCIe (give pinned memory for that overlap).  pieces = 1 is open + scan + close.
- * [from, to) is the node range to scan (a shard of a multi-GPU scan, or 0, nodes).  offsets_stream may be NULL (no
- * .offsets file): the boundaries are found from the stream first, which sends it to the device one more time. */
+ * [from, to) is the node range to scan (a shard of a multi-GPU scan, or 0, nodes).  offsets_stream is required here
+ * (a graph without .offsets is opened with bvg_open / bvg_open_memory and scanned with bvg_scan_range). */
 int  bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                      int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                      uint32_t flags, int device, int32_t from, int32_t to, int pieces, int64_t* arcs_out, uint64_t* checksum_out);

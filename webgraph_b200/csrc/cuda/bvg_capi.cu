@@ -867,7 +867,7 @@ int bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
 int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                     int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                     uint32_t flags, int device, int32_t from, int32_t to, int pieces, int64_t* arcs_out, uint64_t* checksum_out) {
-    if (nodes < 0 || (!graph && graph_bytes) || pieces < 1) return BVG_EINVAL;
+    if (nodes < 0 || (!graph && graph_bytes) || !offsets_stream || pieces < 1) return BVG_EINVAL;
     if (from < 0 || to < from || to > nodes) return BVG_EINVAL;
     int dev;
     int dl[1] = { device };
@@ -893,13 +893,7 @@ int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
         cudaStreamDestroy(st[0]); cudaStreamDestroy(st[1]);
         cudaGetLastError();
     };
-    if (offsets_stream) rc = device_decode_offsets(st[0], offsets_stream, offsets_bytes, oc, nodes, &d_full);
-    else {  // no .offsets: record boundaries from the stream itself (the whole stream visits the device once more for that)
-        bvg_graph probe;
-        probe.flags = flags; probe.zetak = zetak; probe.window = window; probe.minlen = minlen;
-        rc = set_codec(&probe);
-        if (!rc) rc = device_offsets_from_graph(st[0], graph, graph_bytes, probe.codec, probe.def_codec, nodes, &d_full, nullptr, nullptr);
-    }
+    rc = device_decode_offsets(st[0], offsets_stream, offsets_bytes, oc, nodes, &d_full);
     if (rc) { cleanup(); return rc; }
     {   // bit-balanced cuts (as bvg_plan_shards), found on the device
         Tmp<int32_t> d_bounds(st[0]);
