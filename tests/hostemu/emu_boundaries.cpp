@@ -31,12 +31,13 @@ extern "C" int emu_boundaries(const uint8_t* graph, uint64_t nbytes, int64_t n,
         a[(size_t)j] = s;
     }
     std::vector<BndMemo> memo(BND_MEMO_SLOTS, BndMemo{0, 0, 0, 0, 0});
+    const int lean = getenv("EMU_BND_LEAN") && atoi(getenv("EMU_BND_LEAN")) != 0;  // BVG_BND_LEAN
     int64_t trusted = 0, nwalks = 0;
     int pass = 0;
     for (;; pass++) {
         for (int64_t j = 0; j < nsub; j++) {
-            if (def_codec) bnd_pass_one<true>(j, words.data(), words.size(), stream_bits, c, a.data(), b.data(), he_a.data(), hx_a.data(), he_b.data(), hx_b.data(), ring.data(), std::min(pass, 1), trusted, cap, memo.data());
-            else bnd_pass_one<false>(j, words.data(), words.size(), stream_bits, c, a.data(), b.data(), he_a.data(), hx_a.data(), he_b.data(), hx_b.data(), ring.data(), std::min(pass, 1), trusted, cap, memo.data());
+            if (def_codec) bnd_pass_one<true>(j, words.data(), words.size(), stream_bits, c, a.data(), b.data(), he_a.data(), hx_a.data(), he_b.data(), hx_b.data(), ring.data(), std::min(pass, 1), trusted, cap, memo.data(), lean);
+            else bnd_pass_one<false>(j, words.data(), words.size(), stream_bits, c, a.data(), b.data(), he_a.data(), hx_a.data(), he_b.data(), hx_b.data(), ring.data(), std::min(pass, 1), trusted, cap, memo.data(), lean);
             nwalks += b[(size_t)j].walked;
         }
         for (int64_t j = 0; j < nsub; j++) bnd_check_one(j, b.data(), he_b.data(), hx_b.data(), W, ok.data());
@@ -64,8 +65,8 @@ extern "C" int emu_boundaries(const uint8_t* graph, uint64_t nbytes, int64_t n,
     if (total < n) return -4;
     if (total == n) out[n] = a[(size_t)nsub - 1].exit;
     for (int64_t j = 0; j < nsub; j++) {
-        if (def_codec) bnd_emit_one<true>(j, words.data(), words.size(), stream_bits, c, a.data(), he_a.data(), ring.data(), hx_b.data(), base.data(), n, out, memo.data());
-        else bnd_emit_one<false>(j, words.data(), words.size(), stream_bits, c, a.data(), he_a.data(), ring.data(), hx_b.data(), base.data(), n, out, memo.data());
+        if (def_codec) bnd_emit_one<true>(j, words.data(), words.size(), stream_bits, c, a.data(), he_a.data(), ring.data(), hx_b.data(), base.data(), n, out, memo.data(), lean);
+        else bnd_emit_one<false>(j, words.data(), words.size(), stream_bits, c, a.data(), he_a.data(), ring.data(), hx_b.data(), base.data(), n, out, memo.data(), lean);
     }
     if (getenv("EMU_BND_TRACE")) { int used = 0; for (auto& m : memo) used += m.ready; fprintf(stderr, "memo slots used %d\n", used); }
     return 0;

@@ -140,9 +140,11 @@ def _emu_boundaries(emu, oracle, base, sub_bits, cap=1 << 26):
     return passes.value, walks.value, nsub
 
 
-def test_emulated_boundaries_from_graph_alone(emu, oracle, tmp_path):
+@pytest.mark.parametrize("lean", [0, 1])  # 1: residual runs through the 32-bit window of the scan kernels (BVG_BND_LEAN)
+def test_emulated_boundaries_from_graph_alone(emu, oracle, tmp_path, monkeypatch, lean):
     """Record boundaries found without .offsets (bvg_boundaries.cuh) == the .offsets the writer (and, for cnr-2000, the
     reference) produced; sub-ranges from far too small (every speculation wrong, passes do the work) to one."""
+    monkeypatch.setenv("EMU_BND_LEAN", str(lean))
     for sub_bits in (1 << 30, 1 << 20, 1 << 17, 1 << 14):
         passes, walks, nsub = _emu_boundaries(emu, oracle, CNR, sub_bits)
         assert passes <= nsub + 1

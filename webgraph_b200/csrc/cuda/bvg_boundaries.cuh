@@ -27,7 +27,7 @@
 // its end): a walk that runs `cap` bits past its sub-range gives up and its exit stays unknown until the sub-range is
 // the first unproven one, which is walked without a cap.
 #pragma once
-#include "bvg_device.cuh"
+#include "bvg_scan.cuh"
 
 namespace bvg {
 
@@ -92,7 +92,7 @@ __device__ inline void bnd_memo_put(BndMemo* memo, uint64_t pos, int64_t count, 
 // r = 1 the latest, at ring[(head + r - 1) % window]).  Returns 0 and the outdegree, 1 if the parse makes no sense, 2 if it
 // ran beyond `stop`.  Follows BVGraph.successors (:1044-1100) without producing anything.
 template <bool DEF>
-__device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const int32_t* ring, int32_t head, int32_t& d_out, BndMemo* memo) {
+__device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const int32_t* ring, int32_t head, int32_t& d_out, BndMemo* memo, int lean) {
     const uint64_t d64 = Rd<DEF>::outdeg(b, c);
     if (b.pos() > stop) return 2;
     if (d64 > 0x7fffffffull) return 1;
@@ -147,6 +147,22 @@ __device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const
         return 0;
     }
     if (extra > 0) (void)Rd<DEF>::resid(b, c);  // :939-972, values not needed; the first residual is often a long code
+    if (DEF && lean && extra > 1) {
+        // BVG_BND_LEAN=1 (to be measured): the run walked with the 32-bit sliding window of the scan kernels (bvg_scan.cuh)
+        GraphDev gw{};
+        gw.words = b.w; gw.nwords = b.maxw + 3;
+        Win w;
+        w.seek(gw, b.pos());
+        const int k = c.zetak;
+        for (int64_t i = 1; i < extra; i++) {
+            uint32_t m, len;
+            if (zeta_fast<0>(w.top(), k, m, len)) w.skip(len);
+            else (void)w.zeta_slow(gw, k);
+            if ((i & 7) == 7 && (w.overrun() || w.pos(gw) > stop)) return 2;
+        }
+        if (w.overrun()) return 2;
+        b.seek(w.pos(gw));
+    } else
     for (int64_t i = 1; i < extra; i++) {
         (void)Rd<DEF>::gap(b, c);               // the 32-bit fast path of the default zeta codes, else the same reader
         if ((i & 7) == 7 && b.pos() > stop) return 2;
@@ -163,7 +179,7 @@ __device__ inline int bnd_record(BitBuf& b, const Codec& c, uint64_t stop, const
 template <bool DEF>
 __device__ inline void bnd_walk(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, const Codec& c, BndSub& s,
                                 const int32_t* hist_in, int32_t* ring, int32_t* hist_out, uint64_t cap,
-                                uint64_t* __restrict__ starts, int64_t ord_base, int64_t n, BndMemo* memo) {
+                                uint64_t* __restrict__ starts, int64_t ord_base, int64_t n, BndMemo* memo, int lean) {
     const int32_t W = c.window;
     for (int32_t k = 0; k < W; k++) ring[k] = hist_in ? hist_in[k] : 0;
     int32_t head = 0;
@@ -178,7 +194,7 @@ __device__ inline void bnd_walk(const uint32_t* __restrict__ words, uint64_t nwo
         if (starts && !(reseek && pos != s.entry) && ord_base + s.count <= n) starts[ord_base + s.count] = pos;
         if (reseek) { b.seek(pos); reseek = false; }
         int32_t d = 0;
-        const int st = bnd_record<DEF>(b, c, stop, ring, head, d, memo);
+        const int st = bnd_record<DEF>(b, c, stop, ring, head, d, memo, lean);
         if (st == 0) {
             pos = b.pos();
             s.count++;
@@ -201,7 +217,7 @@ __device__ inline void bnd_pass_one(int64_t j, const uint32_t* __restrict__ word
                                     const BndSub* __restrict__ in, BndSub* __restrict__ out,
                                     const int32_t* __restrict__ hist_entry_in, const int32_t* __restrict__ hist_exit_in,
                                     int32_t* __restrict__ hist_entry_out, int32_t* __restrict__ hist_exit_out, int32_t* __restrict__ ring,
-                                    int pass, int64_t trusted, uint64_t cap, BndMemo* memo) {
+                                    int pass, int64_t trusted, uint64_t cap, BndMemo* memo, int lean = 0) {
     const int32_t W = c.window;
     BndSub s = in[j];
     const int32_t* he = hist_entry_in + j * W;
@@ -242,7 +258,7 @@ __device__ inline void bnd_pass_one(int64_t j, const uint32_t* __restrict__ word
         s.exit = s.entry; s.count = 0; s.bad_pos = BND_UNKNOWN; s.bad_index = 0; s.walked = 1; s.capped = 0;
         for (int32_t k = 0; k < W; k++) hist_exit_out[j * W + k] = hin ? hin[k] : 0;
     } else {
-        bnd_walk<DEF>(words, nwords, stream_bits, c, s, hin, ring + j * (W > 0 ? W : 1), hist_exit_out + j * W, proven_entry ? 0 : cap, nullptr, 0, 0, memo);
+        bnd_walk<DEF>(words, nwords, stream_bits, c, s, hin, ring + j * (W > 0 ? W : 1), hist_exit_out + j * W, proven_entry ? 0 : cap, nullptr, 0, 0, memo, lean);
     }
     out[j] = s;
 }
@@ -261,11 +277,11 @@ __device__ inline void bnd_check_one(int64_t j, const BndSub* __restrict__ sub, 
 template <bool DEF>
 __device__ inline void bnd_emit_one(int64_t j, const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, Codec c,
                                     const BndSub* __restrict__ sub, const int32_t* __restrict__ hist_entry, int32_t* __restrict__ ring,
-                                    int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo) {
+                                    int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo, int lean = 0) {
     const int32_t W = c.window;
     BndSub s = sub[j];
     if (s.entry >= s.hi || s.entry >= stream_bits) return;
-    bnd_walk<DEF>(words, nwords, stream_bits, c, s, hist_entry + j * W, ring + j * (W > 0 ? W : 1), hist_scratch + j * W, 0, starts, base[j], n, memo);
+    bnd_walk<DEF>(words, nwords, stream_bits, c, s, hist_entry + j * W, ring + j * (W > 0 ? W : 1), hist_scratch + j * W, 0, starts, base[j], n, memo, lean);
 }
 
 #ifndef BVG_HOST_EMULATION
@@ -284,14 +300,14 @@ __global__ void k_bnd_walk(const uint32_t* __restrict__ words, uint64_t nwords, 
                            const BndSub* __restrict__ in, BndSub* __restrict__ out,
                            const int32_t* __restrict__ hist_entry_in, const int32_t* __restrict__ hist_exit_in,
                            int32_t* __restrict__ hist_entry_out, int32_t* __restrict__ hist_exit_out, int32_t* __restrict__ ring,
-                           int pass, int64_t trusted, uint64_t cap, BndMemo* memo, int lanes) {
+                           int pass, int64_t trusted, uint64_t cap, BndMemo* memo, int lanes, int lean) {
     // `lanes` walks per warp (default 1, lane 0 only; BVG_BND_LANES).  With 32 walks per warp there are too few warps to
     // hide latency and the walks of a warp diverge (2.4 s for the 1 B-arc graph); with one, every issue slot serves a
     // single lane (1.15 s).  The walks run the same loops, so a few per warp should converge most of the time.
     const int lane = threadIdx.x & 31;
     if (lane >= lanes) return;
     const int64_t j = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane;
-    if (j < nsub) bnd_pass_one<DEF>(j, words, nwords, stream_bits, c, in, out, hist_entry_in, hist_exit_in, hist_entry_out, hist_exit_out, ring, pass, trusted, cap, memo);
+    if (j < nsub) bnd_pass_one<DEF>(j, words, nwords, stream_bits, c, in, out, hist_entry_in, hist_exit_in, hist_entry_out, hist_exit_out, ring, pass, trusted, cap, memo, lean);
 }
 
 __global__ void k_bnd_check(const BndSub* __restrict__ sub, int64_t nsub, const int32_t* __restrict__ hist_entry,
@@ -303,11 +319,11 @@ __global__ void k_bnd_check(const BndSub* __restrict__ sub, int64_t nsub, const 
 template <bool DEF>
 __global__ void k_bnd_emit(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t stream_bits, Codec c, int64_t nsub,
                            const BndSub* __restrict__ sub, const int32_t* __restrict__ hist_entry, int32_t* __restrict__ ring,
-                           int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo, int lanes) {
+                           int32_t* __restrict__ hist_scratch, const int64_t* __restrict__ base, int64_t n, uint64_t* __restrict__ starts, BndMemo* memo, int lanes, int lean) {
     const int lane = threadIdx.x & 31;  // `lanes` walks per warp, as in k_bnd_walk
     if (lane >= lanes) return;
     const int64_t j = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane;
-    if (j < nsub) bnd_emit_one<DEF>(j, words, nwords, stream_bits, c, sub, hist_entry, ring, hist_scratch, base, n, starts, memo);
+    if (j < nsub) bnd_emit_one<DEF>(j, words, nwords, stream_bits, c, sub, hist_entry, ring, hist_scratch, base, n, starts, memo, lean);
 }
 #endif
 

@@ -421,6 +421,7 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     if (const char* e = getenv("BVG_BND_SUB_BITS")) sub_bits = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("BVG_BND_CAP_BITS")) cap = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
     const int lanes = env_int("BVG_BND_LANES", 1, 1, 32);  // walks per warp (k_bnd_walk)
+    const int lean = env_int("BVG_BND_LEAN", 0, 0, 1);      // residual runs through the 32-bit window of the scan kernels (to be measured)
     const int32_t W = c.window;
     const int64_t max_sub = std::max<int64_t>(1, std::min<int64_t>(16384, ((int64_t)1 << 24) / std::max<int32_t>(W, 1)));
     while ((int64_t)((stream_bits + sub_bits - 1) / sub_bits) > max_sub) sub_bits *= 2;
@@ -441,8 +442,8 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     int64_t trusted = 0;
     for (int64_t pass = 0;; pass++) {
         // one walk per warp (see k_bnd_walk), two warps per block
-        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap, memo.p, lanes);
-        else LAUNCH(k_bnd_walk<false>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap, memo.p, lanes);
+        if (def_codec) LAUNCH(k_bnd_walk<true>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap, memo.p, lanes, lean);
+        else LAUNCH(k_bnd_walk<false>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, out, he_in, hx_in, he_out, hx_out, ring.p, (int)std::min<int64_t>(pass, 1), trusted, cap, memo.p, lanes, lean);
         LAUNCH(k_bnd_check, grid_for(nsub, 128), 128, 0, s, out, nsub, he_out, hx_out, W, ok.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_ok.data(), ok.p, (size_t)nsub * 4, cudaMemcpyDeviceToHost, s));
@@ -480,8 +481,8 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
         const uint64_t end = h_sub[(size_t)nsub - 1].exit;
         CK(cudaMemcpyAsync(*d_full + n, &end, 8, cudaMemcpyHostToDevice, s));
     }
-    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full, memo.p, lanes);
-    else LAUNCH(k_bnd_emit<false>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full, memo.p, lanes);
+    if (def_codec) LAUNCH(k_bnd_emit<true>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full, memo.p, lanes, lean);
+    else LAUNCH(k_bnd_emit<false>, grid_for((nsub + lanes - 1) / lanes * 32, 64), 64, 0, s, words.p, nwords, stream_bits, c, nsub, in, he_in, ring.p, hx_out, d_base.p, n, *d_full, memo.p, lanes, lean);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // base and end are host memory
     return BVG_OK;
