@@ -9,6 +9,7 @@
 #include "bvg_long.cuh"
 #include "bvg_offsets.cuh"
 #include "bvg_boundaries.cuh"
+#include "bvg_tile.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -201,6 +202,18 @@ struct bvg_graph {
         li.seg_pos = d_seg_pos; li.seg_val = d_seg_val;
         return li;
     }
+    // tile plan of the scan (bvg_tile.cuh): tiles in node order, launch order (heaviest first), host copy of the first
+    // consumed node of every tile (which tiles does a node range touch?)
+    TileEntry* d_tiles = nullptr;
+    int32_t* d_tile_order = nullptr;
+    int32_t ntiles = 0;
+    std::vector<int32_t> h_tile_from;
+    bool tile_ok = false;
+    int tile_nt = 256;
+    uint32_t tile_smem = 0;
+    int64_t long_scan_entries = 0;     // scratch of the long records somebody copies from (3 d entries each)
+    mutable std::mutex sched_mu;       // the length-bucketed schedules of the range-decode kernels are built on first use
+    bool schedules_ready = false;
     // halo imported from the previous shard (bvg_halo_import)
     int32_t* d_halo_lists = nullptr;
     int64_t* d_halo_off = nullptr;
@@ -523,9 +536,10 @@ static int build_long_index(bvg_graph* g) {
     const int32_t levels = g->max_depth;
     const int fam_spec = 3 + levels;  // families: 0 residual segments, 1 row chunks, 2 extras chunks, 3.. merge chunks per level, then sub-ranges
     std::vector<int64_t> cum((size_t)(fam_spec + 1) * stride, 0);
-    int64_t cb = 0, iv = 0, seg = 0, tmp = 0;
+    int64_t cb = 0, iv = 0, seg = 0, tmp = 0, scan = 0;
     for (int64_t l = 0; l < nl; l++) {
         LongMeta& m = meta[(size_t)l];
+        m.scan_off = scan; if (m.flags & 1) scan += 3 * (int64_t)m.d;
         m.cb_off = cb; cb += (int64_t)m.ncb + 1;
         m.iv_off = iv; iv += (int64_t)m.ic + 1;
         m.seg_off = seg;
@@ -600,6 +614,7 @@ static int build_long_index(bvg_graph* g) {
     g->n_items_merge.assign((size_t)levels + 1, 0);
     for (int32_t lv = 1; lv <= levels; lv++) g->n_items_merge[(size_t)lv] = cum[(size_t)(2 + lv) * stride + (size_t)nl];
     g->long_tmp_entries = tmp;
+    g->long_scan_entries = scan;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // cum / meta are host vectors
     return BVG_OK;
@@ -608,15 +623,23 @@ static int build_long_index(bvg_graph* g) {
 // Counting sort of the nodes into the two length-bucketed schedules (see bvg_kernels.cuh).  Chains deeper than
 // MAX_LEVEL_KEYS levels (only files written with an unbounded maxrefcount) keep the natural-order kernels.
 constexpr int32_t MAX_LEVEL_KEYS = 64;
+static int build_parents(bvg_graph* g) {
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    if (nn == 0) return BVG_OK;
+    cudaStream_t s = g->stream;
+    CK(dev_alloc((void**)&g->d_is_parent, (size_t)nn, g->stream));
+    CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
+    LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+
 static int build_schedules(bvg_graph* g) {
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
     g->level_start.clear();
     if (nn == 0) return BVG_OK;
     cudaStream_t s = g->stream;
     Trace tr(s);
-    CK(dev_alloc((void**)&g->d_is_parent, (size_t)nn, g->stream));
-    CK(cudaMemsetAsync(g->d_is_parent, 0, (size_t)nn, s));
-    LAUNCH(k_mark_parents, grid_for(nn, 256), 256, 0, s, g->dev(), g->d_is_parent);
     const int32_t levels = std::min<int32_t>(g->max_depth, MAX_LEVEL_KEYS);
     const int64_t nchunks = ((nn + ((int64_t)1 << ORDER_CHUNK_LOG) - 1) >> ORDER_CHUNK_LOG) + 1;  // + the slot of the heavy records, scheduled first
     const int64_t per_level = nchunks * 2 * ORDER_BUCKETS;  // chunk x (parent | not) x half-octave bucket
@@ -662,7 +685,74 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaStreamSynchronize(s));
     tr.mark("  sched: scatter");
     g->copied_ready = true;
-    { Trace t2(s); const int rl = build_long_index(g); t2.mark("  long index"); return rl; }
+    g->schedules_ready = true;
+    return BVG_OK;
+}
+
+// The range-decode kernels and the pre-tile scan run over the length-bucketed schedules; a graph that is only ever scanned
+// through the tile kernel never builds them (2.3 GB on the 1 B-arc benchmark graph).
+static int ensure_schedules(const bvg_graph* cg) {
+    bvg_graph* g = const_cast<bvg_graph*>(cg);
+    std::lock_guard<std::mutex> lk(g->sched_mu);
+    if (g->schedules_ready) return BVG_OK;
+    return build_schedules(g);
+}
+
+// Tile plan of the scan (bvg_tile.cuh): node costs, their running sum, greedy cuts per super-block (count, scan, write),
+// launch order by stream bits.
+static int build_tile_plan(bvg_graph* g) {
+    g->tile_ok = false; g->ntiles = 0;
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    if (nn == 0 || !g->def_codec || g->window > 255 || env_int("BVG_TILE", 1, 0, 1) == 0) return BVG_OK;
+    if (g->max_outdeg > g->long_d && g->nlong == 0) return BVG_OK;  // chains too deep for the long index: general kernels
+    cudaStream_t s = g->stream;
+    g->tile_nt = env_int("BVG_TILE_NT", 256, 64, 1024);
+    if (g->tile_nt != 512 && g->tile_nt != 256) g->tile_nt = 256;
+    g->tile_smem = (uint32_t)env_int("BVG_TILE_SMEM_KB", g->tile_nt == 512 ? 112 : 55, 16, 226) * 1024u;
+    const uint32_t budget = tile_budget(g->tile_smem, g->tile_nt);
+    GraphDev gd = g->dev();
+    Tmp<int32_t> cost(s), counts(s);
+    Tmp<uint8_t> clean(s);
+    Tmp<int64_t> cum(s), base(s);
+    CK(cost.alloc((size_t)nn));
+    CK(clean.alloc((size_t)nn + 1));
+    CK(cum.alloc((size_t)nn + 1));
+    LAUNCH(k_plan_nodes, grid_for(nn, 256), 256, 0, s, gd, g->d_is_parent, g->long_d, budget, cost.p, clean.p);
+    int rc = device_exclusive_scan(s, cost.p, nn, cum.p);
+    if (rc) return rc;
+    const int64_t first = (int64_t)g->ext_from - g->node_lo;
+    const int32_t nsb = (int32_t)((nn - first + PLAN_SB - 1) / PLAN_SB);
+    if (nsb <= 0) return BVG_OK;
+    CK(counts.alloc((size_t)nsb));
+    CK(base.alloc((size_t)nsb + 1));
+    LAUNCH(k_plan_tiles, grid_for(nsb, 64), 64, 0, s, gd, cum.p, clean.p, g->d_long_nodes, g->nlong, budget, nsb, g->ext_from, counts.p, (const int64_t*)nullptr, (TileEntry*)nullptr);
+    std::vector<int32_t> h_counts((size_t)nsb);
+    CK(cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)nsb * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int64_t> h_base((size_t)nsb + 1, 0);
+    for (int32_t i = 0; i < nsb; i++) {
+        if (h_counts[(size_t)i] < 0) return BVG_OK;  // some node and its ancestors do not fit a tile: the general kernels stay
+        h_base[(size_t)i + 1] = h_base[(size_t)i] + h_counts[(size_t)i];
+    }
+    const int64_t nt = h_base[(size_t)nsb];
+    if (nt <= 0 || nt > 0x7fffffff) return BVG_OK;
+    { const int r1 = small_h2d(base.p, h_base.data(), ((size_t)nsb + 1) * 8, s); if (r1) return r1; }
+    CK(dev_alloc((void**)&g->d_tiles, (size_t)nt * sizeof(TileEntry), g->stream));
+    CK(dev_alloc((void**)&g->d_tile_order, (size_t)nt * 4, g->stream));
+    LAUNCH(k_plan_tiles, grid_for(nsb, 64), 64, 0, s, gd, cum.p, clean.p, g->d_long_nodes, g->nlong, budget, nsb, g->ext_from, counts.p, base.p, g->d_tiles);
+    CK(cudaGetLastError());
+    std::vector<TileEntry> h_tiles((size_t)nt);
+    CK(cudaMemcpyAsync(h_tiles.data(), g->d_tiles, (size_t)nt * sizeof(TileEntry), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    g->h_tile_from.resize((size_t)nt);
+    std::vector<int32_t> order((size_t)nt);
+    for (int64_t i = 0; i < nt; i++) { g->h_tile_from[(size_t)i] = h_tiles[(size_t)i].from; order[(size_t)i] = (int32_t)i; }
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return h_tiles[(size_t)a].cost > h_tiles[(size_t)b].cost; });
+    { const int r2 = small_h2d(g->d_tile_order, order.data(), (size_t)nt * 4, s); if (r2) return r2; }
+    CK(cudaStreamSynchronize(s));
+    g->ntiles = (int32_t)nt;
+    g->tile_ok = true;
+    return BVG_OK;
 }
 
 // Uploads the stream bytes + offsets of nodes [node_lo, node_hi] and builds the decode index.
@@ -726,8 +816,12 @@ static int build_index(bvg_graph* g, uint64_t* d_offsets_full, int64_t n_full, b
     const int e = fetch_error(g);
     if (e) return e;
     tr.mark("header + scan + depth");
-    const int rs = build_schedules(g);
-    tr.mark("schedules + long index");
+    int rs = build_parents(g);
+    if (!rs) rs = build_long_index(g);
+    tr.mark("parents + long index");
+    if (!rs) rs = build_tile_plan(g);
+    tr.mark("tile plan");
+    if (!rs && !g->tile_ok) { rs = build_schedules(g); tr.mark("schedules"); }
     return rs;
 }
 
@@ -737,7 +831,7 @@ static void destroy(bvg_graph* g) {
     // graph memory comes from the device's stream-ordered pool (kept warm): a later open reuses it without going back
     // to the driver, which is what makes open-scan-close cycles cheap
     void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
-                     g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
+                     g->d_tiles, g->d_tile_order, g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
                      g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum };
     for (void* p : ptrs) if (p) dev_free(p, g->stream);
     cudaStreamSynchronize(g->stream);
@@ -1232,8 +1326,12 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     const int32_t lo = hp.lo;
     const int64_t cnt = (int64_t)to - lo;
     // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
-    const bool ordered = g->d_order_e && g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
-    if (ordered) return run_ordered_decode(g, lo, to, from, rm);
+    const bool ordered = g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
+    if (ordered) {
+        const int rc = ensure_schedules(g);
+        if (rc) return rc;
+        return run_ordered_decode(g, lo, to, from, rm);
+    }
     // Small ranges (cursor batches, boundary lists): natural node order, one thread per record -- except the long records,
     // which are split across threads exactly as in a whole-graph decode (their items are filtered by [lo, to)).
     const bool split = g->nlong > 0 &&
@@ -1394,10 +1492,45 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     return BVG_OK;
 }
 
+}  // extern "C" (templates cannot have C linkage)
+// The scan through the tile kernel (bvg_tile.cuh): one launch over the tiles that touch [from, to).
+template <int K, int NT, int MINB>
+static int launch_tile_scan(const bvg_graph* g, const TileArgs& a, unsigned grid, cudaStream_t s) {
+    CK(cudaFuncSetAttribute(k_tile_scan<K, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes));
+    LAUNCH_P(g, "k_tile_scan", (k_tile_scan<K, NT, MINB>), grid, NT, a.smem_bytes, s, g->dev(), a);
+    CK(cudaGetLastError());
+    return BVG_OK;
+}
+extern "C" {
+
+static int enqueue_scan_tiles(const bvg_graph* g, int32_t from, int32_t to, unsigned long long* d_result) {
+    cudaStream_t s = g->stream;
+    // tiles are in node order and partition the extent: the first one that ends after `from`, the last one that starts before `to`
+    const auto& tf = g->h_tile_from;
+    const int32_t t0 = (int32_t)(std::upper_bound(tf.begin(), tf.end(), from) - tf.begin()) - 1;
+    const int32_t t1 = (int32_t)(std::lower_bound(tf.begin(), tf.end(), to) - tf.begin());
+    if (t0 < 0 || t1 <= t0) return BVG_EINVAL;
+    Tmp<int32_t> scr(s);
+    CK(scr.alloc((size_t)g->long_scan_entries + 8));
+    TileArgs a{};
+    a.tiles = g->d_tiles;
+    a.order = (t0 == 0 && t1 == g->ntiles) ? g->d_tile_order : nullptr;  // whole extent: heaviest tiles first
+    a.first = t0; a.count = t1 - t0;
+    a.fold_lo = from; a.fold_hi = to;
+    a.li = g->long_index();
+    a.long_scr = scr.p;
+    a.result = d_result;
+    a.smem_bytes = g->tile_smem;
+    const unsigned grid = (unsigned)(t1 - t0);
+    if (g->tile_nt == 512) return g->zetak == 3 ? launch_tile_scan<3, 512, 2>(g, a, grid, s) : launch_tile_scan<0, 512, 2>(g, a, grid, s);
+    return g->zetak == 3 ? launch_tile_scan<3, 256, 4>(g, a, grid, s) : launch_tile_scan<0, 256, 4>(g, a, grid, s);
+}
+
 // Scan = decode into a stream-ordered scratch + checksum kernel (general path); ranges are split so that the scratch
 // stays below 2^30 arcs.
 static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned long long* d_result) {
     if (to == from) return BVG_OK;
+    if (g->tile_ok) return enqueue_scan_tiles(g, from, to, d_result);
     int64_t ra, rb;
     int rc = fetch_rowoff(g, from, to, &ra, &rb);
     if (rc) return rc;
@@ -1411,8 +1544,11 @@ static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned l
     cudaStream_t s = g->stream;
     Tmp<int32_t> rows(s);
     CK(rows.alloc((size_t)arcs));
-    if (g->d_order_e && g->d_is_parent && g->max_depth <= MAX_LEVEL_KEYS && ((int64_t)to - from) * 4 >= (int64_t)g->node_hi - g->node_lo)
+    if (g->d_is_parent && g->max_depth <= MAX_LEVEL_KEYS && ((int64_t)to - from) * 4 >= (int64_t)g->node_hi - g->node_lo) {
+        rc = ensure_schedules(g);
+        if (rc) return rc;
         return enqueue_scan_fused(g, from, to, rows.p, ra, d_result);
+    }
     rc = enqueue_decode(g, from, to, rows.p, ra);
     if (rc) return rc;
     const int64_t cnt = (int64_t)to - from;
@@ -1514,7 +1650,7 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
     if (!on_device) { CK(d_off.alloc((size_t)nx + 1)); off_dev = d_off.p; }
     // queries whose chain holds a long record go through the range kernels (k_query_sizes marks their chains)
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
-    const bool split_long = g->nlong > 0 && g->d_order_e && g->d_rec_e && g->max_depth <= MAX_LEVEL_KEYS;
+    const bool split_long = g->nlong > 0 && g->max_depth <= MAX_LEVEL_KEYS;
     Tmp<uint8_t> mask(s), heavy(s);
     Tmp<int32_t> nheavy(s);
     if (split_long) {
@@ -1557,6 +1693,8 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
         RowMap rm;
         rm.out = rows.p; rm.out_base = ra; rm.from = g->node_lo; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = g->node_lo; rm.halo_base = ra;
         rm.mask = mask.p;
+        rc = ensure_schedules(g);
+        if (rc) return rc;
         rc = run_ordered_decode(g, g->node_lo, g->node_hi, g->node_lo, rm);
         if (rc) return rc;
         LAUNCH_P(g, "k_gather_rows", k_gather_rows, 148 * 8, 256, 0, s, gd, xs_dev, nx, heavy.p, off_dev, out_dev, rm);

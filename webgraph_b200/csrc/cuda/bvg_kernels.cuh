@@ -113,12 +113,6 @@ constexpr int ORDER_CHUNK_LOG = 18;
 // benchmark graph when the heavy records start with their chunk.
 constexpr int ORDER_HEAVY = 192;
 
-__device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // quarter octaves: 0..255, monotone in v
-    if (v == 0) return 0;
-    const int l = 63 - __clzll((long long)v);
-    const int frac = l >= 2 ? (int)((v >> (l - 2)) & 3) : (l == 1 ? (int)((v & 1) << 1) : 0);
-    return 4 * l + frac;
-}
 
 // key_e: extras schedule (all nodes with successors); key_m: merge schedule (nodes with a reference), level-major.
 // The merge work of a node is its block list (walked twice) plus the elements it copies, plus -- when its own list has

@@ -41,6 +41,7 @@ struct LongMeta {
     int64_t iv_off;       // iv_cum[iv_off .. +ic] (ic+1 entries), iv_left (ic entries)
     int64_t seg_off;      // seg_pos / seg_val, ceil(rc / LONG_SEG) entries
     int64_t tmp_off;      // per-scan temp: residuals at [tmp_off, +rc), extras at [tmp_off + d, +d-copied)
+    int64_t scan_off;     // tile scan (bvg_tile.cuh), records somebody copies from only: 3 d entries -- residuals, extras, the list
     uint64_t after_header;  // bit position (relative to word 0) right after outdegree + reference
     uint64_t resid_pos;     // bit position of the first residual code
     uint64_t rec_end;       // bit position one past the record (= end of the residual section)

@@ -17,6 +17,13 @@
 
 namespace bvg {
 
+__device__ __forceinline__ int half_octave_bucket(uint64_t v) {  // quarter octaves: 0..255, monotone in v
+    if (v == 0) return 0;
+    const int l = 63 - __clzll((long long)v);
+    const int frac = l >= 2 ? (int)((v >> (l - 2)) & 3) : (l == 1 ? (int)((v & 1) << 1) : 0);
+    return 4 * l + frac;
+}
+
 __device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
@@ -26,6 +33,13 @@ __device__ BVG_NOINLINE uint64_t slow_gamma(const uint32_t* __restrict__ words, 
     Bits t;
     t.w = words; t.maxw = nwords - 3; t.pos = *pos;
     const uint64_t r = t.gamma();
+    *pos = t.pos;
+    return r;
+}
+__device__ BVG_NOINLINE uint64_t slow_unary(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t* pos) {
+    Bits t;
+    t.w = words; t.maxw = nwords - 3; t.pos = *pos;
+    const uint64_t r = t.unary();
     *pos = t.pos;
     return r;
 }
@@ -134,6 +148,19 @@ struct WinT {
             return (uint64_t)((t >> (31 - 2 * m)) - 1u);
         }
         return gamma_slow(g);
+    }
+    // unary (BVGraph's reference code): zeros before the first one; at most 31 of them in the 32-bit window
+    __device__ __forceinline__ uint64_t unary(const GraphDev& g) {
+        const uint32_t t = top();
+        if (t != 0u) {
+            const uint32_t z = (uint32_t)__clz((int)t);
+            skip(z + 1u);
+            return z;
+        }
+        uint64_t p = pos(g);
+        const uint64_t r = slow_unary(g.words, g.nwords, &p);
+        seek(g, p);
+        return r;
     }
 };
 #ifndef BVG_WIN_LA
@@ -578,7 +605,8 @@ struct ScanExtras {
 // ---------------------------------------------------------------------------------------------------
 constexpr int COPY_RUNS = 8;  // runs staged per lane at a time (16 blocks); longer lists are staged in rounds
 
-struct CopyRuns {
+template <int NR>
+struct CopyRunsT {
     Win b;
     int32_t* __restrict__ st;   // this lane's slots: start of run i at st[2 * i * stride], end at st[(2 * i + 1) * stride]
     int32_t stride;
@@ -598,7 +626,7 @@ struct CopyRuns {
     // so a malformed list can make the result wrong but never the reads out of bounds.
     __device__ __forceinline__ void stage(const GraphDev& g) {
         nr = 0; r = 0;
-        while (nr < COPY_RUNS && bi <= bc) {
+        while (nr < NR && bi <= bc) {
             if (bi == bc) {
                 if (!(bc & 1u) && ppos < dp) { st[2 * nr * stride] = (int32_t)ppos; st[(2 * nr + 1) * stride] = (int32_t)dp; nr++; ppos = dp; }
                 bi++;
@@ -642,10 +670,11 @@ struct CopyRuns {
         return true;
     }
 };
+typedef CopyRunsT<COPY_RUNS> CopyRuns;
 
 // nobody copies from x: its copied successors are only consumed
-template <int BATCH>
-__device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CopyRuns& c, int32_t x, const int32_t* __restrict__ parent) {
+template <int BATCH, class CR>
+__device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CR& c, int32_t x, const int32_t* __restrict__ parent) {
     Fold32 f;
     f.begin(x);
     // BATCH positions first, then their loads together: a lane opens a new sector of its parent's row every eighth element,
@@ -719,7 +748,8 @@ __device__ __forceinline__ unsigned long long copied_fold_v2(const GraphDev& g, 
 // (MergedIntIterator.java:50-74: ascending union, equal heads once; a list that loses duplicates is padded with -1 as
 // BVGraphNodeIterator does when it drains, BVGraph.java:1210).  Folds the copied successors only: the extras were
 // folded when they were decoded.
-__device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CopyRuns& c, int32_t x, int32_t d, int32_t copied,
+template <class CR>
+__device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CR& c, int32_t x, int32_t d, int32_t copied,
                                                            int32_t* row, const int32_t* __restrict__ parent) {
     Fold32 f;
     f.begin(x);
