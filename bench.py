@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+WEBLIKE = dict(zipf_s=0.45, p_copy=0.97, copy_run=40.0, skip_run=1.5, p_interval=0.4, p_local=0.97, local_bits=9, max_degree=3000,
+               interval_max=2, p_same_degree=0.95)
 METRIC = "decoded_edges_per_second"
 UNIT = "edges/s"
 
@@ -46,6 +48,8 @@ def parse_args():
     ap.add_argument("--nodes", type=int, default=32_000_000)
     ap.add_argument("--arcs", type=int, default=1_070_000_000)  # dedup shortfall ~6 %: lands on ~1.0e9 arcs
     ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--workload", default="powerlaw", choices=["powerlaw", "weblike"],
+                    help="powerlaw: the no-locality power-law graph BASELINE's metric is quoted on; weblike: a copy-heavy graph with cnr-2000's mix")
     ap.add_argument("--max-degree", type=int, default=1 << 22, help="experiments only: cap on the generator's outdegree law")
     ap.add_argument("--workdir", default=os.environ.get("BVG_BENCH_DIR", "/tmp/bvg_bench"))
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -60,13 +64,19 @@ def parse_args():
 def graph_files(args, rank, world, barrier):
     """Rank 0 generates + compresses the synthetic graph once per box (host tools, all cores); others wait."""
     from webgraph_b200 import tools
-    base = os.path.join(args.workdir, "pl_n%d_m%d_s%x_d%d" % (args.nodes, args.arcs, args.seed, args.max_degree), "g")
+    kw = dict(max_degree=args.max_degree)
+    tag = "pl"
+    if args.workload == "weblike":
+        # lands near the reference's own fixture (cnr-2000: 3.56 bits/arc, 66 % copied arcs, avgref 1.38): ~3.6 bits/arc, 63 % copied, avgref 1.26
+        kw = dict(WEBLIKE)
+        tag = "web"
+    base = os.path.join(args.workdir, "%s_n%d_m%d_s%x_d%d" % (tag, args.nodes, args.arcs, args.seed, args.max_degree), "g")
     meta = base + ".meta.json"
     if rank == 0 and not os.path.exists(meta):
         os.makedirs(os.path.dirname(base), exist_ok=True)
         t = time.time()
         st = tools.generate_store(base, args.nodes, args.arcs, seed=args.seed, window=7, maxref=3, minlen=4, zetak=3,
-                                  threads=os.cpu_count() or 1, max_degree=args.max_degree)
+                                  threads=os.cpu_count() or 1, **kw)
         st["generate_seconds"] = time.time() - t
         with open(meta + ".tmp", "w") as f:
             json.dump(st, f)

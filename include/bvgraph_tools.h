@@ -58,6 +58,12 @@ typedef struct bvgt_gen_params {
     double   p_local;      /* fraction of the remaining successors drawn near x instead of globally */
     int32_t  block;        /* nodes per generation block ("host"): prototypes never cross a block */
     int32_t  max_degree;   /* cap on the outdegree law (default 2^22; experiments use smaller caps) */
+    /* shape of the copied part and of the local successors (defaults reproduce the round-1 benchmark graph) */
+    double   copy_run;     /* mean length of a copied run of the prototype (default 8) */
+    double   skip_run;     /* mean length of a skipped run (default 3) */
+    int32_t  local_bits;   /* local successors sit at a log-uniform distance below 2^local_bits (default 16) */
+    int32_t  interval_max; /* intervals per node: 1 .. interval_max (default 3) */
+    double   p_same_degree;/* probability that a copying node takes its prototype's outdegree (+ 0..3) instead of the law's: pages of a site (default 0) */
 } bvgt_gen_params;
 
 void bvgt_gen_defaults(bvgt_gen_params* p, int32_t n, int64_t target_arcs, uint64_t seed);

@@ -29,8 +29,8 @@ struct BitWriter {
 // blocks[0..bc): the block lengths as MaskedIntIterator takes them (first block may be 0, the others >= 1); written to a
 // stream the way BVGraph writes them (first as it is, the others minus one, gamma: BVGraph.java:1062-1066, 2177-2180).
 // variant 0: the masked sequence pulled one position at a time (CopyRuns::next)            -> out[0 .. *out_len)
-//         1: copied_fold<4>, 2: copied_fold_v2<2>                                            -> *fold (out untouched)
-//         3: copied_merge, 4: copied_merge_v2<2>: row = [copied slots | extras], d = copied + ne -> out[0 .. d), *fold
+//         1: copied_fold<4>                                                                   -> *fold (out untouched)
+//         3: copied_merge: row = [copied slots | extras], d = copied + ne                    -> out[0 .. d), *fold
 extern "C" int emu_masked(const int32_t* parent, int32_t dp, const int32_t* blocks, int32_t bc, const int32_t* extras, int32_t ne,
                           int32_t copied, int32_t x, int variant, int32_t* out, int32_t* out_len, unsigned long long* fold) {
     BitWriter bw;
@@ -44,7 +44,7 @@ extern "C" int emu_masked(const int32_t* parent, int32_t dp, const int32_t* bloc
     g.offsets = offsets.data(); g.node_lo = 0; g.node_hi = 1;
     g.c = Codec{ C_GAMMA, C_GAMMA, C_ZETA, C_UNARY, C_GAMMA, 3, 7, 4 };
     g.err = &err;
-    // the parent's list in a buffer with guard values on both sides (the 16-byte group reads of the v2 walkers must ignore them)
+    // the parent's list in a buffer with guard values on both sides (nothing may be read outside the list)
     std::vector<int32_t> pbuf((size_t)dp + 16, -12345);
     int32_t* prow = pbuf.data() + 5;  // deliberately not 16-byte aligned
     for (int32_t i = 0; i < dp; i++) prow[i] = parent[i];
@@ -60,12 +60,10 @@ extern "C" int emu_masked(const int32_t* parent, int32_t dp, const int32_t* bloc
         return err.code;
     }
     if (variant == 1) { *fold = copied_fold<4>(g, c, x, prow); return err.code; }
-    if (variant == 2) { *fold = copied_fold_v2<2>(g, c, x, prow); return err.code; }
     const int32_t d = copied + ne;
     std::vector<int32_t> row((size_t)d + 8, -777);
     for (int32_t i = 0; i < ne; i++) row[(size_t)copied + i] = extras[i];
-    if (variant == 3) *fold = copied_merge(g, c, x, d, copied, row.data(), prow);
-    else *fold = copied_merge_v2<2>(g, c, x, d, copied, row.data(), prow);
+    *fold = copied_merge(g, c, x, d, copied, row.data(), prow);
     for (int32_t i = 0; i < d; i++) out[i] = row[(size_t)i];
     *out_len = d;
     for (size_t i = (size_t)d; i < row.size(); i++) if (row[i] != -777) return -99;  // wrote past the row

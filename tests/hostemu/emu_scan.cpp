@@ -13,8 +13,6 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
                     const std::vector<int32_t>& depth, int maxdepth, const std::vector<int64_t>& rowoff,
                     int32_t* rows, uint8_t* parent_flag, unsigned long long* out) {
     unsigned long long acc = 0, arcs = 0;
-    const bool v2 = getenv("EMU_SCAN_V2") && atoi(getenv("EMU_SCAN_V2")) != 0;  // ScanExtras::resid_v2 instead of resid
-    const bool merge_v2 = getenv("EMU_MERGE_V2") && atoi(getenv("EMU_MERGE_V2")) != 0;  // copied_fold_v2 instead of copied_fold
     std::vector<uint64_t> blocks_pos(n, 0);
     std::vector<int32_t> copied(n, 0), bcs(n, 0);
     for (int32_t x = 0; x < n; x++) if (ref[x]) parent_flag[x - ref[x]] = 1;
@@ -51,8 +49,7 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             ScanExtras<K, WinRing<1>> w;
             w.begin(g, x, nout, epos, true, ring_address(ring));
             if (has_iv) w.iv_fold(g); else w.iv_none(g);
-            if (v2) { if (store) w.template resid_v2<true>(g, row, true); else w.template resid_v2<false>(g, row, false); }
-            else { if (store) w.template resid<true>(g, row, true); else w.template resid<false>(g, row, false); }
+            if (store) w.template resid<true>(g, row, true); else w.template resid<false>(g, row, false);
             if (store && has_iv) w.iv_merge(g, row);
             if (w.err) return w.err;
             f = w.finish();
@@ -67,9 +64,7 @@ static int scan_all(const GraphDev& g, int32_t n, const std::vector<int32_t>& ou
             CopyRuns c;
             c.begin(g, blocks_pos[x], bcs[x], outdeg[px], slots, 1, true);
             c.stage(g);
-            if (parent_flag[x] && merge_v2) acc ^= copied_merge_v2<2>(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
-            else if (parent_flag[x]) acc ^= copied_merge(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
-            else if (merge_v2) acc ^= copied_fold_v2<2>(g, c, x, rows + rowoff[px]);
+            if (parent_flag[x]) acc ^= copied_merge(g, c, x, outdeg[x], copied[x], rows + rowoff[x], rows + rowoff[px]);
             else acc ^= copied_fold<8>(g, c, x, rows + rowoff[px]);
         }
     out[0] = arcs; out[1] = acc;

@@ -90,9 +90,9 @@ int run_tile(EmuGraph& E, const TileEntry& e, const TileArgs& a, int nt, unsigne
     for (int t = 0; t < nt; t++) T.levels(t, nt);
     T.scan_buckets(0); T.scan_levels(0); T.scan_rows(0);
     for (int t = 0; t < nt; t++) T.scatter(t, nt);
-    for (int t = 0; t < nt; t++) T.long_resid_phase(t, nt, acc, arcs);
+    if (T.nlong) { T.long_count(0, 0); for (int t = 0; t < nt; t++) T.long_phase(0, t, nt, acc, arcs); }
     for (uint32_t it = 0; it < T.sh->nE; it++) T.extras_item((int32_t)T.ordE[it], acc, arcs);
-    if (T.nlong) for (int t = 0; t < nt; t++) T.long_extras_phase(t, nt, acc, arcs);
+    if (T.nlong) { T.long_count(1, 0); for (int t = 0; t < nt; t++) T.long_phase(1, t, nt, acc, arcs); }
     const int32_t maxlevel = T.sh->maxlevel;
     for (int32_t level = 1; level <= maxlevel; level++) {
         uint32_t la, lb;
@@ -102,7 +102,7 @@ int run_tile(EmuGraph& E, const TileEntry& e, const TileArgs& a, int nt, unsigne
             if (level >= TILE_LEVELS && (int32_t)T.lvl[i] != level) i = -1;
             T.merge_item(i, (int)(it % (uint32_t)nt), nt, acc);
         }
-        if (T.nlong) for (int t = 0; t < nt; t++) T.long_merge_phase(level, t, nt, acc, arcs);
+        if (T.nlong) { T.long_count(2, level); for (int t = 0; t < nt; t++) T.long_phase(2, t, nt, acc, arcs); }
     }
     const int err = T.sh->err;
     for (size_t i = 0; i < GUARD; i++) if (buf[i] != 0xA5) return -100;

@@ -26,12 +26,13 @@ def _find_asan():
 def emu():
     cuda_dir = os.path.join(ROOT, "webgraph_b200", "csrc", "cuda")
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(EMU_DIR, "emu_long.cpp"), os.path.join(EMU_DIR, "emu_offsets.cpp"),
-            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "emu_boundaries.cpp"), os.path.join(EMU_DIR, "emu_iterators.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
-            os.path.join(cuda_dir, "bvg_offsets.cuh"), os.path.join(cuda_dir, "bvg_scan.cuh"), os.path.join(cuda_dir, "bvg_boundaries.cuh")]
+            os.path.join(EMU_DIR, "emu_scan.cpp"), os.path.join(EMU_DIR, "emu_boundaries.cpp"), os.path.join(EMU_DIR, "emu_iterators.cpp"), os.path.join(EMU_DIR, "emu_tile.cpp"), os.path.join(EMU_DIR, "emu_stream.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"), os.path.join(cuda_dir, "bvg_device.cuh"), os.path.join(cuda_dir, "bvg_long.cuh"),
+            os.path.join(cuda_dir, "bvg_offsets.cuh"), os.path.join(cuda_dir, "bvg_scan.cuh"), os.path.join(cuda_dir, "bvg_boundaries.cuh"),
+            os.path.join(cuda_dir, "bvg_tile.cuh"), os.path.join(cuda_dir, "bvg_stream.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(s) > os.path.getmtime(EMU) for s in srcs):
         # UBSan only (ASan needs LD_PRELOAD under python); bounds are enforced by guard words below
         subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-fPIC",
-                               "-shared", "-I" + EMU_DIR, "-o", EMU, srcs[0], srcs[1], srcs[2], srcs[3], srcs[4], srcs[5]])
+                               "-shared", "-I" + EMU_DIR, "-o", EMU] + srcs[:8])
     lib = C.CDLL(EMU)
     lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.emu_decode_long.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int64]
@@ -40,6 +41,10 @@ def emu():
     lib.emu_masked.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                                C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_ulonglong)]
     lib.emu_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.emu_tile_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                  C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.emu_stream_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_stream_fold.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     return lib
@@ -211,12 +216,9 @@ def _emu_scan(emu, oracle, base):
     return int(parent.sum())
 
 
-@pytest.mark.parametrize("v2", [0, 1, 2])  # 1: the alternative residual loop ScanExtras::resid_v2 (BVG_SCAN_V2); 2: copied_fold_v2 (BVG_MERGE_V2)
-def test_emulated_fused_scan(emu, oracle, tmp_path, monkeypatch, v2):
+def test_emulated_fused_scan(emu, oracle, tmp_path):
     """k_scan_extras_lean / k_scan_merge logic (bvg_scan.cuh) record by record on the host: checksum == oracle's scan,
     parents' rows == oracle's lists."""
-    monkeypatch.setenv("EMU_SCAN_V2", "1" if v2 == 1 else "0")
-    monkeypatch.setenv("EMU_MERGE_V2", "1" if v2 == 2 else "0")
     assert _emu_scan(emu, oracle, CNR) > 1000
     for k, w, r, ml in [(3, 7, 3, 4), (3, 7, 3, 0), (2, 1, 1, 2), (5, 16, 10, 3), (1, 3, 2, 4)]:
         off, succ, _ = graphs.copy_heavy(2000, seed=5 + k + ml)
@@ -289,7 +291,7 @@ def test_masked_iterator_like_the_reference(emu):
                     curr = 1
             got, _ = _masked(emu, x, blocks, [], 0, 7, 0)
             assert got == expected, (length, zeros, blocks)
-            for variant in (1, 2):
+            for variant in (1,):
                 _, f = _masked(emu, x, blocks, [], 0, 12345, variant)
                 assert f == _fold(12345, expected), (length, zeros, blocks, variant)
 
@@ -297,7 +299,7 @@ def test_masked_iterator_like_the_reference(emu):
 def test_merged_iterator_like_the_reference(emu):
     """MergedIntIteratorTest.testMerge (reference test/.../MergedIntIteratorTest.java:31-66): the ascending union of two
     ascending lists, an element present in both emitted once (MergedIntIterator.java:50-74) -- here the in-place merge
-    of a record's copied successors with its extras (copied_merge / copied_merge_v2); what the union loses to
+    of a record's copied successors with its extras (copied_merge); what the union loses to
     duplicates is padded with -1, as BVGraphNodeIterator leaves it (BVGraph.java:1210)."""
     rng = np.random.default_rng(21)
     for i in range(10):
@@ -305,7 +307,7 @@ def test_merged_iterator_like_the_reference(emu):
             a = sorted(set(np.cumsum(rng.integers(0, 10, n0)).tolist()))   # the reference builds sets of the two lists
             b = sorted(set(np.cumsum(rng.integers(0, 10, n1)).tolist()))
             union = sorted(set(a) | set(b))
-            for variant in (3, 4):
+            for variant in (3,):
                 got, f = _masked(emu, a, [], b, len(a), 99, variant)  # no blocks: the whole parent is copied
                 assert got[:len(union)] == union and all(v == -1 for v in got[len(union):]), (a, b, variant)
                 assert len(got) == len(a) + len(b)
@@ -327,7 +329,81 @@ def test_merged_iterator_like_the_reference(emu):
         pool = sorted(set(range(int(parent[-1]) + 20)) - set(copied))
         extras = sorted(rng.choice(pool, size=min(len(pool), int(rng.integers(0, 30))), replace=False).tolist())
         union = sorted(copied + extras)
-        for variant in (3, 4):
+        for variant in (3,):
             got, f = _masked(emu, parent, blocks, extras, len(copied), 5, variant)
             assert got == union, (trial, variant)
             assert f == _fold(5, copied)
+
+
+def _emu_tile(emu, oracle, base, long_d=1024, seg=128, chunk=128, smem=56 * 1024, nt=256, lo=0, hi=None, may_refuse=False):
+    g = oracle.load(base)
+    hi = g.n if hi is None else hi
+    graph = np.fromfile(base + ".graph", dtype=np.uint8)
+    nb = len(graph)
+    graph = np.concatenate([graph, np.zeros(64, dtype=np.uint8)])
+    offs = g.offsets()
+    out = np.zeros(2, dtype=np.uint64)
+    st = np.zeros(5, dtype=np.int64)
+    rc = emu.emu_tile_scan(graph.ctypes.data, nb, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak, long_d, seg, chunk, smem, nt, lo, hi,
+                           out.ctypes.data, st.ctypes.data)
+    if may_refuse and rc == -300:  # the planner found a node whose ancestors do not fit one tile: the library keeps the general kernels
+        return None
+    assert rc == 0
+    assert (int(out[0]), int(out[1])) == g.scan_range(lo, hi)
+    return st.tolist()  # tiles, tiles with a halo, halo nodes, long records, largest tile
+
+
+def test_emulated_tile_kernel(emu, oracle, tmp_path):
+    """The tile kernel (bvg_tile.cuh: planner, staged stream, in-tile header parse, chain levels in shared memory, long records
+    split at the sync points) phase by phase on the host, a byte buffer with guard bytes as the block's shared memory."""
+    tiles, with_halo, halo_nodes, nlong, biggest = _emu_tile(emu, oracle, CNR)
+    assert tiles > 100 and biggest <= 1024
+    _emu_tile(emu, oracle, CNR, long_d=64, seg=16, chunk=16)                  # ~2000 records through the split path
+    st = _emu_tile(emu, oracle, CNR, long_d=8, seg=3, chunk=4, smem=24 * 1024, nt=64)   # a third of all records long, small tiles
+    assert st[3] > 100000 and st[1] > 0                                         # ... and tiles that need a halo
+    _emu_tile(emu, oracle, CNR, lo=1000, hi=200000)                            # a sub-range: tiles cut by the range at both ends
+    for k, w, r, ml in [(3, 7, 3, 4), (2, 1, 1, 0), (5, 16, -1, 2), (3, 0, 3, 4)]:  # -1: unbounded chains
+        off, succ, _ = graphs.copy_heavy(3000, seed=11 + k)
+        base = str(tmp_path / ("t%d_%d" % (k, w)))
+        tools.store_csr(base, off, succ, zetak=k, window=w, maxref=r, minlen=ml)
+        _emu_tile(emu, oracle, base, long_d=16, seg=8, chunk=8, smem=20 * 1024, nt=64, may_refuse=(r < 0))
+        if r < 0:
+            _emu_tile(emu, oracle, base, long_d=1024, smem=200 * 1024, nt=64, may_refuse=True)
+
+
+def _emu_stream(emu, oracle, base, lo=0, hi=None):
+    g = oracle.load(base)
+    hi = g.n if hi is None else hi
+    graph = np.fromfile(base + ".graph", dtype=np.uint8)
+    nb = len(graph)
+    graph = np.concatenate([graph, np.zeros(64, dtype=np.uint8)])
+    offs = g.offsets()
+    toff, tsucc = g.decode_range(0, g.n)
+    GUARD = 64
+    rows = np.full(len(tsucc) + 2 * GUARD, -77, dtype=np.int32)
+    out_off = np.zeros(g.n + 1, dtype=np.int64)
+    pf = np.zeros(g.n + 1, dtype=np.uint8)
+    out = np.zeros(2, dtype=np.uint64)
+    st = np.zeros(2, dtype=np.int64)
+    rc = emu.emu_stream_scan(graph.ctypes.data, nb, offs.ctypes.data, g.n, g.window, g.minlen, g.zetak, lo, hi, out_off.ctypes.data,
+                             rows[GUARD:].ctypes.data, pf.ctypes.data, out.ctypes.data, st.ctypes.data)
+    assert rc == 0
+    assert (int(out[0]), int(out[1])) == g.scan_range(lo, hi)
+    assert np.all(rows[:GUARD] == -77) and np.all(rows[GUARD + len(tsucc):] == -77), "row write out of bounds"
+    r = rows[GUARD:GUARD + len(tsucc)]
+    for x in np.nonzero(pf[:g.n])[0]:
+        if lo <= x < hi:
+            assert np.array_equal(r[toff[x]:toff[x + 1]], tsucc[toff[x]:toff[x + 1]]), x
+    return st.tolist()  # chunks, records whose intervals were merged by the fix-up step
+
+
+def test_emulated_stream_position_extras(emu, oracle, tmp_path):
+    """The stream-position extras kernel (bvg_stream.cuh): an entry per 2048-bit chunk, every lane walked through its chunk,
+    deferred interval merges, then the copied parts: checksum == oracle's scan, stored rows == oracle's lists."""
+    chunks, deferred = _emu_stream(emu, oracle, CNR)
+    assert chunks > 5000 and deferred > 100
+    for k, w, r, ml in [(3, 7, 3, 4), (2, 1, 1, 0), (5, 16, 10, 2), (3, 0, 3, 4)]:
+        off, succ, _ = graphs.copy_heavy(3000, seed=5)
+        base = str(tmp_path / ("q%d_%d" % (k, w)))
+        tools.store_csr(base, off, succ, zetak=k, window=w, maxref=r, minlen=ml)
+        _emu_stream(emu, oracle, base)

@@ -10,6 +10,7 @@
 #include "bvg_offsets.cuh"
 #include "bvg_boundaries.cuh"
 #include "bvg_tile.cuh"
+#include "bvg_stream.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -212,6 +213,11 @@ struct bvg_graph {
     int tile_nt = 256;
     uint32_t tile_smem = 0;
     int64_t long_scan_entries = 0;     // scratch of the long records somebody copies from (3 d entries each)
+    // stream-position entries of the extras kernel (bvg_stream.cuh): one per STREAM_CHUNK_BITS bits of the loaded stream
+    StreamEntry* d_stream_entries = nullptr;
+    int64_t stream_chunks = 0;
+    uint64_t stream_bit0 = 0;
+    mutable std::map<int32_t, uint64_t> offset_seen;   // host-side memo of record positions (guarded by mu)
     mutable std::mutex sched_mu;       // the length-bucketed schedules of the range-decode kernels are built on first use
     bool schedules_ready = false;
     // halo imported from the previous shard (bvg_halo_import)
@@ -698,17 +704,41 @@ static int ensure_schedules(const bvg_graph* cg) {
     return build_schedules(g);
 }
 
+// Entries of the stream-position extras kernel (bvg_stream.cuh): one thread per chunk.
+static int build_stream_entries(bvg_graph* g) {
+    g->stream_chunks = 0;
+    const int64_t nn = (int64_t)g->node_hi - g->node_lo;
+    if (nn == 0 || !g->def_codec || env_int("BVG_STREAM", 0, 0, 1) == 0) return BVG_OK;
+    if (g->max_outdeg > g->long_d && g->nlong == 0) return BVG_OK;  // no long index (chains too deep): the per-record kernels stay
+    cudaStream_t s = g->stream;
+    uint64_t o2[2];
+    CK(cudaMemcpyAsync(&o2[0], g->d_offsets, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&o2[1], g->d_offsets + nn, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    g->stream_bit0 = o2[0] - g->bit_base;
+    const int64_t nchunks = (int64_t)((o2[1] - o2[0] + STREAM_CHUNK_BITS - 1) / STREAM_CHUNK_BITS);
+    if (nchunks <= 0) return BVG_OK;
+    CK(dev_alloc((void**)&g->d_stream_entries, ((size_t)nchunks + 1) * sizeof(StreamEntry), g->stream));
+    if (g->zetak == 3) LAUNCH(k_stream_entries<3>, grid_for(nchunks + 1, 128), 128, 0, s, g->dev(), nchunks, g->stream_bit0, g->node_lo, g->d_long_nodes, g->nlong, g->long_d, g->long_index(), g->d_stream_entries);
+    else LAUNCH(k_stream_entries<0>, grid_for(nchunks + 1, 128), 128, 0, s, g->dev(), nchunks, g->stream_bit0, g->node_lo, g->d_long_nodes, g->nlong, g->long_d, g->long_index(), g->d_stream_entries);
+    CK(cudaGetLastError());
+    g->stream_chunks = nchunks;
+    return BVG_OK;
+}
+
 // Tile plan of the scan (bvg_tile.cuh): node costs, their running sum, greedy cuts per super-block (count, scan, write),
 // launch order by stream bits.
 static int build_tile_plan(bvg_graph* g) {
     g->tile_ok = false; g->ntiles = 0;
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
-    if (nn == 0 || !g->def_codec || g->window > 255 || env_int("BVG_TILE", 1, 0, 1) == 0) return BVG_OK;
+    // off by default: measured 28.8 ms per scan of the 1 B-arc benchmark graph against 5.9 ms of the per-record kernels
+    // (profiles/r02_tile.md: the phases of a tile are latency-bound, ~10 of 32 warps active)
+    if (nn == 0 || !g->def_codec || g->window > 255 || env_int("BVG_TILE", 0, 0, 1) == 0) return BVG_OK;
     if (g->max_outdeg > g->long_d && g->nlong == 0) return BVG_OK;  // chains too deep for the long index: general kernels
     cudaStream_t s = g->stream;
     g->tile_nt = env_int("BVG_TILE_NT", 256, 64, 1024);
-    if (g->tile_nt != 512 && g->tile_nt != 256) g->tile_nt = 256;
-    g->tile_smem = (uint32_t)env_int("BVG_TILE_SMEM_KB", g->tile_nt == 512 ? 112 : 55, 16, 226) * 1024u;
+    if (g->tile_nt != 512 && g->tile_nt != 256 && g->tile_nt != 64 && g->tile_nt != 32) g->tile_nt = 256;
+    g->tile_smem = (uint32_t)env_int("BVG_TILE_SMEM_KB", g->tile_nt == 512 ? 112 : g->tile_nt == 256 ? 55 : g->tile_nt == 64 ? 13 : 6, 4, 226) * 1024u;
     const uint32_t budget = tile_budget(g->tile_smem, g->tile_nt);
     GraphDev gd = g->dev();
     Tmp<int32_t> cost(s), counts(s);
@@ -819,9 +849,11 @@ static int build_index(bvg_graph* g, uint64_t* d_offsets_full, int64_t n_full, b
     int rs = build_parents(g);
     if (!rs) rs = build_long_index(g);
     tr.mark("parents + long index");
+    if (!rs) rs = build_stream_entries(g);
+    tr.mark("stream entries");
     if (!rs) rs = build_tile_plan(g);
     tr.mark("tile plan");
-    if (!rs && !g->tile_ok) { rs = build_schedules(g); tr.mark("schedules"); }
+    if (!rs && !g->tile_ok && env_int("BVG_LAZY_SCHEDULES", 0, 0, 1) == 0) { rs = build_schedules(g); tr.mark("schedules"); }
     return rs;
 }
 
@@ -831,7 +863,7 @@ static void destroy(bvg_graph* g) {
     // graph memory comes from the device's stream-ordered pool (kept warm): a later open reuses it without going back
     // to the driver, which is what makes open-scan-close cycles cheap
     void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
-                     g->d_tiles, g->d_tile_order, g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
+                     g->d_tiles, g->d_tile_order, g->d_stream_entries, g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
                      g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum };
     for (void* p : ptrs) if (p) dev_free(p, g->stream);
     cudaStreamSynchronize(g->stream);
@@ -1207,6 +1239,22 @@ static int fetch_rowoff(const bvg_graph* g, int32_t a, int32_t b, int64_t* va, i
     return BVG_OK;
 }
 
+// Record start positions of two nodes on the host (memoised like the row offsets).
+static int fetch_offsets(const bvg_graph* g, int32_t a, int32_t b, uint64_t* va, uint64_t* vb) {
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        auto ia = g->offset_seen.find(a), ib = g->offset_seen.find(b);
+        if (ia != g->offset_seen.end() && ib != g->offset_seen.end()) { *va = ia->second; *vb = ib->second; return BVG_OK; }
+    }
+    CK(cudaMemcpyAsync(va, g->d_offsets + (a - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(vb, g->d_offsets + (b - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->offset_seen.size() > 4096) g->offset_seen.clear();
+    g->offset_seen[a] = *va; g->offset_seen[b] = *vb;
+    return BVG_OK;
+}
+
 int bvg_range_arcs(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs) {
     int rc = range_check(g, from, to);
     if (rc) return rc;
@@ -1447,10 +1495,33 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
     static const int dbg_nostore = env_int("BVG_DEBUG_NOSTORE", 0, 0, 1);  // timing experiments only: no row stores, results are wrong
     static const bool ring = env_int("BVG_SCAN_RING", 1, 0, 1) != 0;  // stream staged in shared memory by cp.async (bvg_scan.cuh, WinRing)
-    // BVG_SCAN_V2=1: the residual loop of ScanExtras::resid_v2 (unrolled by the topup period, selects instead of the refill
-    // branch, second zeta_3 formulation, 64-bit fold).  Off until measured against the default on the GPU.
-    static const bool scan_v2 = env_int("BVG_SCAN_V2", 0, 0, 1) != 0;
-    if (g->def_codec && lean && g->zetak == 3 && ring && scan_v2) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
+    const bool stream_extras = g->d_stream_entries != nullptr && g->stream_chunks > 0;
+    if (stream_extras) {
+        // every record's extras and every residual run, long records included, by stream position (bvg_stream.cuh)
+        uint64_t oa, ob;
+        { const int rc = fetch_offsets(g, lo, to, &oa, &ob); if (rc) return rc; }
+        StreamArgs a{};
+        a.entries = g->d_stream_entries; a.nchunks = g->stream_chunks; a.bit0 = g->stream_bit0;
+        a.first_chunk = (int64_t)((oa - g->bit_base - g->stream_bit0) / STREAM_CHUNK_BITS);
+        const int64_t c1 = (int64_t)((ob - g->bit_base - g->stream_bit0 + STREAM_CHUNK_BITS - 1) / STREAM_CHUNK_BITS);
+        a.count = std::max<int64_t>(0, std::min<int64_t>(c1, g->stream_chunks) - a.first_chunk);
+        a.lo = lo; a.hi = to; a.from = from;
+        a.is_parent = g->d_is_parent; a.long_nodes = g->d_long_nodes; a.nlong = g->nlong; a.long_d = g->long_d;
+        a.li = li; a.long_tmp = ld.tmp; a.result = d_result; a.debug_nostore = dbg_nostore;
+        if (a.count > 0) {
+            Tmp<int32_t> defer(s);
+            CK(defer.alloc((size_t)a.count + 2));   // a lane defers at most one record; [count] is the counter
+            a.defer_list = defer.p; a.defer_count = (unsigned int*)(defer.p + a.count);
+            CK(cudaMemsetAsync(a.defer_count, 0, 4, s));
+            const int64_t lanes = (a.count + 32 * BVG_STREAM_GROUP - 1) / (32 * BVG_STREAM_GROUP) * 32;   // a warp per 32 * GROUP chunks
+            if (g->zetak == 3) LAUNCH_P(g, "k_stream_extras", (k_stream_extras<3, RowMap>), grid_for(lanes, STREAM_BLOCK), STREAM_BLOCK, 0, s, gd, a, rm);
+            else LAUNCH_P(g, "k_stream_extras", (k_stream_extras<0, RowMap>), grid_for(lanes, STREAM_BLOCK), STREAM_BLOCK, 0, s, gd, a, rm);
+            if (g->minlen != 0) {
+                if (g->zetak == 3) LAUNCH_P(g, "k_stream_ivfix", (k_stream_ivfix<3, RowMap>), sms * 2, 128, 0, s, gd, a, rm);
+                else LAUNCH_P(g, "k_stream_ivfix", (k_stream_ivfix<0, RowMap>), sms * 2, 128, 0, s, gd, a, rm);
+            }
+        }
+    }
     else if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
@@ -1458,7 +1529,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     else if (g->def_codec) LAUNCH_P(g, "k_scan_extras", k_scan_extras<true>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     if (g->nlong) {
-        if (g->n_items_resid) {
+        if (g->n_items_resid && !stream_extras) {
             if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
             else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
         }
@@ -1473,11 +1544,8 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             // 8 resident blocks per SM (64 registers) and 4 parent loads in flight per lane: measured against 8/8, 6/8 and
             // 5/16 (blocks / batch): 1.92, 2.12, 2.19, 2.52 ms for the three levels -- occupancy beats deeper batching here
             // (10 / 12 resident blocks, 48 / 40 registers: 1.89 -> 2.16 / 2.50 ms, spills)
-            // BVG_MERGE_V2=1: consumed-only children read their parent's row in aligned 16-byte groups (copied_fold_v2).
-            // Off until measured against the default on the GPU.
-            static const bool merge_v2 = env_int("BVG_MERGE_V2", 0, 0, 1) != 0;
-            if (g->def_codec && lean_m && merge_v2) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4, true>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
-            else if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            // (measured and dropped in round 2: parent rows read in aligned 16-byte groups, 1.89 -> 3.57 ms)
+            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
             else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }
@@ -1521,8 +1589,25 @@ static int enqueue_scan_tiles(const bvg_graph* g, int32_t from, int32_t to, unsi
     a.long_scr = scr.p;
     a.result = d_result;
     a.smem_bytes = g->tile_smem;
+    a.timeline = nullptr;
     const unsigned grid = (unsigned)(t1 - t0);
+    Tmp<unsigned long long> tline(s);
+    const char* tl_path = getenv("BVG_TILE_TIMELINE");  // debugging: per-block phase times dumped to this file after the scan
+    if (tl_path) { CK(tline.alloc((size_t)grid * 40)); CK(cudaMemsetAsync(tline.p, 0, (size_t)grid * 40 * 8, s)); a.timeline = tline.p; }
+    struct Dump {
+        const char* path; unsigned long long* p; unsigned grid; cudaStream_t s;
+        ~Dump() {
+            if (!path) return;
+            std::vector<unsigned long long> h((size_t)grid * 40);
+            if (cudaStreamSynchronize(s) == cudaSuccess && cudaMemcpy(h.data(), p, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                if (FILE* f = fopen(path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+            }
+            cudaGetLastError();
+        }
+    } dump{ tl_path, tline.p, grid, s };
     if (g->tile_nt == 512) return g->zetak == 3 ? launch_tile_scan<3, 512, 2>(g, a, grid, s) : launch_tile_scan<0, 512, 2>(g, a, grid, s);
+    if (g->tile_nt == 64) return g->zetak == 3 ? launch_tile_scan<3, 64, 16>(g, a, grid, s) : launch_tile_scan<0, 64, 16>(g, a, grid, s);
+    if (g->tile_nt == 32) return g->zetak == 3 ? launch_tile_scan<3, 32, 32>(g, a, grid, s) : launch_tile_scan<0, 32, 32>(g, a, grid, s);
     return g->zetak == 3 ? launch_tile_scan<3, 256, 4>(g, a, grid, s) : launch_tile_scan<0, 256, 4>(g, a, grid, s);
 }
 

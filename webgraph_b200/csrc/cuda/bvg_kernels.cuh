@@ -1,9 +1,9 @@
 // bvg_kernels.cuh -- the general ("any file") kernel set: index build at open, level-synchronous range decode,
 // per-query chain decode for random access, consume-only checksum.  One thread walks one record; reference chains
 // are resolved level by level (depth of the chain, <= maxrefcount for files the reference's writer produced,
-// BVGraph.java:2315,2326), each level reading parents' finished rows.  The tiled shared-memory kernels for the
-// default codings live in bvg_tile.cuh; this set is the fallback they defer to (giant lists, exotic codings,
-// unbounded chains) and the first-round correctness baseline.
+// BVGraph.java:2315,2326), each level reading parents' finished rows.  Two alternatives to the per-record scan kernels
+// were built and measured in round 2 and are kept, off by default: the tile kernel (bvg_tile.cuh, BVG_TILE=1) and the
+// stream-position extras kernel (bvg_stream.cuh, BVG_STREAM=1); profiles/r02_kernels.md has the numbers.
 #pragma once
 #include <type_traits>
 #include "bvg_device.cuh"
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // Every kind runs the same tight residual loop, preceded for records with intervals by a walk of the interval section
 // that folds its elements; stored records with intervals write their residuals right-aligned and merge the intervals in
 // front of them in a second walk (ScanExtras::iv_merge).
-template <int K, bool RING, bool V2 = false>
+template <int K, bool RING>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
                               int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all, int items) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
@@ -602,13 +602,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         w.begin(g, r.x, r.nout, r.pos, active, my_ring);
         if (has_iv) w.iv_fold(g); else w.iv_none(g);
         __syncwarp();
-        if (V2) {
-            if (__any_sync(0xffffffffu, store)) w.template resid_v2<true>(g, row, store);
-            else w.template resid_v2<false>(g, row, false);
-        } else {
-            if (__any_sync(0xffffffffu, store)) w.template resid<true>(g, row, store);
-            else w.template resid<false>(g, row, false);
-        }
+        if (__any_sync(0xffffffffu, store)) w.template resid<true>(g, row, store);
+        else w.template resid<false>(g, row, false);
         __syncwarp();
         if (store && has_iv) w.iv_merge(g, row);
         __syncwarp();
@@ -647,7 +642,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(G
 }
 
 // Merge step with the staged copy runs of bvg_scan.cuh (default codings).
-template <int MINB, int BATCH, bool V2 = false>
+template <int MINB, int BATCH>
 __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int store_all) {
     __shared__ int32_t runs[2 * COPY_RUNS * SCAN_BLOCK];
@@ -668,10 +663,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g
         __syncwarp();
         const int32_t* parent = active ? rm.at(r.px, r.prow) : nullptr;
         unsigned long long f = 0;
-        if (active && !store) f = V2 ? copied_fold_v2<2>(g, c, r.x, parent) : copied_fold<BATCH>(g, c, r.x, parent);
+        if (active && !store) f = copied_fold<BATCH>(g, c, r.x, parent);
         __syncwarp();
-        if (store) f = V2 ? copied_merge_v2<2>(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent)
-                          : copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
+        if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
         __syncwarp();
         if (fold) acc ^= f;
     }

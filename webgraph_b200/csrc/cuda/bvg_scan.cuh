@@ -126,7 +126,6 @@ struct WinT {
             if (LA == 3) { q0 = q1; q1 = q2; q2 = p0[idx]; }
         }
     }
-    __device__ __forceinline__ void skip_sel(uint32_t n) { skip(n); }
     __device__ __forceinline__ uint64_t gamma_slow(const GraphDev& g) {
         uint64_t p = pos(g);
         const uint64_t r = slow_gamma(g.words, g.nwords, &p);
@@ -243,17 +242,6 @@ struct WinRing {
             q = word(r);
         }
     }
-    // The same written with selects (resid_v2): a refill branch is taken by about half of the lanes on every trip, so the
-    // warp pays for both sides of it almost always.
-    __device__ __forceinline__ void skip_sel(uint32_t n) {  // n <= 32
-        s += n;
-        const bool adv = s >= 32u;
-        s &= 31u;
-        w0 = adv ? w1 : w0;
-        w1 = adv ? q : w1;
-        r += adv ? 1u : 0u;
-        if (adv) q = word(r);
-    }
     __device__ __forceinline__ uint64_t gamma_slow(const GraphDev& g) {
         uint64_t p = pos(g);
         const uint64_t v = slow_gamma(g.words, g.nwords, &p);
@@ -276,19 +264,6 @@ struct WinRing {
         return gamma_slow(g);
     }
 };
-
-// zeta_3 code of at most 32 bits (t >= 2^24, i.e. h <= 7), second formulation (resid_v2): with r the top 4h + 4 bits of
-// the window and P8 = 8^(h+1) its leading one, u = r ^ P8 is what follows the leading one; the short form (4h + 3 bits)
-// holds iff u < P8 / 4, its value + 1 is u / 2 + P8 / 8, and the long form's is u.  Same results as zeta_fast<3>.
-__device__ __forceinline__ void zeta3_fast_v2(uint32_t t, uint32_t& m, uint32_t& len) {
-    const uint32_t h = (uint32_t)__clz((int)t);
-    const uint32_t r = t >> (28u - 4u * h);
-    const uint32_t P8 = 8u << (3u * h);
-    const uint32_t u = r ^ P8;
-    const bool sh = u < (P8 >> 2);
-    m = sh ? (u >> 1) + (P8 >> 3) : u;
-    len = 4u * h + (sh ? 3u : 4u);
-}
 
 // zeta_k code that fits the 32-bit window: m = value + 1, len = code length.  K = 3 is BVGraph's default and gets
 // constants; K = 0 takes k at run time.  With h = leading zeros, P = 2^(hk): the bits after the unary part, read with
@@ -430,8 +405,6 @@ struct ScanExtras {
     int err;
     uint32_t ic;       // intervals (iv_fold)
     uint64_t iv_pos;   // bit position of the first interval's left extreme
-    unsigned long long acc2;  // residuals folded by resid_v2 (plain 64-bit XOR of x*MIX + y), joined in finish()
-    uint32_t n_acc2;          // how many
 
     __device__ __forceinline__ void fail(const GraphDev& g, int code) {
         report(g.err, code, x, b.pos(g) + g.bit_base);
@@ -439,7 +412,7 @@ struct ScanExtras {
     }
 
     __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active, ring_addr ring_slot = ring_addr()) {
-        x = x_; nout = 0; rc = 0; err = 0; v = 0; ic = 0; iv_pos = 0; acc2 = 0; n_acc2 = 0;
+        x = x_; nout = 0; rc = 0; err = 0; v = 0; ic = 0; iv_pos = 0;
         f.begin(x_);
         b.attach(ring_slot);
         if (!active) return;
@@ -534,65 +507,9 @@ struct ScanExtras {
         if (b.overrun() || b.pos(g) > g.bit_end - g.bit_base) fail(g, E_IO);
     }
 
-    // The residual loop rewritten for the instruction count (BVG_SCAN_V2=1; measured against resid() on the GPU before it
-    // becomes the default): four codes between two topups in an unrolled body (no per-code topup test, a quarter of the
-    // loop overhead), the window advanced with selects (skip_sel), the second formulation of the zeta_3 decode, and the
-    // checksum as a plain 64-bit add + XOR (the residuals' share of n is taken out of the 32-bit fold in finish()).
-    template <bool STORE>
-    __device__ __forceinline__ void resid_v2(const GraphDev& g, int32_t* __restrict__ row, bool store) {
-        if (rc <= 0) return;
-        const int k = g.c.zetak;
-        const unsigned long long base = (unsigned long long)(uint32_t)x * BVG_MIX;
-        unsigned long long acc = 0;
-        b.topup();
-        v = (uint32_t)(int32_t)((int64_t)x + nat2int(zeta_any<K>(b, g, k) - 1ull));  // :954
-        acc ^= base + v;
-        RowWriter<true> wr;
-        if (STORE) wr.begin(row + (nout - rc));
-        if (STORE && store) wr.put(v);
-        // Groups of up to four codes between two topups; a code that does not fit the 32-bit window ends its group and is
-        // read by the one out-of-line-sized step below (a single copy of the slow path in the loop).
-        int32_t i = 1;
-#pragma unroll 1
-        while (i < rc) {
-            b.topup();  // at most four words are consumed before the next one
-            const int32_t left = rc - i;
-            bool slow = false;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (!slow && u < left) {
-                    const uint32_t t = b.top();
-                    uint32_t m, len;
-                    bool fast;
-                    if (K == 3) { fast = t >= 0x1000000u; if (fast) zeta3_fast_v2(t, m, len); }
-                    else fast = zeta_fast<K>(t, k, m, len);
-                    if (fast) {
-                        b.skip_sel(len);
-                        v += m;  // :966 (gap + 1)
-                        acc ^= base + v;
-                        if (STORE && store) wr.put(v);
-                        i++;
-                    } else slow = true;
-                }
-            }
-            if (slow) {  // gap >= 2^24: up to two words, between two out-of-turn topups
-                b.topup();
-                v += (uint32_t)zeta_any<K>(b, g, k);
-                b.topup();
-                acc ^= base + v;
-                if (STORE && store) wr.put(v);
-                i++;
-            }
-        }
-        if (STORE && store) wr.flush();
-        acc2 ^= acc;
-        n_acc2 += (uint32_t)rc;  // folded here, not in the 32-bit halves
-        if (b.overrun() || b.pos(g) > g.bit_end - g.bit_base) fail(g, E_IO);
-    }
-
     __device__ __forceinline__ unsigned long long finish() {
-        f.n = (uint32_t)nout - n_acc2;  // n_acc2, acc2: successors resid_v2 folded on its own (0 with resid())
-        return err ? 0ull : f.finish(x) ^ acc2;
+        f.n = (uint32_t)nout;
+        return err ? 0ull : f.finish(x);
     }
 };
 
@@ -642,18 +559,6 @@ struct CopyRunsT {
         }
     }
     __device__ __forceinline__ bool done() const { return pos == end && r == nr && bi > bc; }
-    // next run [s, e) of parent positions as a whole (copied_fold_v2); false when the list is exhausted
-    __device__ __forceinline__ bool next_run(const GraphDev& g, uint32_t& s, uint32_t& e) {
-        if (r == nr) {
-            if (bi > bc) return false;
-            stage(g);
-            if (nr == 0) return false;
-        }
-        s = (uint32_t)st[2 * r * stride];
-        e = (uint32_t)st[(2 * r + 1) * stride];
-        r++;
-        return true;
-    }
     // next parent position to copy; false when the list is exhausted
     __device__ __forceinline__ bool next(const GraphDev& g, uint32_t& at) {
         if (pos == end) {
@@ -695,55 +600,6 @@ __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CR&
     return f.finish(x);
 }
 
-// The same with the parent's row read in aligned 16-byte groups (BVG_MERGE_V2=1; to be measured against copied_fold on
-// the GPU before it becomes the default).  copied_fold issues one 4-byte load per copied successor; the merge kernels are
-// latency-bound on exactly those loads (IPC 1.2-1.4, long-scoreboard stall 10-12 warps per issue).  Copy runs are short
-// and close together, so here the row is streamed group by group from the first copied position on -- four successors
-// per load, NG loads in flight -- and every slot is tested against the current run; groups that lie wholly inside a
-// skipped block are jumped over.  Slots are counted from the 16-byte boundary at or before the row (slot = position +
-// mis), so the slots in front of the row and behind it belong to neighbouring rows: they are loaded and ignored, and they
-// never leave the allocation (rows live in library-owned buffers: 512-byte aligned, sizes rounded up to 512 bytes).
-template <int NG>
-__device__ __forceinline__ unsigned long long copied_fold_v2(const GraphDev& g, CopyRuns& c, int32_t x, const int32_t* __restrict__ parent) {
-    Fold32 f;
-    f.begin(x);
-    uint32_t rs, re;
-    if (!c.next_run(g, rs, re)) return f.finish(x);
-    const uint32_t mis = (uint32_t)(((uintptr_t)parent) >> 2) & 3u;
-    const uint32_t glast = (c.dp + mis - 1u) >> 2;  // dp >= 1: a run exists
-    rs += mis; re += mis;                           // slot space
-    uint32_t gi = rs >> 2;
-    bool more = true;
-#pragma unroll 1
-    while (more) {
-        uint32_t val[4 * NG];
-#pragma unroll
-        for (int u = 0; u < NG; u++) {
-            const uint32_t gq = umin32(gi + (uint32_t)u, glast);
-#ifdef BVG_HOST_EMULATION
-            for (int e = 0; e < 4; e++) {  // element-wise and guarded: the emulated rows are not padded to 16 bytes
-                const int64_t idx = (int64_t)gq * 4 + e - (int64_t)mis;
-                val[4 * u + e] = idx >= 0 && idx < (int64_t)c.dp ? (uint32_t)parent[idx] : 0xdeadbeefu;
-            }
-#else
-            const uint4 q = *(reinterpret_cast<const uint4*>(parent - mis) + gq);
-            val[4 * u + 0] = q.x; val[4 * u + 1] = q.y; val[4 * u + 2] = q.z; val[4 * u + 3] = q.w;
-#endif
-        }
-#pragma unroll
-        for (int t = 0; t < 4 * NG; t++) {
-            const uint32_t slot = gi * 4u + (uint32_t)t;
-            if (more && slot >= re) {  // the run ended at the slot before: the next one starts at least one slot further on
-                more = c.next_run(g, rs, re);
-                rs += mis; re += mis;
-            }
-            if (more && slot >= rs) { f.add(val[t]); f.n++; }
-        }
-        gi = umax32(gi + (uint32_t)NG, rs >> 2);
-    }
-    return f.finish(x);
-}
-
 // somebody copies from x: merge the copied successors, forward and in place, with the extras at row[copied .. d)
 // (MergedIntIterator.java:50-74: ascending union, equal heads once; a list that loses duplicates is padded with -1 as
 // BVGraphNodeIterator does when it drains, BVGraph.java:1210).  Folds the copied successors only: the extras were
@@ -781,72 +637,6 @@ __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CR
         }
     }
     wr.flush();
-    return f.finish(x);
-}
-
-// copied_merge with the parent's row read in aligned 16-byte groups, as copied_fold_v2 does (BVG_MERGE_V2=1).  The merge is
-// driven by the parent's side: for every copied successor a, the own extras below a are moved down first, then a itself
-// (equal heads once).  copied_merge pays one dependent load round trip per copied successor -- c.next(), parent[at],
-// compare -- with nothing in flight; here NG groups are.  Same in-place argument: the write index never overtakes the
-// unread extras while the parent yields no more than `copied` successors, and every write is bounded by d.
-template <int NG>
-__device__ __forceinline__ unsigned long long copied_merge_v2(const GraphDev& g, CopyRuns& c, int32_t x, int32_t d, int32_t copied,
-                                                              int32_t* row, const int32_t* __restrict__ parent) {
-    Fold32 f;
-    f.begin(x);
-    int32_t j = copied, k = 0;
-    uint32_t bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
-    uint32_t rs, re;
-    bool more = c.next_run(g, rs, re);
-    if (more) {
-        const uint32_t mis = (uint32_t)(((uintptr_t)parent) >> 2) & 3u;
-        const uint32_t glast = (c.dp + mis - 1u) >> 2;
-        rs += mis; re += mis;
-        uint32_t gi = rs >> 2;
-#pragma unroll 1
-        while (more) {
-            uint32_t val[4 * NG];
-#pragma unroll
-            for (int u = 0; u < NG; u++) {
-                const uint32_t gq = umin32(gi + (uint32_t)u, glast);
-#ifdef BVG_HOST_EMULATION
-                for (int e = 0; e < 4; e++) {
-                    const int64_t idx = (int64_t)gq * 4 + e - (int64_t)mis;
-                    val[4 * u + e] = idx >= 0 && idx < (int64_t)c.dp ? (uint32_t)parent[idx] : 0xdeadbeefu;
-                }
-#else
-                const uint4 q = *(reinterpret_cast<const uint4*>(parent - mis) + gq);
-                val[4 * u + 0] = q.x; val[4 * u + 1] = q.y; val[4 * u + 2] = q.z; val[4 * u + 3] = q.w;
-#endif
-            }
-#pragma unroll
-            for (int t = 0; t < 4 * NG; t++) {
-                const uint32_t slot = gi * 4u + (uint32_t)t;
-                if (more && slot >= re) {
-                    more = c.next_run(g, rs, re);
-                    rs += mis; re += mis;
-                }
-                if (more && slot >= rs) {
-                    const uint32_t a = val[t];
-                    while (bv < a && k < d) {  // own extras below a (bv is 0xffffffff once they are used up)
-                        row[k++] = (int32_t)bv;
-                        j++;
-                        bv = j < d ? (uint32_t)row[j] : 0xffffffffu;
-                    }
-                    if (k < d) {
-                        row[k++] = (int32_t)a;
-                        f.add(a); f.n++;
-                        if (a == bv) { j++; bv = j < d ? (uint32_t)row[j] : 0xffffffffu; }  // equal heads are emitted once
-                    } else more = false;  // a malformed record copies more than its outdegree: stop, the checksum will tell
-                }
-            }
-            gi = umax32(gi + (uint32_t)NG, rs >> 2);
-        }
-    }
-    if (k != j) {  // duplicates were dropped: move the remaining extras down and pad (BVGraph.java:1210)
-        while (j < d && k < d) row[k++] = row[j++];
-        while (k < d) row[k++] = -1;
-    }
     return f.finish(x);
 }
 

@@ -49,6 +49,7 @@ struct TileSh {
     int32_t err;
     uint32_t bucket[TILE_BUCKETS + 1];
     uint32_t levcnt[TILE_LEVELS + 2];
+    uint32_t long_cum[TILE_MAX_LONG + 1];               // running number of parts of the long records in the current phase
 };
 
 // Shared memory a tile needs: planner and kernel use the same arithmetic.
@@ -78,6 +79,7 @@ struct TileArgs {
     int32_t* long_scr;                   // 3 d entries per long record somebody copies from, at LongMeta.scan_off
     unsigned long long* result;          // FOLD_SLOTS slot pairs (arcs, XOR)
     uint32_t smem_bytes;
+    unsigned long long* timeline;        // debugging (BVG_TILE_TIMELINE): per block (tile, start ns, phase ends ..., sm), 8 words each
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -546,29 +548,32 @@ struct Tile {
         return ((L.stored ? m.d : m.copied) + li.chunk - 1) / li.chunk;
     }
 
-    // The three long phases as loops over (record, part) for thread `tid` of `nt`.
-    __device__ __forceinline__ void long_resid_phase(int tid, int nt, unsigned long long& acc, long long& arcs) {
+    // The three long phases.  The parts of all long records of the tile form one list (long_cum = running part counts,
+    // written by one thread before the phase): thread `tid` of `nt` takes parts tid, tid + nt, ... so that the parts of
+    // different records run side by side.
+    // kind 0: residual segments, 1: extras chunks, 2: merge chunks of the records at `level`
+    __device__ __forceinline__ void long_count(int kind, int32_t level) {
+        uint32_t run = 0;
         for (int k = 0; k < nlong; k++) {
+            sh->long_cum[k] = run;
             const LongRec L = long_rec(k);
             if (!L.active) continue;
-            const int32_t n = long_resid_parts(*L.m);
-            for (int32_t p = tid; p < n; p += nt) long_resid_part(L, p, acc, arcs);
+            if (kind == 0) run += (uint32_t)long_resid_parts(*L.m);
+            else if (kind == 1) run += (uint32_t)long_extras_parts(L);
+            else if ((int32_t)lvl[L.local] == level) run += (uint32_t)long_merge_parts(L);
         }
+        sh->long_cum[nlong] = run;
     }
-    __device__ __forceinline__ void long_extras_phase(int tid, int nt, unsigned long long& acc, long long& arcs) {
-        for (int k = 0; k < nlong; k++) {
+    __device__ __forceinline__ void long_phase(int kind, int tid, int nt, unsigned long long& acc, long long& arcs) {
+        const uint32_t total = sh->long_cum[nlong];
+        int k = 0;
+        for (uint32_t it = (uint32_t)tid; it < total; it += (uint32_t)nt) {
+            while (sh->long_cum[k + 1] <= it) k++;
             const LongRec L = long_rec(k);
-            if (!L.active) continue;
-            const int32_t n = long_extras_parts(L);
-            for (int32_t p = tid; p < n; p += nt) long_extras_part(L, p, acc, arcs);
-        }
-    }
-    __device__ __forceinline__ void long_merge_phase(int32_t level, int tid, int nt, unsigned long long& acc, long long& arcs) {
-        for (int k = 0; k < nlong; k++) {
-            const LongRec L = long_rec(k);
-            if (!L.active || (int32_t)lvl[L.local] != level) continue;
-            const int32_t n = long_merge_parts(L);
-            for (int32_t p = tid; p < n; p += nt) long_merge_part(L, p, acc, arcs);
+            const int32_t part = (int32_t)(it - sh->long_cum[k]);
+            if (kind == 0) long_resid_part(L, part, acc, arcs);
+            else if (kind == 1) long_extras_part(L, part, acc, arcs);
+            else long_merge_part(L, part, acc, arcs);
         }
     }
 };
@@ -718,6 +723,9 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_scan(GraphDev g, TileArgs a) 
     T.carve(smem, a.smem_bytes, NT, e, g, a);
     unsigned long long acc = 0;
     long long arcs = 0;
+    unsigned long long tl[8];
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (a.timeline && tid == 0) { tl[0] = (unsigned long long)t_idx; tl[1] = now(); }
     if (tid == 0) {
         mbar_init(&T.sh->mbar, 1);
         typename Tile<K>::RunCopy rc[TILE_MAX_LONG + 1];
@@ -737,30 +745,51 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_scan(GraphDev g, TileArgs a) 
     __syncthreads();
     T.levels(tid, NT);
     __syncthreads();
+    constexpr int NW = NT / 32;
     if (wid == 0) T.scan_buckets(lane);
-    else if (wid == 1) T.scan_levels(lane);
-    else if (wid == 2) T.scan_rows(lane);
+    if (wid == 1 % NW) T.scan_levels(lane);
+    if (wid == 2 % NW) T.scan_rows(lane);
     __syncthreads();
     T.scatter(tid, NT);
     __syncthreads();
+    if (a.timeline && tid == 0) tl[2] = now();
     // level 0: residual segments of the long records, then the short records from the ticket
-    T.long_resid_phase(tid, NT, acc, arcs);
+    if (T.nlong) {
+        if (tid == 0) T.long_count(0, 0);
+        __syncthreads();
+        T.long_phase(0, tid, NT, acc, arcs);
+    }
     {
         const uint32_t nE = T.sh->nE;
+        unsigned long long w0 = 0, wmax = 0, wbase = 0, nit = 0;
+        if (a.timeline) w0 = now();
         for (;;) {
             const uint32_t base = warp_ticket(&T.sh->next_item, 32u);
             if (base >= nE) break;
             const uint32_t it = base + (uint32_t)lane;
+            unsigned long long i0 = 0;
+            if (a.timeline) i0 = now();
             T.extras_item(it < nE ? (int32_t)T.ordE[it] : -1, acc, arcs);
+            if (a.timeline) { __syncwarp(); const unsigned long long dt = now() - i0; nit++; if (dt > wmax) { wmax = dt; wbase = base; } }
+        }
+        if (a.timeline && lane == 0) {
+            unsigned long long* w = a.timeline + (size_t)blockIdx.x * 40 + 8 + (wid & 7) * 4;
+            w[0] = w0; w[1] = now(); w[2] = nit; w[3] = (wmax << 32) | wbase;
         }
     }
+    if (a.timeline && tid == 0) tl[3] = now();
     __syncthreads();
+    if (a.timeline && tid == 0) tl[4] = now();
     if (T.nlong) {
-        T.long_extras_phase(tid, NT, acc, arcs);
+        if (tid == 0) T.long_count(1, 0);
+        __syncthreads();
+        T.long_phase(1, tid, NT, acc, arcs);
         __syncthreads();
     }
+    if (a.timeline && tid == 0) tl[5] = now();
     const int32_t maxlevel = T.sh->maxlevel;
     for (int32_t level = 1; level <= maxlevel; level++) {
+        if (T.nlong && tid == 0) T.long_count(2, level);   // read after the barrier that ends the short merges below
         uint32_t la, lb;
         T.level_range(level, la, lb);
         for (uint32_t base = la + (uint32_t)(tid & ~31); base < lb; base += NT) {
@@ -769,8 +798,18 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_scan(GraphDev g, TileArgs a) 
             if (level >= TILE_LEVELS && i >= 0 && (int32_t)T.lvl[i] != level) i = -1;  // the deep levels share one list
             T.merge_item(i, tid, NT, acc);
         }
-        if (T.nlong) T.long_merge_phase(level, tid, NT, acc, arcs);
+        if (T.nlong) {
+            __syncthreads();
+            T.long_phase(2, tid, NT, acc, arcs);
+        }
         __syncthreads();
+    }
+    if (a.timeline && tid == 0) {
+        tl[6] = now();
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tl[7] = ((unsigned long long)smid << 32) | (unsigned)T.nn | ((unsigned long long)(unsigned)T.nlong << 16);
+        for (int i = 0; i < 8; i++) a.timeline[(size_t)blockIdx.x * 40 + i] = tl[i];
     }
     if (a.result) warp_fold(acc, arcs, a.result);
 }

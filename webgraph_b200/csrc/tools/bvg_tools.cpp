@@ -448,17 +448,19 @@ struct Generator {
     // successors of x; block_lists[y - block_start] holds the lists of the earlier nodes of the same block
     void successors(int32_t x, int32_t block_start, const std::vector<std::vector<int32_t>>& block_lists, std::vector<int32_t>& out) const {
         out.clear();
-        const int32_t d = degree(x);
+        int32_t d = degree(x);
         if (d <= 0) return;
         Rng rng{ mix64(p.seed * 0x2545F4914F6CDD1DULL + (uint64_t)x) };
         const int32_t back = x - block_start;
         if (back > 0 && rng.unit() < p.p_copy) {
             const int32_t r = 1 + (int32_t)rng.below((uint32_t)std::min(7, back));
             const std::vector<int32_t>& proto = block_lists[(size_t)(back - r)];
+            if (p.p_same_degree > 0.0 && !proto.empty() && rng.unit() < p.p_same_degree)
+                d = (int32_t)std::min<int64_t>((int64_t)proto.size() + (int64_t)rng.below(4), (int64_t)p.n - 1);
             size_t pos = 0;
             bool copying = rng.unit() < 0.8;
             while (pos < proto.size() && (int32_t)out.size() < d) {
-                const double mean = copying ? 8.0 : 3.0;
+                const double mean = copying ? p.copy_run : p.skip_run;
                 size_t run = 1 + (size_t)(-mean * std::log(1.0 - rng.unit()));
                 run = std::min(run, proto.size() - pos);
                 if (copying) for (size_t i = 0; i < run && (int32_t)out.size() < d; i++) out.push_back(proto[pos + i]);
@@ -467,7 +469,7 @@ struct Generator {
             }
         }
         if ((int32_t)out.size() < d && rng.unit() < p.p_interval) {
-            const int32_t k = 1 + (int32_t)rng.below(3);
+            const int32_t k = 1 + (int32_t)rng.below((uint32_t)std::max(1, p.interval_max));
             for (int32_t i = 0; i < k && (int32_t)out.size() < d; i++) {
                 int64_t start = (int64_t)x + (int64_t)rng.below(8192) - 4096;
                 const int32_t len = 4 + (int32_t)rng.below(17);
@@ -481,7 +483,7 @@ struct Generator {
         for (int32_t i = 0; i < missing; i++) {
             int64_t t;
             if (rng.unit() < p.p_local) {  // log-uniform distance up to 2^16, either side
-                const uint32_t bits = 1 + rng.below(16);
+                const uint32_t bits = 1 + rng.below((uint32_t)std::min(30, std::max(1, p.local_bits)));
                 const int64_t dist = 1 + (int64_t)rng.below(1u << bits);
                 t = (rng.next() & 1) ? (int64_t)x + dist : (int64_t)x - dist;
                 if (t < 0) t = -t;
@@ -547,6 +549,7 @@ int64_t bvgt_write_codes(int coding, int32_t k, const uint64_t* values, int64_t 
 void bvgt_gen_defaults(bvgt_gen_params* p, int32_t n, int64_t target_arcs, uint64_t seed) {
     p->n = n; p->target_arcs = target_arcs; p->seed = seed;
     p->zipf_s = 0.65; p->p_copy = 0.5; p->p_interval = 0.1; p->p_local = 0.5; p->block = 1024; p->max_degree = 1 << 22;
+    p->copy_run = 8.0; p->skip_run = 3.0; p->local_bits = 16; p->interval_max = 3; p->p_same_degree = 0.0;
 }
 
 int bvgt_generate_store(const char* basename, const bvgt_gen_params* gp,

@@ -36,7 +36,8 @@ class StoreStats(C.Structure):
 class GenParams(C.Structure):
     _fields_ = [("n", C.c_int32), ("target_arcs", C.c_int64), ("seed", C.c_uint64), ("zipf_s", C.c_double),
                 ("p_copy", C.c_double), ("p_interval", C.c_double), ("p_local", C.c_double), ("block", C.c_int32),
-                ("max_degree", C.c_int32)]
+                ("max_degree", C.c_int32), ("copy_run", C.c_double), ("skip_run", C.c_double), ("local_bits", C.c_int32),
+                ("interval_max", C.c_int32), ("p_same_degree", C.c_double)]
 
 
 _lib = None
