@@ -7,7 +7,7 @@
 A "step" is one whole-graph consume-only scan (what the reference's SpeedTest sequential loop does,
 reference src/it/unimi/dsi/webgraph/test/SpeedTest.java:157-185) of a synthetic power-law BVGraph
 (1 B arcs, zeta_3, W=7, R=3 at N=1: BASELINE config C3).  At N>1 the same graph is range-sharded into
-bit-balanced contiguous node ranges, one per rank (config C5, strong scaling); every step the shards
+cost-balanced contiguous node ranges, one per rank (config C5, strong scaling); every step the shards
 exchange their boundary reference lists with one NCCL all-gather and each rank scans its shard.
 
 value      : arcs decoded by all ranks / max-over-ranks device time, inputs resident in HBM
@@ -15,8 +15,13 @@ e2e        : same metric through the public call with HOST buffers: bvg_scan_mem
              of the rank's .graph range and .offsets from pinned memory, decodes the offsets, builds the index, scans and
              brings (arcs, checksum) back; the node range goes in --e2e-pieces pieces over two streams so that piece
              p + 1 crosses PCIe while piece p is indexed and scanned (1 piece = open + scan + close)
-roofline   : dominant kernel's algorithmic bytes (.graph bits of the scanned range / 8) / its CUDA-event time,
-             against MEASURED_PEAKS.json's hbm_gbs
+roofline   : HBM-read roofline.  `achieved` / `frac` are the dominant kernel FAMILY's: the stream bytes its launches of one
+             step read (kernel_bytes) / the summed CUDA-event time of those launches (kernel_ms), against
+             MEASURED_PEAKS.json's hbm_gbs; whole_step_frac is the same for the whole step (every stream byte the step's
+             kernels read / ms_per_step); `kernels` lists every family (ms and launches per step); `traffic` is the DRAM
+             traffic of one step from the committed ncu capture of this command (profiles/r02_traffic.json), null where no
+             capture exists (N > 1); `other_configs` holds the other BASELINE configs measured on the same graph (C4 random
+             access, materialising decode, NodeIterator route, open without .offsets) and the second workload (web-like)
 cpu_baseline: the oracle (C restatement of BVGraph.nodeIterator(), kind "port": no JVM exists in the image) on one
              host core, bounded sample
 """
@@ -33,8 +38,16 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# the second workload: lands near the reference's own fixture (cnr-2000: 3.56 bits/arc, 66 % copied arcs, avgref 1.38):
+# ~3.7 bits/arc, 64 % copied arcs, avgref 1.26 at 1 B arcs
 WEBLIKE = dict(zipf_s=0.45, p_copy=0.97, copy_run=40.0, skip_run=1.5, p_interval=0.4, p_local=0.97, local_bits=9, max_degree=3000,
                interval_max=2, p_same_degree=0.95)
+WORKLOADS = {
+    "powerlaw": dict(nodes=32_000_000, arcs=1_070_000_000, tag="pl",
+                     name="consume-only sequential scan of a 1 B-arc synthetic power-law BVGraph (zeta_3, W=7, R=3, minLen=4)"),
+    "weblike": dict(nodes=64_000_000, arcs=900_000_000, tag="web",
+                    name="consume-only sequential scan of a 1 B-arc synthetic web-like BVGraph (copy-heavy: ~64 % copied arcs, ~3.7 bits/arc; zeta_3, W=7, R=3, minLen=4)"),
+}
 METRIC = "decoded_edges_per_second"
 UNIT = "edges/s"
 
@@ -45,37 +58,38 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nodes", type=int, default=32_000_000)
-    ap.add_argument("--arcs", type=int, default=1_070_000_000)  # dedup shortfall ~6 %: lands on ~1.0e9 arcs
+    ap.add_argument("--workload", default="powerlaw", choices=sorted(WORKLOADS),
+                    help="the headline workload; the other one is measured as roofline.other_configs (unless --no-second-workload)")
+    ap.add_argument("--nodes", type=int, default=0, help="override the workload's node count (experiments)")
+    ap.add_argument("--arcs", type=int, default=0, help="override the workload's arc target (dedup shortfall ~6 %%)")
     ap.add_argument("--seed", type=int, default=0x5EED)
-    ap.add_argument("--workload", default="powerlaw", choices=["powerlaw", "weblike"],
-                    help="powerlaw: the no-locality power-law graph BASELINE's metric is quoted on; weblike: a copy-heavy graph with cnr-2000's mix")
-    ap.add_argument("--max-degree", type=int, default=1 << 22, help="experiments only: cap on the generator's outdegree law")
+    ap.add_argument("--max-degree", type=int, default=1 << 22, help="experiments only: cap on the power-law generator's outdegree law")
     ap.add_argument("--workdir", default=os.environ.get("BVG_BENCH_DIR", "/tmp/bvg_bench"))
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-pieces", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the informational random-access / materialise legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs (random access, materialise, NodeIterator, open without .offsets)")
+    ap.add_argument("--no-second-workload", action="store_true")
     ap.add_argument("--random-nodes", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample-arcs", type=float, default=3.0e8)
+    ap.add_argument("--profile-only", default="", choices=["", "scan", "c4"],
+                    help="for ncu captures (profiles/traffic.py): only the timed scan / only the C4 batch, nothing else launched after the open")
     return ap.parse_args()
 
 
-def graph_files(args, rank, world, barrier):
+def graph_files(args, workload, rank, barrier):
     """Rank 0 generates + compresses the synthetic graph once per box (host tools, all cores); others wait."""
     from webgraph_b200 import tools
-    kw = dict(max_degree=args.max_degree)
-    tag = "pl"
-    if args.workload == "weblike":
-        # lands near the reference's own fixture (cnr-2000: 3.56 bits/arc, 66 % copied arcs, avgref 1.38): ~3.6 bits/arc, 63 % copied, avgref 1.26
-        kw = dict(WEBLIKE)
-        tag = "web"
-    base = os.path.join(args.workdir, "%s_n%d_m%d_s%x_d%d" % (tag, args.nodes, args.arcs, args.seed, args.max_degree), "g")
+    w = WORKLOADS[workload]
+    nodes = args.nodes or w["nodes"]
+    arcs = args.arcs or w["arcs"]
+    kw = dict(WEBLIKE) if workload == "weblike" else dict(max_degree=args.max_degree)
+    base = os.path.join(args.workdir, "%s_n%d_m%d_s%x_d%d" % (w["tag"], nodes, arcs, args.seed, args.max_degree), "g")
     meta = base + ".meta.json"
     if rank == 0 and not os.path.exists(meta):
         os.makedirs(os.path.dirname(base), exist_ok=True)
         t = time.time()
-        st = tools.generate_store(base, args.nodes, args.arcs, seed=args.seed, window=7, maxref=3, minlen=4, zetak=3,
+        st = tools.generate_store(base, nodes, arcs, seed=args.seed, window=7, maxref=3, minlen=4, zetak=3,
                                   threads=os.cpu_count() or 1, **kw)
         st["generate_seconds"] = time.time() - t
         with open(meta + ".tmp", "w") as f:
@@ -136,13 +150,22 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture of
-    this same workload (profiles/r01_traffic.json, written by profiles/summarise.py); None when there is no capture."""
+
+def hbm_peak():
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)
-        return t["kernels"].get(kernel)
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ncu_traffic(workload, n_gpus):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one step of this workload, per kernel family and in total,
+    from the committed ncu capture of this same command (profiles/r02_traffic.json, written by profiles/traffic.py); None when
+    there is no capture for this (workload, N)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)[workload][str(n_gpus)]
     except Exception:
         return None
 
@@ -161,11 +184,22 @@ def cpu_port_baseline(base, sample_arcs, threads):
     return arcs, dt, hi
 
 
-def workload_name(n_gpus):
+def workload_name(workload, n_gpus):
     """config.workload, the same string on both arms (BASELINE configs C3 / C5)."""
+    name = WORKLOADS[workload]["name"]
     if n_gpus <= 1:
-        return "C3: consume-only sequential scan of a 1 B-arc synthetic power-law BVGraph (zeta_3, W=7, R=3, minLen=4)"
-    return "C5: the C3 graph range-sharded over %d GPUs (bit-balanced node ranges), NCCL all-gather of boundary reference lists per step" % n_gpus
+        return "C3: " + name
+    return "C5: the C3 graph (%s) range-sharded over %d GPUs, NCCL all-gather of boundary reference lists per step" % (name, n_gpus)
+
+
+def config_of(args, workload, st, world):
+    """The same dictionary on both arms (the driver compares them)."""
+    return {"workload": workload_name(workload, world), "nodes": st["nodes"], "arcs": st["arcs"],
+            "bits_per_arc": st["graph_bits"] / max(st["arcs"], 1), "graph_bytes": (int(st["graph_bits"]) + 7) // 8,
+            "avg_ref": st["tot_ref"] / max(st["nodes"], 1), "copied_arcs_fraction": st["copied_arcs"] / max(st["arcs"], 1),
+            "max_outdegree": st["max_outdegree"], "seed": args.seed, "generator": "webgraph_b200.tools.generate_store (SURVEY 8d)",
+            "l2": "the input stream (%.2f GB) is far larger than L2; no flush needed" % (st["graph_bits"] / 8e9),
+            "mode": "consume-only scan: every successor consumed, (arcs, XOR checksum) verified against the generator's"}
 
 
 def run_reference(args, rank, world):
@@ -174,7 +208,7 @@ def run_reference(args, rank, world):
     host threads exactly like ImmutableGraph.splitNodeIterators."""
     if rank != 0:
         return
-    base, st = graph_files(args, 0, 1, lambda: None)
+    base, st = graph_files(args, args.workload, 0, lambda: None)
     threads = os.cpu_count() or 1
     # each step: a bounded sample sized for ~a few seconds with all threads
     sample = min(float(st["arcs"]), args.cpu_sample_arcs * max(1, threads // 4))
@@ -189,16 +223,376 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(args.gpus),
-                       "nodes": st["nodes"], "arcs": st["arcs"], "bits_per_arc": st["graph_bits"] / max(st["arcs"], 1),
-                       "graph_bytes": (int(st["graph_bits"]) + 7) // 8, "max_outdegree": st["max_outdegree"], "seed": args.seed,
-                       "generator": "webgraph_b200.tools.generate_store (SURVEY 8d)",
-                       "mode": "the same graph scanned by the CPU port of BVGraph.nodeIterator() (every successor consumed, arcs + XOR checksum)"},
+            "config": config_of(args, args.workload, st, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "first %d nodes (%d arcs) per step, all host threads, node ranges split like splitNodeIterators" % (hi, arcs)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+class Bench:
+    """One workload on this rank's shard: the timed scan, its roofline object, and (for the headline workload) the e2e leg and
+    the other configs."""
+
+    def __init__(self, args, workload, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        from webgraph_b200 import bvgraph, sharding
+        self.torch, self.dist, self.bvgraph, self.sharding = torch, dist, bvgraph, sharding
+        self.args, self.workload, self.rank, self.local_rank, self.world = args, workload, rank, local_rank, world
+        self.dev = torch.device("cuda", local_rank)
+        self.L = bvgraph.lib()
+        self.base, self.st = graph_files(args, workload, rank, self.barrier)
+        self.n_total, self.m_total = int(self.st["nodes"]), int(self.st["arcs"])
+        graph_np = np.fromfile(self.base + ".graph", dtype=np.uint8)
+        offs_np = np.fromfile(self.base + ".offsets", dtype=np.uint8)
+        self.graph_pin = torch.from_numpy(graph_np).pin_memory()   # host copies in pinned memory: the e2e leg uploads them every step
+        self.offs_pin = torch.from_numpy(offs_np).pin_memory()
+        self.bounds = bvgraph.plan_shards(self.base, world)   # equal bits, cuts where no reference crosses
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.stream = torch.cuda.current_stream()
+        self.rebalanced = []
+        if world > 1 and not os.environ.get("BVG_BENCH_NO_REBALANCE"):
+            self.rebalance(2)
+
+    def rebalance(self, rounds):
+        """Equal bits are not equal time (long records, copy density): every rank times a few scans of its shard, the times are
+        all-gathered and the cuts moved to equal shares of the measured cost (bvg_replan_shards).  Setup, not timed."""
+        torch, dist, bvgraph = self.torch, self.dist, self.bvgraph
+        for _ in range(rounds):
+            g = self.open_shard()
+            g.scanRange(self.lo, self.hi)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            res = torch.zeros(2, dtype=torch.int64, device=self.dev)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                bvgraph._check(self.L.bvg_scan_range_async(g.handle, self.lo, self.hi, res.data_ptr()))
+            e1.record()
+            torch.cuda.synchronize()
+            g.close()
+            t = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=self.dev)
+            parts = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(parts, t)
+            times = [float(p.item()) for p in parts]
+            self.rebalanced.append({"bounds": list(self.bounds), "ms": times})
+            if max(times) <= 1.05 * (sum(times) / len(times)):
+                break
+            self.bounds = bvgraph.replan_shards(self.base, self.bounds, times)   # same inputs on every rank: same cuts
+            self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.barrier()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def open_shard(self, lo=None, hi=None, offset_type=1, offsets=True):
+        from webgraph_b200.bvgraph import BVGraph
+        lo = self.lo if lo is None else lo
+        hi = self.hi if hi is None else hi
+        h = C.c_void_p()
+        self.bvgraph._check(self.L.bvg_open_memory_shard(
+            self.graph_pin.data_ptr(), self.graph_pin.numel(), self.offs_pin.data_ptr() if offsets else None, self.offs_pin.numel() if offsets else 0,
+            self.n_total, self.m_total, 7, 3, 4, 3, 0, offset_type, self.local_rank, lo, hi, C.byref(h)))
+        g = BVGraph(h, self.base)
+        g.setStream(self.stream.cuda_stream)
+        return g
+
+    # ---- the timed scan ----
+    def scan(self, steps, warmup):
+        torch, dist, L, bvgraph, sharding = self.torch, self.dist, self.L, self.bvgraph, self.sharding
+        world, rank, dev, lo, hi = self.world, self.rank, self.dev, self.lo, self.hi
+        g = self.open_shard()
+        result = torch.zeros(2, dtype=torch.int64, device=dev)
+        # boundary reference lists: one NCCL all-gather per step when any chain crosses a shard cut
+        need_halo = False
+        if world > 1:
+            first = C.c_int32()
+            bvgraph._check(L.bvg_halo_needed(g.handle, C.byref(first)))
+            flag = torch.tensor([1 if first.value < lo else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            need_halo = bool(flag.item())
+        bcount = C.c_int32(0)
+        if need_halo:
+            bvgraph._check(L.bvg_boundary_count(g.handle, C.byref(bcount)))
+            bc = bcount.value
+            barcs = g.rangeArcs(hi - bc, hi)
+            cap_t = torch.tensor([barcs], device=dev)
+            dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+            bcap = int(cap_t.item())
+            # fixed-size message: [count+1 offsets as int64 | bcap successors as int32 padded to int64 words] (webgraph_b200/sharding.py)
+            msg_words = sharding.message_words(bc, bcap)
+            send = torch.zeros(msg_words, dtype=torch.int64, device=dev)
+            recv = torch.zeros(world * msg_words, dtype=torch.int64, device=dev)
+
+        def step():
+            if need_halo:
+                bc = bcount.value
+                bvgraph._check(L.bvg_boundary_export(g.handle, send.data_ptr(), send.data_ptr() + 8 * (bc + 1), bcap, 1))
+                sharding.exchange(send, recv)
+                if rank > 0:
+                    src = sharding.previous_rank_message(recv, rank, msg_words).data_ptr()
+                    bvgraph._check(L.bvg_halo_import(g.handle, bc, src, src + 8 * (bc + 1), 1))
+            bvgraph._check(L.bvg_scan_range_async(g.handle, lo, hi, result.data_ptr()))
+
+        # correctness of what is being timed: arcs and checksum against the generator's own
+        step()
+        torch.cuda.synchronize()
+        chk = result.clone()
+        if world > 1:
+            arcs_t = chk[0:1].clone()
+            dist.all_reduce(arcs_t, op=dist.ReduceOp.SUM)
+            parts = [torch.zeros_like(chk) for _ in range(world)]
+            dist.all_gather(parts, chk)
+            cs = 0
+            for p in parts:
+                cs ^= int(p[1].item()) & 0xFFFFFFFFFFFFFFFF
+            arcs_all = int(arcs_t.item())
+        else:
+            arcs_all, cs = int(chk[0].item()), int(chk[1].item()) & 0xFFFFFFFFFFFFFFFF
+        if (arcs_all != self.m_total or cs != int(self.st["xor_checksum"])) and not os.environ.get("BVG_BENCH_NOCHECK"):  # NOCHECK: timing experiments with BVG_DEBUG_* only
+            raise SystemExit("decode mismatch (%s): arcs %d vs %d, checksum %#x vs %#x" % (self.workload, arcs_all, self.m_total, cs, int(self.st["xor_checksum"])))
+        for _ in range(max(warmup - 1, 0)):
+            step()
+        torch.cuda.synchronize()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
+        launches0 = bvgraph.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = bvgraph.kernel_launches() - launches0
+        clocks = sampler.result()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        ms = float(t.item())
+        out = {"value": self.m_total * steps / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(lt.item()), "clocks": clocks,
+               "halo_exchange": bool(need_halo)}
+        # per-kernel timing of the same step (CUDA events on the launching stream), for the roofline object
+        psteps = min(steps, 5)
+        g.profile(True)
+        for _ in range(psteps):
+            step()
+        torch.cuda.synchronize()
+        g.profile(False)
+        out["roofline"] = self.roofline(g, g.profileRead(), psteps, ms / steps)
+        out["footprint"] = g.memoryFootprint()
+        g.close()
+        torch.cuda.synchronize()
+        self.barrier()
+        return out
+
+    def roofline(self, g, prof, psteps, ms_per_step):
+        """HBM-read roofline of rank 0's shard.  Stream bits a scan's kernels read: everything but the outdegree and reference
+        codes (parsed once at open into the header arrays) and the copy-block / interval sections of the long records
+        (expanded once at open); k_scan_extras reads the interval and residual sections of the records it walks, k_scan_merge
+        the copy blocks, k_long_resid the residual runs of the long records."""
+        if not prof:
+            return None
+        st = self.st
+        bits = g.scanBits()
+        frac_shard = bits["extent_bits"] / max(float(st["graph_bits"]), 1.0)   # generator statistics are whole-graph: scaled to the shard
+        blocks, intervals, resid = (float(st[k]) * frac_shard for k in ("bits_blocks", "bits_intervals", "bits_residuals"))
+        step_bits = blocks + intervals + resid - bits["long_preexpanded_bits"]
+        family_bits = {"k_scan_extras": intervals + resid - bits["long_residual_bits"], "k_scan_merge": blocks,
+                       "k_long_resid": float(bits["long_residual_bits"]), "k_tile_scan": float(bits["extent_bits"]) - bits["long_preexpanded_bits"],
+                       "k_stream_extras": intervals + resid}
+        peak, which = hbm_peak()
+        kernels = {k: {"ms": v["ms"] / psteps, "launches": v["launches"] / psteps} for k, v in prof.items()}
+        total_ms = sum(v["ms"] for v in kernels.values())
+        dom = max(kernels.items(), key=lambda kv: kv[1]["ms"])[0]
+        dom_bytes = family_bits.get(dom, step_bits) / 8
+        ach = dom_bytes / (kernels[dom]["ms"] * 1e-3) / 1e9
+        traffic = ncu_traffic(self.workload, self.world)
+        return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic["step_bytes"] if traffic else None,
+                "traffic_by_kernel": traffic["kernels"] if traffic else None,
+                "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if which == "measured" else "fallback",
+                "kernel_ms": kernels[dom]["ms"], "kernel_launches_per_step": kernels[dom]["launches"], "kernel_bytes": dom_bytes,
+                "kernel_share_of_step": kernels[dom]["ms"] / max(total_ms, 1e-9),
+                "kernels": kernels, "step_kernels_ms": {k: v["ms"] for k, v in kernels.items()},
+                "step_bytes": step_bits / 8, "whole_step_frac": (step_bits / 8 / (ms_per_step * 1e-3) / 1e9) / peak,
+                "shard": "rank 0 of %d: %.3f of the graph's bits" % (self.world, frac_shard),
+                "long_records": bits["long_records"], "long_arcs": bits["long_arcs"]}
+
+    # ---- e2e: host buffers in, result out, every step (open from pinned host memory + scan + close) ----
+    def e2e(self, es, pieces, footprint):
+        torch, dist, L, bvgraph = self.torch, self.dist, self.L, self.bvgraph
+        for _ in range(1):  # one untimed open-scan-close cycle: allocator pools and page tables warm, as for `value`
+            g2 = self.open_shard()
+            g2.scanRange(self.lo, self.hi)
+            g2.close()
+        torch.cuda.synchronize()
+        self.barrier()
+        a_out, c_out = C.c_int64(), C.c_uint64()
+
+        def scan_from_host():
+            bvgraph._check(L.bvg_scan_memory(self.graph_pin.data_ptr(), self.graph_pin.numel(), self.offs_pin.data_ptr(), self.offs_pin.numel(),
+                                             self.n_total, self.m_total, 7, 3, 4, 3, 0, self.local_rank, self.lo, self.hi, pieces,
+                                             C.byref(a_out), C.byref(c_out)))
+            return a_out.value, c_out.value
+
+        for _ in range(2):  # two more untimed calls: the piece-sized blocks of the device memory cache
+            scan_from_host()
+        torch.cuda.synchronize()
+        self.barrier()
+        parts = []
+        t0 = time.perf_counter()
+        for _ in range(es):
+            parts.append(scan_from_host())
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        if self.world == 1 and any(r != (self.m_total, int(self.st["xor_checksum"])) for r in parts):
+            raise SystemExit("e2e decode mismatch: %r" % (parts,))
+        tt = torch.tensor([te], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        return {"value": self.m_total * es / te, "unit": UNIT,
+                "h2d_bytes_per_step": int(footprint["stream_bytes"] + footprint["offsets_bytes"]), "d2h_bytes_per_step": 16 + 24,
+                "steps": es, "warmup": 3, "pieces": pieces,
+                "what": "bvg_scan_memory(pinned host .graph/.offsets, %d pieces): per step H2D of every byte, offsets decode, index build and scan of each piece (piece p + 1 crosses PCIe while piece p is indexed and scanned), result back to the host" % pieces}
+
+    # ---- C4: random access to uniformly random nodes (seeded, as SpeedTest -r, reference test/SpeedTest.java:96-122).  At N > 1
+    # every rank holds a replica of the whole graph and serves its share of the queries (SURVEY 8e: replicas) ----
+    def random_access(self, nq_total):
+        torch, dist, L, bvgraph = self.torch, self.dist, self.L, self.bvgraph
+        g3 = self.open_shard(0, self.n_total)
+        nq = nq_total // self.world
+        gen = torch.Generator(device=self.dev)
+        gen.manual_seed(self.args.seed + self.rank)
+        xs = torch.randint(0, self.n_total, (nq,), device=self.dev, dtype=torch.int32, generator=gen)
+        qoff = torch.zeros(nq + 1, dtype=torch.int64, device=self.dev)
+        bvgraph._check(L.bvg_successors_batch(g3.handle, xs.data_ptr(), nq, qoff.data_ptr(), None, 0, 1))
+        torch.cuda.synchronize()
+        qarcs = int(qoff[-1].item())
+        qout = torch.empty(max(qarcs, 1), dtype=torch.int32, device=self.dev)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times = []
+        for rep in range(1 + 3 + 10 if self.world == 1 else 1 + 3):  # SpeedTest's protocol: warm-up repeats, then timed repeats, mean
+            self.barrier()
+            r0.record()
+            bvgraph._check(L.bvg_successors_batch(g3.handle, xs.data_ptr(), nq, qoff.data_ptr(), qout.data_ptr(), qarcs, 1))
+            r1.record()
+            torch.cuda.synchronize()
+            if rep >= (4 if self.world == 1 else 1):
+                times.append(r0.elapsed_time(r1))
+        rms = float(np.mean(times))
+        # parity of what was timed: a sample of the queries against single-node calls is covered by the GPU tests; here the
+        # arcs of the batch must equal the sum of the outdegrees
+        d = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+        bvgraph._check(L.bvg_outdegree_batch(g3.handle, xs.data_ptr(), 0, nq, d.data_ptr(), 1))
+        torch.cuda.synchronize()
+        ok = int(d.sum(dtype=torch.int64).item()) == qarcs
+        tt = torch.tensor([rms, float(qarcs)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            tmax = tt[0:1].clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            asum = tt[1:2].clone()
+            dist.all_reduce(asum, op=dist.ReduceOp.SUM)
+            rms, qarcs_all = float(tmax.item()), int(asum.item())
+        else:
+            qarcs_all = qarcs
+        g3.close()
+        tr = ncu_traffic(self.workload + "_c4", self.world)
+        return {"config": "C4", "nodes": nq * self.world, "arcs": qarcs_all, "ms": rms, "repeats": len(times), "nodes_per_s": nq * self.world / (rms * 1e-3),
+                "edges_per_s": qarcs_all / (rms * 1e-3), "arcs_equal_sum_of_outdegrees": bool(ok),
+                "dram_bytes": tr["step_bytes"] if tr else None,
+                "what": "bvg_successors_batch, device buffers (sizes + decode), uniformly random nodes, %s" % ("one GPU" if self.world == 1 else "%d replicas, queries split evenly, max over ranks" % self.world)}
+
+    def other_configs(self):
+        """Materialising decode, NodeIterator route, open without .offsets: N = 1 only, outside the timed region."""
+        torch, L, bvgraph = self.torch, self.L, self.bvgraph
+        from webgraph_b200.bvgraph import BVGraph
+        out = {}
+        g3 = self.open_shard()
+        try:
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            moff = torch.zeros(self.n_total + 1, dtype=torch.int64, device=self.dev)
+            mout = torch.empty(self.m_total, dtype=torch.int32, device=self.dev)
+            for rep in range(2):
+                r0.record()
+                bvgraph._check(L.bvg_decode_range(g3.handle, 0, self.n_total, moff.data_ptr(), mout.data_ptr(), self.m_total, 1))
+                r1.record()
+                torch.cuda.synchronize()
+            mms = r0.elapsed_time(r1)
+            # every list at full size: arcs, sum of all successors against the generator's, ascending rows
+            sum_ok = int(mout.sum(dtype=torch.int64).item()) == int(self.st["sum_successors"]) and int(moff[-1].item()) == self.m_total
+            out["materialise"] = {"ms": mms, "edges_per_s": self.m_total / (mms * 1e-3), "bytes_written": 4 * self.m_total + 8 * (self.n_total + 1),
+                                  "write_GBps": (4 * self.m_total + 8 * (self.n_total + 1)) / (mms * 1e-3) / 1e9,
+                                  "sum_of_successors_matches_generator": bool(sum_ok),
+                                  "what": "bvg_decode_range of the whole graph into device CSR (int64 offsets + int32 successors)"}
+            del moff, mout
+            # the NodeIterator route (bvg_cursor_*: batches decoded on the device, copied to pinned host memory, iterated in C)
+            cur = C.c_void_p()
+            bvgraph._check(L.bvg_cursor_open(g3.handle, 0, 2 ** 31 - 1, C.byref(cur)))
+            cn, ca, cc = C.c_int64(), C.c_int64(), C.c_uint64()
+            bvgraph._check(L.bvg_cursor_drain(cur, 500_000, C.byref(cn), C.byref(ca), C.byref(cc)))  # warm: pinned buffers
+            t0 = time.perf_counter()
+            bvgraph._check(L.bvg_cursor_drain(cur, 8_000_000, C.byref(cn), C.byref(ca), C.byref(cc)))
+            dt = time.perf_counter() - t0
+            L.bvg_cursor_close(cur)
+            out["node_iterator"] = {"nodes": cn.value, "arcs": ca.value, "ms": dt * 1e3, "edges_per_s": ca.value / dt,
+                                    "what": "bvg_cursor_drain: bvg_cursor_next over 8 M nodes, every successor consumed on one host thread"}
+            out["node_iterator_threads"] = self.cursor_threads(g3)
+        except Exception as e:  # informational legs must never take the headline down
+            out["error"] = repr(e)
+        g3.close()
+        # a graph that comes without .offsets (loadSequential / loadOffline in the reference, BVGraph.java:1581-1609): the
+        # record boundaries are found from the .graph stream on the device (bvg_boundaries.cuh); timed against the same
+        # open with .offsets, result checked by a scan
+        try:
+            def timed_open(offsets):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                g = self.open_shard(0, self.n_total, offset_type=0, offsets=offsets)
+                torch.cuda.synchronize()
+                return g, (time.perf_counter() - t0) * 1e3
+            g4, with_ms = timed_open(True)
+            g4.close()
+            g4, without_ms = timed_open(False)
+            ok = g4.scanRange(0, self.n_total) == (self.m_total, int(self.st["xor_checksum"]))
+            g4.close()
+            out["open_without_offsets"] = {"ms": without_ms, "ms_with_offsets": with_ms, "scan_matches": bool(ok),
+                                           "what": "bvg_open_memory of the pinned .graph with offsets = NULL (offset_type 0): record boundaries from the stream alone, then the usual index build; beside the same open given .offsets"}
+        except Exception as e:
+            out["open_without_offsets"] = {"error": repr(e)}
+        return out
+
+    def cursor_threads(self, g):
+        """k host threads, each draining its own cursor over a node range split as ImmutableGraph.splitNodeIterators does
+        (reference ImmutableGraph.java:379-409)."""
+        import concurrent.futures as cf
+        L, bvgraph = self.L, self.bvgraph
+        res = {}
+        nodes = min(self.n_total, 16_000_000)
+        for k in (4, 8):
+            step = (nodes + k - 1) // k
+
+            def drain(i):
+                cur = C.c_void_p()
+                bvgraph._check(L.bvg_cursor_open(g.handle, i * step, min(nodes, (i + 1) * step), C.byref(cur)))
+                cn, ca, cc = C.c_int64(), C.c_int64(), C.c_uint64()
+                bvgraph._check(L.bvg_cursor_drain(cur, -1, C.byref(cn), C.byref(ca), C.byref(cc)))
+                L.bvg_cursor_close(cur)
+                return ca.value
+            t0 = time.perf_counter()
+            with cf.ThreadPoolExecutor(k) as ex:
+                arcs = sum(ex.map(drain, range(k)))
+            dt = time.perf_counter() - t0
+            res[str(k)] = {"arcs": arcs, "ms": dt * 1e3, "edges_per_s": arcs / dt}
+        return res
 
 
 def main():
@@ -212,300 +606,64 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from webgraph_b200 import bvgraph, sharding
-    from webgraph_b200.bvgraph import BVGraph
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the decode path is CUDA-only (no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    base, st = graph_files(args, rank, world, barrier)
-    L = bvgraph.lib()
-    n_total, m_total = int(st["nodes"]), int(st["arcs"])
-
-    # ---- host copies of the files in pinned memory (the e2e leg uploads them every step) ----
-    graph_np = np.fromfile(base + ".graph", dtype=np.uint8)
-    offs_np = np.fromfile(base + ".offsets", dtype=np.uint8)
-    graph_pin = torch.from_numpy(graph_np).pin_memory()
-    offs_pin = torch.from_numpy(offs_np).pin_memory()
-    del graph_np, offs_np
-
-    bounds = bvgraph.plan_shards(base, world)
-    lo, hi = bounds[rank], bounds[rank + 1]
-
-    def open_shard():
-        h = C.c_void_p()
-        bvgraph._check(L.bvg_open_memory_shard(graph_pin.data_ptr(), graph_pin.numel(), offs_pin.data_ptr(), offs_pin.numel(),
-                                               n_total, m_total, 7, 3, 4, 3, 0, 1, local_rank, lo, hi, C.byref(h)))
-        return BVGraph(h, base)
-
-    g = open_shard()
-    stream = torch.cuda.current_stream()
-    g.setStream(stream.cuda_stream)
-    result = torch.zeros(2, dtype=torch.int64, device=dev)
-
-    # ---- boundary reference lists: one NCCL all-gather per step when any chain crosses a shard cut ----
-    need_halo = False
-    if world > 1:
-        first = C.c_int32()
-        bvgraph._check(L.bvg_halo_needed(g.handle, C.byref(first)))
-        flag = torch.tensor([1 if first.value < lo else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        need_halo = bool(flag.item())
-    bcount = C.c_int32(0)
-    if need_halo:
-        bvgraph._check(L.bvg_boundary_count(g.handle, C.byref(bcount)))
-        bc = bcount.value
-        barcs = g.rangeArcs(hi - bc, hi)
-        cap_t = torch.tensor([barcs], device=dev)
-        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
-        bcap = int(cap_t.item())
-        # fixed-size message: [count+1 offsets as int64 | bcap successors as int32 padded to int64 words] (webgraph_b200/sharding.py)
-        msg_words = sharding.message_words(bc, bcap)
-        send = torch.zeros(msg_words, dtype=torch.int64, device=dev)
-        recv = torch.zeros(world * msg_words, dtype=torch.int64, device=dev)
-
-    def exchange_halo():
-        if not need_halo:
-            return
-        bc = bcount.value
-        off_ptr = send.data_ptr()
-        lists_ptr = send.data_ptr() + 8 * (bc + 1)
-        bvgraph._check(L.bvg_boundary_export(g.handle, off_ptr, lists_ptr, bcap, 1))
-        sharding.exchange(send, recv)
-        if rank > 0:
-            src = sharding.previous_rank_message(recv, rank, msg_words).data_ptr()
-            bvgraph._check(L.bvg_halo_import(g.handle, bc, src, src + 8 * (bc + 1), 1))
-
-    def step():
-        exchange_halo()
-        bvgraph._check(L.bvg_scan_range_async(g.handle, lo, hi, result.data_ptr()))
-
-    # ---- correctness of what is being timed: arcs and checksum against the generator's own ----
-    step()
-    torch.cuda.synchronize()
-    chk = result.clone()
-    if world > 1:
-        arcs_t = chk[0:1].clone()
-        dist.all_reduce(arcs_t, op=dist.ReduceOp.SUM)
-        parts = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(parts, chk)
-        cs = 0
-        for p in parts:
-            cs ^= int(p[1].item()) & 0xFFFFFFFFFFFFFFFF
-        arcs_all = int(arcs_t.item())
-    else:
-        arcs_all, cs = int(chk[0].item()), int(chk[1].item()) & 0xFFFFFFFFFFFFFFFF
-    if (arcs_all != m_total or cs != int(st["xor_checksum"])) and not os.environ.get("BVG_BENCH_NOCHECK"):  # NOCHECK: timing experiments with BVG_DEBUG_* only
-        raise SystemExit("decode mismatch: arcs %d vs %d, checksum %#x vs %#x" % (arcs_all, m_total, cs, int(st["xor_checksum"])))
-
-    for _ in range(max(args.warmup - 1, 0)):
-        step()
-    torch.cuda.synchronize()
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = bvgraph.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = bvgraph.kernel_launches() - launches0
-    clocks = sampler.result()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    ms = float(t.item())
-    value = m_total * args.steps / (ms * 1e-3)
-
-    # ---- per-kernel timing of the same step (CUDA events on the launching stream), for the roofline object ----
-    g.profile(True)
-    for _ in range(min(args.steps, 5)):
-        step()
-    torch.cuda.synchronize()
-    g.profile(False)
-    prof = g.profileRead()
-    shard_bits = None
-    off_np = None
-    roof = None
-    if prof:
-        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
-        per_step_launches = {k: v["launches"] / min(args.steps, 5) for k, v in prof.items()}
-        dom_ms = dom[1]["ms"] / dom[1]["launches"]
-        total_ms = sum(v["ms"] for v in prof.values()) / min(args.steps, 5)
-        # algorithmic bytes of one launch of the dominant kernel: the .graph bits of the nodes it decodes
-        bits = shard_graph_bits(base, bounds, rank, st)
-        peak, which = hbm_peak()
-        ach = bits / 8 / (dom_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)" if which == "measured" else "fallback",
-                "kernel_ms": dom_ms, "kernel_share_of_step": dom[1]["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
-                "step_kernels_ms": {k: v["ms"] / min(args.steps, 5) for k, v in prof.items()},
-                "launches_per_step": per_step_launches,
-                "whole_step_frac": (bits / 8 / (ms / args.steps * 1e-3) / 1e9) / peak}
-        roof["traffic"] = ncu_traffic(dom[0])
-
-    # ---- e2e: host buffers in, result out, every step (open from pinned host memory + scan + close) ----
-    e2e = None
-    es = max(1, args.e2e_steps)
-    foot = g.memoryFootprint()
-    g.close()
-    torch.cuda.synchronize()
-    barrier()
-    for _ in range(1):  # one untimed open-scan-close cycle: allocator pools and page tables warm, as for `value`
-        g2 = open_shard()
-        g2.setStream(stream.cuda_stream)
-        g2.scanRange(lo, hi)
-        g2.close()
-    torch.cuda.synchronize()
-    barrier()
-    pieces = args.e2e_pieces
-    a_out, c_out = C.c_int64(), C.c_uint64()
-
-    def scan_from_host():
-        bvgraph._check(L.bvg_scan_memory(graph_pin.data_ptr(), graph_pin.numel(), offs_pin.data_ptr(), offs_pin.numel(),
-                                         n_total, m_total, 7, 3, 4, 3, 0, local_rank, lo, hi, pieces, C.byref(a_out), C.byref(c_out)))
-        return a_out.value, c_out.value
-
-    for _ in range(2):  # two more untimed calls: the piece-sized blocks of the device memory cache
-        scan_from_host()
-    torch.cuda.synchronize()
-    barrier()
-    e2e_parts = []
-    t0 = time.perf_counter()
-    for _ in range(es):
-        e2e_parts.append(scan_from_host())
-    torch.cuda.synchronize()
-    te = time.perf_counter() - t0
-    if world == 1 and any(r != (m_total, int(st["xor_checksum"])) for r in e2e_parts):
-        raise SystemExit("e2e decode mismatch: %r" % (e2e_parts,))
-    tt = torch.tensor([te], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    te = float(tt.item())
-    e2e = {"value": m_total * es / te, "unit": UNIT,
-           "h2d_bytes_per_step": int(foot["stream_bytes"] + foot["offsets_bytes"]), "d2h_bytes_per_step": 16 + 24,
-           "steps": es, "warmup": 1,
-           "pieces": pieces,
-           "what": "bvg_scan_memory(pinned host .graph/.offsets, %d pieces): per step H2D of every byte, offsets decode, index build and scan of each piece (piece p + 1 crosses PCIe while piece p is indexed and scanned), result back to the host" % pieces}
-
-    # ---- the other BASELINE configs on the same graph, outside the timed region (N = 1 only): C4 random access to 10 M
-    # uniformly random nodes (seeded, as SpeedTest -r, reference test/SpeedTest.java:98-111) and the materialising decode ----
-    extra = None
-    if world == 1 and not args.no_extras:
-        extra = {}
-        g3 = open_shard()
-        g3.setStream(stream.cuda_stream)
+    b = Bench(args, args.workload, rank, local_rank, world)
+    if args.profile_only == "c4":
+        print(json.dumps(b.random_access(args.random_nodes)), flush=True)
+        return
+    main_res = b.scan(args.steps, args.warmup)
+    if args.profile_only == "scan":
+        print(json.dumps({"ms_per_step": main_res["ms_per_step"], "kernels": main_res["roofline"]["kernels"]}), flush=True)
+        return
+    roof = main_res["roofline"]
+    # the pieces of a pass overlap upload and index build; a rank of N holds 1/N of the graph, so it cuts it into fewer pieces
+    e2e = b.e2e(max(1, args.e2e_steps), max(1, args.e2e_pieces // world), main_res["footprint"])
+    other = {}
+    if not args.no_extras:
         try:
-            nq = args.random_nodes
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(args.seed)
-            xs = torch.randint(0, n_total, (nq,), device=dev, dtype=torch.int32, generator=gen)
-            qoff = torch.zeros(nq + 1, dtype=torch.int64, device=dev)
-            bvgraph._check(L.bvg_successors_batch(g3.handle, xs.data_ptr(), nq, qoff.data_ptr(), None, 0, 1))
-            torch.cuda.synchronize()
-            qarcs = int(qoff[-1].item())
-            qout = torch.empty(max(qarcs, 1), dtype=torch.int32, device=dev)
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for rep in range(2):  # first repetition warms the allocator
-                r0.record()
-                bvgraph._check(L.bvg_successors_batch(g3.handle, xs.data_ptr(), nq, qoff.data_ptr(), qout.data_ptr(), qarcs, 1))
-                r1.record()
-                torch.cuda.synchronize()
-            rms = r0.elapsed_time(r1)
-            extra["random_access"] = {"config": "C4", "nodes": nq, "arcs": qarcs, "ms": rms, "nodes_per_s": nq / (rms * 1e-3),
-                                      "edges_per_s": qarcs / (rms * 1e-3), "what": "bvg_successors_batch, device buffers, sizes + decode"}
-            del qout, qoff, xs
-            moff = torch.zeros(n_total + 1, dtype=torch.int64, device=dev)
-            mout = torch.empty(m_total, dtype=torch.int32, device=dev)
-            for rep in range(2):
-                r0.record()
-                bvgraph._check(L.bvg_decode_range(g3.handle, 0, n_total, moff.data_ptr(), mout.data_ptr(), m_total, 1))
-                r1.record()
-                torch.cuda.synchronize()
-            mms = r0.elapsed_time(r1)
-            extra["materialise"] = {"ms": mms, "edges_per_s": m_total / (mms * 1e-3), "bytes_written": 4 * m_total + 8 * (n_total + 1),
-                                    "what": "bvg_decode_range of the whole graph into device CSR (int64 offsets + int32 successors)"}
-            del moff, mout
-            # the NodeIterator route (bvg_cursor_*: batches decoded on the device, copied to pinned host memory, iterated in C)
-            cur = C.c_void_p()
-            bvgraph._check(L.bvg_cursor_open(g3.handle, 0, 2 ** 31 - 1, C.byref(cur)))
-            cn, ca, cc = C.c_int64(), C.c_int64(), C.c_uint64()
-            bvgraph._check(L.bvg_cursor_drain(cur, 500_000, C.byref(cn), C.byref(ca), C.byref(cc)))  # warm: pinned buffers
-            t0 = time.perf_counter()
-            bvgraph._check(L.bvg_cursor_drain(cur, 8_000_000, C.byref(cn), C.byref(ca), C.byref(cc)))
-            dt = time.perf_counter() - t0
-            L.bvg_cursor_close(cur)
-            extra["node_iterator"] = {"nodes": cn.value, "arcs": ca.value, "ms": dt * 1e3, "edges_per_s": ca.value / dt,
-                                      "what": "bvg_cursor_drain: bvg_cursor_next over 8 M nodes, every successor consumed on one host thread"}
-        except Exception as e:  # informational legs must never take the headline down
-            extra["error"] = repr(e)
-        g3.close()
-        # a graph that comes without .offsets (loadSequential / loadOffline in the reference, BVGraph.java:1581-1609): the
-        # record boundaries are found from the .graph stream on the device (bvg_boundaries.cuh); timed against the same
-        # open with .offsets, result checked by a scan
-        try:
-            def timed_open(offs_ptr, offs_len):
-                h = C.c_void_p()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                bvgraph._check(L.bvg_open_memory(graph_pin.data_ptr(), graph_pin.numel(), offs_ptr, offs_len, n_total, m_total,
-                                                 7, 3, 4, 3, 0, 0, local_rank, C.byref(h)))
-                torch.cuda.synchronize()
-                return BVGraph(h), (time.perf_counter() - t0) * 1e3
-            g4, with_ms = timed_open(offs_pin.data_ptr(), offs_pin.numel())
-            g4.close()
-            g4, without_ms = timed_open(None, 0)
-            ok = g4.scanRange(0, n_total) == (m_total, int(st["xor_checksum"]))
-            g4.close()
-            extra["open_without_offsets"] = {"ms": without_ms, "ms_with_offsets": with_ms, "scan_matches": bool(ok),
-                                             "what": "bvg_open_memory of the pinned .graph with offsets = NULL (offset_type 0): record boundaries from the stream alone, then the usual index build; beside the same open given .offsets"}
+            other["random_access"] = b.random_access(args.random_nodes)
         except Exception as e:
-            extra["open_without_offsets"] = {"error": repr(e)}
-
+            other["random_access"] = {"error": repr(e)}
+        if world == 1:
+            other.update(b.other_configs())
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        arcs_c, dt_c, hi_c = cpu_port_baseline(base, args.cpu_sample_arcs, 1)
+        arcs_c, dt_c, hi_c = cpu_port_baseline(b.base, args.cpu_sample_arcs, 1)
         cpu = {"value": arcs_c / dt_c, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "oracle sequential scan of the first %d nodes (%d arcs), 1 thread, %.1f s; host has %d cores" % (hi_c, arcs_c, dt_c, os.cpu_count() or 0)}
-
+    st, footprint, bounds_used, rebalanced = b.st, main_res["footprint"], list(b.bounds), b.rebalanced
+    del b
+    torch.cuda.empty_cache()
+    if not args.no_second_workload:
+        second = "weblike" if args.workload == "powerlaw" else "powerlaw"
+        try:
+            b2 = Bench(args, second, rank, local_rank, world)
+            r2 = b2.scan(max(5, args.steps // 2), max(3, args.warmup))
+            e2 = b2.e2e(2, max(1, args.e2e_pieces // world), r2["footprint"]) if world == 1 else None
+            other["second_workload"] = {"config": config_of(args, second, b2.st, world), "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"],
+                                        "roofline": r2["roofline"], "e2e": e2, "halo_exchange": r2["halo_exchange"]}
+            del b2
+        except Exception as e:
+            other["second_workload"] = {"error": repr(e)}
+    if roof is not None:
+        roof["other_configs"] = other
+        roof["halo_exchange"] = main_res["halo_exchange"]
+        roof["shard_bounds"] = bounds_used
+        roof["rebalance_rounds"] = rebalanced
+        roof["hbm_footprint_bytes"] = footprint
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "int32", "data": "synthetic",
-                "config": {"workload": workload_name(world),
-                           "nodes": n_total, "arcs": m_total, "bits_per_arc": st["graph_bits"] / max(m_total, 1),
-                           "graph_bytes": (int(st["graph_bits"]) + 7) // 8, "avg_ref_chain": st["tot_ref"] / max(n_total, 1),
-                           "max_outdegree": st["max_outdegree"], "seed": args.seed, "generator": "webgraph_b200.tools.generate_store (SURVEY 8d)",
-                           "l2": "input stream (%.2f GB) is far larger than L2; no flush needed" % (st["graph_bits"] / 8e9),
-                           "halo_exchange": bool(need_halo), "mode": "consume-only scan (arcs + XOR checksum verified against the generator)"},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks, "extra": extra}
+        line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": config_of(args, args.workload, st, world),
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def shard_graph_bits(base, bounds, rank, st):
-    """.graph bits of this rank's node range (algorithmic bytes of one scan).  Whole graph: the file's bit length."""
-    if len(bounds) == 2:
-        return float(st["graph_bits"])
-    # equal-bit shards by construction (bvg_plan_shards)
-    return float(st["graph_bits"]) / (len(bounds) - 1)
 
 
 if __name__ == "__main__":

@@ -70,8 +70,13 @@ int  bvg_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* 
 int  bvg_open_memory_shard(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
                            int32_t nodes, int64_t arcs, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
                            uint32_t flags, int offset_type, int device, int32_t from, int32_t to, bvg_graph** out);
-/* Host-only: bounds[0..nshards] of contiguous node ranges holding equal shares of the .graph bits. */
+/* Host-only: bounds[0..nshards] of contiguous node ranges holding equal shares of the .graph bits, every cut moved to
+ * the nearest node no reference crosses (within 4096 nodes) so that the shards owe each other no boundary lists.  The range
+ * split itself is ImmutableGraph.splitNodeIterators' (ImmutableGraph.java:379-409). */
 int  bvg_plan_shards(const char* basename, int nshards, int32_t* bounds);
+/* The same from measured costs: old_cost[j] = what shard [old_bounds[j], old_bounds[j+1]) cost (e.g. device seconds per scan);
+ * the new cuts sit at equal shares of that cost, taken as uniform over the bits of each old shard. */
+int  bvg_replan_shards(const char* basename, int nshards, const int32_t* old_bounds, const double* old_cost, int32_t* bounds);
 void bvg_close(bvg_graph* g);
 
 /* numNodes / numArcs / windowSize / maxRefCount / minIntervalLength / zetaK / flags (BVGraph.java:579-625). */
@@ -156,8 +161,13 @@ int64_t bvg_release_cached_memory(int device);
  * events on the launching stream; bvg_profile_read drains them into a JSON object {"kernel": {"launches": n, "ms": t}}. */
 int  bvg_profile(const bvg_graph* g, int enable);
 int  bvg_profile_read(const bvg_graph* g, char* buf, int cap);
-/* Bytes of HBM held by the graph: bit stream, offsets, decode index. */
+/* Bytes of HBM held by the graph: bit stream, offsets, decode index (header arrays, long-record index and, once a range decode or
+ * a scan has asked for them, the length-bucketed schedules). */
 int  bvg_memory_footprint(const bvg_graph* g, int64_t* stream_bytes, int64_t* offsets_bytes, int64_t* index_bytes);
+/* What a scan of the graph's extent reads of the stream, for roofline arithmetic (out[6]): [0] stream bits of the extent,
+ * [1] long records, [2] bits of their residual runs (decoded by every scan), [3] bits of their copy-block and interval
+ * sections (expanded once at open, not read again), [4] their arcs, [5] 1 when the schedules are built. */
+int  bvg_scan_bits(const bvg_graph* g, int64_t* out);
 
 #ifdef __cplusplus
 }

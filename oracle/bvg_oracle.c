@@ -668,3 +668,22 @@ int64_t orc_chain_bits(const orc_graph* g, int32_t x, int32_t* depth) {
     if (depth) *depth = dep;
     return bits;
 }
+
+/* Root of x's reference chain: the node the recursion of successors(x) bottoms out at (BVGraph.java:1110-1121). */
+int32_t orc_chain_root(const orc_graph* g, int32_t x) {
+    if (x < 0 || x >= g->n) return BVGO_EINVAL;
+    if (!g->offsets) return BVGO_EUNSUPPORTED;
+    for (;;) {
+        ibs_t s = { g->graph, g->graph_bytes * 8, g->offsets[x] };
+        int err = 0;
+        const int32_t d = read_outdegree(g, &s, &err);
+        if (err) return err;
+        if (d == 0 || g->window == 0) return x;
+        const uint64_t ref = read_coded(&s, g->reference_coding, 0, &err);
+        if (err) return err;
+        if (ref == 0) return x;
+        if (ref > (uint64_t)g->window) return BVGO_ESTATE;
+        if (ref > (uint64_t)x) return BVGO_EFORMAT;
+        x -= (int32_t)ref;
+    }
+}

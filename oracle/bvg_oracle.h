@@ -96,6 +96,8 @@ int  orc_rebuild_offsets(const orc_graph* g, uint64_t* out);
 /* Algorithmic bits needed to answer successors(x) by random access: the record of x plus the
  * records of its reference-chain ancestors. Returns bits or an error. */
 int64_t orc_chain_bits(const orc_graph* g, int32_t x, int32_t* depth);
+/* Root of x's reference chain (x itself when it has no reference); negative = error. */
+int32_t orc_chain_root(const orc_graph* g, int32_t x);
 
 /* Raw code readers, exported for known-answer tests of the dsiutils restatement. */
 uint64_t orc_read_code(const uint8_t* buf, uint64_t nbytes, uint64_t* bitpos, int coding, int k);

@@ -4,7 +4,7 @@
 # e.g. BENCH_ARGS="--steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1" keeps the extras (random access, materialise,
 # NodeIterator, open without .offsets) in the line.
 TAG=$1; shift
-BENCH_ARGS=${BENCH_ARGS:---steps 10 --warmup 3 --no-extras --no-cpu-baseline --e2e-steps 2}
+BENCH_ARGS=${BENCH_ARGS:---steps 10 --warmup 3 --no-extras --no-cpu-baseline --e2e-steps 2 --no-second-workload}
 mkdir -p gpurun_out
 i=0
 for envs in "$@"; do
@@ -16,7 +16,7 @@ envs,f,e=sys.argv[1:4]
 try:
     d=json.loads(open(f).read().strip().splitlines()[-1])
     k={a:round(b,3) for a,b in d["roofline"]["step_kernels_ms"].items()}
-    x=d.get("extra") or {}
+    x=(d["roofline"].get("other_configs") or {})
     ow=x.get("open_without_offsets") or {}
     tail="  open w/o offsets %.0f ms" % ow["ms"] if "ms" in ow else ""
     print("[%s] ms/step %.3f  e2e %.2f G/s  %s%s" % (envs, d["ms_per_step"], d["e2e"]["value"]/1e9, k, tail))

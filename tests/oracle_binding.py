@@ -52,6 +52,8 @@ class Oracle:
         lib.orc_rebuild_offsets.argtypes = [P(OrcGraph), C.c_void_p]
         lib.orc_chain_bits.argtypes = [P(OrcGraph), C.c_int32, P(C.c_int32)]
         lib.orc_chain_bits.restype = C.c_int64
+        lib.orc_chain_root.argtypes = [P(OrcGraph), C.c_int32]
+        lib.orc_chain_root.restype = C.c_int32
         lib.orc_read_code.argtypes = [C.c_void_p, C.c_uint64, P(C.c_uint64), C.c_int, C.c_int]
         lib.orc_read_code.restype = C.c_uint64
 
@@ -137,6 +139,12 @@ class OracleGraph:
         if rc:
             raise OracleError(rc)
         return out
+
+    def first_ancestor(self, x):
+        r = self.orc.lib.orc_chain_root(self.g, x)
+        if r < 0:
+            raise OracleError(r)
+        return r
 
     def chain_bits(self, x):
         dep = C.c_int32()

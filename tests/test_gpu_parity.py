@@ -296,6 +296,55 @@ def test_synthetic_100k_full_decode(synth100k, oracle):
     g.close()
 
 
+@pytest.mark.parametrize("env", [{"BVG_TILE": "1"}, {"BVG_TILE": "1", "BVG_TILE_NT": "512"}, {"BVG_TILE": "1", "BVG_LONG_D": "64", "BVG_LONG_SEG": "16", "BVG_LONG_CHUNK": "16"},
+                                 {"BVG_STREAM": "1"}, {"BVG_STREAM": "1", "BVG_LONG_D": "64", "BVG_LONG_SEG": "16", "BVG_LONG_CHUNK": "16"}])
+def test_alternative_scan_kernels(synth100k, cnr_truth, monkeypatch, env):
+    """The two scan kernels of round 2 that are off by default (tile kernel, bvg_tile.cuh; stream-position extras kernel,
+    bvg_stream.cuh): same (arcs, XOR checksum) as the truth on the reference's fixture and on the synthetic graph, whole graph,
+    sub-ranges and shards with re-decoded halos."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    off, succ = cnr_truth
+    g = BVGraph.load(CNR)
+    assert g.scanRange(0, g.numNodes()) == (len(succ), ob.xor_checksum(off, succ))
+    for lo, hi in [(0, 1), (17, 18), (1000, 200000), (325000, g.numNodes())]:
+        assert g.scanRange(lo, hi) == (int(off[hi] - off[lo]), ob.xor_checksum(off[lo:hi + 1] - off[lo], succ[off[lo]:off[hi]], lo)), (lo, hi)
+    g.close()
+    base, st, soff, ssucc = synth100k
+    g = BVGraph.load(base)
+    assert g.scanRange(0, g.numNodes()) == (st["arcs"], st["xor_checksum"])
+    g.close()
+    bounds = bvgraph.plan_shards(base, 3)
+    tot_a, tot_c = 0, 0
+    for r in range(3):
+        gs = BVGraph.loadShard(base, bounds[r], bounds[r + 1])
+        a, c = gs.scanRange(bounds[r], bounds[r + 1])
+        tot_a += a
+        tot_c ^= c
+        gs.close()
+    assert (tot_a, tot_c) == (st["arcs"], st["xor_checksum"])
+
+
+def test_weblike_1m_full_parity(tmp_path, oracle):
+    """The second benchmark workload (copy-heavy, cnr-2000's mix: ~3.6 bits/arc, ~63 % copied arcs, avgref ~1.3) at 1 M nodes:
+    every list against the generator's own and against the oracle; scan checksum and sum of successors."""
+    import bench
+    base = str(tmp_path / "web1m")
+    st, off, succ = tools.generate_store(base, 1000000, 14000000, seed=0x5EED, return_csr=True, threads=8, **bench.WEBLIKE)
+    assert st["copied_arcs"] > 0.5 * st["arcs"] and st["tot_ref"] > 1.1 * st["nodes"] and st["graph_bits"] < 6 * st["arcs"]
+    g = BVGraph.load(base)
+    o, s = g.decodeRange(0, g.numNodes())
+    assert np.array_equal(o, off) and np.array_equal(s, succ)
+    assert g.scanRange(0, g.numNodes()) == (st["arcs"], st["xor_checksum"])
+    assert int(s.astype(np.uint64).sum()) == st["sum_successors"]
+    g.close()
+    og = oracle.load(base)
+    assert og.scan_range(0, og.n, threads=8) == (st["arcs"], st["xor_checksum"])
+    lo, hi = 400000, 402000
+    oo, os_ = og.decode_range(lo, hi)
+    assert np.array_equal(os_, succ[off[lo]:off[hi]])
+
+
 def test_synthetic_100k_random_access(synth100k):
     base, st, off, succ = synth100k
     g = BVGraph.load(base)

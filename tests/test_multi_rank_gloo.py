@@ -76,3 +76,26 @@ def test_shards_exchange_boundaries_over_gloo(tmp_path, world):
     mp.spawn(_rank_main, args=(world, base, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert os.path.exists(str(tmp_path / ("ok%d" % r)))
+
+
+def test_shard_plans_are_partitions_with_clean_cuts(tmp_path):
+    """bvg_plan_shards / bvg_replan_shards (host only): monotone partitions of [0, n); the cuts sit where no reference crosses
+    (checked against the oracle's successor lists through the compressor's own reference choices: a node whose list was
+    written with a reference r copies from x - r, reference test fixture and a copy-heavy graph), and re-planning from a
+    cost vector moves the cuts towards the cheaper shards."""
+    from tests.conftest import CNR
+    off, succ, _ = graphs.copy_heavy(20000, seed=3)
+    base = str(tmp_path / "ch")
+    tools.store_csr(base, off, succ)
+    for b in (CNR, base):
+        g = ob.load().load(b)
+        for k in (1, 2, 3, 8):
+            bounds = bvgraph.plan_shards(b, k)
+            assert bounds[0] == 0 and bounds[-1] == g.n and all(x <= y for x, y in zip(bounds, bounds[1:]))
+            for c in bounds[1:-1]:  # no chain crosses: every node of [c, c + W) decodes with nodes >= c alone
+                hi = min(g.n, c + g.window)
+                assert all(g.first_ancestor(x) >= c for x in range(c, hi)), (b, k, c)
+        bounds = bvgraph.plan_shards(b, 4)
+        again = bvgraph.replan_shards(b, bounds, [1.0, 1.0, 1.0, 5.0])
+        assert again[0] == 0 and again[-1] == g.n and all(x <= y for x, y in zip(again, again[1:]))
+        assert again[3] > bounds[3]  # the expensive last shard shrinks

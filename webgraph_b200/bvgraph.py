@@ -55,6 +55,7 @@ SYMBOLS = [
     "bvg_cursor_copy", "bvg_cursor_close", "bvg_cursor_drain", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
     "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_release_cached_memory", "bvg_profile", "bvg_profile_read",
+    "bvg_scan_bits", "bvg_replan_shards",
 ]
 
 
@@ -70,6 +71,7 @@ def lib():
     L.bvg_open_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, P(vp)]
     L.bvg_open_memory_shard.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, C.c_int, i32, i32, P(vp)]
     L.bvg_plan_shards.argtypes = [C.c_char_p, C.c_int, P(i32)]
+    L.bvg_replan_shards.argtypes = [C.c_char_p, C.c_int, P(i32), P(C.c_double), P(i32)]
     L.bvg_release_cached_memory.argtypes = [C.c_int]
     L.bvg_release_cached_memory.restype = C.c_int64
     L.bvg_scan_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, i32, i32, u32, C.c_int, i32, i32, C.c_int, P(i64), P(u64)]
@@ -106,6 +108,7 @@ def lib():
     L.bvg_kernel_launches.argtypes = []
     L.bvg_kernel_launches.restype = i64
     L.bvg_memory_footprint.argtypes = [vp, P(i64), P(i64), P(i64)]
+    L.bvg_scan_bits.argtypes = [vp, P(i64)]
     _lib = L
     return L
 
@@ -491,6 +494,13 @@ class BVGraph(ImmutableGraph):
         _check(lib().bvg_memory_footprint(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"stream_bytes": a.value, "offsets_bytes": b.value, "index_bytes": c.value}
 
+    def scanBits(self):
+        """What a scan of this graph's extent reads of the stream (bvg_scan_bits)."""
+        out = (C.c_int64 * 6)()
+        _check(lib().bvg_scan_bits(self._h, out))
+        return {"extent_bits": out[0], "long_records": out[1], "long_residual_bits": out[2], "long_preexpanded_bits": out[3],
+                "long_arcs": out[4], "schedules_built": bool(out[5])}
+
     @property
     def graphBits(self):
         return self._graph_bits
@@ -502,6 +512,16 @@ class BVGraph(ImmutableGraph):
 
 def kernel_launches():
     return int(lib().bvg_kernel_launches())
+
+
+def replan_shards(basename, old_bounds, old_cost):
+    """Cuts at equal shares of a measured cost (bvg_replan_shards): old_cost[j] is what shard j of old_bounds cost."""
+    n = len(old_bounds) - 1
+    ob = (C.c_int32 * (n + 1))(*old_bounds)
+    oc = (C.c_double * n)(*[float(c) for c in old_cost])
+    b = (C.c_int32 * (n + 1))()
+    _check(lib().bvg_replan_shards(os.fsencode(basename), n, ob, oc, b))
+    return list(b)
 
 
 def plan_shards(basename, nshards):

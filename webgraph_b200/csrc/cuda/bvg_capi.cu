@@ -146,6 +146,8 @@ static cudaError_t dev_free(void* p, cudaStream_t s) {
 }
 
 static int env_int(const char* name, int dflt, int lo, int hi);
+struct bvg_graph;
+extern "C" { static int fetch_offsets(const bvg_graph* g, int32_t a, int32_t b, uint64_t* va, uint64_t* vb); }
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
 
 struct bvg_graph {
@@ -194,6 +196,9 @@ struct bvg_graph {
     std::vector<int64_t> n_items_merge;  // [level]
     ItemMap item_map(int family) const { return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong }; }
     int64_t long_tmp_entries = 0;
+    // what a scan reads of the long records, for the roofline arithmetic of bench.py (bvg_scan_bits)
+    int64_t long_arcs = 0, long_resid_bits = 0, long_pre_bits = 0, long_index_bytes = 0;
+    int64_t order_m_count = 0;
     // tunables (BVG_LONG_D / BVG_LONG_SEG / BVG_LONG_CHUNK override the defaults of bvg_long.cuh)
     int32_t long_d = LONG_D, long_seg = LONG_SEG, long_chunk = LONG_CHUNK;
     LongIndex long_index() const {
@@ -621,6 +626,14 @@ static int build_long_index(bvg_graph* g) {
     for (int32_t lv = 1; lv <= levels; lv++) g->n_items_merge[(size_t)lv] = cum[(size_t)(2 + lv) * stride + (size_t)nl];
     g->long_tmp_entries = tmp;
     g->long_scan_entries = scan;
+    g->long_arcs = 0; g->long_resid_bits = 0; g->long_pre_bits = 0;
+    for (int64_t l = 0; l < nl; l++) {
+        const LongMeta& m = meta[(size_t)l];
+        g->long_arcs += m.d;
+        g->long_resid_bits += (int64_t)(m.rec_end - m.resid_pos);
+        g->long_pre_bits += (int64_t)(m.resid_pos - m.after_header);
+    }
+    g->long_index_bytes = nl * (int64_t)sizeof(LongMeta) + 8 * (cb + iv) + 16 * seg + (int64_t)cum.size() * 8 + nl * 4;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // cum / meta are host vectors
     return BVG_OK;
@@ -680,6 +693,7 @@ static int build_schedules(bvg_graph* g) {
         const int32_t c = h[(size_t)(nb_e + i)]; h[(size_t)(nb_e + i)] = (int32_t)run; run += c;
     }
     g->level_start[(size_t)levels] = run;
+    g->order_m_count = run;
     { const int r1 = small_h2d(bins.p, h.data(), h.size() * 4, s); if (r1) return r1; }
     CK(dev_alloc((void**)&g->d_order_e, std::max<size_t>((size_t)g->order_e_count, 1) * 4, g->stream));
     CK(dev_alloc((void**)&g->d_order_m, std::max<size_t>((size_t)run, 1) * 4, g->stream));
@@ -1086,25 +1100,100 @@ int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
     return BVG_OK;
 }
 
+// Shard planning (host only).  Cuts are placed at equal shares of a cost that is piecewise linear in the .graph bits -- plain
+// bits for bvg_plan_shards, measured seconds per bit of every old shard for bvg_replan_shards -- and then moved to the
+// nearest node no reference crosses (no node at or after the cut copies from a node before it), so that the shards need
+// no boundary lists from each other at all; only when no such node exists within SHARD_CLEAN_REACH nodes does the cut stay
+// where the cost puts it (and the shard re-decodes or imports its halo).
+static const int64_t SHARD_CLEAN_REACH = 4096;
+
+struct ShardPlanner {
+    Properties p;
+    std::vector<uint64_t> offs;
+    FILE* graph = nullptr;
+    int oc = C_GAMMA, rc = C_UNARY, dc = C_GAMMA;
+    ~ShardPlanner() { if (graph) fclose(graph); }
+    int open(const char* basename) {
+        int r = load_properties(basename, p);
+        if (r) return r;
+        std::vector<uint8_t> ostream;
+        if (!slurp_file(std::string(basename) + ".offsets", ostream)) return BVG_EIO;
+        oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
+        rc = ((p.flags >> 12) & 0xF) ? (int)((p.flags >> 12) & 0xF) : C_UNARY;
+        dc = (p.flags & 0xF) ? (int)(p.flags & 0xF) : C_GAMMA;
+        r = decode_offsets_stream(ostream.data(), ostream.size(), oc, p.nodes, offs);
+        if (r) return r;
+        graph = fopen((std::string(basename) + ".graph").c_str(), "rb");
+        return BVG_OK;  // without the .graph file the cuts are simply not moved
+    }
+    static uint64_t code(HostBits& b, int coding) { return coding == C_GAMMA ? b.gamma() : coding == C_DELTA ? b.delta() : b.unary(); }
+    // reference of node y (0 = none), from the first bytes of its record (BVGraph.java:1048-1053)
+    int64_t ref_of(int64_t y) {
+        if (!graph || p.window <= 0) return 0;
+        uint8_t buf[64 + 16] = {0};
+        const uint64_t bit = offs[(size_t)y];
+        if (fseeko(graph, (off_t)(bit >> 3), SEEK_SET) != 0) return -1;
+        const size_t got = fread(buf, 1, 64, graph);
+        HostBits b{ buf, (uint64_t)got * 8 };
+        b.pos = bit & 7;
+        const uint64_t d = code(b, dc);
+        if (d == 0) return 0;
+        const uint64_t r = code(b, rc);
+        return b.pos > b.nbits ? -1 : (int64_t)r;
+    }
+    bool clean(int64_t c) {
+        for (int64_t y = c; y < p.nodes && y < c + p.window; y++) {
+            const int64_t r = ref_of(y);
+            if (r < 0 || r > y - c) return false;
+        }
+        return true;
+    }
+    int32_t cut_near(uint64_t target_bit, int64_t lo_limit) {
+        const int64_t k = (int64_t)(std::lower_bound(offs.begin(), offs.end(), target_bit) - offs.begin());
+        const int64_t k0 = std::max<int64_t>(lo_limit, std::min<int64_t>(k, p.nodes));
+        for (int64_t dlt = 0; dlt <= SHARD_CLEAN_REACH; dlt++) {
+            for (int sgn = 0; sgn < 2; sgn++) {
+                const int64_t c = sgn ? k0 - dlt : k0 + dlt;
+                if (dlt == 0 && sgn) continue;
+                if (c <= lo_limit || c >= p.nodes) continue;
+                if (clean(c)) return (int32_t)c;
+            }
+        }
+        return (int32_t)k0;
+    }
+};
+
 int bvg_plan_shards(const char* basename, int nshards, int32_t* bounds) {
     if (!basename || nshards < 1 || !bounds) return BVG_EINVAL;
-    Properties p;
-    int rc = load_properties(basename, p);
+    ShardPlanner sp;
+    int rc = sp.open(basename);
     if (rc) return rc;
-    std::vector<uint8_t> ostream;
-    if (!slurp_file(std::string(basename) + ".offsets", ostream)) return BVG_EIO;
-    std::vector<uint64_t> offs;
-    const int oc = ((p.flags >> 20) & 0xF) ? (int)((p.flags >> 20) & 0xF) : C_GAMMA;
-    rc = decode_offsets_stream(ostream.data(), ostream.size(), oc, p.nodes, offs);
-    if (rc) return rc;
-    const uint64_t total = offs[(size_t)p.nodes];
+    const uint64_t total = sp.offs[(size_t)sp.p.nodes];
     bounds[0] = 0;
-    for (int i = 1; i < nshards; i++) {  // equal bits, cut at the nearest node boundary
-        const uint64_t target = total / (uint64_t)nshards * (uint64_t)i;
-        const size_t k = (size_t)(std::lower_bound(offs.begin(), offs.end(), target) - offs.begin());
-        bounds[i] = (int32_t)std::max<int64_t>(bounds[i - 1], std::min<int64_t>((int64_t)k, p.nodes));
+    for (int i = 1; i < nshards; i++) bounds[i] = sp.cut_near(total / (uint64_t)nshards * (uint64_t)i, bounds[i - 1]);  // equal bits
+    bounds[nshards] = (int32_t)sp.p.nodes;
+    return BVG_OK;
+}
+
+int bvg_replan_shards(const char* basename, int nshards, const int32_t* old_bounds, const double* old_cost, int32_t* bounds) {
+    if (!basename || nshards < 1 || !bounds || !old_bounds || !old_cost) return BVG_EINVAL;
+    ShardPlanner sp;
+    int rc = sp.open(basename);
+    if (rc) return rc;
+    if (old_bounds[0] != 0 || old_bounds[nshards] != sp.p.nodes) return BVG_EINVAL;
+    double total = 0;
+    for (int j = 0; j < nshards; j++) { if (old_bounds[j + 1] < old_bounds[j] || !(old_cost[j] >= 0)) return BVG_EINVAL; total += old_cost[j]; }
+    bounds[0] = 0;
+    int j = 0;
+    double before = 0;  // cost of the old shards 0 .. j-1
+    for (int i = 1; i < nshards; i++) {
+        const double want = total * i / nshards;
+        while (j < nshards - 1 && before + old_cost[j] < want) { before += old_cost[j]; j++; }
+        const uint64_t b0 = sp.offs[(size_t)old_bounds[j]], b1 = sp.offs[(size_t)old_bounds[j + 1]];
+        const double f = old_cost[j] > 0 ? std::min(1.0, std::max(0.0, (want - before) / old_cost[j])) : 0.0;
+        bounds[i] = sp.cut_near(b0 + (uint64_t)((double)(b1 - b0) * f), bounds[i - 1]);
     }
-    bounds[nshards] = (int32_t)p.nodes;
+    bounds[nshards] = (int32_t)sp.p.nodes;
     return BVG_OK;
 }
 
@@ -1208,7 +1297,26 @@ int bvg_memory_footprint(const bvg_graph* g, int64_t* stream_bytes, int64_t* off
     const int64_t nn = (int64_t)g->node_hi - g->node_lo;
     if (stream_bytes) *stream_bytes = (int64_t)g->nwords * 4;
     if (offsets_bytes) *offsets_bytes = (nn + 1) * 8;
-    if (index_bytes) *index_bytes = nn * 12 + (nn + 1) * 8;
+    if (index_bytes) {
+        int64_t b = nn * 12 + (nn + 1) * 8;                                         // outdegree, reference, depth; row offsets
+        if (g->d_is_parent) b += nn;
+        b += g->long_index_bytes;
+        if (g->schedules_ready) b += nn * 4 + g->order_e_count * (4 + (int64_t)sizeof(ExtraRec)) + g->order_m_count * (4 + (int64_t)sizeof(MergeRec));
+        if (g->d_tiles) b += (int64_t)g->ntiles * ((int64_t)sizeof(TileEntry) + 4);
+        if (g->d_stream_entries) b += (g->stream_chunks + 1) * (int64_t)sizeof(StreamEntry);
+        *index_bytes = b;
+    }
+    return BVG_OK;
+}
+
+int bvg_scan_bits(const bvg_graph* g, int64_t* out) {
+    if (!g || !out) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    uint64_t oa = 0, ob = 0;
+    if (g->ext_to > g->ext_from) { const int rc = fetch_offsets(g, g->ext_from, g->ext_to, &oa, &ob); if (rc) return rc; }
+    out[0] = (int64_t)(ob - oa);
+    out[1] = g->nlong; out[2] = g->long_resid_bits; out[3] = g->long_pre_bits; out[4] = g->long_arcs;
+    out[5] = g->schedules_ready ? 1 : 0;
     return BVG_OK;
 }
 

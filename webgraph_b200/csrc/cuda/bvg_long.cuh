@@ -362,13 +362,13 @@ __global__ void k_long_count(GraphDev g, const int32_t* __restrict__ long_nodes,
                              LongMeta* __restrict__ meta) {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlong) return;
-    LongMeta m;
+    LongMeta m{};   // every byte defined: the array is copied to the host (offsets are laid out there)
     m.x = long_nodes[l];
     m.level = g.depth[m.x - g.node_lo];
     m.flags = (is_parent && is_parent[m.x - g.node_lo]) ? 1 : 0;
     m.rec_end = g.offsets[m.x - g.node_lo + 1] - g.bit_base;
     long_walk<DEF>(g, m, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-    m.cb_off = m.iv_off = m.seg_off = m.tmp_off = 0;
+    m.cb_off = m.iv_off = m.seg_off = m.tmp_off = m.scan_off = 0;
     meta[l] = m;
 }
 
