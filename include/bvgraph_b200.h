@@ -122,6 +122,15 @@ int  bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* 
  * {arcs, checksum} in the two-word device buffer d_result (int64, uint64). */
 int  bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_result);
 
+/* ---- fused consumers of the decode path: the successors never leave the device ----
+ * bvg_indegrees: the counting pass of a transposition (Transform.java:977-987, numPred[a[d]]++): counts[y] += number of arcs
+ * (x, y) with x in [from, to).  counts holds counts_len entries (host, or device with on_device); successors >= counts_len are
+ * ignored.  *arcs = arcs scanned.  Ranks of a sharded graph add their counts up (an all-reduce).
+ * bvg_bfs: breadth-first visit from `source` (algo/ParallelBreadthFirstVisit.java:155-181): dist[x] = distance, -1 when
+ * unreachable (n entries); *levels = eccentricity of the source, *reached = nodes reached.  Whole graphs with offsets only. */
+int  bvg_indegrees(const bvg_graph* g, int32_t from, int32_t to, uint32_t* counts, int64_t counts_len, int on_device, int64_t* arcs);
+int  bvg_bfs(const bvg_graph* g, int32_t source, int32_t* dist, int on_device, int32_t* levels, int64_t* reached);
+
 /* ---- NodeIterator: BVGraphNodeIterator :1136-1281 (nextInt, outdegree, successorArray, copy(upperBound)) ---- */
 int  bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor** out);
 /* succ stays valid until the next call on this cursor (NodeIterator.successorArray() aliasing, BVGraph.java:1228-1233). */

@@ -17,6 +17,7 @@ static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v)
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 static inline int atomicCAS(int* p, int cmp, int val) { int old = *p; if (old == cmp) *p = val; return old; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long val) { unsigned long long old = *p; if (old == cmp) *p = val; return old; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 static inline void __threadfence() {}
 // kernels in the included headers are compiled but never called on the host: give their index variables a meaning
 struct Dim3Shim { unsigned x = 0, y = 0, z = 0; };

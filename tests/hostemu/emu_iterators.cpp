@@ -43,7 +43,7 @@ extern "C" int emu_masked(const int32_t* parent, int32_t dp, const int32_t* bloc
     g.words = bw.w.data(); g.nwords = bw.w.size(); g.bit_base = 0; g.bit_end = bw.n;
     g.offsets = offsets.data(); g.node_lo = 0; g.node_hi = 1;
     g.c = Codec{ C_GAMMA, C_GAMMA, C_ZETA, C_UNARY, C_GAMMA, 3, 7, 4 };
-    g.err = &err;
+    g.err = &err; g.hist = nullptr; g.hist_len = 0;
     // the parent's list in a buffer with guard values on both sides (nothing may be read outside the list)
     std::vector<int32_t> pbuf((size_t)dp + 16, -12345);
     int32_t* prow = pbuf.data() + 5;  // deliberately not 16-byte aligned

@@ -34,7 +34,7 @@ extern "C" int emu_stream_scan(const uint8_t* graph, uint64_t nbytes, const uint
     g.words = words.data(); g.nwords = words.size(); g.bit_base = 0; g.bit_end = offsets[n];
     g.offsets = offsets; g.node_lo = 0; g.node_hi = n;
     g.c = Codec{ C_GAMMA, C_GAMMA, C_ZETA, C_UNARY, C_GAMMA, zetak, window, minlen };
-    g.outdeg = outdeg.data(); g.ref = ref.data(); g.depth = depth.data(); g.rowoff = rowoff.data(); g.copied = nullptr; g.err = &err;
+    g.outdeg = outdeg.data(); g.ref = ref.data(); g.depth = depth.data(); g.rowoff = rowoff.data(); g.copied = nullptr; g.err = &err; g.hist = nullptr; g.hist_len = 0;
     int maxdepth = 0;
     for (int32_t x = 0; x < n; x++) {
         Bits b = cursor_at(g, x);

@@ -36,7 +36,7 @@ void build(EmuGraph& E, const uint8_t* graph, uint64_t nbytes, const uint64_t* o
     g.words = E.words.data(); g.nwords = E.words.size(); g.bit_base = 0; g.bit_end = offsets[n];
     g.offsets = offsets; g.node_lo = 0; g.node_hi = n;
     g.c = Codec{ C_GAMMA, C_GAMMA, C_ZETA, C_UNARY, C_GAMMA, zetak, window, minlen };
-    g.outdeg = E.outdeg.data(); g.ref = E.ref.data(); g.depth = E.depth.data(); g.rowoff = nullptr; g.copied = nullptr; g.err = &E.err;
+    g.outdeg = E.outdeg.data(); g.ref = E.ref.data(); g.depth = E.depth.data(); g.rowoff = nullptr; g.copied = nullptr; g.err = &E.err; g.hist = nullptr; g.hist_len = 0;
     for (int32_t x = 0; x < n; x++) {
         Bits b = cursor_at(g, x);
         const uint64_t d = Rd<true>::outdeg(b, g.c);

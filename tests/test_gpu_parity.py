@@ -325,6 +325,52 @@ def test_alternative_scan_kernels(synth100k, cnr_truth, monkeypatch, env):
     assert (tot_a, tot_c) == (st["arcs"], st["xor_checksum"])
 
 
+def _bfs_numpy(off, succ, source):
+    n = len(off) - 1
+    dist = np.full(n, -1, dtype=np.int32)
+    dist[source] = 0
+    frontier = np.array([source], dtype=np.int64)
+    level = 0
+    while len(frontier):
+        starts, ends = off[frontier], off[frontier + 1]
+        idx = np.concatenate([np.arange(a, b) for a, b in zip(starts, ends)]) if len(frontier) else np.zeros(0, dtype=np.int64)
+        nxt = np.unique(succ[idx]) if len(idx) else np.zeros(0, dtype=np.int64)
+        nxt = nxt[dist[nxt] < 0]
+        level += 1
+        dist[nxt] = level
+        frontier = nxt.astype(np.int64)
+    return dist
+
+
+def test_fused_consumers_indegrees_and_bfs(cnr, cnr_truth, synth100k):
+    """the counting pass of a transposition (Transform.java:977-987) done by the scan itself, and a breadth-first
+    visit (ParallelBreadthFirstVisit.java:155-181) over device-side random access, against numpy on the truth."""
+    off, succ = cnr_truth
+    n = len(off) - 1
+    assert np.array_equal(cnr.indegrees(), np.bincount(succ, minlength=n).astype(np.uint32))
+    lo, hi = 1000, 200000   # a sub-range: only the arcs leaving [lo, hi)
+    assert np.array_equal(cnr.indegrees(lo, hi), np.bincount(succ[off[lo]:off[hi]], minlength=n).astype(np.uint32))
+    for source in (0, 12345, 325556):
+        dist, levels, reached = cnr.bfs(source)
+        want = _bfs_numpy(off, succ, source)
+        assert np.array_equal(dist, want), source
+        assert levels == int(want.max()) and reached == int((want >= 0).sum())
+    base, st, soff, ssucc = synth100k
+    g = BVGraph.load(base)
+    assert np.array_equal(g.indegrees(), np.bincount(ssucc, minlength=g.numNodes()).astype(np.uint32))   # long records included
+    dist, levels, reached = g.bfs(7)
+    assert np.array_equal(dist, _bfs_numpy(soff, ssucc, 7))
+    g.close()
+    # shards add up (what an all-reduce of the ranks' counts gives)
+    bounds = bvgraph.plan_shards(base, 3)
+    tot = np.zeros(len(soff) - 1, dtype=np.uint32)
+    for r in range(3):
+        gs = BVGraph.loadShard(base, bounds[r], bounds[r + 1])
+        tot += gs.indegrees()
+        gs.close()
+    assert np.array_equal(tot, np.bincount(ssucc, minlength=len(soff) - 1).astype(np.uint32))
+
+
 def test_weblike_1m_full_parity(tmp_path, oracle):
     """The second benchmark workload (copy-heavy, cnr-2000's mix: ~3.6 bits/arc, ~63 % copied arcs, avgref ~1.3) at 1 M nodes:
     every list against the generator's own and against the oracle; scan checksum and sum of successors."""

@@ -55,7 +55,7 @@ SYMBOLS = [
     "bvg_cursor_copy", "bvg_cursor_close", "bvg_cursor_drain", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
     "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_release_cached_memory", "bvg_profile", "bvg_profile_read",
-    "bvg_scan_bits", "bvg_replan_shards",
+    "bvg_scan_bits", "bvg_replan_shards", "bvg_indegrees", "bvg_bfs",
 ]
 
 
@@ -109,6 +109,8 @@ def lib():
     L.bvg_kernel_launches.restype = i64
     L.bvg_memory_footprint.argtypes = [vp, P(i64), P(i64), P(i64)]
     L.bvg_scan_bits.argtypes = [vp, P(i64)]
+    L.bvg_indegrees.argtypes = [vp, i32, i32, vp, i64, C.c_int, P(i64)]
+    L.bvg_bfs.argtypes = [vp, i32, vp, C.c_int, P(i32), P(i64)]
     _lib = L
     return L
 
@@ -493,6 +495,27 @@ class BVGraph(ImmutableGraph):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(lib().bvg_memory_footprint(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"stream_bytes": a.value, "offsets_bytes": b.value, "index_bytes": c.value}
+
+    def indegrees(self, frm=None, to=None, counts=None):
+        """In-degree of every node from the arcs leaving [frm, to) (the counting pass of Transform.transposeOffline, reference
+        Transform.java:977-987), counted on the device by the scan itself.  Returns a uint32 array of numNodes() entries."""
+        ext_from, ext_to = C.c_int32(), C.c_int32()
+        _check(lib().bvg_extent(self._h, C.byref(ext_from), C.byref(ext_to), None, None))
+        frm = ext_from.value if frm is None else frm
+        to = ext_to.value if to is None else to
+        if counts is None:
+            counts = np.zeros(self._n, dtype=np.uint32)
+        arcs = C.c_int64()
+        _check(lib().bvg_indegrees(self._h, frm, to, counts.ctypes.data, len(counts), 0, C.byref(arcs)))
+        return counts
+
+    def bfs(self, source):
+        """Distances of a breadth-first visit from `source` (-1 = unreachable), the eccentricity of the source and the number of
+        nodes reached (reference algo/ParallelBreadthFirstVisit.java:155-181)."""
+        dist = np.empty(self._n, dtype=np.int32)
+        levels, reached = C.c_int32(), C.c_int64()
+        _check(lib().bvg_bfs(self._h, source, dist.ctypes.data, 0, C.byref(levels), C.byref(reached)))
+        return dist, levels.value, reached.value
 
     def scanBits(self):
         """What a scan of this graph's extent reads of the stream (bvg_scan_bits)."""

@@ -273,6 +273,7 @@ struct bvg_graph {
         g.offsets = d_offsets; g.node_lo = node_lo; g.node_hi = node_hi; g.c = codec;
         g.outdeg = d_outdeg; g.ref = d_ref; g.depth = d_depth; g.rowoff = d_rowoff; g.err = d_err;
         g.copied = copied_ready ? d_copied : nullptr;
+        g.hist = nullptr; g.hist_len = 0;
         return g;
     }
 };
@@ -1556,9 +1557,11 @@ int bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_
 // Fused consume-only scan over the length-bucketed schedules: parents' rows go to `rows` (addressed like the CSR of
 // [from, to)), everything else is folded in registers; long records are materialised by the split path and folded by
 // k_checksum_nodes.
-static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int32_t* rows, int64_t row_from, unsigned long long* d_result) {
+static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int32_t* rows, int64_t row_from, unsigned long long* d_result,
+                              uint32_t* hist = nullptr, int64_t hist_len = 0) {
     cudaStream_t s = g->stream;
     GraphDev gd = g->dev();
+    gd.hist = hist; gd.hist_len = hist_len;
     RowMap rm;
     HaloPlan hp(s);
     { const int rc = plan_halo(g, from, to, rows, row_from, rm, hp); if (rc) return rc; }
@@ -1579,11 +1582,13 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     LongDst ld{ nullptr };
     const LongIndex li = g->long_index();
     const LongFold lf{ d_result, from };  // long records nobody copies from are folded where their parts are produced
-    // BVG_SCAN_OVERLAP=1: the long-record kernels run on a second stream beside the short-record kernels of the same chain
-    // level; the two streams meet before every level, because a short record may copy from a long one and the other way
-    // round.  Measured 6.54 -> 6.44 ms per scan: the short-record kernels already fill the machine, so it is off by default
-    // and the per-kernel times of bvg_profile stay disjoint.
-    static const bool overlap = env_int("BVG_SCAN_OVERLAP", 0, 0, 1) != 0;
+    // The long-record kernels run on a second stream beside the short-record kernels of the same chain level; the two streams
+    // meet before every level, because a short record may copy from a long one and the other way round.
+    // Round 2: on by default (5.95 -> 5.67 ms at 1 GPU, 3.41 -> 3.09 ms per rank at 2 GPUs: the long-record kernels are chains of
+    // dependent loads -- merge-path searches over prefix sums -- whose ~0.1 ms floors no longer add up with the short kernels');
+    // off while per-kernel profiling is on, so that the kernel times of bvg_profile stay disjoint.
+    static const bool overlap_default = env_int("BVG_SCAN_OVERLAP", 1, 0, 1) != 0;
+    const bool overlap = overlap_default && !g->prof_on;
     std::unique_lock<std::mutex> scan_lock(g->scan_mu, std::defer_lock);
     cudaStream_t sa = s;
     if (g->nlong && overlap) { scan_lock.lock(); if (g->aux_ready()) sa = g->aux; else scan_lock.unlock(); }
@@ -1603,7 +1608,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     static const bool lean = !(getenv("BVG_SCAN_LEAN") && atoi(getenv("BVG_SCAN_LEAN")) == 0);
     static const int dbg_nostore = env_int("BVG_DEBUG_NOSTORE", 0, 0, 1);  // timing experiments only: no row stores, results are wrong
     static const bool ring = env_int("BVG_SCAN_RING", 1, 0, 1) != 0;  // stream staged in shared memory by cp.async (bvg_scan.cuh, WinRing)
-    const bool stream_extras = g->d_stream_entries != nullptr && g->stream_chunks > 0;
+    const bool stream_extras = g->d_stream_entries != nullptr && g->stream_chunks > 0 && hist == nullptr;
     if (stream_extras) {
         // every record's extras and every residual run, long records included, by stream position (bvg_stream.cuh)
         uint64_t oa, ob;
@@ -1641,6 +1646,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
             else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
         }
+        if (stream_extras) CK(meet());   // the residuals of the long records were written on the main stream
         if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
@@ -1721,32 +1727,43 @@ static int enqueue_scan_tiles(const bvg_graph* g, int32_t from, int32_t to, unsi
 
 // Scan = decode into a stream-ordered scratch + checksum kernel (general path); ranges are split so that the scratch
 // stays below 2^30 arcs.
-static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned long long* d_result) {
+// k_checksum's companion for the general path of bvg_indegrees: counts every successor of a decoded CSR chunk
+__global__ void k_hist_rows(const int32_t* __restrict__ rows, int64_t n, uint32_t* __restrict__ hist, int64_t hist_len) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t y = (uint32_t)rows[i];
+        if ((int64_t)y < hist_len) atomicAdd(hist + y, 1u);
+    }
+}
+
+static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned long long* d_result, uint32_t* hist = nullptr, int64_t hist_len = 0) {
     if (to == from) return BVG_OK;
-    if (g->tile_ok) return enqueue_scan_tiles(g, from, to, d_result);
+    if (g->tile_ok && !hist) return enqueue_scan_tiles(g, from, to, d_result);
     int64_t ra, rb;
     int rc = fetch_rowoff(g, from, to, &ra, &rb);
     if (rc) return rc;
     const int64_t arcs = rb - ra;
     if (arcs > ((int64_t)1 << 30) && to - from > 1) {
         const int32_t mid = from + (to - from) / 2;
-        rc = enqueue_scan(g, from, mid, d_result);
+        rc = enqueue_scan(g, from, mid, d_result, hist, hist_len);
         if (rc) return rc;
-        return enqueue_scan(g, mid, to, d_result);
+        return enqueue_scan(g, mid, to, d_result, hist, hist_len);
     }
     cudaStream_t s = g->stream;
     Tmp<int32_t> rows(s);
     CK(rows.alloc((size_t)arcs));
-    if (g->d_is_parent && g->max_depth <= MAX_LEVEL_KEYS && ((int64_t)to - from) * 4 >= (int64_t)g->node_hi - g->node_lo) {
+    // (the fused consumer counts in the lean walkers' fold: default codings; anything else decodes and counts the rows)
+    if (g->d_is_parent && g->max_depth <= MAX_LEVEL_KEYS && ((int64_t)to - from) * 4 >= (int64_t)g->node_hi - g->node_lo && (!hist || g->def_codec)) {
         rc = ensure_schedules(g);
         if (rc) return rc;
-        return enqueue_scan_fused(g, from, to, rows.p, ra, d_result);
+        return enqueue_scan_fused(g, from, to, rows.p, ra, d_result, hist, hist_len);
     }
     rc = enqueue_decode(g, from, to, rows.p, ra);
     if (rc) return rc;
     const int64_t cnt = (int64_t)to - from;
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (cnt + 7) / 8));
     LAUNCH_P(g, "k_checksum", k_checksum, grid, 256, 0, s, rows.p, g->d_rowoff + (from - g->node_lo), from, cnt, d_result);
+    if (hist) LAUNCH_P(g, "k_hist_rows", k_hist_rows, 148 * 8, 256, 0, s, rows.p, arcs, hist, hist_len);
     CK(cudaGetLastError());
     return BVG_OK;
 }
@@ -1783,6 +1800,117 @@ int bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, 
     if (e) return e;
     if (arcs) *arcs = (int64_t)h[0];
     if (checksum) *checksum = h[1];
+    return BVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fused consumers of the sequential scan
+// ------------------------------------------------------------------------------------------------------------
+
+// The counting pass of a transposition (reference Transform.java:977-987: for every arc (x, y) numPred[y]++): a scan whose
+// consumer counts instead of only folding; the successors never leave the device.
+int bvg_indegrees(const bvg_graph* g, int32_t from, int32_t to, uint32_t* counts, int64_t counts_len, int on_device, int64_t* arcs) {
+    int rc = range_check(g, from, to);
+    if (rc) return rc;
+    if (!counts || counts_len < 0) return BVG_EINVAL;
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    Tmp<uint32_t> d_counts(s);
+    uint32_t* hist = counts;
+    if (!on_device) {
+        CK(d_counts.alloc((size_t)std::max<int64_t>(counts_len, 1)));
+        CK(cudaMemcpyAsync(d_counts.p, counts, (size_t)counts_len * 4, cudaMemcpyHostToDevice, s));
+        hist = d_counts.p;
+    }
+    Tmp<unsigned long long> slots(s), res(s);
+    CK(slots.alloc(2 * FOLD_SLOTS));
+    CK(res.alloc(2));
+    CK(cudaMemsetAsync(slots.p, 0, 2 * FOLD_SLOTS * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(res.p, 0, 16, s));
+    rc = enqueue_scan(g, from, to, slots.p, hist, counts_len);
+    if (rc) return rc;
+    LAUNCH(k_reduce_slots, 1, 256, 0, s, slots.p, res.p);
+    CK(cudaGetLastError());
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, res.p, 16, cudaMemcpyDeviceToHost, s));
+    if (!on_device) CK(cudaMemcpyAsync(counts, d_counts.p, (size_t)counts_len * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int e = fetch_error(g);
+    if (e) return e;
+    if (arcs) *arcs = (int64_t)h[0];
+    return BVG_OK;
+}
+
+// One level of a breadth-first visit: every successor y of the frontier that has no distance yet gets `level` and joins the
+// next frontier (the marker test-and-set of ParallelBreadthFirstVisit.java:163-172).
+__global__ void k_bfs_expand(const int32_t* __restrict__ succ, int64_t n, int32_t* __restrict__ dist, int64_t dist_len, int32_t level,
+                             int32_t* __restrict__ next, unsigned int* __restrict__ next_count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t y = succ[i];
+        if (y >= 0 && y < dist_len && dist[y] < 0 && atomicCAS(dist + y, -1, level) == -1) next[atomicAdd(next_count, 1u)] = y;
+    }
+}
+__global__ void k_fill_i32(int32_t* __restrict__ p, int64_t n, int32_t v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// Breadth-first visit from `source` (reference algo/ParallelBreadthFirstVisit.java:155-181: frontier by frontier, the
+// successors of a frontier decoded by random access): dist[x] = distance from source, -1 when unreachable.  Frontier,
+// successor lists and distances stay on the device; the host sees one counter per level.
+int bvg_bfs(const bvg_graph* g, int32_t source, int32_t* dist, int on_device, int32_t* levels, int64_t* reached) {
+    if (!g || !dist) return BVG_EINVAL;
+    if (source < g->ext_from || source >= g->ext_to) return BVG_EINVAL;
+    if (g->offset_type <= 0) return BVG_EUNSUPPORTED;  // random access (BVGraph.java:901)
+    if (g->ext_from != 0 || g->ext_to != g->n_total) return BVG_EUNSUPPORTED;  // a visit follows arcs anywhere: whole graphs (replicas) only
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    const int64_t n = g->n_total;
+    Tmp<int32_t> d_dist(s), fa(s), fb(s), lists(s);
+    Tmp<int64_t> off(s);
+    Tmp<unsigned int> cnt(s);
+    int32_t* dd = dist;
+    if (!on_device) { CK(d_dist.alloc((size_t)n)); dd = d_dist.p; }
+    CK(fa.alloc((size_t)n));
+    CK(fb.alloc((size_t)n));
+    CK(cnt.alloc(1));
+    LAUNCH(k_fill_i32, 148 * 4, 256, 0, s, dd, n, -1);
+    LAUNCH(k_set_i32, 1, 1, 0, s, dd + source, 0);
+    LAUNCH(k_set_i32, 1, 1, 0, s, fa.p, source);
+    CK(cudaGetLastError());
+    int32_t *cur = fa.p, *nxt = fb.p;
+    int64_t nf = 1, total = 1;
+    int32_t level = 0;
+    size_t off_cap = 0, lists_cap = 0;
+    while (nf > 0) {
+        if ((size_t)nf + 1 > off_cap) { off_cap = (size_t)nf + 1 + (size_t)nf / 2; Tmp<int64_t> t(s); CK(t.alloc(off_cap)); std::swap(t.p, off.p); }
+        int rc = bvg_successors_batch(g, cur, nf, off.p, nullptr, 0, 1);   // sizes
+        if (rc) return rc;
+        int64_t arcs = 0;
+        CK(cudaMemcpyAsync(&arcs, off.p + nf, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        unsigned int next_n = 0;
+        if (arcs > 0) {
+            if ((size_t)arcs > lists_cap) { lists_cap = (size_t)arcs + (size_t)arcs / 2; Tmp<int32_t> t(s); CK(t.alloc(lists_cap)); std::swap(t.p, lists.p); }
+            rc = bvg_successors_batch(g, cur, nf, off.p, lists.p, arcs, 1);
+            if (rc) return rc;
+            CK(cudaMemsetAsync(cnt.p, 0, 4, s));
+            LAUNCH(k_bfs_expand, 148 * 4, 256, 0, s, lists.p, arcs, dd, n, level + 1, nxt, cnt.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&next_n, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        nf = next_n;
+        total += nf;
+        if (nf > 0) level++;
+        std::swap(cur, nxt);
+    }
+    if (!on_device) { CK(cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+    const int e = fetch_error(g);
+    if (e) return e;
+    if (levels) *levels = level;
+    if (reached) *reached = total;
     return BVG_OK;
 }
 

@@ -62,6 +62,10 @@ struct GraphDev {
     const int64_t* __restrict__ rowoff;   // [x - node_lo]  cumulative outdegree, node_hi - node_lo + 1 entries
     const int32_t* __restrict__ copied;   // [x - node_lo]  successors copied from the parent (k_order_keys); may be null
     ErrWord* err;
+    // fused consumer of a scan (bvg_indegrees): when set, every successor y the scan folds also counts in hist[y]
+    // (the transposition counting pass, reference Transform.java:977-987: numPred[a[d]]++)
+    uint32_t* hist;
+    int64_t hist_len;
 };
 
 __device__ __forceinline__ void report(ErrWord* e, int code, int node, uint64_t bitpos) {

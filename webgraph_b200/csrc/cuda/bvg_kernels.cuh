@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
         unsigned long long f = 0;
         ScanExtras<K, W> w;
-        w.begin(g, r.x, r.nout, r.pos, active, my_ring);
+        w.begin(g, r.x, r.nout, r.pos, active, my_ring, fold);
         if (has_iv) w.iv_fold(g); else w.iv_none(g);
         __syncwarp();
         if (__any_sync(0xffffffffu, store)) w.template resid<true>(g, row, store);
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g
         unsigned long long f = 0;
         if (active && !store) f = copied_fold<BATCH>(g, c, r.x, parent);
         __syncwarp();
-        if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent);
+        if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent, fold);
         __syncwarp();
         if (fold) acc ^= f;
     }

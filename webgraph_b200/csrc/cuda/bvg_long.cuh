@@ -425,7 +425,7 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
                     const int32_t first = part * li.seg;
                     const int32_t cnt = min(li.seg, m.rc - first);
                     Fold32 f;
-                    f.begin(m.x);
+                    f.begin(m.x, g, true);
                     BitBuf b;
                     b.w = g.words; b.maxw = g.nwords - 3;
                     b.seek(li.seg_pos[m.seg_off + part]);
@@ -442,8 +442,10 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
             } else if (!consume || m.x >= lf.from) {
                 const int32_t first = part * li.seg;
                 const int32_t cnt = min(li.seg, m.rc - first);
+                // stored records with neither intervals nor a copied part get their final row here: fold it now
+                const bool final_here = (consume || (lf.result != nullptr && m.ic == 0 && m.copied == 0)) && m.x >= lf.from;
                 Fold32 f;
-                f.begin(m.x);
+                f.begin(m.x, g, final_here);
                 const int k = g.c.zetak;
                 Win b;
                 b.seek(g, li.seg_pos[m.seg_off + part]);
@@ -461,8 +463,7 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
                     f.add(v);
                     if (!consume) out[t] = (int32_t)v;
                 }
-                // stored records with neither intervals nor a copied part get their final row here: fold it now
-                if (consume || (lf.result != nullptr && m.ic == 0 && m.copied == 0 && m.x >= lf.from)) {
+                if (final_here) {
                     f.n = (uint32_t)cnt;
                     acc = f.finish(m.x);
                     arcs = cnt;
@@ -491,14 +492,14 @@ __global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t nite
                 const int32_t cnt = min(li.chunk, total - q0);
                 const bool final_row = lf.result != nullptr && m.copied == 0 && m.x >= lf.from;  // no copied part follows
                 Fold32 f;
-                f.begin(m.x);
+                f.begin(m.x, g, true);
                 merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
                             cnt, dst.extras(m, rm.row(g, m.x)), final_row ? &f : nullptr);
                 if (final_row) { f.n = (uint32_t)cnt; acc = f.finish(m.x); arcs = cnt; }
             } else if (m.x >= lf.from && q0 < m.ilen) {  // interval elements [q0, q0 + chunk) of the concatenated intervals
                 const int32_t cnt = min(li.chunk, m.ilen - q0);
                 Fold32 f;
-                f.begin(m.x);
+                f.begin(m.x, g, true);
                 int32_t t = upper_slot(a.cum, a.n, q0), t_end = a.cum[t + 1];
                 for (int32_t q = q0; q < q0 + cnt; q++) {
                     while (q >= t_end) { t++; t_end = a.cum[t + 1]; }
@@ -531,14 +532,14 @@ __global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
                 const int32_t cnt = min(li.chunk, m.d - q0);
                 const bool final_row = lf.result != nullptr && m.x >= lf.from;
                 Fold32 f;
-                f.begin(m.x);
+                f.begin(m.x, g, true);
                 merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
                             m.d - m.copied, q0, cnt, rm.row(g, m.x), final_row ? &f : nullptr);
                 if (final_row) { f.n = (uint32_t)cnt; acc = f.finish(m.x); arcs = cnt; }
             } else if (m.x >= lf.from && q0 < m.copied) {  // copied elements [q0, q0 + chunk) seen through the copy blocks
                 const int32_t cnt = min(li.chunk, m.copied - q0);
                 Fold32 f;
-                f.begin(m.x);
+                f.begin(m.x, g, true);
                 int32_t t = upper_slot(a.cum, a.n, q0), t_end = a.cum[t + 1];
                 for (int32_t q = q0; q < q0 + cnt; q++) {
                     while (q >= t_end) { t++; t_end = a.cum[t + 1]; }

@@ -329,11 +329,20 @@ __device__ __forceinline__ uint64_t zeta_any(W& b, const GraphDev& g, int k) {  
 // 32-bit halves of the checksum of one record: XOR of lo(base + y), number of carries out of the low word.
 struct Fold32 {
     uint32_t base_lo, xlo, carries, n;
-    __device__ __forceinline__ void begin(int32_t x) { base_lo = (uint32_t)((unsigned long long)(uint32_t)x * BVG_MIX); xlo = 0; carries = 0; n = 0; }
+    uint32_t* hist;      // fused in-degree count (GraphDev.hist), nullptr in a plain scan
+    uint32_t hist_len;
+    __device__ __forceinline__ void begin(int32_t x) { base_lo = (uint32_t)((unsigned long long)(uint32_t)x * BVG_MIX); xlo = 0; carries = 0; n = 0; hist = nullptr; hist_len = 0; }
+    // counted: the successors added here are consumed by the scan (not a halo record, not a fold that a later step repeats on
+    // the final list): only then do they count in the fused histogram
+    __device__ __forceinline__ void begin(int32_t x, const GraphDev& g, bool counted) {
+        begin(x);
+        if (counted) { hist = g.hist; hist_len = (uint32_t)(g.hist_len > 0xffffffffll ? 0xffffffffll : g.hist_len); }
+    }
     __device__ __forceinline__ void add(uint32_t y) {
         const uint32_t lo = base_lo + y;
         carries += lo < y ? 1u : 0u;
         xlo ^= lo;
+        if (hist != nullptr && y < hist_len) atomicAdd(hist + y, 1u);
     }
     // XOR over the n folded successors of (x*MIX + y): hi word is base_hi for the ones without a carry, base_hi + 1 with
     __device__ __forceinline__ unsigned long long finish(int32_t x) const {
@@ -411,9 +420,10 @@ struct ScanExtras {
         err = code; rc = 0;
     }
 
-    __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active, ring_addr ring_slot = ring_addr()) {
+    __device__ __forceinline__ void begin(const GraphDev& g, int32_t x_, int32_t nout_, uint64_t pos, bool active, ring_addr ring_slot = ring_addr(),
+                                          bool counted = true) {
         x = x_; nout = 0; rc = 0; err = 0; v = 0; ic = 0; iv_pos = 0;
-        f.begin(x_);
+        f.begin(x_, g, counted);
         b.attach(ring_slot);
         if (!active) return;
         nout = nout_;
@@ -581,7 +591,7 @@ typedef CopyRunsT<COPY_RUNS> CopyRuns;
 template <int BATCH, class CR>
 __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CR& c, int32_t x, const int32_t* __restrict__ parent) {
     Fold32 f;
-    f.begin(x);
+    f.begin(x, g, true);
     // BATCH positions first, then their loads together: a lane opens a new sector of its parent's row every eighth element,
     // the 32 lanes read 32 unrelated rows, and with one load per trip the warp waits a memory round trip on every trip
 #pragma unroll 1
@@ -606,9 +616,9 @@ __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CR&
 // folded when they were decoded.
 template <class CR>
 __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CR& c, int32_t x, int32_t d, int32_t copied,
-                                                           int32_t* row, const int32_t* __restrict__ parent) {
+                                                           int32_t* row, const int32_t* __restrict__ parent, bool counted = true) {
     Fold32 f;
-    f.begin(x);
+    f.begin(x, g, counted);
     int32_t j = copied, k = 0;
     RowWriter<false> wr;  // measured: combining helps the extras kernel (3.92 -> 3.71 ms) and costs registers here (2.22 -> 2.49 ms)
     wr.begin(row);
