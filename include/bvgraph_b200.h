@@ -14,9 +14,13 @@
  * are device pointers on the graph's device (e.g. torch tensors' data_ptr()), and the call is
  * asynchronous on the graph's stream (bvg_set_stream); otherwise they are host pointers and the
  * call returns after the results have been copied back.
- * A bvg_graph is immutable after open and may be shared by host threads that each use their own
- * stream (== BVGraph.copy() flyweights, ImmutableGraph.java:157-165,411-420); a bvg_cursor is
- * single-threaded (== BVGraphNodeIterator).
+ * Threading (reference contract: an ImmutableGraph instance is not thread-safe, copy() is, and copies share the
+ * immutable data, ImmutableGraph.java:157-165,411-420): the data of a bvg_graph is immutable after open and shared
+ * by everything opened on it.  The entry points that take a bvg_graph run on the graph's one stream and report into
+ * its one error word; they lock the graph, so concurrent callers are serialised, never corrupted (a binding's copy()
+ * may hand out the same handle).  A bvg_cursor (== BVGraphNodeIterator) owns a stream, an error word and its batch
+ * buffers: cursors of one graph run concurrently, one per host thread, and that is the way to scale the sequential
+ * route across host threads (ImmutableGraph.splitNodeIterators).  A single cursor is single-threaded.
  */
 #ifndef BVGRAPH_B200_H
 #define BVGRAPH_B200_H
@@ -135,6 +139,11 @@ int  bvg_bfs(const bvg_graph* g, int32_t source, int32_t* dist, int on_device, i
 int  bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor** out);
 /* succ stays valid until the next call on this cursor (NodeIterator.successorArray() aliasing, BVGraph.java:1228-1233). */
 int  bvg_cursor_next(bvg_cursor* c, int32_t* node, int32_t* d, const int32_t** succ);
+/* The whole batch that holds the next node, zero-copy: nodes first .. first + count - 1, their successors are
+ * succ[off[i] .. off[i + 1]) for i in [0, count) (pinned host memory owned by the cursor, valid until the next call on it).
+ * The cursor moves past the batch.  A binding wraps the two arrays (JNI NewDirectByteBuffer, numpy) and iterates without
+ * further native calls; batches are decoded on the device one ahead of the caller. */
+int  bvg_cursor_next_batch(bvg_cursor* c, int32_t* first, int32_t* count, const int64_t** off, const int32_t** succ);
 int  bvg_cursor_copy(const bvg_cursor* c, int32_t upper, bvg_cursor** out);
 void bvg_cursor_close(bvg_cursor* c);
 /* The inner loop of a binding, in C: up to max_nodes calls of bvg_cursor_next (all that is left when max_nodes < 0),

@@ -492,6 +492,49 @@ def test_size_independent_properties_on_a_larger_graph(tmp_path):
     g.close()
 
 
+def test_cursor_batches_zero_copy_and_concurrent(cnr, cnr_truth, synth100k):
+    """bvg_cursor_next_batch: whole batches as views of the cursor's pinned memory; cursors of one graph drained by several
+    host threads at once (each has its own stream and error word), split like ImmutableGraph.splitNodeIterators."""
+    import concurrent.futures as cf
+    toff, tsucc = cnr_truth
+    it = cnr.nodeIterator(1234)
+    seen = 1234
+    while True:
+        b = it.nextBatch()
+        if b is None:
+            break
+        first, off, succ = b
+        assert first == seen
+        cnt = len(off) - 1
+        assert np.array_equal(off - off[0], toff[first:first + cnt + 1] - toff[first])
+        assert np.array_equal(succ[off[0]:off[-1]], tsucc[toff[first]:toff[first + cnt]])
+        seen += cnt
+    assert seen == cnr.numNodes()
+    base, st, off, succ = synth100k
+    g = BVGraph.load(base)
+    L = bvgraph.lib()
+    import ctypes as C
+
+    def drain(lo, hi):
+        cur = C.c_void_p()
+        bvgraph._check(L.bvg_cursor_open(g.handle, lo, hi, C.byref(cur)))
+        cn, ca, cc = C.c_int64(), C.c_int64(), C.c_uint64()
+        bvgraph._check(L.bvg_cursor_drain(cur, -1, C.byref(cn), C.byref(ca), C.byref(cc)))
+        L.bvg_cursor_close(cur)
+        return cn.value, ca.value, cc.value
+    k = 6
+    n = g.numNodes()
+    step = (n + k - 1) // k
+    with cf.ThreadPoolExecutor(k) as ex:
+        res = list(ex.map(lambda i: drain(i * step, min(n, (i + 1) * step)), range(k)))
+    assert sum(r[0] for r in res) == n and sum(r[1] for r in res) == st["arcs"]
+    cs = 0
+    for r in res:
+        cs ^= r[2]
+    assert cs == st["xor_checksum"]
+    g.close()
+
+
 def test_cursor_drain_equals_scan(cnr, synth100k):
     """bvg_cursor_drain (the C loop a binding runs over bvg_cursor_next: double-buffered batches in pinned memory) consumes
     exactly what the consume-only scan does; mixing single steps, partial drains and a copied cursor keeps the position."""

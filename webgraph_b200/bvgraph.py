@@ -55,7 +55,7 @@ SYMBOLS = [
     "bvg_cursor_copy", "bvg_cursor_close", "bvg_cursor_drain", "bvg_boundary_count", "bvg_boundary_export", "bvg_halo_needed",
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
     "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_release_cached_memory", "bvg_profile", "bvg_profile_read",
-    "bvg_scan_bits", "bvg_replan_shards", "bvg_indegrees", "bvg_bfs",
+    "bvg_scan_bits", "bvg_replan_shards", "bvg_indegrees", "bvg_bfs", "bvg_cursor_next_batch",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
     L.bvg_scan_range_async.argtypes = [vp, i32, i32, vp]
     L.bvg_cursor_open.argtypes = [vp, i32, i32, P(vp)]
     L.bvg_cursor_next.argtypes = [vp, P(i32), P(i32), P(P(i32))]
+    L.bvg_cursor_next_batch.argtypes = [vp, P(i32), P(i32), P(P(i64)), P(P(i32))]
     L.bvg_cursor_copy.argtypes = [vp, i32, P(vp)]
     L.bvg_cursor_close.argtypes = [vp]
     L.bvg_cursor_close.restype = None
@@ -228,10 +229,27 @@ class NodeIterator:
             raise IllegalStateError("nextInt() has never been called")  # BVGraph.java:1237
         return self._d
 
-    def successorArray(self):
+    def successorArray(self, copy=True):
+        """A fresh array by default.  copy=False returns a view of the cursor's pinned batch (the aliasing the reference allows,
+        BVGraph.java:1228-1233): it is overwritten by a later refill and dangles once the iterator is closed."""
         if self._curr == self._from - 1:
             raise IllegalStateError("nextInt() has never been called")  # :1230
-        return self._succ
+        return self._succ.copy() if copy else self._succ
+
+    def nextBatch(self):
+        """(first node, offsets, successors) of the whole batch holding the next node, zero-copy views of the cursor's pinned
+        memory (bvg_cursor_next_batch): successors of node first + i are succ[off[i]:off[i + 1]].  None at the end.  Valid until
+        the next call on this iterator."""
+        first, count = C.c_int32(), C.c_int32()
+        off, succ = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        rc = lib().bvg_cursor_next_batch(self._h, C.byref(first), C.byref(count), C.byref(off), C.byref(succ))
+        if rc == -8:  # BVG_EEND
+            return None
+        _check(rc, self._g._h)
+        o = np.ctypeslib.as_array(off, shape=(count.value + 1,))
+        sarr = np.ctypeslib.as_array(succ, shape=(max(int(o[-1]), 1),))
+        self._curr = first.value + count.value - 1
+        return first.value, o, sarr
 
     def successors(self):
         if self._curr == self._from - 1:

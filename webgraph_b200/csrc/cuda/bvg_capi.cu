@@ -145,6 +145,45 @@ static cudaError_t dev_free(void* p, cudaStream_t s) {
     return cudaSuccess;
 }
 
+// Pinned host memory of the cursors' batches comes from a cache as well: cudaHostAlloc / cudaFreeHost pin and unpin pages
+// (~10 ms per 32 MB) and synchronise the whole device, which would stall every other cursor's stream.
+struct PinCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> idle;
+    std::map<void*, size_t> live;
+};
+static PinCache& pin_cache() { static PinCache* c = new PinCache(); return *c; }
+static cudaError_t pin_alloc(void** out, size_t bytes) {
+    size_t cls = (size_t)1 << 20;
+    while (cls < bytes) cls <<= 1;
+    PinCache& c = pin_cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.idle.find(cls);
+        if (it != c.idle.end()) { *out = it->second; c.idle.erase(it); c.live[*out] = cls; return cudaSuccess; }
+    }
+    const cudaError_t e = cudaHostAlloc(out, cls, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live[*out] = cls;
+    return cudaSuccess;
+}
+static size_t pin_capacity(void* p) {
+    PinCache& c = pin_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    return it == c.live.end() ? 0 : it->second;
+}
+static void pin_free(void* p) {
+    if (!p) return;
+    PinCache& c = pin_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return;
+    c.idle.emplace(it->second, p);
+    c.live.erase(it);
+}
+
 static int env_int(const char* name, int dflt, int lo, int hi);
 struct bvg_graph;
 extern "C" { static int fetch_offsets(const bvg_graph* g, int32_t a, int32_t b, uint64_t* va, uint64_t* vb); }
@@ -195,6 +234,7 @@ struct bvg_graph {
     int64_t n_items_resid = 0, n_items_extras = 0;
     std::vector<int64_t> n_items_merge;  // [level]
     ItemMap item_map(int family) const { return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong }; }
+    std::vector<int64_t> h_long_cum;   // the same on the host: which items belong to the long records of a node range
     int64_t long_tmp_entries = 0;
     // what a scan reads of the long records, for the roofline arithmetic of bench.py (bvg_scan_bits)
     int64_t long_arcs = 0, long_resid_bits = 0, long_pre_bits = 0, long_index_bytes = 0;
@@ -223,6 +263,14 @@ struct bvg_graph {
     int64_t stream_chunks = 0;
     uint64_t stream_bit0 = 0;
     mutable std::map<int32_t, uint64_t> offset_seen;   // host-side memo of record positions (guarded by mu)
+    // Threading (ImmutableGraph.java:157-165: an instance is not thread-safe, copy() is): the entry points that take a graph
+    // lock call_mu, so concurrent callers are serialised instead of racing on the stream and the error word; cursors carry
+    // their own stream and error word and run beside each other and beside everything else.
+    mutable std::recursive_mutex call_mu;
+    // where the records of each 2^ORDER_CHUNK_LOG-node chunk sit in the schedules (slot 0: the heavy records of all chunks), so
+    // that a range decode walks only its own chunks: e_slot[s] .. e_slot[s + 1], m_slot[level - 1][s] .. [s + 1]
+    std::vector<int64_t> e_slot;
+    std::vector<std::vector<int64_t>> m_slot;
     mutable std::mutex sched_mu;       // the length-bucketed schedules of the range-decode kernels are built on first use
     bool schedules_ready = false;
     // halo imported from the previous shard (bvg_halo_import)
@@ -354,18 +402,23 @@ static int set_codec(bvg_graph* g) {
     return BVG_OK;
 }
 
+// Where a call runs and where its kernels report: the graph's own stream and error word, or a cursor's.
+struct Exec { cudaStream_t s; ErrWord* err; };
+static inline Exec exec_of(const bvg_graph* g) { return Exec{ g->stream, g->d_err }; }
+
 // Pulls the device error word; returns its code (0 if none) and remembers node/bitpos.
-static int fetch_error(const bvg_graph* g) {
+static int fetch_error(const bvg_graph* g, Exec ex) {
     ErrWord e{};
-    if (cudaMemcpyAsync(&e, g->d_err, sizeof e, cudaMemcpyDeviceToHost, g->stream) != cudaSuccess ||
-        cudaStreamSynchronize(g->stream) != cudaSuccess) { cudaGetLastError(); return BVG_ECUDA; }
+    if (cudaMemcpyAsync(&e, ex.err, sizeof e, cudaMemcpyDeviceToHost, ex.s) != cudaSuccess ||
+        cudaStreamSynchronize(ex.s) != cudaSuccess) { cudaGetLastError(); return BVG_ECUDA; }
     if (e.code) {
         std::lock_guard<std::mutex> lk(g->mu);
         g->err_node = e.node; g->err_bitpos = e.bitpos;
-        cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord), g->stream);
+        cudaMemsetAsync(ex.err, 0, sizeof(ErrWord), ex.s);
     }
     return e.code;
 }
+static int fetch_error(const bvg_graph* g) { return fetch_error(g, exec_of(g)); }
 
 static int device_exclusive_scan(cudaStream_t s, const int32_t* d_in, int64_t n, int64_t* d_out /* n+1 */) {
     const int64_t nblocks = std::max<int64_t>(1, (n + SCAN_TILE - 1) / SCAN_TILE);
@@ -569,6 +622,7 @@ static int build_long_index(bvg_graph* g) {
     g->nlong = (int32_t)nl;  // item_map() below needs it; reset on failure by the caller's destroy
     g->h_long_nodes.resize((size_t)nl);
     for (int64_t l = 0; l < nl; l++) g->h_long_nodes[(size_t)l] = meta[(size_t)l].x;
+    g->h_long_cum = cum;
     CK(dev_alloc((void**)&g->d_long_cum, cum.size() * 8, g->stream));
     { const int r1 = small_h2d(g->d_long_cum, cum.data(), cum.size() * 8, s); if (r1) return r1; }
     { const int r2 = small_h2d(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), s); if (r2) return r2; }
@@ -685,13 +739,21 @@ static int build_schedules(bvg_graph* g) {
     CK(cudaStreamSynchronize(s));
     tr.mark("  sched: histograms");
     int64_t run = 0;
-    for (int64_t i = 0; i < nb_e; i++) { const int32_t c = h[(size_t)i]; h[(size_t)i] = (int32_t)run; run += c; }
+    g->e_slot.assign((size_t)nchunks + 1, 0);
+    for (int64_t i = 0; i < nb_e; i++) {
+        if (i % (4 * ORDER_BUCKETS) == 0) g->e_slot[(size_t)(i / (4 * ORDER_BUCKETS))] = run;
+        const int32_t c = h[(size_t)i]; h[(size_t)i] = (int32_t)run; run += c;
+    }
+    g->e_slot[(size_t)nchunks] = run;
     g->order_e_count = run;
     run = 0;
     g->level_start.assign((size_t)levels + 1, 0);
+    g->m_slot.assign((size_t)std::max(levels, 1), std::vector<int64_t>((size_t)nchunks + 1, 0));
     for (int64_t i = 0; i < nb_m; i++) {
         if (i % per_level == 0 && i / per_level <= levels) g->level_start[(size_t)(i / per_level)] = run;
+        if (i % (2 * ORDER_BUCKETS) == 0) g->m_slot[(size_t)(i / per_level)][(size_t)((i % per_level) / (2 * ORDER_BUCKETS))] = run;
         const int32_t c = h[(size_t)(nb_e + i)]; h[(size_t)(nb_e + i)] = (int32_t)run; run += c;
+        if ((i + 1) % per_level == 0) g->m_slot[(size_t)(i / per_level)][(size_t)nchunks] = run;
     }
     g->level_start[(size_t)levels] = run;
     g->order_m_count = run;
@@ -1287,6 +1349,7 @@ int bvg_random_access(const bvg_graph* g) { return g && g->offset_type > 0 ? 1 :
 
 int bvg_set_stream(bvg_graph* g, void* cuda_stream) {
     if (!g) return BVG_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(g->call_mu);
     g->stream = (cudaStream_t)cuda_stream;
     return BVG_OK;
 }
@@ -1311,6 +1374,8 @@ int bvg_memory_footprint(const bvg_graph* g, int64_t* stream_bytes, int64_t* off
 }
 
 int bvg_scan_bits(const bvg_graph* g, int64_t* out) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || !out) return BVG_EINVAL;
     DeviceGuard dg(g->device);
     uint64_t oa = 0, ob = 0;
@@ -1333,15 +1398,16 @@ static int range_check(const bvg_graph* g, int32_t from, int32_t to) {
 
 // Row offsets of two nodes on the host.  The graph is immutable, so what has been fetched once is remembered: the calls
 // of a steady-state step (range decode of the boundary lists, scan of the shard) then cost no device round trip.
-static int fetch_rowoff(const bvg_graph* g, int32_t a, int32_t b, int64_t* va, int64_t* vb) {
+static int fetch_rowoff(const bvg_graph* g, int32_t a, int32_t b, int64_t* va, int64_t* vb, cudaStream_t st = nullptr) {
     {
         std::lock_guard<std::mutex> lk(g->mu);
         auto ia = g->rowoff_seen.find(a), ib = g->rowoff_seen.find(b);
         if (ia != g->rowoff_seen.end() && ib != g->rowoff_seen.end()) { *va = ia->second; *vb = ib->second; return BVG_OK; }
     }
-    CK(cudaMemcpyAsync(va, g->d_rowoff + (a - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
-    CK(cudaMemcpyAsync(vb, g->d_rowoff + (b - g->node_lo), 8, cudaMemcpyDeviceToHost, g->stream));
-    CK(cudaStreamSynchronize(g->stream));
+    if (!st) st = g->stream;
+    CK(cudaMemcpyAsync(va, g->d_rowoff + (a - g->node_lo), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vb, g->d_rowoff + (b - g->node_lo), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     std::lock_guard<std::mutex> lk(g->mu);
     if (g->rowoff_seen.size() > 4096) g->rowoff_seen.clear();
     g->rowoff_seen[a] = *va; g->rowoff_seen[b] = *vb;
@@ -1365,6 +1431,8 @@ static int fetch_offsets(const bvg_graph* g, int32_t a, int32_t b, uint64_t* va,
 }
 
 int bvg_range_arcs(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     int rc = range_check(g, from, to);
     if (rc) return rc;
     DeviceGuard dg(g->device);
@@ -1383,9 +1451,10 @@ struct HaloPlan {
     explicit HaloPlan(cudaStream_t s) : halo(s), halo_off(s), lo(0) {}
 };
 
-static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from, RowMap& rm, HaloPlan& hp) {
-    cudaStream_t s = g->stream;
+static int plan_halo(const bvg_graph* g, Exec ex, int32_t from, int32_t to, int32_t* d_out, int64_t row_from, RowMap& rm, HaloPlan& hp) {
+    cudaStream_t s = ex.s;
     GraphDev gd = g->dev();
+    gd.err = ex.err;
     rm.out = d_out; rm.out_base = row_from; rm.from = from; rm.halo = nullptr; rm.halo_off = nullptr; rm.halo_lo = from; rm.halo_base = row_from;
     rm.mask = nullptr;
     hp.lo = from;
@@ -1393,7 +1462,7 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
         if (g->halo_count > 0 && from == g->ext_from) {  // lists imported from the previous shard
             rm.halo = g->d_halo_lists; rm.halo_off = g->d_halo_off; rm.halo_lo = from - g->halo_count;
             int64_t hb, dummy;
-            { const int rc = fetch_rowoff(g, rm.halo_lo, from, &hb, &dummy); if (rc) return rc; }
+            { const int rc = fetch_rowoff(g, rm.halo_lo, from, &hb, &dummy, s); if (rc) return rc; }
             rm.halo_base = hb;
         } else {  // re-decode the halo, as BVGraphNodeIterator's ctor re-reads the window (BVGraph.java:1173-1183)
             const int64_t reach = std::min<int64_t>((int64_t)to - from, (int64_t)g->window * g->max_depth);
@@ -1417,7 +1486,7 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
             }
             if (h < from) {
                 int64_t ra, rb;
-                int rc = fetch_rowoff(g, h, from, &ra, &rb);
+                int rc = fetch_rowoff(g, h, from, &ra, &rb, s);
                 if (rc) return rc;
                 CK(hp.halo.alloc((size_t)(rb - ra)));
                 CK(hp.halo_off.alloc((size_t)(from - h) + 1));
@@ -1430,67 +1499,100 @@ static int plan_halo(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_ou
     return BVG_OK;
 }
 
+// The work items of one family that belong to the long records of the nodes [lo, to): a contiguous run of items, because the
+// long records are listed in node order.
+struct LongSlice { LongIndex li; ItemMap im; int64_t item0, end; int64_t count() const { return end - item0; } };
+static LongSlice long_slice(const bvg_graph* g, int family, int32_t lo, int32_t to) {
+    LongSlice sl{ g->long_index(), g->item_map(family), 0, 0 };
+    if (g->nlong == 0 || g->h_long_cum.empty()) return sl;
+    const size_t l0 = (size_t)(std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), lo) - g->h_long_nodes.begin());
+    const size_t l1 = (size_t)(std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), to) - g->h_long_nodes.begin());
+    const size_t base = (size_t)family * ((size_t)g->nlong + 1);
+    sl.li.meta += l0;
+    sl.im.cum += l0; sl.im.nlong = (int32_t)(l1 - l0);
+    sl.item0 = g->h_long_cum[base + l0];
+    sl.end = g->h_long_cum[base + l1];
+    return sl;
+}
+#define LAUNCH_LONG(g, name, kernel, sl, stream, gd, lo, to, rm, ld, lf) do { \
+    if ((sl).count() > 0) LAUNCH_P(g, name, kernel, grid_for((sl).count(), 64), 64, 0, stream, gd, (sl).li, (sl).im, (sl).item0, (sl).end, lo, to, rm, ld, lf); } while (0)
+
 // Enqueues the decode of [from, to) into d_out (device, >= arcs entries). All temporaries are stream-ordered.
 // Range decode over the length-bucketed schedules: extras of every wanted node, long records split across threads, one
-// merge launch per chain level.
-static int run_ordered_decode(const bvg_graph* g, int32_t lo, int32_t to, int32_t from, const RowMap& rm) {
-    cudaStream_t s = g->stream;
+// merge launch per chain level.  Only the schedule slices of the chunks [lo, to) touches are walked (plus the slot of the
+// heavy records), so that the cost follows the range, not the graph.
+static int run_ordered_decode(const bvg_graph* g, Exec ex, int32_t lo, int32_t to, int32_t from, const RowMap& rm) {
+    cudaStream_t s = ex.s;
     GraphDev gd = g->dev();
+    gd.err = ex.err;
     // default codings: the lean walkers of the consume-only scan with every list stored (bvg_scan.cuh)
     static const bool lean = !(getenv("BVG_DECODE_LEAN") && atoi(getenv("BVG_DECODE_LEAN")) == 0);
     const bool use_lean = g->def_codec && lean && g->d_rec_e && g->d_rec_m;
     unsigned long long* const no_fold = nullptr;
-    if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1, 1);
-    else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, no_fold, 0, 1, 1);
-    else if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
-    else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(g->order_e_count, 128), 128, 0, s, gd, g->d_order_e, g->order_e_count, lo, to, rm);
+    const size_t c0 = (size_t)(((int64_t)lo - g->node_lo) >> ORDER_CHUNK_LOG) + 1, c1 = (size_t)(((int64_t)to - 1 - g->node_lo) >> ORDER_CHUNK_LOG) + 2;  // slots [c0, c1)
+    auto extras = [&](int64_t a, int64_t c) {
+        if (c <= 0) return;
+        if (use_lean && g->zetak == 3) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<3, true>), grid_for(c, 128), 128, 0, s, gd, g->d_rec_e + a, c, lo, to, from, rm, no_fold, 0, 1, 1);
+        else if (use_lean) LAUNCH_P(g, "k_extras_lean", (k_scan_extras_lean<0, true>), grid_for(c, 128), 128, 0, s, gd, g->d_rec_e + a, c, lo, to, from, rm, no_fold, 0, 1, 1);
+        else if (g->def_codec) LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_e + a, c, lo, to, rm);
+        else LAUNCH_P(g, "k_extras_ordered", k_extras_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_e + a, c, lo, to, rm);
+    };
+    extras(g->e_slot[0], g->e_slot[1] - g->e_slot[0]);            // heavy records of all chunks, filtered by [lo, to)
+    extras(g->e_slot[c0], g->e_slot[c1] - g->e_slot[c0]);
     Tmp<int32_t> long_tmp(s);
     LongDst ld{ nullptr };
-    const LongIndex li = g->long_index();
-    if (g->nlong) {
+    const LongFold lf{ nullptr, 0 };  // range decode: every long record is materialised
+    const LongSlice sr = long_slice(g, 0, lo, to), se = long_slice(g, 2, lo, to);
+    const bool any_long = g->nlong && (sr.count() > 0 || se.count() > 0 || long_slice(g, 2 + std::max(1, g->max_depth), lo, to).im.nlong > 0);
+    if (any_long) {
         CK(long_tmp.alloc((size_t)g->long_tmp_entries));
         ld.tmp = long_tmp.p;
-        const LongFold lf{ nullptr, 0 };  // range decode: every long record is materialised
-        if (g->n_items_resid) {
-            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-        }
-        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
+        if (g->def_codec) LAUNCH_LONG(g, "k_long_resid", (k_long_resid<true, RowMap>), sr, s, gd, lo, to, rm, ld, lf);
+        else LAUNCH_LONG(g, "k_long_resid", (k_long_resid<false, RowMap>), sr, s, gd, lo, to, rm, ld, lf);
+        LAUNCH_LONG(g, "k_long_extras", k_long_extras<RowMap>, se, s, gd, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
-        const int64_t a = g->level_start[(size_t)level - 1], c = g->level_start[(size_t)level] - a;
-        if (c > 0) {
+        const std::vector<int64_t>& ms = g->m_slot[(size_t)level - 1];
+        auto merge = [&](int64_t a, int64_t c) {
+            if (c <= 0) return;
             if (use_lean) LAUNCH_P(g, "k_merge_lean", (k_scan_merge_lean<8, 4>), grid_for(c, 128), 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, no_fold, 1);
             else if (g->def_codec) LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<true>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
             else LAUNCH_P(g, "k_merge_ordered", k_merge_ordered<false>, grid_for(c, 128), 128, 0, s, gd, g->d_order_m + a, c, lo, to, rm);
-        }
-        if (g->nlong) {
-            const int64_t mc = g->n_items_merge[(size_t)level];
-            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, LongFold{ nullptr, 0 });
+        };
+        merge(ms[0], ms[1] - ms[0]);
+        merge(ms[c0], ms[c1] - ms[c0]);
+        if (any_long) {
+            const LongSlice sm = long_slice(g, 2 + level, lo, to);
+            LAUNCH_LONG(g, "k_long_merge", k_long_merge<RowMap>, sm, s, gd, lo, to, rm, ld, lf);
         }
     }
     CK(cudaGetLastError());
     return BVG_OK;
 }
 
-static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t* d_out, int64_t row_from) {
+// Ranges of at least this many nodes are decoded over the schedules (built on first use), shorter ones in natural node order.
+static const int64_t ORDERED_MIN_NODES = 32768;
+
+static int enqueue_decode(const bvg_graph* g, Exec ex, int32_t from, int32_t to, int32_t* d_out, int64_t row_from) {
     if (to == from) return BVG_OK;
-    cudaStream_t s = g->stream;
+    cudaStream_t s = ex.s;
     GraphDev gd = g->dev();
+    gd.err = ex.err;
     RowMap rm;
     HaloPlan hp(s);
-    { const int rc = plan_halo(g, from, to, d_out, row_from, rm, hp); if (rc) return rc; }
+    { const int rc = plan_halo(g, ex, from, to, d_out, row_from, rm, hp); if (rc) return rc; }
     const int32_t lo = hp.lo;
     const int64_t cnt = (int64_t)to - lo;
-    // big ranges run over the length-bucketed schedules; small ones (cursor batches, halos) in natural node order
-    const bool ordered = g->max_depth <= MAX_LEVEL_KEYS && cnt * 4 >= (int64_t)g->node_hi - g->node_lo;
+    // big ranges run over the length-bucketed schedules; small ones (halos, boundary lists) in natural node order
+    const bool ordered = g->max_depth <= MAX_LEVEL_KEYS && (cnt >= ORDERED_MIN_NODES || cnt * 4 >= (int64_t)g->node_hi - g->node_lo);
     if (ordered) {
         const int rc = ensure_schedules(g);
         if (rc) return rc;
-        return run_ordered_decode(g, lo, to, from, rm);
+        return run_ordered_decode(g, ex, lo, to, from, rm);
     }
-    // Small ranges (cursor batches, boundary lists): natural node order, one thread per record -- except the long records,
-    // which are split across threads exactly as in a whole-graph decode (their items are filtered by [lo, to)).
+    // Small ranges: natural node order, one thread per record -- except the long records, which are split across threads
+    // exactly as in a whole-graph decode.
+    const LongSlice sr = long_slice(g, 0, lo, to), se = long_slice(g, 2, lo, to);
     const bool split = g->nlong > 0 &&
         std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), lo) != std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), to);
     const int32_t skip_above = split ? g->long_d : INT32_MAX;
@@ -1498,23 +1600,20 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
     else LAUNCH_P(g, "k_extras", k_extras<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, rm, skip_above);
     Tmp<int32_t> long_tmp(s);
     LongDst ld{ nullptr };
-    const LongIndex li = g->long_index();
     const LongFold lf{ nullptr, 0 };
     if (split) {
         CK(long_tmp.alloc((size_t)g->long_tmp_entries));
         ld.tmp = long_tmp.p;
-        if (g->n_items_resid) {
-            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, s, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-        }
-        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, s, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
+        if (g->def_codec) LAUNCH_LONG(g, "k_long_resid", (k_long_resid<true, RowMap>), sr, s, gd, lo, to, rm, ld, lf);
+        else LAUNCH_LONG(g, "k_long_resid", (k_long_resid<false, RowMap>), sr, s, gd, lo, to, rm, ld, lf);
+        LAUNCH_LONG(g, "k_long_extras", k_long_extras<RowMap>, se, s, gd, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
         if (g->def_codec) LAUNCH_P(g, "k_merge", k_merge<true>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm, skip_above);
         else LAUNCH_P(g, "k_merge", k_merge<false>, grid_for(cnt, 128), 128, 0, s, gd, lo, to, level, rm, skip_above);
         if (split) {
-            const int64_t mc = g->n_items_merge[(size_t)level];
-            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, s, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
+            const LongSlice sm = long_slice(g, 2 + level, lo, to);
+            LAUNCH_LONG(g, "k_long_merge", k_long_merge<RowMap>, sm, s, gd, lo, to, rm, ld, lf);
         }
     }
     CK(cudaGetLastError());
@@ -1522,6 +1621,8 @@ static int enqueue_decode(const bvg_graph* g, int32_t from, int32_t to, int32_t*
 }
 
 int bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     int rc = range_check(g, from, to);
     if (rc) return rc;
     if (!out_off) return BVG_EINVAL;
@@ -1534,7 +1635,7 @@ int bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_
     if (out && cap < arcs) return BVG_ENOMEM;
     if (on_device) {
         LAUNCH(k_rel_offsets, grid_for(cnt + 1, 256), 256, 0, s, g->d_rowoff + (from - g->node_lo), cnt, out_off);
-        if (out) { rc = enqueue_decode(g, from, to, out, ra); if (rc) return rc; }
+        if (out) { rc = enqueue_decode(g, exec_of(g), from, to, out, ra); if (rc) return rc; }
         CK(cudaGetLastError());
         return BVG_OK;
     }
@@ -1545,7 +1646,7 @@ int bvg_decode_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* out_
     CK(cudaMemcpyAsync(out_off, d_off.p, ((size_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
     if (out) {
         CK(d_out.alloc((size_t)arcs));
-        rc = enqueue_decode(g, from, to, d_out.p, ra);
+        rc = enqueue_decode(g, exec_of(g), from, to, d_out.p, ra);
         if (rc) return rc;
         if (arcs) CK(cudaMemcpyAsync(out, d_out.p, (size_t)arcs * 4, cudaMemcpyDeviceToHost, s));
     }
@@ -1564,7 +1665,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     gd.hist = hist; gd.hist_len = hist_len;
     RowMap rm;
     HaloPlan hp(s);
-    { const int rc = plan_halo(g, from, to, rows, row_from, rm, hp); if (rc) return rc; }
+    { const int rc = plan_halo(g, exec_of(g), from, to, rows, row_from, rm, hp); if (rc) return rc; }
     const int32_t lo = hp.lo;
     // One item per thread and as many blocks as that takes: the schedules are longest-first, so the hardware block
     // scheduler balances the SMs by itself (BVG_SCAN_PERSISTENT=1 keeps one resident wave looping instead).
@@ -1643,11 +1744,11 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     if (g->nlong) {
         if (g->n_items_resid && !stream_extras) {
-            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
-            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), g->n_items_resid, lo, to, rm, ld, lf);
+            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), (int64_t)0, g->n_items_resid, lo, to, rm, ld, lf);
+            else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), (int64_t)0, g->n_items_resid, lo, to, rm, ld, lf);
         }
         if (stream_extras) CK(meet());   // the residuals of the long records were written on the main stream
-        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), g->n_items_extras, lo, to, rm, ld, lf);
+        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), (int64_t)0, g->n_items_extras, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
         CK(meet());
@@ -1665,7 +1766,7 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
         }
         if (g->nlong) {
             const int64_t mc = g->n_items_merge[(size_t)level];
-            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), mc, lo, to, rm, ld, lf);
+            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), (int64_t)0, mc, lo, to, rm, ld, lf);
         }
     }
     // (stored long records are folded where their final rows are produced: k_long_resid / k_long_extras / k_long_merge)
@@ -1758,7 +1859,7 @@ static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned l
         if (rc) return rc;
         return enqueue_scan_fused(g, from, to, rows.p, ra, d_result, hist, hist_len);
     }
-    rc = enqueue_decode(g, from, to, rows.p, ra);
+    rc = enqueue_decode(g, exec_of(g), from, to, rows.p, ra);
     if (rc) return rc;
     const int64_t cnt = (int64_t)to - from;
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (cnt + 7) / 8));
@@ -1769,6 +1870,8 @@ static int enqueue_scan(const bvg_graph* g, int32_t from, int32_t to, unsigned l
 }
 
 int bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_result) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     int rc = range_check(g, from, to);
     if (rc) return rc;
     if (!d_result) return BVG_EINVAL;
@@ -1786,6 +1889,8 @@ int bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_r
 }
 
 int bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     int rc = range_check(g, from, to);
     if (rc) return rc;
     DeviceGuard dg(g->device);
@@ -1810,6 +1915,8 @@ int bvg_scan_range(const bvg_graph* g, int32_t from, int32_t to, int64_t* arcs, 
 // The counting pass of a transposition (reference Transform.java:977-987: for every arc (x, y) numPred[y]++): a scan whose
 // consumer counts instead of only folding; the successors never leave the device.
 int bvg_indegrees(const bvg_graph* g, int32_t from, int32_t to, uint32_t* counts, int64_t counts_len, int on_device, int64_t* arcs) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     int rc = range_check(g, from, to);
     if (rc) return rc;
     if (!counts || counts_len < 0) return BVG_EINVAL;
@@ -1860,6 +1967,8 @@ __global__ void k_fill_i32(int32_t* __restrict__ p, int64_t n, int32_t v) {
 // successors of a frontier decoded by random access): dist[x] = distance from source, -1 when unreachable.  Frontier,
 // successor lists and distances stay on the device; the host sees one counter per level.
 int bvg_bfs(const bvg_graph* g, int32_t source, int32_t* dist, int on_device, int32_t* levels, int64_t* reached) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || !dist) return BVG_EINVAL;
     if (source < g->ext_from || source >= g->ext_to) return BVG_EINVAL;
     if (g->offset_type <= 0) return BVG_EUNSUPPORTED;  // random access (BVGraph.java:901)
@@ -1919,6 +2028,8 @@ int bvg_bfs(const bvg_graph* g, int32_t source, int32_t* dist, int on_device, in
 // ------------------------------------------------------------------------------------------------------------
 
 int bvg_outdegree_batch(const bvg_graph* g, const int32_t* xs, int32_t from, int64_t nx, int32_t* d, int on_device) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || nx < 0 || !d) return BVG_EINVAL;
     if (g->offset_type <= 0) return BVG_ESTATE;  // BVGraph.java:869
     if (nx == 0) return BVG_OK;
@@ -1941,6 +2052,8 @@ int bvg_outdegree_batch(const bvg_graph* g, const int32_t* xs, int32_t from, int
 }
 
 int bvg_outdegree(const bvg_graph* g, int32_t x, int32_t* d) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || !d) return BVG_EINVAL;
     if (x < g->ext_from || x >= g->ext_to) return BVG_EINVAL;  // BVGraph.java:860
     if (g->offset_type <= 0) return BVG_ESTATE;                 // :869
@@ -1951,6 +2064,8 @@ int bvg_outdegree(const bvg_graph* g, int32_t x, int32_t* d) {
 }
 
 int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || nx < 0 || !out_off || (!xs && nx)) return BVG_EINVAL;
     if (g->offset_type <= 0) return BVG_EUNSUPPORTED;  // BVGraph.java:901
     DeviceGuard dg(g->device);
@@ -2016,7 +2131,7 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
         rm.mask = mask.p;
         rc = ensure_schedules(g);
         if (rc) return rc;
-        rc = run_ordered_decode(g, g->node_lo, g->node_hi, g->node_lo, rm);
+        rc = run_ordered_decode(g, exec_of(g), g->node_lo, g->node_hi, g->node_lo, rm);
         if (rc) return rc;
         LAUNCH_P(g, "k_gather_rows", k_gather_rows, 148 * 8, 256, 0, s, gd, xs_dev, nx, heavy.p, off_dev, out_dev, rm);
     }
@@ -2029,6 +2144,8 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
 }
 
 int bvg_successors(const bvg_graph* g, int32_t x, int32_t* out, int32_t cap, int32_t* d) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || !d) return BVG_EINVAL;
     if (x < g->ext_from || x >= g->ext_to) return BVG_EINVAL;  // BVGraph.java:900
     if (g->offset_type <= 0) return BVG_EUNSUPPORTED;          // :901
@@ -2064,52 +2181,69 @@ struct CursorBatch {
 };
 struct bvg_cursor {
     const bvg_graph* g;
+    cudaStream_t stream = nullptr;   // every cursor decodes on a stream of its own and reports into an error word of its own:
+    ErrWord* d_err = nullptr;        // cursors of one graph run beside each other, one per host thread
+    Exec ex() const { return Exec{ stream, d_err }; }
     int32_t next;        // next node to return
     int32_t upper;       // no node >= upper is returned (BVGraph.java:1185)
     CursorBatch b[2];
     int cur = 0;         // b[cur] is the batch being iterated; b[1 - cur] the one in flight
     bool have = false;   // b[cur] holds [lo, hi)
 };
-static const int32_t CURSOR_BATCH_NODES = 65536;
+// A batch is one schedule chunk (2^18 nodes, cut at chunk boundaries): a range decode walks the schedule slices of the chunks it
+// touches, so a chunk-aligned batch costs exactly its own records.
+static const int32_t CURSOR_BATCH_NODES = 1 << ORDER_CHUNK_LOG;
 
 static void cursor_release(bvg_cursor* c) {
     for (CursorBatch& b : c->b) {
         if (b.pending) { cudaEventSynchronize(b.ready); b.pending = false; }
-        if (b.h_off) cudaFreeHost(b.h_off);
-        if (b.h_succ) cudaFreeHost(b.h_succ);
-        dev_free(b.d_off, c->g->stream);
-        dev_free(b.d_succ, c->g->stream);
+        pin_free(b.h_off);
+        pin_free(b.h_succ);
+        dev_free(b.d_off, c->stream);
+        dev_free(b.d_succ, c->stream);
         if (b.ready) cudaEventDestroy(b.ready);
         b = CursorBatch();
     }
+    if (c->d_err) { dev_free(c->d_err, c->stream); c->d_err = nullptr; }
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->stream = nullptr; }
     cudaGetLastError();
+}
+
+static int cursor_init(bvg_cursor* c) {
+    DeviceGuard dg(c->g->device);
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(dev_alloc((void**)&c->d_err, sizeof(ErrWord), c->stream));
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(ErrWord), c->stream));
+    return BVG_OK;
 }
 
 // Enqueues decode + copy-out of the batch starting at `lo` into b; returns without waiting.
 static int cursor_enqueue(bvg_cursor* c, CursorBatch& b, int32_t lo) {
     const bvg_graph* g = c->g;
-    cudaStream_t s = g->stream;
-    int32_t hi = (int32_t)std::min<int64_t>(c->upper, (int64_t)lo + CURSOR_BATCH_NODES);
+    cudaStream_t s = c->stream;
+    // up to the next chunk boundary (counted from the first loaded node, as the schedules count them)
+    const int64_t next_chunk = ((((int64_t)lo - g->node_lo) >> ORDER_CHUNK_LOG) + 1) << ORDER_CHUNK_LOG;
+    int32_t hi = (int32_t)std::min<int64_t>(c->upper, next_chunk + g->node_lo);
     int64_t ra = 0, rb = 0;
     for (;;) {
-        int rc = fetch_rowoff(g, lo, hi, &ra, &rb);
+        int rc = fetch_rowoff(g, lo, hi, &ra, &rb, s);
         if (rc) return rc;
         if (rb - ra <= ((int64_t)1 << 26) || hi - lo <= 1) break;
         hi = lo + (hi - lo) / 2;
     }
     const int64_t arcs = rb - ra, cnt = (int64_t)hi - lo;
     if ((size_t)cnt + 1 > b.hcap_nodes) {
-        if (b.h_off) cudaFreeHost(b.h_off);
+        pin_free(b.h_off);
         b.h_off = nullptr; b.hcap_nodes = 0;
-        CK(cudaHostAlloc((void**)&b.h_off, ((size_t)CURSOR_BATCH_NODES + 1) * 8, cudaHostAllocDefault));
+        CK(pin_alloc((void**)&b.h_off, ((size_t)CURSOR_BATCH_NODES + 1) * 8));
         b.hcap_nodes = (size_t)CURSOR_BATCH_NODES + 1;
     }
     if ((size_t)arcs > b.hcap_arcs) {
-        if (b.h_succ) cudaFreeHost(b.h_succ);
+        pin_free(b.h_succ);
         b.h_succ = nullptr; b.hcap_arcs = 0;
         const size_t want = std::max<size_t>((size_t)arcs + (size_t)arcs / 4, (size_t)1 << 20);
-        CK(cudaHostAlloc((void**)&b.h_succ, want * 4, cudaHostAllocDefault));
-        b.hcap_arcs = want;
+        CK(pin_alloc((void**)&b.h_succ, want * 4));
+        b.hcap_arcs = pin_capacity(b.h_succ) / 4;
     }
     if ((size_t)cnt + 1 > b.dcap_nodes) {
         dev_free(b.d_off, s); b.d_off = nullptr; b.dcap_nodes = 0;
@@ -2124,7 +2258,7 @@ static int cursor_enqueue(bvg_cursor* c, CursorBatch& b, int32_t lo) {
     }
     if (!b.ready) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
     LAUNCH(k_rel_offsets, grid_for(cnt + 1, 256), 256, 0, s, g->d_rowoff + (lo - g->node_lo), cnt, b.d_off);
-    if (arcs) { const int rc = enqueue_decode(g, lo, hi, b.d_succ, ra); if (rc) return rc; }
+    if (arcs) { const int rc = enqueue_decode(g, c->ex(), lo, hi, b.d_succ, ra); if (rc) return rc; }
     CK(cudaMemcpyAsync(b.h_off, b.d_off, ((size_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
     if (arcs) CK(cudaMemcpyAsync(b.h_succ, b.d_succ, (size_t)arcs * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(b.ready, s));
@@ -2144,7 +2278,7 @@ static int cursor_refill(bvg_cursor* c) {
     }
     CK(cudaEventSynchronize(nb.ready));
     nb.pending = false;
-    const int e = fetch_error(g);
+    const int e = fetch_error(g, c->ex());
     if (e) return e;
     c->cur = 1 - c->cur;
     c->have = true;
@@ -2162,6 +2296,8 @@ int bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor*
     bvg_cursor* c = new (std::nothrow) bvg_cursor();
     if (!c) return BVG_ENOMEM;
     c->g = g; c->next = from; c->upper = std::min(upper, g->ext_to);
+    const int rc = cursor_init(c);
+    if (rc) { cursor_release(c); delete c; return rc; }
     *out = c;
     return BVG_OK;
 }
@@ -2182,11 +2318,34 @@ int bvg_cursor_next(bvg_cursor* c, int32_t* node, int32_t* d, const int32_t** su
     return BVG_OK;
 }
 
+// The batch that holds the cursor's next node, as it sits in pinned host memory (no copy): nodes first .. first + count - 1,
+// off[0 .. count] arc offsets relative to succ (off[0] is the first remaining node's), succ the successors.  The cursor moves
+// past the batch; the pointers stay valid until the next call on this cursor.  What a binding iterates over without a
+// per-node FFI call (a JNI direct ByteBuffer, a numpy view).
+int bvg_cursor_next_batch(bvg_cursor* c, int32_t* first, int32_t* count, const int64_t** off, const int32_t** succ) {
+    if (!c || !first || !count || !off || !succ) return BVG_EINVAL;
+    if (c->next >= c->upper) return BVG_EEND;
+    if (!c->have || c->next >= c->b[c->cur].hi || c->next < c->b[c->cur].lo) {
+        const int rc = cursor_refill(c);
+        if (rc) return rc;
+    }
+    const CursorBatch& b = c->b[c->cur];
+    const size_t i = (size_t)(c->next - b.lo);
+    *first = c->next;
+    *count = (int32_t)(std::min(b.hi, c->upper) - c->next);
+    *off = b.h_off + i;
+    *succ = b.h_succ;
+    c->next += *count;
+    return BVG_OK;
+}
+
 int bvg_cursor_copy(const bvg_cursor* c, int32_t upper, bvg_cursor** out) {  // BVGraph.java:1252-1260
     if (!c || !out) return BVG_EINVAL;
     bvg_cursor* n = new (std::nothrow) bvg_cursor();
     if (!n) return BVG_ENOMEM;
     n->g = c->g; n->next = c->next; n->upper = std::min(upper, c->g->ext_to);
+    const int rc = cursor_init(n);
+    if (rc) { cursor_release(n); delete n; return rc; }
     *out = n;
     return BVG_OK;
 }
@@ -2232,6 +2391,8 @@ int bvg_boundary_count(const bvg_graph* g, int32_t* count) {
 }
 
 int bvg_boundary_export(const bvg_graph* g, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     int32_t cnt;
     int rc = bvg_boundary_count(g, &cnt);
     if (rc) return rc;
@@ -2239,6 +2400,8 @@ int bvg_boundary_export(const bvg_graph* g, int64_t* out_off, int32_t* out, int6
 }
 
 int bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || !first_needed_node) return BVG_EINVAL;
     DeviceGuard dg(g->device);
     cudaStream_t s = g->stream;
@@ -2257,6 +2420,8 @@ int bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node) {
 }
 
 int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32_t* lists, int on_device) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || count < 0 || (count && (!off || !lists))) return BVG_EINVAL;
     if (count > g->ext_from) return BVG_EINVAL;
     DeviceGuard dg(g->device);
@@ -2339,6 +2504,12 @@ int64_t bvg_release_cached_memory(int device) {
         } else ++it;
     }
     if (prev >= 0) cudaSetDevice(prev);
+    {
+        PinCache& pc = pin_cache();
+        std::lock_guard<std::mutex> lk2(pc.mu);
+        for (auto& kv : pc.idle) { cudaFreeHost(kv.second); freed += (int64_t)kv.first; }
+        pc.idle.clear();
+    }
     cudaGetLastError();
     return freed;
 }

@@ -407,8 +407,8 @@ struct LongFold {
 
 #ifndef BVG_HOST_EMULATION
 template <bool DEF, class RM>
-__global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t item0, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
+    const int64_t i = item0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // items [item0, nitems): the long records of [lo, hi)
     unsigned long long acc = 0;
     long long arcs = 0;
     if (i < nitems) {
@@ -475,8 +475,8 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t nitem
 }
 
 template <class RM>
-__global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t item0, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
+    const int64_t i = item0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc = 0;
     long long arcs = 0;
     if (i < nitems) {
@@ -515,8 +515,8 @@ __global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t nite
 }
 
 template <class RM>
-__global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t item0, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
+    const int64_t i = item0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc = 0;
     long long arcs = 0;
     if (i < nitems) {
