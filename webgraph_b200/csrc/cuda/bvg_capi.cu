@@ -278,6 +278,8 @@ struct bvg_graph {
     int64_t* d_halo_off = nullptr;
     int32_t halo_count = 0;
     int64_t halo_off_cap = 0, halo_lists_cap = 0;
+    mutable int32_t halo_first = 0;   // bvg_halo_needed, remembered
+    mutable bool halo_first_known = false;
     int32_t halo_import_count = -1;   // shape of the last import (bvg_halo_import)
     int64_t halo_import_total = -1;
     // per-kernel timing (bench.py's roofline object): spans recorded while prof_on
@@ -997,6 +999,14 @@ static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to) {
 
 static int open_common(bvg_graph* g, const Properties& p, int offset_type) {
     if (offset_type < -1 || offset_type > 2) return BVG_EINVAL;  // BVGraph.java:1545
+    // the memory entry points get their parameters from the caller, not from a .properties file: the same checks
+    // load_properties makes (a negative window would make the shard halo run backwards, zeta_0 shifts by -1)
+    if (p.nodes < 0 || p.arcs < 0 || p.window < 0 || p.minlen < 0) return BVG_EINVAL;
+    {
+        const int resid = ((p.flags >> 8) & 0xF) ? (int)((p.flags >> 8) & 0xF) : C_ZETA;
+        if (resid == C_ZETA && p.zetak < 1) return BVG_EINVAL;
+        if (resid == C_GOLOMB && p.zetak < 0) return BVG_EINVAL;
+    }
     keep_pool_warm(g->device);
     g->long_d = env_int("BVG_LONG_D", LONG_D, 2, 1 << 30);
     g->long_seg = env_int("BVG_LONG_SEG", LONG_SEG, 1, 1 << 20);
@@ -2403,6 +2413,7 @@ int bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node) {
     std::unique_lock<std::recursive_mutex> call_lock;
     if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || !first_needed_node) return BVG_EINVAL;
+    if (g->halo_first_known) { *first_needed_node = g->halo_first; return BVG_OK; }  // the graph is immutable: asked once
     DeviceGuard dg(g->device);
     cudaStream_t s = g->stream;
     int32_t h = g->ext_from;
@@ -2416,6 +2427,7 @@ int bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node) {
         CK(cudaStreamSynchronize(s));
     }
     *first_needed_node = h;
+    g->halo_first = h; g->halo_first_known = true;
     return BVG_OK;
 }
 
@@ -2423,16 +2435,26 @@ int bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32
     std::unique_lock<std::recursive_mutex> call_lock;
     if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
     if (!g || count < 0 || (count && (!off || !lists))) return BVG_EINVAL;
-    if (count > g->ext_from) return BVG_EINVAL;
+    // the imported lists are those of the nodes [ext_from - count, ext_from): they must lie inside the loaded window (row
+    // offsets of the halo are taken from this shard's own index) ...
+    if (count > g->ext_from - g->node_lo) return BVG_EINVAL;
     DeviceGuard dg(g->device);
     cudaStream_t s = g->stream;
     g->halo_count = 0;
     if (count == 0) return BVG_OK;
+    {   // ... and reach back at least as far as this shard's chains do: a shorter import would leave a parent without a row
+        int32_t first = g->ext_from;
+        const int rc = bvg_halo_needed(g, &first);
+        if (rc) return rc;
+        if (first < g->ext_from - count) return BVG_EINVAL;
+    }
     int64_t total = 0;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (on_device && g->halo_import_count == count && g->halo_import_total >= 0 && count + 1 <= g->halo_off_cap) {
         // same shape as the previous import (a shard re-imports its neighbour's boundary every step): copy by a kernel that
         // reads the arc count on the device and checks it against the capacity, no round trip to the host
+        // (an import larger than the buffers is caught on the device: k_halo_copy reports E_NOMEM and copies nothing, the next
+        // call that fetches the error word fails; the offsets of the previous import stay in place, so no read goes out of bounds)
         LAUNCH(k_halo_copy, 64, 256, 0, s, off, lists, count, g->d_halo_off, g->d_halo_lists, g->halo_lists_cap, g->d_err);
         CK(cudaGetLastError());
         g->halo_count = count;
