@@ -1746,6 +1746,9 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             }
         }
     }
+    // the fused in-degree count (bvg_indegrees) is a compile-time variant of the lean kernels (default codings, enqueue_scan sees to that)
+    else if (hist && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, 0, 0, items);
+    else if (hist) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, 0, 0, items);
     else if (g->def_codec && lean && g->zetak == 3 && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && g->zetak == 3) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<3, false>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
     else if (g->def_codec && lean && ring) LAUNCH_P(g, "k_scan_extras", (k_scan_extras_lean<0, true>), grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result, dbg_nostore, 0, items);
@@ -1754,11 +1757,13 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
     else LAUNCH_P(g, "k_scan_extras", k_scan_extras<false>, grid, 128, 0, s, gd, g->d_rec_e, g->order_e_count, lo, to, from, rm, d_result);
     if (g->nlong) {
         if (g->n_items_resid && !stream_extras) {
-            if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), (int64_t)0, g->n_items_resid, lo, to, rm, ld, lf);
+            if (hist) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap, true>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), (int64_t)0, g->n_items_resid, lo, to, rm, ld, lf);
+            else if (g->def_codec) LAUNCH_P(g, "k_long_resid", (k_long_resid<true, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), (int64_t)0, g->n_items_resid, lo, to, rm, ld, lf);
             else LAUNCH_P(g, "k_long_resid", (k_long_resid<false, RowMap>), grid_for(g->n_items_resid, 64), 64, 0, sa, gd, li, g->item_map(0), (int64_t)0, g->n_items_resid, lo, to, rm, ld, lf);
         }
         if (stream_extras) CK(meet());   // the residuals of the long records were written on the main stream
-        if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), (int64_t)0, g->n_items_extras, lo, to, rm, ld, lf);
+        if (g->n_items_extras && hist) LAUNCH_P(g, "k_long_extras", (k_long_extras<RowMap, true>), grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), (int64_t)0, g->n_items_extras, lo, to, rm, ld, lf);
+        else if (g->n_items_extras) LAUNCH_P(g, "k_long_extras", k_long_extras<RowMap>, grid_for(g->n_items_extras, 64), 64, 0, sa, gd, li, g->item_map(2), (int64_t)0, g->n_items_extras, lo, to, rm, ld, lf);
     }
     for (int32_t level = 1; level <= g->max_depth; level++) {
         CK(meet());
@@ -1770,13 +1775,15 @@ static int enqueue_scan_fused(const bvg_graph* g, int32_t from, int32_t to, int3
             // 5/16 (blocks / batch): 1.92, 2.12, 2.19, 2.52 ms for the three levels -- occupancy beats deeper batching here
             // (10 / 12 resident blocks, 48 / 40 registers: 1.89 -> 2.16 / 2.50 ms, spills)
             // (measured and dropped in round 2: parent rows read in aligned 16-byte groups, 1.89 -> 3.57 ms)
-            if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            if (hist) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4, true>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
+            else if (g->def_codec && lean_m) LAUNCH_P(g, "k_scan_merge", (k_scan_merge_lean<8, 4>), gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result, 0);
             else if (g->def_codec) LAUNCH_P(g, "k_scan_merge", k_scan_merge<true>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
             else LAUNCH_P(g, "k_scan_merge", k_scan_merge<false>, gm, 128, 0, s, gd, g->d_rec_m + a, c, lo, to, from, rm, d_result);
         }
         if (g->nlong) {
             const int64_t mc = g->n_items_merge[(size_t)level];
-            if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), (int64_t)0, mc, lo, to, rm, ld, lf);
+            if (mc > 0 && hist) LAUNCH_P(g, "k_long_merge", (k_long_merge<RowMap, true>), grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), (int64_t)0, mc, lo, to, rm, ld, lf);
+            else if (mc > 0) LAUNCH_P(g, "k_long_merge", k_long_merge<RowMap>, grid_for(mc, 64), 64, 0, sa, gd, li, g->item_map(2 + level), (int64_t)0, mc, lo, to, rm, ld, lf);
         }
     }
     // (stored long records are folded where their final rows are produced: k_long_resid / k_long_extras / k_long_merge)

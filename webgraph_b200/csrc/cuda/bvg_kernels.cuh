@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras(
 // Every kind runs the same tight residual loop, preceded for records with intervals by a walk of the interval section
 // that folds its elements; stored records with intervals write their residuals right-aligned and merge the intervals in
 // front of them in a second walk (ScanExtras::iv_merge).
-template <int K, bool RING>
+template <int K, bool RING, bool HIST = false>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_lean(GraphDev g, const ExtraRec* __restrict__ recs, int64_t count,
                               int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int debug_nostore, int store_all, int items) {
     __shared__ uint4 ring[RING ? RING_GROUPS * SCAN_BLOCK : 1];
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_extras_
         const bool has_iv = (r.flags & 2u) != 0;
         int32_t* row = store ? rm.at(r.x, r.row) : nullptr;
         unsigned long long f = 0;
-        ScanExtras<K, W> w;
+        ScanExtras<K, W, HIST> w;
         w.begin(g, r.x, r.nout, r.pos, active, my_ring, fold);
         if (has_iv) w.iv_fold(g); else w.iv_none(g);
         __syncwarp();
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_BLOCKS_PER_SM) k_scan_merge(G
 }
 
 // Merge step with the staged copy runs of bvg_scan.cuh (default codings).
-template <int MINB, int BATCH>
+template <int MINB, int BATCH, bool HIST = false>
 __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g, const MergeRec* __restrict__ recs, int64_t count,
                              int32_t lo, int32_t hi, int32_t from, RowMap rm, unsigned long long* __restrict__ result, int store_all) {
     __shared__ int32_t runs[2 * COPY_RUNS * SCAN_BLOCK];
@@ -663,9 +663,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, MINB) k_scan_merge_lean(GraphDev g
         __syncwarp();
         const int32_t* parent = active ? rm.at(r.px, r.prow) : nullptr;
         unsigned long long f = 0;
-        if (active && !store) f = copied_fold<BATCH>(g, c, r.x, parent);
+        if (active && !store) f = copied_fold<BATCH, CopyRuns, HIST>(g, c, r.x, parent);
         __syncwarp();
-        if (store) f = copied_merge(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent, fold);
+        if (store) f = copied_merge<CopyRuns, HIST>(g, c, r.x, r.d, r.copied, rm.at(r.x, r.row), parent, fold);
         __syncwarp();
         if (fold) acc ^= f;
     }

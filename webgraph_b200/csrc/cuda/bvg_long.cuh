@@ -317,9 +317,9 @@ __device__ __forceinline__ int32_t merge_path(const A& a, const int32_t* __restr
 }
 
 // Outputs [q0, q0 + cnt) of merge(A, B) into out, A being a virtual block-structured sequence walked by (slot, offset).
-template <class A, class ValueOf>
+template <class A, class ValueOf, class F = Fold32>
 __device__ void merge_chunk(const A& a, ValueOf value_of, const int32_t* __restrict__ bv, int32_t blen,
-                            int32_t q0, int32_t cnt, int32_t* __restrict__ out, Fold32* fold = nullptr) {
+                            int32_t q0, int32_t cnt, int32_t* __restrict__ out, F* fold = nullptr) {
     int32_t i = merge_path(a, bv, blen, q0), j = q0 - i;
     int32_t t = 0, t_end = 0;  // current slot of A and the index where it ends
     if (i < a.len) { t = upper_slot(a.cum, a.n, i); t_end = a.cum[t + 1]; }
@@ -406,7 +406,7 @@ struct LongFold {
 };
 
 #ifndef BVG_HOST_EMULATION
-template <bool DEF, class RM>
+template <bool DEF, class RM, bool HIST = false>
 __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t item0, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
     const int64_t i = item0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // items [item0, nitems): the long records of [lo, hi)
     unsigned long long acc = 0;
@@ -424,7 +424,7 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t item0
                 else if (m.x >= lf.from) {
                     const int32_t first = part * li.seg;
                     const int32_t cnt = min(li.seg, m.rc - first);
-                    Fold32 f;
+                    FoldT<HIST> f;
                     f.begin(m.x, g, true);
                     BitBuf b;
                     b.w = g.words; b.maxw = g.nwords - 3;
@@ -444,7 +444,7 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t item0
                 const int32_t cnt = min(li.seg, m.rc - first);
                 // stored records with neither intervals nor a copied part get their final row here: fold it now
                 const bool final_here = (consume || (lf.result != nullptr && m.ic == 0 && m.copied == 0)) && m.x >= lf.from;
-                Fold32 f;
+                FoldT<HIST> f;
                 f.begin(m.x, g, final_here);
                 const int k = g.c.zetak;
                 Win b;
@@ -474,7 +474,7 @@ __global__ void k_long_resid(GraphDev g, LongIndex li, ItemMap im, int64_t item0
     if (lf.result) warp_fold(acc, arcs, lf.result);
 }
 
-template <class RM>
+template <class RM, bool HIST = false>
 __global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t item0, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
     const int64_t i = item0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc = 0;
@@ -491,14 +491,14 @@ __global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t item
                 const int32_t* left = a.left;
                 const int32_t cnt = min(li.chunk, total - q0);
                 const bool final_row = lf.result != nullptr && m.copied == 0 && m.x >= lf.from;  // no copied part follows
-                Fold32 f;
+                FoldT<HIST> f;
                 f.begin(m.x, g, true);
                 merge_chunk(a, [left](int32_t t, int32_t o) { return left[t] + o; }, dst.tmp + m.tmp_off, m.rc, q0,
                             cnt, dst.extras(m, rm.row(g, m.x)), final_row ? &f : nullptr);
                 if (final_row) { f.n = (uint32_t)cnt; acc = f.finish(m.x); arcs = cnt; }
             } else if (m.x >= lf.from && q0 < m.ilen) {  // interval elements [q0, q0 + chunk) of the concatenated intervals
                 const int32_t cnt = min(li.chunk, m.ilen - q0);
-                Fold32 f;
+                FoldT<HIST> f;
                 f.begin(m.x, g, true);
                 int32_t t = upper_slot(a.cum, a.n, q0), t_end = a.cum[t + 1];
                 for (int32_t q = q0; q < q0 + cnt; q++) {
@@ -514,7 +514,7 @@ __global__ void k_long_extras(GraphDev g, LongIndex li, ItemMap im, int64_t item
     if (lf.result) warp_fold(acc, arcs, lf.result);
 }
 
-template <class RM>
+template <class RM, bool HIST = false>
 __global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t item0, int64_t nitems, int32_t lo, int32_t hi, RM rm, LongDst dst, LongFold lf) {
     const int64_t i = item0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc = 0;
@@ -531,14 +531,14 @@ __global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t item0
             if (!lf.only_consumed(m)) {
                 const int32_t cnt = min(li.chunk, m.d - q0);
                 const bool final_row = lf.result != nullptr && m.x >= lf.from;
-                Fold32 f;
+                FoldT<HIST> f;
                 f.begin(m.x, g, true);
                 merge_chunk(a, [ppos, parent](int32_t t, int32_t o) { return parent[ppos[t] + o]; }, dst.tmp + m.tmp_off + m.d,
                             m.d - m.copied, q0, cnt, rm.row(g, m.x), final_row ? &f : nullptr);
                 if (final_row) { f.n = (uint32_t)cnt; acc = f.finish(m.x); arcs = cnt; }
             } else if (m.x >= lf.from && q0 < m.copied) {  // copied elements [q0, q0 + chunk) seen through the copy blocks
                 const int32_t cnt = min(li.chunk, m.copied - q0);
-                Fold32 f;
+                FoldT<HIST> f;
                 f.begin(m.x, g, true);
                 int32_t t = upper_slot(a.cum, a.n, q0), t_end = a.cum[t + 1];
                 for (int32_t q = q0; q < q0 + cnt; q++) {

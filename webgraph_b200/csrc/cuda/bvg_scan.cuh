@@ -327,22 +327,25 @@ __device__ __forceinline__ uint64_t zeta_any(W& b, const GraphDev& g, int k) {  
 }
 
 // 32-bit halves of the checksum of one record: XOR of lo(base + y), number of carries out of the low word.
-struct Fold32 {
+// HIST: the fused in-degree count of bvg_indegrees (GraphDev.hist) -- a compile-time variant, so that the plain scan's loops
+// carry neither the pointer nor the test (a run-time test cost the residual loop 20 %: 2.72 -> 3.26 ms)
+template <bool HIST>
+struct FoldT {
     uint32_t base_lo, xlo, carries, n;
-    uint32_t* hist;      // fused in-degree count (GraphDev.hist), nullptr in a plain scan
+    uint32_t* hist;
     uint32_t hist_len;
-    __device__ __forceinline__ void begin(int32_t x) { base_lo = (uint32_t)((unsigned long long)(uint32_t)x * BVG_MIX); xlo = 0; carries = 0; n = 0; hist = nullptr; hist_len = 0; }
+    __device__ __forceinline__ void begin(int32_t x) { base_lo = (uint32_t)((unsigned long long)(uint32_t)x * BVG_MIX); xlo = 0; carries = 0; n = 0; if (HIST) { hist = nullptr; hist_len = 0; } }
     // counted: the successors added here are consumed by the scan (not a halo record, not a fold that a later step repeats on
     // the final list): only then do they count in the fused histogram
     __device__ __forceinline__ void begin(int32_t x, const GraphDev& g, bool counted) {
         begin(x);
-        if (counted) { hist = g.hist; hist_len = (uint32_t)(g.hist_len > 0xffffffffll ? 0xffffffffll : g.hist_len); }
+        if (HIST && counted) { hist = g.hist; hist_len = (uint32_t)(g.hist_len > 0xffffffffll ? 0xffffffffll : g.hist_len); }
     }
     __device__ __forceinline__ void add(uint32_t y) {
         const uint32_t lo = base_lo + y;
         carries += lo < y ? 1u : 0u;
         xlo ^= lo;
-        if (hist != nullptr && y < hist_len) atomicAdd(hist + y, 1u);
+        if (HIST) { if (hist != nullptr && y < hist_len) atomicAdd(hist + y, 1u); }
     }
     // XOR over the n folded successors of (x*MIX + y): hi word is base_hi for the ones without a carry, base_hi + 1 with
     __device__ __forceinline__ unsigned long long finish(int32_t x) const {
@@ -353,6 +356,8 @@ struct Fold32 {
         return ((unsigned long long)hi << 32) | xlo;
     }
 };
+typedef FoldT<false> Fold32;
+
 
 // Sequential writer of one lane's row with 16-byte write combining.  The 32 lanes of a warp write 32 unrelated rows, so
 // a 4-byte store per successor is 32 separate sector writes per instruction at the L2; measured on the benchmark graph
@@ -405,10 +410,10 @@ struct RowWriter {
 //                   ExtrasWalk::with_intervals instead (kept in separate warps by the schedule)
 //   phase resid()   residuals, tight loop
 // ---------------------------------------------------------------------------------------------------
-template <int K, class W = Win>
+template <int K, class W = Win, bool HIST = false>
 struct ScanExtras {
     W b;
-    Fold32 f;
+    FoldT<HIST> f;
     int32_t x, nout, rc;
     uint32_t v;
     int err;
@@ -588,9 +593,9 @@ struct CopyRunsT {
 typedef CopyRunsT<COPY_RUNS> CopyRuns;
 
 // nobody copies from x: its copied successors are only consumed
-template <int BATCH, class CR>
+template <int BATCH, class CR, bool HIST = false>
 __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CR& c, int32_t x, const int32_t* __restrict__ parent) {
-    Fold32 f;
+    FoldT<HIST> f;
     f.begin(x, g, true);
     // BATCH positions first, then their loads together: a lane opens a new sector of its parent's row every eighth element,
     // the 32 lanes read 32 unrelated rows, and with one load per trip the warp waits a memory round trip on every trip
@@ -614,10 +619,10 @@ __device__ __forceinline__ unsigned long long copied_fold(const GraphDev& g, CR&
 // (MergedIntIterator.java:50-74: ascending union, equal heads once; a list that loses duplicates is padded with -1 as
 // BVGraphNodeIterator does when it drains, BVGraph.java:1210).  Folds the copied successors only: the extras were
 // folded when they were decoded.
-template <class CR>
+template <class CR, bool HIST = false>
 __device__ __forceinline__ unsigned long long copied_merge(const GraphDev& g, CR& c, int32_t x, int32_t d, int32_t copied,
                                                            int32_t* row, const int32_t* __restrict__ parent, bool counted = true) {
-    Fold32 f;
+    FoldT<HIST> f;
     f.begin(x, g, counted);
     int32_t j = copied, k = 0;
     RowWriter<false> wr;  // measured: combining helps the extras kernel (3.92 -> 3.71 ms) and costs registers here (2.22 -> 2.49 ms)
