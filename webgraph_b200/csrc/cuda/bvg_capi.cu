@@ -234,7 +234,9 @@ struct bvg_graph {
     int64_t n_items_resid = 0, n_items_extras = 0;
     std::vector<int64_t> n_items_merge;  // [level]
     ItemMap item_map(int family) const { return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong }; }
-    std::vector<int64_t> h_long_cum;   // the same on the host: which items belong to the long records of a node range
+    mutable std::vector<int64_t> h_long_cum;   // the same on the host (fetched on first use): which items belong to the long records of a node range
+    size_t long_cum_entries = 0;
+    std::vector<int64_t> fam_total;    // items of every family
     int64_t long_tmp_entries = 0;
     // what a scan reads of the long records, for the roofline arithmetic of bench.py (bvg_scan_bits)
     int64_t long_arcs = 0, long_resid_bits = 0, long_pre_bits = 0, long_index_bytes = 0;
@@ -577,6 +579,7 @@ static int build_long_index(bvg_graph* g) {
     if (nn == 0 || g->max_outdeg <= g->long_d || g->max_depth > 64) return BVG_OK;
     const int32_t LSEG = g->long_seg, LCHUNK = g->long_chunk;
     GraphDev gd = g->dev();
+    Trace tr(s);
     Tmp<int32_t> flags(s);
     struct { int32_t* p; } long_nodes{ nullptr };
     Tmp<int64_t> pos(s);
@@ -595,39 +598,46 @@ static int build_long_index(bvg_graph* g) {
     CK(dev_alloc((void**)&g->d_long_meta, (size_t)nl * sizeof(LongMeta), g->stream));
     if (g->def_codec) LAUNCH(k_long_count<true>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_is_parent, g->d_long_meta);
     else LAUNCH(k_long_count<false>, grid_for(nl, 64), 64, 0, s, gd, long_nodes.p, (int32_t)nl, g->d_is_parent, g->d_long_meta);
-    std::vector<LongMeta> meta((size_t)nl);
-    CK(cudaMemcpyAsync(meta.data(), g->d_long_meta, (size_t)nl * sizeof(LongMeta), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    // Array offsets and running item counts: one pass over the long records (not over their items).
+    tr.mark("    long: list + count walk");
+    // Array offsets and running item counts, laid out on the device (k_long_layout_*): one scan per running sum.
     const size_t stride = (size_t)nl + 1;
     const int32_t levels = g->max_depth;
-    const int fam_spec = 3 + levels;  // families: 0 residual segments, 1 row chunks, 2 extras chunks, 3.. merge chunks per level, then sub-ranges
-    std::vector<int64_t> cum((size_t)(fam_spec + 1) * stride, 0);
-    int64_t cb = 0, iv = 0, seg = 0, tmp = 0, scan = 0;
-    for (int64_t l = 0; l < nl; l++) {
-        LongMeta& m = meta[(size_t)l];
-        m.scan_off = scan; if (m.flags & 1) scan += 3 * (int64_t)m.d;
-        m.cb_off = cb; cb += (int64_t)m.ncb + 1;
-        m.iv_off = iv; iv += (int64_t)m.ic + 1;
-        m.seg_off = seg;
-        const int64_t nseg = ((int64_t)m.rc + LSEG - 1) / LSEG;
-        seg += nseg;
-        m.tmp_off = tmp; tmp += 2 * (int64_t)m.d;
-        int64_t add[3] = { nseg, 0 /* unused family */, m.ic > 0 ? ((int64_t)m.ilen + m.rc + LCHUNK - 1) / LCHUNK : 0 };
-        for (int f = 0; f < 3; f++) cum[(size_t)f * stride + (size_t)l + 1] = cum[(size_t)f * stride + (size_t)l] + add[f];
-        for (int32_t lv = 1; lv <= levels; lv++)
-            cum[(size_t)(2 + lv) * stride + (size_t)l + 1] = cum[(size_t)(2 + lv) * stride + (size_t)l] +
-                ((m.copied > 0 && m.level == lv) ? ((int64_t)m.d + LCHUNK - 1) / LCHUNK : 0);
-        cum[(size_t)fam_spec * stride + (size_t)l + 1] = cum[(size_t)fam_spec * stride + (size_t)l] +
-            (m.rc > 0 ? (int64_t)((m.rec_end - m.resid_pos + (uint64_t)LSPEC_BITS - 1) / (uint64_t)LSPEC_BITS) : 0);
-    }
+    const int fam_spec = 3 + levels;  // families: 0 residual segments, 1 unused, 2 extras chunks, 3.. merge chunks per level, then sub-ranges
     g->nlong = (int32_t)nl;  // item_map() below needs it; reset on failure by the caller's destroy
+    const int nvals = 7 + levels;
+    Tmp<int32_t> vals(s);
+    Tmp<int64_t> offs(s), totals(s);   // scans that are not item families: 0 copy blocks, 1 intervals, 2 outdegree, 3 stored outdegree
+    Tmp<unsigned long long> stats(s);
+    CK(vals.alloc((size_t)nvals * (size_t)nl));
+    CK(offs.alloc(4 * stride));
+    CK(totals.alloc(8));
+    CK(stats.alloc(3));
+    CK(cudaMemsetAsync(stats.p, 0, 24, s));
+    CK(dev_alloc((void**)&g->d_long_cum, (size_t)(fam_spec + 1) * stride * 8, g->stream));
+    CK(cudaMemsetAsync(g->d_long_cum + stride, 0, stride * 8, s));   // family 1 is empty
+    LAUNCH(k_long_layout_vals, grid_for(nl, 128), 128, 0, s, g->d_long_meta, (int32_t)nl, levels, LSEG, LCHUNK, (int64_t)LSPEC_BITS, vals.p);
+    auto scan_row = [&](int row, int64_t* out) { return device_exclusive_scan(s, vals.p + (size_t)row * (size_t)nl, nl, out); };
+    if ((rc = scan_row(0, offs.p)) || (rc = scan_row(1, offs.p + stride)) || (rc = scan_row(3, offs.p + 2 * stride)) || (rc = scan_row(4, offs.p + 3 * stride)) ||
+        (rc = scan_row(2, g->d_long_cum)) || (rc = scan_row(5, g->d_long_cum + 2 * stride)) || (rc = scan_row(6, g->d_long_cum + (size_t)fam_spec * stride))) return rc;
+    for (int32_t lv = 1; lv <= levels; lv++) if ((rc = scan_row(6 + lv, g->d_long_cum + (size_t)(2 + lv) * stride))) return rc;
+    LAUNCH(k_long_layout_apply, grid_for(nl, 128), 128, 0, s, g->d_long_meta, (int32_t)nl, offs.p, offs.p + stride, g->d_long_cum, offs.p + 2 * stride, offs.p + 3 * stride);
+    LAUNCH(k_long_stats, 64, 256, 0, s, g->d_long_meta, (int32_t)nl, stats.p);
+    // totals: last entries of the scans, and the item counts of every family; the host copies of the node list and of the item
+    // counts (which items belong to a node range: long_slice) come back in the same round trip
+    // (the item counts per record stay on the device until a range decode asks which items belong to a node range: long_slice)
+    std::vector<int64_t> h_tot(4), fam_total((size_t)fam_spec + 1, 0);
     g->h_long_nodes.resize((size_t)nl);
-    for (int64_t l = 0; l < nl; l++) g->h_long_nodes[(size_t)l] = meta[(size_t)l].x;
-    g->h_long_cum = cum;
-    CK(dev_alloc((void**)&g->d_long_cum, cum.size() * 8, g->stream));
-    { const int r1 = small_h2d(g->d_long_cum, cum.data(), cum.size() * 8, s); if (r1) return r1; }
-    { const int r2 = small_h2d(g->d_long_meta, meta.data(), (size_t)nl * sizeof(LongMeta), s); if (r2) return r2; }
+    g->h_long_cum.clear();
+    g->long_cum_entries = (size_t)(fam_spec + 1) * stride;
+    unsigned long long h_stats[3] = { 0, 0, 0 };
+    for (int t = 0; t < 4; t++) CK(cudaMemcpyAsync(&h_tot[(size_t)t], offs.p + (size_t)t * stride + nl, 8, cudaMemcpyDeviceToHost, s));
+    for (int f = 0; f <= fam_spec; f++) CK(cudaMemcpyAsync(&fam_total[(size_t)f], g->d_long_cum + (size_t)f * stride + nl, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(g->h_long_nodes.data(), g->d_long_nodes, (size_t)nl * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_stats, stats.p, 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    g->fam_total = fam_total;
+    const int64_t cb = h_tot[0], iv = h_tot[1], seg = fam_total[0], tmp = 2 * h_tot[2], scan = 3 * h_tot[3];
     CK(dev_alloc((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
     CK(dev_alloc((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
     CK(dev_alloc((void**)&g->d_iv_cum, (size_t)std::max<int64_t>(iv, 1) * 4, g->stream));
@@ -637,7 +647,8 @@ static int build_long_index(bvg_graph* g) {
     // copy blocks and intervals: one short walk per record; residual sync points: speculative sub-ranges (bvg_long.cuh)
     if (g->def_codec) LAUNCH(k_long_fill<true>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
     else LAUNCH(k_long_fill<false>, grid_for(nl, 64), 64, 0, s, gd, (int32_t)nl, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos, g->d_iv_cum, g->d_iv_left, (uint64_t*)nullptr, (int64_t*)nullptr);
-    const int64_t ni = cum[(size_t)fam_spec * stride + (size_t)nl];
+    const int64_t ni = fam_total[(size_t)fam_spec];
+    tr.mark("    long: layout + fill walk");
     if (ni > 0) {
         const ItemMap im = g->item_map(fam_spec);
         Tmp<SpecItem> ia(s), ib(s);
@@ -657,6 +668,7 @@ static int build_long_index(bvg_graph* g) {
             LAUNCH(k_lspec_first<false>, grid_for(nl, 128), 128, 0, s, gd, g->d_long_meta, (int32_t)nl, v0.p);
             LAUNCH(k_lspec_speculate<false>, grid_for(ni, 128), 128, 0, s, gd, ia.p, ni);
         }
+        tr.mark("    long: speculate");
         SpecItem *in = ia.p, *out = ib.p;
         for (int64_t pass = 0;; pass++) {
             CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
@@ -669,6 +681,7 @@ static int build_long_index(bvg_graph* g) {
             if (!ch) break;
             if (pass > ni + 2) return BVG_EIO;
         }
+        tr.mark("    long: fix passes");
         LAUNCH(k_lspec_scan, grid_for(nl, 64), 64, 0, s, gd, g->d_long_meta, im, in, cbase.p, sbase.p);
         if (g->def_codec) LAUNCH(k_lspec_emit<true>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
         else LAUNCH(k_lspec_emit<false>, grid_for(ni, 128), 128, 0, s, gd, in, ni, g->d_long_meta, cbase.p, sbase.p, v0.p, g->d_seg_pos, g->d_seg_val, LSEG);
@@ -676,21 +689,16 @@ static int build_long_index(bvg_graph* g) {
         CK(cudaStreamSynchronize(s));
         const int e = fetch_error(g);  // a record that does not hold rc residuals (k_lspec_scan)
         if (e) return e;
+        tr.mark("    long: scan + emit");
     }
-    g->n_items_resid = cum[0 * stride + (size_t)nl];
-    g->n_items_extras = cum[2 * stride + (size_t)nl];
+    g->n_items_resid = fam_total[0];
+    g->n_items_extras = fam_total[2];
     g->n_items_merge.assign((size_t)levels + 1, 0);
-    for (int32_t lv = 1; lv <= levels; lv++) g->n_items_merge[(size_t)lv] = cum[(size_t)(2 + lv) * stride + (size_t)nl];
+    for (int32_t lv = 1; lv <= levels; lv++) g->n_items_merge[(size_t)lv] = fam_total[(size_t)(2 + lv)];
     g->long_tmp_entries = tmp;
     g->long_scan_entries = scan;
-    g->long_arcs = 0; g->long_resid_bits = 0; g->long_pre_bits = 0;
-    for (int64_t l = 0; l < nl; l++) {
-        const LongMeta& m = meta[(size_t)l];
-        g->long_arcs += m.d;
-        g->long_resid_bits += (int64_t)(m.rec_end - m.resid_pos);
-        g->long_pre_bits += (int64_t)(m.resid_pos - m.after_header);
-    }
-    g->long_index_bytes = nl * (int64_t)sizeof(LongMeta) + 8 * (cb + iv) + 16 * seg + (int64_t)cum.size() * 8 + nl * 4;
+    g->long_resid_bits = (int64_t)h_stats[0]; g->long_pre_bits = (int64_t)h_stats[1]; g->long_arcs = (int64_t)h_stats[2];
+    g->long_index_bytes = nl * (int64_t)sizeof(LongMeta) + 8 * (cb + iv) + 16 * seg + (int64_t)g->long_cum_entries * 8 + nl * 4;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // cum / meta are host vectors
     return BVG_OK;
@@ -1514,7 +1522,18 @@ static int plan_halo(const bvg_graph* g, Exec ex, int32_t from, int32_t to, int3
 struct LongSlice { LongIndex li; ItemMap im; int64_t item0, end; int64_t count() const { return end - item0; } };
 static LongSlice long_slice(const bvg_graph* g, int family, int32_t lo, int32_t to) {
     LongSlice sl{ g->long_index(), g->item_map(family), 0, 0 };
-    if (g->nlong == 0 || g->h_long_cum.empty()) return sl;
+    if (g->nlong == 0) return sl;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        if (g->h_long_cum.empty() && g->long_cum_entries) {
+            g->h_long_cum.assign(g->long_cum_entries, 0);
+            if (cudaMemcpy(g->h_long_cum.data(), g->d_long_cum, g->long_cum_entries * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); g->h_long_cum.clear(); }
+        }
+    }
+    if (g->h_long_cum.empty()) {   // could not fetch: every item of the family, filtered by the kernels
+        sl.end = (size_t)family < g->fam_total.size() ? g->fam_total[(size_t)family] : 0;
+        return sl;
+    }
     const size_t l0 = (size_t)(std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), lo) - g->h_long_nodes.begin());
     const size_t l1 = (size_t)(std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), to) - g->h_long_nodes.begin());
     const size_t base = (size_t)family * ((size_t)g->nlong + 1);

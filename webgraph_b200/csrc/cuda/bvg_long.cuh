@@ -554,6 +554,50 @@ __global__ void k_long_merge(GraphDev g, LongIndex li, ItemMap im, int64_t item0
     if (lf.result) warp_fold(acc, arcs, lf.result);
 }
 
+// Layout of the long index on the device (round 2; the host pass it replaces copied every LongMeta both ways and cost 6 ms per
+// open of a 125 M-arc shard).  k_long_layout_vals writes, per long record, what it adds to each running sum (rows of `vals`,
+// nl entries each): 0 copy blocks + 1, 1 intervals + 1, 2 residual segments, 3 outdegree (per-scan temp: 2 d), 4 outdegree when
+// somebody copies from the record (tile scratch: 3 d), 5 extras chunks, 6 speculative sub-ranges, 7 .. 6 + levels merge chunks
+// of each chain level, and three statistics for bvg_scan_bits: 7 + levels residual bits, 8 + levels block / interval bits.
+// Exclusive scans of the rows give the offsets; k_long_layout_apply stores them into the metas.
+__global__ void k_long_layout_vals(const LongMeta* __restrict__ meta, int32_t nl, int32_t levels, int32_t seg, int32_t chunk, int64_t lspec_bits,
+                                   int32_t* __restrict__ vals) {
+    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nl) return;
+    const LongMeta m = meta[l];
+    const size_t n = (size_t)nl;
+    vals[0 * n + l] = m.ncb + 1;
+    vals[1 * n + l] = m.ic + 1;
+    vals[2 * n + l] = (m.rc + seg - 1) / seg;
+    vals[3 * n + l] = m.d;
+    vals[4 * n + l] = (m.flags & 1) ? m.d : 0;
+    vals[5 * n + l] = m.ic > 0 ? (int32_t)(((int64_t)m.ilen + m.rc + chunk - 1) / chunk) : 0;
+    vals[6 * n + l] = m.rc > 0 ? (int32_t)((m.rec_end - m.resid_pos + (uint64_t)lspec_bits - 1) / (uint64_t)lspec_bits) : 0;
+    for (int32_t lv = 1; lv <= levels; lv++)
+        vals[(size_t)(6 + lv) * n + l] = (m.copied > 0 && m.level == lv) ? (int32_t)(((int64_t)m.d + chunk - 1) / chunk) : 0;
+}
+__global__ void k_long_layout_apply(LongMeta* __restrict__ meta, int32_t nl, const int64_t* __restrict__ cb, const int64_t* __restrict__ iv,
+                                    const int64_t* __restrict__ sg, const int64_t* __restrict__ dsum, const int64_t* __restrict__ dstored) {
+    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nl) return;
+    meta[l].cb_off = cb[l]; meta[l].iv_off = iv[l]; meta[l].seg_off = sg[l];
+    meta[l].tmp_off = 2 * dsum[l]; meta[l].scan_off = 3 * dstored[l];
+}
+// what a scan reads of the long records (bvg_scan_bits): residual bits, block + interval bits, arcs
+__global__ void k_long_stats(const LongMeta* __restrict__ meta, int32_t nl, unsigned long long* __restrict__ out) {
+    unsigned long long r = 0, p = 0, a = 0;
+    for (int32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < nl; l += gridDim.x * blockDim.x) {
+        r += meta[l].rec_end - meta[l].resid_pos; p += meta[l].resid_pos - meta[l].after_header; a += (unsigned long long)meta[l].d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); p += __shfl_xor_sync(0xffffffffu, p, o); a += __shfl_xor_sync(0xffffffffu, a, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, r); atomicAdd(out + 1, p); atomicAdd(out + 2, a); }
+}
+__global__ void k_gather_i64(const int64_t* const* __restrict__ ptrs, int32_t n, int64_t* __restrict__ out) {
+    const int32_t i = threadIdx.x;
+    if (i < n) out[i] = *ptrs[i];
+}
+
 // Speculative sub-ranges of the residual sections (see above), listed on the device: item j of record l covers
 // LSPEC_BITS bits from resid_pos + part * LSPEC_BITS.
 __global__ void k_lspec_init(const LongMeta* __restrict__ meta, ItemMap im, int64_t nitems, SpecItem* __restrict__ items) {
