@@ -165,6 +165,45 @@ int  bvg_boundary_export(const bvg_graph* g, int64_t* out_off, int32_t* out, int
 int  bvg_halo_needed(const bvg_graph* g, int32_t* first_needed_node);
 int  bvg_halo_import(bvg_graph* g, int32_t count, const int64_t* off, const int32_t* lists, int on_device);
 
+/* ---- arc labels: BitStreamArcLabelledImmutableGraph ----
+ * A labelled graph is <basename>.properties (graphclass, labelspec, underlyinggraph), <basename>.labels (the labels of
+ * node 0's arcs in successor order, then node 1's, ... written by Label.toBitStream with no separators) and
+ * <basename>.labeloffsets (gamma-coded gaps) over an underlying BVGraph (reference labelling/
+ * BitStreamArcLabelledImmutableGraph.java:139-145, 385-470).  The three Label classes the reference ships are decoded on
+ * the device: GammaCodedIntLabel (readGamma, GammaCodedIntLabel.java:52-56), FixedWidthIntLabel (readInt(width),
+ * FixedWidthIntLabel.java:69-73), FixedWidthIntListLabel (readGamma length, then length x readInt(width),
+ * FixedWidthIntListLabel.java:72-78).  Anything else in labelspec is BVG_EUNSUPPORTED.
+ * A bvg_labels is opened ON a bvg_graph (the underlying graph, or a shard of it: only the shard's stretch of the label
+ * stream is loaded), uses its device, stream and call lock, and must be closed before it. */
+typedef struct bvg_labels bvg_labels;
+enum { BVG_LABEL_GAMMA = 0, BVG_LABEL_FIXED = 1, BVG_LABEL_FIXED_LIST = 2 };
+
+/* Resolves the underlyinggraph property of <basename>.properties against the labelled graph's directory
+ * (BitStreamArcLabelledImmutableGraph.java:391-395) into buf.  BVG_EIO when the file or the key is missing. */
+int  bvg_labels_underlying(const char* basename, char* buf, int cap);
+/* load(): parses labelspec, decodes .labeloffsets on the device, uploads the label stream.  BVG_EIO: a file or the
+ * labelspec key is missing (IOException, :409), or the offsets run past the stream; BVG_EFORMAT: unparsable labelspec;
+ * BVG_EINVAL: width outside 0..31 (IllegalArgumentException, FixedWidthIntLabel.java:41). */
+int  bvg_labels_open(const bvg_graph* g, const char* basename, bvg_labels** out);
+/* The same from caller-owned buffers (the whole .labels and .labeloffsets files) with the label class given. */
+int  bvg_labels_open_memory(const bvg_graph* g, const uint8_t* labels, uint64_t label_bytes, const uint8_t* label_offsets,
+                            uint64_t offsets_bytes, int kind, int width, bvg_labels** out);
+void bvg_labels_close(bvg_labels* l);
+/* kind, width, length of the whole label stream in bits, bytes of HBM held (any pointer may be NULL). */
+int  bvg_labels_info(const bvg_labels* l, int* kind, int* width, int64_t* label_bits, int64_t* loaded_bytes);
+/* The labels of all arcs of nodes [from, to), in the order bvg_decode_range returns the successors: the label of the k-th
+ * successor of x is entry (row offset of x) + k, what nodeIterator().labelArray() / successors(x).label() give
+ * (BitStreamArcLabelledImmutableGraph.java:225-262).  Integer labels: values[arc]; list_off (may be NULL) gets 0..arcs.
+ * List labels: arc j carries values[list_off[j] .. list_off[j+1]).  list_off has arcs + 1 entries, values `cap` entries
+ * (BVG_ENOMEM when that is too few; call with both NULL to get the sizes); nvalues (may be NULL) receives the number of
+ * values.  on_device != 0: the pointers are device pointers on the graph's device, filled in stream order on the graph's
+ * stream.  BVG_EFORMAT when the stretch between two label offsets does not hold one label per arc. */
+int  bvg_labels_decode_range(const bvg_labels* l, int32_t from, int32_t to, int64_t* list_off, int32_t* values, int64_t cap,
+                             int on_device, int64_t* nvalues);
+/* Consume-only pass over the labels of [from, to): sum over arcs j = 0, 1, ... of the range of
+ * (2j + 1) * (0x9E3779B97F4A7C15 * len_j + sum_i (v_ji + 1) * (2i + 1)) mod 2^64 (len = 1 for integer labels). */
+int  bvg_labels_scan_range(const bvg_labels* l, int32_t from, int32_t to, int64_t* arcs, int64_t* nvalues, uint64_t* checksum);
+
 /* ---- diagnostics ---- */
 const char* bvg_strerror(int status);
 /* Node and bit position of the first record a kernel rejected (BVGraph.java:1129-1131 logs the same pair). */

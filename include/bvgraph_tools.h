@@ -77,6 +77,23 @@ int bvgt_generate_store(const char* basename, const bvgt_gen_params* p,
                         int threads, int64_t* out_off, int32_t* out_succ, int64_t succ_cap,
                         bvgt_store_stats* stats);
 
+/* Arc labels: the three Label classes of the reference that a BitStreamArcLabelledImmutableGraph can carry.
+ * GAMMA = GammaCodedIntLabel (toBitStream = writeGamma(value), GammaCodedIntLabel.java:58-61), FIXED = FixedWidthIntLabel
+ * (writeInt(value, width), FixedWidthIntLabel.java:75-78), FIXED_LIST = FixedWidthIntListLabel (writeGamma(length) then
+ * length x writeInt(element, width), FixedWidthIntListLabel.java:80-85). */
+enum { BVGT_LABEL_GAMMA = 0, BVGT_LABEL_FIXED = 1, BVGT_LABEL_FIXED_LIST = 2 };
+
+/* Writes <basename>.labels (the labels of node 0's arcs in successor order, then node 1's, ... with no separators),
+ * <basename>.labeloffsets (gamma(0), then for every node the gamma-coded number of bits its labels took) and
+ * <basename>.properties (graphclass, labelspec = <class>(<key>[,<width>]), underlyinggraph = `underlying`), the layout
+ * BitStreamArcLabelledImmutableGraph.load reads (BitStreamArcLabelledImmutableGraph.java:385-470; written the way
+ * BitStreamArcLabelledGraphTest.java:131-203 writes its fixtures).  off[n+1] = CSR row offsets of the underlying graph.
+ * GAMMA / FIXED: values[off[n]] holds one label per arc, list_off is ignored.  FIXED_LIST: arc j carries
+ * values[list_off[j] .. list_off[j+1]).  Values must be >= 0 and, for the fixed-width kinds, < 2^width (0 <= width <= 31).
+ * label_bits (may be NULL) receives the length of the label stream.  Returns 0, -1 (bad argument / value), -4 (I/O). */
+int bvgt_store_labels(const char* basename, const char* underlying, const char* key, int32_t n, const int64_t* off,
+                      const int64_t* list_off, const int32_t* values, int kind, int width, int threads, int64_t* label_bits);
+
 #ifdef __cplusplus
 }
 #endif

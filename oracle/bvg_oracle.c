@@ -687,3 +687,113 @@ int32_t orc_chain_root(const orc_graph* g, int32_t x) {
         x -= (int32_t)ref;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Arc labels: labelling/BitStreamArcLabelledImmutableGraph.java.  PARITY UNPINNED: the reference
+ * ships no .labels fixture (its test writes them with dsiutils' OutputBitStream at run time,
+ * test/.../labelling/BitStreamArcLabelledGraphTest.java:131-203) and no JVM exists in this image;
+ * the restatement is anchored on that test's layout and on the three fromBitStream methods.
+ * ---------------------------------------------------------------------------------------- */
+
+/* labelspec = <class>(<key>[,<width>]) (ObjectParser.fromSpec call, :409-425). */
+static int parse_labelspec(const char* spec, int* kind, int* width) {
+    char cls[256];
+    const char* par = strchr(spec, '(');
+    size_t cl = par ? (size_t)(par - spec) : strlen(spec);
+    while (cl && isspace((unsigned char)spec[cl - 1])) cl--;
+    size_t start = cl;
+    while (start && spec[start - 1] != '.') start--;
+    if (cl - start >= sizeof cls) return BVGO_EFORMAT;
+    memcpy(cls, spec + start, cl - start);
+    cls[cl - start] = 0;
+    *width = 0;
+    if (!strcmp(cls, "GammaCodedIntLabel")) { *kind = ORC_LABEL_GAMMA; return par ? BVGO_OK : BVGO_EFORMAT; }
+    if (!strcmp(cls, "FixedWidthIntLabel")) *kind = ORC_LABEL_FIXED;
+    else if (!strcmp(cls, "FixedWidthIntListLabel")) *kind = ORC_LABEL_FIXED_LIST;
+    else return BVGO_EUNSUPPORTED;
+    const char* comma = par ? strchr(par, ',') : NULL;
+    if (!comma) return BVGO_EFORMAT;
+    char* end = NULL;
+    const long w = strtol(comma + 1, &end, 10);
+    if (end == comma + 1) return BVGO_EFORMAT;
+    if (w < 0 || w > 31) return BVGO_EINVAL; /* FixedWidthIntLabel.java:41, FixedWidthIntListLabel.java:44 */
+    *width = (int)w;
+    return BVGO_OK;
+}
+
+void orc_labels_free(orc_labels* l) {
+    if (!l) return;
+    free(l->labels);
+    free(l->offsets);
+    free(l);
+}
+
+/* load(), :385-470, for a graph of n nodes: labelspec -> prototype, .labels bytes, .labeloffsets = n+1 gamma gaps summed
+ * (LabelOffsetsLongIterator, :330-358). */
+int orc_labels_load(const char* basename, int32_t n, orc_labels** out) {
+    char path[4096], val[1024];
+    uint64_t psz = 0;
+    snprintf(path, sizeof path, "%s.properties", basename);
+    char* props = (char*)slurp(path, &psz, 1);
+    if (!props) return BVGO_EIO;
+    orc_labels* l = (orc_labels*)calloc(1, sizeof *l);
+    int rc = BVGO_OK;
+    if (!prop_get(props, "labelspec", val, sizeof val)) { rc = BVGO_EIO; goto fail; } /* :409 */
+    rc = parse_labelspec(val, &l->kind, &l->width);
+    if (rc) goto fail;
+    l->n = n;
+    snprintf(path, sizeof path, "%s.labels", basename);
+    l->labels = slurp(path, &l->label_bytes, 16);
+    if (!l->labels) { rc = BVGO_EIO; goto fail; }
+    {
+        uint64_t osz = 0;
+        snprintf(path, sizeof path, "%s.labeloffsets", basename);
+        uint8_t* ob = slurp(path, &osz, 16);
+        if (!ob) { rc = BVGO_EIO; goto fail; }
+        l->offsets = (uint64_t*)malloc(((size_t)n + 1) * sizeof(uint64_t));
+        ibs_t s = { ob, osz * 8, 0 };
+        uint64_t off = 0;
+        for (int64_t i = 0; i <= n; i++) {
+            off += ibs_read_gamma(&s);
+            l->offsets[i] = off;
+            if (s.pos > s.nbits) { free(ob); rc = BVGO_EIO; goto fail; }
+        }
+        free(ob);
+        if (l->offsets[n] > l->label_bytes * 8) { rc = BVGO_EIO; goto fail; }
+    }
+    free(props);
+    *out = l;
+    return BVGO_OK;
+fail:
+    free(props);
+    orc_labels_free(l);
+    return rc;
+}
+
+/* BitStreamLabelledArcIterator (:225-262): position(offset(x)), then one fromBitStream per successor of x
+ * (GammaCodedIntLabel.java:52-56 readGamma; FixedWidthIntLabel.java:69-73 readInt(width);
+ * FixedWidthIntListLabel.java:72-78 readGamma then length x readInt(width)).  d = outdegree of x in the
+ * underlying graph.  list_off (d+1 entries, may be NULL) = where each arc's values start; returns the
+ * number of values (== d for the integer labels) or an error; values may be NULL (count only). */
+int64_t orc_labels_node(const orc_labels* l, int32_t x, int32_t d, int64_t* list_off, int32_t* values, int64_t cap) {
+    if (x < 0 || x >= l->n || d < 0) return BVGO_EINVAL;
+    ibs_t s = { l->labels, l->label_bytes * 8, l->offsets[x] };
+    int64_t nv = 0;
+    for (int32_t k = 0; k < d; k++) {
+        if (list_off) list_off[k] = nv;
+        uint64_t len = 1;
+        if (l->kind == ORC_LABEL_FIXED_LIST) len = ibs_read_gamma(&s);
+        if (len > 0x7fffffffULL || s.pos > s.nbits) return BVGO_EIO;
+        for (uint64_t i = 0; i < len; i++) {
+            const uint64_t v = l->kind == ORC_LABEL_GAMMA ? ibs_read_gamma(&s) : ibs_read_bits(&s, l->width);
+            if (s.pos > s.nbits) return BVGO_EIO;
+            if (values) {
+                if (nv >= cap) return BVGO_ENOMEM;
+                values[nv] = (int32_t)v;
+            }
+            nv++;
+        }
+    }
+    if (list_off) list_off[d] = nv;
+    return nv;
+}

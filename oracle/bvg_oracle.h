@@ -102,6 +102,20 @@ int32_t orc_chain_root(const orc_graph* g, int32_t x);
 /* Raw code readers, exported for known-answer tests of the dsiutils restatement. */
 uint64_t orc_read_code(const uint8_t* buf, uint64_t nbytes, uint64_t* bitpos, int coding, int k);
 
+/* ---- arc labels (labelling/BitStreamArcLabelledImmutableGraph.java) -- PARITY UNPINNED: no .labels fixture exists in the
+ * reference tree; see bvg_oracle.c. ---- */
+enum { ORC_LABEL_GAMMA = 0, ORC_LABEL_FIXED = 1, ORC_LABEL_FIXED_LIST = 2 };
+typedef struct orc_labels {
+    int kind, width;
+    int32_t n;
+    uint8_t* labels;        /* .labels bytes + 16 bytes of padding */
+    uint64_t label_bytes;
+    uint64_t* offsets;      /* n+1 bit offsets */
+} orc_labels;
+int  orc_labels_load(const char* basename, int32_t n, orc_labels** out);
+void orc_labels_free(orc_labels* l);
+int64_t orc_labels_node(const orc_labels* l, int32_t x, int32_t d, int64_t* list_off, int32_t* values, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

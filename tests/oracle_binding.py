@@ -20,6 +20,11 @@ class OrcGraph(C.Structure):
                 ("offsets", C.POINTER(C.c_uint64))]
 
 
+class OrcLabels(C.Structure):
+    _fields_ = [("kind", C.c_int), ("width", C.c_int), ("n", C.c_int32), ("labels", C.POINTER(C.c_uint8)),
+                ("label_bytes", C.c_uint64), ("offsets", C.POINTER(C.c_uint64))]
+
+
 def build():
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("bvg_oracle.c", "bvg_oracle_mt.c", "bvg_oracle.h", "Makefile")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
@@ -56,6 +61,18 @@ class Oracle:
         lib.orc_chain_root.restype = C.c_int32
         lib.orc_read_code.argtypes = [C.c_void_p, C.c_uint64, P(C.c_uint64), C.c_int, C.c_int]
         lib.orc_read_code.restype = C.c_uint64
+        lib.orc_labels_load.argtypes = [C.c_char_p, C.c_int32, P(P(OrcLabels))]
+        lib.orc_labels_free.argtypes = [P(OrcLabels)]
+        lib.orc_labels_free.restype = None
+        lib.orc_labels_node.argtypes = [P(OrcLabels), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+        lib.orc_labels_node.restype = C.c_int64
+
+    def load_labels(self, basename, n):
+        l = C.POINTER(OrcLabels)()
+        rc = self.lib.orc_labels_load(basename.encode(), n, C.byref(l))
+        if rc:
+            raise OracleError(rc)
+        return OracleLabels(self, l)
 
     def load(self, basename, offsets=True):
         g = C.POINTER(OrcGraph)()
@@ -155,6 +172,60 @@ class OracleGraph:
 
 
 _ORACLE = None
+
+
+class OracleLabels:
+    """orc_labels: the label stream read the way BitStreamLabelledArcIterator reads it (one node at a time)."""
+
+    def __init__(self, orc, l):
+        self.orc, self.l = orc, l
+        c = l.contents
+        self.kind, self.width, self.n = c.kind, c.width, c.n
+
+    def close(self):
+        if self.l:
+            self.orc.lib.orc_labels_free(self.l)
+            self.l = None
+
+    def offsets(self):
+        return np.ctypeslib.as_array(self.l.contents.offsets, shape=(self.n + 1,)).copy()
+
+    def node(self, x, d):
+        """(list_off int64[d + 1], values int32[...]) of node x, whose outdegree is d."""
+        lo = np.zeros(d + 1, dtype=np.int64)
+        nv = self.orc.lib.orc_labels_node(self.l, x, d, lo.ctypes.data, None, 0)
+        if nv < 0:
+            raise OracleError(nv)
+        vals = np.empty(max(nv, 1), dtype=np.int32)
+        nv2 = self.orc.lib.orc_labels_node(self.l, x, d, lo.ctypes.data, vals.ctypes.data, nv)
+        if nv2 < 0:
+            raise OracleError(nv2)
+        return lo, vals[:nv]
+
+    def range(self, frm, to, row_off):
+        """Labels of the arcs of frm..to-1 (row_off: CSR offsets of the underlying graph), as (list_off, values)."""
+        los, vals, base = [np.zeros(1, dtype=np.int64)], [], 0
+        for x in range(frm, to):
+            lo, v = self.node(x, int(row_off[x + 1] - row_off[x]))
+            los.append(lo[1:] + base)
+            vals.append(v)
+            base += len(v)
+        return np.concatenate(los), (np.concatenate(vals) if vals else np.empty(0, dtype=np.int32))
+
+def label_checksum(list_off, values):
+    """The fold of bvg_labels_scan_range restated with numpy (tests; include/bvgraph_b200.h)."""
+    M = np.uint64(0x9E3779B97F4A7C15)
+    lo = np.asarray(list_off, dtype=np.int64)
+    v = np.asarray(values, dtype=np.int64).astype(np.uint64)
+    arcs = len(lo) - 1
+    with np.errstate(over="ignore"):
+        arc_of = np.repeat(np.arange(arcs, dtype=np.int64), np.diff(lo))
+        i = (np.arange(len(v), dtype=np.int64) - lo[arc_of]).astype(np.uint64)
+        t = np.zeros(arcs, dtype=np.uint64)
+        np.add.at(t, arc_of, (v + np.uint64(1)) * (np.uint64(2) * i + np.uint64(1)))
+        t += M * np.diff(lo).astype(np.uint64)
+        j = np.arange(arcs, dtype=np.uint64)
+        return int(((np.uint64(2) * j + np.uint64(1)) * t).sum(dtype=np.uint64))
 
 
 def load():

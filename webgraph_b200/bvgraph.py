@@ -56,6 +56,8 @@ SYMBOLS = [
     "bvg_halo_import", "bvg_strerror", "bvg_last_error_node", "bvg_kernel_launches", "bvg_memory_footprint",
     "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_release_cached_memory", "bvg_profile", "bvg_profile_read",
     "bvg_scan_bits", "bvg_replan_shards", "bvg_indegrees", "bvg_bfs", "bvg_cursor_next_batch",
+    "bvg_labels_underlying", "bvg_labels_open", "bvg_labels_open_memory", "bvg_labels_close", "bvg_labels_info",
+    "bvg_labels_decode_range", "bvg_labels_scan_range",
 ]
 
 
@@ -112,6 +114,14 @@ def lib():
     L.bvg_scan_bits.argtypes = [vp, P(i64)]
     L.bvg_indegrees.argtypes = [vp, i32, i32, vp, i64, C.c_int, P(i64)]
     L.bvg_bfs.argtypes = [vp, i32, vp, C.c_int, P(i32), P(i64)]
+    L.bvg_labels_underlying.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.bvg_labels_open.argtypes = [vp, C.c_char_p, P(vp)]
+    L.bvg_labels_open_memory.argtypes = [vp, vp, u64, vp, u64, C.c_int, C.c_int, P(vp)]
+    L.bvg_labels_close.argtypes = [vp]
+    L.bvg_labels_close.restype = None
+    L.bvg_labels_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(i64), P(i64)]
+    L.bvg_labels_decode_range.argtypes = [vp, i32, i32, vp, vp, i64, C.c_int, P(i64)]
+    L.bvg_labels_scan_range.argtypes = [vp, i32, i32, P(i64), P(i64), P(u64)]
     _lib = L
     return L
 

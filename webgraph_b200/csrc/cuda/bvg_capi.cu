@@ -8,6 +8,7 @@
 #include "bvg_kernels.cuh"
 #include "bvg_long.cuh"
 #include "bvg_offsets.cuh"
+#include "bvg_labels.cuh"
 #include "bvg_boundaries.cuh"
 #include "bvg_tile.cuh"
 #include "bvg_stream.cuh"
@@ -2598,3 +2599,5 @@ int bvg_profile_read(const bvg_graph* g, char* buf, int cap) {
 }
 
 }  // extern "C"
+
+#include "bvg_labels_capi.cuh"

@@ -603,4 +603,64 @@ int bvgt_generate_store(const char* basename, const bvgt_gen_params* gp,
     return rc;
 }
 
+int bvgt_store_labels(const char* basename, const char* underlying, const char* key, int32_t n, const int64_t* off,
+                      const int64_t* list_off, const int32_t* values, int kind, int width, int threads, int64_t* label_bits) {
+    if (!basename || !underlying || !key || n < 0 || !off) return -1;
+    if (kind < BVGT_LABEL_GAMMA || kind > BVGT_LABEL_FIXED_LIST) return -1;
+    if (kind != BVGT_LABEL_GAMMA && (width < 0 || width > 31)) return -1;
+    if (kind == BVGT_LABEL_FIXED_LIST && !list_off) return -1;
+    if (off[n] > 0 && !values && !(kind == BVGT_LABEL_FIXED_LIST && list_off[off[n]] == 0)) return -1;
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n > 0 ? n : 1;
+    struct Part { BitBuf labels, offs; bool bad = false; };
+    std::vector<Part> parts((size_t)threads);
+    const int64_t step = ((int64_t)n + threads - 1) / threads;
+    const uint64_t lim = kind == BVGT_LABEL_GAMMA ? 0x7fffffffULL : 1ULL << width;
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) th.emplace_back([&, t] {
+        Part& p = parts[(size_t)t];
+        const int64_t a = t * step, b = std::min<int64_t>(n, a + step);
+        for (int64_t x = a; x < b && !p.bad; x++) {
+            const uint64_t before = p.labels.nbits;
+            for (int64_t j = off[x]; j < off[x + 1]; j++) {
+                if (kind == BVGT_LABEL_FIXED_LIST) {
+                    const int64_t la = list_off[j], lb = list_off[j + 1];
+                    if (lb < la || lb - la > 0x7ffffffe) { p.bad = true; break; }
+                    put_gamma(p.labels, (uint64_t)(lb - la));
+                    for (int64_t k = la; k < lb; k++) {
+                        if (values[k] < 0 || (uint64_t)values[k] >= lim) { p.bad = true; break; }
+                        p.labels.put((uint64_t)values[k], width);
+                    }
+                } else {
+                    if (values[j] < 0 || (uint64_t)values[j] >= lim) { p.bad = true; break; }
+                    if (kind == BVGT_LABEL_GAMMA) put_gamma(p.labels, (uint64_t)values[j]);
+                    else p.labels.put((uint64_t)values[j], width);
+                }
+            }
+            put_gamma(p.offs, p.labels.nbits - before);
+        }
+    });
+    for (auto& t : th) t.join();
+    BitBuf labels, offs;
+    put_gamma(offs, 0);
+    for (Part& p : parts) {
+        if (p.bad) return -1;
+        if (parts.size() == 1) labels = std::move(p.labels); else { labels.append(p.labels); p.labels = BitBuf(); }
+        offs.append(p.offs);
+    }
+    const std::string base(basename);
+    if (!labels.write_file(base + ".labels")) return -4;
+    if (!offs.write_file(base + ".labeloffsets")) return -4;
+    FILE* f = fopen((base + ".properties").c_str(), "w");
+    if (!f) return -4;
+    static const char* cls[] = { "GammaCodedIntLabel", "FixedWidthIntLabel", "FixedWidthIntListLabel" };
+    fprintf(f, "graphclass = it.unimi.dsi.webgraph.labelling.BitStreamArcLabelledImmutableGraph\n");
+    if (kind == BVGT_LABEL_GAMMA) fprintf(f, "labelspec = it.unimi.dsi.webgraph.labelling.%s(%s)\n", cls[kind], key);
+    else fprintf(f, "labelspec = it.unimi.dsi.webgraph.labelling.%s(%s,%d)\n", cls[kind], key, width);
+    fprintf(f, "underlyinggraph = %s\n", underlying);
+    fclose(f);
+    if (label_bits) *label_bits = (int64_t)labels.nbits;
+    return 0;
+}
+
 }  // extern "C"

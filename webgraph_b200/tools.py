@@ -55,6 +55,8 @@ def lib():
                                              C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(StoreStats)]
         _lib.bvgt_write_codes.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         _lib.bvgt_write_codes.restype = C.c_int64
+        _lib.bvgt_store_labels.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     return _lib
 
 
@@ -111,3 +113,22 @@ def generate_store(basename, n, target_arcs, seed=0x5EED, window=7, maxref=3, mi
     if return_csr:
         return st.as_dict(), off, succ[:off[-1]].copy()
     return st.as_dict()
+
+
+LABEL_GAMMA, LABEL_FIXED, LABEL_FIXED_LIST = 0, 1, 2
+
+
+def store_labels(basename, underlying, off, values, kind, width=0, list_off=None, key="TEST", threads=1):
+    """Writes <basename>.labels / .labeloffsets / .properties for the graph whose CSR row offsets are `off`
+    (BitStreamArcLabelledGraphTest.java:131-203).  `values`: one int per arc (LABEL_GAMMA, LABEL_FIXED) or the
+    concatenated lists addressed by `list_off` (LABEL_FIXED_LIST).  Returns the length of the label stream in bits."""
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    values = np.ascontiguousarray(values, dtype=np.int32)
+    lo = None if list_off is None else np.ascontiguousarray(list_off, dtype=np.int64)
+    bits = C.c_int64(0)
+    rc = lib().bvgt_store_labels(os.fsencode(basename), os.fsencode(underlying), key.encode(), len(off) - 1, off.ctypes.data,
+                                 None if lo is None else lo.ctypes.data, values.ctypes.data if len(values) else None,
+                                 kind, width, threads, C.byref(bits))
+    if rc:
+        raise ValueError("bvgt_store_labels failed: %d" % rc)
+    return int(bits.value)
