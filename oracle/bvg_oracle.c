@@ -797,3 +797,22 @@ int64_t orc_labels_node(const orc_labels* l, int32_t x, int32_t d, int64_t* list
     if (list_off) list_off[d] = nv;
     return nv;
 }
+
+/* Sequential pass over the labels of nodes [from, to) (what ArcLabelledNodeIterator does: the label stream read front
+ * to back, one fromBitStream per arc), integer labels only; row_off = CSR row offsets of the underlying graph.
+ * values may be NULL (consume only); returns the number of labels or an error; *sum gets the sum of the values. */
+int64_t orc_labels_range(const orc_labels* l, int32_t from, int32_t to, const int64_t* row_off, int32_t* values, int64_t cap, uint64_t* sum) {
+    if (from < 0 || to < from || to > l->n || l->kind == ORC_LABEL_FIXED_LIST) return BVGO_EINVAL;
+    ibs_t s = { l->labels, l->label_bytes * 8, l->offsets[from] };
+    const int64_t arcs = row_off[to] - row_off[from];
+    if (values && cap < arcs) return BVGO_ENOMEM;
+    uint64_t acc = 0;
+    for (int64_t j = 0; j < arcs; j++) {
+        const uint64_t v = l->kind == ORC_LABEL_GAMMA ? ibs_read_gamma(&s) : ibs_read_bits(&s, l->width);
+        if (values) values[j] = (int32_t)v;
+        acc += v;
+    }
+    if (s.pos > s.nbits) return BVGO_EIO;
+    if (sum) *sum = acc;
+    return arcs;
+}

@@ -115,6 +115,7 @@ typedef struct orc_labels {
 int  orc_labels_load(const char* basename, int32_t n, orc_labels** out);
 void orc_labels_free(orc_labels* l);
 int64_t orc_labels_node(const orc_labels* l, int32_t x, int32_t d, int64_t* list_off, int32_t* values, int64_t cap);
+int64_t orc_labels_range(const orc_labels* l, int32_t from, int32_t to, const int64_t* row_off, int32_t* values, int64_t cap, uint64_t* sum);
 
 #ifdef __cplusplus
 }

@@ -52,23 +52,24 @@ def main():
             res[what + "_ms"] = ms
             res[what + "_G_labels_per_s"] = arcs / ms / 1e6
             res[what + "_stream_GBps"] = bits / 8 / ms / 1e6
+        alg.g.profile(True)
+        bvgraph._check(L.bvg_labels_decode_range(alg._h, 0, n, None, d_vals.data_ptr(), arcs, 1, None))
+        alg.scanLabels(0, n)
+        torch.cuda.synchronize()
+        res["kernels_ms_decode_plus_scan"] = alg.g.profileRead()
+        alg.g.profile(False)
         assert np.array_equal(d_vals.cpu().numpy(), values)
         lo = np.arange(arcs + 1, dtype=np.int64)
         assert cs == ob.label_checksum(lo, values)
         # the oracle (BitStreamLabelledArcIterator restated) on one core, first nodes holding ~20 M arcs
         orc = ob.load().load_labels(lbase, n)
         upto = int(np.searchsorted(off, min(arcs, 20_000_000)))
-        deg = np.diff(off)
         t0 = time.perf_counter()
-        buf = np.empty(int(deg[:upto].max()) + 1, dtype=np.int32)
-        tot = 0
-        for x in range(upto):
-            d = int(deg[x])
-            if d:
-                tot += orc.orc.lib.orc_labels_node(orc.l, x, d, None, buf.ctypes.data, len(buf))
+        _, tot = orc.sequential(0, upto, off, store=False)
         dt = time.perf_counter() - t0
-        res["cpu_oracle_G_labels_per_s_1core"] = tot / dt / 1e9
-        res["cpu_sample"] = "%d nodes / %d labels, one ctypes call per node" % (upto, tot)
+        assert tot == int(values[:off[upto]].astype(np.int64).sum())
+        res["cpu_oracle_G_labels_per_s_1core"] = int(off[upto]) / dt / 1e9
+        res["cpu_sample"] = "first %d nodes / %d labels read front to back, consume only" % (upto, int(off[upto]))
         orc.close()
         alg.close()
         out[name] = res

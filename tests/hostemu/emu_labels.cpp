@@ -33,20 +33,26 @@ extern "C" int emu_labels(const uint8_t* labels, uint64_t nbytes, const uint64_t
         for (int64_t tile = ra; tile < rb; tile += LAB_FIXED_TILE) {
             const int64_t tile_end = std::min<int64_t>(tile + LAB_FIXED_TILE, rb);
             const int32_t nlo = lab_node_of(rowoff, from, to - 1, tile), nhi = lab_node_of(rowoff, from, to - 1, tile_end - 1);
-            for (int64_t j = tile; j < tile_end; j++) {
-                const uint32_t v = lab_fixed_value(L, nlo, nhi, j);
-                values[j - ra] = (int32_t)v;
-                acc += lab_fold_int(j - ra, v);
+            for (int64_t j0 = tile; j0 < tile_end; j0 += LAB_FIXED_ITEMS) {  // one thread's run
+                uint32_t v[LAB_FIXED_ITEMS];
+                const int c = lab_fixed_run(L, nlo, nhi, j0, tile_end, v);
+                if (c != (int)std::min<int64_t>(LAB_FIXED_ITEMS, tile_end - j0)) return -101;
+                for (int k = 0; k < c; k++) {
+                    if (v[k] != lab_fixed_value(L, nlo, nhi, j0 + k)) return -102;  // the per-arc search and the walk must agree
+                    values[j0 + k - ra] = (int32_t)v[k];
+                    acc += lab_fold_int(j0 + k - ra, v[k]);
+                }
             }
         }
     } else if (kind == LAB_GAMMA) {
         const uint64_t base = off[from] - L.bit_base, end = off[to] - L.bit_base;
-        const int64_t nsub = std::max<int64_t>(1, (int64_t)((end - base + OFF_SUB_BITS - 1) / OFF_SUB_BITS));
+        const uint64_t sub_bits = 80;  // not the offsets' pitch: the run-time pitch is what the label path uses
+        const int64_t nsub = std::max<int64_t>(1, (int64_t)((end - base + sub_bits - 1) / sub_bits));
         std::vector<OffSub> a((size_t)nsub), b((size_t)nsub);
-        for (int64_t j = 0; j < nsub; j++) off_speculate_one(j, words.data(), words.size(), end, C_GAMMA, a.data(), base);
+        for (int64_t j = 0; j < nsub; j++) off_speculate_one(j, words.data(), words.size(), end, C_GAMMA, a.data(), base, sub_bits);
         for (int it = 0;; it++) {
             int changed = 0;
-            for (int64_t j = 0; j < nsub; j++) off_fix_one(j, words.data(), words.size(), end, C_GAMMA, a.data(), b.data(), &changed, base);
+            for (int64_t j = 0; j < nsub; j++) off_fix_one(j, words.data(), words.size(), end, C_GAMMA, a.data(), b.data(), &changed, base, sub_bits);
             a.swap(b);
             if (!changed) break;
             if (it > nsub + 2) return -100;
@@ -54,8 +60,8 @@ extern "C" int emu_labels(const uint8_t* labels, uint64_t nbytes, const uint64_t
         std::vector<int64_t> cbase((size_t)nsub + 1, 0);
         for (int64_t j = 0; j < nsub; j++) cbase[j + 1] = cbase[j] + a[j].count;
         if (cbase[nsub] != arcs) return -5;
-        for (int64_t j = 0; j < nsub; j++) lab_gamma_emit_one(j, words.data(), words.size(), base, end, a.data(), cbase.data(), ra, arcs, values, false);
-        for (int64_t j = 0; j < nsub; j++) acc += lab_gamma_emit_one(j, words.data(), words.size(), base, end, a.data(), cbase.data(), ra, arcs, nullptr, true);
+        for (int64_t j = 0; j < nsub; j++) lab_gamma_emit_one(j, words.data(), words.size(), base, end, sub_bits, a.data(), cbase.data(), ra, arcs, values, false);
+        for (int64_t j = 0; j < nsub; j++) acc += lab_gamma_emit_one(j, words.data(), words.size(), base, end, sub_bits, a.data(), cbase.data(), ra, arcs, nullptr, true);
     } else {
         const int64_t cnt = (int64_t)to - from;
         std::vector<int32_t> counts((size_t)cnt + 1, 0);

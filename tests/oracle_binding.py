@@ -66,6 +66,8 @@ class Oracle:
         lib.orc_labels_free.restype = None
         lib.orc_labels_node.argtypes = [P(OrcLabels), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
         lib.orc_labels_node.restype = C.c_int64
+        lib.orc_labels_range.argtypes = [P(OrcLabels), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, P(C.c_uint64)]
+        lib.orc_labels_range.restype = C.c_int64
 
     def load_labels(self, basename, n):
         l = C.POINTER(OrcLabels)()
@@ -201,6 +203,17 @@ class OracleLabels:
         if nv2 < 0:
             raise OracleError(nv2)
         return lo, vals[:nv]
+
+    def sequential(self, frm, to, row_off, store=True):
+        """Integer labels of frm..to-1 read front to back; returns (values or None, sum of the values)."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+        arcs = int(row_off[to] - row_off[frm])
+        vals = np.empty(max(arcs, 1), dtype=np.int32) if store else None
+        tot = C.c_uint64()
+        rc = self.orc.lib.orc_labels_range(self.l, frm, to, row_off.ctypes.data, vals.ctypes.data if store else None, arcs, C.byref(tot))
+        if rc < 0:
+            raise OracleError(rc)
+        return (vals[:arcs] if store else None), tot.value
 
     def range(self, frm, to, row_off):
         """Labels of the arcs of frm..to-1 (row_off: CSR offsets of the underlying graph), as (list_off, values)."""

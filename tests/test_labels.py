@@ -258,14 +258,14 @@ def test_gpu_labels_on_shards_device_buffers_and_long_gamma_codes(tmp_path, orac
     base, lbase, values, list_off, _ = write_case(tmp_path, "sk", off, succ, tools.LABEL_GAMMA, 0, values=values)
     n = len(off) - 1
     # a shard of the underlying graph loads only its stretch of the label stream
-    for frm, to in ((0, n), (4, 120), (6, n), (1000, 1000)):
+    for frm, to in ((0, n), (4, 120), (40, n), (1000, 1000)):
         g = bvgraph.BVGraph.loadShard(base, frm, to)
         h = C.c_void_p()
-        bvgraph._check(bvgraph.lib().bvg_labels_open(g.handle(), os.fsencode(lbase), C.byref(h)))
+        bvgraph._check(bvgraph.lib().bvg_labels_open(g.handle, os.fsencode(lbase), C.byref(h)))
         alg = labelling.BitStreamArcLabelledImmutableGraph(g, h)
         lo, vals = alg.decodeLabels(frm, to)
         assert np.array_equal(vals, values[off[frm]:off[to]])
-        if (frm, to) == (6, n):
+        if (frm, to) == (40, n):  # node 5 holds 99 % of the labels and lies before the shard's halo
             assert alg.heldBytes < 0.2 * (len(values) * 4)
         # device buffers, filled in stream order
         arcs = int(off[to] - off[frm])

@@ -996,11 +996,21 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 // threshold follows the arcs this graph object holds: 512 for the 1 B-arc benchmark graph, 128 for one eighth of it
 // (measured on 125 M arcs: 2.64 ms per scan with 1024, 1.52 ms with 128; on 1 B arcs 512 and 1024 are level at 6.5 ms,
 // 256 costs 0.7 ms more).  BVG_LONG_D / BVG_LONG_SEG / BVG_LONG_CHUNK override.
+// Which records take the split path (bvg_long.cuh) and how finely they are split, by the arcs of the extent.  A launch of the
+// per-record kernels lasts at least as long as its longest record takes one thread, and the fewer records a launch has the
+// less the longest-first schedule can hide that; the split path spreads a record over threads.  Measured on the 1 B-arc
+// power-law graph (profiles/shard_profile.py, ms per scan of a shard, long_d / segment / chunk):
+//   whole graph  1024/128/128 5.91   512/128/128 5.72   512/32/32 5.63   256/64/64 5.72
+//   1/2          512/128/128  3.30   256/64/64   3.16   128/32/32 3.19
+//   1/4          256/64/64    1.91   128/64/64   1.83   96/32/32  1.74
+//   1/8          1024/128/128 2.44   128/64/64   1.15   96/32/32  1.03   64/16/16 0.99   48/16/16 1.01
 static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to) {
     const double arcs = (double)g->m_total * (double)(to - from) / (double)std::max<int32_t>(g->n_total, 1);
-    int32_t d = 1024;
-    while (d > 128 && (double)d > arcs * 7e-7) d >>= 1;
-    const int32_t part = d <= 256 ? 64 : 128;
+    int32_t d, part;
+    if (arcs > 7.5e8) { d = 512; part = 32; }
+    else if (arcs > 3.7e8) { d = 256; part = 32; }
+    else if (arcs > 1.8e8) { d = 96; part = 32; }
+    else { d = 64; part = 16; }
     g->long_d = env_int("BVG_LONG_D", d, 2, 1 << 30);
     g->long_seg = env_int("BVG_LONG_SEG", part, 1, 1 << 20);
     g->long_chunk = env_int("BVG_LONG_CHUNK", part, 1, 1 << 20);

@@ -78,8 +78,32 @@ __device__ __forceinline__ uint32_t lab_fixed_value(const LabelsDev& L, int32_t 
     return lab_bits_at(L, p, L.width);
 }
 
+// ITEMS consecutive arcs from j0 (all inside [j0, jend), nodes inside [nlo, nhi]): one search for the first arc's node, then a
+// walk -- the next arc's label starts where this one ends unless the node changes.  Returns how many were read.
+__device__ __forceinline__ int lab_fixed_run(const LabelsDev& L, int32_t nlo, int32_t nhi, int64_t j0, int64_t jend, uint32_t* v /* ITEMS */) {
+    int32_t x = lab_node_of(L.rowoff, nlo, nhi, j0);
+    int64_t next = L.rowoff[x + 1];
+    uint64_t p = L.off[x] - L.bit_base + (uint64_t)(j0 - L.rowoff[x]) * (uint64_t)L.width;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < LAB_FIXED_ITEMS; k++) {
+        const int64_t j = j0 + k;
+        if (j < jend) {
+            if (j >= next) {
+                do { x++; next = L.rowoff[x + 1]; } while (j >= next);   // empty nodes in between
+                p = L.off[x] - L.bit_base;
+            }
+            v[k] = lab_bits_at(L, p, L.width);
+            p += (uint64_t)L.width;
+            c = k + 1;
+        }
+    }
+    return c;
+}
+
 #ifndef BVG_HOST_EMULATION
-// Arcs [ra, rb) of nodes [from, to) (node indices relative to node_lo); out[j - ra] = label of arc j.
+// Arcs [ra, rb) of nodes [from, to) (node indices relative to node_lo); out[j - ra] = label of arc j.  A thread takes
+// LAB_FIXED_ITEMS consecutive arcs: its reads are one contiguous stretch of the stream, its writes two 16-byte stores.
 template <bool FOLD>
 __global__ void __launch_bounds__(LAB_FIXED_THREADS)
 k_lab_fixed(LabelsDev L, int32_t from, int32_t to, int64_t ra, int64_t rb, int32_t* __restrict__ out, unsigned long long* __restrict__ result) {
@@ -89,49 +113,76 @@ k_lab_fixed(LabelsDev L, int32_t from, int32_t to, int64_t ra, int64_t rb, int32
     if (threadIdx.x == 0) s_lo = lab_node_of(L.rowoff, from, to - 1, tile);
     if (threadIdx.x == 32) s_hi = lab_node_of(L.rowoff, from, to - 1, tile_end - 1);
     __syncthreads();
-    const int32_t nlo = s_lo, nhi = s_hi;
+    const int64_t j0 = tile + (int64_t)threadIdx.x * LAB_FIXED_ITEMS;
     uint64_t acc = 0;
+    if (j0 < tile_end) {
+        uint32_t v[LAB_FIXED_ITEMS];
+        const int c = lab_fixed_run(L, s_lo, s_hi, j0, tile_end, v);
+        if (FOLD) {
 #pragma unroll
-    for (int k = 0; k < LAB_FIXED_ITEMS; k++) {
-        const int64_t j = tile + (int64_t)k * LAB_FIXED_THREADS + threadIdx.x;
-        if (j < tile_end) {
-            const uint32_t v = lab_fixed_value(L, nlo, nhi, j);
-            if (FOLD) acc += lab_fold_int(j - ra, v);
-            else out[j - ra] = (int32_t)v;
+            for (int k = 0; k < LAB_FIXED_ITEMS; k++) if (k < c) acc += lab_fold_int(j0 + k - ra, v[k]);
+        } else {
+            int32_t* o = out + (j0 - ra);
+            if (c == LAB_FIXED_ITEMS && ((uintptr_t)o & 15) == 0) {
+#pragma unroll
+                for (int k = 0; k < LAB_FIXED_ITEMS; k += 4) *reinterpret_cast<uint4*>(o + k) = uint4{ v[k], v[k + 1], v[k + 2], v[k + 3] };
+            } else {
+#pragma unroll
+                for (int k = 0; k < LAB_FIXED_ITEMS; k++) if (k < c) o[k] = (int32_t)v[k];
+            }
         }
     }
     if (FOLD) lab_block_add(acc, result);
 }
 #endif
 
+#ifndef BVG_LAB_SUB_BITS
+#define BVG_LAB_SUB_BITS 8192
+#endif
+constexpr uint64_t LAB_SUB_BITS = BVG_LAB_SUB_BITS;   // sub-range pitch of the gamma labels (default; BVG_LAB_SUB_BITS in the environment overrides)
+
 // ---- GammaCodedIntLabel: the proven sub-range chains (OffSub) emitted -----------------------------------------------------
 // cbase: exclusive scan of the sub-ranges' counts; label number ord (from the first label of the range) belongs to arc ra + ord.
 __device__ inline uint64_t lab_gamma_emit_one(int64_t j, const uint32_t* __restrict__ words, uint64_t nwords, uint64_t base, uint64_t end_bits,
-                                              const OffSub* __restrict__ sub, const int64_t* __restrict__ cbase, int64_t ra, int64_t narcs,
-                                              int32_t* __restrict__ out, bool fold) {
-    const uint64_t hi = off_min(base + (uint64_t)(j + 1) * OFF_SUB_BITS, end_bits);
+                                              uint64_t sub_bits, const OffSub* __restrict__ sub, const int64_t* __restrict__ cbase, int64_t ra,
+                                              int64_t narcs, int32_t* __restrict__ out, bool fold) {
+    const uint64_t hi = off_min(base + (uint64_t)(j + 1) * sub_bits, end_bits);
     BitBuf b;
     b.w = words; b.maxw = nwords - 3;
     b.seek(sub[j].entry);
     int64_t ord = cbase[j];
     uint64_t acc = 0;
+    (void)ra;
+    if (fold) {
+        while (b.pos() < hi && ord < narcs) { acc += lab_fold_int(ord, (uint32_t)b.gamma()); ord++; }
+        return acc;
+    }
+    // a thread's labels are consecutive in `out`: groups of four go out as one 16-byte store (a full half sector instead of
+    // four partial writes from 32 lanes that are ~100 labels apart)
+    const bool vec = ((uintptr_t)out & 15) == 0;
     while (b.pos() < hi && ord < narcs) {
-        const uint32_t v = (uint32_t)b.gamma();
-        if (fold) acc += lab_fold_int(ord, v);
-        else out[ord] = (int32_t)v;
-        ord++;
+        if (vec && (ord & 3) == 0) {
+            int32_t v[4];
+            int c = 0;
+            while (c < 4 && b.pos() < hi && ord + c < narcs) v[c++] = (int32_t)(uint32_t)b.gamma();
+            if (c == 4) *reinterpret_cast<uint4*>(out + ord) = uint4{ (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3] };
+            else for (int i = 0; i < c; i++) out[ord + i] = v[i];
+            ord += c;
+        } else {
+            out[ord++] = (int32_t)(uint32_t)b.gamma();
+        }
     }
     return acc;
 }
 
 #ifndef BVG_HOST_EMULATION
 template <bool FOLD>
-__global__ void k_lab_gamma_emit(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t base, uint64_t end_bits, int64_t nsub,
+__global__ void k_lab_gamma_emit(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t base, uint64_t end_bits, uint64_t sub_bits, int64_t nsub,
                                  const OffSub* __restrict__ sub, const int64_t* __restrict__ cbase, int64_t ra, int64_t narcs,
                                  int32_t* __restrict__ out, unsigned long long* __restrict__ result) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t acc = 0;
-    if (j < nsub) acc = lab_gamma_emit_one(j, words, nwords, base, end_bits, sub, cbase, ra, narcs, out, FOLD);
+    if (j < nsub) acc = lab_gamma_emit_one(j, words, nwords, base, end_bits, sub_bits, sub, cbase, ra, narcs, out, FOLD);
     if (FOLD) lab_block_add(acc, result);
 }
 #endif

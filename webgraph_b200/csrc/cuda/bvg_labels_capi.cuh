@@ -113,18 +113,18 @@ static int labels_build(bvg_labels* l, const uint8_t* offsets_stream, uint64_t o
 
 // The gamma labels of bits [base, end) (positions in the loaded words): speculate, fix until stable, scan of the counts.
 // On return *sub / *cbase are valid until the Tmp objects die; *total = labels found.
-static int labels_gamma_chains(const bvg_labels* l, cudaStream_t s, uint64_t base, uint64_t end, int64_t nsub, Tmp<OffSub>& sa, Tmp<OffSub>& sb,
+static int labels_gamma_chains(const bvg_labels* l, cudaStream_t s, uint64_t base, uint64_t end, uint64_t sub_bits, int64_t nsub, Tmp<OffSub>& sa, Tmp<OffSub>& sb,
                                Tmp<int32_t>& counts, Tmp<int64_t>& cbase, Tmp<int>& changed, const OffSub** sub, int64_t* total) {
     CK(sa.alloc((size_t)nsub));
     CK(sb.alloc((size_t)nsub));
     CK(counts.alloc((size_t)nsub));
     CK(cbase.alloc((size_t)nsub + 1));
     CK(changed.alloc(1));
-    LAUNCH_P(l->g, "k_lab_speculate", k_off_speculate, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, end, C_GAMMA, nsub, sa.p, base);
+    LAUNCH_P(l->g, "k_lab_speculate", k_off_speculate, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, end, C_GAMMA, nsub, sa.p, base, sub_bits);
     OffSub *in = sa.p, *out = sb.p;
     for (int64_t pass = 0;; pass++) {
         CK(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
-        LAUNCH_P(l->g, "k_lab_fix", k_off_fix, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, end, C_GAMMA, nsub, in, out, changed.p, base);
+        LAUNCH_P(l->g, "k_lab_fix", k_off_fix, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, end, C_GAMMA, nsub, in, out, changed.p, base, sub_bits);
         int ch = 0;
         CK(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -166,22 +166,23 @@ static int labels_run(const bvg_labels* l, int32_t from, int32_t to, int64_t ra,
         CK(cudaMemcpyAsync(&ob, l->d_off + rt, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         const uint64_t base = oa - l->bit_base, end = ob - l->bit_base;
-        const int64_t nsub = std::max<int64_t>(1, (int64_t)((end - base + OFF_SUB_BITS - 1) / OFF_SUB_BITS));
+        static const uint64_t sub_bits = (uint64_t)env_int("BVG_LAB_SUB_BITS", (int)LAB_SUB_BITS, 64, 1 << 24);
+        const int64_t nsub = std::max<int64_t>(1, (int64_t)((end - base + sub_bits - 1) / sub_bits));
         Tmp<OffSub> sa(s), sb(s);
         Tmp<int32_t> counts(s);
         Tmp<int64_t> cbase(s);
         Tmp<int> changed(s);
         const OffSub* sub = nullptr;
         int64_t total = 0;
-        const int rc = labels_gamma_chains(l, s, base, end, nsub, sa, sb, counts, cbase, changed, &sub, &total);
+        const int rc = labels_gamma_chains(l, s, base, end, sub_bits, nsub, sa, sb, counts, cbase, changed, &sub, &total);
         if (rc) return rc;
         if (total != arcs) {  // the stretch between the two label offsets does not hold one label per arc
             std::lock_guard<std::mutex> lk(g->mu);
             g->err_node = from; g->err_bitpos = (int64_t)oa;
             return BVG_EFORMAT;
         }
-        if (fold) LAUNCH_P(g, "k_lab_gamma_emit", k_lab_gamma_emit<true>, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, base, end, nsub, sub, cbase.p, ra, arcs, nullptr, d_result);
-        else LAUNCH_P(g, "k_lab_gamma_emit", k_lab_gamma_emit<false>, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, base, end, nsub, sub, cbase.p, ra, arcs, d_values, nullptr);
+        if (fold) LAUNCH_P(g, "k_lab_gamma_emit", k_lab_gamma_emit<true>, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, base, end, sub_bits, nsub, sub, cbase.p, ra, arcs, nullptr, d_result);
+        else LAUNCH_P(g, "k_lab_gamma_emit", k_lab_gamma_emit<false>, grid_for(nsub, 128), 128, 0, s, l->d_words, l->nwords, base, end, sub_bits, nsub, sub, cbase.p, ra, arcs, d_values, nullptr);
     } else {
         const int64_t cnt = (int64_t)to - from;
         Tmp<int32_t> counts(s);

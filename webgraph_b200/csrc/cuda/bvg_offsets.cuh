@@ -16,8 +16,9 @@
 //   k_off_emit       after an exclusive scan of counts and sums every thread re-reads its sub-range from its proven
 //                    entry and writes the absolute offsets.
 // The result is bit-exact by construction (every entry point has been walked to from bit 0), not probabilistic.
-// `base` (default 0) moves bit 0 of the sub-range grid: the gamma-coded label stream (bvg_labels.cuh) is read the same way
-// from the first label of a node range, a position its label offsets give exactly.
+// `base` (default 0) moves bit 0 of the sub-range grid and `sub_bits` sets its pitch: the gamma-coded label stream
+// (bvg_labels.cuh) is read the same way from the first label of a node range, a position its label offsets give exactly,
+// with longer sub-ranges (label codes are longer than offset gaps, and two chains over long codes take longer to meet).
 #pragma once
 #include "bvg_device.cuh"
 
@@ -50,8 +51,8 @@ __device__ __forceinline__ void off_walk(const uint32_t* __restrict__ words, uin
 __device__ __forceinline__ uint64_t off_min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
 __device__ inline void off_speculate_one(int64_t j, const uint32_t* __restrict__ words, uint64_t nwords, uint64_t total_bits,
-                                         int coding, OffSub* __restrict__ sub, uint64_t base = 0) {
-    const uint64_t lo = base + (uint64_t)j * OFF_SUB_BITS, hi = off_min(lo + (uint64_t)OFF_SUB_BITS, total_bits);
+                                         int coding, OffSub* __restrict__ sub, uint64_t base = 0, uint64_t sub_bits = OFF_SUB_BITS) {
+    const uint64_t lo = base + (uint64_t)j * sub_bits, hi = off_min(lo + sub_bits, total_bits);
     OffSub s;
     s.entry = lo;
     off_walk(words, nwords - 3, coding, lo, hi, s.exit, s.count, s.sum);
@@ -59,18 +60,18 @@ __device__ inline void off_speculate_one(int64_t j, const uint32_t* __restrict__
 }
 
 __global__ void k_off_speculate(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t total_bits, int coding,
-                                int64_t nsub, OffSub* __restrict__ sub, uint64_t base = 0) {
+                                int64_t nsub, OffSub* __restrict__ sub, uint64_t base = 0, uint64_t sub_bits = OFF_SUB_BITS) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nsub) off_speculate_one(j, words, nwords, total_bits, coding, sub, base);
+    if (j < nsub) off_speculate_one(j, words, nwords, total_bits, coding, sub, base, sub_bits);
 }
 
 __device__ inline void off_fix_one(int64_t j, const uint32_t* __restrict__ words, uint64_t nwords, uint64_t total_bits, int coding,
                                    const OffSub* __restrict__ in, OffSub* __restrict__ out, int* __restrict__ changed,
-                                   uint64_t base = 0) {
+                                   uint64_t base = 0, uint64_t sub_bits = OFF_SUB_BITS) {
     OffSub s = in[j];
     if (j > 0) {
         const uint64_t t = in[j - 1].exit;  // the entry the previous sub-range's chain dictates
-        const uint64_t hi = off_min(base + (uint64_t)(j + 1) * OFF_SUB_BITS, total_bits);
+        const uint64_t hi = off_min(base + (uint64_t)(j + 1) * sub_bits, total_bits);
         if (t != s.entry) {
             BitBuf a, b;
             a.w = b.w = words; a.maxw = b.maxw = nwords - 3;
@@ -98,9 +99,10 @@ __device__ inline void off_fix_one(int64_t j, const uint32_t* __restrict__ words
 }
 
 __global__ void k_off_fix(const uint32_t* __restrict__ words, uint64_t nwords, uint64_t total_bits, int coding, int64_t nsub,
-                          const OffSub* __restrict__ in, OffSub* __restrict__ out, int* __restrict__ changed, uint64_t base = 0) {
+                          const OffSub* __restrict__ in, OffSub* __restrict__ out, int* __restrict__ changed, uint64_t base = 0,
+                          uint64_t sub_bits = OFF_SUB_BITS) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nsub) off_fix_one(j, words, nwords, total_bits, coding, in, out, changed, base);
+    if (j < nsub) off_fix_one(j, words, nwords, total_bits, coding, in, out, changed, base, sub_bits);
 }
 
 // cbase / sbase: exclusive scans of count / sum.  offsets[i] = sum of the first i+1 gaps, i = 0..n.

@@ -112,7 +112,7 @@ class BitStreamArcLabelledImmutableGraph:
         g = graph_loader(underlying_basename(basename), device=device)
         h = C.c_void_p()
         try:
-            _check(lib().bvg_labels_open(g.handle(), os.fsencode(basename), C.byref(h)), g.handle())
+            _check(lib().bvg_labels_open(g.handle, os.fsencode(basename), C.byref(h)), g.handle)
         except Exception:
             g.close()
             raise
@@ -139,8 +139,8 @@ class BitStreamArcLabelledImmutableGraph:
         lb = np.frombuffer(labels, dtype=np.uint8)
         ob = np.frombuffer(label_offsets, dtype=np.uint8)
         h = C.c_void_p()
-        _check(lib().bvg_labels_open_memory(g.handle(), lb.ctypes.data if len(lb) else None, len(lb), ob.ctypes.data, len(ob),
-                                            kind, width, C.byref(h)), g.handle())
+        _check(lib().bvg_labels_open_memory(g.handle, lb.ctypes.data if len(lb) else None, len(lb), ob.ctypes.data, len(ob),
+                                            kind, width, C.byref(h)), g.handle)
         return cls(g, h)
 
     def close(self, close_graph=True):
@@ -179,11 +179,11 @@ class BitStreamArcLabelledImmutableGraph:
     def decodeLabels(self, frm, to):
         """(list_off int64[arcs + 1], values int32[nvalues]) for the arcs of frm..to-1 in successor order."""
         nv = C.c_int64()
-        _check(lib().bvg_labels_decode_range(self._h, frm, to, None, None, 0, 0, C.byref(nv)), self.g.handle())
+        _check(lib().bvg_labels_decode_range(self._h, frm, to, None, None, 0, 0, C.byref(nv)), self.g.handle)
         arcs = self.g.rangeArcs(frm, to)
         lo = np.zeros(arcs + 1, dtype=np.int64)
         vals = np.empty(max(nv.value, 1), dtype=np.int32)
-        _check(lib().bvg_labels_decode_range(self._h, frm, to, lo.ctypes.data, vals.ctypes.data, nv.value, 0, C.byref(nv)), self.g.handle())
+        _check(lib().bvg_labels_decode_range(self._h, frm, to, lo.ctypes.data, vals.ctypes.data, nv.value, 0, C.byref(nv)), self.g.handle)
         return lo, vals[:nv.value]
 
     def labelsOfRange(self, frm, to):
@@ -198,7 +198,7 @@ class BitStreamArcLabelledImmutableGraph:
 
     def scanLabels(self, frm, to):
         arcs, nv, cs = C.c_int64(), C.c_int64(), C.c_uint64()
-        _check(lib().bvg_labels_scan_range(self._h, frm, to, C.byref(arcs), C.byref(nv), C.byref(cs)), self.g.handle())
+        _check(lib().bvg_labels_scan_range(self._h, frm, to, C.byref(arcs), C.byref(nv), C.byref(cs)), self.g.handle)
         return arcs.value, nv.value, cs.value
 
     def successors(self, x):
