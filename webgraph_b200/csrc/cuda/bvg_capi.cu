@@ -1003,14 +1003,14 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 //   whole graph  1024/128/128 5.91   512/128/128 5.72   512/32/32 5.63   256/64/64 5.72
 //   1/2          512/128/128  3.30   256/64/64   3.16   128/32/32 3.19
 //   1/4          256/64/64    1.91   128/64/64   1.83   96/32/32  1.74
-//   1/8          1024/128/128 2.44   128/64/64   1.15   96/32/32  1.03   64/16/16 0.99   48/16/16 1.01
+//   1/8          1024/128/128 2.44   128/64/64   1.15   96/32/32  1.03   64/16/16 0.99   64/24/24 0.95   48/16/16 1.01
 static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to) {
     const double arcs = (double)g->m_total * (double)(to - from) / (double)std::max<int32_t>(g->n_total, 1);
     int32_t d, part;
     if (arcs > 7.5e8) { d = 512; part = 32; }
     else if (arcs > 3.7e8) { d = 256; part = 32; }
     else if (arcs > 1.8e8) { d = 96; part = 32; }
-    else { d = 64; part = 16; }
+    else { d = 64; part = 24; }
     g->long_d = env_int("BVG_LONG_D", d, 2, 1 << 30);
     g->long_seg = env_int("BVG_LONG_SEG", part, 1, 1 << 20);
     g->long_chunk = env_int("BVG_LONG_CHUNK", part, 1, 1 << 20);
