@@ -1,0 +1,21 @@
+import sys, os, time, ctypes as C
+sys.path.insert(0, '.')
+import numpy as np, torch
+import bench
+from webgraph_b200 import bvgraph
+class A: pass
+args = A(); args.nodes=0; args.arcs=0; args.seed=0x5EED; args.max_degree=1<<22; args.workdir='/tmp/bvg_bench'
+base, st = bench.graph_files(args, 'powerlaw', 0, lambda: None)
+L = bvgraph.lib()
+graph = torch.from_numpy(np.fromfile(base+'.graph', dtype=np.uint8)).pin_memory()
+offs = torch.from_numpy(np.fromfile(base+'.offsets', dtype=np.uint8)).pin_memory()
+n, m = st['nodes'], st['arcs']
+bounds = bvgraph.plan_shards(base, 8)
+a_out, c_out = C.c_int64(), C.c_uint64()
+def one(lo, hi, pieces):
+    t=time.perf_counter()
+    bvgraph._check(L.bvg_scan_memory(graph.data_ptr(), graph.numel(), offs.data_ptr(), offs.numel(), n, m, 7,3,4,3,0,0, lo, hi, pieces, C.byref(a_out), C.byref(c_out)))
+    return (time.perf_counter()-t)*1e3
+for lo, hi, p in ((bounds[3], bounds[4], 1), (0, n, 4), (0, n, 6)):
+    for _ in range(3): one(lo, hi, p)
+    print(os.environ.get('BVG_ONESHOT_D'), os.environ.get('BVG_ONESHOT_PART'), 'range', lo, hi, 'pieces', p, [round(one(lo, hi, p),2) for _ in range(4)])

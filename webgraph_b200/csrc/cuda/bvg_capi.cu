@@ -443,6 +443,7 @@ static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t
     const uint64_t nwords = ((nbytes + 3) / 4 + 8 + 3) & ~(uint64_t)3;
     const uint64_t total_bits = nbytes * 8;
     const int64_t nsub = std::max<int64_t>(1, (int64_t)((total_bits + OFF_SUB_BITS - 1) / OFF_SUB_BITS));
+    Trace tr(s);
     Tmp<uint32_t> words(s);
     Tmp<OffSub> sa(s), sb(s);
     Tmp<int> changed(s);
@@ -452,6 +453,7 @@ static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t
     CK(cudaMemsetAsync(words.p, 0, (size_t)nwords * 4, s));
     if (nbytes) CK(cudaMemcpyAsync(words.p, stream, (size_t)nbytes, cudaMemcpyHostToDevice, s));
     LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, words.p, nwords);
+    tr.mark("  offsets: upload + swap");
     CK(sa.alloc((size_t)nsub));
     CK(sb.alloc((size_t)nsub));
     CK(changed.alloc(1));
@@ -467,23 +469,22 @@ static int device_decode_offsets(cudaStream_t s, const uint8_t* stream, uint64_t
         if (!ch) break;
         if (pass > nsub + 2) return BVG_EIO;
     }
-    std::vector<OffSub> h((size_t)nsub);
-    CK(cudaMemcpyAsync(h.data(), in, (size_t)nsub * sizeof(OffSub), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    std::vector<int64_t> cb((size_t)nsub);
-    std::vector<uint64_t> sbv((size_t)nsub);
-    int64_t c = 0;
-    uint64_t sum = 0;
-    for (int64_t j = 0; j < nsub; j++) { cb[(size_t)j] = c; sbv[(size_t)j] = sum; c += h[(size_t)j].count; sum += h[(size_t)j].sum; }
-    if (c < n + 1) return BVG_EIO;  // the stream ends before n+1 gaps (EOFException in the reference)
+    tr.mark("  offsets: speculate + fix");
+    Tmp<unsigned long long> totals(s);
+    CK(totals.alloc(2));
     CK(cbase.alloc((size_t)nsub));
     CK(sbase.alloc((size_t)nsub));
-    CK(cudaMemcpyAsync(cbase.p, cb.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(sbase.p, sbv.data(), (size_t)nsub * 8, cudaMemcpyHostToDevice, s));
+    LAUNCH(k_off_prefix, 1, SCAN_THREADS, 0, s, in, nsub, cbase.p, sbase.p, totals.p);
+    unsigned long long ht[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(ht, totals.p, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if ((int64_t)ht[0] < n + 1) return BVG_EIO;  // the stream ends before n+1 gaps (EOFException in the reference)
+    tr.mark("  offsets: prefix");
     CK(dev_alloc((void**)d_full, ((size_t)n + 1) * 8, s));
     LAUNCH(k_off_emit, grid_for(nsub, 128), 128, 0, s, words.p, nwords, total_bits, coding, nsub, in, cbase.p, sbase.p, n, *d_full);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s));  // cb / sbv are host vectors
+    CK(cudaStreamSynchronize(s));  // the temporaries die with this scope
+    tr.mark("  offsets: emit");
     return BVG_OK;
 }
 
@@ -1004,10 +1005,13 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 //   1/2          512/128/128  3.30   256/64/64   3.16   128/32/32 3.19
 //   1/4          256/64/64    1.91   128/64/64   1.83   96/32/32  1.74
 //   1/8          1024/128/128 2.44   128/64/64   1.15   96/32/32  1.03   64/16/16 0.99   64/24/24 0.95   48/16/16 1.01
-static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to) {
+// one_shot: the graph object lives for a single scan (bvg_scan_memory), so the index of the long records is paid per scan and
+// a finer split costs more to build than it saves.
+static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to, bool one_shot = false) {
     const double arcs = (double)g->m_total * (double)(to - from) / (double)std::max<int32_t>(g->n_total, 1);
     int32_t d, part;
-    if (arcs > 7.5e8) { d = 512; part = 32; }
+    if (one_shot) { d = env_int("BVG_ONESHOT_D", 512, 2, 1 << 30); part = env_int("BVG_ONESHOT_PART", 128, 1, 1 << 20); }
+    else if (arcs > 7.5e8) { d = 512; part = 32; }
     else if (arcs > 3.7e8) { d = 256; part = 32; }
     else if (arcs > 1.8e8) { d = 96; part = 32; }
     else { d = 64; part = 24; }
@@ -1148,7 +1152,7 @@ int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
         g->stream = st[q & 1];
         const int32_t pf = bounds[(size_t)q], pt = bounds[(size_t)q + 1];
         g->ext_from = pf; g->ext_to = pt;
-        choose_long_threshold(g, from, to);  // by the whole range: the index of the long records is paid at every open, here once per piece
+        choose_long_threshold(g, from, to, true);  // the index of the long records is paid at every open, here once per piece
         g->node_lo = shard_halo(g, pf); g->node_hi = pt;
         uint64_t o2[2];
         CK(cudaMemcpyAsync(&o2[0], d_full + g->node_lo, 8, cudaMemcpyDeviceToHost, g->stream));

@@ -7,6 +7,7 @@
 #pragma once
 #include <type_traits>
 #include "bvg_device.cuh"
+#include "bvg_offsets.cuh"
 #include "bvg_scan.cuh"
 
 namespace bvg {
@@ -331,6 +332,26 @@ __global__ void k_scan_apply(const int32_t* __restrict__ in, int64_t n, const in
         if (base + k == n - 1) out[n] = run;
     }
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+// Exclusive prefixes of the counts and sums of the .offsets sub-ranges (bvg_offsets.cuh), one block: every thread takes a
+// contiguous stretch.  cbase / sbase get nsub entries, totals[0] / totals[1] the grand totals.  (The sums are 64-bit gaps, so
+// the int32 scan above does not serve.)
+__global__ void __launch_bounds__(SCAN_THREADS) k_off_prefix(const OffSub* __restrict__ sub, int64_t nsub, int64_t* __restrict__ cbase,
+                                                             uint64_t* __restrict__ sbase, unsigned long long* __restrict__ totals) {
+    const int64_t per = (nsub + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int64_t a = (int64_t)threadIdx.x * per, b = a + per < nsub ? a + per : nsub;
+    int64_t c = 0;
+    uint64_t sm = 0;
+    for (int64_t j = a; j < b; j++) { c += sub[j].count; sm += sub[j].sum; }
+    int64_t ctot, stot;
+    int64_t cb = block_exclusive_scan(c, &ctot);
+    uint64_t sb = (uint64_t)block_exclusive_scan((int64_t)sm, &stot);   // wrap-around arithmetic: exact modulo 2^64
+    for (int64_t j = a; j < b; j++) {
+        cbase[j] = cb; sbase[j] = sb;
+        cb += sub[j].count; sb += sub[j].sum;
+    }
+    if (threadIdx.x == 0) { totals[0] = (unsigned long long)ctot; totals[1] = (unsigned long long)stot; }
 }
 
 // ---------------------------------------------------------------------------------------------------
