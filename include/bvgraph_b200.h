@@ -134,6 +134,14 @@ int  bvg_scan_range_async(const bvg_graph* g, int32_t from, int32_t to, void* d_
  * unreachable (n entries); *levels = eccentricity of the source, *reached = nodes reached.  Whole graphs with offsets only. */
 int  bvg_indegrees(const bvg_graph* g, int32_t from, int32_t to, uint32_t* counts, int64_t counts_len, int on_device, int64_t* arcs);
 int  bvg_bfs(const bvg_graph* g, int32_t source, int32_t* dist, int on_device, int32_t* levels, int64_t* reached);
+/* One HyperBall iteration over nodes [from, to) (reference algo/HyperBall.java:875-915, the branch in which every node
+ * enumerates its successors): out[x] = register-wise max of in[x] and in[s] for every successor s of x.  A counter is
+ * 2^log2m registers of ONE BYTE each (4 <= log2m <= 9; the reference packs 5-7-bit registers into longs), counters of all
+ * numNodes() nodes back to back in `in` / `out` (distinct buffers, 16-byte aligned; out is written for [from, to) only).
+ * modified (may be NULL) receives the number of nodes whose counter changed (the reference's modified-counter count).
+ * Rows are decoded on the device chunk by chunk and consumed there.  on_device != 0: device pointers, stream-ordered. */
+int  bvg_hyperball_step(const bvg_graph* g, int32_t from, int32_t to, int log2m, const uint8_t* in, uint8_t* out, int on_device,
+                        int64_t* modified);
 
 /* ---- NodeIterator: BVGraphNodeIterator :1136-1281 (nextInt, outdegree, successorArray, copy(upperBound)) ---- */
 int  bvg_cursor_open(const bvg_graph* g, int32_t from, int32_t upper, bvg_cursor** out);

@@ -701,3 +701,59 @@ def test_cpp_mirror(tmp_path):
                            "-L", libdir, "-lbvgraph_b200", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe, CNR], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["3216152", "f941dd3471d172f1", "1", "-1", "1", "3216152", "f941dd3471d172f1"]
+
+
+@pytest.mark.gpu
+def test_fused_consumer_hyperball_step(tmp_path, cnr_truth):
+    """HyperBall's inner loop (HyperBall.java:875-915; its own assert block :918-929 states the property): every register of a
+    node becomes the maximum over the node and its successors."""
+    from webgraph_b200.bvgraph import BVGraph
+
+    def expect(off, succ, cin):
+        n = len(off) - 1
+        src = np.repeat(np.arange(n), np.diff(off))
+        out = cin.copy()
+        np.maximum.at(out, src, cin[succ])
+        return out, int(np.any(out != cin, axis=1).sum())
+
+    rng = np.random.default_rng(7)
+    off, succ = cnr_truth
+    g = BVGraph.load(CNR)
+    for log2m in (4, 6):
+        cin = rng.integers(0, 32, (g.numNodes(), 1 << log2m), dtype=np.uint8)
+        want, wmod = expect(off, succ, cin)
+        got, mod = g.hyperballStep(cin, log2m)
+        assert np.array_equal(got, want) and mod == wmod
+        # iterating to the fixed point keeps agreeing (two more rounds)
+        for _ in range(2):
+            want, wmod = expect(off, succ, want)
+            got, mod = g.hyperballStep(got, log2m)
+            assert np.array_equal(got, want) and mod == wmod
+    # a sub-range leaves the other rows alone
+    cin = rng.integers(0, 32, (g.numNodes(), 16), dtype=np.uint8)
+    want, _ = expect(off, succ, cin)
+    got, mod = g.hyperballStep(cin, 4, 1000, 300000)
+    assert np.array_equal(got[1000:300000], want[1000:300000]) and np.array_equal(got[:1000], cin[:1000]) and np.array_equal(got[300000:], cin[300000:])
+    assert mod == int(np.any(want[1000:300000] != cin[1000:300000], axis=1).sum())
+    with pytest.raises(ValueError):
+        g.hyperballStep(cin, 5)   # shape does not match 2^log2m
+    g.close()
+    # a node with 60 000 successors (the block-per-node path), empty nodes, a self-loop, 512 registers
+    n = 70000
+    deg = np.zeros(n, dtype=np.int64)
+    deg[5] = 60000
+    deg[100:140] = 7
+    deg[n - 1] = 2
+    off2 = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=off2[1:])
+    lists = [np.arange(60000, dtype=np.int32)] + [np.arange(x, x + 7, dtype=np.int32) for x in range(100, 140)] + [np.array([3, n - 1], dtype=np.int32)]
+    succ2 = np.concatenate(lists)
+    base = str(tmp_path / "hb")
+    tools.store_csr(base, off2, succ2)
+    g = BVGraph.load(base)
+    for log2m in (4, 9):
+        cin = rng.integers(0, 60, (n, 1 << log2m), dtype=np.uint8)
+        want, wmod = expect(off2, succ2, cin)
+        got, mod = g.hyperballStep(cin, log2m)
+        assert np.array_equal(got, want) and mod == wmod
+    g.close()

@@ -57,7 +57,7 @@ SYMBOLS = [
     "bvg_open_memory_shard", "bvg_plan_shards", "bvg_scan_memory", "bvg_release_cached_memory", "bvg_profile", "bvg_profile_read",
     "bvg_scan_bits", "bvg_replan_shards", "bvg_indegrees", "bvg_bfs", "bvg_cursor_next_batch",
     "bvg_labels_underlying", "bvg_labels_open", "bvg_labels_open_memory", "bvg_labels_close", "bvg_labels_info",
-    "bvg_labels_decode_range", "bvg_labels_scan_range",
+    "bvg_labels_decode_range", "bvg_labels_scan_range", "bvg_hyperball_step",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
     L.bvg_scan_bits.argtypes = [vp, P(i64)]
     L.bvg_indegrees.argtypes = [vp, i32, i32, vp, i64, C.c_int, P(i64)]
     L.bvg_bfs.argtypes = [vp, i32, vp, C.c_int, P(i32), P(i64)]
+    L.bvg_hyperball_step.argtypes = [vp, i32, i32, C.c_int, vp, vp, C.c_int, P(i64)]
     L.bvg_labels_underlying.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.bvg_labels_open.argtypes = [vp, C.c_char_p, P(vp)]
     L.bvg_labels_open_memory.argtypes = [vp, vp, u64, vp, u64, C.c_int, C.c_int, P(vp)]
@@ -544,6 +545,18 @@ class BVGraph(ImmutableGraph):
         levels, reached = C.c_int32(), C.c_int64()
         _check(lib().bvg_bfs(self._h, source, dist.ctypes.data, 0, C.byref(levels), C.byref(reached)))
         return dist, levels.value, reached.value
+
+    def hyperballStep(self, counters, log2m, frm=None, to=None):
+        """One HyperBall iteration (HyperBall.java:875-915) on byte registers: counters uint8[numNodes, 2^log2m] ->
+        (new counters, number of modified nodes); rows outside [frm, to) are returned unchanged."""
+        frm, to = (0 if frm is None else frm), (self._n if to is None else to)
+        cin = np.ascontiguousarray(counters, dtype=np.uint8)
+        if cin.shape != (self._n, 1 << log2m):
+            raise ValueError("counters must be uint8[numNodes, 2^log2m]")
+        out = cin.copy()
+        mod = C.c_int64()
+        _check(lib().bvg_hyperball_step(self._h, frm, to, log2m, cin.ctypes.data, out.ctypes.data, 0, C.byref(mod)), self._h)
+        return out, mod.value
 
     def scanBits(self):
         """What a scan of this graph's extent reads of the stream (bvg_scan_bits)."""

@@ -9,6 +9,7 @@
 #include "bvg_long.cuh"
 #include "bvg_offsets.cuh"
 #include "bvg_labels.cuh"
+#include "bvg_consumers.cuh"
 #include "bvg_boundaries.cuh"
 #include "bvg_tile.cuh"
 #include "bvg_stream.cuh"
@@ -2012,6 +2013,82 @@ __global__ void k_bfs_expand(const int32_t* __restrict__ succ, int64_t n, int32_
 __global__ void k_fill_i32(int32_t* __restrict__ p, int64_t n, int32_t v) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// One HyperBall iteration (reference algo/HyperBall.java:875-915, the non-systolic branch: every node enumerates its successors):
+// out[x] = register-wise max(in[x], in[s] for every successor s of x), x in [from, to).  Rows are decoded chunk by chunk into
+// a scratch CSR on the device and consumed there; nothing but the counters crosses PCIe.
+int bvg_hyperball_step(const bvg_graph* g, int32_t from, int32_t to, int log2m, const uint8_t* in, uint8_t* out, int on_device, int64_t* modified) {
+    std::unique_lock<std::recursive_mutex> call_lock;
+    if (g) call_lock = std::unique_lock<std::recursive_mutex>(g->call_mu);
+    int rc = range_check(g, from, to);
+    if (rc) return rc;
+    if (!in || !out || log2m < 4 || log2m > 9) return BVG_EINVAL;   // 16 .. 512 registers of one byte
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    const int lanes_log = log2m - 4;
+    const size_t m = (size_t)1 << log2m, total = (size_t)g->n_total * m;
+    Tmp<uint8_t> d_in(s), d_out(s);
+    const uint8_t* din = in;
+    uint8_t* dout = out;
+    if (!on_device) {
+        CK(d_in.alloc(total));
+        CK(d_out.alloc(total));
+        CK(cudaMemcpyAsync(d_in.p, in, total, cudaMemcpyHostToDevice, s));
+        din = d_in.p; dout = d_out.p;
+    }
+    if (((uintptr_t)din | (uintptr_t)dout) & 15) return BVG_EINVAL;   // counters are read and written 16 bytes at a time
+    Tmp<unsigned long long> d_mod(s);
+    Tmp<int32_t> d_heavy(s), d_nheavy(s);
+    CK(d_mod.alloc(1));
+    CK(d_nheavy.alloc(1));
+    CK(cudaMemsetAsync(d_mod.p, 0, 8, s));
+    // chunks of whole 2^ORDER_CHUNK_LOG-node schedule chunks holding about HB_CHUNK_ARCS arcs
+    const int64_t chunk_arcs = (int64_t)env_int("BVG_HB_CHUNK_MARCS", 256, 1, 1 << 14) << 20;
+    int32_t lo = from;
+    while (lo < to) {
+        int32_t hi = (int32_t)std::min<int64_t>(to, (((int64_t)lo >> ORDER_CHUNK_LOG) + 1) << ORDER_CHUNK_LOG);
+        int64_t ra, rb;
+        rc = fetch_rowoff(g, lo, hi, &ra, &rb);
+        if (rc) return rc;
+        while (hi < to) {   // extend while the chunk stays under the arc budget
+            const int32_t nh = (int32_t)std::min<int64_t>(to, (int64_t)hi + ((int64_t)1 << ORDER_CHUNK_LOG));
+            int64_t r2a, r2b;
+            rc = fetch_rowoff(g, lo, nh, &r2a, &r2b);
+            if (rc) return rc;
+            if (r2b - r2a > chunk_arcs) break;
+            hi = nh; rb = r2b;
+        }
+        const int64_t arcs = rb - ra, cnt = (int64_t)hi - lo;
+        Tmp<int64_t> d_off(s);
+        Tmp<int32_t> d_rows(s);
+        CK(d_off.alloc((size_t)cnt + 1));
+        CK(d_rows.alloc((size_t)std::max<int64_t>(arcs, 1)));
+        CK(d_heavy.alloc((size_t)std::max<int64_t>(1, arcs / HB_HEAVY + 1)));
+        CK(cudaMemsetAsync(d_nheavy.p, 0, 4, s));
+        rc = bvg_decode_range(g, lo, hi, d_off.p, d_rows.p, arcs, 1);
+        if (rc) return rc;
+        LAUNCH_P(g, "k_hb_update", k_hb_update, grid_for(cnt << lanes_log, HB_THREADS), HB_THREADS, 0, s, d_rows.p, d_off.p, lo, cnt,
+                 (const uint4*)din, (uint4*)dout, lanes_log, d_heavy.p, d_nheavy.p, d_mod.p);
+        int32_t nheavy = 0;
+        CK(cudaMemcpyAsync(&nheavy, d_nheavy.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (nheavy > 0) LAUNCH_P(g, "k_hb_update_heavy", k_hb_update_heavy, (unsigned)nheavy, HB_THREADS, 0, s, d_rows.p, d_off.p, lo, d_heavy.p,
+                                 (const uint4*)din, (uint4*)dout, lanes_log, d_mod.p);
+        CK(cudaGetLastError());
+        lo = hi;
+    }
+    unsigned long long hm = 0;
+    CK(cudaMemcpyAsync(&hm, d_mod.p, 8, cudaMemcpyDeviceToHost, s));
+    if (!on_device) {
+        const size_t a = (size_t)from * m, b = (size_t)to * m;
+        if (b > a) CK(cudaMemcpyAsync(out + a, d_out.p + a, b - a, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    const int e = fetch_error(g);
+    if (e) return e;
+    if (modified) *modified = (int64_t)hm;
+    return BVG_OK;
 }
 
 // Breadth-first visit from `source` (reference algo/ParallelBreadthFirstVisit.java:155-181: frontier by frontier, the
