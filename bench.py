@@ -592,6 +592,49 @@ class Bench:
                                   "sum_of_successors_matches_generator": bool(sum_ok),
                                   "what": "bvg_decode_range of the whole graph into device CSR (int64 offsets + int32 successors)"}
             del moff, mout
+            # fused consumers: what a WebGraph algorithm gets without the successors ever leaving the device
+            try:
+                fc = {}
+                cnts = torch.zeros(self.n_total, dtype=torch.int32, device=self.dev)
+                arcs_c = C.c_int64()
+                for rep in range(2):
+                    cnts.zero_()
+                    r0.record()
+                    bvgraph._check(L.bvg_indegrees(g3.handle, 0, self.n_total, cnts.data_ptr(), self.n_total, 1, C.byref(arcs_c)))
+                    r1.record()
+                    torch.cuda.synchronize()
+                fc["indegrees"] = {"ms": r0.elapsed_time(r1), "arcs_per_s": self.m_total / (r0.elapsed_time(r1) * 1e-3),
+                                   "sum_equals_arcs": bool(int(cnts.sum(dtype=torch.int64).item()) == self.m_total == arcs_c.value),
+                                   "what": "bvg_indegrees: Transform.transpose's counting pass (numPred[y]++) inside the scan, device buffer"}
+                del cnts
+                dist_t = torch.empty(self.n_total, dtype=torch.int32, device=self.dev)
+                lv, reached = C.c_int32(), C.c_int64()
+                for rep in range(2):
+                    r0.record()
+                    bvgraph._check(L.bvg_bfs(g3.handle, 0, dist_t.data_ptr(), 1, C.byref(lv), C.byref(reached)))
+                    r1.record()
+                    torch.cuda.synchronize()
+                fc["bfs"] = {"ms": r0.elapsed_time(r1), "levels": lv.value, "reached": reached.value, "source": 0,
+                             "what": "bvg_bfs: ParallelBreadthFirstVisit's frontier expansion over device-side random access"}
+                del dist_t
+                log2m = 4
+                cin = torch.randint(0, 32, (self.n_total, 1 << log2m), dtype=torch.uint8, device=self.dev)
+                cout = cin.clone()
+                mod = C.c_int64()
+                for rep in range(2):
+                    r0.record()
+                    bvgraph._check(L.bvg_hyperball_step(g3.handle, 0, self.n_total, log2m, cin.data_ptr(), cout.data_ptr(), 1, C.byref(mod)))
+                    r1.record()
+                    torch.cuda.synchronize()
+                hms = r0.elapsed_time(r1)
+                fc["hyperball_step"] = {"ms": hms, "arcs_per_s": self.m_total / (hms * 1e-3), "registers": 1 << log2m, "modified_nodes": mod.value,
+                                        "never_decreases": bool((cout >= cin).all().item()),
+                                        "gather_GBps": self.m_total * (1 << log2m) / (hms * 1e-3) / 1e9,
+                                        "what": "bvg_hyperball_step: HyperBall's register-wise max over successors (byte registers), rows decoded on the device in 256 M-arc chunks"}
+                del cin, cout
+                out["fused_consumers"] = fc
+            except Exception as e:
+                out["fused_consumers"] = {"error": repr(e)}
             # the NodeIterator route (bvg_cursor_*: batches decoded on the device, copied to pinned host memory, iterated in C)
             cur = C.c_void_p()
             bvgraph._check(L.bvg_cursor_open(g3.handle, 0, 2 ** 31 - 1, C.byref(cur)))
