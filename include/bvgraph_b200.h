@@ -212,6 +212,29 @@ int  bvg_labels_decode_range(const bvg_labels* l, int32_t from, int32_t to, int6
  * (2j + 1) * (0x9E3779B97F4A7C15 * len_j + sum_i (v_ji + 1) * (2i + 1)) mod 2^64 (len = 1 for integer labels). */
 int  bvg_labels_scan_range(const bvg_labels* l, int32_t from, int32_t to, int64_t* arcs, int64_t* nvalues, uint64_t* checksum);
 
+/* ---- EFGraph (decode half): the reference's quasi-succinct format ----
+ * <basename>.graph is an LSB-first stream of 64-bit words (byteorder property): per node gamma(outdegree), then the
+ * Elias-Fano encoding of the successors and the terminator upperbound -- skip pointers, lower bits, upper bits in unary
+ * (reference EFGraph.java:420-556 written, :1064-1145 read); <basename>.offsets holds delta-coded gaps (:641-672).
+ * bvg_ef_open mirrors EFGraph.loadInternal (:709-790): BVG_EIO for a missing file, a wrong graphclass or a version > 0
+ * (IOException), BVG_EINVAL for a quantum that is no power of two or an unknown byteorder (IllegalArgumentException),
+ * BVG_EFORMAT when the outdegrees do not add up to the arcs property.  outdegree / successors / decode_range / scan_range
+ * have the meaning of their bvg_* namesakes (same CSR layout, same (arcs, XOR) checksum), so that an EFGraph and a
+ * BVGraph of the same graph can be compared by their scans. */
+typedef struct bvg_efgraph bvg_efgraph;
+int  bvg_ef_open(const char* basename, int device, bvg_efgraph** out);
+int  bvg_ef_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes,
+                        int32_t nodes, int64_t arcs, int32_t upper_bound, int32_t quantum, int big_endian, int device,
+                        bvg_efgraph** out);
+void bvg_ef_close(bvg_efgraph* g);
+int  bvg_ef_info(const bvg_efgraph* g, int32_t* nodes, int64_t* arcs, int32_t* upper_bound, int32_t* quantum, int64_t* graph_bits);
+int  bvg_ef_outdegree(const bvg_efgraph* g, int32_t x, int32_t* d);                                   /* EFGraph.java:1054-1060 */
+int  bvg_ef_successors(const bvg_efgraph* g, int32_t x, int32_t* out, int32_t cap, int32_t* d);      /* :1223-1225 */
+int  bvg_ef_range_arcs(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* arcs);
+int  bvg_ef_decode_range(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* out_off, int32_t* out, int64_t cap, int on_device);
+int  bvg_ef_scan_range(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum);
+int  bvg_ef_last_error_node(const bvg_efgraph* g, int32_t* node, int64_t* bitpos);
+
 /* ---- diagnostics ---- */
 const char* bvg_strerror(int status);
 /* Node and bit position of the first record a kernel rejected (BVGraph.java:1129-1131 logs the same pair). */

@@ -94,6 +94,16 @@ enum { BVGT_LABEL_GAMMA = 0, BVGT_LABEL_FIXED = 1, BVGT_LABEL_FIXED_LIST = 2 };
 int bvgt_store_labels(const char* basename, const char* underlying, const char* key, int32_t n, const int64_t* off,
                       const int64_t* list_off, const int32_t* values, int kind, int width, int threads, int64_t* label_bits);
 
+/* EFGraph.store(graph, upperBound, basename, log2Quantum, cacheSize, byteOrder, pl) (reference EFGraph.java:812-888): the
+ * quasi-succinct format -- per node gamma(outdegree) (LSB-first long-word stream, LongWordOutputBitStream :298-418), then the
+ * Elias-Fano encoding of the successors plus the terminator upperBound (Accumulator :420-556): skip pointers to zeros
+ * (numberOfPointers x pointerSize bits), lower bits ((outdegree + 1) x l), upper bits in unary.  Writes <basename>.graph (long
+ * words in the given byte order, one trailing word as LongWordOutputBitStream.close() does), .offsets (delta-coded gaps,
+ * MSB-first OutputBitStream) and .properties.  upper_bound <= 0 means n.  Returns 0, -1 (bad argument), -4 (I/O); graph_bits
+ * (may be NULL) receives the bits written before the final padding. */
+int bvgt_store_ef(const char* basename, int32_t n, const int64_t* off, const int32_t* succ, int32_t upper_bound,
+                  int log2_quantum, int big_endian, int threads, int64_t* graph_bits);
+
 #ifdef __cplusplus
 }
 #endif

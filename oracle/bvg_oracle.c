@@ -816,3 +816,145 @@ int64_t orc_labels_range(const orc_labels* l, int32_t from, int32_t to, const in
     if (sum) *sum = acc;
     return arcs;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * EFGraph (EFGraph.java): the quasi-succinct format.  PARITY UNPINNED: the reference ships no
+ * EFGraph fixture (EFGraphTest.java stores its graphs at run time) and no JVM exists here; the
+ * restatement follows LongWordBitReader (:892-1036) and EliasFanoSuccessorReader (:1064-1145).
+ * The stream is LSB-first in 64-bit words: bit i is bit i % 64 of word i / 64.
+ * ---------------------------------------------------------------------------------------- */
+static inline uint64_t ef_bits(const uint64_t* w, uint64_t pos, int width) { /* extract(position), :981-1000 */
+    if (width == 0) return 0;
+    const uint64_t i = pos >> 6;
+    const int s = (int)(pos & 63);
+    uint64_t v = w[i] >> s;
+    if (s && s + width > 64) v |= w[i + 1] << (64 - s);
+    return width == 64 ? v : v & ((1ULL << width) - 1);
+}
+static inline int ef_msb(uint64_t x) { return x ? 63 - __builtin_clzll(x) : -1; }
+static inline int ef_lower_bits(uint64_t length, uint64_t ub) { /* :145-147 */
+    if (length == 0) return 0;
+    const int m = ef_msb(ub / length);
+    return m < 0 ? 0 : m;
+}
+static inline int ef_ceil_log2(uint64_t x) { return x <= 1 ? 0 : 64 - __builtin_clzll(x - 1); }
+
+void orc_ef_free(orc_efgraph* g) {
+    if (!g) return;
+    free(g->words);
+    free(g->offsets);
+    free(g);
+}
+
+int orc_ef_load(const char* basename, orc_efgraph** out) { /* loadInternal, :709-790 */
+    char path[4096], val[512];
+    uint64_t psz = 0;
+    snprintf(path, sizeof path, "%s.properties", basename);
+    char* props = (char*)slurp(path, &psz, 1);
+    if (!props) return BVGO_EIO;
+    orc_efgraph* g = (orc_efgraph*)calloc(1, sizeof *g);
+    int rc = BVGO_OK, big = 0;
+    if (!prop_get(props, "graphclass", val, sizeof val) ||
+        (strcmp(val, "it.unimi.dsi.webgraph.EFGraph") && strcmp(val, "it.unimi.dsi.big.webgraph.EFGraph"))) { rc = BVGO_EIO; goto fail; }
+    if (!prop_get(props, "version", val, sizeof val) || atoi(val) > 0) { rc = BVGO_EIO; goto fail; }
+    if (!prop_get(props, "nodes", val, sizeof val)) { rc = BVGO_EFORMAT; goto fail; }
+    if (atoll(val) > 2147483647LL || atoll(val) < 0) { rc = BVGO_EINVAL; goto fail; }
+    g->n = (int32_t)atoll(val);
+    if (!prop_get(props, "arcs", val, sizeof val)) { rc = BVGO_EFORMAT; goto fail; }
+    g->m = atoll(val);
+    g->upper_bound = g->n;
+    if (prop_get(props, "upperbound", val, sizeof val)) g->upper_bound = atoi(val);
+    if (!prop_get(props, "quantum", val, sizeof val)) { rc = BVGO_EFORMAT; goto fail; }
+    {
+        const long long quantum = atoll(val);
+        g->log2_quantum = ef_msb((uint64_t)quantum);
+        if (quantum <= 0 || (1LL << g->log2_quantum) != quantum) { rc = BVGO_EINVAL; goto fail; } /* "Illegal quantum" */
+    }
+    if (!prop_get(props, "byteorder", val, sizeof val)) { rc = BVGO_EFORMAT; goto fail; }
+    if (!strcmp(val, "BIG_ENDIAN")) big = 1;
+    else if (strcmp(val, "LITTLE_ENDIAN")) { rc = BVGO_EINVAL; goto fail; } /* "Unknown byte order" */
+    {
+        uint64_t bytes = 0;
+        snprintf(path, sizeof path, "%s.graph", basename);
+        uint8_t* b = slurp(path, &bytes, 32);
+        if (!b) { rc = BVGO_EIO; goto fail; }
+        g->nwords = bytes / 8;
+        g->words = (uint64_t*)b; /* calloc'ed: aligned; two padding words follow */
+        if (big) for (uint64_t i = 0; i < g->nwords; i++) g->words[i] = __builtin_bswap64(g->words[i]);
+    }
+    {
+        uint64_t osz = 0;
+        snprintf(path, sizeof path, "%s.offsets", basename);
+        uint8_t* ob = slurp(path, &osz, 16);
+        if (!ob) { rc = BVGO_EIO; goto fail; }
+        g->offsets = (uint64_t*)malloc(((size_t)g->n + 1) * sizeof(uint64_t));
+        ibs_t s = { ob, osz * 8, 0 };
+        uint64_t off = 0;
+        for (int64_t i = 0; i <= g->n; i++) { /* OffsetsLongIterator, :641-672: delta-coded gaps */
+            off += ibs_read_delta(&s);
+            g->offsets[i] = off;
+            if (s.pos > s.nbits) { free(ob); rc = BVGO_EIO; goto fail; }
+        }
+        free(ob);
+        if (g->offsets[g->n] > g->nwords * 64) { rc = BVGO_EIO; goto fail; }
+    }
+    free(props);
+    *out = g;
+    return BVGO_OK;
+fail:
+    free(props);
+    orc_ef_free(g);
+    return rc;
+}
+
+/* readGamma at a bit position (:1002-1036): trailing zeros = msb, then msb bits. */
+static uint64_t ef_read_gamma(const uint64_t* w, uint64_t* pos) {
+    uint64_t p = *pos;
+    int msb = 0;
+    for (;;) {
+        const uint64_t v = w[p >> 6] >> (p & 63);
+        if (v) { const int z = __builtin_ctzll(v); msb += z; p += (uint64_t)z + 1; break; }
+        msb += 64 - (int)(p & 63);
+        p = ((p >> 6) + 1) << 6;
+        if (msb > 64) { *pos = p; return ~0ULL; }
+    }
+    const uint64_t low = ef_bits(w, p, msb);
+    *pos = p + (uint64_t)msb;
+    return (low | (1ULL << msb)) - 1;
+}
+
+int orc_ef_outdegree(const orc_efgraph* g, int32_t x, int32_t* d) { /* :1054-1060 */
+    if (x < 0 || x >= g->n) return BVGO_EINVAL;
+    uint64_t pos = g->offsets[x];
+    const uint64_t v = ef_read_gamma(g->words, &pos);
+    if (v > 0x7fffffffULL) return BVGO_EIO;
+    *d = (int32_t)v;
+    return BVGO_OK;
+}
+
+/* successors(x) drained (EliasFanoSuccessorReader, :1100-1145): returns d or an error. */
+int64_t orc_ef_successors(const orc_efgraph* g, int32_t x, int32_t* out, int64_t cap) {
+    if (x < 0 || x >= g->n) return BVGO_EINVAL;
+    uint64_t pos = g->offsets[x];
+    const uint64_t d = ef_read_gamma(g->words, &pos);
+    if (d > 0x7fffffffULL) return BVGO_EIO;
+    if (out && (int64_t)d > cap) return BVGO_ENOMEM;
+    if (d == 0 || !out) return (int64_t)d;
+    const uint64_t ub = (uint64_t)g->upper_bound, len = d + 1;
+    const int l = ef_lower_bits(len, ub);
+    const int psize = ef_ceil_log2(len + (ub >> l));
+    const uint64_t npointers = (ub >> l) >> g->log2_quantum;
+    const uint64_t lower_start = pos + (uint64_t)psize * npointers, upper_start = lower_start + (uint64_t)l * len;
+    uint64_t curr = upper_start >> 6;
+    uint64_t window = g->words[curr] & (~0ULL << (upper_start & 63));
+    for (uint64_t k = 0; k < d; k++) {
+        while (window == 0) {
+            if (++curr >= g->nwords + 2) return BVGO_EIO;
+            window = g->words[curr];
+        }
+        const uint64_t upper = curr * 64 + (uint64_t)__builtin_ctzll(window) - k - upper_start;
+        window &= window - 1;
+        out[k] = (int32_t)((upper << l) | ef_bits(g->words, lower_start + (uint64_t)l * k, l));
+    }
+    return (int64_t)d;
+}

@@ -117,6 +117,20 @@ void orc_labels_free(orc_labels* l);
 int64_t orc_labels_node(const orc_labels* l, int32_t x, int32_t d, int64_t* list_off, int32_t* values, int64_t cap);
 int64_t orc_labels_range(const orc_labels* l, int32_t from, int32_t to, const int64_t* row_off, int32_t* values, int64_t cap, uint64_t* sum);
 
+/* ---- EFGraph (EFGraph.java) -- PARITY UNPINNED: no EFGraph fixture exists in the reference tree; see bvg_oracle.c. ---- */
+typedef struct orc_efgraph {
+    int32_t n;
+    int64_t m;
+    int32_t upper_bound, log2_quantum;
+    uint64_t* words;        /* the .graph long words in host order + two zero words */
+    uint64_t nwords;
+    uint64_t* offsets;      /* n+1 bit offsets */
+} orc_efgraph;
+int  orc_ef_load(const char* basename, orc_efgraph** out);
+void orc_ef_free(orc_efgraph* g);
+int  orc_ef_outdegree(const orc_efgraph* g, int32_t x, int32_t* d);
+int64_t orc_ef_successors(const orc_efgraph* g, int32_t x, int32_t* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,28 @@
+// emu_ef.cpp -- the per-thread EFGraph walkers (bvg_ef.cuh: ef_outdegree_one, ef_decode_one) on the host.  The block-per-node
+// kernel for heavy lists is covered on the device only (tests/test_efgraph.py, -m gpu).
+#define BVG_HOST_EMULATION
+#include <algorithm>
+using std::min;
+using std::max;
+#include "../../webgraph_b200/csrc/cuda/bvg_ef.cuh"
+#include <vector>
+using namespace bvg;
+
+// words: nwords long words in host order followed by >= 2 zero words.  out_off: n + 1, out: cap entries.
+extern "C" int emu_ef_decode(const uint64_t* words, uint64_t nwords, const uint64_t* offsets, int32_t n, uint32_t upper_bound, int log2_quantum,
+                             int64_t* out_off, int32_t* out, int64_t cap, unsigned long long* checksum) {
+    EfDev g;
+    g.w = words; g.nwords = nwords; g.offsets = offsets; g.n = n; g.upper_bound = upper_bound; g.log2_quantum = log2_quantum;
+    ErrWord err{};
+    std::vector<int32_t> deg((size_t)n + 1, 0);
+    for (int64_t x = 0; x < n; x++) ef_outdegree_one(g, x, deg.data(), x, &err);
+    if (err.code) return err.code;
+    out_off[0] = 0;
+    for (int64_t x = 0; x < n; x++) out_off[x + 1] = out_off[x] + deg[(size_t)x];
+    if (out_off[n] > cap) return -6;
+    unsigned long long acc = 0;
+    for (int64_t x = 0; x < n; x++) if (deg[(size_t)x]) acc ^= ef_decode_one(g, x, out + out_off[x], &err);
+    if (err.code) return err.code;
+    *checksum = acc;
+    return 0;
+}

@@ -20,6 +20,11 @@ class OrcGraph(C.Structure):
                 ("offsets", C.POINTER(C.c_uint64))]
 
 
+class OrcEFGraph(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int64), ("upper_bound", C.c_int32), ("log2_quantum", C.c_int32),
+                ("words", C.POINTER(C.c_uint64)), ("nwords", C.c_uint64), ("offsets", C.POINTER(C.c_uint64))]
+
+
 class OrcLabels(C.Structure):
     _fields_ = [("kind", C.c_int), ("width", C.c_int), ("n", C.c_int32), ("labels", C.POINTER(C.c_uint8)),
                 ("label_bytes", C.c_uint64), ("offsets", C.POINTER(C.c_uint64))]
@@ -61,6 +66,12 @@ class Oracle:
         lib.orc_chain_root.restype = C.c_int32
         lib.orc_read_code.argtypes = [C.c_void_p, C.c_uint64, P(C.c_uint64), C.c_int, C.c_int]
         lib.orc_read_code.restype = C.c_uint64
+        lib.orc_ef_load.argtypes = [C.c_char_p, P(P(OrcEFGraph))]
+        lib.orc_ef_free.argtypes = [P(OrcEFGraph)]
+        lib.orc_ef_free.restype = None
+        lib.orc_ef_outdegree.argtypes = [P(OrcEFGraph), C.c_int32, P(C.c_int32)]
+        lib.orc_ef_successors.argtypes = [P(OrcEFGraph), C.c_int32, C.c_void_p, C.c_int64]
+        lib.orc_ef_successors.restype = C.c_int64
         lib.orc_labels_load.argtypes = [C.c_char_p, C.c_int32, P(P(OrcLabels))]
         lib.orc_labels_free.argtypes = [P(OrcLabels)]
         lib.orc_labels_free.restype = None
@@ -68,6 +79,13 @@ class Oracle:
         lib.orc_labels_node.restype = C.c_int64
         lib.orc_labels_range.argtypes = [P(OrcLabels), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, P(C.c_uint64)]
         lib.orc_labels_range.restype = C.c_int64
+
+    def load_ef(self, basename):
+        g = C.POINTER(OrcEFGraph)()
+        rc = self.lib.orc_ef_load(basename.encode(), C.byref(g))
+        if rc:
+            raise OracleError(rc)
+        return OracleEFGraph(self, g)
 
     def load_labels(self, basename, n):
         l = C.POINTER(OrcLabels)()
@@ -174,6 +192,44 @@ class OracleGraph:
 
 
 _ORACLE = None
+
+
+class OracleEFGraph:
+    """orc_efgraph: EFGraph read the way EliasFanoSuccessorReader reads it (one node at a time)."""
+
+    def __init__(self, orc, g):
+        self.orc, self.g = orc, g
+        c = g.contents
+        self.n, self.m, self.upper_bound, self.log2_quantum = c.n, c.m, c.upper_bound, c.log2_quantum
+
+    def close(self):
+        if self.g:
+            self.orc.lib.orc_ef_free(self.g)
+            self.g = None
+
+    def offsets(self):
+        return np.ctypeslib.as_array(self.g.contents.offsets, shape=(self.n + 1,)).copy()
+
+    def outdegree(self, x):
+        d = C.c_int32()
+        rc = self.orc.lib.orc_ef_outdegree(self.g, x, C.byref(d))
+        if rc:
+            raise OracleError(rc)
+        return d.value
+
+    def successors(self, x):
+        d = self.outdegree(x)
+        out = np.empty(max(d, 1), dtype=np.int32)
+        r = self.orc.lib.orc_ef_successors(self.g, x, out.ctypes.data, d)
+        if r < 0:
+            raise OracleError(r)
+        return out[:d]
+
+    def decode_range(self, lo, hi):
+        rows = [self.successors(x) for x in range(lo, hi)]
+        off = np.zeros(hi - lo + 1, dtype=np.int64)
+        np.cumsum([len(r) for r in rows], out=off[1:])
+        return off, (np.concatenate(rows) if rows else np.empty(0, dtype=np.int32)).astype(np.int32)
 
 
 class OracleLabels:

@@ -58,6 +58,8 @@ SYMBOLS = [
     "bvg_scan_bits", "bvg_replan_shards", "bvg_indegrees", "bvg_bfs", "bvg_cursor_next_batch",
     "bvg_labels_underlying", "bvg_labels_open", "bvg_labels_open_memory", "bvg_labels_close", "bvg_labels_info",
     "bvg_labels_decode_range", "bvg_labels_scan_range", "bvg_hyperball_step",
+    "bvg_ef_open", "bvg_ef_open_memory", "bvg_ef_close", "bvg_ef_info", "bvg_ef_outdegree", "bvg_ef_successors", "bvg_ef_range_arcs",
+    "bvg_ef_decode_range", "bvg_ef_scan_range", "bvg_ef_last_error_node",
 ]
 
 
@@ -114,6 +116,17 @@ def lib():
     L.bvg_scan_bits.argtypes = [vp, P(i64)]
     L.bvg_indegrees.argtypes = [vp, i32, i32, vp, i64, C.c_int, P(i64)]
     L.bvg_bfs.argtypes = [vp, i32, vp, C.c_int, P(i32), P(i64)]
+    L.bvg_ef_open.argtypes = [C.c_char_p, C.c_int, P(vp)]
+    L.bvg_ef_open_memory.argtypes = [vp, u64, vp, u64, i32, i64, i32, i32, C.c_int, C.c_int, P(vp)]
+    L.bvg_ef_close.argtypes = [vp]
+    L.bvg_ef_close.restype = None
+    L.bvg_ef_info.argtypes = [vp, P(i32), P(i64), P(i32), P(i32), P(i64)]
+    L.bvg_ef_outdegree.argtypes = [vp, i32, P(i32)]
+    L.bvg_ef_successors.argtypes = [vp, i32, vp, i32, P(i32)]
+    L.bvg_ef_range_arcs.argtypes = [vp, i32, i32, P(i64)]
+    L.bvg_ef_decode_range.argtypes = [vp, i32, i32, vp, vp, i64, C.c_int]
+    L.bvg_ef_scan_range.argtypes = [vp, i32, i32, P(i64), P(u64)]
+    L.bvg_ef_last_error_node.argtypes = [vp, P(i32), P(i64)]
     L.bvg_hyperball_step.argtypes = [vp, i32, i32, C.c_int, vp, vp, C.c_int, P(i64)]
     L.bvg_labels_underlying.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.bvg_labels_open.argtypes = [vp, C.c_char_p, P(vp)]

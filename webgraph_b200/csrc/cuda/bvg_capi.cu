@@ -10,6 +10,7 @@
 #include "bvg_offsets.cuh"
 #include "bvg_labels.cuh"
 #include "bvg_consumers.cuh"
+#include "bvg_ef.cuh"
 #include "bvg_boundaries.cuh"
 #include "bvg_tile.cuh"
 #include "bvg_stream.cuh"
@@ -2692,3 +2693,4 @@ int bvg_profile_read(const bvg_graph* g, char* buf, int cap) {
 }  // extern "C"
 
 #include "bvg_labels_capi.cuh"
+#include "bvg_ef_capi.cuh"

@@ -1,0 +1,196 @@
+// bvg_ef.cuh -- EFGraph, the reference's quasi-succinct format (EFGraph.java), decoded on the device (decode half).
+//
+// Per node the stream holds gamma(outdegree), then the Elias-Fano encoding of the d successors plus the terminator upperBound:
+// skip pointers (numberOfPointers x pointerSize bits, not needed to enumerate), lower bits ((d + 1) x l), upper bits in unary
+// (EFGraph.java:420-556, 1100-1145).  The stream is LSB-first in 64-bit words (LongWordBitReader, :892-1036); `.offsets` holds
+// delta-coded gaps (MSB-first, decoded by bvg_offsets.cuh).  Successor k is ((position of the k-th one) - k) << l | lower[k]:
+// selection in a bit vector, which the reference does with a running 64-bit window and here is
+//   * one thread per node for lists up to EF_HEAVY successors (the same window walk: ctz, clear lowest one), and
+//   * one block per node above that: every thread takes a word of the upper bits, a block-wide exclusive scan of the
+//     popcounts gives each word the rank of its first one, and the ones are emitted in parallel.
+// There are no reference chains and no intervals: every list decodes on its own.
+#pragma once
+#include "bvg_device.cuh"
+
+namespace bvg {
+
+constexpr int32_t EF_HEAVY = 2048;
+constexpr int EF_BLOCK = 256;
+
+struct EfDev {
+    const uint64_t* __restrict__ w;       // long words in host order, >= 2 zero words of padding
+    uint64_t nwords;                      // without the padding
+    const uint64_t* __restrict__ offsets; // n + 1 bit positions
+    int32_t n;
+    uint32_t upper_bound;
+    int log2_quantum;
+};
+
+__device__ __forceinline__ uint64_t ef_word(const EfDev& g, uint64_t i) { return g.w[i < g.nwords + 1 ? i : g.nwords + 1]; }
+
+// `width` bits at bit position pos (0 <= width <= 32 here).
+__device__ __forceinline__ uint32_t ef_bits(const EfDev& g, uint64_t pos, int width) {
+    if (width == 0) return 0u;
+    const uint64_t i = pos >> 6;
+    const int s = (int)(pos & 63);
+    uint64_t v = ef_word(g, i) >> s;
+    if (s + width > 64) v |= ef_word(g, i + 1) << (64 - s);
+    return (uint32_t)(v & ((1ull << width) - 1ull));
+}
+
+// readGamma at *pos (:1002-1036): the number of zeros before the first one is the msb, then msb bits follow.
+__device__ __forceinline__ uint64_t ef_gamma(const EfDev& g, uint64_t& pos) {
+    int msb = 0;
+    for (;;) {
+        const uint64_t v = ef_word(g, pos >> 6) >> (pos & 63);
+        if (v) { const int z = __ffsll((long long)v) - 1; msb += z; pos += (uint64_t)z + 1; break; }
+        msb += 64 - (int)(pos & 63);
+        pos = ((pos >> 6) + 1) << 6;
+        if (msb > 64) return ~0ull;
+    }
+    if (msb > 32) { pos += (uint64_t)msb; return ~0ull; }   // an outdegree does not need more
+    const uint64_t low = ef_bits(g, pos, msb);
+    pos += (uint64_t)msb;
+    return (low | (1ull << msb)) - 1ull;
+}
+
+// Geometry of node x's list: EFGraph.lowerBits / pointerSize / numberOfPointers (:145-171) for length d + 1.
+struct EfList {
+    uint64_t lower_start, upper_start;
+    int64_t d;
+    int l;
+};
+__device__ __forceinline__ bool ef_list(const EfDev& g, int64_t x, EfList& e) {
+    uint64_t pos = g.offsets[x];
+    const uint64_t d = ef_gamma(g, pos);
+    if (d > 0x7fffffffull || pos > g.offsets[x + 1]) { e.d = 0; return false; }
+    e.d = (int64_t)d;
+    const uint64_t len = d + 1, ub = g.upper_bound;
+    const uint64_t q = ub / len;
+    e.l = q == 0 ? 0 : 63 - __clzll((long long)q);
+    const uint64_t ulen = len + (ub >> e.l);
+    const int psize = ulen <= 1 ? 0 : 64 - __clzll((long long)(ulen - 1));
+    const uint64_t npointers = (ub >> e.l) >> g.log2_quantum;
+    e.lower_start = pos + (uint64_t)psize * npointers;
+    e.upper_start = e.lower_start + (uint64_t)e.l * len;
+    (void)ulen;
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long ef_arc_hash(int64_t x, uint32_t y) { return (unsigned long long)x * 0x9E3779B97F4A7C15ull + (unsigned long long)y; }
+
+// Outdegrees of nodes [from, to) (for the row offsets).
+__device__ inline void ef_outdegree_one(const EfDev& g, int64_t x, int32_t* __restrict__ outdeg, int64_t at, ErrWord* err) {
+    uint64_t pos = g.offsets[x];
+    const uint64_t d = ef_gamma(g, pos);
+    if (d > 0x7fffffffull || pos > g.offsets[x + 1]) { report(err, E_IO, (int)x, g.offsets[x]); outdeg[at] = 0; return; }
+    outdeg[at] = (int32_t)d;
+}
+
+// One thread, one list (d <= EF_HEAVY or any d on the host): out may be null (fold only).  Returns the XOR fold.
+__device__ inline unsigned long long ef_decode_one(const EfDev& g, int64_t x, int32_t* __restrict__ out, ErrWord* err) {
+    EfList e;
+    if (!ef_list(g, x, e)) { report(err, E_IO, (int)x, g.offsets[x]); return 0; }
+    unsigned long long acc = 0;
+    uint64_t curr = e.upper_start >> 6;
+    uint64_t window = ef_word(g, curr) & (~0ull << (e.upper_start & 63));
+    const uint64_t end_word = (g.offsets[x + 1] + 63) >> 6;
+    for (int64_t k = 0; k < e.d; k++) {
+        while (window == 0) {
+            if (++curr > end_word) { report(err, E_IO, (int)x, g.offsets[x]); return acc; }
+            window = ef_word(g, curr);
+        }
+        const uint64_t upper = curr * 64 + (uint64_t)(__ffsll((long long)window) - 1) - (uint64_t)k - e.upper_start;
+        window &= window - 1;
+        const uint32_t v = (uint32_t)(upper << e.l) | ef_bits(g, e.lower_start + (uint64_t)e.l * (uint64_t)k, e.l);
+        if (out) out[k] = (int32_t)v;
+        acc ^= ef_arc_hash(x, v);
+    }
+    return acc;
+}
+
+#ifndef BVG_HOST_EMULATION
+__global__ void k_ef_outdegrees(EfDev g, int32_t from, int32_t to, int32_t* __restrict__ outdeg, ErrWord* err) {
+    const int64_t x = (int64_t)from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < to) ef_outdegree_one(g, x, outdeg, x - from, err);
+}
+
+__device__ __forceinline__ void ef_block_fold(unsigned long long arcs, unsigned long long acc, unsigned long long* __restrict__ result) {
+    for (int o = 16; o > 0; o >>= 1) { arcs += __shfl_down_sync(0xffffffffu, arcs, o); acc ^= __shfl_down_sync(0xffffffffu, acc, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (arcs) atomicAdd(result, arcs);
+        if (acc) atomicXor(result + 1, acc);
+    }
+}
+
+// rowoff: row offsets of nodes from.. (rowoff[0] = first arc of `from`); rows = out - rowoff[0].  Lists above EF_HEAVY go to
+// heavy[] for k_ef_decode_heavy.  result (arcs, xor) may be null; out may be null (scan).
+__global__ void __launch_bounds__(EF_BLOCK) k_ef_decode(EfDev g, int32_t from, int32_t to, const int64_t* __restrict__ rowoff, int32_t* __restrict__ out,
+                                                        int32_t* __restrict__ heavy, int32_t* __restrict__ nheavy,
+                                                        unsigned long long* __restrict__ result, ErrWord* err) {
+    const int64_t x = (int64_t)from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long acc = 0, arcs = 0;
+    if (x < to) {
+        const int64_t a = rowoff[x - from], d = rowoff[x - from + 1] - a;
+        if (d > EF_HEAVY) heavy[atomicAdd(nheavy, 1)] = (int32_t)x;
+        else if (d > 0) { acc = ef_decode_one(g, x, out ? out + (a - rowoff[0]) : nullptr, err); arcs = (unsigned long long)d; }
+    }
+    if (result) ef_block_fold(arcs, acc, result);
+}
+
+// One block per heavy list: words of the upper bits in tiles of EF_BLOCK, ranks by a block scan of the popcounts.
+__global__ void __launch_bounds__(EF_BLOCK) k_ef_decode_heavy(EfDev g, int32_t from, const int32_t* __restrict__ heavy, const int64_t* __restrict__ rowoff,
+                                                              int32_t* __restrict__ out, unsigned long long* __restrict__ result, ErrWord* err) {
+    __shared__ int32_t warp_sums[EF_BLOCK / 32];
+    __shared__ int64_t carry;
+    const int64_t x = heavy[blockIdx.x];
+    EfList e;
+    const bool ok = ef_list(g, x, e);
+    const int64_t a = rowoff[x - from];
+    int32_t* o = out ? out + (a - rowoff[0]) : nullptr;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) report(err, E_IO, (int)x, g.offsets[x]); return; }
+    const uint64_t first_word = e.upper_start >> 6;
+    const uint64_t ulen = (uint64_t)e.d + 1 + ((uint64_t)g.upper_bound >> e.l);
+    const uint64_t last_word = (e.upper_start + ulen - 1) >> 6;
+    unsigned long long acc = 0, arcs = 0;
+    for (uint64_t base = first_word; base <= last_word; base += EF_BLOCK) {
+        const uint64_t wi = base + threadIdx.x;
+        uint64_t word = 0;
+        if (wi <= last_word) {
+            word = ef_word(g, wi);
+            if (wi == first_word) word &= ~0ull << (e.upper_start & 63);
+        }
+        const int pc = __popcll(word);
+        // block exclusive scan of pc
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int inc = pc;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, s); if (lane >= s) inc += t; }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        int wbase = 0, tot = 0;
+#pragma unroll
+        for (int wv = 0; wv < EF_BLOCK / 32; wv++) { const int sv = warp_sums[wv]; if (wv < wid) wbase += sv; tot += sv; }
+        int64_t k = carry + wbase + inc - pc;
+        while (word && k < e.d) {
+            const uint64_t p = wi * 64 + (uint64_t)(__ffsll((long long)word) - 1);
+            word &= word - 1;
+            const uint32_t v = (uint32_t)((p - (uint64_t)k - e.upper_start) << e.l) | ef_bits(g, e.lower_start + (uint64_t)e.l * (uint64_t)k, e.l);
+            if (o) o[k] = (int32_t)v;
+            acc ^= ef_arc_hash(x, v);
+            arcs++;
+            k++;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+        if (carry > e.d) break;   // the terminator has been passed: nothing but zeros follows
+    }
+    if (threadIdx.x == 0 && carry < e.d) report(err, E_IO, (int)x, g.offsets[x]);   // fewer ones than successors
+    if (result) ef_block_fold(arcs, acc, result);
+}
+#endif
+
+}  // namespace bvg

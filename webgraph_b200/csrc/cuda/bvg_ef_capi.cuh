@@ -1,0 +1,264 @@
+// bvg_ef_capi.cuh -- C ABI of the EFGraph decoder (include/bvgraph_b200.h, "EFGraph"); part of bvg_capi.cu.  Kernels: bvg_ef.cuh.
+// Replaces EFGraph.loadInternal (EFGraph.java:709-790), outdegree (:1054-1060), successors (:1223-1225) and the sequential
+// nodeIterator() an ImmutableGraph inherits, for graphs whose graphclass is it.unimi.dsi.webgraph.EFGraph.
+
+struct bvg_efgraph {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int32_t n = 0;
+    int64_t m = 0;
+    int32_t upper_bound = 0;
+    int log2_quantum = 0;
+    uint64_t* d_words = nullptr;
+    uint64_t nwords = 0, graph_bits = 0;
+    uint64_t* d_offsets = nullptr;
+    int64_t* d_rowoff = nullptr;   // n + 1
+    ErrWord* d_err = nullptr;
+    mutable std::recursive_mutex call_mu;
+    mutable int32_t err_node = -1;
+    mutable int64_t err_bitpos = -1;
+    EfDev dev() const {
+        EfDev g;
+        g.w = d_words; g.nwords = nwords; g.offsets = d_offsets; g.n = n; g.upper_bound = (uint32_t)upper_bound; g.log2_quantum = log2_quantum;
+        return g;
+    }
+};
+
+static void ef_destroy(bvg_efgraph* g) {
+    if (!g) return;
+    DeviceGuard dg(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    void* ptrs[] = { g->d_words, g->d_offsets, g->d_rowoff, g->d_err };
+    for (void* p : ptrs) if (p) dev_free(p, g->stream);
+    if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
+    cudaGetLastError();
+    delete g;
+}
+
+static int ef_fetch_error(const bvg_efgraph* g) {
+    ErrWord e{};
+    if (cudaMemcpyAsync(&e, g->d_err, sizeof e, cudaMemcpyDeviceToHost, g->stream) != cudaSuccess ||
+        cudaStreamSynchronize(g->stream) != cudaSuccess) { cudaGetLastError(); return BVG_ECUDA; }
+    if (e.code) {
+        g->err_node = e.node; g->err_bitpos = e.bitpos;
+        cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord), g->stream);
+    }
+    return e.code;
+}
+
+__global__ void k_bswap64(uint64_t* __restrict__ w, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint64_t v = w[i];
+        w[i] = ((uint64_t)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(v >> 32), 0, 0x0123);
+    }
+}
+
+extern "C" {
+
+int bvg_ef_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* offsets_stream, uint64_t offsets_bytes, int32_t nodes, int64_t arcs,
+                       int32_t upper_bound, int32_t quantum, int big_endian, int device, bvg_efgraph** out) {
+    if (!out || nodes < 0 || arcs < 0 || (!graph && graph_bytes) || !offsets_stream) return BVG_EINVAL;
+    if (quantum <= 0 || (quantum & (quantum - 1))) return BVG_EINVAL;   // "Illegal quantum (must be a power of 2)", :731
+    if (upper_bound < 0) return BVG_EINVAL;
+    int dev;
+    int dl[1] = { device };
+    int rc = pick_device(device >= 0 ? dl : nullptr, device >= 0 ? 1 : 0, &dev);
+    if (rc) return rc;
+    DeviceGuard dg(dev);
+    bvg_efgraph* g = new (std::nothrow) bvg_efgraph();
+    if (!g) return BVG_ENOMEM;
+    g->device = dev; g->n = nodes; g->m = arcs; g->upper_bound = upper_bound;
+    g->log2_quantum = 31 - __builtin_clz((unsigned)quantum);
+    keep_pool_warm(dev);
+    if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete g; return BVG_ECUDA; }
+    cudaStream_t s = g->stream;
+    auto fail = [&](int code) { ef_destroy(g); return code; };
+    rc = device_decode_offsets(s, offsets_stream, offsets_bytes, C_DELTA, nodes, &g->d_offsets);   // OffsetsLongIterator, :641-672
+    if (rc) return fail(rc);
+    uint64_t last = 0;
+    if (cudaMemcpyAsync(&last, g->d_offsets + nodes, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
+    g->nwords = graph_bytes / 8;
+    g->graph_bits = last;
+    if (last > g->nwords * 64) return fail(BVG_EIO);   // offsets point past the stream
+    if (dev_alloc((void**)&g->d_words, ((size_t)g->nwords + 2) * 8, s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ENOMEM); }
+    if (dev_alloc((void**)&g->d_rowoff, ((size_t)nodes + 1) * 8, s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ENOMEM); }
+    if (dev_alloc((void**)&g->d_err, sizeof(ErrWord), s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ENOMEM); }
+    if (cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord), s) != cudaSuccess || cudaMemsetAsync(g->d_words + g->nwords, 0, 16, s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
+    if (g->nwords && cudaMemcpyAsync(g->d_words, graph, (size_t)g->nwords * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
+    if (big_endian && g->nwords) LAUNCH(k_bswap64, grid_for((int64_t)g->nwords, 256), 256, 0, s, g->d_words, g->nwords);
+    {
+        Tmp<int32_t> outdeg(s);
+        if (outdeg.alloc((size_t)std::max<int32_t>(nodes, 1)) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ENOMEM); }
+        if (nodes) LAUNCH(k_ef_outdegrees, grid_for(nodes, 256), 256, 0, s, g->dev(), 0, nodes, outdeg.p, g->d_err);
+        rc = device_exclusive_scan(s, outdeg.p, nodes, g->d_rowoff);
+        if (rc) return fail(rc);
+        int64_t total = 0;
+        if (cudaMemcpyAsync(&total, g->d_rowoff + nodes, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
+        const int e = ef_fetch_error(g);
+        if (e) return fail(e);
+        if (total != arcs) return fail(BVG_EFORMAT);   // the outdegrees do not add up to the arcs property
+    }
+    *out = g;
+    return BVG_OK;
+}
+
+int bvg_ef_open(const char* basename, int device, bvg_efgraph** out) {
+    if (!basename || !out) return BVG_EINVAL;
+    std::map<std::string, std::string> kv;
+    if (!read_properties_file(std::string(basename) + ".properties", kv)) return BVG_EIO;
+    auto has = [&](const char* k) { return kv.find(k) != kv.end(); };
+    if (!has("graphclass")) return BVG_EIO;
+    const std::string gc = kv["graphclass"];
+    if (gc != "it.unimi.dsi.webgraph.EFGraph" && gc != "it.unimi.dsi.big.webgraph.EFGraph") return BVG_EIO;   // IOException, :716-718
+    if (!has("version") || atoi(kv["version"].c_str()) > 0) return BVG_EIO;                                   // :720-722
+    if (!has("nodes") || !has("arcs") || !has("quantum") || !has("byteorder")) return BVG_EFORMAT;
+    const long long nodes = atoll(kv["nodes"].c_str());
+    if (nodes > 2147483647LL || nodes < 0) return BVG_EINVAL;                                                 // :724
+    const long long arcs = atoll(kv["arcs"].c_str());
+    const long long ub = has("upperbound") ? atoll(kv["upperbound"].c_str()) : nodes;
+    const long long quantum = atoll(kv["quantum"].c_str());
+    if (quantum <= 0 || quantum > (1LL << 30) || (quantum & (quantum - 1)) || ub < 0 || ub > 2147483647LL) return BVG_EINVAL;
+    int big;
+    if (kv["byteorder"] == "BIG_ENDIAN") big = 1;
+    else if (kv["byteorder"] == "LITTLE_ENDIAN") big = 0;
+    else return BVG_EINVAL;                                                                                   // "Unknown byte order", :736
+    std::vector<uint8_t> graph, offs;
+    if (!slurp_file(std::string(basename) + ".graph", graph)) return BVG_EIO;
+    if (!slurp_file(std::string(basename) + ".offsets", offs)) return BVG_EIO;
+    return bvg_ef_open_memory(graph.data(), graph.size(), offs.data(), offs.size(), (int32_t)nodes, arcs, (int32_t)ub, (int32_t)quantum, big, device, out);
+}
+
+void bvg_ef_close(bvg_efgraph* g) { ef_destroy(g); }
+
+int bvg_ef_info(const bvg_efgraph* g, int32_t* nodes, int64_t* arcs, int32_t* upper_bound, int32_t* quantum, int64_t* graph_bits) {
+    if (!g) return BVG_EINVAL;
+    if (nodes) *nodes = g->n;
+    if (arcs) *arcs = g->m;
+    if (upper_bound) *upper_bound = g->upper_bound;
+    if (quantum) *quantum = 1 << g->log2_quantum;
+    if (graph_bits) *graph_bits = (int64_t)g->graph_bits;
+    return BVG_OK;
+}
+
+// Shared body of decode / scan.  d_off (device, may be null) gets to - from + 1 relative row offsets, d_out (device, may be
+// null: scan) the successors, d_result (device, may be null) (arcs, xor).
+static int ef_run(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* d_off, int32_t* d_out, unsigned long long* d_result) {
+    cudaStream_t s = g->stream;
+    const int64_t cnt = (int64_t)to - from;
+    if (d_off) LAUNCH(k_rel_offsets, grid_for(cnt + 1, 256), 256, 0, s, g->d_rowoff + from, cnt, d_off);
+    if (cnt == 0 || (!d_out && !d_result)) { CK(cudaGetLastError()); return BVG_OK; }
+    Tmp<int32_t> heavy(s), nheavy(s);
+    CK(heavy.alloc((size_t)std::max<int64_t>(1, g->m / EF_HEAVY + 1)));
+    CK(nheavy.alloc(1));
+    CK(cudaMemsetAsync(nheavy.p, 0, 4, s));
+    LAUNCH(k_ef_decode, grid_for(cnt, EF_BLOCK), EF_BLOCK, 0, s, g->dev(), from, to, g->d_rowoff + from, d_out, heavy.p, nheavy.p, d_result, g->d_err);
+    int32_t nh = 0;
+    CK(cudaMemcpyAsync(&nh, nheavy.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (nh > 0) LAUNCH(k_ef_decode_heavy, (unsigned)nh, EF_BLOCK, 0, s, g->dev(), from, heavy.p, g->d_rowoff + from, d_out, d_result, g->d_err);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));   // heavy / nheavy die with this scope
+    return BVG_OK;
+}
+
+static int ef_range_check(const bvg_efgraph* g, int32_t from, int32_t to) {
+    if (!g) return BVG_EINVAL;
+    if (from < 0 || to < from || to > g->n) return BVG_EINVAL;
+    return BVG_OK;
+}
+
+int bvg_ef_range_arcs(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* arcs) {
+    int rc = ef_range_check(g, from, to);
+    if (rc) return rc;
+    if (!arcs) return BVG_EINVAL;
+    std::unique_lock<std::recursive_mutex> lk(g->call_mu);
+    DeviceGuard dg(g->device);
+    int64_t ab[2];
+    CK(cudaMemcpyAsync(&ab[0], g->d_rowoff + from, 8, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(&ab[1], g->d_rowoff + to, 8, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    *arcs = ab[1] - ab[0];
+    return BVG_OK;
+}
+
+int bvg_ef_decode_range(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* out_off, int32_t* out, int64_t cap, int on_device) {
+    int rc = ef_range_check(g, from, to);
+    if (rc) return rc;
+    if (!out_off || cap < 0) return BVG_EINVAL;
+    std::unique_lock<std::recursive_mutex> lk(g->call_mu);
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    int64_t arcs = 0;
+    rc = bvg_ef_range_arcs(g, from, to, &arcs);
+    if (rc) return rc;
+    if (out && cap < arcs) return BVG_ENOMEM;
+    if (on_device) {
+        rc = ef_run(g, from, to, out_off, out, nullptr);
+        if (rc) return rc;
+        const int e = ef_fetch_error(g);
+        return e ? e : BVG_OK;
+    }
+    const int64_t cnt = (int64_t)to - from;
+    Tmp<int64_t> d_off(s);
+    Tmp<int32_t> d_out(s);
+    CK(d_off.alloc((size_t)cnt + 1));
+    if (out) CK(d_out.alloc((size_t)std::max<int64_t>(arcs, 1)));
+    rc = ef_run(g, from, to, d_off.p, out ? d_out.p : nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_off, d_off.p, ((size_t)cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (out && arcs) CK(cudaMemcpyAsync(out, d_out.p, (size_t)arcs * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int e = ef_fetch_error(g);
+    return e ? e : BVG_OK;
+}
+
+int bvg_ef_scan_range(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum) {
+    int rc = ef_range_check(g, from, to);
+    if (rc) return rc;
+    std::unique_lock<std::recursive_mutex> lk(g->call_mu);
+    DeviceGuard dg(g->device);
+    cudaStream_t s = g->stream;
+    Tmp<unsigned long long> res(s);
+    CK(res.alloc(2));
+    CK(cudaMemsetAsync(res.p, 0, 16, s));
+    rc = ef_run(g, from, to, nullptr, nullptr, res.p);
+    if (rc) return rc;
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, res.p, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int e = ef_fetch_error(g);
+    if (e) return e;
+    if (arcs) *arcs = (int64_t)h[0];
+    if (checksum) *checksum = h[1];
+    return BVG_OK;
+}
+
+int bvg_ef_outdegree(const bvg_efgraph* g, int32_t x, int32_t* d) {
+    if (!g || !d) return BVG_EINVAL;
+    if (x < 0 || x >= g->n) return BVG_EINVAL;   // IllegalArgumentException as for every ImmutableGraph
+    int64_t a = 0;
+    const int rc = bvg_ef_range_arcs(g, x, x + 1, &a);
+    if (rc) return rc;
+    *d = (int32_t)a;
+    return BVG_OK;
+}
+
+int bvg_ef_successors(const bvg_efgraph* g, int32_t x, int32_t* out, int32_t cap, int32_t* d) {
+    if (!g || !d || cap < 0) return BVG_EINVAL;
+    if (x < 0 || x >= g->n) return BVG_EINVAL;
+    int64_t off[2] = { 0, 0 };
+    const int rc = bvg_ef_decode_range(g, x, x + 1, off, out, cap, 0);
+    if (rc) return rc;
+    *d = (int32_t)off[1];
+    return BVG_OK;
+}
+
+int bvg_ef_last_error_node(const bvg_efgraph* g, int32_t* node, int64_t* bitpos) {
+    if (!g) return BVG_EINVAL;
+    if (node) *node = g->err_node;
+    if (bitpos) *bitpos = g->err_bitpos;
+    return BVG_OK;
+}
+
+}  // extern "C"

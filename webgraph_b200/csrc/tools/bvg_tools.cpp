@@ -65,6 +65,50 @@ struct BitBuf {
 
 inline int msb64(uint64_t x) { return 63 - __builtin_clzll(x); }
 
+// ----------------------------------------------------------------------------------------------
+// LSB-first long-word stream (the write half of EFGraph.LongWordOutputBitStream, EFGraph.java:298-418, restated): bit i of the
+// stream is bit i % 64 of word i / 64.
+// ----------------------------------------------------------------------------------------------
+struct LsbBuf {
+    std::vector<uint64_t> w;
+    uint64_t nbits = 0;
+    inline void put(uint64_t v, int n) {  // low n bits of v, 0 <= n <= 64
+        if (n == 0) return;
+        if (n < 64) v &= (~0ULL >> (64 - n));
+        const uint64_t idx = nbits >> 6;
+        const int off = (int)(nbits & 63);
+        if (w.size() < idx + 2) w.resize(std::max<uint64_t>(idx + 2, w.size() * 2), 0);
+        w[idx] |= v << off;
+        if (off && n > 64 - off) w[idx + 1] |= v >> (64 - off);
+        nbits += (uint64_t)n;
+    }
+    inline void unary(uint64_t zeros) {  // zeros, then a one
+        while (zeros >= 64) { put(0, 64); zeros -= 64; }
+        put(1ULL << zeros, (int)zeros + 1);
+    }
+    inline void gamma(uint64_t x) {  // writeGamma: unary(msb) as the word 1 << msb, then the msb low bits of x + 1 (:396-409)
+        const uint64_t v = x + 1;
+        const int msb = msb64(v);
+        put(1ULL << msb, msb + 1);
+        put(v ^ (1ULL << msb), msb);
+    }
+    void append(const LsbBuf& o) {
+        const uint64_t full = o.nbits >> 6;
+        for (uint64_t i = 0; i < full; i++) put(o.w[i], 64);
+        const int tail = (int)(o.nbits & 63);
+        if (tail) put(o.w[full], tail);
+    }
+};
+
+inline int ef_lower_bits(uint64_t length, uint64_t ub) {  // EFGraph.lowerBits, :145-147
+    if (length == 0) return 0;
+    const uint64_t q = ub / length;
+    return q == 0 ? 0 : msb64(q);
+}
+inline int ef_ceil_log2(uint64_t x) { return x <= 1 ? 0 : 64 - __builtin_clzll(x - 1); }  // Fast.ceilLog2
+inline int ef_pointer_size(uint64_t length, uint64_t ub) { return ef_ceil_log2(length + (ub >> ef_lower_bits(length, ub))); }  // :156-158
+
+
 // Code lengths and writers (definitions: SURVEY Appendix A.2).
 inline int len_unary(uint64_t x) { return (int)x + 1; }
 inline int len_gamma(uint64_t x) { return 2 * msb64(x + 1) + 1; }
@@ -660,6 +704,93 @@ int bvgt_store_labels(const char* basename, const char* underlying, const char* 
     fprintf(f, "underlyinggraph = %s\n", underlying);
     fclose(f);
     if (label_bits) *label_bits = (int64_t)labels.nbits;
+    return 0;
+}
+
+int bvgt_store_ef(const char* basename, int32_t n, const int64_t* off, const int32_t* succ, int32_t upper_bound,
+                  int log2_quantum, int big_endian, int threads, int64_t* graph_bits) {
+    if (!basename || n < 0 || !off || log2_quantum < 0 || log2_quantum > 30) return -1;
+    if (off[n] > 0 && !succ) return -1;
+    const uint64_t ub = upper_bound > 0 ? (uint64_t)upper_bound : (uint64_t)n;
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n > 0 ? n : 1;
+    struct Part { LsbBuf graph; BitBuf offs; int64_t arcs = 0; uint64_t bits_out = 0, bits_succ = 0; bool bad = false; };
+    std::vector<Part> parts((size_t)threads);
+    const int64_t step = ((int64_t)n + threads - 1) / threads;
+    const int q = log2_quantum;
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) th.emplace_back([&, t] {
+        Part& p = parts[(size_t)t];
+        LsbBuf pointers, lower, upper;
+        const int64_t a = t * step, b = std::min<int64_t>(n, a + step);
+        for (int64_t x = a; x < b && !p.bad; x++) {
+            const int64_t d = off[x + 1] - off[x];
+            if (d < 0 || d > 0x7ffffffe) { p.bad = true; break; }
+            const uint64_t before = p.graph.nbits;
+            p.graph.gamma((uint64_t)d);
+            p.bits_out += p.graph.nbits - before;
+            // Accumulator.init(outdegree, upperBound, strict = false, indexZeroes = true, log2Quantum), :472-497
+            const uint64_t len = (uint64_t)d + 1;
+            const int l = ef_lower_bits(len, ub), psize = ef_pointer_size(len, ub);
+            const uint64_t mask = l ? (~0ULL >> (64 - l)) : 0;
+            pointers.w.clear(); pointers.nbits = 0; lower.w.clear(); lower.nbits = 0; upper.w.clear(); upper.nbits = 0;
+            int64_t last_one = -1, cur_len = 0;
+            uint64_t prev = 0;
+            for (int64_t k = 0; k <= d; k++) {   // Accumulator.add for every successor, then for the terminator (dump, :524-528)
+                const uint64_t v = k < d ? (uint64_t)(uint32_t)succ[off[x] + k] : ub;
+                // successors strictly increasing and below the upper bound (Accumulator.add throws otherwise, :499-503)
+                if (k < d && (succ[off[x] + k] < 0 || v >= ub || (k > 0 && v <= prev))) { p.bad = true; break; }
+                prev = v;
+                if (l) lower.put(v & mask, l);
+                const int64_t one_pos = (int64_t)(v >> l) + cur_len;
+                upper.unary((uint64_t)(one_pos - last_one - 1));
+                int64_t zeroes_before = last_one - cur_len + 1;
+                for (int64_t pos = last_one + (zeroes_before & ~((1LL << q) - 1)) + (1LL << q) - zeroes_before; pos < one_pos; pos += 1LL << q, zeroes_before += 1LL << q)
+                    pointers.put((uint64_t)(pos + 1), psize);
+                last_one = one_pos;
+                cur_len++;
+            }
+            if (p.bad) break;
+            p.graph.append(pointers); p.graph.append(lower); p.graph.append(upper);
+            put_delta(p.offs, p.graph.nbits - before);
+            p.bits_succ += pointers.nbits + lower.nbits + upper.nbits;
+            p.arcs += d;
+        }
+    });
+    for (auto& t : th) t.join();
+    LsbBuf graph;
+    BitBuf offs;
+    put_delta(offs, 0);
+    int64_t arcs = 0;
+    uint64_t bits_out = 0, bits_succ = 0;
+    for (Part& p : parts) {
+        if (p.bad) return -1;
+        if (parts.size() == 1) graph = std::move(p.graph); else { graph.append(p.graph); p.graph = LsbBuf(); }
+        offs.append(p.offs);
+        arcs += p.arcs; bits_out += p.bits_out; bits_succ += p.bits_succ;
+    }
+    const std::string base(basename);
+    {
+        FILE* f = fopen((base + ".graph").c_str(), "wb");
+        if (!f) return -4;
+        const uint64_t nw = (graph.nbits >> 6) + 1;   // close() always writes the buffer, :413-418
+        graph.w.resize((size_t)std::max<uint64_t>(nw, graph.w.size()), 0);
+        bool ok = true;
+        if (!big_endian) ok = fwrite(graph.w.data(), 8, (size_t)nw, f) == nw;
+        else for (uint64_t i = 0; i < nw && ok; i++) { const uint64_t v = __builtin_bswap64(graph.w[(size_t)i]); ok = fwrite(&v, 8, 1, f) == 1; }
+        if (fclose(f) != 0 || !ok) return -4;
+    }
+    if (!offs.write_file(base + ".offsets")) return -4;
+    FILE* f = fopen((base + ".properties").c_str(), "w");
+    if (!f) return -4;
+    fprintf(f, "#EFGraph properties\n#written by webgraph_b200 bvg_tools\n");
+    fprintf(f, "nodes=%d\narcs=%lld\n", n, (long long)arcs);
+    if (ub != (uint64_t)n) fprintf(f, "upperbound=%llu\n", (unsigned long long)ub);
+    fprintf(f, "quantum=%lld\nbyteorder=%s\n", 1LL << q, big_endian ? "BIG_ENDIAN" : "LITTLE_ENDIAN");
+    fprintf(f, "bitsforoutdegrees=%llu\nbitsforsuccessors=%llu\n", (unsigned long long)bits_out, (unsigned long long)bits_succ);
+    fprintf(f, "graphclass=it.unimi.dsi.webgraph.EFGraph\nversion=0\n");
+    fclose(f);
+    if (graph_bits) *graph_bits = (int64_t)graph.nbits;
     return 0;
 }
 

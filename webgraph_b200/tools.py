@@ -55,6 +55,7 @@ def lib():
                                              C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(StoreStats)]
         _lib.bvgt_write_codes.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         _lib.bvgt_write_codes.restype = C.c_int64
+        _lib.bvgt_store_ef.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
         _lib.bvgt_store_labels.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     return _lib
@@ -131,4 +132,17 @@ def store_labels(basename, underlying, off, values, kind, width=0, list_off=None
                                  kind, width, threads, C.byref(bits))
     if rc:
         raise ValueError("bvgt_store_labels failed: %d" % rc)
+    return int(bits.value)
+
+
+def store_ef(basename, off, succ, upper_bound=0, log2_quantum=8, big_endian=False, threads=1):
+    """EFGraph.store for a CSR graph (reference EFGraph.java:812-888; defaults :94, upper bound = n).  Returns the bits of the
+    graph stream."""
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    succ = np.ascontiguousarray(succ, dtype=np.int32)
+    bits = C.c_int64(0)
+    rc = lib().bvgt_store_ef(os.fsencode(basename), len(off) - 1, off.ctypes.data, succ.ctypes.data if len(succ) else None,
+                             upper_bound, log2_quantum, 1 if big_endian else 0, threads, C.byref(bits))
+    if rc:
+        raise ValueError("bvgt_store_ef failed: %d" % rc)
     return int(bits.value)
