@@ -214,6 +214,50 @@ def arc_labels(workdir, nodes=4_000_000, arcs=125_000_000, cpu_labels=20_000_000
         alg.close()
         del d_vals
         out[name] = res
+    # SURVEY 8 f4 (decode half): the same graph stored as an EFGraph (the reference's quasi-succinct format) beside its BVGraph
+    try:
+        from webgraph_b200.efgraph import EFGraph
+        ebase = base + "-ef"
+        ebits = tools.store_ef(ebase, off, succ, threads=os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        eg = EFGraph.load(ebase)
+        ef = {"graph_bits": ebits, "bits_per_arc": ebits / narcs, "load_s": time.perf_counter() - t0,
+              "what": "bvg_ef_scan_range / bvg_ef_decode_range (device CSR) of the same graph stored with EFGraph.store's layout (quantum 256)"}
+        d_off = torch.empty(nodes + 1, dtype=torch.int64, device="cuda")
+        d_out = torch.empty(narcs, dtype=torch.int32, device="cuda")
+        for what in ("scan", "decode"):
+            times = []
+            for it in range(6):
+                torch.cuda.synchronize()
+                ev[0].record()
+                if what == "scan":
+                    sres = eg.scanRange(0, nodes)
+                else:
+                    bvgraph._check(L.bvg_ef_decode_range(eg.handle, 0, nodes, d_off.data_ptr(), d_out.data_ptr(), narcs, 1))
+                ev[1].record()
+                torch.cuda.synchronize()
+                times.append(ev[0].elapsed_time(ev[1]))
+            ms = float(np.median(times[2:]))
+            byts = ebits / 8 + (4 * narcs if what == "decode" else 0)
+            ef[what] = {"ms": ms, "edges_per_s": narcs / (ms * 1e-3), "algorithmic_GBps": byts / (ms * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": byts / (ms * 1e-3) / 1e9 / peak}
+        bg = bvgraph.BVGraph.load(base)
+        times = []
+        for it in range(6):
+            torch.cuda.synchronize()
+            ev[0].record()
+            bres = bg.scanRange(0, nodes)
+            ev[1].record()
+            torch.cuda.synchronize()
+            times.append(ev[0].elapsed_time(ev[1]))
+        ef["bvgraph_scan_of_the_same_graph"] = {"ms": float(np.median(times[2:])), "bits_per_arc": st["graph_bits"] / narcs}
+        ef["scan_equals_bvgraph_scan"] = bool(sres == bres)
+        ef["decode_matches_csr"] = bool(np.array_equal(d_out.cpu().numpy(), succ) and np.array_equal(d_off.cpu().numpy(), off))
+        bg.close()
+        eg.close()
+        out["efgraph"] = ef
+    except Exception as e:
+        out["efgraph"] = {"error": repr(e)}
     return out
 
 
@@ -737,6 +781,7 @@ def main():
             other.update(b.other_configs())
             try:
                 other["arc_labels"] = arc_labels(args.workdir)
+                other["efgraph"] = other["arc_labels"].pop("efgraph", None)
             except Exception as e:
                 other["arc_labels"] = {"error": repr(e)}
     cpu = None

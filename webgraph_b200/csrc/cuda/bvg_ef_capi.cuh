@@ -87,18 +87,19 @@ int bvg_ef_open_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t
     if (cudaMemsetAsync(g->d_err, 0, sizeof(ErrWord), s) != cudaSuccess || cudaMemsetAsync(g->d_words + g->nwords, 0, 16, s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
     if (g->nwords && cudaMemcpyAsync(g->d_words, graph, (size_t)g->nwords * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
     if (big_endian && g->nwords) LAUNCH(k_bswap64, grid_for((int64_t)g->nwords, 256), 256, 0, s, g->d_words, g->nwords);
-    {
+    rc = [&]() -> int {   // the temporaries of this scope must be gone before a failure destroys the stream
         Tmp<int32_t> outdeg(s);
-        if (outdeg.alloc((size_t)std::max<int32_t>(nodes, 1)) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ENOMEM); }
+        if (outdeg.alloc((size_t)std::max<int32_t>(nodes, 1)) != cudaSuccess) { cudaGetLastError(); return BVG_ENOMEM; }
         if (nodes) LAUNCH(k_ef_outdegrees, grid_for(nodes, 256), 256, 0, s, g->dev(), 0, nodes, outdeg.p, g->d_err);
-        rc = device_exclusive_scan(s, outdeg.p, nodes, g->d_rowoff);
-        if (rc) return fail(rc);
+        const int r = device_exclusive_scan(s, outdeg.p, nodes, g->d_rowoff);
+        if (r) return r;
         int64_t total = 0;
-        if (cudaMemcpyAsync(&total, g->d_rowoff + nodes, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); return fail(BVG_ECUDA); }
+        if (cudaMemcpyAsync(&total, g->d_rowoff + nodes, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); return BVG_ECUDA; }
         const int e = ef_fetch_error(g);
-        if (e) return fail(e);
-        if (total != arcs) return fail(BVG_EFORMAT);   // the outdegrees do not add up to the arcs property
-    }
+        if (e) return e;
+        return total == arcs ? BVG_OK : BVG_EFORMAT;   // the outdegrees do not add up to the arcs property
+    }();
+    if (rc) return fail(rc);
     *out = g;
     return BVG_OK;
 }
