@@ -14,6 +14,8 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift)
     return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
 }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline int __ffs(int v) { return v == 0 ? 0 : __builtin_ctz((unsigned)v) + 1; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffsll(long long v) { return v == 0 ? 0 : __builtin_ctzll((unsigned long long)v) + 1; }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }

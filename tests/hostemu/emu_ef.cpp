@@ -23,6 +23,29 @@ extern "C" int emu_ef_decode(const uint64_t* words, uint64_t nwords, const uint6
     unsigned long long acc = 0;
     for (int64_t x = 0; x < n; x++) if (deg[(size_t)x]) acc ^= ef_decode_one(g, x, out + out_off[x], &err);
     if (err.code) return err.code;
+    // the warp path's per-lane pieces (one byte of upper bits per lane, ranks by a prefix over the 32 lanes), lane loop spelled out
+    std::vector<int32_t> again((size_t)out_off[n] + 1, -1);
+    unsigned long long acc2 = 0;
+    for (int64_t x = 0; x < n; x++) {
+        EfList e;
+        if (!ef_list(g, x, e) || e.d != deg[(size_t)x]) return -101;
+        if (e.d == 0) continue;
+        const uint64_t ulen = (uint64_t)e.d + 1 + ((uint64_t)upper_bound >> e.l);
+        int64_t carry = 0;
+        for (uint64_t base = 0; base < ulen && carry < e.d; base += 256) {
+            uint32_t bytes[32];
+            int64_t rank = carry;
+            for (int lane = 0; lane < 32; lane++) bytes[lane] = ef_upper_byte(g, e, ulen, base + (uint64_t)lane * 8);
+            for (int lane = 0; lane < 32; lane++) {
+                acc2 ^= ef_emit_byte(g, x, e, base + (uint64_t)lane * 8, bytes[lane], rank, again.data() + out_off[x]);
+                rank += __builtin_popcount(bytes[lane]);
+            }
+            carry = rank;
+        }
+        if (carry < e.d) return -102;
+    }
+    if (acc2 != acc) return -103;
+    for (int64_t j = 0; j < out_off[n]; j++) if (again[(size_t)j] != out[j]) return -104;
     *checksum = acc;
     return 0;
 }

@@ -1137,7 +1137,7 @@ int bvg_scan_memory(const uint8_t* graph, uint64_t graph_bytes, const uint8_t* o
     {   // bit-balanced cuts (as bvg_plan_shards), found on the device
         Tmp<int32_t> d_bounds(st[0]);
         if (d_bounds.alloc((size_t)pieces + 1) != cudaSuccess) { cleanup(); return BVG_ECUDA; }
-        LAUNCH(k_plan_cuts, 1, 64, 0, st[0], d_full, from, to, pieces, d_bounds.p);
+        LAUNCH(k_plan_cuts, 1, 64, 0, st[0], d_full, from, to, pieces, d_bounds.p, env_int("BVG_E2E_TAPER", 0, -(1 << 20), 1 << 20));
         if (cudaMemcpyAsync(bounds.data(), d_bounds.p, ((size_t)pieces + 1) * 4, cudaMemcpyDeviceToHost, st[0]) != cudaSuccess ||
             cudaStreamSynchronize(st[0]) != cudaSuccess) { cudaGetLastError(); cleanup(); return BVG_ECUDA; }
     }

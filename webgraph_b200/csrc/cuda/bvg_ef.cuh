@@ -5,7 +5,12 @@
 // (EFGraph.java:420-556, 1100-1145).  The stream is LSB-first in 64-bit words (LongWordBitReader, :892-1036); `.offsets` holds
 // delta-coded gaps (MSB-first, decoded by bvg_offsets.cuh).  Successor k is ((position of the k-th one) - k) << l | lower[k]:
 // selection in a bit vector, which the reference does with a running 64-bit window and here is
-//   * one thread per node for lists up to EF_HEAVY successors (the same window walk: ctz, clear lowest one), and
+//   * one thread per node for lists of up to EF_SMALL successors (the same window walk: ctz, clear lowest one);
+//   * one WARP per list up to EF_HEAVY: a step covers 256 upper bits, every lane takes one byte of them (about four ones at
+//     the format's density of one half), a warp scan of the popcounts gives each byte the rank of its first one, and the
+//     lanes emit their ones -- consecutive ranks land in consecutive lanes, so stores and lower-bit reads are contiguous.
+//     A warp owns 32 consecutive nodes: its lanes first walk their own small lists, then the warp goes through the
+//     medium ones among the 32 one after the other (geometry broadcast by shuffle);
 //   * one block per node above that: every thread takes a word of the upper bits, a block-wide exclusive scan of the
 //     popcounts gives each word the rank of its first one, and the ones are emitted in parallel.
 // There are no reference chains and no intervals: every list decodes on its own.
@@ -14,7 +19,8 @@
 
 namespace bvg {
 
-constexpr int32_t EF_HEAVY = 2048;
+constexpr int32_t EF_SMALL = 8;
+constexpr int32_t EF_HEAVY = 8192;
 constexpr int EF_BLOCK = 256;
 
 struct EfDev {
@@ -28,14 +34,22 @@ struct EfDev {
 
 __device__ __forceinline__ uint64_t ef_word(const EfDev& g, uint64_t i) { return g.w[i < g.nwords + 1 ? i : g.nwords + 1]; }
 
-// `width` bits at bit position pos (0 <= width <= 32 here).
+// `width` bits at bit position pos (0 <= width <= 32 here).  The long words are little-endian in device memory, so the
+// stream is just as well a stream of 32-bit words: bit p is bit p % 32 of 32-bit word p / 32 -- two 4-byte loads and a funnel
+// shift instead of 64-bit shifts.
 __device__ __forceinline__ uint32_t ef_bits(const EfDev& g, uint64_t pos, int width) {
     if (width == 0) return 0u;
-    const uint64_t i = pos >> 6;
-    const int s = (int)(pos & 63);
-    uint64_t v = ef_word(g, i) >> s;
-    if (s + width > 64) v |= ef_word(g, i + 1) << (64 - s);
-    return (uint32_t)(v & ((1ull << width) - 1ull));
+    const uint32_t* __restrict__ w32 = reinterpret_cast<const uint32_t*>(g.w);
+    uint64_t i = pos >> 5;
+    const uint64_t last = 2 * g.nwords + 2;   // the padding words are readable
+    i = i < last ? i : last;
+#ifdef BVG_HOST_EMULATION
+    const uint64_t two = (uint64_t)w32[i] | ((uint64_t)w32[i + 1] << 32);
+    const uint32_t v = (uint32_t)(two >> (pos & 31));
+#else
+    const uint32_t v = __funnelshift_r(w32[i], w32[i + 1], (uint32_t)pos & 31u);
+#endif
+    return width == 32 ? v : v & ((1u << width) - 1u);
 }
 
 // readGamma at *pos (:1002-1036): the number of zeros before the first one is the msb, then msb bits follow.
@@ -66,8 +80,8 @@ __device__ __forceinline__ bool ef_list(const EfDev& g, int64_t x, EfList& e) {
     if (d > 0x7fffffffull || pos > g.offsets[x + 1]) { e.d = 0; return false; }
     e.d = (int64_t)d;
     const uint64_t len = d + 1, ub = g.upper_bound;
-    const uint64_t q = ub / len;
-    e.l = q == 0 ? 0 : 63 - __clzll((long long)q);
+    const uint32_t q = (uint32_t)ub / (uint32_t)len;   // both below 2^31 + 1: a 32-bit division
+    e.l = q == 0 ? 0 : 31 - __clz((int)q);
     const uint64_t ulen = len + (ub >> e.l);
     const int psize = ulen <= 1 ? 0 : 64 - __clzll((long long)(ulen - 1));
     const uint64_t npointers = (ub >> e.l) >> g.log2_quantum;
@@ -87,10 +101,8 @@ __device__ inline void ef_outdegree_one(const EfDev& g, int64_t x, int32_t* __re
     outdeg[at] = (int32_t)d;
 }
 
-// One thread, one list (d <= EF_HEAVY or any d on the host): out may be null (fold only).  Returns the XOR fold.
-__device__ inline unsigned long long ef_decode_one(const EfDev& g, int64_t x, int32_t* __restrict__ out, ErrWord* err) {
-    EfList e;
-    if (!ef_list(g, x, e)) { report(err, E_IO, (int)x, g.offsets[x]); return 0; }
+// One thread, one list whose geometry is known: out may be null (fold only).  Returns the XOR fold.
+__device__ inline unsigned long long ef_walk(const EfDev& g, int64_t x, const EfList& e, int32_t* __restrict__ out, ErrWord* err) {
     unsigned long long acc = 0;
     uint64_t curr = e.upper_start >> 6;
     uint64_t window = ef_word(g, curr) & (~0ull << (e.upper_start & 63));
@@ -105,6 +117,35 @@ __device__ inline unsigned long long ef_decode_one(const EfDev& g, int64_t x, in
         const uint32_t v = (uint32_t)(upper << e.l) | ef_bits(g, e.lower_start + (uint64_t)e.l * (uint64_t)k, e.l);
         if (out) out[k] = (int32_t)v;
         acc ^= ef_arc_hash(x, v);
+    }
+    return acc;
+}
+
+__device__ inline unsigned long long ef_decode_one(const EfDev& g, int64_t x, int32_t* __restrict__ out, ErrWord* err) {
+    EfList e;
+    if (!ef_list(g, x, e)) { report(err, E_IO, (int)x, g.offsets[x]); return 0; }
+    return ef_walk(g, x, e, out, err);
+}
+
+// The warp path, one lane's share of a step: the byte of upper bits at bit `at` (relative to upper_start, clipped to ulen).
+__device__ __forceinline__ uint32_t ef_upper_byte(const EfDev& g, const EfList& e, uint64_t ulen, uint64_t at) {
+    if (at >= ulen) return 0u;
+    uint32_t b = ef_bits(g, e.upper_start + at, 8);
+    const uint64_t left = ulen - at;
+    if (left < 8) b &= (1u << left) - 1u;
+    return b;
+}
+// Emits the ones of `byte` (first one has rank k): values ((at + j) - rank) << l | lower[rank].
+__device__ __forceinline__ unsigned long long ef_emit_byte(const EfDev& g, int64_t x, const EfList& e, uint64_t at, uint32_t byte, int64_t k,
+                                                           int32_t* __restrict__ out) {
+    unsigned long long acc = 0;
+    while (byte && k < e.d) {
+        const int j = __ffs((int)byte) - 1;
+        byte &= byte - 1;
+        const uint32_t v = (uint32_t)((at + (uint64_t)j - (uint64_t)k) << e.l) | ef_bits(g, e.lower_start + (uint64_t)e.l * (uint64_t)k, e.l);
+        if (out) out[k] = (int32_t)v;
+        acc ^= ef_arc_hash(x, v);
+        k++;
     }
     return acc;
 }
@@ -129,33 +170,76 @@ __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode(EfDev g, int32_t from, i
                                                         int32_t* __restrict__ heavy, int32_t* __restrict__ nheavy,
                                                         unsigned long long* __restrict__ result, ErrWord* err) {
     const int64_t x = (int64_t)from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     unsigned long long acc = 0, arcs = 0;
+    EfList e;
+    e.d = 0; e.l = 0; e.lower_start = e.upper_start = 0;
+    int64_t a = 0;
+    bool ok = false;
     if (x < to) {
-        const int64_t a = rowoff[x - from], d = rowoff[x - from + 1] - a;
-        if (d > EF_HEAVY) heavy[atomicAdd(nheavy, 1)] = (int32_t)x;
-        else if (d > 0) { acc = ef_decode_one(g, x, out ? out + (a - rowoff[0]) : nullptr, err); arcs = (unsigned long long)d; }
+        a = rowoff[x - from];
+        const int64_t d = rowoff[x - from + 1] - a;
+        if (d > 0) {
+            ok = ef_list(g, x, e) && e.d == d;
+            if (!ok) report(err, E_IO, (int)x, g.offsets[x]);
+        }
+    }
+    if (ok) {
+        if (e.d > EF_HEAVY) heavy[atomicAdd(nheavy, 1)] = (int32_t)x;
+        else arcs = (unsigned long long)e.d;
+        if (e.d <= EF_SMALL) acc = ef_walk(g, x, e, out ? out + (a - rowoff[0]) : nullptr, err);
+    }
+    // the medium lists of this warp's 32 nodes, one after the other, all lanes on each
+    unsigned med = __ballot_sync(0xffffffffu, ok && e.d > EF_SMALL && e.d <= EF_HEAVY);
+    while (med) {
+        const int src = __ffs((int)med) - 1;
+        med &= med - 1;
+        EfList w;
+        w.d = __shfl_sync(0xffffffffu, e.d, src);
+        w.l = __shfl_sync(0xffffffffu, e.l, src);
+        w.lower_start = __shfl_sync(0xffffffffu, e.lower_start, src);
+        w.upper_start = __shfl_sync(0xffffffffu, e.upper_start, src);
+        const int64_t wa = __shfl_sync(0xffffffffu, a, src);
+        const int64_t wx = x - lane + src;
+        int32_t* o = out ? out + (wa - rowoff[0]) : nullptr;
+        const uint64_t ulen = (uint64_t)w.d + 1 + ((uint64_t)g.upper_bound >> w.l);
+        int64_t carry = 0;
+        for (uint64_t base = 0; base < ulen && carry < w.d; base += 256) {
+            const uint64_t at = base + (uint64_t)lane * 8;
+            const uint32_t byte = ef_upper_byte(g, w, ulen, at);
+            const int pc = __popc(byte);
+            int inc = pc;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, s); if (lane >= s) inc += t; }
+            acc ^= ef_emit_byte(g, wx, w, at, byte, carry + inc - pc, o);
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (carry < w.d && lane == 0) report(err, E_IO, (int)wx, g.offsets[wx]);   // fewer ones than successors
     }
     if (result) ef_block_fold(arcs, acc, result);
 }
 
-// One block per heavy list: words of the upper bits in tiles of EF_BLOCK, ranks by a block scan of the popcounts.
+// EF_SPLIT blocks per heavy list.  Every block of a list goes through all tiles of EF_BLOCK upper words (cheap: popcounts, the
+// words sit in L2 after the first block) to keep the running rank, and emits the ones of every EF_SPLIT-th tile only: the
+// emission -- a dependent chain of ~32 successors per word and thread -- is what takes the time, and it is spread S ways.
+constexpr int EF_SPLIT = 8;
 __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode_heavy(EfDev g, int32_t from, const int32_t* __restrict__ heavy, const int64_t* __restrict__ rowoff,
                                                               int32_t* __restrict__ out, unsigned long long* __restrict__ result, ErrWord* err) {
     __shared__ int32_t warp_sums[EF_BLOCK / 32];
-    __shared__ int64_t carry;
-    const int64_t x = heavy[blockIdx.x];
+    const int64_t x = heavy[blockIdx.x / EF_SPLIT];
+    const int part = blockIdx.x % EF_SPLIT;
     EfList e;
     const bool ok = ef_list(g, x, e);
     const int64_t a = rowoff[x - from];
     int32_t* o = out ? out + (a - rowoff[0]) : nullptr;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    if (!ok) { if (threadIdx.x == 0) report(err, E_IO, (int)x, g.offsets[x]); return; }
+    if (!ok) { if (threadIdx.x == 0 && part == 0) report(err, E_IO, (int)x, g.offsets[x]); return; }
     const uint64_t first_word = e.upper_start >> 6;
     const uint64_t ulen = (uint64_t)e.d + 1 + ((uint64_t)g.upper_bound >> e.l);
     const uint64_t last_word = (e.upper_start + ulen - 1) >> 6;
     unsigned long long acc = 0, arcs = 0;
-    for (uint64_t base = first_word; base <= last_word; base += EF_BLOCK) {
+    int64_t carry = 0;
+    int tile = 0;
+    for (uint64_t base = first_word; base <= last_word && carry < e.d; base += EF_BLOCK, tile++) {
         const uint64_t wi = base + threadIdx.x;
         uint64_t word = 0;
         if (wi <= last_word) {
@@ -163,7 +247,6 @@ __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode_heavy(EfDev g, int32_t f
             if (wi == first_word) word &= ~0ull << (e.upper_start & 63);
         }
         const int pc = __popcll(word);
-        // block exclusive scan of pc
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         int inc = pc;
 #pragma unroll
@@ -173,22 +256,22 @@ __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode_heavy(EfDev g, int32_t f
         int wbase = 0, tot = 0;
 #pragma unroll
         for (int wv = 0; wv < EF_BLOCK / 32; wv++) { const int sv = warp_sums[wv]; if (wv < wid) wbase += sv; tot += sv; }
-        int64_t k = carry + wbase + inc - pc;
-        while (word && k < e.d) {
-            const uint64_t p = wi * 64 + (uint64_t)(__ffsll((long long)word) - 1);
-            word &= word - 1;
-            const uint32_t v = (uint32_t)((p - (uint64_t)k - e.upper_start) << e.l) | ef_bits(g, e.lower_start + (uint64_t)e.l * (uint64_t)k, e.l);
-            if (o) o[k] = (int32_t)v;
-            acc ^= ef_arc_hash(x, v);
-            arcs++;
-            k++;
+        __syncthreads();
+        if (tile % EF_SPLIT == part) {
+            int64_t k = carry + wbase + inc - pc;
+            while (word && k < e.d) {
+                const uint64_t p = wi * 64 + (uint64_t)(__ffsll((long long)word) - 1);
+                word &= word - 1;
+                const uint32_t v = (uint32_t)((p - (uint64_t)k - e.upper_start) << e.l) | ef_bits(g, e.lower_start + (uint64_t)e.l * (uint64_t)k, e.l);
+                if (o) o[k] = (int32_t)v;
+                acc ^= ef_arc_hash(x, v);
+                arcs++;
+                k++;
+            }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += tot;
-        __syncthreads();
-        if (carry > e.d) break;   // the terminator has been passed: nothing but zeros follows
+        carry += tot;   // every thread keeps the same running rank
     }
-    if (threadIdx.x == 0 && carry < e.d) report(err, E_IO, (int)x, g.offsets[x]);   // fewer ones than successors
+    if (threadIdx.x == 0 && part == 0 && carry < e.d) report(err, E_IO, (int)x, g.offsets[x]);   // fewer ones than successors
     if (result) ef_block_fold(arcs, acc, result);
 }
 #endif

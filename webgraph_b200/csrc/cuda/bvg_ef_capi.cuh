@@ -157,7 +157,7 @@ static int ef_run(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* d_off
     int32_t nh = 0;
     CK(cudaMemcpyAsync(&nh, nheavy.p, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (nh > 0) LAUNCH(k_ef_decode_heavy, (unsigned)nh, EF_BLOCK, 0, s, g->dev(), from, heavy.p, g->d_rowoff + from, d_out, d_result, g->d_err);
+    if (nh > 0) LAUNCH(k_ef_decode_heavy, (unsigned)nh * EF_SPLIT, EF_BLOCK, 0, s, g->dev(), from, heavy.p, g->d_rowoff + from, d_out, d_result, g->d_err);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));   // heavy / nheavy die with this scope
     return BVG_OK;

@@ -74,13 +74,22 @@ __global__ void k_depth(GraphDev g, int32_t* __restrict__ depth, int32_t* __rest
 }
 
 // Bit-balanced cuts of the node range [from, to) (bvg_plan_shards on the device): bounds[i] = first node whose record starts
-// at or after offsets[from] + i * bits / pieces; one thread per cut.
-__global__ void k_plan_cuts(const uint64_t* __restrict__ offsets, int32_t from, int32_t to, int32_t pieces, int32_t* __restrict__ bounds) {
+// at or after offsets[from] + i * bits / pieces; one thread per cut.  taper != 0: the pieces shrink (> 0) or grow (< 0) linearly instead of
+// being equal (bvg_scan_memory; measured).
+__global__ void k_plan_cuts(const uint64_t* __restrict__ offsets, int32_t from, int32_t to, int32_t pieces, int32_t* __restrict__ bounds, int32_t taper = 0) {
     const uint64_t first = offsets[from], total = offsets[to] - first;
     for (int32_t i = threadIdx.x; i <= pieces; i += blockDim.x) {
         if (i == 0) { bounds[0] = from; continue; }
         if (i == pieces) { bounds[pieces] = to; continue; }
-        const uint64_t target = first + total / (uint64_t)pieces * (uint64_t)i;
+        uint64_t target = first + total / (uint64_t)pieces * (uint64_t)i;
+        if (taper != 0) {
+            // taper > 0: weights taper + pieces - 1, ..., taper (shrinking pieces); taper < 0: |taper|, ..., |taper| + pieces - 1 (growing)
+            const uint64_t t = (uint64_t)(taper > 0 ? taper : -taper);
+            const uint64_t wsum = (uint64_t)pieces * t + (uint64_t)pieces * (uint64_t)(pieces - 1) / 2;
+            const uint64_t wi = taper > 0 ? (uint64_t)i * t + (uint64_t)i * (uint64_t)(2 * pieces - 1 - i) / 2
+                                          : (uint64_t)i * t + (uint64_t)i * (uint64_t)(i - 1) / 2;
+            target = first + (uint64_t)((double)total * ((double)wi / (double)wsum));
+        }
         int32_t lo = from, hi = to;  // first node with offsets[node] >= target
         while (lo < hi) {
             const int32_t mid = lo + (hi - lo) / 2;
