@@ -2225,7 +2225,13 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
         CK(cudaMemsetAsync(mask.p, 0, (size_t)nn, s));
         CK(cudaMemsetAsync(nheavy.p, 0, 4, s));
     }
-    if (nx) LAUNCH(k_query_sizes, grid_for(nx, 256), 256, 0, s, gd, xs_dev, nx, dq.p, need.p, g->long_d, mask.p, heavy.p, nheavy.p);
+    // A batch that asks for a sizeable part of the graph goes through the range kernels as a whole (every chain marked, rows
+    // gathered afterwards): their length-sorted schedules and lean walkers decode an arc several times cheaper than k_random's
+    // one thread per query, which is the better deal only while the batch touches a small part of the schedules (measured on
+    // the 32 M-node graph, profiles/c4_sweep.py: 10 M queries 27.2 -> 13.0 ms, 3 M 10.2 -> 8.0, 1 M 4.1 -> 4.4, 100 k 1.6 -> 1.8).
+    static const int range_pct = env_int("BVG_RANDOM_RANGE_PCT", 5, 0, 100000);   // batch size in percent of the nodes from which on
+    const bool all_range = split_long && nx > 0 && (double)nx * 100.0 >= (double)range_pct * (double)nn;
+    if (nx) LAUNCH(k_query_sizes, grid_for(nx, 256), 256, 0, s, gd, xs_dev, nx, dq.p, need.p, all_range ? -1 : g->long_d, mask.p, heavy.p, nheavy.p);
     int rc = device_exclusive_scan(s, dq.p, nx, off_dev);
     if (rc) return rc;
     rc = device_exclusive_scan(s, need.p, nx, scratch_off.p);
@@ -2262,7 +2268,7 @@ int bvg_successors_batch(const bvg_graph* g, const int32_t* xs, int64_t nx, int6
         if (rc) return rc;
         rc = run_ordered_decode(g, exec_of(g), g->node_lo, g->node_hi, g->node_lo, rm);
         if (rc) return rc;
-        LAUNCH_P(g, "k_gather_rows", k_gather_rows, 148 * 8, 256, 0, s, gd, xs_dev, nx, heavy.p, off_dev, out_dev, rm);
+        LAUNCH_P(g, "k_gather_rows", k_gather_rows, (unsigned)std::min<int64_t>(148 * env_int("BVG_GATHER_BLOCKS", 32, 1, 1024), std::max<int64_t>(1, (nx + 7) / 8)), 256, 0, s, gd, xs_dev, nx, heavy.p, off_dev, out_dev, rm);
     }
     CK(cudaGetLastError());
     if (on_device) return BVG_OK;
