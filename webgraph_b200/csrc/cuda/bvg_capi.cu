@@ -236,7 +236,12 @@ struct bvg_graph {
     int64_t* d_long_cum = nullptr;
     int64_t n_items_resid = 0, n_items_extras = 0;
     std::vector<int64_t> n_items_merge;  // [level]
-    ItemMap item_map(int family) const { return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong }; }
+    int32_t* d_long_hint = nullptr;        // search hints of every family (ItemMap::hint), family f at hint_off[f]
+    std::vector<int64_t> hint_off;
+    ItemMap item_map(int family) const {
+        return ItemMap{ d_long_cum + (size_t)family * ((size_t)nlong + 1), nlong,
+                        d_long_hint && (size_t)family < hint_off.size() ? d_long_hint + hint_off[(size_t)family] : nullptr };
+    }
     mutable std::vector<int64_t> h_long_cum;   // the same on the host (fetched on first use): which items belong to the long records of a node range
     size_t long_cum_entries = 0;
     std::vector<int64_t> fam_total;    // items of every family
@@ -641,6 +646,17 @@ static int build_long_index(bvg_graph* g) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     g->fam_total = fam_total;
+    if (env_int("BVG_ITEM_HINTS", 1, 0, 1)) {   // search hints for the work items of every family
+        std::vector<int64_t> hoff((size_t)fam_spec + 2, 0);
+        for (int f = 0; f <= fam_spec; f++) hoff[(size_t)f + 1] = hoff[(size_t)f] + (fam_total[(size_t)f] >> ITEM_HINT_SHIFT) + 2;
+        CK(dev_alloc((void**)&g->d_long_hint, (size_t)hoff[(size_t)fam_spec + 1] * 4, g->stream));
+        for (int f = 0; f <= fam_spec; f++) {
+            const int64_t cnt = hoff[(size_t)f + 1] - hoff[(size_t)f];
+            LAUNCH(k_item_hints, grid_for(cnt, 256), 256, 0, s, g->d_long_cum + (size_t)f * stride, (int32_t)nl, fam_total[(size_t)f], g->d_long_hint + hoff[(size_t)f], cnt);
+        }
+        hoff.pop_back();
+        g->hint_off = hoff;
+    }
     const int64_t cb = h_tot[0], iv = h_tot[1], seg = fam_total[0], tmp = 2 * h_tot[2], scan = 3 * h_tot[3];
     CK(dev_alloc((void**)&g->d_cb_cum, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
     CK(dev_alloc((void**)&g->d_cb_ppos, (size_t)std::max<int64_t>(cb, 1) * 4, g->stream));
@@ -955,7 +971,7 @@ static void destroy(bvg_graph* g) {
     // to the driver, which is what makes open-scan-close cycles cheap
     void* ptrs[] = { g->d_words, g->d_offsets, g->d_outdeg, g->d_ref, g->d_depth, g->d_rowoff, g->d_err, g->d_halo_lists, g->d_halo_off,
                      g->d_tiles, g->d_tile_order, g->d_stream_entries, g->d_order_e, g->d_order_m, g->d_rec_e, g->d_rec_m, g->d_is_parent, g->d_long_nodes, g->d_copied, g->d_long_meta, g->d_cb_cum, g->d_cb_ppos,
-                     g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum };
+                     g->d_iv_cum, g->d_iv_left, g->d_seg_pos, g->d_seg_val, g->d_long_cum, g->d_long_hint };
     for (void* p : ptrs) if (p) dev_free(p, g->stream);
     cudaStreamSynchronize(g->stream);
     if (g->aux) { cudaStreamSynchronize(g->aux); cudaStreamDestroy(g->aux); cudaEventDestroy(g->ev_fork); cudaEventDestroy(g->ev_join); }
@@ -1554,8 +1570,10 @@ static LongSlice long_slice(const bvg_graph* g, int family, int32_t lo, int32_t 
     const size_t l0 = (size_t)(std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), lo) - g->h_long_nodes.begin());
     const size_t l1 = (size_t)(std::lower_bound(g->h_long_nodes.begin(), g->h_long_nodes.end(), to) - g->h_long_nodes.begin());
     const size_t base = (size_t)family * ((size_t)g->nlong + 1);
-    sl.li.meta += l0;
-    sl.im.cum += l0; sl.im.nlong = (int32_t)(l1 - l0);
+    if (!sl.im.hint) {   // without search hints: narrow the search to the slice's records (the hints hold absolute record numbers)
+        sl.li.meta += l0;
+        sl.im.cum += l0; sl.im.nlong = (int32_t)(l1 - l0);
+    }
     sl.item0 = g->h_long_cum[base + l0];
     sl.end = g->h_long_cum[base + l1];
     return sl;

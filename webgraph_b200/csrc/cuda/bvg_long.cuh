@@ -344,11 +344,21 @@ __device__ void merge_chunk(const A& a, ValueOf value_of, const int32_t* __restr
 // Work items of every per-scan kernel are (long record, part) pairs.  They are not listed: item i belongs to the record l
 // with cum[l] <= i < cum[l + 1] (cum = running item count per record, nlong + 1 entries built at open), found by
 // binary search; a list would cost one host-side push per 128 successors of every long record at every open.
+// hint (may be null): hint[j] = record of item j << ITEM_HINT_SHIFT, one more entry than needed past the last item: the
+// search then starts in the handful of records those 64 items span instead of in all of them (20 dependent steps for 10^6
+// long records, most of them the same for every thread but each an L1 / L2 round trip).
+constexpr int ITEM_HINT_SHIFT = 6;
 struct ItemMap {
     const int64_t* __restrict__ cum;
     int32_t nlong;
+    const int32_t* __restrict__ hint;
     __device__ __forceinline__ void find(int64_t i, int32_t& l, int32_t& part) const {
         int32_t lo = 0, hi = nlong;  // invariant: cum[lo] <= i < cum[hi]
+        if (hint) {
+            lo = hint[i >> ITEM_HINT_SHIFT];
+            const int32_t h = hint[(i >> ITEM_HINT_SHIFT) + 1] + 1;
+            hi = h < nlong ? h : nlong;
+        }
         while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
             if (cum[mid] <= i) lo = mid; else hi = mid;
@@ -356,6 +366,20 @@ struct ItemMap {
         l = lo; part = (int32_t)(i - cum[lo]);
     }
 };
+
+#ifndef BVG_HOST_EMULATION
+// hint[j] for j = 0 .. count - 1 (count = (total >> ITEM_HINT_SHIFT) + 2); items past the end map to the last record.
+__global__ void k_item_hints(const int64_t* __restrict__ cum, int32_t nlong, int64_t total, int32_t* __restrict__ hint, int64_t count) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int64_t i = j << ITEM_HINT_SHIFT;
+    if (i >= total) { hint[j] = nlong > 0 ? nlong - 1 : 0; return; }
+    ItemMap im{ cum, nlong, nullptr };
+    int32_t l, part;
+    im.find(i, l, part);
+    hint[j] = l;
+}
+#endif
 
 template <bool DEF>
 __global__ void k_long_count(GraphDev g, const int32_t* __restrict__ long_nodes, int32_t nlong, const uint8_t* __restrict__ is_parent,
