@@ -1023,15 +1023,20 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 //   1/2          512/128/128  3.30   256/64/64   3.16   128/32/32 3.19
 //   1/4          256/64/64    1.91   128/64/64   1.83   96/32/32  1.74
 //   1/8          1024/128/128 2.44   128/64/64   1.15   96/32/32  1.03   64/16/16 0.99   64/24/24 0.95   48/16/16 1.01
+// and again with the search hints of the work items (ItemMap::hint), which make fine items cheap:
+//   whole graph  512/32/32 5.58   256/32/32 5.61   256/16/16 5.21   256/12/12 5.23   192/16/16 5.25   128/16/16 5.36
+//   1/2          256/32/32 3.10   128/32/32 3.06   128/16/16 2.82   192/16/16 2.85   96/16/16 2.87
+//   1/4          96/32/32  1.70   96/16/16  1.57   64/24/24  1.57   64/16/16  1.59   48/16/16 1.63
+//   1/8          64/24/24  0.896  64/16/16  0.909  48/16/16  0.918  32/16/16  0.955
 // one_shot: the graph object lives for a single scan (bvg_scan_memory), so the index of the long records is paid per scan and
 // a finer split costs more to build than it saves.
 static void choose_long_threshold(bvg_graph* g, int32_t from, int32_t to, bool one_shot = false) {
     const double arcs = (double)g->m_total * (double)(to - from) / (double)std::max<int32_t>(g->n_total, 1);
     int32_t d, part;
     if (one_shot) { d = env_int("BVG_ONESHOT_D", 512, 2, 1 << 30); part = env_int("BVG_ONESHOT_PART", 128, 1, 1 << 20); }
-    else if (arcs > 7.5e8) { d = 512; part = 32; }
-    else if (arcs > 3.7e8) { d = 256; part = 32; }
-    else if (arcs > 1.8e8) { d = 96; part = 32; }
+    else if (arcs > 7.5e8) { d = 256; part = 16; }
+    else if (arcs > 3.7e8) { d = 128; part = 16; }
+    else if (arcs > 1.8e8) { d = 96; part = 16; }
     else { d = 64; part = 24; }
     g->long_d = env_int("BVG_LONG_D", d, 2, 1 << 30);
     g->long_seg = env_int("BVG_LONG_SEG", part, 1, 1 << 20);
