@@ -5,7 +5,7 @@
 // (EFGraph.java:420-556, 1100-1145).  The stream is LSB-first in 64-bit words (LongWordBitReader, :892-1036); `.offsets` holds
 // delta-coded gaps (MSB-first, decoded by bvg_offsets.cuh).  Successor k is ((position of the k-th one) - k) << l | lower[k]:
 // selection in a bit vector, which the reference does with a running 64-bit window and here is
-//   * one thread per node for lists of up to EF_SMALL successors (the same window walk: ctz, clear lowest one);
+//   * one thread per node for lists of up to EF_SMALL = 64 successors (the same window walk: ctz, clear lowest one);
 //   * one WARP per list up to EF_HEAVY: a step covers 256 upper bits, every lane takes one byte of them (about four ones at
 //     the format's density of one half), a warp scan of the popcounts gives each byte the rank of its first one, and the
 //     lanes emit their ones -- consecutive ranks land in consecutive lanes, so stores and lower-bit reads are contiguous.
@@ -19,7 +19,7 @@
 
 namespace bvg {
 
-constexpr int32_t EF_SMALL = 8;
+constexpr int32_t EF_SMALL = 64;   // measured (117 M arcs, scan): 4: 1.86 ms, 8: 1.74, 16: 1.53, 32: 1.23, 64: 1.10, 96: 1.19, 128: 1.30, 256: 1.63, 1024: 2.44
 constexpr int32_t EF_HEAVY = 8192;
 constexpr int EF_BLOCK = 256;
 
@@ -168,7 +168,7 @@ __device__ __forceinline__ void ef_block_fold(unsigned long long arcs, unsigned 
 // heavy[] for k_ef_decode_heavy.  result (arcs, xor) may be null; out may be null (scan).
 __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode(EfDev g, int32_t from, int32_t to, const int64_t* __restrict__ rowoff, int32_t* __restrict__ out,
                                                         int32_t* __restrict__ heavy, int32_t* __restrict__ nheavy,
-                                                        unsigned long long* __restrict__ result, ErrWord* err) {
+                                                        unsigned long long* __restrict__ result, ErrWord* err, int32_t small = EF_SMALL) {
     const int64_t x = (int64_t)from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     unsigned long long acc = 0, arcs = 0;
@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode(EfDev g, int32_t from, i
     if (ok) {
         if (e.d > EF_HEAVY) heavy[atomicAdd(nheavy, 1)] = (int32_t)x;
         else arcs = (unsigned long long)e.d;
-        if (e.d <= EF_SMALL) acc = ef_walk(g, x, e, out ? out + (a - rowoff[0]) : nullptr, err);
+        if (e.d <= small) acc = ef_walk(g, x, e, out ? out + (a - rowoff[0]) : nullptr, err);
     }
     // the medium lists of this warp's 32 nodes, one after the other, all lanes on each
-    unsigned med = __ballot_sync(0xffffffffu, ok && e.d > EF_SMALL && e.d <= EF_HEAVY);
+    unsigned med = __ballot_sync(0xffffffffu, ok && e.d > small && e.d <= EF_HEAVY);
     while (med) {
         const int src = __ffs((int)med) - 1;
         med &= med - 1;

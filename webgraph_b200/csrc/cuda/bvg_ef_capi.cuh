@@ -153,7 +153,7 @@ static int ef_run(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* d_off
     CK(heavy.alloc((size_t)std::max<int64_t>(1, g->m / EF_HEAVY + 1)));
     CK(nheavy.alloc(1));
     CK(cudaMemsetAsync(nheavy.p, 0, 4, s));
-    LAUNCH(k_ef_decode, grid_for(cnt, EF_BLOCK), EF_BLOCK, 0, s, g->dev(), from, to, g->d_rowoff + from, d_out, heavy.p, nheavy.p, d_result, g->d_err);
+    LAUNCH(k_ef_decode, grid_for(cnt, EF_BLOCK), EF_BLOCK, 0, s, g->dev(), from, to, g->d_rowoff + from, d_out, heavy.p, nheavy.p, d_result, g->d_err, env_int("BVG_EF_SMALL", EF_SMALL, 0, EF_HEAVY));
     int32_t nh = 0;
     CK(cudaMemcpyAsync(&nh, nheavy.p, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
