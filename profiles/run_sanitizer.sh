@@ -11,8 +11,8 @@ for tool in memcheck racecheck synccheck initcheck; do
   timeout 1500 compute-sanitizer --tool $tool $extra --print-limit 20 --error-exitcode 99 \
       python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$SUBSET" > gpurun_out/${TAG}_${tool}.txt 2>&1
   echo "[$tool] exit $? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/${TAG}_${tool}.txt | tr '\n' ' ')"
-  # the label stream (gamma / fixed / list labels, shards, device buffers) and the HyperBall iteration
+  # the label stream (gamma / fixed / list labels, shards, device buffers), the HyperBall iteration, EFGraph, random access and cursors
   timeout 1500 compute-sanitizer --tool $tool $extra --print-limit 20 --error-exitcode 99 \
-      python -m pytest tests/test_labels.py tests/test_gpu_parity.py -x -q -m gpu -k "test_gpu_labels_match_the_oracle or test_gpu_labels_on_shards or test_fused_consumer_hyperball_step" > gpurun_out/${TAG}_${tool}_f.txt 2>&1
-  echo "[$tool, labels + hyperball] exit $? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/${TAG}_${tool}_f.txt | tr '\n' ' ')"
+      python -m pytest tests/test_labels.py tests/test_efgraph.py tests/test_gpu_parity.py -x -q -m gpu -k "test_gpu_labels_match_the_oracle or test_gpu_labels_on_shards or test_fused_consumer_hyperball_step or test_gpu_efgraph_matches_csr or test_gpu_efgraph_loader_errors or test_cnr2000_random_access_all_nodes or test_cnr2000_node_iterator" > gpurun_out/${TAG}_${tool}_f.txt 2>&1
+  echo "[$tool, labels + hyperball + efgraph] exit $? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/${TAG}_${tool}_f.txt | tr '\n' ' ')"
 done
