@@ -722,7 +722,7 @@ class Bench:
         L, bvgraph = self.L, self.bvgraph
         res = {}
         nodes = self.n_total
-        for k in (8, 4, 8):   # the first round warms the pinned batch buffers of 8 cursors
+        for k in (16, 8, 4, 8, 16):   # the first round warms the pinned batch buffers of 16 cursors
             step = (nodes + k - 1) // k
 
             def drain(i):

@@ -14,7 +14,7 @@
  * the device decodes the next batch while Java iterates the current one).  A batch reaches Java as two direct buffers
  * over that pinned memory -- no JNI call per node, no array copy per batch; successors() reads straight from the buffer,
  * successorArray() makes the one copy its int[] contract asks for.  Iterators obtained from splitNodeIterators() run
- * concurrently, one per thread (measured in C with bvg_cursor_drain: 7.5 G edges/s with 8 threads on a 16-core host).
+ * concurrently, one per thread (measured in C with bvg_cursor_drain: 8.0 / 10.5 G edges/s with 8 / 16 threads on a 16-core host).
  */
 package it.unimi.dsi.webgraph.b200;
 

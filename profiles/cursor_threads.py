@@ -28,8 +28,8 @@ def run(k, nodes):
     arcs = sum(r[0] for r in res); cs = 0
     for r in res: cs ^= r[1]
     return arcs, cs, dt
-run(8, nodes)  # warm: pinned buffers, schedules
-for k in (1, 2, 4, 8, 16):
+run(16, nodes)  # warm: pinned buffers of 16 cursors, schedules
+for k in (1, 2, 4, 8, 16, 12, 16):
     arcs, cs, dt = run(k, nodes)
     ok = (arcs, cs) == (b.m_total, int(b.st["xor_checksum"]))
     print("%2d threads: %.2f G edges/s (%d arcs in %.1f ms) %s" % (k, arcs / dt / 1e9, arcs, dt * 1e3, "checksum ok" if ok else "MISMATCH"), flush=True)
