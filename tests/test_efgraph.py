@@ -254,3 +254,41 @@ def test_gpu_efgraph_loader_errors(tmp_path):
         EFGraph.load(base)
     with pytest.raises(IOError):
         EFGraph.load(str(tmp_path / "nothing"))
+
+
+@pytest.mark.gpu
+def test_gpu_efgraph_corrupted_streams_fail_cleanly(tmp_path):
+    """Random byte flips in .graph: every call returns (an error or lists inside the node range is not promised, memory safety
+    is), and the device keeps working afterwards."""
+    from webgraph_b200 import bvgraph
+    from webgraph_b200.efgraph import EFGraph
+    off, succ = graphs.copy_heavy(3000, seed=11)[:2]
+    base, ub, bits = store(tmp_path, "c", off, succ)
+    data = bytearray(open(base + ".graph", "rb").read())
+    rng = np.random.default_rng(3)
+    outcomes = set()
+    for trial in range(12):
+        bad = bytearray(data)
+        for p in rng.integers(0, len(bad), 1 + trial % 4):
+            bad[p] ^= 1 << int(rng.integers(0, 8))
+        with open(base + ".graph", "wb") as f:
+            f.write(bad)
+        try:
+            g = EFGraph.load(base)
+        except (IOError, ValueError, bvgraph.FormatError) as e:
+            outcomes.add(type(e).__name__)
+            continue
+        try:
+            g.decodeRange(0, g.numNodes())
+            g.scanRange(0, g.numNodes())
+            outcomes.add("decoded")
+        except (IOError, bvgraph.FormatError) as e:
+            outcomes.add(type(e).__name__)
+        g.close()
+    assert outcomes   # something happened, nothing crashed
+    with open(base + ".graph", "wb") as f:
+        f.write(data)
+    g = EFGraph.load(base)
+    o, s = g.decodeRange(0, g.numNodes())
+    assert np.array_equal(o, off) and np.array_equal(s, succ)
+    g.close()

@@ -363,3 +363,43 @@ def test_gpu_labels_on_cnr2000_all_kinds(tmp_path, oracle, cnr_truth):
             assert np.array_equal(alg.labelArray(x), L.node(x, int(off[x + 1] - off[x]))[1])
         L.close()
         alg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,width", [(tools.LABEL_GAMMA, 0), (tools.LABEL_FIXED, 11), (tools.LABEL_FIXED_LIST, 5)])
+def test_gpu_labels_corrupted_streams_fail_cleanly(tmp_path, kind, width):
+    """Random byte flips in .labels / .labeloffsets: calls return (an error, or labels that differ), nothing crashes, and the
+    device keeps working afterwards."""
+    from webgraph_b200 import bvgraph, labelling
+    off, succ = graphs.erdos_renyi(400, .1, 21) if kind != tools.LABEL_FIXED_LIST else graphs.erdos_renyi(60, .2, 21)
+    base, lbase, values, list_off, _ = write_case(tmp_path, "c", off, succ, kind, width)
+    n = len(off) - 1
+    rng = np.random.default_rng(5)
+    outcomes = set()
+    for ext in (".labels", ".labeloffsets"):
+        data = bytearray(open(lbase + ext, "rb").read())
+        for trial in range(8):
+            bad = bytearray(data)
+            for p in rng.integers(0, len(bad), 1 + trial % 3):
+                bad[p] ^= 1 << int(rng.integers(0, 8))
+            with open(lbase + ext, "wb") as f:
+                f.write(bad)
+            try:
+                alg = labelling.BitStreamArcLabelledImmutableGraph.load(lbase)
+            except (IOError, ValueError, bvgraph.FormatError) as e:
+                outcomes.add(type(e).__name__)
+                continue
+            try:
+                alg.decodeLabels(0, n)
+                alg.scanLabels(0, n)
+                outcomes.add("decoded")
+            except (IOError, MemoryError, bvgraph.FormatError) as e:
+                outcomes.add(type(e).__name__)
+            alg.close()
+        with open(lbase + ext, "wb") as f:
+            f.write(data)
+    assert outcomes
+    alg = labelling.BitStreamArcLabelledImmutableGraph.load(lbase)
+    lo, vals = alg.decodeLabels(0, n)
+    assert np.array_equal(lo, list_off) and np.array_equal(vals, values)
+    alg.close()
