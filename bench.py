@@ -218,11 +218,22 @@ def arc_labels(workdir, nodes=4_000_000, arcs=125_000_000, cpu_labels=20_000_000
     try:
         from webgraph_b200.efgraph import EFGraph
         ebase = base + "-ef"
+        t0 = time.perf_counter()
         ebits = tools.store_ef(ebase, off, succ, threads=os.cpu_count() or 1)
+        host_store_s = time.perf_counter() - t0
+        EFGraph.store(ebase + "-dev", off, succ)   # first call: device buffers are allocated
+        t0 = time.perf_counter()
+        dbits, dev_ms = EFGraph.store(ebase + "-dev", off, succ)
+        dev_store_s = time.perf_counter() - t0
+        same = all(open(ebase + ext, "rb").read() == open(ebase + "-dev" + ext, "rb").read() for ext in (".graph", ".offsets"))
         t0 = time.perf_counter()
         eg = EFGraph.load(ebase)
         ef = {"graph_bits": ebits, "bits_per_arc": ebits / narcs, "load_s": time.perf_counter() - t0,
-              "what": "bvg_ef_scan_range / bvg_ef_decode_range (device CSR) of the same graph stored with EFGraph.store's layout (quantum 256)"}
+              "what": "bvg_ef_scan_range / bvg_ef_decode_range (device CSR) of the same graph stored with EFGraph.store's layout (quantum 256)",
+              "store": {"device_kernels_ms": dev_ms, "device_call_s_incl_copies_and_files": dev_store_s, "host_writer_s": host_store_s,
+                        "host_threads": os.cpu_count() or 1, "edges_per_s_device_kernels": narcs / (dev_ms * 1e-3),
+                        "byte_identical_to_host_writer": bool(same and dbits == ebits),
+                        "what": "bvg_ef_compress: EFGraph.store's stream written element-parallel on the device from a host CSR, beside the host writer (bvgt_store_ef)"}}
         d_off = torch.empty(nodes + 1, dtype=torch.int64, device="cuda")
         d_out = torch.empty(narcs, dtype=torch.int32, device="cuda")
         for what in ("scan", "decode"):

@@ -234,6 +234,15 @@ int  bvg_ef_range_arcs(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* 
 int  bvg_ef_decode_range(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* out_off, int32_t* out, int64_t cap, int on_device);
 int  bvg_ef_scan_range(const bvg_efgraph* g, int32_t from, int32_t to, int64_t* arcs, uint64_t* checksum);
 int  bvg_ef_last_error_node(const bvg_efgraph* g, int32_t* node, int64_t* bitpos);
+/* EFGraph.store on the device (EFGraph.java:812-888, Accumulator :420-556), the compress half for this format: the stream is
+ * written element-parallel (every field is a function of one successor of one list) from a CSR (off[n + 1], succ[off[n]];
+ * host or device pointers).  graph_out (host, graph_cap bytes) receives the long words in little-endian order including the
+ * trailing word LongWordOutputBitStream.close() writes, *graph_bytes their size (set also on BVG_ENOMEM: call again with a
+ * larger buffer), node_bits (host, n + 1 entries) the bit offset of every node -- the gaps the caller delta-codes into
+ * .offsets.  upper_bound <= 0 means n.  BVG_EINVAL for a list that is not strictly increasing or reaches the upper bound
+ * (IllegalArgumentException in Accumulator.add).  device_ms (may be NULL): time of the kernels. */
+int  bvg_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t upper_bound, int log2_quantum, int on_device,
+                     int device, uint8_t* graph_out, uint64_t graph_cap, uint64_t* graph_bytes, int64_t* node_bits, double* device_ms);
 
 /* ---- diagnostics ---- */
 const char* bvg_strerror(int status);

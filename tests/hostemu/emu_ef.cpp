@@ -49,3 +49,20 @@ extern "C" int emu_ef_decode(const uint64_t* words, uint64_t nwords, const uint6
     *checksum = acc;
     return 0;
 }
+
+// EFGraph.store's element-parallel writer (efc_*), every element in turn: words (zeroed, nwords + 1 entries) and node_bits out.
+extern "C" int64_t emu_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, uint32_t upper_bound, int log2_quantum,
+                                   unsigned long long* words, uint64_t cap_words, int64_t* node_bits) {
+    EfcDev c;
+    c.off = off; c.succ = succ; c.n = n; c.upper_bound = upper_bound; c.log2_quantum = log2_quantum;
+    int bad = 0;
+    std::vector<int32_t> sizes((size_t)n + 1, 0);
+    for (int64_t x = 0; x < n; x++) efc_sizes_one(c, x, sizes.data(), &bad);
+    if (bad) return -1;
+    node_bits[0] = 0;
+    for (int64_t x = 0; x < n; x++) node_bits[x + 1] = node_bits[x] + sizes[(size_t)x];
+    if ((uint64_t)(node_bits[n] >> 6) + 2 > cap_words) return -6;
+    for (int64_t x = n - 1; x >= 0; x--)   // any order must do: the device runs the elements concurrently
+        for (int64_t k = off[x + 1] - off[x]; k >= 0; k--) efc_write_one(c, x, k, node_bits, words, &bad);
+    return bad ? -1 : node_bits[n];
+}

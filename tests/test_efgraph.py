@@ -148,6 +148,30 @@ def test_emulated_walkers_match_the_oracle(tmp_path, oracle, emu_ef, q, big):
         g.close()
 
 
+def test_emulated_element_parallel_writer_is_byte_identical_to_the_host_writer(tmp_path, emu_ef):
+    emu_ef.emu_ef_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    emu_ef.emu_ef_compress.restype = C.c_int64
+    for q in (8, 0, 3):
+        for name, make in CASES:
+            off, succ = make()
+            if name == "skew":
+                off, succ = off[:2000], succ[:off[1999]]   # keep the host loop short: the 60 000-arc node stays in
+            base, ub, bits = store(tmp_path, "%s_%d" % (name, q), off, succ, q=q)
+            want = np.fromfile(base + ".graph", dtype=np.uint64)
+            words = np.zeros(len(want) + 2, dtype=np.uint64)
+            node_bits = np.zeros(len(off), dtype=np.int64)
+            got = emu_ef.emu_ef_compress(off.ctypes.data, succ.ctypes.data if len(succ) else None, len(off) - 1, ub, q,
+                                         words.ctypes.data, len(words), node_bits.ctypes.data)
+            assert got == bits, (name, q)
+            assert np.array_equal(words[:len(want)], want), (name, q)
+            assert np.all(words[len(want):] == 0)
+    off = np.array([0, 3], dtype=np.int64)
+    words = np.zeros(64, dtype=np.uint64)
+    nb = np.zeros(2, dtype=np.int64)
+    bad = np.array([0, 0, 1], dtype=np.int32)
+    assert emu_ef.emu_ef_compress(off.ctypes.data, bad.ctypes.data, 1, 5, 8, words.ctypes.data, 64, nb.ctypes.data) == -1
+
+
 # ---------------------------------------------------------------- GPU
 
 @pytest.mark.gpu
@@ -292,3 +316,26 @@ def test_gpu_efgraph_corrupted_streams_fail_cleanly(tmp_path):
     o, s = g.decodeRange(0, g.numNodes())
     assert np.array_equal(o, off) and np.array_equal(s, succ)
     g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_efgraph_store_on_the_device_is_byte_identical(tmp_path, cnr_truth):
+    """EFGraph.store with the stream written by the element-parallel kernels: same .graph and .offsets bytes as the host
+    writer (which restates Accumulator), and what it wrote loads and decodes."""
+    from webgraph_b200.efgraph import EFGraph
+    cases = [(n, m) for n, m in CASES if n not in ("empty",)] + [("cnr", lambda: cnr_truth)]
+    for q in (8, 2):
+        for name, make in cases:
+            off, succ = make()
+            base, ub, bits = store(tmp_path, "%s_%d" % (name, q), off, succ, q=q, threads=4)
+            dbase = base + "-dev"
+            dbits, ms = EFGraph.store(dbase, off, succ, upperBound=ub, log2Quantum=q)
+            assert dbits == bits, (name, q)
+            for ext in (".graph", ".offsets"):
+                assert open(base + ext, "rb").read() == open(dbase + ext, "rb").read(), (name, q, ext)
+            g = EFGraph.load(dbase)
+            o, s = g.decodeRange(0, g.numNodes())
+            assert np.array_equal(o, off) and np.array_equal(s, succ)
+            g.close()
+    with pytest.raises(ValueError):   # not strictly increasing
+        EFGraph.store(str(tmp_path / "bad"), np.array([0, 3], dtype=np.int64), np.array([0, 0, 1], dtype=np.int32), upperBound=5)

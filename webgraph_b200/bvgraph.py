@@ -59,7 +59,7 @@ SYMBOLS = [
     "bvg_labels_underlying", "bvg_labels_open", "bvg_labels_open_memory", "bvg_labels_close", "bvg_labels_info",
     "bvg_labels_decode_range", "bvg_labels_scan_range", "bvg_hyperball_step",
     "bvg_ef_open", "bvg_ef_open_memory", "bvg_ef_close", "bvg_ef_info", "bvg_ef_outdegree", "bvg_ef_successors", "bvg_ef_range_arcs",
-    "bvg_ef_decode_range", "bvg_ef_scan_range", "bvg_ef_last_error_node",
+    "bvg_ef_decode_range", "bvg_ef_scan_range", "bvg_ef_last_error_node", "bvg_ef_compress",
 ]
 
 
@@ -127,6 +127,7 @@ def lib():
     L.bvg_ef_decode_range.argtypes = [vp, i32, i32, vp, vp, i64, C.c_int]
     L.bvg_ef_scan_range.argtypes = [vp, i32, i32, P(i64), P(u64)]
     L.bvg_ef_last_error_node.argtypes = [vp, P(i32), P(i64)]
+    L.bvg_ef_compress.argtypes = [vp, vp, i32, i32, C.c_int, C.c_int, C.c_int, vp, u64, P(u64), vp, P(C.c_double)]
     L.bvg_hyperball_step.argtypes = [vp, i32, i32, C.c_int, vp, vp, C.c_int, P(i64)]
     L.bvg_labels_underlying.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.bvg_labels_open.argtypes = [vp, C.c_char_p, P(vp)]

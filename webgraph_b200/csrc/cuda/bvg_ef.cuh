@@ -277,3 +277,129 @@ __global__ void __launch_bounds__(EF_BLOCK) k_ef_decode_heavy(EfDev g, int32_t f
 #endif
 
 }  // namespace bvg
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// EFGraph.store on the device (EFGraph.java:812-888 with Accumulator :420-556): every field of the format is a function of one
+// element of one list, so the stream is written element-parallel.  Elements are the successors plus one terminator per node
+// (value upperBound); element k of node x has high part h = v >> l and contributes
+//   * its l lower bits at lower_start + k * l,
+//   * a one at upper position h + k,
+//   * the skip pointers b with h_prev < b * quantum <= h (h_prev = high part of element k - 1, or 0 zeros before the first):
+//     pointer b - 1 = b * quantum + k  (the position just after the (b * quantum)-th zero: that many zeros and k ones precede it),
+//   * and, for k = 0, gamma(outdegree).
+// Neighbouring nodes share words, so fields are ORed in with atomics on 64-bit words (the buffer starts zeroed).
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace bvg {
+
+struct EfcDev {
+    const int64_t* __restrict__ off;    // CSR row offsets, n + 1
+    const int32_t* __restrict__ succ;
+    int32_t n;
+    uint32_t upper_bound;
+    int log2_quantum;
+};
+
+struct EfcGeom { int l, psize, gbits; uint64_t npointers, ulen, bits; };
+__device__ __forceinline__ EfcGeom efc_geometry(uint64_t d, uint32_t ub, int q) {
+    EfcGeom e;
+    const uint64_t len = d + 1;
+    const uint32_t quot = ub / (uint32_t)len;
+    e.l = quot == 0 ? 0 : 31 - __clz((int)quot);
+    e.ulen = len + ((uint64_t)ub >> e.l);
+    e.psize = e.ulen <= 1 ? 0 : 64 - __clzll((long long)(e.ulen - 1));
+    e.npointers = ((uint64_t)ub >> e.l) >> q;
+    const int msb = 63 - __clzll((long long)(d + 1));
+    e.gbits = 2 * msb + 1;
+    e.bits = (uint64_t)e.gbits + (uint64_t)e.psize * e.npointers + (uint64_t)e.l * len + e.ulen;
+    return e;
+}
+
+// ORs the low `width` bits of v into the stream at bit position pos (width <= 64).
+__device__ __forceinline__ void efc_put(unsigned long long* __restrict__ w, uint64_t pos, uint64_t v, int width) {
+    if (width == 0) return;
+    if (width < 64) v &= (~0ull >> (64 - width));
+    const uint64_t i = pos >> 6;
+    const int s = (int)(pos & 63);
+    if (v << s) atomicOr(w + i, (unsigned long long)(v << s));
+    if (s && width > 64 - s && (v >> (64 - s))) atomicOr(w + i + 1, (unsigned long long)(v >> (64 - s)));
+}
+
+__device__ inline void efc_sizes_one(const EfcDev& c, int64_t x, int32_t* __restrict__ bits, int* __restrict__ bad) {
+    const int64_t d = c.off[x + 1] - c.off[x];
+    if (d < 0 || d > 0x7ffffffe) { *bad = 1; bits[x] = 0; return; }
+    const EfcGeom e = efc_geometry((uint64_t)d, c.upper_bound, c.log2_quantum);
+    if (e.bits > 0x7fffffffull) { *bad = 1; bits[x] = 0; return; }   // a record of 2^31 bits or more: not a case for this writer
+    bits[x] = (int32_t)e.bits;
+}
+
+// Element e of the whole graph (elements of node x: eoff(x) = off[x] + x .. eoff(x + 1)); node_bits: bit offset of every node.
+__device__ inline void efc_write_one(const EfcDev& c, int64_t x, int64_t k, const int64_t* __restrict__ node_bits,
+                                     unsigned long long* __restrict__ w, int* __restrict__ bad) {
+    const int64_t a = c.off[x], d = c.off[x + 1] - a;
+    const EfcGeom e = efc_geometry((uint64_t)d, c.upper_bound, c.log2_quantum);
+    const uint64_t start = (uint64_t)node_bits[x];
+    const uint64_t pointer_start = start + (uint64_t)e.gbits;
+    const uint64_t lower_start = pointer_start + (uint64_t)e.psize * e.npointers;
+    const uint64_t upper_start = lower_start + (uint64_t)e.l * (uint64_t)(d + 1);
+    if (k == 0) {   // gamma(d): the word 1 << msb in msb + 1 bits, then the msb low bits of d + 1 (LongWordOutputBitStream, :396-409)
+        const uint64_t v = (uint64_t)d + 1;
+        const int msb = (e.gbits - 1) / 2;
+        efc_put(w, start, 1ull << msb, msb + 1);
+        efc_put(w, start + (uint64_t)msb + 1, v ^ (1ull << msb), msb);
+    }
+    const uint64_t v = k < d ? (uint64_t)(uint32_t)c.succ[a + k] : (uint64_t)c.upper_bound;
+    uint64_t prev_h = 0;
+    if (k > 0) {
+        const uint64_t pv = (uint64_t)(uint32_t)c.succ[a + k - 1];
+        if (k < d && v <= pv) *bad = 1;   // lists are strictly increasing (Accumulator.add, :499)
+        prev_h = pv >> e.l;
+    }
+    if (k < d && (c.succ[a + k] < 0 || v >= c.upper_bound)) *bad = 1;
+    const uint64_t h = v >> e.l;
+    if (e.l) efc_put(w, lower_start + (uint64_t)e.l * (uint64_t)k, v, e.l);
+    efc_put(w, upper_start + h + (uint64_t)k, 1ull, 1);
+    const uint64_t quantum = 1ull << c.log2_quantum;
+    for (uint64_t b = prev_h / quantum + 1; b * quantum <= h; b++)   // pointers to the zeros this element is the first one after
+        if (b <= e.npointers) efc_put(w, pointer_start + (b - 1) * (uint64_t)e.psize, b * quantum + (uint64_t)k, e.psize);
+}
+
+#ifndef BVG_HOST_EMULATION
+__global__ void k_efc_sizes(EfcDev c, int32_t* __restrict__ bits, int* __restrict__ bad) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < c.n) efc_sizes_one(c, x, bits, bad);
+}
+
+constexpr int EFC_THREADS = 256, EFC_ITEMS = 4, EFC_TILE = EFC_THREADS * EFC_ITEMS;
+
+// Last node x in [lo, hi] with off[x] + x <= e.
+__device__ __forceinline__ int32_t efc_node_of(const int64_t* __restrict__ off, int32_t lo, int32_t hi, int64_t e) {
+    while (lo < hi) {
+        const int32_t mid = lo + (int32_t)(((int64_t)hi - lo + 1) >> 1);
+        if (off[mid] + mid <= e) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// One thread per EFC_ITEMS consecutive elements; a block's node range is found first so that the per-thread search is short.
+__global__ void __launch_bounds__(EFC_THREADS) k_efc_write(EfcDev c, const int64_t* __restrict__ node_bits, unsigned long long* __restrict__ w,
+                                                           int* __restrict__ bad) {
+    __shared__ int32_t s_lo, s_hi;
+    const int64_t total = c.off[c.n] + c.n;
+    const int64_t tile = (int64_t)blockIdx.x * EFC_TILE;
+    const int64_t tile_end = tile + EFC_TILE < total ? tile + EFC_TILE : total;
+    if (threadIdx.x == 0) s_lo = efc_node_of(c.off, 0, c.n - 1, tile);
+    if (threadIdx.x == 32) s_hi = efc_node_of(c.off, 0, c.n - 1, tile_end - 1);
+    __syncthreads();
+    int64_t e = tile + (int64_t)threadIdx.x * EFC_ITEMS;
+    if (e >= tile_end) return;
+    int32_t x = efc_node_of(c.off, s_lo, s_hi, e);
+#pragma unroll
+    for (int i = 0; i < EFC_ITEMS; i++, e++) {
+        if (e >= tile_end) break;
+        while (e >= c.off[x + 1] + x + 1) x++;
+        efc_write_one(c, x, e - (c.off[x] + x), node_bits, w, bad);
+    }
+}
+#endif
+
+}  // namespace bvg

@@ -262,4 +262,79 @@ int bvg_ef_last_error_node(const bvg_efgraph* g, int32_t* node, int64_t* bitpos)
     return BVG_OK;
 }
 
+// EFGraph.store on the device (bvg_ef.cuh, second half).  off / succ: the CSR (host or device pointers); graph_out: host buffer
+// for the long words in little-endian order (one trailing word as LongWordOutputBitStream.close() writes); node_bits: host
+// buffer of n + 1 bit offsets (the caller writes .offsets' delta-coded gaps and .properties from them).
+int bvg_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t upper_bound, int log2_quantum, int on_device, int device,
+                    uint8_t* graph_out, uint64_t graph_cap, uint64_t* graph_bytes, int64_t* node_bits, double* device_ms) {
+    if (!off || n < 0 || log2_quantum < 0 || log2_quantum > 30 || !graph_bytes || !node_bits) return BVG_EINVAL;
+    int dev;
+    int dl[1] = { device };
+    int rc = pick_device(device >= 0 ? dl : nullptr, device >= 0 ? 1 : 0, &dev);
+    if (rc) return rc;
+    DeviceGuard dg(dev);
+    keep_pool_warm(dev);
+    cudaStream_t s = nullptr;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    rc = [&]() -> int {
+        Tmp<int64_t> d_off(s), d_bits(s);
+        Tmp<int32_t> d_succ(s), d_sizes(s);
+        Tmp<int> d_bad(s);
+        Tmp<unsigned long long> d_words(s);
+        int64_t m = 0;
+        const int64_t* off_dev = off;
+        const int32_t* succ_dev = succ;
+        if (on_device) CK(cudaMemcpyAsync(&m, off + n, 8, cudaMemcpyDeviceToHost, s)); else m = off[n];
+        CK(cudaStreamSynchronize(s));
+        if (m < 0 || (m > 0 && !succ)) return BVG_EINVAL;
+        if (!on_device) {
+            CK(d_off.alloc((size_t)n + 1));
+            CK(d_succ.alloc((size_t)std::max<int64_t>(m, 1)));
+            CK(cudaMemcpyAsync(d_off.p, off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
+            if (m) CK(cudaMemcpyAsync(d_succ.p, succ, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+            off_dev = d_off.p; succ_dev = d_succ.p;
+        }
+        EfcDev c;
+        c.off = off_dev; c.succ = succ_dev; c.n = n; c.upper_bound = (uint32_t)(upper_bound > 0 ? upper_bound : n); c.log2_quantum = log2_quantum;
+        CK(d_sizes.alloc((size_t)std::max<int32_t>(n, 1)));
+        CK(d_bits.alloc((size_t)n + 1));
+        CK(d_bad.alloc(1));
+        CK(cudaMemsetAsync(d_bad.p, 0, 4, s));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, s));
+        if (n) LAUNCH(k_efc_sizes, grid_for(n, 256), 256, 0, s, c, d_sizes.p, d_bad.p);
+        int r = device_exclusive_scan(s, d_sizes.p, n, d_bits.p);
+        if (r) return r;
+        int64_t total_bits = 0;
+        int bad = 0;
+        CK(cudaMemcpyAsync(&total_bits, d_bits.p + n, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (bad) return BVG_EINVAL;
+        const uint64_t nwords = ((uint64_t)total_bits >> 6) + 1;
+        *graph_bytes = nwords * 8;
+        if (!graph_out || graph_cap < nwords * 8) return BVG_ENOMEM;   // *graph_bytes says how much is needed
+        CK(d_words.alloc((size_t)nwords + 1));
+        CK(cudaMemsetAsync(d_words.p, 0, ((size_t)nwords + 1) * 8, s));
+        const int64_t elements = m + n;
+        if (elements) LAUNCH(k_efc_write, grid_for(elements, EFC_TILE), EFC_THREADS, 0, s, c, d_bits.p, d_words.p, d_bad.p);
+        CK(cudaEventRecord(e1, s));
+        CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(graph_out, d_words.p, (size_t)nwords * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(node_bits, d_bits.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (device_ms) *device_ms = ms;
+        CK(cudaGetLastError());
+        return bad ? BVG_EINVAL : BVG_OK;   // a list that is not strictly increasing or reaches the upper bound (Accumulator.add, :499-503)
+    }();
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    cudaGetLastError();
+    return rc;
+}
+
 }  // extern "C"

@@ -79,6 +79,37 @@ class EFGraph(ImmutableGraph):
 
     loadMapped = loadOffline = loadSequential = load
 
+    @staticmethod
+    def store(basename, off, succ, upperBound=0, log2Quantum=8, device=-1):
+        """EFGraph.store (EFGraph.java:812-888) with the stream written on the device (bvg_ef_compress): <basename>.graph
+        (little-endian long words), .offsets (delta-coded gaps, written here from the node bit offsets the device returns) and
+        .properties.  Returns (graph bits, milliseconds of the device kernels)."""
+        from . import tools
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        succ = np.ascontiguousarray(succ, dtype=np.int32)
+        n = len(off) - 1
+        need, ms = C.c_uint64(0), C.c_double(0)
+        node_bits = np.zeros(n + 1, dtype=np.int64)
+        L = lib()
+        args = (off.ctypes.data, succ.ctypes.data if len(succ) else None, n, upperBound, log2Quantum, 0, device)
+        rc = L.bvg_ef_compress(*args, None, 0, C.byref(need), node_bits.ctypes.data, C.byref(ms))
+        if rc != -6:   # BVG_ENOMEM carries the size; anything else is the verdict
+            _check(rc)
+        words = np.zeros(max(need.value, 8), dtype=np.uint8)
+        _check(L.bvg_ef_compress(*args, words.ctypes.data, len(words), C.byref(need), node_bits.ctypes.data, C.byref(ms)))
+        words[:need.value].tofile(basename + ".graph")
+        gaps = np.concatenate([[0], np.diff(node_bits)]).astype(np.uint64)
+        data, _ = tools.write_codes(tools.DELTA, 0, gaps)
+        with open(basename + ".offsets", "wb") as f:
+            f.write(data)
+        ub = upperBound if upperBound > 0 else n
+        with open(basename + ".properties", "w") as f:
+            f.write("#EFGraph properties\nnodes=%d\narcs=%d\n" % (n, len(succ)))
+            if ub != n:
+                f.write("upperbound=%d\n" % ub)
+            f.write("quantum=%d\nbyteorder=LITTLE_ENDIAN\ngraphclass=it.unimi.dsi.webgraph.EFGraph\nversion=0\n" % (1 << log2Quantum))
+        return int(node_bits[-1]), ms.value
+
     def close(self):
         if self._h:
             lib().bvg_ef_close(self._h)
