@@ -244,6 +244,20 @@ int  bvg_ef_last_error_node(const bvg_efgraph* g, int32_t* node, int64_t* bitpos
 int  bvg_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t upper_bound, int log2_quantum, int on_device,
                      int device, uint8_t* graph_out, uint64_t graph_cap, uint64_t* graph_bytes, int64_t* node_bits, double* device_ms);
 
+/* ---- BVGraph.store on the device (compress half) ----
+ * The reference's compressor (CompressionThread / diffComp / intervalize, BVGraph.java:2049-2386) for the default codings
+ * (gamma outdegrees, blocks, block counts and intervals, unary references, zeta_k residuals; compressionflags empty), from a
+ * CSR (off[n + 1], succ[off[n]]; host or device pointers).  The node range is cut into ranges of `range_nodes` nodes (<= 0:
+ * 256) compressed with an empty window each, as the reference's own multi-threaded store cuts it (:2471-2550): with one range
+ * the bytes are those of the single-threaded reference (cnr-2000.graph is reproduced), with the ranges of a T-threaded host
+ * writer the bytes of that writer.  graph_out (host, graph_cap bytes) receives .graph, *graph_bytes its size (also on
+ * BVG_ENOMEM: call again), node_bits (host, n + 1) the bit position of every node -- the gaps the caller gamma-codes into
+ * .offsets.  window <= 31; maxref < 0 = unbounded.  BVG_EINVAL for a list that is not strictly increasing
+ * (IllegalArgumentException, :2201). */
+int  bvg_bv_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t window, int32_t maxref, int32_t minlen,
+                     int32_t zetak, int32_t range_nodes, int on_device, int device, uint8_t* graph_out, uint64_t graph_cap,
+                     uint64_t* graph_bytes, int64_t* node_bits, double* device_ms);
+
 /* ---- diagnostics ---- */
 const char* bvg_strerror(int status);
 /* Node and bit position of the first record a kernel rejected (BVGraph.java:1129-1131 logs the same pair). */

@@ -22,6 +22,7 @@ static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((u
 static inline int atomicCAS(int* p, int cmp, int val) { int old = *p; if (old == cmp) *p = val; return old; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long val) { unsigned long long old = *p; if (old == cmp) *p = val; return old; }
 static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o | v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 static inline void __threadfence() {}
 // kernels in the included headers are compiled but never called on the host: give their index variables a meaning

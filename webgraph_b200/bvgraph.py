@@ -59,7 +59,7 @@ SYMBOLS = [
     "bvg_labels_underlying", "bvg_labels_open", "bvg_labels_open_memory", "bvg_labels_close", "bvg_labels_info",
     "bvg_labels_decode_range", "bvg_labels_scan_range", "bvg_hyperball_step",
     "bvg_ef_open", "bvg_ef_open_memory", "bvg_ef_close", "bvg_ef_info", "bvg_ef_outdegree", "bvg_ef_successors", "bvg_ef_range_arcs",
-    "bvg_ef_decode_range", "bvg_ef_scan_range", "bvg_ef_last_error_node", "bvg_ef_compress",
+    "bvg_ef_decode_range", "bvg_ef_scan_range", "bvg_ef_last_error_node", "bvg_ef_compress", "bvg_bv_compress",
 ]
 
 
@@ -127,6 +127,7 @@ def lib():
     L.bvg_ef_decode_range.argtypes = [vp, i32, i32, vp, vp, i64, C.c_int]
     L.bvg_ef_scan_range.argtypes = [vp, i32, i32, P(i64), P(u64)]
     L.bvg_ef_last_error_node.argtypes = [vp, P(i32), P(i64)]
+    L.bvg_bv_compress.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, C.c_int, C.c_int, vp, u64, P(u64), vp, P(C.c_double)]
     L.bvg_ef_compress.argtypes = [vp, vp, i32, i32, C.c_int, C.c_int, C.c_int, vp, u64, P(u64), vp, P(C.c_double)]
     L.bvg_hyperball_step.argtypes = [vp, i32, i32, C.c_int, vp, vp, C.c_int, P(i64)]
     L.bvg_labels_underlying.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
@@ -414,6 +415,38 @@ class BVGraph(ImmutableGraph):
                                      len(o) if o is not None else 0, nodes, arcs, window, maxref,
                                      minlen, zetak, flags, offsetType, device, C.byref(h)))
         return cls(h)
+
+    @staticmethod
+    def store(basename, off, succ, windowSize=7, maxRefCount=3, minIntervalLength=4, zetaK=3, rangeNodes=256, device=-1):
+        """BVGraph.store (BVGraph.java:1679-1688, 2436-2650; defaults :454-472) with the stream produced on the device
+        (bvg_bv_compress, default codings): writes <basename>.graph, .offsets (gamma-coded gaps, from the node bit positions the
+        device returns) and .properties.  rangeNodes: nodes per independently compressed range (the whole graph = the
+        single-threaded reference's bytes).  Returns (graph bits, milliseconds of the device kernels)."""
+        from . import tools
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        succ = np.ascontiguousarray(succ, dtype=np.int32)
+        n = len(off) - 1
+        need, ms = C.c_uint64(0), C.c_double(0)
+        node_bits = np.zeros(n + 1, dtype=np.int64)
+        L = lib()
+        args = (off.ctypes.data, succ.ctypes.data if len(succ) else None, n, windowSize, maxRefCount, minIntervalLength, zetaK, rangeNodes, 0, device)
+        rc = L.bvg_bv_compress(*args, None, 0, C.byref(need), node_bits.ctypes.data, C.byref(ms))
+        if rc != BVG_ENOMEM:
+            _check(rc)
+        data = np.zeros(max(need.value, 1), dtype=np.uint8)
+        _check(L.bvg_bv_compress(*args, data.ctypes.data, len(data), C.byref(need), node_bits.ctypes.data, C.byref(ms)))
+        data[:need.value].tofile(basename + ".graph")
+        gaps = np.concatenate([[0], np.diff(node_bits)]).astype(np.uint64)
+        codes, _ = tools.write_codes(tools.GAMMA, 0, gaps)
+        with open(basename + ".offsets", "wb") as f:
+            f.write(codes)
+        bits = int(node_bits[-1])
+        with open(basename + ".properties", "w") as f:
+            f.write("#BVGraph properties\ngraphclass=it.unimi.dsi.webgraph.BVGraph\nversion=0\nnodes=%d\narcs=%d\n" % (n, len(succ)))
+            f.write("windowsize=%d\nmaxrefcount=%d\nminintervallength=%d\nzetak=%d\ncompressionflags=\n"
+                    % (windowSize, 2147483647 if maxRefCount < 0 else maxRefCount, minIntervalLength, zetaK))
+            f.write("bitsperlink=%.3f\nbitspernode=%.3f\n" % (bits / max(len(succ), 1), bits / max(n, 1)))
+        return bits, ms.value
 
     def close(self):
         if self._h:

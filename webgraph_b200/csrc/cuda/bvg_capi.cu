@@ -11,6 +11,7 @@
 #include "bvg_labels.cuh"
 #include "bvg_consumers.cuh"
 #include "bvg_ef.cuh"
+#include "bvg_compress.cuh"
 #include "bvg_boundaries.cuh"
 #include "bvg_tile.cuh"
 #include "bvg_stream.cuh"

@@ -337,4 +337,85 @@ int bvg_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
     return rc;
 }
 
+// BVGraph.store on the device (bvg_compress.cuh), default codings.  off / succ: the CSR (host or device pointers).  graph_out
+// (host) receives the bytes of .graph, node_bits (host, n + 1) the bit position of every node (the caller gamma-codes the gaps
+// into .offsets).  range_nodes: nodes per independently compressed range (<= 0: 256).
+int bvg_bv_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t window, int32_t maxref, int32_t minlen, int32_t zetak,
+                    int32_t range_nodes, int on_device, int device, uint8_t* graph_out, uint64_t graph_cap, uint64_t* graph_bytes,
+                    int64_t* node_bits, double* device_ms) {
+    if (!off || n < 0 || window < 0 || minlen < 0 || zetak < 1 || !graph_bytes || !node_bits) return BVG_EINVAL;
+    if (window > BVC_MAX_WINDOW) return BVG_EUNSUPPORTED;
+    if (range_nodes <= 0) range_nodes = 256;
+    int dev;
+    int dl[1] = { device };
+    int rc = pick_device(device >= 0 ? dl : nullptr, device >= 0 ? 1 : 0, &dev);
+    if (rc) return rc;
+    DeviceGuard dg(dev);
+    keep_pool_warm(dev);
+    cudaStream_t s = nullptr;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    rc = [&]() -> int {
+        Tmp<int64_t> d_off(s), d_bits(s);
+        Tmp<int32_t> d_succ(s), d_sizes(s);
+        Tmp<int8_t> d_ref(s);
+        Tmp<int> d_bad(s);
+        Tmp<uint32_t> d_words(s);
+        int64_t m = 0;
+        const int64_t* off_dev = off;
+        const int32_t* succ_dev = succ;
+        if (on_device) CK(cudaMemcpyAsync(&m, off + n, 8, cudaMemcpyDeviceToHost, s)); else m = off[n];
+        CK(cudaStreamSynchronize(s));
+        if (m < 0 || (m > 0 && !succ)) return BVG_EINVAL;
+        if (!on_device) {
+            CK(d_off.alloc((size_t)n + 1));
+            CK(d_succ.alloc((size_t)std::max<int64_t>(m, 1)));
+            CK(cudaMemcpyAsync(d_off.p, off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, s));
+            if (m) CK(cudaMemcpyAsync(d_succ.p, succ, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+            off_dev = d_off.p; succ_dev = d_succ.p;
+        }
+        BvcDev g;
+        g.off = off_dev; g.succ = succ_dev; g.n = n; g.c = BvcCodec{ window, maxref, minlen, zetak }; g.range_nodes = range_nodes;
+        CK(d_sizes.alloc((size_t)std::max<int32_t>(n, 1)));
+        CK(d_ref.alloc((size_t)std::max<int32_t>(n, 1)));
+        CK(d_bits.alloc((size_t)n + 1));
+        CK(d_bad.alloc(1));
+        CK(cudaMemsetAsync(d_bad.p, 0, 4, s));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, s));
+        const int64_t nranges = ((int64_t)n + range_nodes - 1) / range_nodes;
+        if (n) LAUNCH(k_bvc_choose, grid_for(nranges, BVC_THREADS / BVC_GROUP), BVC_THREADS, 0, s, g, nranges, d_ref.p, d_sizes.p, d_bad.p);
+        int r = device_exclusive_scan(s, d_sizes.p, n, d_bits.p);
+        if (r) return r;
+        int64_t total_bits = 0;
+        int bad = 0;
+        CK(cudaMemcpyAsync(&total_bits, d_bits.p + n, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (bad) return BVG_EINVAL;   // a list that is not strictly increasing (IllegalArgumentException, BVGraph.java:2201)
+        const uint64_t nbytes = ((uint64_t)total_bits + 7) >> 3;
+        *graph_bytes = nbytes;
+        if (nbytes && (!graph_out || graph_cap < nbytes)) return BVG_ENOMEM;   // *graph_bytes says how much is needed
+        const uint64_t nwords = nbytes / 4 + 2;
+        CK(d_words.alloc((size_t)nwords));
+        CK(cudaMemsetAsync(d_words.p, 0, (size_t)nwords * 4, s));
+        if (n) LAUNCH(k_bvc_write, grid_for(n, 128), 128, 0, s, g, d_ref.p, d_bits.p, d_words.p);
+        LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, d_words.p, nwords);   // big-endian words -> bytes in stream order
+        CK(cudaEventRecord(e1, s));
+        if (nbytes) CK(cudaMemcpyAsync(graph_out, d_words.p, (size_t)nbytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(node_bits, d_bits.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (device_ms) *device_ms = ms;
+        CK(cudaGetLastError());
+        return BVG_OK;
+    }();
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    cudaGetLastError();
+    return rc;
+}
+
 }  // extern "C"
