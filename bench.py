@@ -269,6 +269,25 @@ def arc_labels(workdir, nodes=4_000_000, arcs=125_000_000, cpu_labels=20_000_000
         out["efgraph"] = ef
     except Exception as e:
         out["efgraph"] = {"error": repr(e)}
+    # SURVEY 8 f4 (compress half): BVGraph.store on the device beside the host writer (byte-identity with equal ranges is a test)
+    try:
+        t0 = time.perf_counter()
+        hst = tools.store_csr(base + "-hoststore", off, succ, threads=os.cpu_count() or 1)
+        host_s = time.perf_counter() - t0
+        bvgraph.BVGraph.store(base + "-devstore", off, succ)   # first call: device buffers are allocated
+        t0 = time.perf_counter()
+        dbits, dms = bvgraph.BVGraph.store(base + "-devstore", off, succ)
+        call_s = time.perf_counter() - t0
+        dg = bvgraph.BVGraph.load(base + "-devstore")
+        back = dg.scanRange(0, nodes) == (narcs, st["xor_checksum"])
+        dg.close()
+        out["bvgraph_store"] = {"device_kernels_ms": dms, "device_call_s_incl_copies_and_files": call_s, "host_writer_s": host_s,
+                                "host_threads": os.cpu_count() or 1, "edges_per_s_device_kernels": narcs / (dms * 1e-3),
+                                "bits": dbits, "bits_over_host_writer": dbits / hst["graph_bits"], "range_nodes": 256,
+                                "decodes_back_to_the_graph": bool(back),
+                                "what": "bvg_bv_compress: BVGraph.store (default codings, W=7, R=3, minLen=4, zeta_3) on the device in 256-node ranges, beside the host writer (bvgt_store_csr)"}
+    except Exception as e:
+        out["bvgraph_store"] = {"error": repr(e)}
     return out
 
 
@@ -793,6 +812,7 @@ def main():
             try:
                 other["arc_labels"] = arc_labels(args.workdir)
                 other["efgraph"] = other["arc_labels"].pop("efgraph", None)
+                other["bvgraph_store"] = other["arc_labels"].pop("bvgraph_store", None)
             except Exception as e:
                 other["arc_labels"] = {"error": repr(e)}
     cpu = None
