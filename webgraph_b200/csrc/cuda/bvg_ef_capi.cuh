@@ -24,6 +24,13 @@ struct bvg_efgraph {
     }
 };
 
+// A pair of timing events that cannot leak on an early return.
+struct EventPair {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t create() { cudaError_t r = cudaEventCreate(&e0); return r != cudaSuccess ? r : cudaEventCreate(&e1); }
+    ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+
 static void ef_destroy(bvg_efgraph* g) {
     if (!g) return;
     DeviceGuard dg(g->device);
@@ -300,9 +307,9 @@ int bvg_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
         CK(d_bits.alloc((size_t)n + 1));
         CK(d_bad.alloc(1));
         CK(cudaMemsetAsync(d_bad.p, 0, 4, s));
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, s));
+        EventPair ev;
+        CK(ev.create());
+        CK(cudaEventRecord(ev.e0, s));
         if (n) LAUNCH(k_efc_sizes, grid_for(n, 256), 256, 0, s, c, d_sizes.p, d_bad.p);
         int r = device_exclusive_scan(s, d_sizes.p, n, d_bits.p);
         if (r) return r;
@@ -319,14 +326,13 @@ int bvg_ef_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
         CK(cudaMemsetAsync(d_words.p, 0, ((size_t)nwords + 1) * 8, s));
         const int64_t elements = m + n;
         if (elements) LAUNCH(k_efc_write, grid_for(elements, EFC_TILE), EFC_THREADS, 0, s, c, d_bits.p, d_words.p, d_bad.p);
-        CK(cudaEventRecord(e1, s));
+        CK(cudaEventRecord(ev.e1, s));
         CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(graph_out, d_words.p, (size_t)nwords * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(node_bits, d_bits.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaEventElapsedTime(&ms, ev.e0, ev.e1);
         if (device_ms) *device_ms = ms;
         CK(cudaGetLastError());
         return bad ? BVG_EINVAL : BVG_OK;   // a list that is not strictly increasing or reaches the upper bound (Accumulator.add, :499-503)
@@ -380,9 +386,9 @@ int bvg_bv_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
         CK(d_bits.alloc((size_t)n + 1));
         CK(d_bad.alloc(1));
         CK(cudaMemsetAsync(d_bad.p, 0, 4, s));
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, s));
+        EventPair ev;
+        CK(ev.create());
+        CK(cudaEventRecord(ev.e0, s));
         const int64_t nranges = ((int64_t)n + range_nodes - 1) / range_nodes;
         if (n) LAUNCH(k_bvc_choose, grid_for(nranges, BVC_THREADS / BVC_GROUP), BVC_THREADS, 0, s, g, nranges, d_ref.p, d_sizes.p, d_bad.p);
         int r = device_exclusive_scan(s, d_sizes.p, n, d_bits.p);
@@ -401,13 +407,12 @@ int bvg_bv_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
         CK(cudaMemsetAsync(d_words.p, 0, (size_t)nwords * 4, s));
         if (n) LAUNCH(k_bvc_write, grid_for(n, 128), 128, 0, s, g, d_ref.p, d_bits.p, d_words.p);
         LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, d_words.p, nwords);   // big-endian words -> bytes in stream order
-        CK(cudaEventRecord(e1, s));
+        CK(cudaEventRecord(ev.e1, s));
         if (nbytes) CK(cudaMemcpyAsync(graph_out, d_words.p, (size_t)nbytes, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(node_bits, d_bits.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaEventElapsedTime(&ms, ev.e0, ev.e1);
         if (device_ms) *device_ms = ms;
         CK(cudaGetLastError());
         return BVG_OK;
