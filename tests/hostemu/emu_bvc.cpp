@@ -12,15 +12,34 @@ extern "C" int64_t emu_bv_compress(const int64_t* off, const int32_t* succ, int3
                                    int32_t range_nodes, uint8_t* out, uint64_t cap, int64_t* node_bits, int8_t* refs) {
     BvcDev g;
     g.off = off; g.succ = succ; g.n = n; g.c = BvcCodec{ window, maxref, minlen, zetak }; g.range_nodes = range_nodes;
-    std::vector<int32_t> refc((size_t)window + 1, 0);
+    std::vector<int32_t> refc((size_t)window + 1, 0), refc2((size_t)window + 1, 0);
+    // the cost table of the device's phase 1a (every pair, any order), then phase 1b; checked against the all-in-one choice
+    const int32_t size = window + 1;
+    std::vector<long long> cost((size_t)std::max<int64_t>((int64_t)n * size, 1), LLONG_MAX);
+    for (int64_t x = n - 1; x >= 0; x--) {
+        const int64_t d = off[x + 1] - off[x];
+        if (d < 0 || d > 0x7ffffffe) return -1;
+        if (d == 0) continue;
+        const int64_t lo = (x / range_nodes) * range_nodes;
+        for (int32_t ref = 0; ref < size; ref++) {
+            const int64_t y = x - ref;
+            if (ref && (y < lo || off[y + 1] == off[y])) continue;
+            bool b = false;
+            cost[(size_t)(x * size + ref)] = (long long)bvc_cost(g, x, ref, b);
+            if (b) return -1;
+        }
+    }
     node_bits[0] = 0;
     for (int64_t lo = 0; lo < n; lo += range_nodes) {
         std::fill(refc.begin(), refc.end(), 0);
+        std::fill(refc2.begin(), refc2.end(), 0);
         const int64_t hi = std::min<int64_t>(n, lo + range_nodes);
         for (int64_t x = lo; x < hi; x++) {
-            int32_t ref = 0;
+            int32_t ref = 0, ref2 = 0;
             const int64_t bits = bvc_choose_one(g, x, lo, refc.data(), &ref);
             if (bits < 0) return -1;
+            const int64_t bits2 = bvc_pick(g, x, cost.data(), refc2.data(), &ref2);
+            if (bits2 != bits || ref2 != ref) return -200;
             refs[x] = (int8_t)ref;
             node_bits[x + 1] = node_bits[x] + bits;
         }

@@ -7,11 +7,14 @@
 // cheapest encoding wins, ties to the smaller ref.  Node x depends on its predecessors only through their chain lengths
 // (refCount), and the reference's own multi-threaded store cuts the node range into pieces compressed with an empty window
 // each and splices the bits (:2471-2550).  Here the pieces are RANGES of `range_nodes` nodes, three phases:
-//   k_bvc_choose  a group of 8 lanes per range walks its nodes in order; the lanes cost the candidates of a node in parallel
-//                 (streaming: blocks, intervals and residuals are costed as the merge of the two lists produces them, nothing
-//                 is materialised), a shuffle reduction picks the winner; best ref and record length per node go out;
+//   k_bvc_costs   what a candidate costs does not depend on the chain lengths, only whether it may be used does: so the cost of
+//                 EVERY (node, candidate) pair is computed first, one thread per pair, nodes taken in the order of a counting
+//                 sort by outdegree class so that the lanes of a warp walk lists of similar length (streaming walker: blocks,
+//                 intervals and residuals are costed as the merge of the two lists produces them, nothing is materialised);
+//   k_bvc_pick    one thread per range goes through its nodes in order and picks, per node, the cheapest candidate whose chain
+//                 is shorter than maxRefCount (ties to the smaller ref); best ref and record length per node go out;
 //   (scan)        record lengths -> bit position of every node;
-//   k_bvc_write   one thread per node streams its list against the chosen reference once more and writes the three sections
+//   k_bvc_write   one thread per node (same order) streams its list against the chosen reference once more and writes the three sections
 //                 (blocks, intervals, residuals) through three cursors -- their lengths are known from the costing pass --
 //                 ORing MSB-first fields into 32-bit big-endian words with atomics (neighbouring records share words).
 // With the same ranges the output is byte-identical to the host writer's (webgraph_b200/csrc/tools/bvg_tools.cpp, itself
@@ -62,7 +65,8 @@ __device__ __forceinline__ int bvc_put_gamma(uint32_t* w, uint64_t pos, uint64_t
 }
 __device__ __forceinline__ int bvc_put_zeta(uint32_t* w, uint64_t pos, uint64_t x, int k) {
     const uint64_t y = x + 1;
-    const int h = bvc_msb(y) / k;
+    const int m = bvc_msb(y);
+    const int h = k == 3 ? (m * 43) >> 7 : m / k;   // m / 3 for m < 64 without a division (the default zeta_3)
     const uint64_t left = 1ull << (h * k);
     if (w) bvc_put(w, pos, 1, h + 1);   // unary(h)
     if (y - left < left) { if (w) bvc_put(w, pos + (uint64_t)h + 1, y - left, h * k + k - 1); return h + 1 + h * k + k - 1; }
@@ -242,62 +246,104 @@ __device__ inline int64_t bvc_choose_one(const BvcDev& g, int64_t x, int64_t ran
     return bits + best;
 }
 
-#ifndef BVG_HOST_EMULATION
-constexpr int BVC_GROUP = 8;       // lanes per range
-constexpr int BVC_THREADS = 128;   // 16 ranges per block
-constexpr int BVC_MAX_WINDOW = 31;
-
-__global__ void __launch_bounds__(BVC_THREADS) k_bvc_choose(BvcDev g, int64_t nranges, int8_t* __restrict__ best_ref, int32_t* __restrict__ bits,
-                                                           int* __restrict__ bad) {
-    __shared__ int32_t s_refc[BVC_THREADS / BVC_GROUP][BVC_MAX_WINDOW + 1];
-    const int lane = threadIdx.x & 31, sl = lane & (BVC_GROUP - 1), grp = threadIdx.x / BVC_GROUP;
-    const unsigned gmask = ((1u << BVC_GROUP) - 1u) << (lane & ~(BVC_GROUP - 1));
-    const int64_t r = (int64_t)blockIdx.x * (BVC_THREADS / BVC_GROUP) + grp;
-    if (r >= nranges) return;   // whole groups leave together
-    int32_t* refc = s_refc[grp];
+// Phase 1b for one node given the cost table (cost[x * size + ref], LLONG_MAX where the candidate does not exist): the choice
+// under the chain-length constraint.  Returns the record length in bits.
+__device__ inline int64_t bvc_pick(const BvcDev& g, int64_t x, const long long* __restrict__ cost, int32_t* __restrict__ refc, int32_t* best_ref) {
     const int32_t size = g.c.window + 1;
-    const int64_t lo = r * g.range_nodes, hi = lo + g.range_nodes < g.n ? lo + g.range_nodes : g.n;
+    const int64_t d = g.off[x + 1] - g.off[x];
+    *best_ref = 0;
+    if (d == 0) return bvc_len_gamma(0);
     const int64_t maxref = g.c.maxref < 0 ? INT64_MAX : g.c.maxref;
-    for (int64_t x = lo; x < hi; x++) {
-        const int64_t d = g.off[x + 1] - g.off[x];
-        if (d < 0 || d > 0x7ffffffe) { if (sl == 0) { *bad = 1; bits[x] = 0; best_ref[x] = 0; } continue; }
-        if (d == 0) { if (sl == 0) { bits[x] = bvc_len_gamma(0); best_ref[x] = 0; } continue; }
-        long long best = LLONG_MAX;
-        int32_t bref = 0x7fffffff;
-        bool any_bad = false;
-        for (int32_t ref = sl; ref < size; ref += BVC_GROUP) {
-            if (ref) {
-                const int64_t y = x - ref;
-                if (y < lo || g.off[y + 1] == g.off[y] || refc[y % size] >= maxref) continue;
-            }
+    long long best = LLONG_MAX;
+    int32_t bref = 0;
+    for (int32_t ref = 0; ref < size; ref++) {
+        const long long c = cost[x * size + ref];
+        if (c == LLONG_MAX) continue;
+        if (ref && refc[(x - ref) % size] >= maxref) continue;
+        if (c < best) { best = c; bref = ref; }
+    }
+    refc[x % size] = bref ? refc[(x - bref) % size] + 1 : 0;
+    *best_ref = bref;
+    return (int64_t)bvc_len_gamma((uint64_t)d) + best;
+}
+
+#ifndef BVG_HOST_EMULATION
+constexpr int BVC_MAX_WINDOW = 31;
+constexpr int BVC_BUCKETS = 64;
+
+// Work class of a node: half octaves of its outdegree, longest first (lanes of a warp then walk lists of similar length).
+__device__ __forceinline__ int bvc_bucket(int64_t d) {
+    if (d <= 1) return BVC_BUCKETS - 1 - (int)d;
+    const int m = 63 - __clzll((long long)d);
+    const int b = 2 * m + (int)((d >> (m - 1)) & 1);
+    return BVC_BUCKETS - 1 - (b < BVC_BUCKETS - 1 ? b : BVC_BUCKETS - 1);
+}
+__global__ void k_iota_i32(int32_t* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+__global__ void k_bvc_hist(BvcDev g, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[BVC_BUCKETS];
+    if (threadIdx.x < BVC_BUCKETS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < g.n) atomicAdd(&sh[bvc_bucket(g.off[x + 1] - g.off[x])], 1u);
+    __syncthreads();
+    if (threadIdx.x < BVC_BUCKETS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void k_bvc_bucket_starts(unsigned int* __restrict__ hist) {   // exclusive scan of 64 bins, in place
+    unsigned int run = 0;
+    for (int b = 0; b < BVC_BUCKETS; b++) { const unsigned int c = hist[b]; hist[b] = run; run += c; }
+}
+__global__ void k_bvc_scatter(BvcDev g, unsigned int* __restrict__ cursor, int32_t* __restrict__ perm) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < g.n) perm[atomicAdd(&cursor[bvc_bucket(g.off[x + 1] - g.off[x])], 1u)] = (int32_t)x;
+}
+
+// Phase 1a: the cost of every (node, candidate) pair, nodes in work-class order: cost[x * size + ref].  A candidate exists when
+// x - ref lies in x's range and has a non-empty list; whether its chain is short enough is decided in phase 1b.
+__global__ void __launch_bounds__(128) k_bvc_costs(BvcDev g, const int32_t* __restrict__ perm, long long* __restrict__ cost, int* __restrict__ bad) {
+    const int32_t size = g.c.window + 1;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)g.n * size) return;
+    const int64_t x = perm[t / size];
+    const int32_t ref = (int32_t)(t % size);
+    const int64_t d = g.off[x + 1] - g.off[x];
+    long long c = LLONG_MAX;
+    if (d < 0 || d > 0x7ffffffe) *bad = 1;
+    else if (d > 0) {
+        const int64_t lo = (x / g.range_nodes) * g.range_nodes, y = x - ref;
+        if (ref == 0 || (y >= lo && g.off[y + 1] > g.off[y])) {
             bool b = false;
-            const long long cost = (long long)bvc_cost(g, x, ref, b);
-            any_bad = any_bad || b;
-            if (cost < best) { best = cost; bref = ref; }   // a lane's refs ascend: ties stay with the smaller one
+            c = (long long)bvc_cost(g, x, ref, b);
+            if (b) *bad = 1;
         }
-        // cheapest over the group, ties to the smaller ref
-#pragma unroll
-        for (int o = BVC_GROUP / 2; o > 0; o >>= 1) {
-            const long long ob = __shfl_xor_sync(gmask, best, o);
-            const int32_t orf = __shfl_xor_sync(gmask, bref, o);
-            if (ob < best || (ob == best && orf < bref)) { best = ob; bref = orf; }
-        }
-        any_bad = __any_sync(gmask, any_bad);
-        __syncwarp(gmask);
-        if (sl == 0) {
-            if (any_bad) { *bad = 1; best = 0; bref = 0; }
-            refc[x % size] = bref ? refc[(x - bref) % size] + 1 : 0;
-            best_ref[x] = (int8_t)bref;
-            const long long tot = (long long)bvc_len_gamma((uint64_t)d) + best;
-            if (tot > 0x7fffffffll) { *bad = 1; bits[x] = 0; } else bits[x] = (int32_t)tot;
-        }
-        __syncwarp(gmask);
+    }
+    cost[x * size + ref] = c;
+}
+
+// Phase 1b: one thread per range walks its nodes in order (the chain lengths are the only thing a node needs of its predecessors).
+__global__ void k_bvc_pick(BvcDev g, int64_t nranges, const long long* __restrict__ cost, int8_t* __restrict__ best_ref, int32_t* __restrict__ bits,
+                           int* __restrict__ bad) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nranges) return;
+    int32_t refc[BVC_MAX_WINDOW + 1];
+    for (int i = 0; i <= BVC_MAX_WINDOW; i++) refc[i] = 0;
+    const int64_t lo = r * g.range_nodes, hi = lo + g.range_nodes < g.n ? lo + g.range_nodes : g.n;
+    for (int64_t x = lo; x < hi; x++) {
+        int32_t ref = 0;
+        const int64_t tot = bvc_pick(g, x, cost, refc, &ref);
+        best_ref[x] = (int8_t)ref;
+        if (tot > 0x7fffffffll || tot < 0) { *bad = 1; bits[x] = 0; } else bits[x] = (int32_t)tot;
     }
 }
 
-__global__ void k_bvc_write(BvcDev g, const int8_t* __restrict__ best_ref, const int64_t* __restrict__ node_bits, uint32_t* __restrict__ w) {
-    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x < g.n) bvc_write_one(g, x, best_ref[x], (uint64_t)node_bits[x], w);
+__global__ void k_bvc_write(BvcDev g, const int32_t* __restrict__ perm, const int8_t* __restrict__ best_ref, const int64_t* __restrict__ node_bits,
+                            uint32_t* __restrict__ w) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    const int64_t x = perm[t];
+    bvc_write_one(g, x, best_ref[x], (uint64_t)node_bits[x], w);
 }
 #endif
 
