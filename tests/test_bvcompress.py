@@ -143,3 +143,23 @@ def test_gpu_compressor_reproduces_the_references_cnr2000(tmp_path, cnr_truth):
     g = BVGraph.load(base + "256")
     assert g.scanRange(0, g.numNodes()) == (3216152, 0xf941dd3471d172f1)
     g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_compress_calls_report_the_size_they_need(tmp_path):
+    """Both compress entry points return BVG_ENOMEM and the size when the output buffer is too small, and succeed when called
+    again with that size (what the store() wrappers fall back to when their guess is too small)."""
+    from webgraph_b200 import bvgraph
+    off, succ = graphs.erdos_renyi(300, .2, 4)
+    n = len(off) - 1
+    L = bvgraph.lib()
+    nb = np.zeros(n + 1, dtype=np.int64)
+    need = C.c_uint64(0)
+    for call, args in ((L.bvg_bv_compress, (off.ctypes.data, succ.ctypes.data, n, 7, 3, 4, 3, 256, 0, -1)),
+                       (L.bvg_ef_compress, (off.ctypes.data, succ.ctypes.data, n, 0, 8, 0, -1))):
+        assert call(*args, None, 0, C.byref(need), nb.ctypes.data, None) == bvgraph.BVG_ENOMEM and need.value > 0
+        small = np.zeros(need.value - 1, dtype=np.uint8)
+        assert call(*args, small.ctypes.data, len(small), C.byref(need), nb.ctypes.data, None) == bvgraph.BVG_ENOMEM
+        buf = np.zeros(need.value, dtype=np.uint8)
+        assert call(*args, buf.ctypes.data, len(buf), C.byref(need), nb.ctypes.data, None) == bvgraph.BVG_OK
+        assert nb[0] == 0 and (nb[-1] + 7) // 8 <= need.value and buf.any()

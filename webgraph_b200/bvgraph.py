@@ -430,11 +430,13 @@ class BVGraph(ImmutableGraph):
         node_bits = np.zeros(n + 1, dtype=np.int64)
         L = lib()
         args = (off.ctypes.data, succ.ctypes.data if len(succ) else None, n, windowSize, maxRefCount, minIntervalLength, zetaK, rangeNodes, 0, device)
-        rc = L.bvg_bv_compress(*args, None, 0, C.byref(need), node_bits.ctypes.data, C.byref(ms))
-        if rc != BVG_ENOMEM:
-            _check(rc)
-        data = np.zeros(max(need.value, 1), dtype=np.uint8)
-        _check(L.bvg_bv_compress(*args, data.ctypes.data, len(data), C.byref(need), node_bits.ctypes.data, C.byref(ms)))
+        # one call when the guess is large enough (5 bytes per arc, 2 per node), a second one with the exact size otherwise
+        data = np.empty(5 * len(succ) + 2 * n + 1024, dtype=np.uint8)   # the device call fills what it reports
+        rc = L.bvg_bv_compress(*args, data.ctypes.data, len(data), C.byref(need), node_bits.ctypes.data, C.byref(ms))
+        if rc == BVG_ENOMEM:
+            data = np.zeros(max(need.value, 1), dtype=np.uint8)
+            rc = L.bvg_bv_compress(*args, data.ctypes.data, len(data), C.byref(need), node_bits.ctypes.data, C.byref(ms))
+        _check(rc)
         data[:need.value].tofile(basename + ".graph")
         gaps = np.concatenate([[0], np.diff(node_bits)]).astype(np.uint64)
         codes, _ = tools.write_codes(tools.GAMMA, 0, gaps)

@@ -92,11 +92,13 @@ class EFGraph(ImmutableGraph):
         node_bits = np.zeros(n + 1, dtype=np.int64)
         L = lib()
         args = (off.ctypes.data, succ.ctypes.data if len(succ) else None, n, upperBound, log2Quantum, 0, device)
-        rc = L.bvg_ef_compress(*args, None, 0, C.byref(need), node_bits.ctypes.data, C.byref(ms))
-        if rc != -6:   # BVG_ENOMEM carries the size; anything else is the verdict
-            _check(rc)
-        words = np.zeros(max(need.value, 8), dtype=np.uint8)
-        _check(L.bvg_ef_compress(*args, words.ctypes.data, len(words), C.byref(need), node_bits.ctypes.data, C.byref(ms)))
+        # one call when the guess is large enough (6 bytes per arc, 16 per node), a second one with the exact size otherwise
+        words = np.empty(6 * len(succ) + 16 * n + 1024, dtype=np.uint8)   # the device call fills what it reports
+        rc = L.bvg_ef_compress(*args, words.ctypes.data, len(words), C.byref(need), node_bits.ctypes.data, C.byref(ms))
+        if rc == -6:   # BVG_ENOMEM carries the size needed
+            words = np.zeros(max(need.value, 8), dtype=np.uint8)
+            rc = L.bvg_ef_compress(*args, words.ctypes.data, len(words), C.byref(need), node_bits.ctypes.data, C.byref(ms))
+        _check(rc)
         words[:need.value].tofile(basename + ".graph")
         gaps = np.concatenate([[0], np.diff(node_bits)]).astype(np.uint64)
         data, _ = tools.write_codes(tools.DELTA, 0, gaps)
