@@ -114,4 +114,62 @@ public:
     bvg_graph* handle() const { return g_.get(); }
 };
 
+// EFGraph (reference EFGraph.java): the same surface over the bvg_ef_* entry points.  nodeIterator() is not offered through
+// a cursor here (the reference inherits ImmutableGraph's generic iterator): use decodeRange for sequential access.
+class EFGraph {
+    std::shared_ptr<bvg_efgraph> g_;
+    int32_t n_ = 0;
+    int64_t m_ = 0;
+    explicit EFGraph(bvg_efgraph* g) : g_(g, bvg_ef_close) { check(bvg_ef_info(g, &n_, &m_, nullptr, nullptr, nullptr)); }
+public:
+    static EFGraph load(const std::string& basename, int device = -1) { bvg_efgraph* g; check(bvg_ef_open(basename.c_str(), device, &g)); return EFGraph(g); }
+    int32_t numNodes() const { return n_; }
+    int64_t numArcs() const { return m_; }
+    bool randomAccess() const { return true; }  // EFGraph.java:1045-1047
+    int32_t outdegree(int32_t x) const { int32_t d; check(bvg_ef_outdegree(g_.get(), x, &d)); return d; }
+    std::vector<int32_t> successorArray(int32_t x) const {
+        std::vector<int32_t> out((size_t)outdegree(x));
+        int32_t d = 0;
+        check(bvg_ef_successors(g_.get(), x, out.data(), (int32_t)out.size(), &d));
+        return out;
+    }
+    LazyIntIterator successors(int32_t x) const { return LazyIntIterator(successorArray(x)); }
+    std::pair<std::vector<int64_t>, std::vector<int32_t>> decodeRange(int32_t from, int32_t to) const {
+        int64_t arcs; check(bvg_ef_range_arcs(g_.get(), from, to, &arcs));
+        std::vector<int64_t> off((size_t)(to - from) + 1);
+        std::vector<int32_t> succ((size_t)arcs);
+        check(bvg_ef_decode_range(g_.get(), from, to, off.data(), succ.data(), arcs, 0));
+        return { std::move(off), std::move(succ) };
+    }
+    std::pair<int64_t, uint64_t> scanRange(int32_t from, int32_t to) const { int64_t a; uint64_t c; check(bvg_ef_scan_range(g_.get(), from, to, &a, &c)); return { a, c }; }
+};
+
+// The label stream of a BitStreamArcLabelledImmutableGraph over an open BVGraph (labelling/BitStreamArcLabelledImmutableGraph.java).
+class ArcLabels {
+    std::shared_ptr<bvg_labels> l_;
+    BVGraph g_;   // keeps the underlying graph alive
+public:
+    ArcLabels(const BVGraph& g, const std::string& labelledBasename) : g_(g) {
+        bvg_labels* l;
+        check(bvg_labels_open(g.handle(), labelledBasename.c_str(), &l));
+        l_.reset(l, bvg_labels_close);
+    }
+    static std::string underlyingBasename(const std::string& labelledBasename) {
+        char buf[4096];
+        check(bvg_labels_underlying(labelledBasename.c_str(), buf, (int)sizeof buf));
+        return buf;
+    }
+    // labels of the arcs of [from, to) in successor order: (list offsets per arc, values)
+    std::pair<std::vector<int64_t>, std::vector<int32_t>> decodeRange(int32_t from, int32_t to) const {
+        int64_t arcs, nv = 0;
+        check(bvg_range_arcs(g_.handle(), from, to, &arcs));
+        check(bvg_labels_decode_range(l_.get(), from, to, nullptr, nullptr, 0, 0, &nv));
+        std::vector<int64_t> lo((size_t)arcs + 1);
+        std::vector<int32_t> vals((size_t)nv);
+        check(bvg_labels_decode_range(l_.get(), from, to, lo.data(), vals.data(), nv, 0, &nv));
+        return { std::move(lo), std::move(vals) };
+    }
+    std::vector<int32_t> labelArray(int32_t x) const { return decodeRange(x, x + 1).second; }
+};
+
 }  // namespace webgraph

@@ -24,5 +24,15 @@ int main(int argc, char** argv) {
     auto sc = g.scanRange(0, g.numNodes());
     std::printf("%lld %llx %d %d %d %lld %llx\n", (long long)arcs, (unsigned long long)cs, first, li.nextInt(), (int)caught,
                 (long long)sc.first, (unsigned long long)sc.second);
+    if (argc > 3) {  // argv[2]: the same graph stored as an EFGraph; argv[3]: gamma labels over argv[1] (label of arc j = j % 1000)
+        EFGraph e = EFGraph::load(argv[2]);
+        auto es = e.scanRange(0, e.numNodes());
+        const bool same0 = e.successorArray(0) == g.successorArray(0) && e.outdegree(7) == g.outdegree(7);
+        ArcLabels labels(g, argv[3]);
+        auto lab = labels.decodeRange(0, g.numNodes());
+        bool ok = (int64_t)lab.second.size() == g.numArcs() && ArcLabels::underlyingBasename(argv[3]) == std::string(argv[1]);
+        for (size_t j = 0; j < lab.second.size() && ok; j += 997) ok = lab.second[j] == (int32_t)(j % 1000);
+        std::printf("%lld %llx %d %d\n", (long long)es.first, (unsigned long long)es.second, (int)same0, (int)ok);
+    }
     return 0;
 }

@@ -701,6 +701,14 @@ def test_cpp_mirror(tmp_path):
                            "-L", libdir, "-lbvgraph_b200", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe, CNR], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["3216152", "f941dd3471d172f1", "1", "-1", "1", "3216152", "f941dd3471d172f1"]
+    # EFGraph and ArcLabels of the mirror: cnr-2000 stored as an EFGraph, gamma labels j % 1000 over the fixture itself
+    off, succ = ob.read_ascii_graph(CNR + ".graph-txt.gz")
+    ef = str(tmp_path / "cnr-ef")
+    tools.store_ef(ef, off, succ, threads=4)
+    lab = str(tmp_path / "cnr-lab")
+    tools.store_labels(lab, CNR, off, (np.arange(len(succ)) % 1000).astype(np.int32), tools.LABEL_GAMMA, threads=4)
+    out = subprocess.run([exe, CNR, ef, lab], capture_output=True, text=True, check=True).stdout.split()
+    assert out[7:] == ["3216152", "f941dd3471d172f1", "1", "1"]
 
 
 @pytest.mark.gpu
