@@ -8,13 +8,12 @@
 // (refCount), and the reference's own multi-threaded store cuts the node range into pieces compressed with an empty window
 // each and splices the bits (:2471-2550).  Here the pieces are RANGES of `range_nodes` nodes, three phases:
 //   k_bvc_costs   what a candidate costs does not depend on the chain lengths, only whether it may be used does: so the cost of
-//                 EVERY (node, candidate) pair is computed first, one thread per pair, nodes taken in the order of a counting
-//                 sort by outdegree class so that the lanes of a warp walk lists of similar length (streaming walker: blocks,
+//                 EVERY (node, candidate) pair is computed first, one thread per pair in node order (streaming walker: blocks,
 //                 intervals and residuals are costed as the merge of the two lists produces them, nothing is materialised);
 //   k_bvc_pick    one thread per range goes through its nodes in order and picks, per node, the cheapest candidate whose chain
 //                 is shorter than maxRefCount (ties to the smaller ref); best ref and record length per node go out;
 //   (scan)        record lengths -> bit position of every node;
-//   k_bvc_write   one thread per node (same order) streams its list against the chosen reference once more and writes the three sections
+//   k_bvc_write   one thread per node streams its list against the chosen reference once more and writes the three sections
 //                 (blocks, intervals, residuals) through three cursors -- their lengths are known from the costing pass --
 //                 ORing MSB-first fields into 32-bit big-endian words with atomics (neighbouring records share words).
 // With the same ranges the output is byte-identical to the host writer's (webgraph_b200/csrc/tools/bvg_tools.cpp, itself
@@ -269,44 +268,14 @@ __device__ inline int64_t bvc_pick(const BvcDev& g, int64_t x, const long long* 
 
 #ifndef BVG_HOST_EMULATION
 constexpr int BVC_MAX_WINDOW = 31;
-constexpr int BVC_BUCKETS = 64;
-
-// Work class of a node: half octaves of its outdegree, longest first (lanes of a warp then walk lists of similar length).
-__device__ __forceinline__ int bvc_bucket(int64_t d) {
-    if (d <= 1) return BVC_BUCKETS - 1 - (int)d;
-    const int m = 63 - __clzll((long long)d);
-    const int b = 2 * m + (int)((d >> (m - 1)) & 1);
-    return BVC_BUCKETS - 1 - (b < BVC_BUCKETS - 1 ? b : BVC_BUCKETS - 1);
-}
-__global__ void k_iota_i32(int32_t* __restrict__ out, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int32_t)i;
-}
-__global__ void k_bvc_hist(BvcDev g, unsigned int* __restrict__ hist) {
-    __shared__ unsigned int sh[BVC_BUCKETS];
-    if (threadIdx.x < BVC_BUCKETS) sh[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x < g.n) atomicAdd(&sh[bvc_bucket(g.off[x + 1] - g.off[x])], 1u);
-    __syncthreads();
-    if (threadIdx.x < BVC_BUCKETS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
-}
-__global__ void k_bvc_bucket_starts(unsigned int* __restrict__ hist) {   // exclusive scan of 64 bins, in place
-    unsigned int run = 0;
-    for (int b = 0; b < BVC_BUCKETS; b++) { const unsigned int c = hist[b]; hist[b] = run; run += c; }
-}
-__global__ void k_bvc_scatter(BvcDev g, unsigned int* __restrict__ cursor, int32_t* __restrict__ perm) {
-    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x < g.n) perm[atomicAdd(&cursor[bvc_bucket(g.off[x + 1] - g.off[x])], 1u)] = (int32_t)x;
-}
-
-// Phase 1a: the cost of every (node, candidate) pair, nodes in work-class order: cost[x * size + ref].  A candidate exists when
-// x - ref lies in x's range and has a non-empty list; whether its chain is short enough is decided in phase 1b.
-__global__ void __launch_bounds__(128) k_bvc_costs(BvcDev g, const int32_t* __restrict__ perm, long long* __restrict__ cost, int* __restrict__ bad) {
+// Phase 1a: the cost of every (node, candidate) pair, in node order (the lanes of a node share its list in L1; the order of a
+// counting sort by outdegree class measured 574 ms against 400): cost[x * size + ref].  A candidate exists when x - ref lies in
+// x's range and has a non-empty list; whether its chain is short enough is decided in phase 1b.
+__global__ void __launch_bounds__(128) k_bvc_costs(BvcDev g, long long* __restrict__ cost, int* __restrict__ bad) {
     const int32_t size = g.c.window + 1;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)g.n * size) return;
-    const int64_t x = perm[t / size];
+    const int64_t x = t / size;
     const int32_t ref = (int32_t)(t % size);
     const int64_t d = g.off[x + 1] - g.off[x];
     long long c = LLONG_MAX;
@@ -338,12 +307,9 @@ __global__ void k_bvc_pick(BvcDev g, int64_t nranges, const long long* __restric
     }
 }
 
-__global__ void k_bvc_write(BvcDev g, const int32_t* __restrict__ perm, const int8_t* __restrict__ best_ref, const int64_t* __restrict__ node_bits,
-                            uint32_t* __restrict__ w) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n) return;
-    const int64_t x = perm[t];
-    bvc_write_one(g, x, best_ref[x], (uint64_t)node_bits[x], w);
+__global__ void k_bvc_write(BvcDev g, const int8_t* __restrict__ best_ref, const int64_t* __restrict__ node_bits, uint32_t* __restrict__ w) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < g.n) bvc_write_one(g, x, best_ref[x], (uint64_t)node_bits[x], w);
 }
 #endif
 

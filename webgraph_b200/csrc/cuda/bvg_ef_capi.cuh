@@ -391,20 +391,10 @@ int bvg_bv_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
         CK(cudaEventRecord(ev.e0, s));
         const int64_t nranges = ((int64_t)n + range_nodes - 1) / range_nodes;
         const int32_t size = window + 1;
-        Tmp<unsigned int> d_hist(s);
-        Tmp<int32_t> d_perm(s);
         Tmp<long long> d_cost(s);
-        CK(d_hist.alloc(BVC_BUCKETS));
-        CK(d_perm.alloc((size_t)std::max<int32_t>(n, 1)));
         CK(d_cost.alloc((size_t)std::max<int64_t>((int64_t)n * size, 1)));
-        CK(cudaMemsetAsync(d_hist.p, 0, BVC_BUCKETS * sizeof(unsigned int), s));
         if (n) {
-            if (env_int("BVG_BVC_SORT", 0, 0, 1)) {   // nodes by outdegree class: measured slower (574 against 400 ms: the lanes of a node no longer share its list in L1)
-                LAUNCH(k_bvc_hist, grid_for(n, 256), 256, 0, s, g, d_hist.p);
-                LAUNCH(k_bvc_bucket_starts, 1, 1, 0, s, d_hist.p);
-                LAUNCH(k_bvc_scatter, grid_for(n, 256), 256, 0, s, g, d_hist.p, d_perm.p);
-            } else LAUNCH(k_iota_i32, grid_for(n, 256), 256, 0, s, d_perm.p, (int64_t)n);
-            LAUNCH(k_bvc_costs, grid_for((int64_t)n * size, 128), 128, 0, s, g, d_perm.p, d_cost.p, d_bad.p);
+            LAUNCH(k_bvc_costs, grid_for((int64_t)n * size, 128), 128, 0, s, g, d_cost.p, d_bad.p);
             LAUNCH(k_bvc_pick, grid_for(nranges, 64), 64, 0, s, g, nranges, d_cost.p, d_ref.p, d_sizes.p, d_bad.p);
         }
         int r = device_exclusive_scan(s, d_sizes.p, n, d_bits.p);
@@ -421,7 +411,7 @@ int bvg_bv_compress(const int64_t* off, const int32_t* succ, int32_t n, int32_t 
         const uint64_t nwords = nbytes / 4 + 2;
         CK(d_words.alloc((size_t)nwords));
         CK(cudaMemsetAsync(d_words.p, 0, (size_t)nwords * 4, s));
-        if (n) LAUNCH(k_bvc_write, grid_for(n, 128), 128, 0, s, g, d_perm.p, d_ref.p, d_bits.p, d_words.p);
+        if (n) LAUNCH(k_bvc_write, grid_for(n, 128), 128, 0, s, g, d_ref.p, d_bits.p, d_words.p);
         LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, d_words.p, nwords);   // big-endian words -> bytes in stream order
         CK(cudaEventRecord(ev.e1, s));
         if (nbytes) CK(cudaMemcpyAsync(graph_out, d_words.p, (size_t)nbytes, cudaMemcpyDeviceToHost, s));
