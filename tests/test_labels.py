@@ -403,3 +403,29 @@ def test_gpu_labels_corrupted_streams_fail_cleanly(tmp_path, kind, width):
     lo, vals = alg.decodeLabels(0, n)
     assert np.array_equal(lo, list_off) and np.array_equal(vals, values)
     alg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,width", [(tools.LABEL_FIXED, 13), (tools.LABEL_FIXED_LIST, 6), (tools.LABEL_GAMMA, 0)])
+def test_gpu_labels_of_every_kind_on_shards(tmp_path, oracle, kind, width):
+    """Labels opened on a shard of the underlying graph (node window with a halo, bit base inside the stream): every kind."""
+    from webgraph_b200 import bvgraph, labelling
+    off, succ = graphs.copy_heavy(900, seed=13, maxdeg=30, universe=120)[:2] if kind == tools.LABEL_FIXED_LIST else graphs.copy_heavy(5000, seed=13)[:2]
+    base, lbase, values, list_off, _ = write_case(tmp_path, "s", off, succ, kind, width, threads=2)
+    n = len(off) - 1
+    L = oracle.load_labels(lbase, n)
+    for frm, to in ((0, n // 3), (n // 3, 2 * n // 3), (2 * n // 3, n), (n - 1, n)):
+        g = bvgraph.BVGraph.loadShard(base, frm, to)
+        h = C.c_void_p()
+        bvgraph._check(bvgraph.lib().bvg_labels_open(g.handle, os.fsencode(lbase), C.byref(h)))
+        alg = labelling.BitStreamArcLabelledImmutableGraph(g, h)
+        want_lo, want_vals = L.range(frm, to, off)
+        lo, vals = alg.decodeLabels(frm, to)
+        assert np.array_equal(lo, want_lo) and np.array_equal(vals, want_vals), (frm, to)
+        mid = (frm + to) // 2
+        lo, vals = alg.decodeLabels(mid, to)
+        w2 = L.range(mid, to, off)
+        assert np.array_equal(lo, w2[0]) and np.array_equal(vals, w2[1])
+        assert alg.scanLabels(frm, to)[2] == ob.label_checksum(want_lo, want_vals)
+        alg.close()
+    L.close()
