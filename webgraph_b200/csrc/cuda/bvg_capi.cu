@@ -719,7 +719,9 @@ static int build_long_index(bvg_graph* g) {
     g->long_tmp_entries = tmp;
     g->long_scan_entries = scan;
     g->long_resid_bits = (int64_t)h_stats[0]; g->long_pre_bits = (int64_t)h_stats[1]; g->long_arcs = (int64_t)h_stats[2];
-    g->long_index_bytes = nl * (int64_t)sizeof(LongMeta) + 8 * (cb + iv) + 16 * seg + (int64_t)g->long_cum_entries * 8 + nl * 4;
+    int64_t hint_entries = 0;
+    if (g->d_long_hint) for (int f = 0; f <= fam_spec; f++) hint_entries += (fam_total[(size_t)f] >> ITEM_HINT_SHIFT) + 2;
+    g->long_index_bytes = nl * (int64_t)sizeof(LongMeta) + 8 * (cb + iv) + 16 * seg + (int64_t)g->long_cum_entries * 8 + nl * 4 + 4 * hint_entries;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));  // cum / meta are host vectors
     return BVG_OK;
