@@ -27,6 +27,15 @@ extern "C" int64_t emu_bv_compress(const int64_t* off, const int32_t* succ, int3
             bool b = false;
             cost[(size_t)(x * size + ref)] = (long long)bvc_cost(g, x, ref, b);
             if (b) return -1;
+            BvcSections sec;
+            if (bvc_cost_fast(g, x, ref, &sec) != cost[(size_t)(x * size + ref)]) return -300;   // the kernel's walker against the plain one
+            {
+                BvcEnc e;
+                bvc_begin(e, nullptr, 0, 0, 0);
+                const int64_t ra = ref ? off[y] : 0;
+                bvc_walk(e, g.c, x, succ + off[x], (int32_t)d, succ + ra, ref ? (int32_t)(off[y + 1] - ra) : 0);
+                if (sec.bc != e.bc || sec.ic != e.ic || sec.extras != e.extras || sec.block_bits != e.block_bits || sec.iv_bits != e.iv_bits) return -301;
+            }
         }
     }
     node_bits[0] = 0;

@@ -196,6 +196,95 @@ __device__ inline int64_t bvc_cost(const BvcDev& g, int64_t x, int32_t ref, bool
     return bvc_total(e, g.c, ref);
 }
 
+// The same cost with O(1) work per list element and two paths in the loop (an extra / an advance, a block boundary folded into
+// the advance): what k_bvc_costs runs.  An extra is costed as a residual as it comes; when the run of consecutive extras it
+// belongs to reaches minlen the run turns into an interval and the residual state of the run's start is restored (the residual
+// codes of a run's second and later elements are gap 0, but restoring is simpler than subtracting).  Equal to bvc_cost for
+// every pair (tests/hostemu/emu_bvc.cpp checks all of them); list validity is bvc_list_ok's business.
+struct BvcSections { int32_t bc, ic, extras, block_bits, iv_bits; };   // what the writer needs to place its three cursors
+__device__ inline int64_t bvc_cost_fast(const BvcDev& g, int64_t x, int32_t ref, BvcSections* sec = nullptr) {
+    const BvcCodec& c = g.c;
+    const int64_t ca = g.off[x];
+    const int32_t d = (int32_t)(g.off[x + 1] - ca);
+    const int32_t* __restrict__ cur = g.succ + ca;
+    const int64_t ra = ref ? g.off[x - ref] : 0;
+    const int32_t rl = ref ? (int32_t)(g.off[x - ref + 1] - ra) : 0;
+    const int32_t* __restrict__ rlist = g.succ + ra;
+    int32_t block_bits = 0, bc = 0, run = 0;
+    bool copying = true;
+    // residuals
+    int32_t res_bits = 0;
+    bool have_res = false;
+    int64_t res_prev = 0;
+    // the current run of consecutive extras and the residual state at its start
+    int64_t run_left = 0;
+    int32_t run_len = 0, s_res_bits = 0;
+    bool s_have_res = false;
+    int64_t s_res_prev = 0;
+    // intervals
+    int32_t iv_bits = 0, ic = 0;
+    bool have_iv = false;
+    int64_t iv_prev = 0;
+    int32_t extras = 0;
+    auto residual = [&](int64_t v) {
+        const uint64_t code = have_res ? (uint64_t)(v - res_prev - 1) : bvc_int2nat(v - x);
+        res_bits += bvc_put_zeta(nullptr, 0, code, c.zetak);
+        have_res = true;
+        res_prev = v;
+    };
+    auto close_run = [&]() {
+        if (run_len >= c.minlen && run_len > 0) {
+            const uint64_t lv = have_iv ? (uint64_t)(run_left - iv_prev - 1) : bvc_int2nat(run_left - x);
+            iv_bits += bvc_len_gamma(lv) + bvc_len_gamma((uint64_t)(run_len - c.minlen));
+            iv_prev = run_left + run_len;
+            have_iv = true;
+            ic++;
+        }
+        run_len = 0;
+    };
+    auto extra = [&](int64_t v) {
+        extras++;
+        if (c.minlen == 0) { residual(v); return; }
+        if (run_len > 0 && v == run_left + run_len) {
+            run_len++;
+            if (run_len < c.minlen) residual(v);
+            else if (run_len == c.minlen) { res_bits = s_res_bits; have_res = s_have_res; res_prev = s_res_prev; }
+        } else {
+            close_run();
+            s_res_bits = res_bits; s_have_res = have_res; s_res_prev = res_prev;
+            run_left = v; run_len = 1;
+            if (run_len < c.minlen) residual(v);
+        }
+    };
+    int32_t j = 0, k = 0;
+    while (j < d && k < rl) {
+        const int32_t a = cur[j], b = rlist[k];
+        if (a < b) { extra(a); j++; }
+        else {
+            const bool eq = a == b;
+            if (copying != eq) {   // a block ends here: copying and a > b, or skipping and a == b
+                block_bits += bvc_len_gamma((uint64_t)(bc == 0 ? run : run - 1));
+                bc++;
+                copying = !copying;
+                run = 0;
+            }
+            k++; run++; j += eq ? 1 : 0;
+        }
+    }
+    if (copying && k < rl) { block_bits += bvc_len_gamma((uint64_t)(bc == 0 ? run : run - 1)); bc++; }
+    while (j < d) { extra(cur[j]); j++; }
+    if (c.minlen != 0) close_run();
+    if (sec) { sec->bc = bc; sec->ic = ic; sec->extras = extras; sec->block_bits = block_bits; sec->iv_bits = iv_bits; }
+    int64_t bits = 0;
+    if (c.window > 0) bits += ref + 1;
+    if (ref != 0) bits += bvc_len_gamma((uint64_t)bc) + block_bits;
+    if (extras > 0) {
+        if (c.minlen != 0) bits += bvc_len_gamma((uint64_t)ic) + iv_bits;
+        bits += res_bits;
+    }
+    return bits;
+}
+
 // Writes the record of node x (outdegree, reference, blocks, intervals, residuals) at bit position start.
 __device__ inline void bvc_write_one(const BvcDev& g, int64_t x, int32_t ref, uint64_t start, uint32_t* __restrict__ w) {
     const int64_t a = g.off[x];
@@ -205,9 +294,8 @@ __device__ inline void bvc_write_one(const BvcDev& g, int64_t x, int32_t ref, ui
     if (d == 0) return;
     const int64_t ra = ref ? g.off[x - ref] : 0;
     const int32_t rl = ref ? (int32_t)(g.off[x - ref + 1] - ra) : 0;
-    BvcEnc e;
-    bvc_begin(e, nullptr, 0, 0, 0);
-    bvc_walk(e, g.c, x, g.succ + a, d, g.succ + ra, rl);   // the section lengths
+    BvcSections e;
+    bvc_cost_fast(g, x, ref, &e);   // the section lengths
     if (g.c.window > 0) { bvc_put(w, pos, 1, ref + 1); pos += (uint64_t)ref + 1; }
     uint64_t pos_b = pos;
     if (ref != 0) { pos_b += (uint64_t)bvc_put_gamma(w, pos, (uint64_t)e.bc); pos = pos_b + (uint64_t)e.block_bits; }
@@ -283,9 +371,8 @@ __global__ void __launch_bounds__(128) k_bvc_costs(BvcDev g, long long* __restri
     else if (d > 0) {
         const int64_t lo = (x / g.range_nodes) * g.range_nodes, y = x - ref;
         if (ref == 0 || (y >= lo && g.off[y + 1] > g.off[y])) {
-            bool b = false;
-            c = (long long)bvc_cost(g, x, ref, b);
-            if (b) *bad = 1;
+            c = (long long)bvc_cost_fast(g, x, ref);
+            if (ref == 0 && !bvc_list_ok(g, x)) *bad = 1;
         }
     }
     cost[x * size + ref] = c;
