@@ -201,7 +201,7 @@ __device__ inline int64_t bvc_cost(const BvcDev& g, int64_t x, int32_t ref, bool
 // belongs to reaches minlen the run turns into an interval and the residual state of the run's start is restored (the residual
 // codes of a run's second and later elements are gap 0, but restoring is simpler than subtracting).  Equal to bvc_cost for
 // every pair (tests/hostemu/emu_bvc.cpp checks all of them); list validity is bvc_list_ok's business.
-struct BvcSections { int32_t bc, ic, extras, block_bits, iv_bits; };   // what the writer needs to place its three cursors
+struct BvcSections { int32_t bc, ic, extras; int64_t block_bits, iv_bits; };   // what the writer needs to place its three cursors
 __device__ inline int64_t bvc_cost_fast(const BvcDev& g, int64_t x, int32_t ref, BvcSections* sec = nullptr) {
     const BvcCodec& c = g.c;
     const int64_t ca = g.off[x];
@@ -210,19 +210,22 @@ __device__ inline int64_t bvc_cost_fast(const BvcDev& g, int64_t x, int32_t ref,
     const int64_t ra = ref ? g.off[x - ref] : 0;
     const int32_t rl = ref ? (int32_t)(g.off[x - ref + 1] - ra) : 0;
     const int32_t* __restrict__ rlist = g.succ + ra;
-    int32_t block_bits = 0, bc = 0, run = 0;
+    int64_t block_bits = 0;   // 64-bit sums: a list of 10^8 successors must not wrap into a plausible length
+    int32_t bc = 0, run = 0;
     bool copying = true;
     // residuals
-    int32_t res_bits = 0;
+    int64_t res_bits = 0;
     bool have_res = false;
     int64_t res_prev = 0;
     // the current run of consecutive extras and the residual state at its start
     int64_t run_left = 0;
-    int32_t run_len = 0, s_res_bits = 0;
+    int32_t run_len = 0;
+    int64_t s_res_bits = 0;
     bool s_have_res = false;
     int64_t s_res_prev = 0;
     // intervals
-    int32_t iv_bits = 0, ic = 0;
+    int64_t iv_bits = 0;
+    int32_t ic = 0;
     bool have_iv = false;
     int64_t iv_prev = 0;
     int32_t extras = 0;
