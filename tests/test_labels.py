@@ -429,3 +429,32 @@ def test_gpu_labels_of_every_kind_on_shards(tmp_path, oracle, kind, width):
         assert alg.scanLabels(frm, to)[2] == ob.label_checksum(want_lo, want_vals)
         alg.close()
     L.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,width", [(tools.LABEL_FIXED, 9), (tools.LABEL_FIXED_LIST, 4)])
+def test_gpu_labels_into_device_buffers(tmp_path, oracle, kind, width):
+    """bvg_labels_decode_range with on_device = 1 for the fixed-width kinds (the gamma kind is covered with the shards): list
+    offsets and values land in caller-owned device memory, sizes come back, too small a buffer is BVG_ENOMEM."""
+    import torch
+    from webgraph_b200 import bvgraph, labelling
+    off, succ = graphs.erdos_renyi(70, .2, 8) if kind == tools.LABEL_FIXED_LIST else graphs.copy_heavy(2000, seed=3)[:2]
+    base, lbase, values, list_off, _ = write_case(tmp_path, "d", off, succ, kind, width)
+    n = len(off) - 1
+    alg = labelling.BitStreamArcLabelledImmutableGraph.load(lbase)
+    L = bvgraph.lib()
+    for frm, to in ((0, n), (n // 4, 3 * n // 4)):
+        arcs = int(off[to] - off[frm])
+        nv = C.c_int64()
+        bvgraph._check(L.bvg_labels_decode_range(alg._h, frm, to, None, None, 0, 1, C.byref(nv)))
+        want_lo = list_off[off[frm]:off[to] + 1] - list_off[off[frm]]
+        want_vals = values[list_off[off[frm]]:list_off[off[to]]]
+        assert nv.value == len(want_vals)
+        d_lo = torch.full((arcs + 1,), -1, dtype=torch.int64, device="cuda")
+        d_vals = torch.full((max(nv.value, 1),), -1, dtype=torch.int32, device="cuda")
+        bvgraph._check(L.bvg_labels_decode_range(alg._h, frm, to, d_lo.data_ptr(), d_vals.data_ptr(), nv.value, 1, C.byref(nv)))
+        torch.cuda.synchronize()
+        assert np.array_equal(d_lo.cpu().numpy(), want_lo) and np.array_equal(d_vals.cpu().numpy()[:nv.value], want_vals)
+        if nv.value:
+            assert L.bvg_labels_decode_range(alg._h, frm, to, d_lo.data_ptr(), d_vals.data_ptr(), nv.value - 1, 1, None) == bvgraph.BVG_ENOMEM
+    alg.close()
