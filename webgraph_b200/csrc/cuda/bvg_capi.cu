@@ -515,7 +515,7 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     const int lanes = env_int("BVG_BND_LANES", 1, 1, 32);  // walks per warp (k_bnd_walk)
     const int lean = env_int("BVG_BND_LEAN", 0, 0, 1);      // residual runs through the 32-bit window of the scan kernels (to be measured)
     const int32_t W = c.window;
-    const int64_t max_sub = std::max<int64_t>(1, std::min<int64_t>(16384, ((int64_t)1 << 24) / std::max<int32_t>(W, 1)));
+    const int64_t max_sub = std::max<int64_t>(1, std::min<int64_t>(env_int("BVG_BND_MAX_SUB", 16384, 1, 1 << 24), ((int64_t)1 << 24) / std::max<int32_t>(W, 1)));
     while ((int64_t)((stream_bits + sub_bits - 1) / sub_bits) > max_sub) sub_bits *= 2;
     const int64_t nsub = std::max<int64_t>(1, (int64_t)((stream_bits + sub_bits - 1) / sub_bits));
     const size_t hw = (size_t)nsub * (size_t)std::max<int32_t>(W, 1);
