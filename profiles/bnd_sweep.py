@@ -19,4 +19,4 @@ for i in range(3):
     g = bvgraph.BVGraph(h)
     ok = g.scanRange(0, st['nodes']) == (st['arcs'], st['xor_checksum'])
     g.close()
-print({k: os.environ.get(k) for k in ('BVG_BND_SUB_BITS', 'BVG_BND_MAX_SUB', 'BVG_BND_LANES')}, [round(t, 1) for t in ts], ok)
+print({k: os.environ.get(k) for k in ('BVG_BND_SUB_BITS', 'BVG_BND_MAX_SUB', 'BVG_BND_LANES', 'BVG_BND_CAP_BITS')}, [round(t, 1) for t in ts], ok)

@@ -509,7 +509,7 @@ static int device_offsets_from_graph(cudaStream_t s, const uint8_t* graph, uint6
     LAUNCH(k_bswap, grid_for((int64_t)nwords, 256), 256, 0, s, words.p, nwords);
     // Sub-ranges long enough for a wrong chain to fall onto the right one well inside them (a few hundred records),
     // few enough that their window-sized histories stay small.
-    uint64_t sub_bits = 1ull << 21, cap = 1ull << 25;
+    uint64_t sub_bits = 1ull << 21, cap = 1ull << 23;   // cap swept on the 1 B-arc graph: 2^25 1097 ms, 2^24 840, 2^23 697, 2^22 747, 2^21 701, 2^20 and below slower
     if (const char* e = getenv("BVG_BND_SUB_BITS")) sub_bits = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
     if (const char* e = getenv("BVG_BND_CAP_BITS")) cap = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
     const int lanes = env_int("BVG_BND_LANES", 1, 1, 32);  // walks per warp (k_bnd_walk)
